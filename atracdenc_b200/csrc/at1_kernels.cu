@@ -1,0 +1,720 @@
+// at1_kernels.cu — ATRAC1 encode hot path on sm_100a.
+//
+// Replaces, for thousands of frames at once (reference: dcherednik/atracdenc):
+//   K1 at1_analysis_kernel  Atrac1AnalysisFilterBank::Analysis (src/atrac/at1/atrac1_qmf.h:37-43)
+//                           TQmf::Analysis                      (src/qmf/qmf.h:47-64)
+//                           TTransientDetector::Detect          (src/transient_detector.cpp:52-93)
+//                           TAtrac1MDCT::Mdct + TMDCT           (src/atrac1denc.cpp:70-102, src/lib/mdct/mdct.h:51-104)
+//                           kiss_fft                            (src/lib/fft/kissfft_impl/kiss_fft.c)
+//                           per-channel loudness term           (src/atrac1denc.cpp:235-240)
+//   K4 at1_loudness_kernel  TrackLoudness recurrence            (src/atrac1denc.cpp:243-247)
+//   K5 at1_pack_kernel      TScaler::ScaleFrame                 (src/atrac/atrac_scale.cpp:141-188)
+//                           TAt1BitAlloc::Write                 (src/atrac/at1/atrac1_bitalloc.cpp:80-409)
+//                           TBitStreamEncoder bisection         (src/lib/bs_encode/encode.cpp:57-129)
+//                           TBitStream::Write                   (src/lib/bitstream/bitstream.cpp:40-63)
+//
+// Frames of a stream are NOT processed sequentially.  Every piece of encoder state the reference
+// carries from frame to frame is either a finite function of the previous PCM frame (QMF history,
+// hi-band delay line, MDCT overlap tail, transient-detector history) — recomputed here from a
+// 304-sample input halo — or the scalar loudness recurrence, which K4 scans per stream.
+// All arithmetic is un-fused IEEE fp32 in the reference's operation order (bit-exact contract).
+#include "at1_kernels.cuh"
+#include "kissfft_dev.cuh"
+#include "glibc_math.cuh"
+
+namespace atde {
+namespace at1 {
+
+__constant__ float c_qmf[48];        // QmfWindow, qmf.cpp:36-45 (uniform-index reads -> constant bank)
+
+void upload_qmf_window(const float w[48]) { cudaMemcpyToSymbol(c_qmf, w, 48 * sizeof(float)); }
+
+// ---- BFU geometry, atrac1.h:89-104 ----
+__device__ const unsigned char kSpecsPerBlock[kMaxBfus] = {
+    8, 8, 8, 8, 4, 4, 4, 4, 8, 8, 8, 8, 6, 6, 6, 6, 6, 6, 6, 6,
+    6, 6, 6, 6, 7, 7, 7, 7, 9, 9, 9, 9, 10, 10, 10, 10,
+    12, 12, 12, 12, 12, 12, 12, 12, 20, 20, 20, 20, 20, 20, 20, 20};
+__device__ const unsigned short kSpecsStartLong[kMaxBfus] = {
+    0, 8, 16, 24, 32, 36, 40, 44, 48, 56, 64, 72, 80, 86, 92, 98, 104, 110, 116, 122,
+    128, 134, 140, 146, 152, 159, 166, 173, 180, 189, 198, 207, 216, 226, 236, 246,
+    256, 268, 280, 292, 304, 316, 328, 340, 352, 372, 392, 412, 432, 452, 472, 492};
+__device__ const unsigned short kSpecsStartShort[kMaxBfus] = {
+    0, 32, 64, 96, 8, 40, 72, 104, 12, 44, 76, 108, 20, 52, 84, 116, 26, 58, 90, 122,
+    128, 160, 192, 224, 134, 166, 198, 230, 141, 173, 205, 237, 150, 182, 214, 246,
+    256, 288, 320, 352, 384, 416, 448, 480, 268, 300, 332, 364, 396, 428, 460, 492};
+// fixed allocation tables and boost mask, atrac1_bitalloc.cpp:37-67
+__device__ const unsigned char kFixLong[kMaxBfus] = {
+    7, 7, 7, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6,
+    6, 6, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 4,
+    4, 4, 3, 3, 3, 3, 3, 3, 2, 1, 1, 1, 1, 0, 0, 0};
+__device__ const unsigned char kFixShort[kMaxBfus] = {
+    6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6,
+    6, 6, 6, 6, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5,
+    4, 4, 4, 4, 4, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 0};
+
+ATDE_D int bfu_band(int b) { return b < 20 ? 0 : (b < 36 ? 1 : 2); }
+ATDE_D int bfu_amount(int idx) { return idx == 0 ? 20 : (idx == 1 ? 28 : 28 + 4 * (idx - 1)); }   // {20,28,32,...,52}
+
+// =====================================================================================
+// K1: QMF tree + transient detection + windowed MDCT + loudness term
+// =====================================================================================
+//
+// One block = kTile consecutive frames of one stream; channels are processed one after another
+// through the same shared-memory tile.  Index conventions (t0 = first frame of the tile):
+//   x[k]     = input sample  512*t0 - 304 + k          k in [0, kNX)
+//   s1lo/hi[j] = stage-1 QMF output n = 256*t0 - 128 + j  j in [0, kNS1)   (taps read x[2j+48-2i], x[2j+49-2i])
+//   lo/mi[j] = stage-2 output    m = 128*t0 - 40 + j    j in [0, kNS2)   (taps read s1lo[2j+48-2i], s1lo[2j+49-2i])
+//   hi band sample q (delayed 39, atrac1_qmf.h:26,38-42) = s1hi[q - 256*t0 + 89]
+constexpr int kNX = kTile * 512 + 304;
+constexpr int kNS1 = kTile * 256 + 128;
+constexpr int kNS2 = kTile * 128 + 40;
+constexpr int kNFilt = kTile * 512 + 48;         // HPF output incl. one 16-sample halo block per band
+constexpr int kNEner = kTile * 32 + 3;
+
+struct BandView {
+    const float* base;   // sample k of tile-frame 0 is base[k]; frame tl adds tl*size
+    int size;            // 128 / 128 / 256
+};
+
+// 48-tap half-band split of one output pair (qmf.h:54-63): sequential sums, taps in order.
+ATDE_D void qmf_pair(const float* src, int j, float& lower, float& upper)
+{
+    float lo = 0.0f, up = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 24; i++) {
+        const float2 v = *reinterpret_cast<const float2*>(src + 2 * j + 48 - 2 * i);
+        lo = fadd(lo, fmul(c_qmf[2 * i], v.y));
+        up = fadd(up, fmul(c_qmf[2 * i + 1], v.x));
+    }
+    upper = fsub(lo, up);
+    lower = fadd(lo, up);
+}
+
+// HPF input sample: band sample k (k may reach -20 into the previous frame), spectrum-inverted
+// for the mid/hi bands (InvertSpectr, util.h:51-63: even indices negated).
+ATDE_D float hpf_in(const float* band0, int k, bool invert)
+{
+    const float v = band0[k];
+    return (invert && !(k & 1)) ? -v : v;
+}
+
+// MDCT input sample tmp[j] of TAtrac1MDCT::Mdct (atrac1denc.cpp:80-90), built on the fly.
+// band0 = pointer to sample 0 of this frame's band (negative indices = previous frame).
+ATDE_D float mdct_in_long(const float* band0, const float* W, int j, int size, int win_start)
+{
+    const int jj = j - win_start;
+    if (jj < 0)
+        return 0.0f;
+    if (jj < 32)
+        return fmul(W[jj], band0[jj - 32]);                  // overlap tail kept from the previous frame
+    const int k = jj - 32;
+    if (k >= size)
+        return 0.0f;
+    const float v = band0[k];
+    return (k >= size - 32) ? fmul(W[31 - (k - (size - 32))], v) : v;
+}
+ATDE_D float mdct_in_short(const float* band0, const float* W, int j, int kb)
+{
+    if (j < 32)
+        return fmul(W[j], band0[32 * kb - 32 + j]);
+    return fmul(W[63 - j], band0[32 * kb + (j - 32)]);
+}
+
+__global__ void __launch_bounds__(256) at1_analysis_kernel(AnalysisParams p)
+{
+    __shared__ __align__(16) float x[kNX];          // input tile; later HPF output; later FFT buffer
+    __shared__ __align__(16) float s1lo[kNS1];
+    __shared__ __align__(16) float s1hi[kNS1];
+    __shared__ __align__(16) float lo[kNS2];
+    __shared__ __align__(16) float mi[kNS2];
+    __shared__ __align__(16) float sp[kTile * 512];
+    __shared__ float ener[kNEner];
+    __shared__ float W[32];
+    __shared__ unsigned char smask[kTile];
+
+    const int s = blockIdx.y;
+    const int t0 = blockIdx.x * kTile;
+    const int C = p.C, F = p.F;
+    const DevTables* __restrict__ T = p.tab;
+    const bool fresh = !(p.started && p.started[s]);       // stream starts at frame 0 of this batch
+
+    ATDE_PAR_FOR(i, 32) W[i] = T->sine_window[i];
+
+    for (int c = 0; c < C; c++) {
+        // ---- load input tile with halo ----
+        const float* __restrict__ pcm = p.pcm + (size_t)s * F * 512 * C + c;
+        ATDE_PAR_FOR(k, kNX) {
+            const int n = 512 * t0 - 304 + k;
+            float v = 0.0f;
+            if (n >= 0) {
+                if (n < F * 512) v = pcm[(size_t)n * C];
+            } else if (p.hist && !fresh) {
+                v = p.hist[((size_t)s * 512 + (512 + n)) * C + c];
+            }
+            x[k] = v;
+        }
+        __syncthreads();
+        // ---- QMF stage 1: full band -> (low+mid, hi) ----
+        ATDE_PAR_FOR(j, kNS1) {
+            float l, u;
+            qmf_pair(x, j, l, u);
+            s1lo[j] = l;
+            s1hi[j] = u;
+        }
+        __syncthreads();
+        // ---- QMF stage 2: (low+mid) -> (low, mid) ----
+        ATDE_PAR_FOR(j, kNS2) {
+            float l, u;
+            qmf_pair(s1lo, j, l, u);
+            lo[j] = l;
+            mi[j] = u;
+        }
+        __syncthreads();
+
+        const float* band0[3] = {lo + 40, mi + 40, s1hi + 89};   // sample 0 of tile-frame 0
+        float* filt = x;                                          // x is dead from here on
+
+        if (p.window_auto) {
+            // ---- 21-tap HPF (transient_detector.cpp:52-70) over every band sample of the tile
+            //      plus the last 16 samples of the frame before it (for LastEnergy) ----
+            ATDE_PAR_FOR(u, kNFilt) {
+                int b, q;
+                if (u < 16 + kTile * 128) { b = 0; q = u; }
+                else if (u < 2 * (16 + kTile * 128)) { b = 1; q = u - (16 + kTile * 128); }
+                else { b = 2; q = u - 2 * (16 + kTile * 128); }
+                const int size = (b == 2) ? 256 : 128;
+                int tl, i;
+                if (q < 16) { tl = -1; i = size - 16 + q; }
+                else { tl = (q - 16) / size; i = (q - 16) - tl * size; }
+                const float* fr = band0[b] + tl * size;          // sample 0 of that frame
+                const bool inv = b != 0;
+                // inBuf[w] = frame sample (w - 20); inBuf[size + 20] is never written by the reference => 0
+                const float c0 = -8.65163e-18 * 2.0, c1 = -0.00851586 * 2.0, c2 = -6.74764e-18 * 2.0,
+                            c3 = 0.0209036 * 2.0, c4 = -3.36639e-17 * 2.0, c5 = -0.0438162 * 2.0,
+                            c6 = -1.54175e-17 * 2.0, c7 = 0.0931738 * 2.0, c8 = -5.52212e-17 * 2.0,
+                            c9 = -0.313819 * 2.0;
+                const float cf[10] = {c0, c1, c2, c3, c4, c5, c6, c7, c8, c9};
+                float sacc = hpf_in(fr, i - 10, inv);
+                float s2 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 9; j += 2) {
+                    const int kr = i + 1 - j;                                 // w = i + 21 - j
+                    const float right = (kr >= size) ? 0.0f : hpf_in(fr, kr, inv);
+                    sacc = fadd(sacc, fmul(cf[j], fadd(hpf_in(fr, i + j - 20, inv), right)));
+                    s2 = fadd(s2, fmul(cf[j + 1], fadd(hpf_in(fr, i + j - 19, inv), hpf_in(fr, i - j, inv))));
+                }
+                filt[u] = __fdiv_rn(fadd(sacc, s2), 2.0f);
+            }
+            __syncthreads();
+            // ---- RMS (dB-ish) of each 16-sample short block (transient_detector.cpp:33-40,81) ----
+            ATDE_PAR_FOR(e, kNEner) {
+                const float* f = filt + 16 * e;
+                float acc = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    acc = fadd(acc, fmul(f[i], f[i]));
+                acc = __fdiv_rn(acc, 16.0f);
+                const float rms = __fsqrt_rn(acc);
+                ener[e] = __double2float_rn(__dmul_rn(19.0, (double)g_log10f(rms)));
+            }
+            __syncthreads();
+            // ---- window decision per frame (transient_detector.cpp:78-91, atrac1denc.cpp:214-229) ----
+            ATDE_PAR_FOR(tl, kTile) {
+                unsigned m = 0;
+                for (int b = 0; b < 3; b++) {
+                    const int nshort = (b == 2) ? 16 : 8;
+                    const int rb = (b == 0) ? 0 : (b == 1 ? 1 + kTile * 8 : 2 + kTile * 16);
+                    float prev = ener[rb + tl * nshort];
+                    if (t0 + tl == 0 && fresh)
+                        prev = 0.0f;                                     // LastEnergy initial value
+                    bool trans = false;
+                    for (int k = 0; k < nshort; k++) {
+                        const float cur = ener[rb + 1 + tl * nshort + k];
+                        if (fsub(cur, prev) > 16.0f) trans = true;
+                        if (fsub(prev, cur) > 20.0f) trans = true;
+                        prev = cur;
+                    }
+                    if (trans) m |= 1u << b;
+                }
+                smask[tl] = (unsigned char)m;
+            }
+        } else {
+            ATDE_PAR_FOR(tl, kTile) smask[tl] = (unsigned char)p.window_mask;
+        }
+        __syncthreads();
+
+        // ---- MDCT: window + fold + pre-twiddle, written straight into kissfft's gather order ----
+        cpx* fft = reinterpret_cast<cpx*>(x);                      // kTile*256 complex
+        ATDE_PAR_FOR(u, kTile * 256) {
+            const int tl = u >> 8, slot = u & 255;
+            const int b = slot < 64 ? 0 : (slot < 128 ? 1 : 2);
+            const int bslot = slot - (b == 0 ? 0 : (b == 1 ? 64 : 128));
+            const int size = (b == 2) ? 256 : 128;
+            const bool shrt = (smask[tl] >> b) & 1;
+            const float* fr = band0[b] + tl * size;
+            int N, i, kb = 0;
+            const float* cs;
+            if (!shrt) {
+                N = 2 * size;
+                i = (b == 2) ? T->perm128[bslot] : T->perm64[bslot];
+                cs = (b == 2) ? T->sincos512 : T->sincos256;
+            } else {
+                N = 64;
+                kb = bslot >> 4;
+                i = T->perm16[bslot & 15];
+                cs = T->sincos64;
+            }
+            const int n = 2 * i, n4 = N >> 2, n34 = 3 * n4, n54 = 5 * n4;
+            const int win_start = (b == 2) ? 112 : 48;
+            float a0, a1, b0, b1;
+            const int ia0 = n34 - 1 - n, ib0 = n4 + n;
+            const int ia1 = (n < n4) ? n34 + n : n - n4;
+            const int ib1 = (n < n4) ? n4 - 1 - n : n54 - 1 - n;
+            if (!shrt) {
+                a0 = mdct_in_long(fr, W, ia0, size, win_start);
+                a1 = mdct_in_long(fr, W, ia1, size, win_start);
+                b0 = mdct_in_long(fr, W, ib0, size, win_start);
+                b1 = mdct_in_long(fr, W, ib1, size, win_start);
+            } else {
+                a0 = mdct_in_short(fr, W, ia0, kb);
+                a1 = mdct_in_short(fr, W, ia1, kb);
+                b0 = mdct_in_short(fr, W, ib0, kb);
+                b1 = mdct_in_short(fr, W, ib1, kb);
+            }
+            float r0, i0;
+            if (n < n4) { r0 = fadd(a0, a1); i0 = fsub(b0, b1); }
+            else        { r0 = fsub(a0, a1); i0 = fadd(b0, b1); }
+            const float cc = cs[n], ss = cs[n + 1];
+            cpx X;
+            X.r = fadd(fmul(r0, cc), fmul(i0, ss));
+            X.i = fsub(fmul(i0, cc), fmul(r0, ss));
+            fft[u] = X;
+        }
+        __syncthreads();
+        // ---- FFT stages, innermost first.  Per frame: 16 (low) + 16 (mid) + 64 (hi) item slots ----
+        for (int st = 0; st < 4; st++) {
+            ATDE_PAR_FOR(u, kTile * 96) {
+                const int tl = u / 96, w = u - tl * 96;
+                const int b = w < 16 ? 0 : (w < 32 ? 1 : 2);
+                const int v = w - (b == 0 ? 0 : (b == 1 ? 16 : 32));
+                const bool shrt = (smask[tl] >> b) & 1;
+                cpx* buf = fft + tl * 256 + (b == 0 ? 0 : (b == 1 ? 64 : 128));
+                if (shrt) {
+                    // FFT16 = 4x4: stages m=1 (fstride 4), m=4 (fstride 1); 4 butterflies per instance
+                    const int ninst4 = (b == 2) ? 32 : 16;
+                    if (st < 2 && v < ninst4) {
+                        const int inst = v >> 2, vv = v & 3;
+                        kf_stage4<false>(buf + 16 * inst, T->tw16, vv, st == 0 ? 1 : 4, st == 0 ? 4 : 1);
+                    }
+                } else if (b != 2) {
+                    // FFT64 = 4x4x4: m = 1, 4, 16
+                    if (st < 3 && v < 16) {
+                        const int m = st == 0 ? 1 : (st == 1 ? 4 : 16);
+                        kf_stage4<false>(buf, T->tw64, v, m, 16 / m);
+                    }
+                } else {
+                    // FFT128 = 4x4x4x2: radix-2 innermost (m=1), then m = 2, 8, 32
+                    if (st == 0) {
+                        kf_stage2(buf, T->tw128, v, 1, 64);
+                    } else if (v < 32) {
+                        const int m = st == 1 ? 2 : (st == 2 ? 8 : 32);
+                        kf_stage4<false>(buf, T->tw128, v, m, 32 / m);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- post-twiddle (mdct.h:92-101), level fix for hi/short, band reversal (atrac1denc.cpp:92-98) ----
+        ATDE_PAR_FOR(u, kTile * 256) {
+            const int tl = u >> 8, slot = u & 255;
+            const int b = slot < 64 ? 0 : (slot < 128 ? 1 : 2);
+            const int bslot = slot - (b == 0 ? 0 : (b == 1 ? 64 : 128));
+            const int size = (b == 2) ? 256 : 128;
+            const bool shrt = (smask[tl] >> b) & 1;
+            int n2, i, kb = 0;
+            const float* cs;
+            if (!shrt) { n2 = size; i = bslot; cs = (b == 2) ? T->sincos512 : T->sincos256; }
+            else { n2 = 32; kb = bslot >> 4; i = bslot & 15; cs = T->sincos64; }
+            const int n = 2 * i;
+            const cpx z = fft[u];
+            const float cc = cs[n], ss = cs[n + 1];
+            float va = fsub(fmul(-z.r, cc), fmul(z.i, ss));
+            float vb = fadd(fmul(-z.r, ss), fmul(z.i, cc));
+            if (shrt && b == 2) { va = fmul(va, 2.0f); vb = fmul(vb, 2.0f); }
+            int pa = n, pb = n2 - 1 - n;
+            if (b) { pa = n2 - 1 - pa; pb = n2 - 1 - pb; }
+            float* out = sp + tl * 512 + (b == 0 ? 0 : (b == 1 ? 128 : 256)) + 32 * kb;
+            out[pa] = va;
+            out[pb] = vb;
+        }
+        __syncthreads();
+        // ---- store spectra, masks; loudness term (sequential sum, atrac1denc.cpp:235-240) ----
+        ATDE_PAR_FOR(u, kTile * 512) {
+            const int tl = u >> 9, i = u & 511;
+            if (t0 + tl < F)
+                p.specs[(((size_t)s * F + t0 + tl) * C + c) * 512 + i] = sp[u];
+        }
+        ATDE_PAR_FOR(tl, kTile) {
+            if (t0 + tl < F) {
+                const float* q = sp + tl * 512;
+                float l = 0.0f;
+                for (int i = 0; i < 512; i++)
+                    l = fadd(l, fmul(fmul(q[i], q[i]), T->loud_curve[i]));
+                const size_t o = ((size_t)s * F + t0 + tl) * C + c;
+                p.chloud[o] = l;
+                p.masks[o] = smask[tl];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launch_analysis(const AnalysisParams& p, cudaStream_t st)
+{
+    dim3 grid((p.F + kTile - 1) / kTile, p.S);
+    ATDE_LAUNCH(at1_analysis_kernel, grid, 256, 0, st, p);
+}
+
+// =====================================================================================
+// K4: loudness recurrence, one thread per stream (atrac1denc.cpp:243-247, atrac_psy_common.h:46-54)
+// =====================================================================================
+__global__ void at1_loudness_kernel(LoudnessParams p)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.S) return;
+    float L = p.loud_in ? p.loud_in[s] : kLoudFactor;
+    for (int f = 0; f < p.F; f++) {
+        const size_t o = ((size_t)s * p.F + f) * p.C;
+        const unsigned m0 = p.masks[o];
+        if (p.C == 2 && m0 == 0 && p.masks[o + 1] == 0) {
+            const float sum = fadd(p.chloud[o], p.chloud[o + 1]);
+            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.01, (double)sum)));
+        } else if (m0 == 0) {
+            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.02, (double)p.chloud[o])));
+        }
+        p.loud[(size_t)s * p.F + f] = L;
+    }
+}
+
+void launch_loudness(const LoudnessParams& p, cudaStream_t st)
+{
+    ATDE_LAUNCH(at1_loudness_kernel, (p.S + 63) / 64, 64, 0, st, p);
+}
+
+// =====================================================================================
+// K5: scale + bit allocation search + boost + bitstream, one warp per channel-frame
+// =====================================================================================
+constexpr int kPackWarps = 4;
+
+ATDE_D unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// CalcBitsAllocation for one BFU (atrac1_bitalloc.cpp:185-203)
+ATDE_D unsigned calc_wl(int sfi, float energy, bool short_block, float fix, float ath, float loud,
+                        float shift, float bias)
+{
+    const float a = fmul(ath, loud);
+    if (!short_block && energy < a)
+        return 0;
+    const float spread = 0.4f;
+    float v = fmul(spread, __fdiv_rn((float)sfi, 3.2f));
+    v = fadd(v, fmul(fsub(1.0f, spread), fix));
+    v = fsub(v, shift);
+    v = fadd(v, bias);
+    const int tmp = __float2int_rz(v);
+    if (tmp > 16) return 16;
+    if (tmp < 2) return 0;
+    return (unsigned)tmp;
+}
+
+// MSB-first bit field into a zeroed big-endian word array (value already masked to n bits)
+ATDE_D void put_bits(unsigned* words, int pos, int n, unsigned val)
+{
+    const int w = pos >> 5, off = pos & 31;
+    const int room = 32 - off;
+    if (n <= room) {
+        atomicOr(&words[w], val << (room - n));
+    } else {
+        atomicOr(&words[w], val >> (n - room));
+        atomicOr(&words[w + 1], val << (32 - (n - room)));
+    }
+}
+
+// TBitStream::Write buffer growth (bitstream.cpp:43-52): only the resulting vector size matters here
+ATDE_D void bs_grow(int& size, int& used, int n)
+{
+    const int bits_left = size * 8 - used;
+    const int bits_req = n - bits_left;
+    const int overlap = used & 7;
+    if (overlap || bits_req >= 0)
+        size += bits_req / 8 + (overlap ? 2 : 1);
+    used += n;
+}
+
+__global__ void __launch_bounds__(kPackWarps * 32) at1_pack_kernel(PackParams p)
+{
+    __shared__ float sv_all[kPackWarps][512];
+    __shared__ unsigned words_all[kPackWarps][56];
+    __shared__ unsigned char wl_all[kPackWarps][kMaxBfus + 4];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long unit = (long long)blockIdx.x * kPackWarps + wib;
+    const long long total = (long long)p.S * p.F * p.C;
+    if (unit >= total) return;                                    // whole warp leaves together
+    float* sv = sv_all[wib];
+    unsigned* words = words_all[wib];
+    unsigned char* wls = wl_all[wib];
+    const DevTables* __restrict__ T = p.tab;
+
+    const long long sf = unit / p.C;                              // s*F + f
+    const unsigned mask = p.masks[unit];
+    const float loud = __fdiv_rn(p.loud[sf], kLoudFactor);        // Loudness / LoudFactor, atrac1denc.cpp:250
+
+    const float* __restrict__ src = p.specs + (size_t)unit * 512;
+    for (int i = lane; i < 512; i += 32) sv[i] = src[i];
+    for (int i = lane; i < 56; i += 32) words[i] = 0;
+    __syncwarp();
+
+    // ---- TScaler::Scale for this lane's BFUs (b = lane, lane + 32) ----
+    int sfi[2] = {0, 0};
+    float energy[2] = {0.0f, 0.0f};
+    for (int h = 0; h < 2; h++) {
+        const int b = lane + 32 * h;
+        if (b < kMaxBfus) {
+            const bool shrt = (mask >> bfu_band(b)) & 1;
+            const int start = shrt ? kSpecsStartShort[b] : kSpecsStartLong[b];
+            const int len = kSpecsPerBlock[b];
+            float mx = 0.0f;
+            for (int j = 0; j < len; j++) {
+                const float a = fabsf(sv[start + j]);
+                if (a > mx) mx = a;
+            }
+            if (mx > 1.0f) mx = 1.0f;
+            int lo_i = 0, hi_i = 63;                               // lower_bound over ScaleTable
+            while (lo_i < hi_i) {
+                const int mid = (lo_i + hi_i) >> 1;
+                if (T->scale_table[mid] < mx) lo_i = mid + 1; else hi_i = mid;
+            }
+            const float scale = T->scale_table[lo_i];
+            sfi[h] = lo_i;
+            float en = 0.0f;
+            for (int j = 0; j < len; j++) {
+                const float xin = sv[start + j];
+                float v = __fdiv_rn(xin, scale);
+                en = fadd(en, fmul(xin, xin));
+                if (fabsf(v) >= 1.0f)
+                    v = (v > 0.0f) ? 0.99999f : -0.99999f;
+                sv[start + j] = v;
+            }
+            energy[h] = en;
+            if (p.tap_sfi) p.tap_sfi[(size_t)unit * kMaxBfus + b] = (unsigned char)lo_i;
+        }
+    }
+    __syncwarp();
+
+    // ---- CalcLowToMidTilt ingredients (integer sums are exact in fp32) ----
+    const unsigned sum_low = warp_sum(lane < 20 ? (unsigned)sfi[0] : 0u);
+    const unsigned sum_m28 = warp_sum((lane >= 20 && lane < 28) ? (unsigned)sfi[0] : 0u);
+    const unsigned sum_m32 = warp_sum(lane >= 20 ? (unsigned)sfi[0] : 0u);
+    const unsigned sum_m36 = sum_m32 + warp_sum(lane < 4 ? (unsigned)sfi[1] : 0u);
+
+    float fix[2], ath[2];
+    bool shrt[2];
+    int len[2];
+    for (int h = 0; h < 2; h++) {
+        const int b = lane + 32 * h;
+        const int bb = b < kMaxBfus ? b : kMaxBfus - 1;
+        shrt[h] = (mask >> bfu_band(bb)) & 1;
+        fix[h] = shrt[h] ? (float)kFixShort[bb] : (float)kFixLong[bb];
+        ath[h] = T->ath_long[bb];
+        len[h] = kSpecsPerBlock[bb];
+    }
+
+    // ---- TBitStreamEncoder over {TConfigure, TBfuAlloc} (encode.cpp:100-129) ----
+    int bfu_idx = p.bfu_idx_const ? p.bfu_idx_const - 1 : 7;
+    const bool auto_bfu = !p.bfu_idx_const;
+    unsigned wl[2] = {0, 0};
+    int nbfu;
+    unsigned bits_used;
+    for (;;) {
+        nbfu = bfu_amount(bfu_idx);
+        const unsigned target = 212 * 8 - 3 - 32 - 2 - 3 - nbfu * 10;
+        // band bias from the low/mid tilt (atrac1_bitalloc.cpp:147-161,176-179)
+        float tilt = 0.0f;
+        if (nbfu > 20) {
+            const int n_mid = (nbfu < 36 ? nbfu : 36) - 20;
+            const unsigned sm = nbfu == 28 ? sum_m28 : (nbfu == 32 ? sum_m32 : sum_m36);
+            tilt = fsub(__fdiv_rn((float)sum_low, 20.0f), __fdiv_rn((float)sm, (float)n_mid));
+        }
+        const float mid_bias = fminf(1.5f, fmul(0.3f, fmaxf(0.0f, fsub(tilt, 7.0f))));
+        const float bias_of_band[3] = {0.0f, mid_bias, fmul(mid_bias, 0.5f)};
+        float bias[2];
+        for (int h = 0; h < 2; h++) {
+            const int b = lane + 32 * h;
+            bias[h] = bias_of_band[bfu_band(b < kMaxBfus ? b : kMaxBfus - 1)];
+        }
+        float mn = -3.0f, mx = 15.0f, cur = 0.0f, last = 15.0f;       // Start(target, -3, 15)
+        for (;;) {
+            const bool exhausted = mx <= mn;
+            const float shift = exhausted ? last
+                                          : __double2float_rn(__ddiv_rn((double)fadd(mx, mn), 2.0));
+            cur = shift;
+            unsigned my_bits = 0;
+            for (int h = 0; h < 2; h++) {
+                const int b = lane + 32 * h;
+                wl[h] = 0;
+                if (b < nbfu) {
+                    wl[h] = calc_wl(sfi[h], energy[h], shrt[h], fix[h], ath[h], loud, shift, bias[h]);
+                    my_bits += (unsigned)len[h] * wl[h];
+                }
+            }
+            bits_used = warp_sum(my_bits);
+            if (exhausted)
+                break;
+            if (bits_used < target) { last = cur; mx = fsub(cur, 0.01f); }
+            else if (bits_used > target) { mn = fadd(cur, 0.01f); }
+            else break;
+        }
+        if (auto_bfu) {
+            // GetMaxUsedBfuId (atrac1_bitalloc.cpp:207-230): amount-table segment of the highest non-zero BFU
+            const unsigned nz0 = __ballot_sync(0xffffffffu, wl[0] != 0);
+            const unsigned nz1 = __ballot_sync(0xffffffffu, wl[1] != 0);
+            const int top = nz1 ? 32 + (31 - __clz((int)nz1)) : (nz0 ? 31 - __clz((int)nz0) : -1);
+            int used = 0;
+            while (used < 7 && bfu_amount(used) <= top) used++;
+            if (top < 0) used = 0;
+            if (used < bfu_idx) { bfu_idx--; continue; }
+        }
+        break;
+    }
+
+    // ---- TBitsBooster::ApplyBoost (atrac1_bitalloc.cpp:80-114): serial, tiny ----
+    if (lane + 0 < kMaxBfus) wls[lane] = (unsigned char)wl[0];
+    if (lane + 32 < kMaxBfus) wls[lane + 32] = (unsigned char)wl[1];
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned target = 212 * 8 - 3 - 32 - 2 - 3 - nbfu * 10;
+        // multimap (bits -> position) in key order, insertion order within a key
+        const unsigned char bpos[12] = {18, 19, 20, 21, 22, 32, 33, 34, 35, 36, 37, 38};
+        const unsigned char bbits[12] = {6, 6, 6, 6, 6, 10, 10, 10, 10, 12, 12, 12};
+        unsigned surplus = target - bits_used;
+        const unsigned key = surplus > 12u ? 12u : surplus;
+        int max_it = 0;
+        while (max_it < 12 && bbits[max_it] <= key) max_it++;
+        if (max_it != 0) {
+            while (surplus >= 6u) {
+                bool done = true;
+                for (int it = 0; it < max_it; ++it) {
+                    const unsigned cb = bbits[it];
+                    const int cp = bpos[it];
+                    if (cp >= nbfu) break;
+                    const unsigned w = wls[cp];
+                    if (w == 16u) continue;
+                    const unsigned per = w ? 1u : 2u;
+                    if (w == 0u && cb * 2 > surplus) continue;
+                    if (cb * per > surplus) continue;
+                    wls[cp] = (unsigned char)(w + per);
+                    surplus -= cb * per;
+                    done = false;
+                }
+                if (done) break;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- TBfuAlloc::Dump (atrac1_bitalloc.cpp:279-327) ----
+    unsigned mbits[2];
+    for (int h = 0; h < 2; h++) {
+        const int b = lane + 32 * h;
+        wl[h] = (b < nbfu) ? wls[b] : 0;
+        mbits[h] = (wl[h] >= 2) ? (unsigned)len[h] * wl[h] : 0u;
+    }
+    // exclusive prefix of mantissa bits in BFU order (b = 0..31 on h=0, 32..51 on h=1)
+    unsigned inc0 = mbits[0], inc1 = mbits[1];
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned a = __shfl_up_sync(0xffffffffu, inc0, d);
+        const unsigned c2 = __shfl_up_sync(0xffffffffu, inc1, d);
+        if (lane >= d) { inc0 += a; inc1 += c2; }
+    }
+    const unsigned tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+    const unsigned start_bits[2] = {inc0 - mbits[0], tot0 + inc1 - mbits[1]};
+
+    if (lane == 0) {
+        const unsigned lc0 = (mask & 1) ? 2 : 0, lc1 = (mask & 2) ? 2 : 0, lc2 = (mask & 4) ? 3 : 0;
+        const unsigned hdr = ((2 - lc0) << 14) | ((2 - lc1) << 12) | ((3 - lc2) << 10) | ((unsigned)bfu_idx << 5);
+        put_bits(words, 0, 16, hdr);
+    }
+    const int mant_base = 16 + 10 * nbfu;
+    for (int h = 0; h < 2; h++) {
+        const int b = lane + 32 * h;
+        if (b < nbfu) {
+            put_bits(words, 16 + 4 * b, 4, wl[h] ? wl[h] - 1 : 0);
+            put_bits(words, 16 + 4 * nbfu + 6 * b, 6, (unsigned)sfi[h]);
+            if (wl[h] >= 2) {
+                const int start = shrt[h] ? kSpecsStartShort[b] : kSpecsStartLong[b];
+                const float mult = (float)((1 << (wl[h] - 1)) - 1);
+                int pos = mant_base + (int)start_bits[h];
+                const unsigned vm = (1u << wl[h]) - 1u;
+                for (int j = 0; j < len[h]; j++) {
+                    const int q = __float2int_rn(fmul(sv[start + j], mult));
+                    put_bits(words, pos, (int)wl[h], (unsigned)q & vm);
+                    pos += (int)wl[h];
+                }
+            }
+        }
+        if (p.tap_wl && b < kMaxBfus)
+            p.tap_wl[(size_t)unit * kMaxBfus + b] = (b < nbfu) ? (unsigned char)wl[h] : 0xff;
+    }
+    __syncwarp();
+    // big-endian words -> byte stream, 53 words = 212 bytes
+    unsigned* __restrict__ dst = reinterpret_cast<unsigned*>(p.out + (size_t)unit * kUnitBytes);
+    for (int i = lane; i < 53; i += 32)
+        dst[i] = __byte_perm(words[i], 0, 0x0123);
+
+    if (p.sizes && lane == 0) {
+        int size = 0, used = 0;
+        bs_grow(size, used, 2); bs_grow(size, used, 2); bs_grow(size, used, 2); bs_grow(size, used, 2);
+        bs_grow(size, used, 3); bs_grow(size, used, 2); bs_grow(size, used, 3);
+        for (int b = 0; b < nbfu; b++) bs_grow(size, used, 4);
+        for (int b = 0; b < nbfu; b++) bs_grow(size, used, 6);
+        for (int b = 0; b < nbfu; b++) {
+            const int w = wls[b];
+            if (w < 2) continue;
+            const int cnt = kSpecsPerBlock[b];
+            for (int j = 0; j < cnt; j++) bs_grow(size, used, w);
+        }
+        bs_grow(size, used, 8); bs_grow(size, used, 8); bs_grow(size, used, 8);
+        p.sizes[unit] = size;
+    }
+}
+
+void launch_pack(const PackParams& p, cudaStream_t st)
+{
+    const long long total = (long long)p.S * p.F * p.C;
+    const unsigned grid = (unsigned)((total + kPackWarps - 1) / kPackWarps);
+    ATDE_LAUNCH(at1_pack_kernel, grid, kPackWarps * 32, 0, st, p);
+}
+
+// =====================================================================================
+// carry: keep the last PCM frame and loudness of every stream for the next batch
+// =====================================================================================
+__global__ void at1_carry_kernel(CarryParams p)
+{
+    const int s = blockIdx.x;
+    const int n = 512 * p.C;
+    const float* src = p.pcm + ((size_t)s * p.F + (p.F - 1)) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        p.hist[(size_t)s * n + i] = src[i];
+    if (threadIdx.x == 0) {
+        p.loud_state[s] = p.loud[(size_t)s * p.F + p.F - 1];
+        p.started[s] = 1;
+    }
+}
+
+void launch_carry(const CarryParams& p, cudaStream_t st)
+{
+    ATDE_LAUNCH(at1_carry_kernel, p.S, 256, 0, st, p);
+}
+
+} // namespace at1
+} // namespace atde

@@ -1,0 +1,79 @@
+// at1_kernels.cuh — device-side interface of the ATRAC1 encode path (see at1_kernels.cu).
+#pragma once
+#include "atde_cuda.h"
+
+namespace atde {
+namespace at1 {
+
+constexpr int kFrame = 512;          // samples per channel-frame (atrac1.h:121)
+constexpr int kMaxBfus = 52;         // atrac1.h:86
+constexpr int kUnitBytes = 212;      // sound unit size (atrac1.h:105)
+constexpr float kLoudFactor = 0.006f; // atrac1denc.h:101
+
+// Tables in global memory (read through L1).  Filled by the host from host_tables.cpp.
+struct DevTables {
+    float sine_window[32];       // atrac1.h:128-132
+    float scale_table[64];       // atrac1.h:122-127
+    float loud_curve[512];       // CreateLoudnessCurve(512)
+    float ath_long[kMaxBfus];    // CalcAt1ATH, atrac1_bitalloc.cpp:118-135
+    float sincos512[256];        // TMDCT<512>(1)
+    float sincos256[128];        // TMDCT<256>(0.5)
+    float sincos64[32];          // TMDCT<64>(0.5)
+    cpx tw128[128], tw64[64], tw16[16];          // forward kissfft twiddles
+    unsigned char perm128[128], perm64[64], perm16[16];
+};
+
+struct AnalysisParams {
+    const float* pcm;            // [S][F*512][C] interleaved, normalised
+    const float* hist;           // [S][512][C] previous frame of each stream, or nullptr (= zeros)
+    const unsigned char* started;// [S] non-zero: stream already ran (frame 0 of this batch is not the stream's first); may be nullptr
+    float* specs;                // [S][F][C][512]
+    unsigned char* masks;        // [S][F][C]  window mask bits low=1 mid=2 hi=4
+    float* chloud;               // [S][F][C]  per-channel loudness term
+    const DevTables* tab;
+    int S, C;
+    int F;
+    int window_auto;             // EWM_AUTO
+    int window_mask;             // used when !window_auto
+};
+
+struct LoudnessParams {
+    const unsigned char* masks;  // [S][F][C]
+    const float* chloud;         // [S][F][C]
+    const float* loud_in;        // [S] carried loudness or nullptr (= LoudFactor)
+    float* loud;                 // [S][F]  Loudness after frame f's update
+    int S, C, F;
+};
+
+struct PackParams {
+    const float* specs;          // [S][F][C][512]
+    const unsigned char* masks;  // [S][F][C]
+    const float* loud;           // [S][F]
+    unsigned char* out;          // [S][F][C][212]
+    int* sizes;                  // [S][F][C] WriteFrame payload length as the reference grows it, or nullptr
+    unsigned char* tap_sfi;      // [S][F][C][52] or nullptr
+    unsigned char* tap_wl;       // [S][F][C][52] or nullptr (after boost; 0xff beyond nbfu)
+    const DevTables* tab;
+    int S, C, F;
+    int bfu_idx_const;
+};
+
+struct CarryParams {
+    const float* pcm;            // [S][F*512][C]
+    const float* loud;           // [S][F]
+    float* hist;                 // [S][512][C]
+    float* loud_state;           // [S]
+    unsigned char* started;      // [S]
+    int S, C, F;
+};
+
+void upload_qmf_window(const float w[48]);
+void launch_analysis(const AnalysisParams& p, cudaStream_t st);
+void launch_loudness(const LoudnessParams& p, cudaStream_t st);
+void launch_pack(const PackParams& p, cudaStream_t st);
+void launch_carry(const CarryParams& p, cudaStream_t st);
+
+constexpr int kTile = 4;             // frames per analysis block
+
+} // namespace at1
+} // namespace atde

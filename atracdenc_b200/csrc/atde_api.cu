@@ -1,0 +1,464 @@
+// atde_api.cu — C ABI (include/atde_b200.h) over the sm_100a kernels.
+//
+// Host-side plumbing only: device buffers, table upload, stream/chunk pipeline, error mapping.
+// There is no CPU implementation of the encode path in this library.
+#include "../../include/atde_b200.h"
+#include "atde_cuda.h"
+#include "at1_kernels.cuh"
+#include "glibc_math.cuh"
+#include "host_tables.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ATDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;     // elements
+    int ensure(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) return fail(ATDE_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        cap = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Per-chunk scratch (one per pipeline slot)
+struct Workspace {
+    DevBuf<float> pcm;              // host path only
+    DevBuf<float> specs;
+    DevBuf<unsigned char> masks;
+    DevBuf<float> chloud;
+    DevBuf<float> loud;
+    DevBuf<unsigned char> out;      // host path only
+    DevBuf<int> sizes;              // host path only
+    DevBuf<unsigned char> tap_sfi, tap_wl;
+    cudaStream_t stream = nullptr;
+    void release()
+    {
+        pcm.release(); specs.release(); masks.release(); chloud.release(); loud.release();
+        out.release(); sizes.release(); tap_sfi.release(); tap_wl.release();
+    }
+};
+
+} // namespace
+
+struct atde_encoder {
+    atde_settings cfg;
+    int frame_samples = 0, units_per_frame = 0, unit_bytes = 0, lookahead = 0;
+    atde::at1::DevTables* d_at1_tab = nullptr;
+    Workspace ws[2];
+    // stream state, sized for n_state_streams
+    DevBuf<float> hist;
+    DevBuf<float> loud_state;
+    DevBuf<unsigned char> started;
+    int n_state_streams = 0;
+    bool have_state = false;
+    bool taps_enabled = false;
+    // geometry of the last batch, for taps
+    int last_S = 0; long long last_F = 0;
+    long long launches = 0;
+    // optional per-kernel CUDA-event timing (atde_set_profiling)
+    bool profiling = false;
+    struct EvPair { cudaEvent_t a, b; int kind; };
+    std::vector<EvPair> ev_pool;
+    size_t ev_used = 0;
+};
+
+namespace {
+
+int build_at1_tables(atde_encoder* e)
+{
+    using namespace atde;
+    at1::DevTables* h = new (std::nothrow) at1::DevTables();
+    if (!h) return fail(ATDE_ERR_NOMEM, "host alloc");
+    float qmf[48];
+    qmf_window(qmf);
+    for (uint32_t i = 0; i < 32; i++)                                   // atrac1.h:128-132
+        h->sine_window[i] = sin((i + 0.5) * (M_PI / (2.0 * 32.0)));
+    for (uint32_t i = 0; i < 64; i++)                                   // atrac1.h:122-127
+        h->scale_table[i] = pow(2.0, (double)(i / 3.0 - 21.0));
+    const std::vector<float> curve = loudness_curve(512);
+    memcpy(h->loud_curve, curve.data(), sizeof(h->loud_curve));
+    {   // CalcAt1ATH (atrac1_bitalloc.cpp:118-135): min over the BFU's lines, dB -> power
+        static const unsigned short start_long[52] = {
+            0, 8, 16, 24, 32, 36, 40, 44, 48, 56, 64, 72, 80, 86, 92, 98, 104, 110, 116, 122,
+            128, 134, 140, 146, 152, 159, 166, 173, 180, 189, 198, 207, 216, 226, 236, 246,
+            256, 268, 280, 292, 304, 316, 328, 340, 352, 372, 392, 412, 432, 452, 472, 492};
+        static const unsigned char per_block[52] = {
+            8, 8, 8, 8, 4, 4, 4, 4, 8, 8, 8, 8, 6, 6, 6, 6, 6, 6, 6, 6,
+            6, 6, 6, 6, 7, 7, 7, 7, 9, 9, 9, 9, 10, 10, 10, 10,
+            12, 12, 12, 12, 12, 12, 12, 12, 20, 20, 20, 20, 20, 20, 20, 20};
+        const std::vector<float> ath = calc_ath(512, 44100);
+        for (int b = 0; b < 52; b++) {
+            float x = 999;
+            for (size_t line = start_long[b]; line < (size_t)start_long[b] + per_block[b]; line++)
+                x = fmin(x, ath[line]);
+            x = pow(10, 0.1 * x);
+            h->ath_long[b] = x;
+        }
+    }
+    const std::vector<float> sc512 = mdct_sincos(512, 1), sc256 = mdct_sincos(256, 0.5), sc64 = mdct_sincos(64, 0.5);
+    memcpy(h->sincos512, sc512.data(), sizeof(h->sincos512));
+    memcpy(h->sincos256, sc256.data(), sizeof(h->sincos256));
+    memcpy(h->sincos64, sc64.data(), sizeof(h->sincos64));
+    const auto tw128 = kiss_twiddles(128, false), tw64 = kiss_twiddles(64, false), tw16 = kiss_twiddles(16, false);
+    memcpy(h->tw128, tw128.data(), sizeof(h->tw128));
+    memcpy(h->tw64, tw64.data(), sizeof(h->tw64));
+    memcpy(h->tw16, tw16.data(), sizeof(h->tw16));
+    const auto p128 = kiss_perm(128), p64 = kiss_perm(64), p16 = kiss_perm(16);
+    for (int i = 0; i < 128; i++) h->perm128[i] = (unsigned char)p128[i];
+    for (int i = 0; i < 64; i++) h->perm64[i] = (unsigned char)p64[i];
+    for (int i = 0; i < 16; i++) h->perm16[i] = (unsigned char)p16[i];
+
+    cudaError_t ce = cudaMalloc(&e->d_at1_tab, sizeof(at1::DevTables));
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->d_at1_tab, h, sizeof(at1::DevTables), cudaMemcpyHostToDevice);
+    delete h;
+    if (ce != cudaSuccess) return fail(ATDE_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(ce));
+    at1::upload_qmf_window(qmf);
+    return 0;
+}
+
+struct KernelTimer {
+    atde_encoder* e; cudaStream_t st; int idx = -1;
+    KernelTimer(atde_encoder* e_, cudaStream_t st_, int kind) : e(e_), st(st_)
+    {
+        if (!e->profiling) return;
+        if (e->ev_used == e->ev_pool.size()) {
+            atde_encoder::EvPair p;
+            if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+            e->ev_pool.push_back(p);
+        }
+        idx = (int)e->ev_used++;
+        e->ev_pool[idx].kind = kind;
+        cudaEventRecord(e->ev_pool[idx].a, st);
+    }
+    ~KernelTimer() { if (idx >= 0) cudaEventRecord(e->ev_pool[idx].b, st); }
+};
+
+// Runs the ATRAC1 pipeline for `S` streams x F frames whose PCM is at d_pcm (device), first
+// stream index s0 inside the handle's state arrays.
+int run_at1(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, long long F,
+            unsigned char* d_out, int* d_sizes)
+{
+    using namespace atde::at1;
+    const int C = e->cfg.channels;
+    const size_t units = (size_t)S * F * C;
+    int rc;
+    if ((rc = w.specs.ensure(units * 512))) return rc;
+    if ((rc = w.masks.ensure(units))) return rc;
+    if ((rc = w.chloud.ensure(units))) return rc;
+    if ((rc = w.loud.ensure((size_t)S * F))) return rc;
+    if (e->taps_enabled) {
+        if ((rc = w.tap_sfi.ensure(units * 52))) return rc;
+        if ((rc = w.tap_wl.ensure(units * 52))) return rc;
+    }
+    AnalysisParams a;
+    a.pcm = d_pcm;
+    a.hist = e->hist.p + (size_t)s0 * 512 * C;
+    a.started = e->started.p + s0;
+    a.specs = w.specs.p; a.masks = w.masks.p; a.chloud = w.chloud.p;
+    a.tab = e->d_at1_tab;
+    a.S = S; a.C = C; a.F = (int)F;
+    a.window_auto = e->cfg.window_mode == 1;
+    a.window_mask = (int)e->cfg.window_mask;
+    { KernelTimer kt(e, w.stream, 0); launch_analysis(a, w.stream); }
+
+    LoudnessParams l;
+    l.masks = w.masks.p; l.chloud = w.chloud.p;
+    l.loud_in = e->loud_state.p + s0;
+    l.loud = w.loud.p;
+    l.S = S; l.C = C; l.F = (int)F;
+    { KernelTimer kt(e, w.stream, 1); launch_loudness(l, w.stream); }
+
+    PackParams k;
+    k.specs = w.specs.p; k.masks = w.masks.p; k.loud = w.loud.p;
+    k.out = d_out; k.sizes = d_sizes;
+    k.tap_sfi = e->taps_enabled ? w.tap_sfi.p : nullptr;
+    k.tap_wl = e->taps_enabled ? w.tap_wl.p : nullptr;
+    k.tab = e->d_at1_tab;
+    k.S = S; k.C = C; k.F = (int)F;
+    k.bfu_idx_const = (int)e->cfg.bfu_idx_const;
+    { KernelTimer kt(e, w.stream, 2); launch_pack(k, w.stream); }
+
+    CarryParams c;
+    c.pcm = d_pcm; c.loud = w.loud.p;
+    c.hist = e->hist.p + (size_t)s0 * 512 * C;
+    c.loud_state = e->loud_state.p + s0;
+    c.started = e->started.p + s0;
+    c.S = S; c.C = C; c.F = (int)F;
+    launch_carry(c, w.stream);
+    e->launches += 4;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void init_state_kernel(float* loud, unsigned char* started, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { loud[i] = atde::at1::kLoudFactor; started[i] = 0; }
+}
+
+int ensure_state(atde_encoder* e, int S)
+{
+    if (e->have_state && e->n_state_streams == S) return 0;
+    if (e->have_state && e->n_state_streams != S)
+        return fail(ATDE_ERR_INVALID, "batch has %d streams but the handle carries state for %d; call atde_reset() first", S, e->n_state_streams);
+    int rc;
+    const int C = e->cfg.channels;
+    if ((rc = e->hist.ensure((size_t)S * e->frame_samples * C))) return rc;
+    if ((rc = e->loud_state.ensure(S))) return rc;
+    if ((rc = e->started.ensure(S))) return rc;
+    ATDE_LAUNCH(init_state_kernel, (S + 255) / 256, 256, 0, e->ws[0].stream, e->loud_state.p, e->started.p, S);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->ws[0].stream));
+    e->n_state_streams = S;
+    e->have_state = true;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* atde_last_error(void) { return g_err.c_str(); }
+const char* atde_version(void) { return "atde_b200 0.1 (sm_100a)"; }
+
+void atde_default_settings(atde_settings* s, int32_t codec, int32_t channels)
+{
+    memset(s, 0, sizeof(*s));
+    s->codec = codec;
+    s->channels = channels;
+    s->window_mode = 1;
+}
+
+int atde_create(const atde_settings* s, atde_encoder** out)
+{
+    if (!s || !out) return fail(ATDE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (s->channels < 1 || s->channels > 2) return fail(ATDE_ERR_INVALID, "channels must be 1 or 2");
+    if (s->codec != ATDE_CODEC_ATRAC1)
+        return fail(ATDE_ERR_UNSUPPORTED, "codec %d is not built yet", s->codec);
+    if (s->bfu_idx_const > 8) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..8");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(ATDE_ERR_CUDA, "no CUDA device: libatde_b200 has no CPU fallback");
+    CK(cudaSetDevice(s->device));
+    atde_encoder* e = new (std::nothrow) atde_encoder();
+    if (!e) return fail(ATDE_ERR_NOMEM, "host alloc");
+    e->cfg = *s;
+    e->frame_samples = 512;
+    e->units_per_frame = s->channels;
+    e->unit_bytes = atde::at1::kUnitBytes;
+    e->lookahead = 0;
+    for (int i = 0; i < 2; i++) {
+        cudaError_t ce = cudaStreamCreateWithFlags(&e->ws[i].stream, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { delete e; return fail(ATDE_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
+    }
+    int rc = build_at1_tables(e);
+    if (rc) { atde_destroy(e); return rc; }
+    *out = e;
+    return 0;
+}
+
+void atde_destroy(atde_encoder* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        e->ws[i].release();
+        if (e->ws[i].stream) cudaStreamDestroy(e->ws[i].stream);
+    }
+    e->hist.release(); e->loud_state.release(); e->started.release();
+    if (e->d_at1_tab) cudaFree(e->d_at1_tab);
+    for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    delete e;
+}
+
+int atde_frame_samples(const atde_encoder* e) { return e ? e->frame_samples : ATDE_ERR_INVALID; }
+int atde_units_per_frame(const atde_encoder* e) { return e ? e->units_per_frame : ATDE_ERR_INVALID; }
+int atde_unit_bytes(const atde_encoder* e) { return e ? e->unit_bytes : ATDE_ERR_INVALID; }
+int atde_lookahead_frames(const atde_encoder* e) { return e ? e->lookahead : ATDE_ERR_INVALID; }
+void* atde_cuda_stream(atde_encoder* e) { return e ? (void*)e->ws[0].stream : nullptr; }
+int64_t atde_launch_count(const atde_encoder* e) { return e ? e->launches : 0; }
+
+int atde_reset(atde_encoder* e)
+{
+    if (!e) return fail(ATDE_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    e->have_state = false;
+    e->n_state_streams = 0;
+    return 0;
+}
+
+int atde_sync(atde_encoder* e)
+{
+    if (!e) return fail(ATDE_ERR_INVALID, "null handle");
+    CK(cudaStreamSynchronize(e->ws[0].stream));
+    CK(cudaStreamSynchronize(e->ws[1].stream));
+    return 0;
+}
+
+int atde_encode_batch_device(atde_encoder* e, const float* d_pcm, int32_t S, int64_t F,
+                             uint8_t* d_out, int32_t* d_sizes)
+{
+    if (!e || !d_pcm || !d_out) return fail(ATDE_ERR_INVALID, "null argument");
+    if (S <= 0 || F <= 0) return fail(ATDE_ERR_INVALID, "empty batch (S=%d, F=%lld)", S, (long long)F);
+    if (F > (1 << 21)) return fail(ATDE_ERR_INVALID, "too many frames per stream in one batch");
+    CK(cudaSetDevice(e->cfg.device));
+    int rc = ensure_state(e, S);
+    if (rc) return rc;
+    e->last_S = S; e->last_F = F;
+    return run_at1(e, e->ws[0], d_pcm, 0, S, F, d_out, d_sizes);
+}
+
+int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
+{
+    if (!e || !pcm || !out) return fail(ATDE_ERR_INVALID, "null argument");
+    if (S <= 0 || F <= 0) return fail(ATDE_ERR_INVALID, "empty batch (S=%d, F=%lld)", S, (long long)F);
+    if (F > (1 << 21)) return fail(ATDE_ERR_INVALID, "too many frames per stream in one batch");
+    CK(cudaSetDevice(e->cfg.device));
+    int rc = ensure_state(e, S);
+    if (rc) return rc;
+    e->last_S = S; e->last_F = F;
+    const int C = e->cfg.channels;
+    const size_t pcm_per_stream = (size_t)F * e->frame_samples * C;            // floats
+    const size_t out_per_stream = (size_t)F * e->units_per_frame * e->unit_bytes;
+    const size_t units_per_stream = (size_t)F * e->units_per_frame;
+    // chunk by streams so H2D of chunk k+1 overlaps compute of chunk k (two pipeline slots)
+    const size_t target_floats = (size_t)48 << 20;                              // ~192 MiB of PCM per chunk
+    int chunk = (int)(target_floats / pcm_per_stream);
+    if (chunk < 1) chunk = 1;
+    if (chunk > S) chunk = S;
+    int slot = 0;
+    for (int s0 = 0; s0 < S; s0 += chunk, slot ^= 1) {
+        const int n = (S - s0 < chunk) ? S - s0 : chunk;
+        Workspace& w = e->ws[slot];
+        if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) return rc;
+        if ((rc = w.out.ensure((size_t)n * out_per_stream))) return rc;
+        if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return rc;
+        CK(cudaMemcpyAsync(w.pcm.p, pcm + (size_t)s0 * pcm_per_stream, (size_t)n * pcm_per_stream * sizeof(float),
+                           cudaMemcpyHostToDevice, w.stream));
+        if ((rc = run_at1(e, w, w.pcm.p, s0, n, F, w.out.p, sizes ? w.sizes.p : nullptr))) return rc;
+        CK(cudaMemcpyAsync(out + (size_t)s0 * out_per_stream, w.out.p, (size_t)n * out_per_stream,
+                           cudaMemcpyDeviceToHost, w.stream));
+        if (sizes)
+            CK(cudaMemcpyAsync(sizes + (size_t)s0 * units_per_stream, w.sizes.p, (size_t)n * units_per_stream * sizeof(int),
+                               cudaMemcpyDeviceToHost, w.stream));
+    }
+    CK(cudaStreamSynchronize(e->ws[0].stream));
+    CK(cudaStreamSynchronize(e->ws[1].stream));
+    return 0;
+}
+
+int atde_set_profiling(atde_encoder* e, int32_t on)
+{
+    if (!e) return fail(ATDE_ERR_INVALID, "null handle");
+    e->profiling = on != 0;
+    e->ev_used = 0;
+    return 0;
+}
+
+int atde_kernel_times(atde_encoder* e, double* ms_sum, int64_t* count, int32_t n_kinds)
+{
+    if (!e || !ms_sum || !count) return fail(ATDE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < n_kinds; k++) { ms_sum[k] = 0; count[k] = 0; }
+    for (size_t i = 0; i < e->ev_used; i++) {
+        float ms = 0;
+        const auto& p = e->ev_pool[i];
+        if (p.kind < n_kinds && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { ms_sum[p.kind] += ms; count[p.kind]++; }
+    }
+    e->ev_used = 0;
+    return 0;
+}
+
+int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* dst, size_t capacity)
+{
+    if (!e || !dst) return fail(ATDE_ERR_INVALID, "null argument");
+    if (what == 0) { e->taps_enabled = true; return 0; }      // arm taps for following batches
+    const size_t units = (size_t)e->last_S * e->last_F * e->cfg.channels;
+    const Workspace& w = e->ws[0];
+    const void* src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case ATDE_TAP_SPECS: src = w.specs.p; bytes = units * e->frame_samples * sizeof(float); break;
+        case ATDE_TAP_MASKS: src = w.masks.p; bytes = units; break;
+        case ATDE_TAP_CHLOUD: src = w.chloud.p; bytes = units * sizeof(float); break;
+        case ATDE_TAP_LOUDNESS: src = w.loud.p; bytes = (size_t)e->last_S * e->last_F * sizeof(float); break;
+        case ATDE_TAP_SFI: src = w.tap_sfi.p; bytes = units * 52; break;
+        case ATDE_TAP_WORDLEN: src = w.tap_wl.p; bytes = units * 52; break;
+        default: return fail(ATDE_ERR_INVALID, "unknown tap %d", what);
+    }
+    if (!src) return fail(ATDE_ERR_INVALID, "tap %d not captured (arm with what=0 before the batch)", what);
+    if (bytes > capacity) return fail(ATDE_ERR_INVALID, "tap needs %zu bytes, capacity %zu", bytes, capacity);
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return (int64_t)bytes;
+}
+
+} // extern "C"
+
+namespace {
+__global__ void math_kernel(int fn, const float* x, float* y, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    y[i] = fn == 0 ? atde::g_log10f(v) : (fn == 1 ? atde::g_log2f(v) : atde::g_logf(v));
+}
+} // namespace
+
+extern "C" int atde_debug_math(int32_t device, int32_t fn, const float* x, float* y, int64_t n)
+{
+    if (!x || !y || n <= 0) return fail(ATDE_ERR_INVALID, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(ATDE_ERR_CUDA, "no CUDA device: libatde_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    float *dx = nullptr, *dy = nullptr;
+    CK(cudaMalloc(&dx, n * sizeof(float)));
+    CK(cudaMalloc(&dy, n * sizeof(float)));
+    CK(cudaMemcpy(dx, x, n * sizeof(float), cudaMemcpyHostToDevice));
+    ATDE_LAUNCH(math_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t) nullptr, (int)fn, (const float*)dx, dy, (long long)n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(y, dy, n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy);
+    return 0;
+}

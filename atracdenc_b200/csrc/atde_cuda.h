@@ -1,0 +1,45 @@
+// atde_cuda.h — single include for every kernel translation unit.
+//
+// Product build: nvcc, sm_100a, -fmad=false (the parity contract forbids FMA contraction: the
+// reference is built for baseline x86-64).
+//
+// ATDE_CPU_EMU build: tests/cpuemu compiles the SAME kernel sources with g++ against a small
+// thread-per-CUDA-thread shim so the kernels can be checked against the oracle on a box without
+// a GPU.  That build is test tooling only; it is never part of libatde_b200.so and the product
+// library has no CPU path.
+#pragma once
+
+#ifdef ATDE_CPU_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#define ATDE_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define ATDE_HD __host__ __device__ __forceinline__
+#define ATDE_D __device__ __forceinline__
+#endif
+
+// Block-wide "parallel for": every phase between two __syncthreads() is a grid-stride loop over
+// independent work items.
+#define ATDE_PAR_FOR(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += (int)blockDim.x)
+
+namespace atde {
+
+struct cpx { float r, i; };
+
+// Un-fused IEEE fp32 helpers.  With -fmad=false plain operators would do, but spelling the
+// rounding out keeps the parity contract visible and survives a stray build flag.
+ATDE_D float fmul(float a, float b) { return __fmul_rn(a, b); }
+ATDE_D float fadd(float a, float b) { return __fadd_rn(a, b); }
+ATDE_D float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+// C_MUL of kissfft (_kiss_fft_guts.h:87-89): 4 products, 1 sub, 1 add, each rounded.
+ATDE_D cpx cmul(cpx a, cpx b)
+{
+    cpx m;
+    m.r = fsub(fmul(a.r, b.r), fmul(a.i, b.i));
+    m.i = fadd(fmul(a.r, b.i), fmul(a.i, b.r));
+    return m;
+}
+
+} // namespace atde

@@ -1,0 +1,313 @@
+#!/usr/bin/env python3
+"""
+bench.py — throughput of the B200 encode hot path (frames/s) with roofline and CPU baseline.
+
+  python bench.py --gpus N --steps K --warmup W            our arm
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU path
+
+A "step" is one pass of the hot path over one batch of synthetic PCM (S streams x F frames,
+44.1 kHz stereo, int16-quantised).  `value` = whole-job stereo frames/s with PCM resident in HBM
+(device entry point, CUDA events on the library's stream); `e2e` = the same metric through
+atde_encode_batch() with HOST (pinned) buffers, H2D/D2H inside the timed region.
+Multi-GPU: one process per GPU (torchrun), streams sharded by rank, no data-path collective
+(the path shards by stream) -> weak scaling; NCCL only for the barrier and the
+max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = {
+    # name: (codec id, frame samples, S, F, units/frame, unit bytes, algorithmic QMF+MDCT bytes per stereo frame)
+    "atrac1_stereo_1e6": dict(codec=1, step=512, S=1024, F=977, alg_bytes=8192,
+                              desc="ATRAC1 encode, 10^6-frame synthetic stereo batch (BASELINE.json configs[1])"),
+}
+DEFAULT_WORKLOAD = "atrac1_stereo_1e6"
+METRIC = "ATRAC3 stereo frames/s at 1/2/4/8 B200; QMF+MDCT achieved HBM GB/s vs peak"
+
+
+def read_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def gen_pcm_device(torch, S, F, step, C, rank):
+    """Synthetic PCM generated on the device (noise + per-stream tone + periodic +20 dB bursts, one silent
+    stream in 61), int16-quantised then /32768 like a 16-bit WAV through libsndfile."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0xA7AC + rank)
+    n = F * step
+    x = torch.empty((S, n, C), dtype=torch.float32, device="cuda")
+    t = torch.arange(n, device="cuda", dtype=torch.float32)
+    blk = 64
+    for s0 in range(0, S, blk):
+        s1 = min(S, s0 + blk)
+        sid = torch.arange(s0, s1, device="cuda", dtype=torch.float32)
+        freq = 100.0 * (1 + (sid % 160))
+        v = 0.025 * (2 * torch.rand((s1 - s0, n, C), generator=g, device="cuda") - 1)
+        ph = 2 * torch.pi * freq[:, None] * t[None, :] / 44100.0
+        for c in range(C):
+            v[:, :, c] += 0.03 * torch.sin(ph + c)
+        fr = v.view(s1 - s0, F, step, C)
+        fr[:, ::7, :64, :] *= 10.0
+        silent = ((sid.long() % 61) == 60)
+        v[silent] = 0
+        x[s0:s1] = torch.round(v * 32767).clamp_(-32768, 32767) / 32768.0
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own encoder (oracle/_ref) on the host cores
+def _cpu_worker(args):
+    codec, C, step, F, n_streams, seed, use_ref = args
+    import numpy as np
+    import atde_testlib as tl
+    pcm = tl.synth_streams(n_streams, F, step, C, seed=seed)
+    t0 = time.perf_counter()
+    for s in range(n_streams):
+        if use_ref:
+            tl.ref_encode(codec, C, pcm[s].reshape(-1))
+        else:
+            tl.port_at1_encode(C, pcm[s].reshape(-1))
+    return time.perf_counter() - t0, n_streams * F
+
+
+def cpu_reference_rate(wl, streams_per_core=8, frames=977):
+    """Stereo frames/s of the reference CPU encoder using every host core (one process per core,
+    whole streams each), PCM generation excluded from the timed region."""
+    import multiprocessing as mp
+    import atde_testlib as tl
+    use_ref = tl.ref_lib() is not None
+    cores = os.cpu_count() or 1
+    jobs = [(wl["codec"], 2, wl["step"], frames, streams_per_core, 1000 + i, use_ref) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    total = sum(r[1] for r in res)
+    return dict(value=total / busy, cores=cores, kind="reference" if use_ref else "port", frames=total, busy_s=busy,
+                sample=f"{cores} processes x {streams_per_core} streams x {frames} stereo frames "
+                       f"({total} frames, {busy:.1f} s busy, {wall:.1f} s wall incl. PCM generation)",
+                unit="frames/s")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_rate(wl, streams_per_core=4, frames=wl["F"])
+        if i >= args.warmup:
+            rates.append(r)
+    value = sum(r["value"] for r in rates) / len(rates)
+    cb = dict(rates[-1]); cb["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * sum(r["busy_s"] for r in rates) / len(rates),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample_per_step": cb["sample"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import atracdenc_b200 as ab
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = WORKLOADS[args.workload]
+    S, F, step, C = args.streams or wl["S"], args.frames or wl["F"], wl["step"], 2
+    enc = ab.Encoder(wl["codec"], C, device=local)
+    units, ub = enc.units_per_frame, enc.unit_bytes
+    d_pcm = gen_pcm_device(torch, S, F, step, C, rank)
+    d_out = torch.empty((S, F, units, ub), dtype=torch.uint8, device="cuda")
+    h_pcm = torch.empty((S, F * step, C), dtype=torch.float32, pin_memory=True)
+    h_pcm.copy_(d_pcm)
+    h_out = torch.empty((S, F, units, ub), dtype=torch.uint8, pin_memory=True)
+    stream = torch.cuda.ExternalStream(enc.cuda_stream, device=torch.device("cuda", local))
+    torch.cuda.synchronize()
+
+    # ---- device-resident loop: `value` ----
+    for _ in range(args.warmup):
+        enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
+    enc.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = enc.launch_count
+    enc.set_profiling(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
+    e1.record(stream)
+    enc.sync()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    kms, kcnt = enc.kernel_times(3)
+    enc.set_profiling(False)
+    launches = enc.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end loop through the host API: `e2e` ----
+    enc.reset()
+    for _ in range(max(1, args.warmup // 2)):
+        enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
+    torch.cuda.synchronize()
+    host_ms = (time.perf_counter() - t0) * 1000.0
+    barrier()
+    same = bool(torch.equal(h_out[:4], d_out[:4].cpu())) if args.steps else True
+
+    t = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, host_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        frames_total = S * F * world
+        value = frames_total * args.steps / (dev_ms / 1000.0)
+        e2e = frames_total * args.steps / (host_ms / 1000.0)
+        peak, peak_kind = read_peak()
+        k1_ms = kms[0] / max(1, kcnt[0])
+        alg_bytes = wl["alg_bytes"] * S * F
+        achieved = alg_bytes / (k1_ms / 1000.0) / 1e9 if k1_ms > 0 else None
+        traffic = None
+        tp = ROOT / "profiles" / "k1_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "streams_per_gpu": S, "frames_per_stream": F, "channels": C,
+                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
+                       "l2_policy": f"inputs larger than L2 ({S * F * step * C * 4 / 2**20:.0f} MiB PCM per step)",
+                       "settings": "reference defaults (EWM_AUTO, bfuidxconst 0)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "kernel": "at1_analysis_kernel (QMF+transient+MDCT)", "peak_source": f"of {peak_kind}",
+                         "kernel_ms": k1_ms, "alg_bytes_per_launch": alg_bytes,
+                         "kernel_share_of_step": (kms[0] / dev_ms) if dev_ms else None,
+                         "other_kernels_ms": {"loudness_scan": kms[1] / max(1, kcnt[1]), "scale_alloc_pack": kms[2] / max(1, kcnt[2])}},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": S * F * step * C * 4,
+                    "d2h_bytes_per_step": S * F * units * ub, "ms_per_step": host_ms / args.steps,
+                    "host_and_device_outputs_equal": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_rate(wl)
+        print(json.dumps(line), flush=True)
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=0, help="override streams per GPU (debug)")
+    ap.add_argument("--frames", type=int, default=0, help="override frames per stream (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

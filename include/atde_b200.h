@@ -1,0 +1,139 @@
+/*
+ * atde_b200.h — C ABI of libatde_b200.so, the B200-native drop-in for atracdenc's per-frame
+ * encode hot path (QMF analysis -> MDCT -> transient detection / gain control -> bit allocation
+ * -> quantisation -> frame bitstream).
+ *
+ * What it replaces in the reference (dcherednik/atracdenc):
+ *   - the frame-processor lambdas returned by IProcessor::GetLambda()  (src/pcmengin.h:195-199)
+ *       TAtrac1Encoder::GetLambda   src/atrac1denc.cpp:180-255
+ *       TAtrac3Encoder::GetLambda   src/atrac3denc.cpp:679-867
+ *   - and, on the output side, produces exactly the byte vectors those lambdas hand to
+ *       ICompressedOutput::WriteFrame(std::vector<char>)             (src/compressed_io.h:56-59)
+ *     in the same order (ATRAC1: one 212-byte sound unit per channel per frame, channel 0 first,
+ *     src/atrac/at1/atrac1_bitalloc.cpp:406; ATRAC3: one FrameSz-byte unit per frame,
+ *     src/atrac/at3/atrac3_bitstream.cpp:845).
+ *
+ * Unit of work: a batch of S independent streams x F consecutive frames.  A "stream" is what
+ * the reference calls one encoder instance.  Streams continue across calls (the handle keeps
+ * the cross-frame state of SURVEY.md §3.4 on the device) until atde_reset().
+ *
+ * Plain C: pointers and sizes only; no C++/torch types.  Every call returns 0 on success or a
+ * negative atde_status; atde_last_error() describes the last failure on the calling thread.
+ * There is NO CPU fallback: without a CUDA device every entry point that computes fails.
+ */
+#ifndef ATDE_B200_H
+#define ATDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ATDE_OK = 0,
+    ATDE_ERR_INVALID = -1,      /* bad argument / unsupported setting */
+    ATDE_ERR_CUDA = -2,         /* CUDA runtime error (message in atde_last_error) */
+    ATDE_ERR_NOMEM = -3,
+    ATDE_ERR_UNSUPPORTED = -4   /* codec or option not built yet */
+} atde_status;
+
+typedef enum {
+    ATDE_CODEC_ATRAC1 = 1,      /* -e atrac1        src/main.cpp:635-655 */
+    ATDE_CODEC_ATRAC3 = 3,      /* -e atrac3 / atrac3_lp4  src/main.cpp:657-678 */
+    ATDE_CODEC_ATRAC3PLUS = 4   /* -e atrac3plus    src/main.cpp:679-686 */
+} atde_codec;
+
+/* Mirrors the reference's settings objects field by field. */
+typedef struct {
+    int32_t codec;              /* atde_codec */
+    int32_t channels;           /* 1 or 2 (ICompressedOutput::GetChannelNum / TAtrac3EncoderSettings::SourceChannels) */
+    /* NAtrac1::TAtrac1EncodeSettings (src/atrac/at1/atrac1.h:33-54) */
+    uint32_t bfu_idx_const;     /* --bfuidxconst, 0 = automatic (also TAtrac3EncoderSettings::BfuIdxConst) */
+    int32_t window_mode;        /* 0 = EWM_NOTRANSIENT, 1 = EWM_AUTO */
+    uint32_t window_mask;       /* used when window_mode == 0 : bit0 low, bit1 mid, bit2 hi short */
+    /* NAtrac3::TAtrac3EncoderSettings (src/atrac/at3/atrac3.h:260-277) */
+    uint32_t bitrate;           /* bits/s as main.cpp passes it (kbit*1024); 0 = LP2 default */
+    int32_t no_gain_control;    /* --nogaincontrol */
+    int32_t no_tonal;           /* --notonal */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t reserved[7];
+} atde_settings;
+
+typedef struct atde_encoder atde_encoder;
+
+/* Fills *s with the reference's defaults for `codec` (main.cpp: TAtrac1EncodeSettings(0, EWM_AUTO, 0);
+ * TAtrac3EncoderSettings(0, false, false, channels, 0)). */
+void atde_default_settings(atde_settings* s, int32_t codec, int32_t channels);
+
+/* Construct / destroy an encoder (== constructing TAtrac1Encoder / TAtrac3Encoder). */
+int atde_create(const atde_settings* s, atde_encoder** out);
+void atde_destroy(atde_encoder* e);
+
+/* Geometry of the codec the handle was built for. */
+int atde_frame_samples(const atde_encoder* e);     /* sample-frames per lambda call: 512 / 1024 / 2048 */
+int atde_units_per_frame(const atde_encoder* e);   /* WriteFrame calls per lambda call: ATRAC1 = channels, ATRAC3 = 1 */
+int atde_unit_bytes(const atde_encoder* e);        /* bytes stored per unit in `out` (container frame size) */
+int atde_lookahead_frames(const atde_encoder* e);  /* lambda calls that return LOOK_AHEAD before output starts (0 / 1) */
+
+/*
+ * Encode S streams x F frames from HOST memory (the reference-facing path: copies in, kernels,
+ * copies out; synchronous).
+ *   pcm   [S][F*frame_samples][channels] interleaved normalised float32 — the memory layout the
+ *         reference lambda receives (data[i*Channels + ch], src/atrac1denc.cpp:206-209), one
+ *         stream after another.
+ *   out   [S][F][units_per_frame][unit_bytes]; each unit is the WriteFrame payload zero-padded or
+ *         truncated to the container frame size exactly as TAeaOutput/TRaw do (src/aea.cpp:182,
+ *         src/raw.cpp:41-43).
+ *   sizes optional [S][F][units_per_frame]: true payload length (std::vector<char>::size()) of
+ *         each WriteFrame call; NULL to skip.
+ * Streams continue from the previous call on this handle (same S required) unless atde_reset()
+ * was called; the first batch after create/reset starts every stream from the reference's
+ * initial encoder state.
+ */
+int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t n_streams, int64_t n_frames,
+                      uint8_t* out, int32_t* sizes);
+
+/* Same, with pcm/out/sizes already resident in DEVICE memory of the handle's GPU; enqueued on the
+ * handle's stream, returns without synchronising (use atde_sync). */
+int atde_encode_batch_device(atde_encoder* e, const float* d_pcm, int32_t n_streams, int64_t n_frames,
+                             uint8_t* d_out, int32_t* d_sizes);
+int atde_sync(atde_encoder* e);
+
+/* Forget all stream state: the next batch starts new streams. */
+int atde_reset(atde_encoder* e);
+
+/* cudaStream_t the handle launches on (as void*), for event timing by the caller. */
+void* atde_cuda_stream(atde_encoder* e);
+/* Number of kernel launches issued by this handle so far. */
+int64_t atde_launch_count(const atde_encoder* e);
+
+/* Per-kernel device timing.  With profiling on, every kernel launch of the handle is bracketed by
+ * CUDA events on its stream; atde_kernel_times() synchronises, returns the summed milliseconds
+ * and launch counts per kernel kind since the last query and clears them.
+ * Kinds: 0 = QMF+MDCT analysis, 1 = loudness scan, 2 = scale/allocate/quantise/pack. */
+int atde_set_profiling(atde_encoder* e, int32_t on);
+int atde_kernel_times(atde_encoder* e, double* ms_sum, int64_t* count, int32_t n_kinds);
+
+/* Test taps: copy an intermediate of the LAST batch to host memory.  Returns bytes copied or <0. */
+typedef enum {
+    ATDE_TAP_SPECS = 1,     /* float  [S][F][C][frame_samples] MDCT spectra */
+    ATDE_TAP_MASKS = 2,     /* uint8  [S][F][C] ATRAC1 window masks */
+    ATDE_TAP_CHLOUD = 3,    /* float  [S][F][C] per-channel loudness term */
+    ATDE_TAP_LOUDNESS = 4,  /* float  [S][F] tracked loudness */
+    ATDE_TAP_SFI = 5,       /* uint8  [S][F][C][52|32] scale factor indices */
+    ATDE_TAP_WORDLEN = 6    /* uint8  [S][F][C][52|32] word lengths / precisions */
+} atde_tap;
+int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* host_dst, size_t capacity);
+
+/* Device-side math self-test hooks (tests only): evaluates the glibc replicas on n inputs. */
+int atde_debug_math(int32_t device, int32_t fn /*0 log10f 1 log2f 2 logf*/, const float* x, float* y, int64_t n);
+
+const char* atde_last_error(void);
+const char* atde_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATDE_B200_H */

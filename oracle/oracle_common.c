@@ -406,3 +406,25 @@ void ocreate_loudness_curve(int sz, float* res)
 
 float otrack_loudness2(float prev, float l0, float l1) { return 0.98 * prev + 0.01 * (l0 + l1); }
 float otrack_loudness1(float prev, float l) { return 0.98 * prev + 0.02 * l; }
+
+/* ------------------------------------------------------------------ self-test hooks -------- */
+/* Restates the fixture of src/lib/bs_encode/encode_ut.cpp:27-33,138-176: one part calls
+ * Start(1000,-15,-1), the next runs Continue/Submit on a synthetic cost function until done.
+ * kind 1 = SomeBitFn1, kind 2 = SomeBitFn2.  Reports Encode() calls and the final bit count. */
+void obisect_selftest(int kind, int* calls, long* bits)
+{
+    obisect b;
+    obisect_start(&b, 1000, -15, -1);
+    int n = 0;
+    size_t got = 0;
+    for (;;) {
+        float lambda = obisect_continue(&b);
+        size_t f1 = sqrtf(lambda * (-1.0f)) * 300;
+        got = (kind == 1) ? f1 : 1 + (f1 & (~(size_t)7));
+        n++;
+        if (obisect_submit(&b, got))
+            break;
+    }
+    *calls = n;
+    *bits = (long)got;
+}

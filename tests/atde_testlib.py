@@ -1,0 +1,174 @@
+"""Shared helpers for the test-suite: oracle bindings (CHECKERS ONLY) and deterministic signals."""
+from __future__ import annotations
+
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_SO = ROOT / "oracle" / "_ref" / "libatde_ref.so"
+PORT_SO = ROOT / "oracle" / "_build" / "libatde_oracle.so"
+EMU_SO = ROOT / "tests" / "cpuemu" / "_build" / "libatde_emu.so"
+P = ctypes.c_void_p
+
+
+def build_port():
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "port"])
+    return PORT_SO
+
+
+def build_emu():
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "tests" / "cpuemu")])
+    return EMU_SO
+
+
+_ref = None
+_port = None
+
+
+def ref_lib():
+    """The UNMODIFIED reference encoder compiled into oracle/_ref (prebuilt on the authoring box)."""
+    global _ref
+    if _ref is None:
+        if not REF_SO.exists():
+            if Path("/root/reference/src").exists():
+                subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "ref"])
+            else:
+                return None
+        _ref = ctypes.CDLL(str(REF_SO))
+        _ref.ref_encode.restype = ctypes.c_long
+        for f in ("ref_log10f", "ref_log2f"):
+            getattr(_ref, f).restype = ctypes.c_float
+            getattr(_ref, f).argtypes = [ctypes.c_float]
+    return _ref
+
+
+def port_lib():
+    """The plain-C restatement in oracle/*.c."""
+    global _port
+    if _port is None:
+        build_port()
+        _port = ctypes.CDLL(str(PORT_SO))
+        for f in ("og_logf", "og_log10f", "og_log2f"):
+            getattr(_port, f).restype = ctypes.c_float
+            getattr(_port, f).argtypes = [ctypes.c_float]
+    return _port
+
+
+def quantise(x):
+    """int16-quantise then /32768 -> what libsndfile hands the reference for a 16-bit WAV."""
+    return (np.rint(np.asarray(x, dtype=np.float64) * 32767).clip(-32768, 32767).astype(np.int16)
+            .astype(np.float32) / np.float32(32768))
+
+
+def ref_encode(codec, channels, pcm, total=None, bitrate_kbit=0, no_gain=0, no_tonal=0, bfu=0,
+               window_auto=1, window_mask=0):
+    """Runs src/main.cpp's PCM loop over `pcm` (interleaved).  Returns (payload bytes, sizes)."""
+    lib = ref_lib()
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    n = pcm.size // channels
+    total = n if total is None else total
+    out = np.zeros(max(1 << 20, pcm.size), dtype=np.uint8)
+    sizes = np.zeros(max(1 << 12, n // 256 + 64), dtype=np.int32)
+    nb = ctypes.c_long()
+    k = lib.ref_encode(codec, channels, pcm.ctypes.data_as(P), ctypes.c_long(n), ctypes.c_long(total),
+                       bitrate_kbit, no_gain, no_tonal, bfu, window_auto, window_mask,
+                       out.ctypes.data_as(P), ctypes.c_long(out.size), sizes.ctypes.data_as(P),
+                       ctypes.c_long(sizes.size), ctypes.byref(nb))
+    assert k >= 0, "reference harness failed"
+    return out[:nb.value].copy(), sizes[:k].copy()
+
+
+def pad_units(payload, sizes, unit_bytes):
+    """Container view of WriteFrame payloads: each resized to unit_bytes (src/aea.cpp:182, src/raw.cpp:41-43)."""
+    o = np.zeros((len(sizes), unit_bytes), np.uint8)
+    p = 0
+    for i, s in enumerate(sizes):
+        m = min(int(s), unit_bytes)
+        o[i, :m] = payload[p:p + m]
+        p += int(s)
+    return o
+
+
+def port_at1_encode(channels, pcm, window_auto=1, window_mask=0, bfu=0):
+    lib = port_lib()
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    F = pcm.size // channels // 512
+    out = np.zeros((F * channels, 212), np.uint8)
+    sizes = np.zeros(F * channels, np.int32)
+    lib.oat1_encode(channels, window_auto, window_mask, bfu, pcm.ctypes.data_as(P), ctypes.c_long(F),
+                    out.ctypes.data_as(P), sizes.ctypes.data_as(P))
+    return out, sizes
+
+
+def ref_at1_stages(channels, pcm, window_auto=1, window_mask=0):
+    lib = ref_lib()
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    F = pcm.size // channels // 512
+    bands = np.zeros((F, channels, 512), np.float32)
+    masks = np.zeros((F, channels), np.uint8)
+    specs = np.zeros((F, channels, 512), np.float32)
+    chloud = np.zeros((F, channels), np.float32)
+    loud = np.zeros(F, np.float32)
+    sfi = np.zeros((F, channels, 52), np.uint8)
+    lib.ref_at1_stages(channels, pcm.ctypes.data_as(P), ctypes.c_long(F), window_auto, window_mask,
+                       bands.ctypes.data_as(P), masks.ctypes.data_as(P), specs.ctypes.data_as(P),
+                       chloud.ctypes.data_as(P), loud.ctypes.data_as(P), sfi.ctypes.data_as(P))
+    return dict(bands=bands, masks=masks, specs=specs, chloud=chloud, loud=loud, sfi=sfi)
+
+
+# ---------------------------------------------------------------------------------------------
+# deterministic workload generator shared by tests and bench.py
+def synth_streams(n_streams, n_frames, frame_samples, channels, seed=0xA7AC):
+    """[S][F*frame_samples][C] float32: noise + per-stream sine, +20 dB bursts every 7th frame,
+    one silent stream; int16-quantised."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    n = n_frames * frame_samples
+    t = np.arange(n, dtype=np.float64)
+    out = np.empty((n_streams, n, channels), np.float32)
+    for s in range(n_streams):
+        f = 100.0 * (1 + s % 160)
+        x = 0.025 * rng.uniform(-1, 1, (n, channels))
+        for c in range(channels):
+            x[:, c] += 0.03 * np.sin(2 * np.pi * f * t / 44100 + c)
+        for fr in range(0, n_frames, 7):
+            x[fr * frame_samples: fr * frame_samples + 64] *= 10.0
+        if s % 61 == 60:
+            x[:] = 0
+        out[s] = quantise(x)
+    return out
+
+
+def engine_view(pcm, channels, step, total=None, buf_frames=4096):
+    """What the frame lambda actually receives when src/main.cpp:697-705 pumps `pcm` through
+    TPCMEngine(4096) + TWav's reader: whole 4096-sample-frame reads; a short last read zeroes only
+    (missing*channels) BYTES after the data (TPCMBuffer::Zero memsets len*NumChannels bytes,
+    src/pcmengin.h:91-94) and leaves the rest of the buffer stale.  Returns interleaved PCM of
+    every frame handed to the lambda, in order."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1, channels)
+    n = pcm.shape[0]
+    total = n if total is None else total
+    buf = np.zeros((buf_frames, channels), np.float32)
+    pos, processed, frames = 0, 0, []
+    while total > processed:
+        got = min(buf_frames, n - pos)
+        if got == 0:
+            break
+        buf[:got] = pcm[pos:pos + got]
+        pos += got
+        if got != buf_frames:
+            flat = buf.reshape(-1).view(np.uint8)
+            start = got * channels * 4
+            flat[start:start + (buf_frames - got) * channels] = 0
+        for i in range(0, buf_frames - step + 1, step):
+            frames.append(buf[i:i + step].copy())
+        processed += (buf_frames // step) * step
+    return np.concatenate(frames).reshape(-1)
+
+
+def config1_sine():
+    """BASELINE.json configs[0]: 1 s mono 44.1 kHz 1 kHz sine at 0.5 FS, int16-quantised."""
+    n = np.arange(44100)
+    return quantise(0.5 * np.sin(2 * np.pi * 1000 * n / 44100))

@@ -1,0 +1,41 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the reference itself (oracle/_ref, built from /root/reference
+by oracle/Makefile).  Run on the authoring box only; the fixtures are committed so the GPU box —
+which has no /root/reference — can still check against reference output.
+
+  python tests/golden/make_golden.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+import atde_testlib as tl  # noqa: E402
+
+
+def main():
+    assert tl.ref_lib() is not None, "needs oracle/_ref (make -C oracle ref)"
+    # config 1: ATRAC1, 1 s mono sine through the reference's own PCM pump
+    pcm = tl.config1_sine()
+    payload, sizes = tl.ref_encode(1, 1, pcm, total=44100)
+    units = tl.pad_units(payload, sizes, 212)
+    np.savez_compressed(HERE / "at1_config1_sine_mono.npz", units=units, sizes=sizes)
+    print("config1:", units.shape, "payload bytes", int(sizes.sum()))
+    # ATRAC1 stereo, noise + tone + bursts (exercises short windows, BFU trimming, boost)
+    S, F, C = 2, 24, 2
+    x = tl.synth_streams(S, F, 512, C, seed=0xA7AC)
+    units, sizes, masks = [], [], []
+    for s in range(S):
+        p, z = tl.ref_encode(1, C, x[s])
+        units.append(tl.pad_units(p, z, 212)[:F * C].reshape(F, C, 212))
+        sizes.append(z[:F * C].reshape(F, C))
+        masks.append(tl.ref_at1_stages(C, x[s])["masks"])
+    np.savez_compressed(HERE / "at1_stereo_bursts.npz", pcm=x, units=np.stack(units), sizes=np.stack(sizes),
+                        masks=np.stack(masks))
+    print("stereo bursts:", np.stack(units).shape, "short-window frames:", int((np.stack(masks) != 0).sum()))
+
+
+if __name__ == "__main__":
+    main()

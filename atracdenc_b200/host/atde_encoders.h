@@ -1,0 +1,66 @@
+// atde_encoders.h — host-side mirror of the reference's frame processors, backed by the C ABI of
+// libatde_b200.so (include/atde_b200.h).  Same class names, constructor signatures and lambda
+// semantics as
+//   NAtracDEnc::TAtrac1Encoder(TCompressedOutputPtr&&, NAtrac1::TAtrac1EncodeSettings&&)   src/atrac1denc.h:105
+// so `src/main.cpp`'s PrepareAtrac1Encoder / PCM loop (:292-340, :697-705) compile against it
+// unchanged.  Differences a caller can observe: WriteFrame calls are DEFERRED — frames are staged
+// and encoded on the GPU in batches; payload bytes, lengths and call order are identical, and
+// everything is flushed by Flush() or the destructor (the processor owns the container, and
+// main.cpp destroys the processor at scope exit).
+#pragma once
+#include "atde_boundary.h"
+#include "../../include/atde_b200.h"
+
+#include <stdexcept>
+
+namespace NAtracDEnc {
+
+#ifndef ATDE_USE_REFERENCE_HEADERS
+namespace NAtrac1 {
+// src/atrac/at1/atrac1.h:33-54
+class TAtrac1EncodeSettings {
+public:
+    enum class EWindowMode { EWM_NOTRANSIENT, EWM_AUTO };
+    TAtrac1EncodeSettings() {}
+    TAtrac1EncodeSettings(uint32_t bfuIdxConst, EWindowMode windowMode, uint32_t windowMask)
+        : BfuIdxConst(bfuIdxConst), WindowMode(windowMode), WindowMask(windowMask) {}
+    uint32_t GetBfuIdxConst() const { return BfuIdxConst; }
+    EWindowMode GetWindowMode() const { return WindowMode; }
+    uint32_t GetWindowMask() const { return WindowMask; }
+private:
+    const uint32_t BfuIdxConst = 0;
+    EWindowMode WindowMode = EWindowMode::EWM_AUTO;
+    const uint32_t WindowMask = 0;
+};
+} // namespace NAtrac1
+#endif
+
+// Common staging/flush machinery for all codecs.
+class TBatchedEncoderBase : public IProcessor {
+public:
+    ~TBatchedEncoderBase() override;
+    // Encode and deliver everything staged so far (idempotent).
+    void Flush();
+    // Frames staged before a batch is sent to the GPU (default 4096; tests use small values).
+    void SetBatchFrames(size_t n) { BatchFrames = n ? n : 1; }
+protected:
+    TBatchedEncoderBase(TCompressedOutputPtr&& out, const atde_settings& settings);
+    TPCMEngine::EProcessResult Push(const float* data);
+    TCompressedOutputPtr Out;
+    atde_encoder* Enc = nullptr;
+    int Channels = 0, FrameSamples = 0, Units = 0, UnitBytes = 0, LookAhead = 0;
+private:
+    std::vector<float> Stage;       // [BatchFrames][FrameSamples][Channels]
+    std::vector<uint8_t> Bytes;
+    std::vector<int32_t> Sizes;
+    size_t Staged = 0, BatchFrames = 4096;
+    uint64_t Calls = 0;
+};
+
+class TAtrac1Encoder : public TBatchedEncoderBase {
+public:
+    TAtrac1Encoder(TCompressedOutputPtr&& aea, NAtrac1::TAtrac1EncodeSettings&& settings);
+    TPCMEngine::TProcessLambda GetLambda() override;
+};
+
+} // namespace NAtracDEnc

@@ -1,0 +1,65 @@
+// tests/host_shim_driver.cpp — drives the C++ host shim exactly like src/main.cpp:697-716 drives
+// the reference's processors: TPCMEngine(4096) + memory reader + GetLambda() loop, capturing the
+// WriteFrame payloads to a file.  usage: driver <pcm.f32> <channels> <total_samples> <out.bin> <batch_frames>
+#include "../atracdenc_b200/host/atde_encoders.h"
+#include <cstdio>
+#include <cstdlib>
+
+using namespace NAtracDEnc;
+
+class TMemReader : public IPCMReader {
+    const std::vector<float>& Data; size_t Ch; mutable size_t Pos = 0;
+public:
+    TMemReader(const std::vector<float>& d, size_t ch) : Data(d), Ch(ch) {}
+    bool Read(TPCMBuffer& buf, const uint32_t size) const override {   // TWav::GetPCMReader, src/wav.cpp:46-61
+        size_t total = Data.size() / Ch, left = total - Pos, n = left < size ? left : size;
+        if (!n) return false;
+        memcpy(buf[0], &Data[Pos * Ch], n * Ch * sizeof(float));
+        Pos += n;
+        if (n != size) buf.Zero(n, size - n);
+        return true;
+    }
+};
+
+class TFileSink : public ICompressedOutput {
+    FILE* F; size_t Ch;
+public:
+    TFileSink(const char* path, size_t ch) : F(fopen(path, "wb")), Ch(ch) {}
+    ~TFileSink() override { if (F) fclose(F); }
+    void WriteFrame(std::vector<char> data) override {
+        int32_t n = (int32_t)data.size();
+        fwrite(&n, 4, 1, F);
+        fwrite(data.data(), 1, data.size(), F);
+    }
+    std::string GetName() const override { return "file"; }
+    size_t GetChannelNum() const override { return Ch; }
+};
+
+int main(int argc, char** argv)
+{
+    if (argc < 6) return 2;
+    const size_t ch = atoi(argv[2]);
+    const uint64_t total = strtoull(argv[3], nullptr, 10);
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) return 3;
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<float> pcm(sz / 4);
+    if (fread(pcm.data(), 4, pcm.size(), f) != pcm.size()) return 4;
+    fclose(f);
+    try {
+        TCompressedOutputPtr sink(new TFileSink(argv[4], ch));
+        std::unique_ptr<TAtrac1Encoder> proc(new TAtrac1Encoder(std::move(sink),
+            NAtrac1::TAtrac1EncodeSettings(0, NAtrac1::TAtrac1EncodeSettings::EWindowMode::EWM_AUTO, 0)));
+        proc->SetBatchFrames(atoi(argv[5]));
+        TPCMEngine eng(4096, ch, TPCMEngine::TReaderPtr(new TMemReader(pcm, ch)));
+        auto lambda = proc->GetLambda();
+        try {
+            while (total > eng.ApplyProcess(512, lambda)) {}
+        } catch (const TNoDataToRead&) {}
+        // processor destroyed here -> flushes the staged tail, as in main.cpp's scope exit
+    } catch (const std::exception& e) {
+        fprintf(stderr, "driver: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -117,3 +117,127 @@ float og_log2f(float x)
     y = fma(r2, y, p);
     return (float)y;
 }
+
+/* e_log.c (__log), fma build (__FP_FAST_FMA path: r = fma(z, invc, -1), no T2 table).
+ * Operation order read off libm-2.39.a:e_log-fma.o. */
+double og_log(double x)
+{
+    const unsigned long long* D = og239_log_data;   /* ln2hi, ln2lo, A[5] @2, B[11] @7, T[128]{invc,logc} @18 */
+    unsigned long long ix;
+    memcpy(&ix, &x, 8);
+    const unsigned top = (unsigned)(ix >> 48);
+    const unsigned long long LO = 0x3fee000000000000ULL, HI = 0x3ff1090000000000ULL;
+    if (ix - LO < HI - LO) {
+        if (ix == 0x3ff0000000000000ULL)
+            return 0;
+        const double* B = (const double*)(const void*)(D + 7);
+        double r = x - 1.0;
+        double r2 = r * r;
+        double r3 = r * r2;
+        double p2 = fma(r, B[2], B[1]);
+        double p3 = fma(r, B[5], B[4]);
+        double p5 = fma(r, B[8], B[7]);
+        p2 = fma(r2, B[3], p2);
+        p3 = fma(r2, B[6], p3);
+        double p1 = fma(r2, B[9], p5);
+        p1 = fma(r3, B[10], p1);
+        p1 = fma(p1, r3, p3);
+        p1 = fma(p1, r3, p2);
+        double t = fma(r, 0x1p27, r);
+        double rhi = fma(-0x1p27, r, t);
+        double rhi2 = rhi * rhi;
+        double rlo = r - rhi;
+        double hi = fma(rhi2, B[0], r);
+        double lo = fma(rhi2, B[0], r - hi);
+        lo = fma(B[0] * rlo, r + rhi, lo);
+        double y = fma(p1, r3, lo);
+        return hi + y;
+    }
+    if (top - 0x0010 >= 0x7ff0 - 0x0010) {
+        if (ix * 2 == 0)
+            return -INFINITY;
+        if (ix == 0x7ff0000000000000ULL)
+            return x;
+        if ((top & 0x8000) || (top & 0x7ff0) == 0x7ff0)
+            return (x - x) / (x - x);
+        double xs = x * 0x1p52;
+        memcpy(&ix, &xs, 8);
+        ix -= 52ULL << 52;
+    }
+    unsigned long long tmp = ix - 0x3fe6000000000000ULL;
+    int i = (int)((tmp >> 45) & 127);
+    int k = (int)((long long)tmp >> 52);
+    unsigned long long iz = ix - (tmp & 0xfffULL << 52);
+    double invc = u2d(D[18 + 2 * i]), logc = u2d(D[18 + 2 * i + 1]);
+    double ln2hi = u2d(D[0]), ln2lo = u2d(D[1]);
+    double A0 = u2d(D[2]), A1 = u2d(D[3]), A2 = u2d(D[4]), A3 = u2d(D[5]), A4 = u2d(D[6]);
+    double z = u2d(iz);
+    double kd = (double)k;
+    double w = fma(kd, ln2hi, logc);
+    double r = fma(z, invc, -1.0);
+    double q = fma(r, A2, A1);
+    double hi = r + w;
+    double r2 = r * r;
+    double lo = (w - hi) + r;
+    lo = fma(kd, ln2lo, lo);
+    double r3 = r * r2;
+    double q2 = fma(r, A4, A3);
+    lo = fma(r2, A0, lo);
+    q2 = fma(q2, r2, q);
+    double y = fma(r3, q2, lo);
+    return y + hi;
+}
+
+/* e_exp.c (__exp), fma build.  Only the ranges the encoder can reach are restated exactly
+ * (|x| < 512); overflow/underflow special cases return what libm returns for +-inf. */
+double og_exp(double x)
+{
+    const unsigned long long* D = og239_exp_data;   /* invln2N, shift, negln2hiN, negln2loN, C2..C5 @4, ..., tab @22 */
+    unsigned long long ix;
+    memcpy(&ix, &x, 8);
+    unsigned abstop = (unsigned)(ix >> 52) & 0x7ff;
+    if (abstop - 0x3c9 >= 0x3f) {
+        if (abstop - 0x3c9 >= 0x80000000u)
+            return 1.0 + x;
+        if (abstop >= 0x409) {
+            if (ix == 0xfff0000000000000ULL) return 0.0;
+            if (abstop >= 0x7ff) return 1.0 + x;
+            return (ix >> 63) ? 0.0 : INFINITY;
+        }
+        abstop = 0;
+    }
+    double invln2N = u2d(D[0]), shift = u2d(D[1]), nhi = u2d(D[2]), nlo = u2d(D[3]);
+    double C2 = u2d(D[4]), C3 = u2d(D[5]), C4 = u2d(D[6]), C5 = u2d(D[7]);
+    double kd = fma(x, invln2N, shift);
+    unsigned long long ki;
+    memcpy(&ki, &kd, 8);
+    kd -= shift;
+    double r = fma(kd, nhi, x);
+    r = fma(kd, nlo, r);
+    unsigned long long idx = 2 * (ki % 128);
+    unsigned long long topb = ki << 45;
+    double tail = u2d(D[22 + idx]);
+    unsigned long long sbits = D[22 + idx + 1] + topb;
+    double p = fma(r, C3, C2);
+    double t3 = r + tail;
+    double r2 = r * r;
+    double q = fma(r, C5, C4);
+    p = fma(p, r2, t3);
+    double r4 = r2 * r2;
+    double tmp = fma(r4, q, p);
+    if (abstop == 0) {
+        /* specialcase(): huge |x|, not reachable from the encoder; approximate via scaling */
+        double scale;
+        if ((ki & 0x80000000) == 0) {
+            sbits -= 1009ULL << 52;
+            scale = u2d(sbits);
+            return 0x1p1009 * (scale + scale * tmp);
+        }
+        sbits += 1022ULL << 52;
+        scale = u2d(sbits);
+        double y = scale + scale * tmp;
+        return 0x1p-1022 * y;
+    }
+    double scale = u2d(sbits);
+    return fma(scale, tmp, scale);
+}

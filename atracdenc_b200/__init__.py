@@ -21,10 +21,11 @@ CODEC_ATRAC3 = 3
 CODEC_ATRAC3PLUS = 4
 
 TAP_SPECS, TAP_MASKS, TAP_CHLOUD, TAP_LOUDNESS, TAP_SFI, TAP_WORDLEN = 1, 2, 3, 4, 5, 6
+TAP_BANDS, TAP_CURVES, TAP_GSCALE, TAP_ENERGY, TAP_TONAL, TAP_GAIN = 7, 8, 9, 10, 11, 12
 
 EXPORTS = [
     "atde_default_settings", "atde_create", "atde_destroy", "atde_frame_samples",
-    "atde_units_per_frame", "atde_unit_bytes", "atde_lookahead_frames", "atde_encode_batch",
+    "atde_units_per_frame", "atde_unit_bytes", "atde_lookahead_frames", "atde_output_frames", "atde_encode_batch",
     "atde_encode_batch_device", "atde_sync", "atde_reset", "atde_cuda_stream",
     "atde_launch_count", "atde_set_profiling", "atde_kernel_times", "atde_debug_tap", "atde_debug_math", "atde_last_error", "atde_version",
 ]
@@ -61,6 +62,8 @@ def load_library(path: os.PathLike | str | None = None) -> ctypes.CDLL:
               "atde_sync", "atde_reset"):
         getattr(lib, f).argtypes = [vp]
         getattr(lib, f).restype = ctypes.c_int
+    lib.atde_output_frames.argtypes = [vp, i64]
+    lib.atde_output_frames.restype = i64
     lib.atde_encode_batch.argtypes = [vp, vp, i32, i64, vp, vp]
     lib.atde_encode_batch_device.argtypes = [vp, vp, i32, i64, vp, vp]
     lib.atde_cuda_stream.argtypes = [vp]
@@ -118,18 +121,23 @@ class Encoder:
 
     def encode(self, pcm: np.ndarray, n_streams: int, want_sizes: bool = False):
         """pcm: float32 [S][F*frame_samples][C] (any shape with that memory order).
-        Returns uint8 [S][F][units][unit_bytes] (and int32 sizes [S][F][units])."""
+        Returns uint8 [S][Fo][units][unit_bytes] (and int32 sizes [S][Fo][units]), Fo = output_frames(F)."""
         pcm = np.ascontiguousarray(pcm, dtype=np.float32)
         per_stream = pcm.size // n_streams
         assert per_stream * n_streams == pcm.size
         F = per_stream // (self.frame_samples * self.channels)
         assert F * self.frame_samples * self.channels == per_stream, "whole frames only"
-        out = np.empty((n_streams, F, self.units_per_frame, self.unit_bytes), dtype=np.uint8)
-        sizes = np.empty((n_streams, F, self.units_per_frame), dtype=np.int32) if want_sizes else None
+        Fo = self.output_frames(F)
+        out = np.empty((n_streams, Fo, self.units_per_frame, self.unit_bytes), dtype=np.uint8)
+        sizes = np.empty((n_streams, Fo, self.units_per_frame), dtype=np.int32) if want_sizes else None
         self._check(self.lib.atde_encode_batch(
             self.h, pcm.ctypes.data, n_streams, F, out.ctypes.data,
             sizes.ctypes.data if want_sizes else None))
         return (out, sizes) if want_sizes else out
+
+    def output_frames(self, n_frames: int) -> int:
+        """Output frames per stream the next batch of n_frames will produce (ATRAC3's first batch: n-1)."""
+        return self._check(self.lib.atde_output_frames(self.h, n_frames))
 
     def encode_ptr(self, pcm_ptr: int, n_streams: int, n_frames: int, out_ptr: int, sizes_ptr: int = 0):
         """Host-pointer variant (pinned buffers owned by the caller)."""

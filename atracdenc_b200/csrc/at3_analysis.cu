@@ -1,0 +1,936 @@
+// at3_analysis.cu — ATRAC3 encode hot path on sm_100a, analysis half.
+//
+// Replaces, for thousands of frames at once (reference: dcherednik/atracdenc):
+//   K1 at3_qmf_kernel        lambda prologue /4.0 + Atrac3AnalysisFilterBank::Analysis (src/atrac3denc.cpp:700-713,
+//                            src/atrac/at3/atrac3_qmf.h:37-41, src/qmf/qmf.h:47-64), Matrixing (atrac3denc.cpp:665-677)
+//   K2 at3_gain_kernel       TSpectralUpsampler::Process (src/transient_spectral_upsampler.cpp:77-180),
+//                            kiss_fftr / kiss_fftri (src/lib/fft/kissfft_impl/tools/kiss_fftr.c:61-153),
+//                            AnalyzeGain (src/transient_detector.cpp:95-136), FindPlateau target (:190-262,298-312)
+//   K3 at3_gain_scan_kernel  the TCurveBuilderCtx recurrence (atrac3denc.cpp:319-346, transient_detector.cpp:322-325)
+//   K4 at3_curve_kernel      CalcCurve (transient_detector.cpp:276-482) + CreateSubbandInfo (atrac3denc.cpp:299-579)
+//   K5 at3_mdct_kernel       CalcGainEnergyScale (atrac3denc.cpp:154-224), TGainProcessor::Modulate (src/gain_processor.h:87-121),
+//                            TAtrac3MDCT::Mdct (atrac3denc.cpp:33-58), TMDCT<512> (src/lib/mdct/mdct.h:51-104),
+//                            per-channel loudness term (atrac3denc.cpp:811-820)
+//   K6 at3_loudness_kernel   TrackLoudness (atrac3denc.cpp:833-841, src/atrac/atrac_psy_common.h:46-54)
+//
+// Frames of a stream are processed in parallel.  The only true recurrences are the three scalars of
+// TCurveBuilderCtx per (channel, band) and the loudness scalar per stream; K3 / K6 scan them.  Every
+// other piece of carried encoder state (QMF histories, look-ahead buffer, the windowed+modulated MDCT
+// half, PrevOverlapGainScale) is a finite function of the neighbouring frames' band samples and gain
+// curves and is recomputed from them with the reference's operations in the reference's order.
+// All arithmetic is un-fused IEEE fp32 (bit-exact contract).
+#include "at3_kernels.cuh"
+#include "kissfft_dev.cuh"
+#include "glibc_math.cuh"
+
+namespace atde {
+namespace at3 {
+
+__constant__ float c_qmf3[48];        // QmfWindow, qmf.cpp:36-45
+
+void upload_qmf_window(const float w[48]) { cudaMemcpyToSymbol(c_qmf3, w, 48 * sizeof(float)); }
+
+// 48-tap half-band split of one output pair (qmf.h:54-63): sequential sums, taps in order.
+// src[2j + 1 - 2i + 47 - 47]: caller passes src so that tap i reads src[2j + 48 - 2i] (even phase)
+// and src[2j + 48 - 2i + 1]... identical convention to at1_kernels.cu:qmf_pair.
+ATDE_D void qmf_pair3(const float* src, int j, float& lower, float& upper)
+{
+    float lo = 0.0f, up = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 24; i++) {
+        const float2 v = *reinterpret_cast<const float2*>(src + 2 * j + 48 - 2 * i);
+        lo = fadd(lo, fmul(c_qmf3[2 * i], v.y));
+        up = fadd(up, fmul(c_qmf3[2 * i + 1], v.x));
+    }
+    upper = fsub(lo, up);
+    lower = fadd(lo, up);
+}
+
+// =====================================================================================
+// K1: PCM -> four 11 kHz bands per channel (two QMF stages), optional M/S matrixing
+// =====================================================================================
+// One block = kQT consecutive band samples u of one stream (both channels).
+//   band sample u <-> m = u - 128 (sample m of the extended sequence, 256 per frame)
+//   stage-1 output index k (512 per frame) feeds stage 2: band m reads s1[2m-47 .. 2m+1]
+//   input sample n (1024 per frame): s1[k] reads x[2k-47 .. 2k+1]
+// Tile-local arrays (m0 = first band sample of the tile):
+//   s1[j] = stage-1 sample k = 2*m0 - 48 + j,  j in [0, 2*kQT + 48)     (tap read: s1[2q + 48 - 2i (+1)], q = m - m0)
+//   x[t]  = input sample n = 4*m0 - 144 + t,   t in [0, 4*kQT + 144)    (tap read: x[2j + 48 - 2i (+1)])
+constexpr int kQT = 512;
+constexpr int kQS1 = 2 * kQT + 48;
+constexpr int kQX = 4 * kQT + 144;
+
+ATDE_D float virt_pcm(const Geometry& g, const Buffers& b, int s, int c, long long n, bool started)
+{
+    // sample n of the extended sequence of stream s (n < 0: the frame before ext frame 0)
+    if (n < 0) {
+        if (!started || n < -1024) return 0.0f;
+        return b.pcm_hist[(((size_t)s * 2 + 0) * 1024 + (size_t)(n + 1024)) * g.C + c];
+    }
+    if (started) {
+        if (n < 1024) return b.pcm_hist[(((size_t)s * 2 + 1) * 1024 + (size_t)n) * g.C + c];
+        n -= 1024;
+    }
+    if (n >= (long long)g.N * 1024) return 0.0f;
+    return b.pcm[((size_t)s * g.N * 1024 + (size_t)n) * g.C + c];
+}
+
+__global__ void __launch_bounds__(256) at3_qmf_kernel(Geometry g, Buffers b)
+{
+    __shared__ __align__(16) float x[kQX];
+    __shared__ __align__(16) float s1lo[kQS1];
+    __shared__ __align__(16) float s1hi[kQS1];
+    __shared__ __align__(16) float outb[2][4][kQT];
+
+    const int s = blockIdx.y;
+    const int u0 = blockIdx.x * kQT;
+    const int m0 = u0 - 128;
+    const bool started = b.started[s] != 0;
+
+    for (int c = 0; c < g.C; c++) {
+        ATDE_PAR_FOR(t, kQX) {
+            const long long n = 4LL * m0 - 144 + t;
+            x[t] = fmul(virt_pcm(g, b, s, c, n, started), 0.25f);       // data / 4.0 (atrac3denc.cpp:704)
+        }
+        __syncthreads();
+        ATDE_PAR_FOR(j, kQS1) {
+            float l, h;
+            qmf_pair3(x, j, l, h);
+            s1lo[j] = l;
+            s1hi[j] = h;
+        }
+        __syncthreads();
+        // Qmf2(Buf1) -> subs[0], subs[1];  Qmf3(Buf2) -> subs[3], subs[2]   (atrac3_qmf.h:37-41)
+        ATDE_PAR_FOR(q2, 2 * kQT) {
+            const int which = q2 >= kQT, q = q2 - which * kQT;
+            float l, h;
+            qmf_pair3(which ? s1hi : s1lo, q, l, h);
+            if (!which) { outb[c][0][q] = l; outb[c][1][q] = h; }
+            else        { outb[c][3][q] = l; outb[c][2][q] = h; }
+        }
+        __syncthreads();
+    }
+    const int nvalid = min(kQT, g.BL - u0);
+    ATDE_PAR_FOR(w, 4 * kQT) {
+        const int band = w / kQT, q = w - band * kQT;
+        if (q < nvalid) {
+            if (g.js) {
+                const float l = outb[0][band][q], r = outb[1][band][q];
+                b.bands[(((size_t)s * 2 + 0) * 4 + band) * g.BL + u0 + q] = fmul(fadd(l, r), 0.5f);
+                b.bands[(((size_t)s * 2 + 1) * 4 + band) * g.BL + u0 + q] = fmul(fsub(l, r), 0.5f);
+            } else {
+                for (int c = 0; c < g.C; c++)
+                    b.bands[(((size_t)s * g.C + c) * 4 + band) * g.BL + u0 + q] = outb[c][band][q];
+            }
+        }
+    }
+}
+
+void launch_qmf(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    dim3 grid((g.BL + kQT - 1) / kQT, g.S);
+    ATDE_LAUNCH(at3_qmf_kernel, grid, 256, 0, st, g, b);
+}
+
+// =====================================================================================
+// K2: spectral upsampler + sub-frame envelope of one (stream, channel, band, frame)
+// =====================================================================================
+// RelationToIdx (transient_detector.cpp:139-147 and atrac3denc.h:44-52: same function of x)
+ATDE_D int relation_to_idx(float x)
+{
+    if (x <= 0.5f) {
+        x = __fdiv_rn(1.0f, fmaxf(x, 0.00048828125f));
+        const unsigned v = (unsigned)__float2int_rz(x);
+        return 4 + (v ? 31 - __clz((int)v) : 0);
+    }
+    x = fminf(x, 16.0f);
+    const unsigned v = (unsigned)__float2int_rz(x);
+    return 4 - (v ? 31 - __clz((int)v) : 0);
+}
+
+ATDE_D float median3(float a, float b, float c)
+{
+    return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
+}
+
+// MedianFilter<1> (transient_detector.cpp:149-163): edges use a 2-element window and take w[1] = max.
+ATDE_D void median_filter1(const float* in, float* out, int n)
+{
+    for (int i = 0; i < n; i++) {
+        if (i == 0) out[i] = fmaxf(in[0], in[1]);
+        else if (i == n - 1) out[i] = fmaxf(in[n - 2], in[n - 1]);
+        else out[i] = median3(in[i - 1], in[i], in[i + 1]);
+    }
+}
+
+// FindPlateau (transient_detector.cpp:175-262) + target selection (:286-299); in[] has 32 entries.
+ATDE_D float plateau_target(const float* in)
+{
+    const int n = 32, minc = 3;
+    float max_raw = 0.0f;
+    for (int i = 0; i < n; i++) max_raw = fmaxf(max_raw, in[i]);
+    float filt[32];
+    median_filter1(in, filt, n);
+    float best = 0.0f;
+    int best_end = -1;
+    for (int j = 0; j + minc <= n; j++) {
+        float mv = filt[j];
+        for (int k = 1; k < minc; k++) mv = fminf(mv, filt[j + k]);
+        if (mv > best) { best = mv; best_end = j + minc - 1; }
+    }
+    float level = best;
+    bool release = false;
+    if (best < 1e-6f) {
+        level = 0.0f;
+    } else {
+        while (best_end + 1 < n && filt[best_end + 1] >= best) ++best_end;
+        if (best_end < n - 1) {
+            if (in[n - 1] < fmul(best, 0.1f)) {
+                release = true;
+            } else {
+                bool any_high = false;
+                for (int i = best_end + 1; i < n; i++)
+                    if (in[i] >= fmul(best, 0.7f)) { any_high = true; break; }
+                release = !any_high && (in[n - 1] < fmul(best, 0.5f));
+            }
+        }
+    }
+    const bool use_plateau = level > 1e-6f && !release && level >= fmul(max_raw, 0.4f);
+    return use_plateau ? level : in[n - 1];
+}
+
+constexpr int kGainThreads = 256;
+
+__global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buffers b)
+{
+    __shared__ __align__(16) cpx big[2048];          // inverse FFT buffer (also the real output, 4096 floats)
+    __shared__ __align__(16) cpx fwd[256];
+    __shared__ __align__(16) cpx freq[257];
+    __shared__ float micro[256];
+    __shared__ float sgain[96];
+
+    const DevTables* __restrict__ T = b.tab;
+    const int f = blockIdx.x;
+    const int band = blockIdx.y % kGainBands, c = blockIdx.y / kGainBands;
+    const int s = blockIdx.z;
+    const float* __restrict__ in = b.bands + (((size_t)s * g.C + c) * 4 + band) * g.BL + 256 * (size_t)f;
+    const int tid = threadIdx.x;
+
+    // 1. Planck window, packed as the complex input of the half-size FFT, in digit-reversed order
+    ATDE_PAR_FOR(o, 256) {
+        const int j = T->perm256[o];
+        cpx z;
+        z.r = fmul(in[2 * j], T->planck[2 * j]);
+        z.i = fmul(in[2 * j + 1], T->planck[2 * j + 1]);
+        fwd[o] = z;
+    }
+    ATDE_PAR_FOR(i, 2048) { big[i].r = 0.0f; big[i].i = 0.0f; }
+    __syncthreads();
+    // 2. forward complex FFT-256 = 4x4x4x4
+    for (int st = 0; st < 4; st++) {
+        const int m = 1 << (2 * st);
+        if (tid < 64) kf_stage4<false>(fwd, T->tw256, tid, m, 64 / m);
+        __syncthreads();
+    }
+    // kiss_fftr post-processing (kiss_fftr.c:84-115)
+    ATDE_PAR_FOR(k, 129) {
+        if (k == 0) {
+            const float tr = fwd[0].r, ti = fwd[0].i;
+            freq[0].r = fadd(tr, ti);   freq[0].i = 0.0f;
+            freq[256].r = fsub(tr, ti); freq[256].i = 0.0f;
+        } else {
+            const cpx fpk = fwd[k];
+            cpx fpnk; fpnk.r = fwd[256 - k].r; fpnk.i = -fwd[256 - k].i;
+            cpx f1k, f2k;
+            f1k.r = fadd(fpk.r, fpnk.r); f1k.i = fadd(fpk.i, fpnk.i);
+            f2k.r = fsub(fpk.r, fpnk.r); f2k.i = fsub(fpk.i, fpnk.i);
+            const cpx tw = cmul(f2k, T->super512[k - 1]);
+            cpx a, bb;
+            a.r = fmul(fadd(f1k.r, tw.r), 0.5f);  a.i = fmul(fadd(f1k.i, tw.i), 0.5f);
+            bb.r = fmul(fsub(f1k.r, tw.r), 0.5f); bb.i = fmul(fsub(tw.i, f1k.i), 0.5f);
+            freq[k] = a;                       // k == 128 writes the same element twice: the second
+            freq[256 - k] = bb;                // store (freqdata[ncfft-k]) wins, as in the reference
+        }
+    }
+    __syncthreads();
+    // 2a. high-frequency energy ratio: sequential double sums (upsampler.cpp:99-118) on one thread,
+    //     while the others build the inverse FFT input.
+    const int lcb = T->low_cut_bin;
+    if (tid == kGainThreads - 1) {
+        double tot = 0.0, hi = 0.0;
+        for (int k = 0; k <= 256; k++) {
+            const double r = (double)freq[k].r, i = (double)freq[k].i;
+            const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
+            tot = __dadd_rn(tot, e);
+            float H = 0.0f;
+            if (k >= lcb + 2) H = 1.0f;
+            else if (k >= lcb) H = T->hpf_h[k - lcb];
+            hi = __dadd_rn(hi, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
+        }
+        sgain[0] = (tot > 0.0) ? __double2float_rn(__ddiv_rn(hi, tot)) : 0.0f;   // parked; moved below
+    }
+    // 3/4a. inverse real FFT input: Y[k] = 8*X[k]*H[k]; kiss_fftri pre-processing (kiss_fftr.c:131-151)
+    //       with Y[2048-k] == 0 for every k that carries data.
+    ATDE_PAR_FOR(k, 257) {
+        if (k < lcb) continue;
+        cpx fk;
+        if (k == 256) {
+            if (lcb + 2 > 256) continue;
+            fk.r = fmul(fmul(freq[256].r, 8.0f), 0.5f);
+            fk.i = 0.0f;
+        } else if (k >= lcb + 2) {
+            fk.r = fmul(freq[k].r, 8.0f);
+            fk.i = fmul(freq[k].i, 8.0f);
+        } else {
+            const float w = T->hpf_h[k - lcb];
+            fk.r = fmul(fmul(freq[k].r, 8.0f), w);
+            fk.i = fmul(fmul(freq[k].i, 8.0f), w);
+        }
+        if (k == 0) {
+            // tmpbuf[0] = (Y[0].r + Y[2048].r, Y[0].r - Y[2048].r)
+            cpx z; z.r = fadd(fk.r, 0.0f); z.i = fsub(fk.r, 0.0f);
+            big[T->iperm2048[0]] = z;
+        } else {
+            // fnkc = conj(Y[2048-k]) = (0, -0)
+            cpx fek, tmp;
+            fek.r = fadd(fk.r, 0.0f);  fek.i = fadd(fk.i, -0.0f);
+            tmp.r = fsub(fk.r, 0.0f);  tmp.i = fsub(fk.i, -0.0f);
+            const cpx fok = cmul(tmp, T->super4096[k - 1]);
+            cpx lo, hi2;
+            lo.r = fadd(fek.r, fok.r);  lo.i = fadd(fek.i, fok.i);
+            hi2.r = fsub(fek.r, fok.r); hi2.i = fmul(fsub(fek.i, fok.i), -1.0f);
+            big[T->iperm2048[k]] = lo;
+            big[T->iperm2048[2048 - k]] = hi2;
+        }
+    }
+    __syncthreads();
+    const float hfr = sgain[0];
+    // 4b. inverse complex FFT-2048 = 4x4x4x4x4x2: radix-2 innermost, then m = 2, 8, 32, 128, 512
+    ATDE_PAR_FOR(v, 1024) kf_stage2(big, T->tw2048, v, 1, 1024);
+    __syncthreads();
+    for (int st = 0; st < 5; st++) {
+        const int m = 2 << (2 * st);
+        ATDE_PAR_FOR(v, 512) kf_stage4<true>(big, T->tw2048, v, m, 512 / m);
+        __syncthreads();
+    }
+    // 5. normalise the analysis region [1024, 3072) (norm = 1/4096) and take the envelopes
+    float* sig = reinterpret_cast<float*>(big);
+    ATDE_PAR_FOR(i, 2048) sig[1024 + i] = fmul(sig[1024 + i], 1.0f / 4096.0f);
+    __syncthreads();
+    // AnalyzeGain(signal + 1024, 2048, 32, rms): 64-sample RMS, plus 8 micro-chunk RMS values each
+    ATDE_PAR_FOR(q, 256) {
+        const float* p = sig + 1024 + 8 * q;
+        float a = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a = fadd(a, fmul(p[i], p[i]));
+        micro[q] = __fsqrt_rn(__fdiv_rn(a, 8.0f));
+    }
+    if (tid >= 64 && tid < 96) {
+        const int sf = tid - 64;
+        const float* p = sig + 1024 + 64 * sf;
+        float a = 0.0f;
+        for (int i = 0; i < 64; i++) a = fadd(a, fmul(p[i], p[i]));
+        sgain[sf] = __fsqrt_rn(__fdiv_rn(a, 64.0f));
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) m[i] = micro[8 * tid + i];
+        // ascending sort of 8 plain floats (any correct sort gives std::sort's result)
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+#pragma unroll
+            for (int j = 7; j >= 1; j--) {
+                if (j >= i) {
+                    const float lo2 = fminf(m[j - 1], m[j]), hi3 = fmaxf(m[j - 1], m[j]);
+                    m[j - 1] = lo2; m[j] = hi3;
+                }
+            }
+        }
+        sgain[32 + tid] = m[2];
+        sgain[64 + tid] = m[6];
+    }
+    __syncthreads();
+    const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
+    ATDE_PAR_FOR(i, 96) b.gain[item * 96 + i] = sgain[i];
+    if (tid == 0) {
+        float cur = 0.0f;
+        for (int i = 0; i < 32; i++) cur = fadd(cur, sgain[i]);
+        cur = __fdiv_rn(cur, 32.0f);
+        float4 st4;
+        st4.x = hfr;
+        st4.y = cur;
+        st4.z = plateau_target(sgain);
+        st4.w = sgain[31];
+        reinterpret_cast<float4*>(b.gstat)[item] = st4;
+    }
+}
+
+void launch_gain_analysis(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    dim3 grid(g.n_out, g.C * kGainBands, g.S);
+    ATDE_LAUNCH(at3_gain_kernel, grid, kGainThreads, 0, st, g, b);
+}
+
+// =====================================================================================
+// K3: TCurveBuilderCtx recurrence, one thread per (stream, channel, band)
+// =====================================================================================
+__global__ void at3_gain_scan_kernel(Geometry g, Buffers b)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // (s*C + c)*3 + band
+    if (idx >= g.S * g.C * kGainBands) return;
+    float4* ctxp = reinterpret_cast<float4*>(b.ctx) + idx;
+    float4 ctx = *ctxp;                                              // x LastLevel, y LastHpfEnergy, z LastTarget
+    const float4* st = reinterpret_cast<const float4*>(b.gstat) + (size_t)idx * g.n_out;
+    float4* pv = reinterpret_cast<float4*>(b.gprev) + (size_t)idx * g.n_out;
+    for (int f = 0; f < g.n_out; f++) {
+        const float4 v = st[f];
+        float4 o;
+        o.x = ctx.y; o.y = ctx.x; o.z = ctx.z; o.w = 0.0f;
+        if (v.x < 0.05f) {                                           // kHighFreqThreshold: LastLevel = 0, continue
+            ctx.x = 0.0f;
+        } else {
+            ctx.y = v.y;
+            ctx.x = v.w;
+            ctx.z = v.z;
+        }
+        pv[f] = o;
+    }
+    *ctxp = ctx;
+}
+
+void launch_gain_scan(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    const int n = g.S * g.C * kGainBands;
+    ATDE_LAUNCH(at3_gain_scan_kernel, (n + 63) / 64, 64, 0, st, g, b);
+}
+
+// =====================================================================================
+// K4: gain curve of one (stream, channel, band, frame), one thread each
+// =====================================================================================
+struct Pts {
+    int n;
+    int level[8];
+    int loc[8];
+};
+
+// BuildSubframeDivisors (atrac3denc.cpp:228-255)
+ATDE_D void subframe_divisors(const DevTables* T, const Pts& p, float* out_div)
+{
+    float sd[256];
+    for (int i = 0; i < 256; i++) sd[i] = 1.0f;
+    int pos = 0;
+    for (int i = 0; i < p.n; i++) {
+        const int last = p.loc[i] << 3;
+        float level = T->gain_level[p.level[i]];
+        const int inc = ((i + 1) < p.n ? p.level[i + 1] : 4) - p.level[i] + 15;
+        const float ginc = T->gain_interp[inc];
+        for (; pos < last && pos < 256; ++pos) sd[pos] = level;
+        for (; pos < last + 8 && pos < 256; ++pos) { sd[pos] = level; level = fmul(level, ginc); }
+    }
+    for (int sf = 0; sf < 32; sf++) {
+        float sum = 0.0f;
+        for (int k = 0; k < 8; k++) sum = fadd(sum, sd[sf * 8 + k]);
+        out_div[sf] = __fdiv_rn(sum, 8.0f);
+    }
+}
+
+// CalcCurveEarlyMismatchScore (atrac3denc.cpp:259-297)
+ATDE_D float mismatch_score(const DevTables* T, const float* gain, float target, const Pts& p)
+{
+    if (target <= 1e-9f) return 0.0f;
+    float div[32];
+    subframe_divisors(T, p, div);
+    int max_loc = 0;
+    for (int i = 0; i < p.n; i++) max_loc = max(max_loc, p.loc[i]);
+    const int eval = min(32, max(3, max_loc + 3));
+    const float eps = 1e-9f;
+    float fit = 0.0f;
+    for (int sf = 0; sf < eval; sf++) {
+        const float mod = __fdiv_rn(gain[sf], fmaxf(div[sf], eps));
+        const float e = g_log2f(__fdiv_rn(fmaxf(mod, eps), fmaxf(target, eps)));
+        fit = fadd(fit, fmul(e, e));
+    }
+    fit = __fdiv_rn(fit, (float)eval);
+    float leak = 0.0f, wsum = 0.0f;
+    for (int sf = 0; sf + 1 < eval; sf++) {
+        const float a = g_log2f(fmaxf(div[sf], eps));
+        const float bb = g_log2f(fmaxf(div[sf + 1], eps));
+        const float d = fsub(bb, a);
+        const float w = fmul(0.5f, fadd(gain[sf], gain[sf + 1]));
+        leak = fadd(leak, fmul(fmul(d, d), w));
+        wsum = fadd(wsum, w);
+    }
+    if (wsum > eps) leak = __fdiv_rn(leak, wsum);
+    return fadd(fit, fmul(0.25f, leak));
+}
+
+// CalcCurve (transient_detector.cpp:276-482) after the ctx update; returns the points in p
+ATDE_D void calc_curve(const float* in, const float* low, const float* high, float target,
+                       float saved_last_level, float saved_last_target, float min_score, Pts& p)
+{
+    p.n = 0;
+    const int n = 32;
+    if (target < 1e-6f) return;
+    if (saved_last_level < 1e-6f) return;
+    float filt[32];
+    median_filter1(in, filt, n);
+    float max_gain = 0.0f;
+    for (int i = 0; i < n; i++) max_gain = fmaxf(max_gain, in[i]);
+    const float intra = __fdiv_rn(max_gain, fmaxf(target, 1e-9f));
+    float inter = 1.0f;
+    if (saved_last_target > 1e-6f) {
+        const float hi = fmaxf(saved_last_target, target), lo = fminf(saved_last_target, target);
+        inter = __fdiv_rn(hi, fmaxf(lo, 1e-9f));
+    }
+    const bool sticky = intra <= 7.0f && inter <= 10.0f;
+    int lev[32];
+    for (int i = 0; i < n; i++) {
+        int level = relation_to_idx(__fdiv_rn(filt[i], target));
+        if (i > 0 && sticky) {
+            float rlo = __fdiv_rn(low[i], target), rhi = __fdiv_rn(high[i], target);
+            if (rlo > rhi) { const float t = rlo; rlo = rhi; rhi = t; }
+            const int ilo = relation_to_idx(rlo), ihi = relation_to_idx(rhi);
+            const int mn = min(ilo, ihi), mx = max(ilo, ihi);
+            const int prev = lev[i - 1];
+            if (mx - mn <= 1 && abs(level - prev) == 1 && prev >= mn && prev <= mx) level = prev;
+        }
+        lev[i] = level;
+    }
+    int target_sf = 0;
+    for (int sf = n - 2; sf >= 0; --sf)
+        if (lev[sf] != 4) { target_sf = sf + 1; break; }
+    if (target_sf == 0) return;
+    // transitions, scanned leftward from target_sf (stored right-to-left, reversed below)
+    int t_loc[32], t_lev[32], t_delta[32], nt = 0;
+    {
+        int prev = 4;
+        for (int sf = target_sf - 1; sf >= 0; --sf) {
+            const int l = lev[sf];
+            if (l != prev) {
+                const int loc = sf + 1;
+                const int delta = abs(l - prev);
+                bool keep = (loc == target_sf) || (delta >= 2);
+                if (!keep) {
+                    // BoundaryTransientScore(filtered, loc, 3) (transient_detector.cpp:251-274)
+                    float lm = 0.0f, rm = 0.0f;
+                    for (int i = max(0, loc - 3); i < loc; i++) lm = fmaxf(lm, filt[i]);
+                    for (int i = loc; i < min(n, loc + 3); i++) rm = fmaxf(rm, filt[i]);
+                    const float eps = 1e-9f;
+                    const float attack = __fdiv_rn(fadd(rm, eps), fadd(lm, eps));
+                    const float release = __fdiv_rn(fadd(lm, eps), fadd(rm, eps));
+                    keep = fmaxf(attack, release) >= min_score;
+                }
+                if (keep) { t_loc[nt] = loc; t_lev[nt] = l; t_delta[nt] = delta; nt++; prev = l; }
+            }
+        }
+    }
+    if (nt == 0) return;
+    // after std::reverse the transitions are in ascending Loc order: index nt-1-k
+    if (nt > 6) {
+        // keep the 6 largest by (Delta desc, Loc desc) — a strict total order since Locs are unique —
+        // then emit in ascending Loc.
+        bool keepf[32];
+        for (int i = 0; i < nt; i++) keepf[i] = false;
+        for (int r = 0; r < 6; r++) {
+            int best = -1;
+            for (int i = 0; i < nt; i++) {
+                if (keepf[i]) continue;
+                if (best < 0 || t_delta[i] > t_delta[best] || (t_delta[i] == t_delta[best] && t_loc[i] > t_loc[best]))
+                    best = i;
+            }
+            keepf[best] = true;
+        }
+        for (int i = nt - 1; i >= 0; --i)
+            if (keepf[i]) { p.level[p.n] = t_lev[i]; p.loc[p.n] = t_loc[i]; p.n++; }
+    } else {
+        for (int i = nt - 1; i >= 0; --i) { p.level[p.n] = t_lev[i]; p.loc[p.n] = t_loc[i]; p.n++; }
+    }
+}
+
+__global__ void __launch_bounds__(128) at3_curve_kernel(Geometry g, Buffers b)
+{
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // ((s*C+c)*3+band)*n_out + f
+    const long long total = (long long)g.S * g.C * kGainBands * g.n_out;
+    if (item >= total) return;
+    const DevTables* __restrict__ T = b.tab;
+    const int f = (int)(item % g.n_out);
+    const long long scb = item / g.n_out;
+    const int band = (int)(scb % kGainBands);
+    const long long sc = scb / kGainBands;
+    Curve out;
+    out.n = 0; out.pad = 0;
+    for (int i = 0; i < 7; i++) { out.level[i] = 0; out.loc[i] = 0; }
+    Curve* dst = b.curves + ((size_t)sc * 4 + band) * g.n_out + f;
+
+    const float4 st = reinterpret_cast<const float4*>(b.gstat)[item];
+    const float4 pv = reinterpret_cast<const float4*>(b.gprev)[item];
+    const float hfr = st.x, cur_hpf = st.y, target = st.z;
+    const float prev_hpf = pv.x, saved_ll = pv.y, saved_lt = pv.z;
+    if (hfr < 0.05f) { *dst = out; return; }
+
+    float gain[32], low[32], high[32];
+    const float* gp = b.gain + (size_t)item * 96;
+    for (int i = 0; i < 32; i++) { gain[i] = gp[i]; low[i] = gp[32 + i]; high[i] = gp[64 + i]; }
+
+    const float ratio = (cur_hpf > 1e-9f && prev_hpf > 1e-9f) ? __fdiv_rn(prev_hpf, cur_hpf) : 1.0f;
+    const float min_score = fmul(1.9f, fminf(1.5f, fmaxf(1.0f, ratio)));
+    const float prev_target = saved_lt;
+    Pts p;
+    calc_curve(gain, low, high, target, saved_ll, saved_lt, min_score, p);
+    if (p.n == 0) { *dst = out; return; }                     // "skip: no_curve" (atrac3denc.cpp:395-400)
+
+    float max_gain = 0.0f;
+    for (int i = 0; i < 32; i++) max_gain = fmaxf(max_gain, gain[i]);
+    if (max_gain < 1e-4f) p.n = 0;
+    if (hfr < 0.3f) p.n = 0;
+
+    // explicit point 0 (atrac3denc.cpp:457-554)
+    const Pts before = p;
+    bool changed = false;
+    float next_mod = 0.0f;
+    bool valid = false;
+    if (p.n > 0 && p.loc[0] > 0) {
+        const int nb = p.loc[0];
+        float sum = 0.0f;
+        for (int sf = 0; sf < nb; sf++) sum = fadd(sum, gain[sf]);
+        next_mod = __fdiv_rn(__fdiv_rn(sum, (float)nb), T->gain_level[p.level[0]]);
+        valid = true;
+    } else if (p.n == 0) {
+        float sum = 0.0f;
+        for (int i = 0; i < 32; i++) sum = fadd(sum, gain[i]);
+        next_mod = __fdiv_rn(sum, 32.0f);
+        valid = true;
+    }
+    const bool have0 = valid && prev_target > 1e-6f && next_mod > 1e-6f;
+    if (have0) {
+        const int l0 = relation_to_idx(__fdiv_rn(prev_target, next_mod));
+        int at = -1;
+        for (int i = 0; i < p.n; i++) if (p.loc[i] == 0) { at = i; break; }
+        if (at >= 0) {
+            if (p.level[at] != l0) { p.level[at] = l0; changed = true; }
+        } else if (l0 != 4 || p.n > 0) {
+            for (int i = p.n; i > 0; --i) { p.level[i] = p.level[i - 1]; p.loc[i] = p.loc[i - 1]; }
+            p.level[0] = l0; p.loc[0] = 0; p.n++;
+            changed = true;
+        }
+    }
+    if (changed) {
+        const float score_before = mismatch_score(T, gain, target, before);
+        const float score_after = mismatch_score(T, gain, target, p);
+        bool keep_by_boundary = false;
+        if (have0) {
+            const float desired = fminf(fmaxf(__fdiv_rn(prev_target, next_mod), T->gain_level[15]), T->gain_level[0]);
+            const float sb = T->gain_level[before.n ? before.level[0] : 4];
+            const float sa = T->gain_level[p.n ? p.level[0] : 4];
+            const float eps = 1e-9f;
+            const float eb = fabsf(g_log2f(__fdiv_rn(fmaxf(sb, eps), fmaxf(desired, eps))));
+            const float ea = fabsf(g_log2f(__fdiv_rn(fmaxf(sa, eps), fmaxf(desired, eps))));
+            keep_by_boundary = fadd(ea, 0.20f) < eb;
+        }
+        if (!keep_by_boundary && score_after > fmul(score_before, fadd(1.0f, 0.02f)))
+            p = before;
+    }
+    if (p.n >= 2 && p.loc[0] == 0 && p.level[0] == p.level[1]) {
+        for (int i = 0; i + 1 < p.n; i++) { p.level[i] = p.level[i + 1]; p.loc[i] = p.loc[i + 1]; }
+        p.n--;
+    }
+    out.n = (unsigned char)p.n;
+    for (int i = 0; i < p.n && i < 7; i++) { out.level[i] = (unsigned char)p.level[i]; out.loc[i] = (unsigned char)p.loc[i]; }
+    *dst = out;
+}
+
+void launch_gain_curve(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    const long long total = (long long)g.S * g.C * kGainBands * g.n_out;
+    ATDE_LAUNCH(at3_curve_kernel, (unsigned)((total + 127) / 128), 128, 0, st, g, b);
+}
+
+// =====================================================================================
+// K5: gain modulation + window + MDCT-512 x4 + energy scales + loudness term, one block per
+//     (stream, frame, channel)
+// =====================================================================================
+// Divisor applied by TGainProcessor::Modulate / BuildSampleDivisors to sample `pos` of the frame the
+// curve belongs to (gain_processor.h:87-121, atrac3denc.cpp:154-173); 1.0 beyond the last ramp.
+ATDE_D float curve_level(const DevTables* T, const Curve& cv, int pos)
+{
+    for (int i = 0; i < cv.n; i++) {
+        const int last = (int)cv.loc[i] << 3;
+        if (pos < last + 8) {
+            float level = T->gain_level[cv.level[i]];
+            if (pos >= last) {
+                const int inc = ((i + 1) < cv.n ? (int)cv.level[i + 1] : 4) - (int)cv.level[i] + 15;
+                const float ginc = T->gain_interp[inc];
+                for (int r = last; r < pos; r++) level = fmul(level, ginc);
+            }
+            return level;
+        }
+    }
+    return 1.0f;
+}
+
+// SafeEnergyScale (atrac3denc.cpp:143-152)
+ATDE_D float safe_energy_scale(float orig, float mod)
+{
+    const float eps = 1.0e-20f;
+    const float inf = __int_as_float(0x7f800000);
+    if (orig <= eps || mod <= eps || !(fabsf(orig) < inf) || !(fabsf(mod) < inf)) return 1.0f;
+    const float sc = __fdiv_rn(orig, mod);
+    return (fabsf(sc) < inf && sc > 0.0f) ? sc : 1.0f;
+}
+
+__global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
+{
+    __shared__ __align__(16) float cur[4][256];        // band samples of this frame, raw
+    __shared__ __align__(16) float curm[4][256];       // ... divided by the gain curve
+    __shared__ __align__(16) float prevw[4][256];      // stored half: window * modulated previous frame
+    __shared__ __align__(16) float pnext[4][2][256];   // previous frame: cur*win[i], (cur/div)*win[i] (for its NextOverlapScale)
+    __shared__ __align__(16) cpx fft[4][128];
+    __shared__ __align__(16) float sp[1024];
+    __shared__ float esum[4][8];
+    __shared__ float sscale[4][4];
+    __shared__ Curve scv[4][2];                        // [band][0] previous frame, [1] this frame
+
+    const DevTables* __restrict__ T = b.tab;
+    const int f = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
+    const int tid = threadIdx.x;
+    const size_t sc = (size_t)s * g.C + c;
+
+    if (tid < 8) {
+        const int band = tid >> 1, which = tid & 1;
+        Curve cv;
+        cv.n = 0;
+        const int ff = f - 1 + which;
+        if (!g.no_gain && band < kGainBands && ff >= 0)
+            cv = b.curves[(sc * 4 + band) * g.n_out + ff];
+        scv[band][which] = cv;
+    }
+    __syncthreads();
+    // ---- per-sample products; every sample is independent ----
+    ATDE_PAR_FOR(w, 1024) {
+        const int band = w >> 8, i = w & 255;
+        const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
+        const float x = bp[i];
+        const Curve& cc = scv[band][1];
+        const float xm = cc.n ? __fdiv_rn(x, curve_level(T, cc, i)) : x;
+        cur[band][i] = x;
+        curm[band][i] = xm;
+        if (f == 0) {
+            prevw[band][i] = b.prevhalf[(sc * 4 + band) * 256 + i];
+        } else {
+            const float y = bp[i - 256];
+            const Curve& pc = scv[band][0];
+            const float ym = pc.n ? __fdiv_rn(y, curve_level(T, pc, i)) : y;
+            const float wi = T->encode_window[i];
+            prevw[band][i] = fmul(wi, ym);
+            pnext[band][0][i] = fmul(y, wi);
+            pnext[band][1][i] = fmul(ym, wi);
+        }
+    }
+    __syncthreads();
+    // ---- energy chains of CalcGainEnergyScale: sequential sums, one thread per chain ----
+    //  chain 0 prevStored, 1 curOriginal, 2 curModulated, 3 nextOriginal, 4 nextModulated,
+    //  5/6 nextOriginal/nextModulated of the previous frame
+    if (tid < 28) {
+        const int band = tid / 7, ch = tid % 7;
+        const bool cur_empty = scv[band][1].n == 0, prev_empty = scv[band][0].n == 0;
+        float a = 0.0f;
+        bool run = true;
+        // with an empty curve the modulated sums equal the original ones bit for bit
+        if ((ch == 2 || ch == 4) && cur_empty) run = false;
+        if (ch >= 5 && (f == 0 || prev_empty)) run = false;
+        if (run) {
+            if (ch == 0) {
+                for (int i = 0; i < 256; i++) { const float v = prevw[band][i]; a = fadd(a, fmul(v, v)); }
+            } else if (ch == 1 || ch == 2) {
+                const float* src = ch == 1 ? cur[band] : curm[band];
+                for (int i = 0; i < 256; i++) { const float v = fmul(src[i], T->encode_window[255 - i]); a = fadd(a, fmul(v, v)); }
+            } else if (ch == 3 || ch == 4) {
+                const float* src = ch == 3 ? cur[band] : curm[band];
+                for (int i = 0; i < 256; i++) { const float v = fmul(src[i], T->encode_window[i]); a = fadd(a, fmul(v, v)); }
+            } else {
+                const float* src = pnext[band][ch - 5];
+                for (int i = 0; i < 256; i++) { const float v = src[i]; a = fadd(a, fmul(v, v)); }
+            }
+        }
+        esum[band][ch] = a;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        const int band = tid;
+        const Curve& cc = scv[band][1];
+        const bool cur_empty = cc.n == 0, prev_empty = scv[band][0].n == 0;
+        float pos_scale;                                       // PrevOverlapGainScale[channel][band]
+        if (f == 0) pos_scale = b.next_scale[sc * 4 + band];
+        else if (prev_empty) pos_scale = safe_energy_scale(1.0f, 1.0f);   // e/e == 1 or the eps branch: 1 either way
+        else pos_scale = safe_energy_scale(esum[band][5], esum[band][6]);
+        const float inf = __int_as_float(0x7f800000);
+        if (!(fabsf(pos_scale) < inf) || pos_scale <= 0.0f) pos_scale = 1.0f;
+        const float prev_div = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
+        const float prev_stored = esum[band][0];
+        const float prev_orig = fmul(prev_stored, pos_scale);
+        const float prev_mod = __fdiv_rn(prev_stored, fmul(prev_div, prev_div));
+        const float cur_orig = esum[band][1], cur_mod = cur_empty ? esum[band][1] : esum[band][2];
+        const float nxt_orig = esum[band][3], nxt_mod = cur_empty ? esum[band][3] : esum[band][4];
+        sscale[band][0] = safe_energy_scale(prev_orig, prev_mod);
+        sscale[band][1] = safe_energy_scale(cur_orig, cur_mod);
+        sscale[band][2] = safe_energy_scale(fadd(prev_orig, cur_orig), fadd(prev_mod, cur_mod));
+        sscale[band][3] = safe_energy_scale(nxt_orig, nxt_mod);
+    }
+    // ---- MDCT-512 per band: fold + pre-twiddle into kissfft's gather order (mdct.h:56-76) ----
+    //   tmp[j]       = prevw[j] / scale           j < 256   (Modulate divides bufCur by GainLevel[first point])
+    //   tmp[256 + j] = win[255-j] * curm[j]
+    ATDE_PAR_FOR(w, 512) {
+        const int band = w >> 7, slot = w & 127;
+        const Curve& cc = scv[band][1];
+        const bool mod = cc.n != 0;
+        const float scale = mod ? T->gain_level[cc.level[0]] : 1.0f;
+        const int i = T->perm128[slot];
+        const int n = 2 * i;                                 // N = 512, n4 = 128, n34 = 384, n54 = 640
+        const int ia0 = 383 - n, ib0 = 128 + n;
+        const int ia1 = (n < 128) ? 384 + n : n - 128;
+        const int ib1 = (n < 128) ? 127 - n : 639 - n;
+        float v[4];
+        const int idx[4] = {ia0, ia1, ib0, ib1};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = idx[q];
+            if (j < 256) v[q] = mod ? __fdiv_rn(prevw[band][j], scale) : prevw[band][j];
+            else v[q] = fmul(T->encode_window[255 - (j - 256)], curm[band][j - 256]);
+        }
+        float r0, i0;
+        if (n < 128) { r0 = fadd(v[0], v[1]); i0 = fsub(v[2], v[3]); }
+        else         { r0 = fsub(v[0], v[1]); i0 = fadd(v[2], v[3]); }
+        const float cc2 = T->sincos512[n], ss = T->sincos512[n + 1];
+        cpx X;
+        X.r = fadd(fmul(r0, cc2), fmul(i0, ss));
+        X.i = fsub(fmul(i0, cc2), fmul(r0, ss));
+        fft[band][slot] = X;
+    }
+    __syncthreads();
+    // FFT-128 = 4x4x4x2: radix-2 innermost (m = 1), then m = 2, 8, 32
+    {
+        const int band = tid >> 6, v = tid & 63;
+        kf_stage2(fft[band], T->tw128, v, 1, 64);
+    }
+    __syncthreads();
+    for (int st = 0; st < 3; st++) {
+        const int m = 2 << (2 * st);
+        if (tid < 128) {
+            const int band = tid >> 5, v = tid & 31;
+            kf_stage4<false>(fft[band], T->tw128, v, m, 32 / m);
+        }
+        __syncthreads();
+    }
+    // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55)
+    ATDE_PAR_FOR(w, 512) {
+        const int band = w >> 7, i = w & 127;
+        const int n = 2 * i;
+        const cpx z = fft[band][i];
+        const float cc2 = T->sincos512[n], ss = T->sincos512[n + 1];
+        const float va = fsub(fmul(-z.r, cc2), fmul(z.i, ss));
+        const float vb = fadd(fmul(-z.r, ss), fmul(z.i, cc2));
+        int pa = n, pb = 255 - n;
+        if (band & 1) { pa = 255 - pa; pb = 255 - pb; }
+        sp[band * 256 + pa] = va;
+        sp[band * 256 + pb] = vb;
+    }
+    __syncthreads();
+    const size_t unit = ((size_t)s * g.n_out + f) * g.C + c;
+    ATDE_PAR_FOR(i, 1024) b.specs[unit * 1024 + i] = sp[i];
+    if (tid < 16) b.gscale[unit * 16 + tid] = sscale[tid >> 2][tid & 3];
+    if (tid == 32) {
+        // sce->Loudness (atrac3denc.cpp:811-820): l += e * Frame * curve, sequential
+        float l = 0.0f;
+        for (int i = 0; i < 1024; i++) {
+            const float e = fmul(sp[i], sp[i]);
+            l = fadd(l, fmul(fmul(e, sscale[i >> 8][2]), T->loud_curve[i]));
+        }
+        b.chloud[unit] = l;
+    }
+    if (f == g.n_out - 1) {
+        // state for the next batch: the half this frame leaves behind and its NextOverlapScale
+        ATDE_PAR_FOR(w, 1024) {
+            const int band = w >> 8, i = w & 255;
+            b.prevhalf_out[(sc * 4 + band) * 256 + i] = fmul(T->encode_window[i], curm[band][i]);
+        }
+        if (tid < 4) b.next_scale_out[sc * 4 + tid] = sscale[tid][3];
+    }
+}
+
+void launch_mdct(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    dim3 grid(g.n_out, g.C, g.S);
+    ATDE_LAUNCH(at3_mdct_kernel, grid, 256, 0, st, g, b);
+}
+
+// =====================================================================================
+// K6: loudness recurrence, one thread per stream
+// =====================================================================================
+__global__ void at3_loudness_kernel(Geometry g, Buffers b)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.S) return;
+    float L = b.loud_state[s];
+    for (int f = 0; f < g.n_out; f++) {
+        const size_t o = ((size_t)s * g.n_out + f) * g.C;
+        if (g.C == 2 && !g.js) {
+            const float sum = fadd(b.chloud[o], b.chloud[o + 1]);
+            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.01, (double)sum)));
+        } else {
+            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.02, (double)b.chloud[o])));
+        }
+        b.loud[(size_t)s * g.n_out + f] = L;
+    }
+    b.loud_state[s] = L;
+}
+
+void launch_loudness(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    ATDE_LAUNCH(at3_loudness_kernel, (g.S + 63) / 64, 64, 0, st, g, b);
+}
+
+// =====================================================================================
+// carry: keep the last two extended PCM frames of every stream for the next batch
+// =====================================================================================
+__global__ void at3_carry_kernel(Geometry g, Buffers b)
+{
+    float* hist_out = b.hist_tmp;
+    const int s = blockIdx.x;
+    const bool started = b.started[s] != 0;
+    const int n = 2 * 1024 * g.C;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = i % g.C;
+        const int t = i / g.C;                                  // 0..2047: ext frames L-2, L-1
+        const long long ext = (long long)(g.L - 2) * 1024 + t;
+        hist_out[(size_t)s * n + i] = virt_pcm(g, b, s, c, ext, started);
+    }
+}
+
+__global__ void at3_carry_commit_kernel(Geometry g, Buffers b)
+{
+    const float* hist_in = b.hist_tmp;
+    unsigned char* started = b.started;
+    const int s = blockIdx.x;
+    const int n = 2 * 1024 * g.C;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        b.pcm_hist[(size_t)s * n + i] = hist_in[(size_t)s * n + i];
+    if (g.n_out > 0) {
+        const int m = g.C * 4 * 256;
+        for (int i = threadIdx.x; i < m; i += blockDim.x)
+            b.prevhalf[(size_t)s * m + i] = b.prevhalf_out[(size_t)s * m + i];
+        for (int i = threadIdx.x; i < g.C * 4; i += blockDim.x)
+            b.next_scale[(size_t)s * g.C * 4 + i] = b.next_scale_out[(size_t)s * g.C * 4 + i];
+    }
+    if (threadIdx.x == 0) started[s] = 1;
+}
+
+void launch_carry(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    ATDE_LAUNCH(at3_carry_kernel, g.S, 256, 0, st, g, b);
+    ATDE_LAUNCH(at3_carry_commit_kernel, g.S, 256, 0, st, g, b);
+}
+
+} // namespace at3
+} // namespace atde

@@ -1,4 +1,13 @@
-// at3_kernels.cuh — device-side interface of the ATRAC3 encode path (see at3_kernels.cu).
+// at3_kernels.cuh — device-side interface of the ATRAC3 encode path (at3_analysis.cu, at3_pack.cu).
+//
+// Frame numbering inside one batch.  The reference encoder runs one frame behind its input
+// (src/atrac3denc.cpp:697-718: the first lambda call only fills the look-ahead slot), so a batch is
+// described by an EXTENDED frame sequence per stream:
+//     ext frame 0      = the frame carried from the previous batch (started) or new frame 0 (fresh)
+//     ext frame 1..L-1 = the remaining new frames
+// Output frame f (0 <= f < n_out = L-1) encodes ext frame f and needs ext frames f-1 .. f+1.
+// Band buffers are indexed u = 128 + 256*f + i for sample i of ext frame f; u < 128 is the tail of
+// the frame before ext frame 0 (zeros for a fresh stream).
 #pragma once
 #include "atde_cuda.h"
 
@@ -8,8 +17,10 @@ namespace at3 {
 constexpr int kFrame = 1024;          // samples per channel-frame (atrac3.h:64)
 constexpr int kBfus = 32;             // atrac3.h:63
 constexpr int kBands = 4;
-constexpr float kLoudFactor = 0.006f; // atrac3denc.h:114
-constexpr int kMaxTonal = 32;         // the reference asserts < 32 tonal groups per channel
+constexpr int kGainBands = 3;         // band 3 never carries a curve (atrac3denc.cpp:444-450)
+constexpr float kLoudFactor = 0.006f; // atrac3denc.h:115
+constexpr int kMaxTonal = 24;         // <= one run per BFU 8..28, runs may only merge
+constexpr int kMaxUnitBytes = 1024;   // largest container frame (atrac3.h:211-220)
 
 // Device tables (global memory), built on the host by atde_api.cu:build_at3_tables
 struct DevTables {
@@ -23,21 +34,23 @@ struct DevTables {
     cpx tw128[128];                   // forward kissfft twiddles, MDCT-512's 128-point FFT
     unsigned char perm128[128];
     // gain control: TSpectralUpsampler (transient_spectral_upsampler.cpp)
-    float planck[512];
-    float hpf_h[2];                   // H at LowCutBin, LowCutBin+1
+    float planck[512];                // Planck-taper window, eps = 0.15
+    float hpf_h[2];                   // raised-cosine H at LowCutBin, LowCutBin+1
     int low_cut_bin;
-    cpx tw256[256];                   // forward, for kiss_fftr(512)
-    cpx super512[128];                // forward super twiddles
-    unsigned short perm256[256];
-    cpx tw2048[2048];                 // inverse, for kiss_fftri(4096)
-    cpx super4096[1024];              // inverse super twiddles
-    unsigned short iperm2048[2048];   // input index -> gather slot
+    cpx tw256[256];                   // forward, kiss_fftr(512) -> complex FFT-256
+    cpx super512[128];                // forward super twiddles of kiss_fftr(512)
+    unsigned char perm256[256];
+    cpx tw2048[2048];                 // inverse, kiss_fftri(4096) -> complex FFT-2048
+    cpx super4096[1024];              // inverse super twiddles of kiss_fftri(4096)
+    unsigned short iperm2048[2048];   // input index k -> gather slot of the digit-reversed order
 };
 
-// A gain curve of one (channel, band, frame): n points, each level (4 bit) / location (5 bit)
+// Gain curve of one (stream, channel, band, frame): n points, each level (4 bit) / location (5 bit)
 struct Curve {
-    unsigned short n;
-    unsigned short pt[7];             // level << 8 | location
+    unsigned char n;
+    unsigned char level[7];
+    unsigned char loc[7];
+    unsigned char pad;
 };
 
 struct TonalBlock {
@@ -56,37 +69,43 @@ struct TonalList {
 
 struct Geometry {
     int S, C;
-    int L;                            // extended frames per stream in this batch (carried + new)
+    int N;                            // new frames per stream in this batch
+    int L;                            // extended frames per stream (N + started)
     int n_out;                        // = L - 1 output frames
-    int started;                      // 1: frame 0 of the extended sequence is the carried one
-    int js;                           // joint stereo (LP4 with 2 channels)
+    int BL;                           // band buffer length per (s,c,band) = 128 + 256*L
+    int js;                           // joint stereo (container Js flag and C == 2)
     int frame_sz;                     // container frame size in bytes
     int no_gain, no_tonal;
     int bfu_idx_const;
 };
 
 struct Buffers {
-    const float* pcm;                 // [S][N][1024][C] new frames of this batch (N = L - started)
+    const float* pcm;                 // [S][N*1024][C] new frames of this batch
+    unsigned char* started;           // [S] (all equal inside a batch; kept per stream for clarity)
+    float* hist_tmp;                  // [S][2][1024][C] staging for the pcm_hist update
+    // carried stream state
     float* pcm_hist;                  // [S][2][1024][C]: frame before the carried one, carried frame
-    float* bands;                     // [S][C][4][128 + L*256]
-    Curve* curves;                    // [S][C][4][L]
-    float* prevhalf;                  // carry [S][C][4][256]
-    float* next_scale;                // carry [S][C][4]   PrevOverlapGainScale
+    float* prevhalf;                  // [S][C][4][256] windowed + modulated half kept for ext frame 0
+    float* next_scale;                // [S][C][4] PrevOverlapGainScale before ext frame 0
+    float* ctx;                       // [S][C][3][4]: LastLevel, LastHpfEnergy, LastTarget, -
+    float* loud_state;                // [S]
+    // per-batch work buffers
+    float* bands;                     // [S][C][4][BL]  (M/S already matrixed when js)
+    float* gain;                      // [S][C][3][n_out][96]: gain[32], low[32], high[32]
+    float* gstat;                     // [S][C][3][n_out][4]: hfr, curHpfEnergy, target, gain[31]
+    float* gprev;                     // [S][C][3][n_out][4]: prevHpfEnergy, savedLastLevel, savedLastTarget, -
+    Curve* curves;                    // [S][C][4][n_out]
+    float* prevhalf_out;              // [S][C][4][256] staging: half left behind by the last output frame
+    float* next_scale_out;            // [S][C][4]
     float* specs;                     // [S][n_out][C][1024] (scaled in place by the scale kernel)
-    float* gscale;                    // [S][n_out][C][4][3] PrevHalf, CurHalf, Frame
+    float* gscale;                    // [S][n_out][C][4][4]: PrevHalf, CurHalf, Frame, NextOverlapScale
     float* chloud;                    // [S][n_out][C]
-    float* loud_state;                // carry [S]
     float* loud;                      // [S][n_out]
     unsigned char* sfi;               // [S][n_out][C][32]
     float* energy;                    // [S][n_out][C][32]
     TonalList* tonal;                 // [S][n_out][C]
     unsigned char* out;               // [S][n_out][frame_sz]
-    // gain control scratch
-    float* gain;                      // [S][C][4][n_out][96]: gain[32], low[32], high[32]
-    float* gstat;                     // [S][C][4][n_out][4]: hfr, curHpf, target, reserved
-    float* gprev;                     // [S][C][4][n_out][4]: prevHpf, savedLastLevel, savedLastTarget, reserved
-    float* ctx;                       // carry [S][C][4][4]: LastLevel, LastHpfEnergy, LastTarget
-    unsigned char* tap_prec;          // [S][n_out][C][32] or nullptr
+    unsigned char* tap_prec;          // [S][n_out][C][32] or nullptr (0xff beyond numBfu)
     const DevTables* tab;
 };
 

@@ -1,0 +1,716 @@
+// at3_pack.cu — ATRAC3 encode hot path on sm_100a, coding half.
+//
+// Replaces (reference: dcherednik/atracdenc):
+//   K7 at3_scale_tonal_kernel  CalcSpectralFlatnessPerBfu (src/atrac/atrac_psy_common.cpp:158-199),
+//                              ExtractTonalComponents / MapTonalComponents (src/atrac3denc.cpp:581-662),
+//                              TScaler::Scale / ScaleFrame (src/atrac/atrac_scale.cpp:141-188)
+//   K8 at3_alloc_pack_kernel   TAtrac3BitStreamWriter::WriteSoundUnit (src/atrac/at3/atrac3_bitstream.cpp:759-847):
+//                              CalcMSBytesShift (:741-757), TConfigure/TAlloc under TBitStreamEncoder's bisection
+//                              (:587-682, src/lib/bs_encode/encode.cpp:57-129), CalcBitsAllocation (:272-336),
+//                              QuantMantisas (src/atrac/atrac_scale.cpp:40-130) behind the (bfu, wordlen) cache
+//                              (:151-227), ConsiderEnergyErr (:241-257), GroupTonalComponents /
+//                              EncodeTonalComponents (:338-524), EncodeSpecs with CLCEnc / VLCEnc (:92-149,526-565),
+//                              TBitStream::Write (src/lib/bitstream/bitstream.cpp:40-63)
+//
+// One warp owns one channel of one frame; lane i owns BFU i (ATRAC3 has exactly 32 BFUs).
+#include "at3_kernels.cuh"
+#include "glibc_math.cuh"
+#include "stdsort_dev.cuh"
+
+namespace atde {
+namespace at3 {
+
+// atrac3.h:83-105
+__device__ const unsigned short kBlockStart[33] = {
+    0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, 176,
+    192, 224, 256, 288, 320, 352, 384, 416, 448, 480, 512, 576, 640, 704, 768, 896, 1024};
+// atrac3_bitstream.cpp:44-49
+__device__ const unsigned char kFixedAlloc[32] = {
+    6, 6, 5, 4, 4, 4, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 0, 0, 0};
+__device__ const float kMaxQuant[8] = {0.0f, 1.5f, 2.5f, 3.5f, 4.5f, 7.5f, 15.5f, 31.5f};   // atrac3.h:79-82
+__device__ const unsigned char kClcLen[8] = {0, 4, 3, 3, 4, 4, 5, 6};                       // atrac3.h:106
+
+// Huffman tables, atrac3.h:110-176.  Selector s uses table s-1 of {1, 2, 3, 1, 5, 6, 7}.
+__device__ const unsigned char kHuffOff[8] = {0, 0, 9, 14, 0, 21, 36, 67};                  // by selector
+__device__ const unsigned char kHuffCode[130] = {
+    // table 1 (selectors 1 and 4)
+    0x0, 0x4, 0x5, 0xC, 0xD, 0x1C, 0x1D, 0x1E, 0x1F,
+    // table 2
+    0x0, 0x4, 0x5, 0x6, 0x7,
+    // table 3
+    0x0, 0x4, 0x5, 0xC, 0xD, 0xE, 0xF,
+    // table 5
+    0x0, 0x2, 0x3, 0x8, 0x9, 0xA, 0xB, 0x1C, 0x1D, 0x3C, 0x3D, 0x3E, 0x3F, 0xC, 0xD,
+    // table 6
+    0x0, 0x2, 0x3, 0x4, 0x5, 0x6, 0x7, 0x14, 0x15, 0x16, 0x17, 0x18, 0x19,
+    0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3A, 0x3B, 0x78, 0x79, 0x7A, 0x7B, 0x7C, 0x7D, 0x7E, 0x7F, 0x8, 0x9,
+    // table 7
+    0x0, 0x8, 0x9, 0xA, 0xB, 0xC, 0xD, 0xE, 0xF, 0x10, 0x11,
+    0x24, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2A, 0x2B, 0x2C, 0x2D, 0x2E, 0x2F, 0x30, 0x31, 0x32, 0x33,
+    0x68, 0x69, 0x6A, 0x6B, 0x6C, 0x6D, 0x6E, 0x6F, 0x70, 0x71, 0x72, 0x73, 0x74, 0x75,
+    0xEC, 0xED, 0xEE, 0xEF, 0xF0, 0xF1, 0xF2, 0xF3, 0xF4, 0xF5, 0xF6, 0xF7, 0xF8, 0xF9, 0xFA, 0xFB, 0xFC, 0xFD, 0xFE, 0xFF,
+    0x2, 0x3};
+__device__ const unsigned char kHuffBits[130] = {
+    1, 3, 3, 4, 4, 5, 5, 5, 5,
+    1, 3, 3, 3, 3,
+    1, 3, 3, 4, 4, 4, 4,
+    2, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 6, 6, 4, 4,
+    3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7, 4, 4,
+    3, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5,
+    6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6,
+    7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7,
+    8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8,
+    4, 4};
+__device__ const unsigned char kVlcPairIdx[9] = {8, 4, 7, 2, 0, 1, 6, 3, 5};                // atrac3.h:227-233
+__device__ const unsigned char kClcIdx[4] = {2, 3, 0, 1};                                   // atrac3.h:221-226
+
+ATDE_D int huff_index(int m)
+{
+    int h = (m < 0) ? (((-m) << 1) | 1) : (m << 1);
+    if (h) h -= 1;
+    return h;
+}
+
+ATDE_D int bfu_band(int i) { return i >= 30 ? 3 : (i >= 26 ? 2 : (i >= 18 ? 1 : 0)); }     // BlocksPerBand {0,18,26,30,32}
+
+ATDE_D unsigned warp_sum_u(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// lower_bound over ScaleTable + TScaler::Scale (atrac_scale.cpp:141-172); writes the scaled values
+// back over v[0..len) and returns sfi / energy.
+ATDE_D int scale_block(const DevTables* T, float* v, int len, float& energy)
+{
+    float mx = 0.0f;
+    for (int j = 0; j < len; j++) {
+        const float a = fabsf(v[j]);
+        if (a > mx) mx = a;
+    }
+    if (mx > 1.0f) mx = 1.0f;
+    int lo = 0, hi = 63;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (T->scale_table[mid] < mx) lo = mid + 1; else hi = mid;
+    }
+    const float scale = T->scale_table[lo];
+    float en = 0.0f;
+    for (int j = 0; j < len; j++) {
+        const float x = v[j];
+        float q = __fdiv_rn(x, scale);
+        en = fadd(en, fmul(x, x));
+        if (fabsf(q) >= 1.0f) q = (q > 0.0f) ? 0.99999f : -0.99999f;
+        v[j] = q;
+    }
+    energy = en;
+    return lo;
+}
+
+// =====================================================================================
+// K7: tonal extraction + scaling, one warp per channel-frame
+// =====================================================================================
+constexpr int kScaleWarps = 4;
+
+__global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geometry g, Buffers b)
+{
+    __shared__ __align__(16) float sv_all[kScaleWarps][1024];
+    __shared__ float run_val[kScaleWarps][32][5];
+    __shared__ short run_start[kScaleWarps][32];
+    __shared__ signed char run_len[kScaleWarps][32];
+
+    const DevTables* __restrict__ T = b.tab;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long unit = (long long)blockIdx.x * kScaleWarps + wib;
+    const long long total = (long long)g.S * g.n_out * g.C;
+    if (unit >= total) return;
+    float* sv = sv_all[wib];
+    float* gsp = b.specs + (size_t)unit * 1024;
+    for (int i = lane; i < 1024; i += 32) sv[i] = gsp[i];
+    run_len[wib][lane] = 0;
+    __syncwarp();
+
+    const int start = kBlockStart[lane], len = kBlockStart[lane + 1] - kBlockStart[lane];
+    TonalList* tl = b.tonal + unit;
+    if (!g.no_tonal) {
+        if (lane >= 8 && lane < 29) {
+            // CalcSpectralFlatnessPerBfu: geometric / arithmetic mean of the line energies, in double
+            const double floor_d = (double)1e-12f;
+            double arith = 0.0, mean_log = 0.0;
+            for (int i = 0; i < len; i++) {
+                const float ef = fmul(sv[start + i], sv[start + i]);
+                const double e = (double)fmaxf(0.0f, ef);
+                arith = __dadd_rn(arith, e);
+                mean_log = __dadd_rn(mean_log, g_log(e > floor_d ? e : floor_d));
+            }
+            arith = __ddiv_rn(arith, (double)len);
+            mean_log = __ddiv_rn(mean_log, (double)len);
+            float flat = 1.0f;
+            if (!(arith <= floor_d)) {
+                const double ratio = __ddiv_rn(g_exp(mean_log), arith);
+                const double cl = ratio < 0.0 ? 0.0 : (ratio > 1.0 ? 1.0 : ratio);   // min(1, max(0, ratio))
+                flat = __double2float_rn(cl);
+            }
+            if (flat < 0.01f) {
+                // ExtractTonalComponents: best run of <= 5 lines by summed magnitude
+                const int max_len = min(5, len);
+                float best = -1.0f;
+                int best_start = start, best_len = 1;
+                for (int st = start; st < start + len; st++) {
+                    const int ml = min(max_len, start + len - st);
+                    float score = 0.0f;
+                    for (int l = 1; l <= ml; l++) {
+                        score = fadd(score, fabsf(sv[st + l - 1]));
+                        if (score > best) { best = score; best_start = st; best_len = l; }
+                    }
+                }
+                if (best > 0.0f) {
+                    run_start[wib][lane] = (short)best_start;
+                    run_len[wib][lane] = (signed char)best_len;
+                    for (int n = 0; n < best_len; n++) {
+                        run_val[wib][lane][n] = sv[best_start + n];
+                        sv[best_start + n] = 0.0f;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // MapTonalComponents: runs of consecutive positions (<= 7 values) become tonal blocks
+            int nblk = 0;
+            int bfu = 8, k = 0;                                  // cursor: component k of BFU bfu's run
+            auto advance = [&]() {
+                while (bfu < 29 && k >= run_len[wib][bfu]) { bfu++; k = 0; }
+            };
+            advance();
+            while (bfu < 29 && nblk < kMaxTonal) {
+                TonalBlock blk;
+                float tmp[8];
+                const int first_pos = run_start[wib][bfu] + k;
+                blk.pos = (unsigned short)first_pos;
+                blk.bfu = (unsigned char)bfu;
+                int cnt = 0, cur_pos;
+                do {
+                    cur_pos = run_start[wib][bfu] + k;
+                    tmp[cnt++] = run_val[wib][bfu][k];
+                    k++;
+                    advance();
+                } while (bfu < 29 && (run_start[wib][bfu] + k) == cur_pos + 1 && cnt < 7);
+                float en;
+                blk.sfi = (unsigned char)scale_block(T, tmp, cnt, en);
+                blk.len = (unsigned char)cnt;
+                blk.pad[0] = blk.pad[1] = blk.pad[2] = 0;
+                for (int j = 0; j < 7; j++) blk.val[j] = j < cnt ? tmp[j] : 0.0f;
+                tl->b[nblk++] = blk;
+            }
+            tl->n = nblk;
+        }
+        __syncwarp();
+    } else if (lane == 0) {
+        tl->n = 0;
+    }
+    // ScaleFrame on what is left of the spectrum
+    float en;
+    const int sfi = scale_block(T, sv + start, len, en);
+    b.sfi[(size_t)unit * 32 + lane] = (unsigned char)sfi;
+    b.energy[(size_t)unit * 32 + lane] = en;
+    __syncwarp();
+    for (int i = lane; i < 1024; i += 32) gsp[i] = sv[i];
+}
+
+void launch_scale_tonal(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    const long long total = (long long)g.S * g.n_out * g.C;
+    ATDE_LAUNCH(at3_scale_tonal_kernel, (unsigned)((total + kScaleWarps - 1) / kScaleWarps), kScaleWarps * 32, 0, st, g, b);
+}
+
+// =====================================================================================
+// K8: bit allocation search + quantisation + entropy coding + frame assembly
+// =====================================================================================
+// QuantMantisas of one BFU at one word length, plus its CLC / VLC cost (TAt3SpecUnit::Provide).
+// `in` = scaled values of the BFU.  m_out (optional) receives the mantissas.
+struct UnitCost {
+    unsigned clc, vlc;
+    float err;
+};
+
+ATDE_D UnitCost quant_unit(const float* in, int len, int bfu, int wl, signed char* m_out)
+{
+    const float mul = kMaxQuant[wl];
+    const float inv2 = __double2float_rn(__ddiv_rn(1.0, (double)fmul(mul, mul)));
+    const bool ea = bfu > 18;                                   // LOSY_NAQ_START
+    signed char m[128];
+    float e1 = 0.0f, e2 = 0.0f;
+    if (!ea) {
+        for (int j = 0; j < len; j++) {
+            const float t = fmul(in[j], mul);
+            e1 = fadd(e1, fmul(in[j], in[j]));
+            const int q = __float2int_rn(t);
+            m[j] = (signed char)q;
+            e2 = fadd(e2, fmul((float)(q * q), inv2));
+        }
+    } else {
+        SortCand cand[128];
+        int nc = 0;
+        for (int j = 0; j < len; j++) {
+            const float t = fmul(in[j], mul);
+            e1 = fadd(e1, fmul(in[j], in[j]));
+            const int q = __float2int_rn(t);
+            m[j] = (signed char)q;
+            e2 = fadd(e2, fmul((float)(q * q), inv2));
+            const float delta = fsub(t, fadd(truncf(t), 0.5f));
+            if (fabsf(delta) < 0.25f) { cand[nc].delta = delta; cand[nc].idx = j; nc++; }
+        }
+        if (nc > 0) {
+            std_sort_cands(cand, nc);
+            if (e2 < e1) {
+                for (int k = 0; k < nc; k++) {
+                    const int j = cand[k].idx;
+                    const float t = fmul(in[j], mul);
+                    const int q = m[j];
+                    const float aq = (float)abs(q);
+                    if (aq < fabsf(t) && aq < fsub(mul, 1.0f)) {
+                        int q2 = q;
+                        if (q > 0) q2++;
+                        if (q < 0) q2--;
+                        if (q == 0) q2 = t > 0.0f ? 1 : -1;
+                        float ex = e2;
+                        ex = fsub(ex, fmul((float)(q * q), inv2));
+                        ex = fadd(ex, fmul((float)(q2 * q2), inv2));
+                        if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
+                    }
+                }
+            } else if (e2 > e1) {
+                for (int k = 0; k < nc; k++) {
+                    const int j = cand[k].idx;
+                    const float t = fmul(in[j], mul);
+                    const int q = m[j];
+                    if ((float)abs(q) > fabsf(t)) {
+                        int q2 = q;
+                        if (q > 0) q2--;
+                        if (q < 0) q2++;
+                        float ex = e2;
+                        ex = fsub(ex, fmul((float)(q * q), inv2));
+                        ex = fadd(ex, fmul((float)(q2 * q2), inv2));
+                        if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
+                    }
+                }
+            }
+        }
+    }
+    UnitCost u;
+    u.err = __fdiv_rn(e1, e2);
+    // CLCEnc / VLCEnc bit counts (atrac3_bitstream.cpp:92-149)
+    if (wl > 1) {
+        u.clc = (unsigned)kClcLen[wl] * len;
+        unsigned v = 0;
+        const int off = kHuffOff[wl];
+        for (int j = 0; j < len; j++) v += kHuffBits[off + huff_index(m[j])];
+        u.vlc = v;
+    } else {
+        u.clc = 4u * len / 2;
+        unsigned v = 0;
+        for (int j = 0; j < len / 2; j++)
+            v += kHuffBits[kVlcPairIdx[3 * (m[2 * j] + 1) + (m[2 * j + 1] + 1)]];
+        u.vlc = v;
+    }
+    if (m_out)
+        for (int j = 0; j < len; j++) m_out[j] = m[j];
+    return u;
+}
+
+// MSB-first bit field into a zeroed big-endian word array (value already masked to n bits);
+// fields that start beyond the buffer are dropped (the reference truncates with resize()).
+ATDE_D void put_bits3(unsigned* words, int cap_bits, int pos, int n, unsigned val)
+{
+    if (n <= 0 || pos + n > cap_bits) return;
+    const int w = pos >> 5, off = pos & 31;
+    const int room = 32 - off;
+    if (n <= room) {
+        atomicOr(&words[w], val << (room - n));
+    } else {
+        atomicOr(&words[w], val >> (n - room));
+        atomicOr(&words[w + 1], val << (32 - (n - room)));
+    }
+}
+
+constexpr int kWordsPerCh = kMaxUnitBytes / 4 + 8;             // bitstream of one channel
+
+struct PackShared {
+    float sv[1024];                    // scaled spectrum of the channel
+    unsigned words[kWordsPerCh];
+    unsigned cache_cv[8][32];          // clc | vlc << 16, indexed [wordlen][bfu]
+    float cache_err[8][32];
+    unsigned short ton_pos[kMaxTonal];
+    unsigned char ton_bfu[kMaxTonal], ton_len[kMaxTonal], ton_sfi[kMaxTonal];
+    unsigned char ton_vlc[kMaxTonal][8];   // VLC bits of the block's mantissas at quantiser 2..7
+    unsigned char prec[32];
+    int hdr_bits;                      // header + gain info bits of this channel
+};
+
+// bits EncodeTonalComponents would emit for the current allocation (atrac3_bitstream.cpp:382-524),
+// warp-cooperative: lane t owns tonal block t.
+ATDE_D unsigned tonal_bits(const PackShared& sh, int n_ton, int lane, unsigned prec, int num_bfu)
+{
+    if (n_ton == 0) return 5;
+    const int t = lane < n_ton ? lane : 0;
+    const int my_bfu = sh.ton_bfu[t];
+    const unsigned my_prec = __shfl_sync(0xffffffffu, prec, my_bfu);
+    const bool active = lane < n_ton && my_bfu < num_bfu;
+    const int quant = (int)max(2u, min(my_prec + 4u, 7u));
+    const int key = active ? quant * 8 + sh.ton_len[t] : -1;
+    const int pos = sh.ton_pos[t];
+    // subgroup automaton of GroupTonalComponents, run by the first member of every (quant, len) group
+    bool leader = active;
+    int start_val = 0, limiter = 0, nsub = 0;
+    unsigned flags = 0, bits = 0;
+    for (int j = 0; j < n_ton; j++) {
+        const int kj = __shfl_sync(0xffffffffu, key, j);
+        const int pj = __shfl_sync(0xffffffffu, pos, j);
+        if (kj < 0 || kj != key) continue;
+        if (j < lane) { leader = false; continue; }
+        if (!leader) continue;
+        if (j == lane) {
+            nsub = 1; start_val = pj; limiter = 0; flags = 1u << (pj >> 8);
+        } else {
+            if (pj - (start_val & ~63) < 64) ++limiter; else { limiter = 0; start_val = pj; }
+            if (limiter < 7) {
+                flags |= 1u << (pj >> 8);
+            } else {
+                bits += 10u + 12u * __popc(flags);
+                nsub++; start_val = pj; limiter = 0; flags = 1u << (pj >> 8);
+            }
+        }
+    }
+    if (leader) bits += 10u + 12u * __popc(flags);
+    if (active) bits += 12u + sh.ton_vlc[t][quant];
+    const unsigned tcsgn = warp_sum_u(leader ? (unsigned)nsub : 0u);
+    const unsigned sum = warp_sum_u(bits);
+    return 5u + (tcsgn ? 2u : 0u) + sum;
+}
+
+__global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers b)
+{
+    __shared__ PackShared shm[2];
+    __shared__ int s_shift;
+
+    const DevTables* __restrict__ T = b.tab;
+    const int lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+    const long long frame = blockIdx.x;                         // s * n_out + f
+    const int f = (int)(frame % g.n_out);
+    const int s = (int)(frame / g.n_out);
+    const long long unit = frame * g.C + ch;
+    PackShared& sh = shm[ch];
+    const int half = g.frame_sz >> 1;
+
+    // ---- load; header + gain info size of both channels (WriteSoundUnit, :771-804) ----
+    const float* gsp = b.specs + (size_t)unit * 1024;
+    for (int i = lane; i < 1024; i += 32) sh.sv[i] = gsp[i];
+    for (int i = lane; i < kWordsPerCh; i += 32) sh.words[i] = 0;
+    const TonalList* tl = b.tonal + unit;
+    const int n_ton = g.no_tonal ? 0 : tl->n;
+    if (lane < n_ton) {
+        const TonalBlock& tb = tl->b[lane];
+        sh.ton_pos[lane] = tb.pos; sh.ton_bfu[lane] = tb.bfu; sh.ton_len[lane] = tb.len; sh.ton_sfi[lane] = tb.sfi;
+        for (int q = 2; q < 8; q++) {
+            unsigned v = 0;
+            const int off = kHuffOff[q];
+            for (int z = 0; z < tb.len; z++)
+                v += kHuffBits[off + huff_index(__float2int_rn(fmul(tb.val[z], kMaxQuant[q])))];
+            sh.ton_vlc[lane][q] = (unsigned char)v;
+        }
+    }
+    Curve cv[4];
+#pragma unroll
+    for (int band = 0; band < 4; band++) {
+        cv[band].n = 0;
+        if (!g.no_gain && band < kGainBands)
+            cv[band] = b.curves[(((size_t)s * g.C + ch) * 4 + band) * g.n_out + f];
+    }
+    if (lane == 0) {
+        int hb = (g.js && ch == 1) ? 14 : 6;
+        hb += 2;
+        for (int band = 0; band < 4; band++) hb += 3 + 9 * cv[band].n;
+        sh.hdr_bits = hb;
+    }
+    __syncthreads();
+    // ---- byte budget of this channel ----
+    int shift_bytes = 0;
+    if (g.js) {
+        if (threadIdx.x == 0) {
+            const int b0 = -6 - shm[0].hdr_bits, b1 = -6 - shm[1].hdr_bits;
+            const int used = 0 - b0 - b1;
+            const int max_shift = half - (int)(1u + ((unsigned)used - 1u) / 8u);
+            const float m_e = b.chloud[frame * 2], s_e = b.chloud[frame * 2 + 1];
+            const float tot = fadd(s_e, m_e);
+            float ratio = 0.0f;
+            if (tot > 0.0f)
+                ratio = __double2float_rn(__dsub_rn((double)__fdiv_rn(m_e, tot), 0.5));
+            const int want = __float2int_rn(fmul((float)g.frame_sz, ratio));
+            s_shift = max(min(want, max_shift), -max_shift);
+        }
+        __syncthreads();
+        shift_bytes = s_shift;
+    }
+    const int my_bytes = (ch == 0) ? half + shift_bytes : half - shift_bytes;
+    int to_alloc = -6 - sh.hdr_bits + 8 * my_bytes;
+    const unsigned target = (unsigned)(unsigned short)max(1, to_alloc);
+    const int cap_bits = kWordsPerCh * 32 - 32;
+    const float loud = __fdiv_rn(b.loud[frame], kLoudFactor);
+
+    // ---- per-BFU constants ----
+    const int start = kBlockStart[lane], len = kBlockStart[lane + 1] - kBlockStart[lane];
+    const int sfi = b.sfi[(size_t)unit * 32 + lane];
+    const float energy = b.energy[(size_t)unit * 32 + lane];
+    float ges = b.gscale[(size_t)unit * 16 + bfu_band(lane) * 4 + 2];
+    {
+        const float inf = __int_as_float(0x7f800000);
+        if (!(fabsf(ges) < inf) || !(ges > 0.0f)) ges = 1.0f;   // SanitizeGainEnergyScale
+    }
+    const bool audible = !(fmul(energy, ges) < fmul(T->ath[lane], loud));
+    const float sfi_corr = fmaxf(0.0f, fminf(63.0f, fadd((float)sfi, fmul(1.5f, g_log2f(ges)))));
+    const float xdiv = lane < 3 ? 2.8f : (lane < 10 ? 2.6f : (lane < 15 ? 3.3f : (lane <= 20 ? 3.6f : (lane <= 28 ? 4.2f : 6.0f))));
+    const float sfi_term = __fdiv_rn(sfi_corr, xdiv);
+    const float fix = (float)kFixedAlloc[lane];
+    int n_ton_mine = 0;                                          // tonal blocks whose first line is in this BFU
+    for (int t = 0; t < n_ton; t++) n_ton_mine += (sh.ton_bfu[t] == lane);
+    // AnalizeScaleFactorSpread (atrac_psy_common.cpp:105-124): sequential float sums
+    float spread;
+    {
+        float sacc = 0.0f;
+        for (int i = 0; i < 32; i++) sacc = fadd(sacc, (float)__shfl_sync(0xffffffffu, sfi, i));
+        sacc = __fdiv_rn(sacc, 32.0f);
+        float sigma = 0.0f;
+        for (int i = 0; i < 32; i++) {
+            float t = fsub((float)__shfl_sync(0xffffffffu, sfi, i), sacc);
+            t = fmul(t, t);
+            sigma = fadd(sigma, t);
+        }
+        sigma = __fsqrt_rn(__fdiv_rn(sigma, 32.0f));
+        if (sigma > 14.0f) sigma = 14.0f;
+        spread = __fdiv_rn(sigma, 14.0f);
+    }
+    const float fix_term = fmul(fsub(1.0f, spread), fix);
+    unsigned cached = 0;                                         // bit w: (lane, w) is in the cache
+
+    // CalcInitialNumBfu (:567-585)
+    int num_bfu = g.bfu_idx_const ? g.bfu_idx_const : 32;
+    if (target < 101u) {
+        int lim = 1;
+        if (target > 5u) lim = (int)(target - 5u) / 3;
+        lim = max(1, lim);
+        num_bfu = min(num_bfu, lim);
+    }
+    num_bfu = max(1, num_bfu);
+
+    unsigned prec = 0;
+    unsigned mode = 1;
+    for (;;) {                                                   // TConfigure: ba.Start(target, -8, 20)
+        float mn = -8.0f, mx = 20.0f, last = 20.0f;
+        for (;;) {                                               // TAlloc::Encode
+            const bool exhausted = mx <= mn;
+            const float shift = exhausted ? last : __double2float_rn(__ddiv_rn((double)fadd(mx, mn), 2.0));
+            // CalcBitsAllocation (:272-336)
+            prec = 0;
+            if (lane < num_bfu && audible) {
+                const int tmp = __float2int_rz(fsub(fadd(fmul(spread, sfi_term), fix_term), shift));
+                prec = tmp > 7 ? 7u : (tmp < 0 ? 0u : (tmp == 0 ? 1u : (unsigned)tmp));
+            }
+            if (lane < num_bfu && n_ton_mine && prec > 2u)
+                prec = max(2u, prec - (unsigned)min(n_ton_mine, 8));
+            // CalcSpecsBitsConsumption + ConsiderEnergyErr (:190-257): every BFU's trajectory is independent
+            unsigned cvb = 0;
+            if (lane < num_bfu) {
+                for (;;) {
+                    if (prec == 0) break;
+                    if (!((cached >> prec) & 1u)) {
+                        const UnitCost u = quant_unit(sh.sv + start, len, lane, (int)prec, nullptr);
+                        sh.cache_cv[prec][lane] = u.clc | (u.vlc << 16);
+                        sh.cache_err[prec][lane] = u.err;
+                        cached |= 1u << prec;
+                    }
+                    cvb = sh.cache_cv[prec][lane];
+                    if (lane >= 10) break;                       // BOOST_NAQ_END
+                    const float e = sh.cache_err[prec][lane];
+                    if (((e > 0.0f && e < 0.7f) || e > 1.2f) && prec < 7u) prec++;
+                    else break;
+                }
+            }
+            const unsigned clc = warp_sum_u(prec ? (cvb & 0xffffu) : 0u);
+            const unsigned vlc = warp_sum_u(prec ? (cvb >> 16) : 0u);
+            const unsigned nz = __popc(__ballot_sync(0xffffffffu, prec != 0));
+            mode = clc <= vlc;
+            unsigned total = (unsigned)num_bfu * 3u + 6u * nz + (mode ? clc : vlc);
+            total += tonal_bits(sh, n_ton, lane, prec, num_bfu);
+            if (exhausted) break;
+            if (total < target) { last = shift; mx = fsub(shift, 0.01f); }
+            else if (total > target) { mn = fadd(shift, 0.01f); }
+            else break;
+        }
+        if (!g.bfu_idx_const && num_bfu > 1) {
+            const unsigned last_prec = __shfl_sync(0xffffffffu, prec, num_bfu - 1);
+            if (last_prec == 0) { num_bfu--; continue; }         // CheckBfus -> EStatus::Repeat
+        }
+        break;
+    }
+    if (b.tap_prec) b.tap_prec[(size_t)unit * 32 + lane] = lane < num_bfu ? (unsigned char)prec : 0xff;
+    sh.prec[lane] = (unsigned char)prec;
+    __syncwarp();
+
+    // ---- write the channel's sound unit ----
+    int pos = 0;
+    if (lane == 0) {
+        unsigned* W = sh.words;
+        auto put = [&](unsigned v, int n) { put_bits3(W, cap_bits, pos, n, v & ((1u << n) - 1u)); pos += n; };
+        if (g.js && ch == 1) {
+            put(0, 1); put(7, 3);
+            for (int i = 0; i < 4; i++) put(3, 2);
+            put(3, 2);
+        } else {
+            put(0x28, 6);
+        }
+        put(3, 2);                                               // numQmfBand - 1
+        for (int band = 0; band < 4; band++) {
+            put(cv[band].n, 3);
+            for (int i = 0; i < cv[band].n; i++) { put(cv[band].level[i], 4); put(cv[band].loc[i], 5); }
+        }
+        // EncodeTonalComponents (:382-524)
+        int order[kMaxTonal], keys[kMaxTonal], na = 0;
+        for (int t = 0; t < n_ton; t++) {
+            if (sh.ton_bfu[t] >= num_bfu) continue;
+            const int quant = max(2, min((int)sh.prec[sh.ton_bfu[t]] + 4, 7));
+            order[na] = t; keys[na] = quant * 8 + sh.ton_len[t]; na++;
+        }
+        // count subgroups first (tcsgn is written ahead of them)
+        int tcsgn = 0;
+        for (int key = 16; key < 64; key++) {
+            int startv = 0, limiter = 0; bool open = false;
+            for (int a = 0; a < na; a++) {
+                if (keys[a] != key) continue;
+                const int p = sh.ton_pos[order[a]];
+                if (!open) { open = true; tcsgn++; startv = p; limiter = 0; }
+                else {
+                    if (p - (startv & ~63) < 64) ++limiter; else { limiter = 0; startv = p; }
+                    if (limiter >= 7) { tcsgn++; startv = p; limiter = 0; }
+                }
+            }
+        }
+        put((unsigned)tcsgn, 5);
+        if (tcsgn) {
+            put(0, 2);
+            for (int key = 16; key < 64; key++) {
+                int mem[kMaxTonal], nm = 0;
+                for (int a = 0; a < na; a++) if (keys[a] == key) mem[nm++] = order[a];
+                if (!nm) continue;
+                const int quant = key >> 3, coded = key & 7;
+                int a0 = 0;
+                while (a0 < nm) {
+                    // extent of the subgroup starting at a0
+                    int startv = sh.ton_pos[mem[a0]], limiter = 0, a1 = a0 + 1;
+                    while (a1 < nm) {
+                        const int p = sh.ton_pos[mem[a1]];
+                        if (p - (startv & ~63) < 64) ++limiter; else { limiter = 0; startv = p; }
+                        if (limiter >= 7) break;
+                        a1++;
+                    }
+                    unsigned char cnt[16];
+                    for (int j = 0; j < 16; j++) cnt[j] = 0;
+                    for (int a = a0; a < a1; a++) cnt[sh.ton_pos[mem[a]] >> 6]++;
+                    unsigned bandf = 0;
+                    for (int j = 0; j < 16; j++) if (cnt[j]) bandf |= 1u << (j >> 2);
+                    for (int j = 0; j < 4; j++) put((bandf >> j) & 1u, 1);
+                    put((unsigned)(coded - 1), 3);
+                    put((unsigned)quant, 3);
+                    int lastp = a0;
+                    for (int j = 0; j < 16; j++) {
+                        if (!((bandf >> (j >> 2)) & 1u)) continue;
+                        put(cnt[j], 3);
+                        for (int k = lastp; k < lastp + cnt[j]; k++) {
+                            const int t = mem[k];
+                            put(sh.ton_sfi[t], 6);
+                            put((unsigned)(sh.ton_pos[t] - j * 64), 6);
+                            const TonalBlock& tb = tl->b[t];
+                            const int off = kHuffOff[quant];
+                            for (int z = 0; z < tb.len; z++) {
+                                const int hi = huff_index(__float2int_rn(fmul(tb.val[z], kMaxQuant[quant])));
+                                put(kHuffCode[off + hi], kHuffBits[off + hi]);
+                            }
+                        }
+                        lastp += cnt[j];
+                    }
+                    a0 = a1;
+                }
+            }
+        }
+        put((unsigned)(num_bfu - 1), 5);
+        put(mode, 1);
+    }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    // precisions, scale factor indices, mantissas (EncodeSpecs :541-564)
+    const bool in_use = lane < num_bfu;
+    if (in_use) put_bits3(sh.words, cap_bits, pos + 3 * lane, 3, prec);
+    pos += 3 * num_bfu;
+    const unsigned nzmask = __ballot_sync(0xffffffffu, in_use && prec != 0);
+    if (in_use && prec) put_bits3(sh.words, cap_bits, pos + 6 * __popc(nzmask & ((1u << lane) - 1u)), 6, (unsigned)sfi);
+    pos += 6 * __popc(nzmask);
+    unsigned mybits = 0;
+    if (in_use && prec) {
+        const unsigned cvb = sh.cache_cv[prec][lane];
+        mybits = mode ? (cvb & 0xffffu) : (cvb >> 16);
+    }
+    unsigned inc = mybits;
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned a = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += a;
+    }
+    if (in_use && prec) {
+        signed char m[128];
+        quant_unit(sh.sv + start, len, lane, (int)prec, m);
+        int p = pos + (int)(inc - mybits);
+        if (mode) {
+            if (prec > 1u) {
+                const int nb = kClcLen[prec];
+                for (int j = 0; j < len; j++) { put_bits3(sh.words, cap_bits, p, nb, (unsigned)m[j] & ((1u << nb) - 1u)); p += nb; }
+            } else {
+                for (int j = 0; j < len / 2; j++) {
+                    const unsigned code = ((unsigned)kClcIdx[m[2 * j] + 2] << 2) | kClcIdx[m[2 * j + 1] + 2];
+                    put_bits3(sh.words, cap_bits, p, 4, code); p += 4;
+                }
+            }
+        } else {
+            const int off = kHuffOff[prec];
+            if (prec > 1u) {
+                for (int j = 0; j < len; j++) {
+                    const int hi = huff_index(m[j]);
+                    put_bits3(sh.words, cap_bits, p, kHuffBits[off + hi], kHuffCode[off + hi]); p += kHuffBits[off + hi];
+                }
+            } else {
+                for (int j = 0; j < len / 2; j++) {
+                    const int hi = kVlcPairIdx[3 * (m[2 * j] + 1) + (m[2 * j + 1] + 1)];
+                    put_bits3(sh.words, cap_bits, p, kHuffBits[hi], kHuffCode[hi]); p += kHuffBits[hi];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- frame assembly (:826-843): channel 0 bytes, then channel 1 (byte-reversed when joint stereo);
+    //      mono without JS duplicates the half frame ----
+    unsigned char* dst = b.out + (size_t)frame * g.frame_sz;
+    const int n0 = half + shift_bytes;
+    for (int i = threadIdx.x; i < g.frame_sz; i += blockDim.x) {
+        int chn, q;
+        if (i < n0) { chn = 0; q = i; }
+        else if (g.C == 2) {
+            chn = 1;
+            q = i - n0;
+            if (g.js) q = (g.frame_sz - n0 - 1) - q;
+        } else { chn = 0; q = i - n0; }
+        const unsigned w = shm[chn].words[q >> 2];
+        dst[i] = (unsigned char)(w >> (24 - 8 * (q & 3)));
+    }
+}
+
+void launch_alloc_pack(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    const long long frames = (long long)g.S * g.n_out;
+    ATDE_LAUNCH(at3_alloc_pack_kernel, (unsigned)frames, 32 * g.C, 0, st, g, b);
+}
+
+} // namespace at3
+} // namespace atde

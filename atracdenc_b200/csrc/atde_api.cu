@@ -5,6 +5,7 @@
 #include "../../include/atde_b200.h"
 #include "atde_cuda.h"
 #include "at1_kernels.cuh"
+#include "at3_kernels.cuh"
 #include "glibc_math.cuh"
 #include "host_tables.h"
 
@@ -64,11 +65,18 @@ struct Workspace {
     DevBuf<unsigned char> out;      // host path only
     DevBuf<int> sizes;              // host path only
     DevBuf<unsigned char> tap_sfi, tap_wl;
+    // ATRAC3
+    DevBuf<float> bands, gain, gstat, gprev, gscale, energy, hist_tmp;
+    DevBuf<atde::at3::Curve> curves;
+    DevBuf<atde::at3::TonalList> tonal;
+    DevBuf<unsigned char> sfi;
     cudaStream_t stream = nullptr;
     void release()
     {
         pcm.release(); specs.release(); masks.release(); chloud.release(); loud.release();
         out.release(); sizes.release(); tap_sfi.release(); tap_wl.release();
+        bands.release(); gain.release(); gstat.release(); gprev.release(); gscale.release();
+        energy.release(); hist_tmp.release(); curves.release(); tonal.release(); sfi.release();
     }
 };
 
@@ -78,6 +86,10 @@ struct atde_encoder {
     atde_settings cfg;
     int frame_samples = 0, units_per_frame = 0, unit_bytes = 0, lookahead = 0;
     atde::at1::DevTables* d_at1_tab = nullptr;
+    atde::at3::DevTables* d_at3_tab = nullptr;
+    int at3_js = 0;
+    // ATRAC3 stream state beyond hist / loud_state / started
+    DevBuf<float> prevhalf, next_scale, ctx;
     Workspace ws[2];
     // stream state, sized for n_state_streams
     DevBuf<float> hist;
@@ -85,6 +97,8 @@ struct atde_encoder {
     DevBuf<unsigned char> started;
     int n_state_streams = 0;
     bool have_state = false;
+    bool streams_started = false;   // at least one batch went through since create/reset
+    long long last_out = 0;         // output frames per stream of the last batch
     bool taps_enabled = false;
     // geometry of the last batch, for taps
     int last_S = 0; long long last_F = 0;
@@ -147,6 +161,100 @@ int build_at1_tables(atde_encoder* e)
     delete h;
     if (ce != cudaSuccess) return fail(ATDE_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(ce));
     at1::upload_qmf_window(qmf);
+    return 0;
+}
+
+
+// Container parameters, atrac3.h:211-220; GetContainerParamsForBitrate (atrac3.cpp:45-51) is a
+// lower_bound on Bitrate with 0 meaning LP2.
+struct At3Container { unsigned bitrate; int frame_sz; int js; };
+const At3Container kAt3Containers[8] = {
+    {66150, 192, 1}, {93713, 272, 1}, {104738, 304, 0}, {132300, 384, 0},
+    {146081, 424, 0}, {176400, 512, 0}, {264600, 768, 0}, {352800, 1024, 0}};
+
+const At3Container* at3_container_for(unsigned bitrate)
+{
+    if (bitrate == 0) bitrate = 132300;
+    for (int i = 0; i < 8; i++)
+        if (!(kAt3Containers[i].bitrate < bitrate)) return &kAt3Containers[i];
+    return nullptr;                                   // past the end: the reference would read out of bounds
+}
+
+int build_at3_tables(atde_encoder* e)
+{
+    using namespace atde;
+    at3::DevTables* h = new (std::nothrow) at3::DevTables();
+    if (!h) return fail(ATDE_ERR_NOMEM, "host alloc");
+    memset(h, 0, sizeof(*h));
+    float qmf[48];
+    qmf_window(qmf);
+    // TAtrac3Data::TAtrac3Data (atrac3.h:178-198)
+    for (uint32_t i = 0; i < 64; i++) h->scale_table[i] = pow(2.0, (double)(i / 3.0 - 21.0));
+    for (int i = 0; i < 256; i++) h->encode_window[i] = (sin(((i + 0.5) / 256.0 - 0.5) * M_PI) + 1.0);
+    for (int i = 0; i < 16; i++) h->gain_level[i] = pow(2.0, 4 - i);
+    for (int i = 0; i < 31; i++) h->gain_interp[i] = pow(2.0, -1.0 / 8 * (i - 15));
+    const std::vector<float> curve = loudness_curve(1024);
+    memcpy(h->loud_curve, curve.data(), sizeof(h->loud_curve));
+    {   // TAtrac3BitStreamWriter ctor (atrac3_bitstream.cpp:705-717)
+        static const unsigned short start[33] = {
+            0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, 176,
+            192, 224, 256, 288, 320, 352, 384, 416, 448, 480, 512, 576, 640, 704, 768, 896, 1024};
+        const std::vector<float> ath = calc_ath(1024, 44100);
+        for (int b = 0; b < 32; b++) {
+            float x = 999;
+            for (size_t line = start[b]; line < start[b + 1]; line++) x = fmin(x, ath[line]);
+            x = pow(10, 0.1f * x);
+            h->ath[b] = x;
+        }
+    }
+    const std::vector<float> sc512 = mdct_sincos(512, 1);
+    memcpy(h->sincos512, sc512.data(), sizeof(h->sincos512));
+    const auto tw128 = kiss_twiddles(128, false);
+    memcpy(h->tw128, tw128.data(), sizeof(h->tw128));
+    const auto p128 = kiss_perm(128);
+    for (int i = 0; i < 128; i++) h->perm128[i] = (unsigned char)p128[i];
+    {   // TSpectralUpsampler(11025.0f, 800.0f, 0.15f) (transient_spectral_upsampler.cpp:32-69)
+        const float sampleRate = 11025.0f, lowCutHz = 800.0f, epsilon = 0.15f;
+        const int kInN = 512;
+        h->low_cut_bin = static_cast<int>(std::ceil(lowCutHz * kInN / sampleRate));
+        const float eN = epsilon * static_cast<float>(kInN);
+        const float fN = static_cast<float>(kInN);
+        for (int n = 0; n < kInN; ++n) {
+            const float fn = static_cast<float>(n);
+            if (n == 0) {
+                h->planck[n] = 0.0f;
+            } else if (fn < eN) {
+                const float Zp = eN * (1.0f / fn + 1.0f / (fn - eN));
+                h->planck[n] = 1.0f / (1.0f + std::exp(Zp));
+            } else if (fn <= fN - eN) {
+                h->planck[n] = 1.0f;
+            } else {
+                const float m = fN - fn;
+                const float Zp = eN * (1.0f / m + 1.0f / (m - eN));
+                h->planck[n] = 1.0f / (1.0f + std::exp(Zp));
+            }
+        }
+        for (int i = 1; i < 3; ++i)                                      // :110-111,152
+            h->hpf_h[i - 1] = 0.5f * (1.0f - std::cos(static_cast<float>(M_PI) * i / 2.0f));
+    }
+    const auto tw256 = kiss_twiddles(256, false);
+    memcpy(h->tw256, tw256.data(), sizeof(h->tw256));
+    const auto s512 = kiss_super_twiddles(512, false);
+    memcpy(h->super512, s512.data(), sizeof(h->super512));
+    const auto p256 = kiss_perm(256);
+    for (int i = 0; i < 256; i++) h->perm256[i] = (unsigned char)p256[i];
+    const auto tw2048 = kiss_twiddles(2048, true);
+    memcpy(h->tw2048, tw2048.data(), sizeof(h->tw2048));
+    const auto s4096 = kiss_super_twiddles(4096, true);
+    memcpy(h->super4096, s4096.data(), sizeof(h->super4096));
+    const auto p2048 = kiss_perm(2048);
+    for (int o = 0; o < 2048; o++) h->iperm2048[p2048[o]] = (unsigned short)o;
+
+    cudaError_t ce = cudaMalloc(&e->d_at3_tab, sizeof(at3::DevTables));
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->d_at3_tab, h, sizeof(at3::DevTables), cudaMemcpyHostToDevice);
+    delete h;
+    if (ce != cudaSuccess) return fail(ATDE_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(ce));
+    at3::upload_qmf_window(qmf);
     return 0;
 }
 
@@ -224,10 +332,92 @@ int run_at1(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
     return 0;
 }
 
+// Runs the ATRAC3 pipeline for S streams x N new frames whose PCM is at d_pcm (device); s0 = first
+// stream index inside the handle's state arrays; `started` says whether the streams carry a frame.
+int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, long long N, bool started,
+            unsigned char* d_out)
+{
+    using namespace atde::at3;
+    const int C = e->cfg.channels;
+    Geometry g;
+    g.S = S; g.C = C; g.N = (int)N;
+    g.L = (int)N + (started ? 1 : 0);
+    g.n_out = g.L - 1;
+    g.BL = 128 + 256 * g.L;
+    g.js = e->at3_js && C == 2;
+    g.frame_sz = e->unit_bytes;
+    g.no_gain = e->cfg.no_gain_control != 0;
+    g.no_tonal = e->cfg.no_tonal != 0;
+    g.bfu_idx_const = (int)e->cfg.bfu_idx_const;
+    const size_t units = (size_t)S * (size_t)(g.n_out > 0 ? g.n_out : 1) * C;
+    const size_t items = (size_t)S * C * kGainBands * (size_t)(g.n_out > 0 ? g.n_out : 1);
+    int rc;
+    if ((rc = w.bands.ensure((size_t)S * C * 4 * g.BL))) return rc;
+    if ((rc = w.hist_tmp.ensure((size_t)S * (2 * 1024 * C + C * 4 * 256 + C * 4)))) return rc;
+    if ((rc = w.specs.ensure(units * 1024))) return rc;
+    if ((rc = w.gscale.ensure(units * 16))) return rc;
+    if ((rc = w.chloud.ensure(units))) return rc;
+    if ((rc = w.loud.ensure((size_t)S * (g.n_out > 0 ? g.n_out : 1)))) return rc;
+    if ((rc = w.sfi.ensure(units * 32))) return rc;
+    if ((rc = w.energy.ensure(units * 32))) return rc;
+    if ((rc = w.tonal.ensure(units))) return rc;
+    if ((rc = w.curves.ensure((size_t)S * C * 4 * (g.n_out > 0 ? g.n_out : 1)))) return rc;
+    if (!g.no_gain) {
+        if ((rc = w.gain.ensure(items * 96))) return rc;
+        if ((rc = w.gstat.ensure(items * 4))) return rc;
+        if ((rc = w.gprev.ensure(items * 4))) return rc;
+    }
+    if (e->taps_enabled && (rc = w.tap_wl.ensure(units * 32))) return rc;
+
+    Buffers b;
+    memset(&b, 0, sizeof(b));
+    b.pcm = d_pcm;
+    b.started = e->started.p + s0;
+    b.hist_tmp = w.hist_tmp.p;
+    b.prevhalf_out = w.hist_tmp.p + (size_t)S * 2 * 1024 * C;
+    b.next_scale_out = b.prevhalf_out + (size_t)S * C * 4 * 256;
+    b.pcm_hist = e->hist.p + (size_t)s0 * 2 * 1024 * C;
+    b.prevhalf = e->prevhalf.p + (size_t)s0 * C * 4 * 256;
+    b.next_scale = e->next_scale.p + (size_t)s0 * C * 4;
+    b.ctx = e->ctx.p + (size_t)s0 * C * kGainBands * 4;
+    b.loud_state = e->loud_state.p + s0;
+    b.bands = w.bands.p; b.gain = w.gain.p; b.gstat = w.gstat.p; b.gprev = w.gprev.p;
+    b.curves = w.curves.p; b.specs = w.specs.p; b.gscale = w.gscale.p; b.chloud = w.chloud.p;
+    b.loud = w.loud.p; b.sfi = w.sfi.p; b.energy = w.energy.p; b.tonal = w.tonal.p;
+    b.out = d_out;
+    b.tap_prec = e->taps_enabled ? w.tap_wl.p : nullptr;
+    b.tab = e->d_at3_tab;
+
+    { KernelTimer kt(e, w.stream, 0); launch_qmf(g, b, w.stream); }
+    e->launches += 1;
+    if (g.n_out > 0) {
+        if (!g.no_gain) {
+            { KernelTimer kt(e, w.stream, 3); launch_gain_analysis(g, b, w.stream); }
+            { KernelTimer kt(e, w.stream, 4); launch_gain_scan(g, b, w.stream); launch_gain_curve(g, b, w.stream); }
+            e->launches += 3;
+        }
+        { KernelTimer kt(e, w.stream, 0); launch_mdct(g, b, w.stream); }
+        { KernelTimer kt(e, w.stream, 1); launch_loudness(g, b, w.stream); }
+        { KernelTimer kt(e, w.stream, 5); launch_scale_tonal(g, b, w.stream); }
+        { KernelTimer kt(e, w.stream, 2); launch_alloc_pack(g, b, w.stream); }
+        e->launches += 4;
+    }
+    launch_carry(g, b, w.stream);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 __global__ void init_state_kernel(float* loud, unsigned char* started, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { loud[i] = atde::at1::kLoudFactor; started[i] = 0; }
+}
+
+__global__ void fill_kernel(float* p, float v, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 int ensure_state(atde_encoder* e, int S)
@@ -237,11 +427,25 @@ int ensure_state(atde_encoder* e, int S)
         return fail(ATDE_ERR_INVALID, "batch has %d streams but the handle carries state for %d; call atde_reset() first", S, e->n_state_streams);
     int rc;
     const int C = e->cfg.channels;
-    if ((rc = e->hist.ensure((size_t)S * e->frame_samples * C))) return rc;
+    const bool at3 = e->cfg.codec == ATDE_CODEC_ATRAC3;
+    if ((rc = e->hist.ensure((size_t)S * e->frame_samples * C * (at3 ? 2 : 1)))) return rc;
     if ((rc = e->loud_state.ensure(S))) return rc;
     if ((rc = e->started.ensure(S))) return rc;
     ATDE_LAUNCH(init_state_kernel, (S + 255) / 256, 256, 0, e->ws[0].stream, e->loud_state.p, e->started.p, S);
     e->launches += 1;
+    if (at3) {
+        // PcmBuffer zero-initialised (delay_buffer.h:28-31), PrevOverlapGainScale = 1 (atrac3denc.cpp:100-101),
+        // CurveCtx = {} (atrac3denc.h:113)
+        const size_t nh = (size_t)S * C * 4 * 256, ns = (size_t)S * C * 4, nc = (size_t)S * C * atde::at3::kGainBands * 4;
+        if ((rc = e->prevhalf.ensure(nh))) return rc;
+        if ((rc = e->next_scale.ensure(ns))) return rc;
+        if ((rc = e->ctx.ensure(nc))) return rc;
+        CK(cudaMemsetAsync(e->prevhalf.p, 0, nh * sizeof(float), e->ws[0].stream));
+        CK(cudaMemsetAsync(e->ctx.p, 0, nc * sizeof(float), e->ws[0].stream));
+        ATDE_LAUNCH(fill_kernel, (unsigned)((ns + 255) / 256), 256, 0, e->ws[0].stream, e->next_scale.p, 1.0f, (long long)ns);
+        e->launches += 1;
+    }
+    e->streams_started = false;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->ws[0].stream));
     e->n_state_streams = S;
@@ -269,9 +473,18 @@ int atde_create(const atde_settings* s, atde_encoder** out)
     if (!s || !out) return fail(ATDE_ERR_INVALID, "null argument");
     *out = nullptr;
     if (s->channels < 1 || s->channels > 2) return fail(ATDE_ERR_INVALID, "channels must be 1 or 2");
-    if (s->codec != ATDE_CODEC_ATRAC1)
+    if (s->codec != ATDE_CODEC_ATRAC1 && s->codec != ATDE_CODEC_ATRAC3)
         return fail(ATDE_ERR_UNSUPPORTED, "codec %d is not built yet", s->codec);
-    if (s->bfu_idx_const > 8) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..8");
+    const At3Container* cont = nullptr;
+    if (s->codec == ATDE_CODEC_ATRAC1) {
+        if (s->bfu_idx_const > 8) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..8");
+    } else {
+        if (s->bfu_idx_const > 32) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..32");
+        cont = at3_container_for(s->bitrate);
+        if (!cont) return fail(ATDE_ERR_INVALID, "bitrate %u is above the largest ATRAC3 container (352800)", s->bitrate);
+        if (cont->js && s->channels == 1)
+            return fail(ATDE_ERR_UNSUPPORTED, "joint-stereo containers with mono input are not built yet");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(ATDE_ERR_CUDA, "no CUDA device: libatde_b200 has no CPU fallback");
@@ -279,15 +492,23 @@ int atde_create(const atde_settings* s, atde_encoder** out)
     atde_encoder* e = new (std::nothrow) atde_encoder();
     if (!e) return fail(ATDE_ERR_NOMEM, "host alloc");
     e->cfg = *s;
-    e->frame_samples = 512;
-    e->units_per_frame = s->channels;
-    e->unit_bytes = atde::at1::kUnitBytes;
-    e->lookahead = 0;
+    if (s->codec == ATDE_CODEC_ATRAC1) {
+        e->frame_samples = 512;
+        e->units_per_frame = s->channels;
+        e->unit_bytes = atde::at1::kUnitBytes;
+        e->lookahead = 0;
+    } else {
+        e->frame_samples = 1024;
+        e->units_per_frame = 1;
+        e->unit_bytes = cont->frame_sz;
+        e->lookahead = 1;
+        e->at3_js = cont->js;
+    }
     for (int i = 0; i < 2; i++) {
         cudaError_t ce = cudaStreamCreateWithFlags(&e->ws[i].stream, cudaStreamNonBlocking);
         if (ce != cudaSuccess) { delete e; return fail(ATDE_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
     }
-    int rc = build_at1_tables(e);
+    int rc = s->codec == ATDE_CODEC_ATRAC1 ? build_at1_tables(e) : build_at3_tables(e);
     if (rc) { atde_destroy(e); return rc; }
     *out = e;
     return 0;
@@ -303,7 +524,9 @@ void atde_destroy(atde_encoder* e)
         if (e->ws[i].stream) cudaStreamDestroy(e->ws[i].stream);
     }
     e->hist.release(); e->loud_state.release(); e->started.release();
+    e->prevhalf.release(); e->next_scale.release(); e->ctx.release();
     if (e->d_at1_tab) cudaFree(e->d_at1_tab);
+    if (e->d_at3_tab) cudaFree(e->d_at3_tab);
     for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     delete e;
 }
@@ -322,7 +545,15 @@ int atde_reset(atde_encoder* e)
     CK(cudaDeviceSynchronize());
     e->have_state = false;
     e->n_state_streams = 0;
+    e->streams_started = false;
     return 0;
+}
+
+int64_t atde_output_frames(const atde_encoder* e, int64_t n_frames)
+{
+    if (!e || n_frames < 0) return ATDE_ERR_INVALID;
+    if (e->lookahead && !(e->have_state && e->streams_started)) return n_frames > 0 ? n_frames - 1 : 0;
+    return n_frames;
 }
 
 int atde_sync(atde_encoder* e)
@@ -343,7 +574,17 @@ int atde_encode_batch_device(atde_encoder* e, const float* d_pcm, int32_t S, int
     int rc = ensure_state(e, S);
     if (rc) return rc;
     e->last_S = S; e->last_F = F;
-    return run_at1(e, e->ws[0], d_pcm, 0, S, F, d_out, d_sizes);
+    if (e->cfg.codec == ATDE_CODEC_ATRAC3) {
+        const bool started = e->streams_started;
+        e->last_out = F - (started ? 0 : 1);
+        rc = run_at3(e, e->ws[0], d_pcm, 0, S, F, started, d_out);
+        if (!rc) e->streams_started = true;
+        return rc;
+    }
+    e->last_out = F;
+    rc = run_at1(e, e->ws[0], d_pcm, 0, S, F, d_out, d_sizes);
+    if (!rc) e->streams_started = true;
+    return rc;
 }
 
 int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
@@ -356,9 +597,13 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
     if (rc) return rc;
     e->last_S = S; e->last_F = F;
     const int C = e->cfg.channels;
+    const bool at3 = e->cfg.codec == ATDE_CODEC_ATRAC3;
+    const bool started = e->streams_started;
+    const long long n_out = F - ((at3 && !started) ? 1 : 0);
+    e->last_out = n_out;
     const size_t pcm_per_stream = (size_t)F * e->frame_samples * C;            // floats
-    const size_t out_per_stream = (size_t)F * e->units_per_frame * e->unit_bytes;
-    const size_t units_per_stream = (size_t)F * e->units_per_frame;
+    const size_t out_per_stream = (size_t)n_out * e->units_per_frame * e->unit_bytes;
+    const size_t units_per_stream = (size_t)n_out * e->units_per_frame;
     // chunk by streams so H2D of chunk k+1 overlaps compute of chunk k (two pipeline slots)
     const size_t target_floats = (size_t)48 << 20;                              // ~192 MiB of PCM per chunk
     int chunk = (int)(target_floats / pcm_per_stream);
@@ -369,19 +614,25 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
         const int n = (S - s0 < chunk) ? S - s0 : chunk;
         Workspace& w = e->ws[slot];
         if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) return rc;
-        if ((rc = w.out.ensure((size_t)n * out_per_stream))) return rc;
+        if ((rc = w.out.ensure((size_t)n * out_per_stream + 1))) return rc;
         if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return rc;
         CK(cudaMemcpyAsync(w.pcm.p, pcm + (size_t)s0 * pcm_per_stream, (size_t)n * pcm_per_stream * sizeof(float),
                            cudaMemcpyHostToDevice, w.stream));
-        if ((rc = run_at1(e, w, w.pcm.p, s0, n, F, w.out.p, sizes ? w.sizes.p : nullptr))) return rc;
-        CK(cudaMemcpyAsync(out + (size_t)s0 * out_per_stream, w.out.p, (size_t)n * out_per_stream,
-                           cudaMemcpyDeviceToHost, w.stream));
-        if (sizes)
+        if (at3) rc = run_at3(e, w, w.pcm.p, s0, n, F, started, w.out.p);
+        else rc = run_at1(e, w, w.pcm.p, s0, n, F, w.out.p, sizes ? w.sizes.p : nullptr);
+        if (rc) return rc;
+        if (out_per_stream)
+            CK(cudaMemcpyAsync(out + (size_t)s0 * out_per_stream, w.out.p, (size_t)n * out_per_stream,
+                               cudaMemcpyDeviceToHost, w.stream));
+        if (sizes && !at3)
             CK(cudaMemcpyAsync(sizes + (size_t)s0 * units_per_stream, w.sizes.p, (size_t)n * units_per_stream * sizeof(int),
                                cudaMemcpyDeviceToHost, w.stream));
     }
     CK(cudaStreamSynchronize(e->ws[0].stream));
     CK(cudaStreamSynchronize(e->ws[1].stream));
+    if (sizes && at3)                                  // every WriteFrame payload is exactly FrameSz bytes
+        for (size_t i = 0; i < (size_t)S * units_per_stream; i++) sizes[i] = e->unit_bytes;
+    e->streams_started = true;
     return 0;
 }
 
@@ -412,10 +663,28 @@ int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* dst, size_t capacity
 {
     if (!e || !dst) return fail(ATDE_ERR_INVALID, "null argument");
     if (what == 0) { e->taps_enabled = true; return 0; }      // arm taps for following batches
-    const size_t units = (size_t)e->last_S * e->last_F * e->cfg.channels;
+    const bool at3 = e->cfg.codec == ATDE_CODEC_ATRAC3;
+    const size_t units = (size_t)e->last_S * e->last_out * e->cfg.channels;
     const Workspace& w = e->ws[0];
     const void* src = nullptr;
     size_t bytes = 0;
+    if (at3) {
+        const size_t L = (size_t)e->last_out + 1;
+        switch (what) {
+            case ATDE_TAP_SPECS: src = w.specs.p; bytes = units * 1024 * sizeof(float); break;      // scaled values
+            case ATDE_TAP_CHLOUD: src = w.chloud.p; bytes = units * sizeof(float); break;
+            case ATDE_TAP_LOUDNESS: src = w.loud.p; bytes = (size_t)e->last_S * e->last_out * sizeof(float); break;
+            case ATDE_TAP_SFI: src = w.sfi.p; bytes = units * 32; break;
+            case ATDE_TAP_WORDLEN: src = w.tap_wl.p; bytes = units * 32; break;
+            case ATDE_TAP_BANDS: src = w.bands.p; bytes = (size_t)e->last_S * e->cfg.channels * 4 * (128 + 256 * L) * sizeof(float); break;
+            case ATDE_TAP_CURVES: src = w.curves.p; bytes = (size_t)e->last_S * e->cfg.channels * 4 * e->last_out * sizeof(atde::at3::Curve); break;
+            case ATDE_TAP_GSCALE: src = w.gscale.p; bytes = units * 16 * sizeof(float); break;
+            case ATDE_TAP_ENERGY: src = w.energy.p; bytes = units * 32 * sizeof(float); break;
+            case ATDE_TAP_TONAL: src = w.tonal.p; bytes = units * sizeof(atde::at3::TonalList); break;
+            case ATDE_TAP_GAIN: src = w.gain.p; bytes = (size_t)e->last_S * e->cfg.channels * 3 * e->last_out * 96 * sizeof(float); break;
+            default: return fail(ATDE_ERR_INVALID, "unknown tap %d", what);
+        }
+    } else
     switch (what) {
         case ATDE_TAP_SPECS: src = w.specs.p; bytes = units * e->frame_samples * sizeof(float); break;
         case ATDE_TAP_MASKS: src = w.masks.p; bytes = units; break;

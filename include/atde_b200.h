@@ -76,6 +76,10 @@ int atde_frame_samples(const atde_encoder* e);     /* sample-frames per lambda c
 int atde_units_per_frame(const atde_encoder* e);   /* WriteFrame calls per lambda call: ATRAC1 = channels, ATRAC3 = 1 */
 int atde_unit_bytes(const atde_encoder* e);        /* bytes stored per unit in `out` (container frame size) */
 int atde_lookahead_frames(const atde_encoder* e);  /* lambda calls that return LOOK_AHEAD before output starts (0 / 1) */
+/* Output frames per stream the NEXT batch of n_frames input frames will produce: n_frames, except
+ * that the first batch of an ATRAC3 stream yields n_frames - 1 (the reference's first lambda call
+ * only fills the look-ahead buffer and returns LOOK_AHEAD, src/atrac3denc.cpp:715-718). */
+int64_t atde_output_frames(const atde_encoder* e, int64_t n_frames);
 
 /*
  * Encode S streams x F frames from HOST memory (the reference-facing path: copies in, kernels,
@@ -83,7 +87,7 @@ int atde_lookahead_frames(const atde_encoder* e);  /* lambda calls that return L
  *   pcm   [S][F*frame_samples][channels] interleaved normalised float32 — the memory layout the
  *         reference lambda receives (data[i*Channels + ch], src/atrac1denc.cpp:206-209), one
  *         stream after another.
- *   out   [S][F][units_per_frame][unit_bytes]; each unit is the WriteFrame payload zero-padded or
+ *   out   [S][Fo][units_per_frame][unit_bytes], Fo = atde_output_frames(e, F); each unit is the WriteFrame payload zero-padded or
  *         truncated to the container frame size exactly as TAeaOutput/TRaw do (src/aea.cpp:182,
  *         src/raw.cpp:41-43).
  *   sizes optional [S][F][units_per_frame]: true payload length (std::vector<char>::size()) of
@@ -112,7 +116,8 @@ int64_t atde_launch_count(const atde_encoder* e);
 /* Per-kernel device timing.  With profiling on, every kernel launch of the handle is bracketed by
  * CUDA events on its stream; atde_kernel_times() synchronises, returns the summed milliseconds
  * and launch counts per kernel kind since the last query and clears them.
- * Kinds: 0 = QMF+MDCT analysis, 1 = loudness scan, 2 = scale/allocate/quantise/pack. */
+ * Kinds: 0 = QMF+MDCT analysis, 1 = loudness scan, 2 = (scale/)allocate/quantise/pack,
+ *        ATRAC3 only: 3 = gain-control envelope analysis, 4 = gain curve scan + build, 5 = tonal + scale. */
 int atde_set_profiling(atde_encoder* e, int32_t on);
 int atde_kernel_times(atde_encoder* e, double* ms_sum, int64_t* count, int32_t n_kinds);
 
@@ -123,7 +128,14 @@ typedef enum {
     ATDE_TAP_CHLOUD = 3,    /* float  [S][F][C] per-channel loudness term */
     ATDE_TAP_LOUDNESS = 4,  /* float  [S][F] tracked loudness */
     ATDE_TAP_SFI = 5,       /* uint8  [S][F][C][52|32] scale factor indices */
-    ATDE_TAP_WORDLEN = 6    /* uint8  [S][F][C][52|32] word lengths / precisions */
+    ATDE_TAP_WORDLEN = 6,   /* uint8  [S][F][C][52|32] word lengths / precisions (0xff beyond the coded BFUs) */
+    /* ATRAC3 only (F = output frames of the batch) */
+    ATDE_TAP_BANDS = 7,     /* float  [S][C][4][128 + 256*(F+1)] QMF bands incl. look-ahead frame (M/S when joint stereo) */
+    ATDE_TAP_CURVES = 8,    /* 16-byte records [S][C][4][F]: n, level[7], loc[7], pad */
+    ATDE_TAP_GSCALE = 9,    /* float  [S][F][C][4][4] PrevHalf, CurHalf, Frame, NextOverlapScale */
+    ATDE_TAP_ENERGY = 10,   /* float  [S][F][C][32] BFU energies */
+    ATDE_TAP_TONAL = 11,    /* tonal block lists [S][F][C] (at3_kernels.cuh: TonalList) */
+    ATDE_TAP_GAIN = 12      /* float  [S][C][3][F][96] sub-frame envelope: gain, low, high */
 } atde_tap;
 int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* host_dst, size_t capacity);
 

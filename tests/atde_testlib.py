@@ -172,3 +172,31 @@ def config1_sine():
     """BASELINE.json configs[0]: 1 s mono 44.1 kHz 1 kHz sine at 0.5 FS, int16-quantised."""
     n = np.arange(44100)
     return quantise(0.5 * np.sin(2 * np.pi * 1000 * n / 44100))
+
+
+# ---------------------------------------------------------------------------------------------
+# ATRAC3 reference taps (oracle/ref_harness_at3.cpp)
+AT3_REC = np.dtype([
+    ("loud_term", np.float32), ("gscale", np.float32, (4, 3)), ("n_points", np.int32, (4,)),
+    ("points", np.int32, (4, 8, 2)), ("sfi", np.int32, (32,)), ("energy", np.float32, (32,)),
+    ("n_tonal", np.int32), ("tonal", np.int32, (64, 4)), ("bands", np.float32, (4, 256)),
+])
+
+
+def ref_at3_stages(channels, pcm, bitrate_kbit=0, no_gain=0, no_tonal=0):
+    """Drives the reference TAtrac3Encoder frame by frame.  Returns (recs[Fo][C], tracked[Fo], frames[Fo][FrameSz])."""
+    lib = ref_lib()
+    assert lib.ref_at3_rec_size() == AT3_REC.itemsize
+    lib.ref_at3_stages.restype = ctypes.c_long
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    F = pcm.size // channels // 1024
+    recs = np.zeros((F, channels), AT3_REC)
+    tracked = np.zeros(F, np.float32)
+    out = np.zeros(F * 1024, np.uint8)
+    nb = ctypes.c_long()
+    k = lib.ref_at3_stages(channels, pcm.ctypes.data_as(P), ctypes.c_long(F), bitrate_kbit, no_gain, no_tonal,
+                           recs.ctypes.data_as(P), tracked.ctypes.data_as(P), out.ctypes.data_as(P),
+                           ctypes.c_long(out.size), ctypes.byref(nb))
+    assert k == F - 1 and nb.value > 0
+    fs = nb.value // k
+    return recs[:k], tracked[:k], out[:nb.value].reshape(k, fs)

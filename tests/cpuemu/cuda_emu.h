@@ -131,6 +131,14 @@ inline int __reduce_add_sync(unsigned m, int v) { return (int)__reduce_add_sync(
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 
+// CUDA's integer min/max overloads
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+
 // ---- arithmetic intrinsics (host FP environment is round-to-nearest, no FMA contraction: the
 // emu build uses -ffp-contract=off and no -march) ----
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }

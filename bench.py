@@ -30,10 +30,22 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 WORKLOADS = {
     # name: (codec id, frame samples, S, F, units/frame, unit bytes, algorithmic QMF+MDCT bytes per stereo frame)
-    "atrac1_stereo_1e6": dict(codec=1, step=512, S=1024, F=977, alg_bytes=8192,
+    "atrac1_stereo_1e6": dict(codec=1, step=512, S=1024, F=977, alg_bytes=8192, kbit=0,
+                              kernel="at1_analysis_kernel (QMF+transient+MDCT)",
+                              settings="reference defaults (EWM_AUTO, bfuidxconst 0)",
                               desc="ATRAC1 encode, 10^6-frame synthetic stereo batch (BASELINE.json configs[1])"),
+    "atrac3_lp2_stereo_1e6": dict(codec=3, step=1024, S=1024, F=977, alg_bytes=16384, kbit=0,
+                                  kernel="at3_qmf_kernel + at3_mdct_kernel (QMF tree, gain modulation, MDCT-512 x4)",
+                                  settings="reference defaults: LP2 132300 bit/s, gain control + tonal components on",
+                                  desc="ATRAC3 LP2 (132 kbps) encode, 10^6-frame synthetic stereo batch (BASELINE.json configs[2])"),
+    "atrac3_lp4_stereo_1p25e6": dict(codec=3, step=1024, S=1024, F=1221, alg_bytes=16384, kbit=64,
+                                     kernel="at3_qmf_kernel + at3_mdct_kernel (QMF tree, M/S, gain modulation, MDCT-512 x4)",
+                                     settings="LP4 66150 bit/s joint stereo, gain control + tonal components on",
+                                     desc="ATRAC3 LP4 (66 kbps, joint-stereo) encode, 1.25*10^6 frames per GPU "
+                                          "(BASELINE.json configs[3] is this shard on each of 8 GPUs)"),
 }
-DEFAULT_WORKLOAD = "atrac1_stereo_1e6"
+DEFAULT_WORKLOAD = "atrac3_lp2_stereo_1e6"
+KIND_NAMES = ["qmf_mdct", "loudness_scan", "alloc_quant_pack", "gain_envelope", "gain_curve", "tonal_scale"]
 METRIC = "ATRAC3 stereo frames/s at 1/2/4/8 B200; QMF+MDCT achieved HBM GB/s vs peak"
 
 
@@ -119,14 +131,14 @@ def gen_pcm_device(torch, S, F, step, C, rank):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own encoder (oracle/_ref) on the host cores
 def _cpu_worker(args):
-    codec, C, step, F, n_streams, seed, use_ref = args
+    codec, C, step, F, n_streams, seed, use_ref, kbit = args
     import numpy as np
     import atde_testlib as tl
     pcm = tl.synth_streams(n_streams, F, step, C, seed=seed)
     t0 = time.perf_counter()
     for s in range(n_streams):
         if use_ref:
-            tl.ref_encode(codec, C, pcm[s].reshape(-1))
+            tl.ref_encode(codec, C, pcm[s].reshape(-1), bitrate_kbit=kbit)
         else:
             tl.port_at1_encode(C, pcm[s].reshape(-1))
     return time.perf_counter() - t0, n_streams * F
@@ -139,7 +151,9 @@ def cpu_reference_rate(wl, streams_per_core=8, frames=977):
     import atde_testlib as tl
     use_ref = tl.ref_lib() is not None
     cores = os.cpu_count() or 1
-    jobs = [(wl["codec"], 2, wl["step"], frames, streams_per_core, 1000 + i, use_ref) for i in range(cores)]
+    if not use_ref and wl["codec"] != 1:
+        raise SystemExit("bench.py: the ATRAC3 CPU arm needs oracle/_ref (the reference build); it did not travel")
+    jobs = [(wl["codec"], 2, wl["step"], frames, streams_per_core, 1000 + i, use_ref, wl["kbit"]) for i in range(cores)]
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -160,7 +174,7 @@ def run_reference_arm(args):
     wl = WORKLOADS[args.workload]
     rates = []
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_rate(wl, streams_per_core=4, frames=wl["F"])
+        r = cpu_reference_rate(wl, streams_per_core=4 if wl["codec"] == 1 else 2, frames=wl["F"])
         if i >= args.warmup:
             rates.append(r)
     value = sum(r["value"] for r in rates) / len(rates)
@@ -197,7 +211,7 @@ def run_ours(args):
 
     wl = WORKLOADS[args.workload]
     S, F, step, C = args.streams or wl["S"], args.frames or wl["F"], wl["step"], 2
-    enc = ab.Encoder(wl["codec"], C, device=local)
+    enc = ab.Encoder(wl["codec"], C, bitrate=wl["kbit"] * 1024, device=local)
     units, ub = enc.units_per_frame, enc.unit_bytes
     d_pcm = gen_pcm_device(torch, S, F, step, C, rank)
     d_out = torch.empty((S, F, units, ub), dtype=torch.uint8, device="cuda")
@@ -225,7 +239,7 @@ def run_ours(args):
     enc.sync()
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    kms, kcnt = enc.kernel_times(3)
+    kms, kcnt = enc.kernel_times(6)
     enc.set_profiling(False)
     launches = enc.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -241,7 +255,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     host_ms = (time.perf_counter() - t0) * 1000.0
     barrier()
-    same = bool(torch.equal(h_out[:4], d_out[:4].cpu())) if args.steps else True
+    # host and device entry points must agree byte for byte from the same (fresh) stream state
+    enc.reset()
+    fo = enc.output_frames(F)
+    enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
+    enc.sync()
+    dev_bytes = d_out.view(-1)[: S * fo * units * ub].cpu()
+    enc.reset()
+    enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
+    same = bool(torch.equal(h_out.view(-1)[: S * fo * units * ub], dev_bytes))
 
     t = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -253,11 +275,11 @@ def run_ours(args):
         value = frames_total * args.steps / (dev_ms / 1000.0)
         e2e = frames_total * args.steps / (host_ms / 1000.0)
         peak, peak_kind = read_peak()
-        k1_ms = kms[0] / max(1, kcnt[0])
+        k1_ms = kms[0] / max(1, args.steps)          # per step: ATRAC3 launches two kernels of kind 0 (QMF, MDCT)
         alg_bytes = wl["alg_bytes"] * S * F
         achieved = alg_bytes / (k1_ms / 1000.0) / 1e9 if k1_ms > 0 else None
         traffic = None
-        tp = ROOT / "profiles" / "k1_traffic.json"
+        tp = ROOT / "profiles" / f"traffic_{args.workload}.json"
         if tp.exists():
             try:
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
@@ -270,13 +292,13 @@ def run_ours(args):
             "config": {"workload": wl["desc"], "streams_per_gpu": S, "frames_per_stream": F, "channels": C,
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                        "l2_policy": f"inputs larger than L2 ({S * F * step * C * 4 / 2**20:.0f} MiB PCM per step)",
-                       "settings": "reference defaults (EWM_AUTO, bfuidxconst 0)"},
+                       "settings": wl["settings"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "at1_analysis_kernel (QMF+transient+MDCT)", "peak_source": f"of {peak_kind}",
+                         "kernel": wl["kernel"], "peak_source": f"of {peak_kind}",
                          "kernel_ms": k1_ms, "alg_bytes_per_launch": alg_bytes,
                          "kernel_share_of_step": (kms[0] / dev_ms) if dev_ms else None,
-                         "other_kernels_ms": {"loudness_scan": kms[1] / max(1, kcnt[1]), "scale_alloc_pack": kms[2] / max(1, kcnt[2])}},
+                         "kernels_ms_per_step": {KIND_NAMES[k]: kms[k] / max(1, args.steps) for k in range(6) if kcnt[k]}},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": S * F * step * C * 4,
                     "d2h_bytes_per_step": S * F * units * ub, "ms_per_step": host_ms / args.steps,
                     "host_and_device_outputs_equal": same},
@@ -284,7 +306,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_rate(wl)
+            line["cpu_baseline"] = cpu_reference_rate(wl, streams_per_core=8 if wl["codec"] == 1 else 4)
         print(json.dumps(line), flush=True)
     enc.close()
     if world > 1:

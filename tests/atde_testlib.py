@@ -200,3 +200,39 @@ def ref_at3_stages(channels, pcm, bitrate_kbit=0, no_gain=0, no_tonal=0):
     assert k == F - 1 and nb.value > 0
     fs = nb.value // k
     return recs[:k], tracked[:k], out[:nb.value].reshape(k, fs)
+
+
+def synth_rich(n_frames, frame_samples, channels, seed=1, kind="mix"):
+    """One stream [n][C] of harder material than synth_streams: strong pure tones (tonal-component
+    extraction), amplitude steps and clicks (gain control), silence gaps, near-full-scale passages."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    n = n_frames * frame_samples
+    t = np.arange(n, dtype=np.float64)
+    x = np.zeros((n, channels))
+    if kind == "tones":
+        for c in range(channels):
+            for k in range(4):
+                f = rng.uniform(1500, 14000)
+                x[:, c] += rng.uniform(0.05, 0.2) * np.sin(2 * np.pi * f * t / 44100 + rng.uniform(0, 6))
+            x[:, c] += 1e-4 * rng.uniform(-1, 1, n)
+    elif kind == "steps":
+        env = np.ones(n)
+        for k in range(0, n, frame_samples * 3):
+            env[k + rng.integers(0, frame_samples):] *= rng.choice([0.05, 0.2, 4.0, 12.0])
+            env = np.clip(env, 1e-3, 30)
+        for c in range(channels):
+            x[:, c] = 0.02 * env * (rng.uniform(-1, 1, n) + np.sin(2 * np.pi * 3000 * t / 44100 + c))
+    else:
+        for c in range(channels):
+            x[:, c] = 0.02 * rng.uniform(-1, 1, n)
+            for k in range(3):
+                f = rng.uniform(200, 12000)
+                x[:, c] += rng.uniform(0.01, 0.25) * np.sin(2 * np.pi * f * t / 44100 + rng.uniform(0, 6))
+        for k in range(0, n_frames, 5):
+            p = k * frame_samples + int(rng.integers(0, frame_samples))
+            x[p:p + 200] += 0.5 * rng.uniform(-1, 1, (min(200, n - p), channels))
+        for k in range(3, n_frames, 11):
+            x[k * frame_samples:(k + 1) * frame_samples] = 0
+        if channels == 2:
+            x[n // 2:, 1] = 0.9 * x[n // 2:, 0] + 0.01 * rng.uniform(-1, 1, n - n // 2)   # correlated half: M/S budget shift
+    return quantise(np.clip(x, -1, 1))

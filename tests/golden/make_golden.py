@@ -35,6 +35,17 @@ def main():
     np.savez_compressed(HERE / "at1_stereo_bursts.npz", pcm=x, units=np.stack(units), sizes=np.stack(sizes),
                         masks=np.stack(masks))
     print("stereo bursts:", np.stack(units).shape, "short-window frames:", int((np.stack(masks) != 0).sum()))
+    # ATRAC3 LP2 (132 kbit/s) and LP4 (66 kbit/s joint stereo): tones (tonal components), level steps
+    # and clicks (gain control), noise; frames straight from TAtrac3Encoder's lambda.  PCM stored as
+    # the int16 it was quantised from.
+    for name, kbit in (("at3_lp2_stereo.npz", 0), ("at3_lp4_js_stereo.npz", 64)):
+        F, C = 24, 2
+        xs = np.stack([tl.synth_rich(F, 1024, C, seed=0xA7AC + i, kind=k) for i, k in enumerate(("mix", "tones", "steps"))])
+        frames = np.stack([tl.ref_at3_stages(C, x.reshape(-1), kbit)[2] for x in xs])
+        pcm16 = np.rint(xs * 32768).astype(np.int16)
+        assert np.array_equal(pcm16.astype(np.float32) / np.float32(32768), xs)
+        np.savez_compressed(HERE / name, pcm=pcm16, frames=frames, kbit=kbit)
+        print(name, frames.shape)
 
 
 if __name__ == "__main__":

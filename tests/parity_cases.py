@@ -165,3 +165,189 @@ def check_errors(lib):
         ab.Encoder(ab.CODEC_ATRAC1, 3, lib=lib)
     with pytest.raises(ab.AtdeError):
         ab.Encoder(99, 2, lib=lib)
+
+
+# =================================================================================================
+# ATRAC3 (LP2 / LP4).  Oracle = the reference encoder itself (oracle/_ref, driven frame by frame
+# through TAtrac3Encoder::GetLambda by oracle/ref_harness_at3.cpp); where it did not travel, the
+# committed fixtures under tests/golden/ (generated from it by make_golden.py) are the pin.
+def oracle_at3(C, pcm_stream, kbit=0, no_gain=0, no_tonal=0):
+    """Reference frames [Fo][FrameSz] for one stream, or None without oracle/_ref."""
+    if tl.ref_lib() is None:
+        return None
+    return tl.ref_at3_stages(C, pcm_stream, kbit, no_gain, no_tonal)[2]
+
+
+def _at3_enc(lib, C, kbit=0, no_gain=0, no_tonal=0, **kw):
+    return ab.Encoder(ab.CODEC_ATRAC3, C, bitrate=kbit * 1024, no_gain_control=bool(no_gain),
+                      no_tonal=bool(no_tonal), lib=lib, **kw)
+
+
+def check_at3_golden(lib, name, max_frames=None):
+    g = np.load(GOLDEN / name)
+    pcm = g["pcm"].astype(np.float32) / np.float32(32768)            # stored as int16
+    frames, kbit = g["frames"], int(g["kbit"])
+    S, F, C = pcm.shape[0], pcm.shape[1] // 1024, pcm.shape[2]
+    if max_frames:
+        F = min(F, max_frames)
+        pcm = pcm[:, :F * 1024]
+    enc = _at3_enc(lib, C, kbit)
+    out = enc.encode(pcm, S)
+    enc.close()
+    assert out.shape == (S, F - 1, 1, frames.shape[-1])
+    bad = np.argwhere((out[:, :, 0] != frames[:, :F - 1]).any(-1))
+    assert bad.size == 0, f"first differing (stream, frame) = {bad[:4].tolist()}"
+
+
+def check_at3_vs_oracle(lib, S, F, C, kbit=0, seed=1, kinds=("mix", "tones", "steps", None), **flags):
+    """Bit-exact frames for S streams of mixed material against the reference."""
+    streams = []
+    for s in range(S):
+        kind = kinds[s % len(kinds)]
+        streams.append(tl.synth_streams(1, F, 1024, C, seed=seed + s)[0] if kind is None
+                       else tl.synth_rich(F, 1024, C, seed=seed + s, kind=kind))
+    pcm = np.stack(streams)
+    enc = _at3_enc(lib, C, kbit, **flags)
+    out = enc.encode(pcm, S)
+    enc.close()
+    checked = 0
+    for s in range(S):
+        want = oracle_at3(C, pcm[s].reshape(-1), kbit, **flags)
+        if want is None:
+            continue
+        bad = np.argwhere((out[s, :, 0] != want).any(-1))
+        assert bad.size == 0, f"stream {s} ({kinds[s % len(kinds)]}): first differing frames {bad[:4, 0].tolist()}"
+        checked += 1
+    return checked
+
+
+def check_at3_stage_taps(lib, C=2, F=12, kbit=0, seed=21, kind="mix"):
+    """Intermediates against the reference's own sub-objects (needs oracle/_ref)."""
+    if tl.ref_lib() is None:
+        return False
+    pcm = tl.synth_rich(F, 1024, C, seed=seed, kind=kind)[None]
+    recs, tracked, frames = tl.ref_at3_stages(C, pcm[0].reshape(-1), kbit)
+    Fo = F - 1
+    enc = _at3_enc(lib, C, kbit)
+    enc.arm_taps()
+    out = enc.encode(pcm, 1)
+    if kbit != 64:          # bands are tapped before matrixing in the reference, after it here
+        bands = enc.tap(ab.TAP_BANDS, (1, C, 4, 128 + 256 * F), np.float32)
+        mine = bands[0][:, :, 128:128 + 256 * Fo].reshape(C, 4, Fo, 256).transpose(2, 0, 1, 3)
+        assert np.array_equal(recs["bands"].view(np.uint32), mine.view(np.uint32))
+    curves = enc.tap(ab.TAP_CURVES, (1, C, 4, Fo, 16), np.uint8)
+    for f in range(Fo):
+        for c in range(C):
+            for b in range(3):
+                n = int(recs[f, c]["n_points"][b])
+                ref_pts = [tuple(int(v) for v in recs[f, c]["points"][b, i]) for i in range(n)]
+                m = curves[0, c, b, f]
+                assert ref_pts == [(int(m[1 + i]), int(m[8 + i])) for i in range(int(m[0]))], (f, c, b)
+            assert int(recs[f, c]["n_points"][3]) == 0
+    gs = enc.tap(ab.TAP_GSCALE, (1, Fo, C, 4, 4), np.float32)
+    assert np.array_equal(recs["gscale"].view(np.uint32), gs[0][..., :3].view(np.uint32))
+    chl = enc.tap(ab.TAP_CHLOUD, (1, Fo, C), np.float32)
+    assert np.array_equal(recs["loud_term"].view(np.uint32), chl[0].view(np.uint32))
+    loud = enc.tap(ab.TAP_LOUDNESS, (1, Fo), np.float32)
+    assert np.array_equal(tracked.view(np.uint32), loud[0].view(np.uint32))
+    sfi = enc.tap(ab.TAP_SFI, (1, Fo, C, 32), np.uint8)
+    assert np.array_equal(recs["sfi"], sfi[0].astype(np.int32))
+    en = enc.tap(ab.TAP_ENERGY, (1, Fo, C, 32), np.float32)
+    assert np.array_equal(recs["energy"].view(np.uint32), en[0].view(np.uint32))
+    enc.close()
+    assert np.array_equal(out[0, :, 0], frames)
+    return True
+
+
+def check_at3_main_loop(lib, C=2, kbit=0, seconds=0.4):
+    """Through src/main.cpp's PCM pump (TPCMEngine(4096) + look-ahead): the frames the reference CLI
+    would hand to WriteFrame for a WAV of `seconds`, against ours on the frames the lambda received."""
+    if tl.ref_lib() is None:
+        return False
+    n = int(44100 * seconds)
+    pcm = tl.synth_rich((n + 1023) // 1024, 1024, C, seed=31)[:n]
+    payload, sizes = tl.ref_encode(3, C, pcm.reshape(-1), total=n, bitrate_kbit=kbit)
+    fs = int(sizes[0])
+    assert (sizes == fs).all()
+    want = payload.reshape(-1, fs)
+    view = tl.engine_view(pcm, C, 1024, total=n)
+    enc = _at3_enc(lib, C, kbit)
+    out = enc.encode(view, 1)
+    enc.close()
+    assert out.shape[1] == want.shape[0]
+    assert np.array_equal(out[0, :, 0], want)
+    return True
+
+
+def check_at3_batch_split_invariance(lib, S=2, F=13, C=2, kbit=0, cuts=(4, 5)):
+    """Streams continue across calls: [0,a) + [a,b) + [b,F) must equal one batch of F frames
+    (carried look-ahead frame, MDCT half, PrevOverlapGainScale, CurveCtx, loudness)."""
+    pcm = np.stack([tl.synth_rich(F, 1024, C, seed=40 + s, kind=("steps", "mix")[s % 2]) for s in range(S)])
+    enc = _at3_enc(lib, C, kbit)
+    whole = enc.encode(pcm, S)
+    enc.reset()
+    a, b = cuts[0], cuts[0] + cuts[1]
+    parts = [enc.encode(pcm[:, :a * 1024], S), enc.encode(pcm[:, a * 1024:b * 1024], S), enc.encode(pcm[:, b * 1024:], S)]
+    enc.close()
+    assert [p.shape[1] for p in parts] == [a - 1, cuts[1], F - b]
+    assert np.array_equal(np.concatenate(parts, axis=1), whole)
+
+
+def check_at3_stream_independence(lib, C=2, F=7, kbit=0):
+    pcm = np.stack([tl.synth_rich(F, 1024, C, seed=50 + s, kind=("mix", "tones", "steps")[s % 3]) for s in range(4)])
+    enc = _at3_enc(lib, C, kbit)
+    batch = enc.encode(pcm, 4)
+    enc.reset()
+    rev = enc.encode(pcm[::-1].copy(), 4)
+    enc.reset()
+    one = enc.encode(pcm[2:3].copy(), 1)
+    enc.close()
+    assert np.array_equal(batch, rev[::-1])
+    assert np.array_equal(batch[2:3], one)
+
+
+def check_at3_edge_inputs(lib, kbit=0):
+    """Silence, digital full scale DC, Nyquist, a single impulse; a one-frame first batch (no output)."""
+    F = 6
+    n = F * 1024
+    cases = {
+        "silence": np.zeros((n, 2), np.float32),
+        "full_scale_dc": np.full((n, 2), 32767 / 32768, np.float32),
+        "nyquist": np.tile(np.array([[1.0], [-1.0]], np.float32), (n // 2, 2)) * np.float32(32767 / 32768),
+        "impulse": np.zeros((n, 2), np.float32),
+    }
+    cases["impulse"][1500, 0] = -1.0
+    checked = 0
+    for name, x in cases.items():
+        enc = _at3_enc(lib, 2, kbit)
+        out = enc.encode(x, 1)
+        enc.close()
+        want = oracle_at3(2, x.reshape(-1), kbit)
+        if want is not None:
+            assert np.array_equal(out[0, :, 0], want), name
+            checked += 1
+    enc = _at3_enc(lib, 2, kbit)
+    first = enc.encode(cases["impulse"][:1024], 1)
+    assert first.shape[1] == 0
+    rest = enc.encode(cases["impulse"][1024:], 1)
+    enc.close()
+    want = oracle_at3(2, cases["impulse"].reshape(-1), kbit)
+    if want is not None:
+        assert np.array_equal(rest[0, :, 0], want)
+    return checked
+
+
+def check_at3_errors(lib):
+    import pytest
+    with pytest.raises(ab.AtdeError):
+        ab.Encoder(ab.CODEC_ATRAC3, 1, bitrate=64 * 1024, lib=lib)       # joint stereo with mono input: not built
+    with pytest.raises(ab.AtdeError):
+        ab.Encoder(ab.CODEC_ATRAC3, 2, bitrate=400 * 1024, lib=lib)      # beyond the largest container
+    with pytest.raises(ab.AtdeError):
+        ab.Encoder(ab.CODEC_ATRAC3PLUS, 2, lib=lib)
+    enc = ab.Encoder(ab.CODEC_ATRAC3, 2, lib=lib)
+    assert (enc.frame_samples, enc.units_per_frame, enc.unit_bytes, enc.lookahead) == (1024, 1, 384, 1)
+    enc.close()
+    enc = ab.Encoder(ab.CODEC_ATRAC3, 2, bitrate=64 * 1024, lib=lib)
+    assert enc.unit_bytes == 192
+    enc.close()

@@ -141,30 +141,47 @@ def synth_streams(n_streams, n_frames, frame_samples, channels, seed=0xA7AC):
     return out
 
 
-def engine_view(pcm, channels, step, total=None, buf_frames=4096):
+def engine_view(pcm, channels, step, total=None, buf_frames=4096, lookahead=0):
     """What the frame lambda actually receives when src/main.cpp:697-705 pumps `pcm` through
     TPCMEngine(4096) + TWav's reader: whole 4096-sample-frame reads; a short last read zeroes only
     (missing*channels) BYTES after the data (TPCMBuffer::Zero memsets len*NumChannels bytes,
-    src/pcmengin.h:91-94) and leaves the rest of the buffer stale.  Returns interleaved PCM of
-    every frame handed to the lambda, in order."""
+    src/pcmengin.h:91-94) and leaves the rest of the buffer stale.  With a look-ahead codec
+    (`lookahead` = number of calls that return LOOK_AHEAD) the engine "drains" at the end of the
+    input: when the reader is exhausted but `total` is not reached it calls the lambda once more per
+    pending look-ahead frame on the STALE buffer (src/pcmengin.h:157-182).  Returns interleaved PCM
+    of every frame handed to the lambda, in order."""
     pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1, channels)
     n = pcm.shape[0]
     total = n if total is None else total
     buf = np.zeros((buf_frames, channels), np.float32)
     pos, processed, frames = 0, 0, []
+    pending, to_drain = lookahead, 0
     while total > processed:
         got = min(buf_frames, n - pos)
+        drain = False
         if got == 0:
-            break
-        buf[:got] = pcm[pos:pos + got]
-        pos += got
-        if got != buf_frames:
-            flat = buf.reshape(-1).view(np.uint8)
-            start = got * channels * 4
-            flat[start:start + (buf_frames - got) * channels] = 0
+            if not to_drain:
+                break
+            drain = True
+        else:
+            buf[:got] = pcm[pos:pos + got]
+            pos += got
+            if got != buf_frames:
+                flat = buf.reshape(-1).view(np.uint8)
+                start = got * channels * 4
+                flat[start:start + (buf_frames - got) * channels] = 0
+        last_pos = 0
         for i in range(0, buf_frames - step + 1, step):
             frames.append(buf[i:i + step].copy())
-        processed += (buf_frames // step) * step
+            if pending:
+                pending -= 1
+                to_drain += 1
+                continue
+            last_pos += step
+            if drain and to_drain:
+                to_drain -= 1
+                break
+        processed += last_pos
     return np.concatenate(frames).reshape(-1)
 
 

@@ -270,7 +270,7 @@ def check_at3_main_loop(lib, C=2, kbit=0, seconds=0.4):
     fs = int(sizes[0])
     assert (sizes == fs).all()
     want = payload.reshape(-1, fs)
-    view = tl.engine_view(pcm, C, 1024, total=n)
+    view = tl.engine_view(pcm, C, 1024, total=n, lookahead=1)
     enc = _at3_enc(lib, C, kbit)
     out = enc.encode(view, 1)
     enc.close()

@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
     __shared__ __align__(16) cpx freq[257];
     __shared__ float micro[256];
     __shared__ float sgain[96];
+    __shared__ double ek[257], ekh[257];
+    __shared__ double esum2[2];
 
     const DevTables* __restrict__ T = b.tab;
     const int f = blockIdx.x;
@@ -253,21 +255,24 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         }
     }
     __syncthreads();
-    // 2a. high-frequency energy ratio: sequential double sums (upsampler.cpp:99-118) on one thread,
-    //     while the others build the inverse FFT input.
+    // 2a. high-frequency energy ratio (upsampler.cpp:99-118): per-bin terms in parallel, then the two
+    //     sequential double sums on two threads while the others build the inverse FFT input.
     const int lcb = T->low_cut_bin;
-    if (tid == kGainThreads - 1) {
-        double tot = 0.0, hi = 0.0;
-        for (int k = 0; k <= 256; k++) {
-            const double r = (double)freq[k].r, i = (double)freq[k].i;
-            const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
-            tot = __dadd_rn(tot, e);
-            float H = 0.0f;
-            if (k >= lcb + 2) H = 1.0f;
-            else if (k >= lcb) H = T->hpf_h[k - lcb];
-            hi = __dadd_rn(hi, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
-        }
-        sgain[0] = (tot > 0.0) ? __double2float_rn(__ddiv_rn(hi, tot)) : 0.0f;   // parked; moved below
+    ATDE_PAR_FOR(k, 257) {
+        const double r = (double)freq[k].r, i = (double)freq[k].i;
+        const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
+        float H = 0.0f;
+        if (k >= lcb + 2) H = 1.0f;
+        else if (k >= lcb) H = T->hpf_h[k - lcb];
+        ek[k] = e;
+        ekh[k] = __dmul_rn(__dmul_rn(e, (double)H), (double)H);
+    }
+    __syncthreads();
+    if (tid == kGainThreads - 1 || tid == kGainThreads - 33) {
+        const double* src = (tid == kGainThreads - 1) ? ek : ekh;
+        double a = 0.0;
+        for (int k = 0; k <= 256; k++) a = __dadd_rn(a, src[k]);
+        esum2[tid == kGainThreads - 1 ? 0 : 1] = a;
     }
     // 3/4a. inverse real FFT input: Y[k] = 8*X[k]*H[k]; kiss_fftri pre-processing (kiss_fftr.c:131-151)
     //       with Y[2048-k] == 0 for every k that carries data.
@@ -304,7 +309,18 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         }
     }
     __syncthreads();
-    const float hfr = sgain[0];
+    const float hfr = (esum2[0] > 0.0) ? __double2float_rn(__ddiv_rn(esum2[1], esum2[0])) : 0.0f;
+    const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
+    if (hfr < 0.05f) {
+        // kHighFreqThreshold: CreateSubbandInfo only resets LastLevel and moves on (atrac3denc.cpp:319-327);
+        // nothing downstream reads the envelope of such a frame.
+        if (tid == 0) {
+            float4 st4;
+            st4.x = hfr; st4.y = 0.0f; st4.z = 0.0f; st4.w = 0.0f;
+            reinterpret_cast<float4*>(b.gstat)[item] = st4;
+        }
+        return;
+    }
     // 4b. inverse complex FFT-2048 = 4x4x4x4x4x2: radix-2 innermost, then m = 2, 8, 32, 128, 512
     ATDE_PAR_FOR(v, 1024) kf_stage2(big, T->tw2048, v, 1, 1024);
     __syncthreads();
@@ -352,7 +368,6 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         sgain[64 + tid] = m[6];
     }
     __syncthreads();
-    const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
     ATDE_PAR_FOR(i, 96) b.gain[item * 96 + i] = sgain[i];
     if (tid == 0) {
         float cur = 0.0f;
@@ -732,11 +747,14 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
     // ---- energy chains of CalcGainEnergyScale: sequential sums, one thread per chain ----
     //  chain 0 prevStored, 1 curOriginal, 2 curModulated, 3 nextOriginal, 4 nextModulated,
     //  5/6 nextOriginal/nextModulated of the previous frame
+    //  A band whose own curve is empty and whose overlap scale is 1 has every scale exactly 1.0
+    //  (SafeEnergyScale(x, x)), so the chains only run for bands that touch a curve.
     if (tid < 28) {
         const int band = tid / 7, ch = tid % 7;
         const bool cur_empty = scv[band][1].n == 0, prev_empty = scv[band][0].n == 0;
+        const bool trivial = cur_empty && (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : prev_empty);
         float a = 0.0f;
-        bool run = true;
+        bool run = !trivial;
         // with an empty curve the modulated sums equal the original ones bit for bit
         if ((ch == 2 || ch == 4) && cur_empty) run = false;
         if (ch >= 5 && (f == 0 || prev_empty)) run = false;
@@ -761,22 +779,27 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
         const int band = tid;
         const Curve& cc = scv[band][1];
         const bool cur_empty = cc.n == 0, prev_empty = scv[band][0].n == 0;
-        float pos_scale;                                       // PrevOverlapGainScale[channel][band]
-        if (f == 0) pos_scale = b.next_scale[sc * 4 + band];
-        else if (prev_empty) pos_scale = safe_energy_scale(1.0f, 1.0f);   // e/e == 1 or the eps branch: 1 either way
-        else pos_scale = safe_energy_scale(esum[band][5], esum[band][6]);
-        const float inf = __int_as_float(0x7f800000);
-        if (!(fabsf(pos_scale) < inf) || pos_scale <= 0.0f) pos_scale = 1.0f;
-        const float prev_div = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
-        const float prev_stored = esum[band][0];
-        const float prev_orig = fmul(prev_stored, pos_scale);
-        const float prev_mod = __fdiv_rn(prev_stored, fmul(prev_div, prev_div));
-        const float cur_orig = esum[band][1], cur_mod = cur_empty ? esum[band][1] : esum[band][2];
-        const float nxt_orig = esum[band][3], nxt_mod = cur_empty ? esum[band][3] : esum[band][4];
-        sscale[band][0] = safe_energy_scale(prev_orig, prev_mod);
-        sscale[band][1] = safe_energy_scale(cur_orig, cur_mod);
-        sscale[band][2] = safe_energy_scale(fadd(prev_orig, cur_orig), fadd(prev_mod, cur_mod));
-        sscale[band][3] = safe_energy_scale(nxt_orig, nxt_mod);
+        const bool trivial = cur_empty && (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : prev_empty);
+        if (trivial) {
+            sscale[band][0] = 1.0f; sscale[band][1] = 1.0f; sscale[band][2] = 1.0f; sscale[band][3] = 1.0f;
+        } else {
+            float pos_scale;                                       // PrevOverlapGainScale[channel][band]
+            if (f == 0) pos_scale = b.next_scale[sc * 4 + band];
+            else if (prev_empty) pos_scale = 1.0f;                 // SafeEnergyScale(e, e)
+            else pos_scale = safe_energy_scale(esum[band][5], esum[band][6]);
+            const float inf = __int_as_float(0x7f800000);
+            if (!(fabsf(pos_scale) < inf) || pos_scale <= 0.0f) pos_scale = 1.0f;
+            const float prev_div = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
+            const float prev_stored = esum[band][0];
+            const float prev_orig = fmul(prev_stored, pos_scale);
+            const float prev_mod = __fdiv_rn(prev_stored, fmul(prev_div, prev_div));
+            const float cur_orig = esum[band][1], cur_mod = cur_empty ? esum[band][1] : esum[band][2];
+            const float nxt_orig = esum[band][3], nxt_mod = cur_empty ? esum[band][3] : esum[band][4];
+            sscale[band][0] = safe_energy_scale(prev_orig, prev_mod);
+            sscale[band][1] = safe_energy_scale(cur_orig, cur_mod);
+            sscale[band][2] = safe_energy_scale(fadd(prev_orig, cur_orig), fadd(prev_mod, cur_mod));
+            sscale[band][3] = safe_energy_scale(nxt_orig, nxt_mod);
+        }
     }
     // ---- MDCT-512 per band: fold + pre-twiddle into kissfft's gather order (mdct.h:56-76) ----
     //   tmp[j]       = prevw[j] / scale           j < 256   (Modulate divides bufCur by GainLevel[first point])
@@ -840,15 +863,6 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
     const size_t unit = ((size_t)s * g.n_out + f) * g.C + c;
     ATDE_PAR_FOR(i, 1024) b.specs[unit * 1024 + i] = sp[i];
     if (tid < 16) b.gscale[unit * 16 + tid] = sscale[tid >> 2][tid & 3];
-    if (tid == 32) {
-        // sce->Loudness (atrac3denc.cpp:811-820): l += e * Frame * curve, sequential
-        float l = 0.0f;
-        for (int i = 0; i < 1024; i++) {
-            const float e = fmul(sp[i], sp[i]);
-            l = fadd(l, fmul(fmul(e, sscale[i >> 8][2]), T->loud_curve[i]));
-        }
-        b.chloud[unit] = l;
-    }
     if (f == g.n_out - 1) {
         // state for the next batch: the half this frame leaves behind and its NextOverlapScale
         ATDE_PAR_FOR(w, 1024) {

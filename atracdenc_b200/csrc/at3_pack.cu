@@ -128,6 +128,19 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
 
     const int start = kBlockStart[lane], len = kBlockStart[lane + 1] - kBlockStart[lane];
     TonalList* tl = b.tonal + unit;
+    if (lane == 0) {
+        // sce->Loudness (atrac3denc.cpp:811-820): l += e * Frame * curve, one sequential chain; runs
+        // on the lane that has no flatness work while lanes 8..28 do theirs
+        const float* gs = b.gscale + (size_t)unit * 16;
+        const float fr[4] = {gs[2], gs[6], gs[10], gs[14]};
+        float l = 0.0f;
+        for (int i = 0; i < 1024; i++) {
+            const float e = fmul(sv[i], sv[i]);
+            l = fadd(l, fmul(fmul(e, fr[i >> 8]), T->loud_curve[i]));
+        }
+        b.chloud[unit] = l;
+    }
+    __syncwarp();
     if (!g.no_tonal) {
         if (lane >= 8 && lane < 29) {
             // CalcSpectralFlatnessPerBfu: geometric / arithmetic mean of the line energies, in double
@@ -163,13 +176,12 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
                 if (best > 0.0f) {
                     run_start[wib][lane] = (short)best_start;
                     run_len[wib][lane] = (signed char)best_len;
-                    for (int n = 0; n < best_len; n++) {
-                        run_val[wib][lane][n] = sv[best_start + n];
-                        sv[best_start + n] = 0.0f;
-                    }
+                    for (int n = 0; n < best_len; n++) run_val[wib][lane][n] = sv[best_start + n];
                 }
             }
         }
+        __syncwarp();                                            // lane 0 has finished reading the spectrum
+        for (int n = 0; n < run_len[wib][lane]; n++) sv[run_start[wib][lane] + n] = 0.0f;
         __syncwarp();
         if (lane == 0) {
             // MapTonalComponents: runs of consecutive positions (<= 7 values) become tonal blocks
@@ -230,72 +242,142 @@ struct UnitCost {
     float err;
 };
 
-ATDE_D UnitCost quant_unit(const float* in, int len, int bfu, int wl, signed char* m_out)
+// Exact restatement with the complete candidate list and libstdc++'s sort order; only used when two
+// candidates that can actually be re-rounded share the same |delta| (see quant_unit).
+ATDE_D float quant_unit_exact(const float* in, int len, float mul, float inv2, signed char* m)
 {
-    const float mul = kMaxQuant[wl];
-    const float inv2 = __double2float_rn(__ddiv_rn(1.0, (double)fmul(mul, mul)));
-    const bool ea = bfu > 18;                                   // LOSY_NAQ_START
-    signed char m[128];
+    SortCand cand[128];
+    int nc = 0;
     float e1 = 0.0f, e2 = 0.0f;
-    if (!ea) {
-        for (int j = 0; j < len; j++) {
-            const float t = fmul(in[j], mul);
-            e1 = fadd(e1, fmul(in[j], in[j]));
-            const int q = __float2int_rn(t);
-            m[j] = (signed char)q;
-            e2 = fadd(e2, fmul((float)(q * q), inv2));
-        }
-    } else {
-        SortCand cand[128];
-        int nc = 0;
-        for (int j = 0; j < len; j++) {
-            const float t = fmul(in[j], mul);
-            e1 = fadd(e1, fmul(in[j], in[j]));
-            const int q = __float2int_rn(t);
-            m[j] = (signed char)q;
-            e2 = fadd(e2, fmul((float)(q * q), inv2));
-            const float delta = fsub(t, fadd(truncf(t), 0.5f));
-            if (fabsf(delta) < 0.25f) { cand[nc].delta = delta; cand[nc].idx = j; nc++; }
-        }
-        if (nc > 0) {
-            std_sort_cands(cand, nc);
-            if (e2 < e1) {
-                for (int k = 0; k < nc; k++) {
-                    const int j = cand[k].idx;
-                    const float t = fmul(in[j], mul);
-                    const int q = m[j];
-                    const float aq = (float)abs(q);
-                    if (aq < fabsf(t) && aq < fsub(mul, 1.0f)) {
-                        int q2 = q;
-                        if (q > 0) q2++;
-                        if (q < 0) q2--;
-                        if (q == 0) q2 = t > 0.0f ? 1 : -1;
-                        float ex = e2;
-                        ex = fsub(ex, fmul((float)(q * q), inv2));
-                        ex = fadd(ex, fmul((float)(q2 * q2), inv2));
-                        if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
-                    }
+    for (int j = 0; j < len; j++) {
+        const float t = fmul(in[j], mul);
+        e1 = fadd(e1, fmul(in[j], in[j]));
+        const int q = __float2int_rn(t);
+        m[j] = (signed char)q;
+        e2 = fadd(e2, fmul((float)(q * q), inv2));
+        const float delta = fsub(t, fadd(truncf(t), 0.5f));
+        if (fabsf(delta) < 0.25f) { cand[nc].delta = delta; cand[nc].idx = j; nc++; }
+    }
+    if (nc > 0) {
+        std_sort_cands(cand, nc);
+        if (e2 < e1) {
+            for (int k = 0; k < nc; k++) {
+                const int j = cand[k].idx;
+                const float t = fmul(in[j], mul);
+                const int q = m[j];
+                const float aq = (float)abs(q);
+                if (aq < fabsf(t) && aq < fsub(mul, 1.0f)) {
+                    int q2 = q;
+                    if (q > 0) q2++;
+                    if (q < 0) q2--;
+                    if (q == 0) q2 = t > 0.0f ? 1 : -1;
+                    float ex = e2;
+                    ex = fsub(ex, fmul((float)(q * q), inv2));
+                    ex = fadd(ex, fmul((float)(q2 * q2), inv2));
+                    if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
                 }
-            } else if (e2 > e1) {
-                for (int k = 0; k < nc; k++) {
-                    const int j = cand[k].idx;
-                    const float t = fmul(in[j], mul);
-                    const int q = m[j];
-                    if ((float)abs(q) > fabsf(t)) {
-                        int q2 = q;
-                        if (q > 0) q2--;
-                        if (q < 0) q2++;
-                        float ex = e2;
-                        ex = fsub(ex, fmul((float)(q * q), inv2));
-                        ex = fadd(ex, fmul((float)(q2 * q2), inv2));
-                        if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
-                    }
+            }
+        } else if (e2 > e1) {
+            for (int k = 0; k < nc; k++) {
+                const int j = cand[k].idx;
+                const float t = fmul(in[j], mul);
+                const int q = m[j];
+                if ((float)abs(q) > fabsf(t)) {
+                    int q2 = q;
+                    if (q > 0) q2--;
+                    if (q < 0) q2++;
+                    float ex = e2;
+                    ex = fsub(ex, fmul((float)(q * q), inv2));
+                    ex = fadd(ex, fmul((float)(q2 * q2), inv2));
+                    if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
                 }
             }
         }
     }
+    return __fdiv_rn(e1, e2);
+}
+
+// QuantMantisas (atrac_scale.cpp:40-130) of one BFU at one word length.
+//   in   scaled values of the BFU (shared memory)
+//   m    mantissas of the BFU (shared memory), written
+//   ckey / cidx   scratch for the BFU's re-rounding candidates (shared memory; BFUs > 18 only)
+//
+// The energy-aware branch of the reference sorts every candidate by |delta| and walks the sorted
+// list, re-rounding a value when that brings the quantised energy e2 closer to e1.  Restated here
+// without the full sort:
+//   * only candidates that pass the walk's own test (|m| < |t| && |m| < mul-1 when e2 < e1, |m| > |t|
+//     when e2 > e1 -- a static property of the element) can change anything, so only those are kept;
+//   * they are visited in ascending |delta| by repeated selection;
+//   * once e2 has reached or crossed e1 every later candidate is rejected (each step moves e2 by at
+//     least inv2 ~ 1e-3 in the same direction, far above the rounding error of the update), so the
+//     walk stops there.
+// With distinct |delta| among the visited candidates this is the reference's order exactly; if two
+// visited candidates tie, the library's sort order matters and quant_unit_exact redoes the block.
+ATDE_D float quant_mantissas(const float* in, int len, bool ea, float mul, float inv2, signed char* m,
+                             float* ckey, unsigned char* cidx)
+{
+    float e1 = 0.0f, e2 = 0.0f;
+    for (int j = 0; j < len; j++) {
+        const float x = in[j];
+        const float t = fmul(x, mul);
+        e1 = fadd(e1, fmul(x, x));
+        const int q = __float2int_rn(t);
+        m[j] = (signed char)q;
+        e2 = fadd(e2, fmul((float)(q * q), inv2));
+    }
+    if (!ea || e2 == e1) return __fdiv_rn(e1, e2);
+    const bool up = e2 < e1;
+    const float lim = fsub(mul, 1.0f);
+    int nc = 0;
+    for (int j = 0; j < len; j++) {
+        const float t = fmul(in[j], mul);
+        const float delta = fsub(t, fadd(truncf(t), 0.5f));
+        if (fabsf(delta) < 0.25f) {
+            const float aq = (float)abs((int)m[j]);
+            const bool qual = up ? (aq < fabsf(t) && aq < lim) : (aq > fabsf(t));
+            if (qual) { ckey[nc] = fabsf(delta); cidx[nc] = (unsigned char)j; nc++; }
+        }
+    }
+    float last = -1.0f;
+    while (up ? (e2 < e1) : (e2 > e1)) {
+        float best = 2.0f;
+        int bi = -1, ties = 0;
+        for (int k = 0; k < nc; k++) {
+            const float key = ckey[k];
+            if (key > last) {
+                if (key < best) { best = key; bi = k; ties = 0; }
+                else if (key == best) ties++;
+            }
+        }
+        if (bi < 0) break;
+        if (ties) return quant_unit_exact(in, len, mul, inv2, m);
+        last = best;
+        const int j = cidx[bi];
+        const int q = m[j];
+        int q2 = q;
+        if (up) {
+            if (q > 0) q2++;
+            if (q < 0) q2--;
+            if (q == 0) q2 = fmul(in[j], mul) > 0.0f ? 1 : -1;
+        } else {
+            if (q > 0) q2--;
+            if (q < 0) q2++;
+        }
+        float ex = e2;
+        ex = fsub(ex, fmul((float)(q * q), inv2));
+        ex = fadd(ex, fmul((float)(q2 * q2), inv2));
+        if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
+    }
+    return __fdiv_rn(e1, e2);
+}
+
+// TAt3SpecUnit::Provide (atrac3_bitstream.cpp:157-173): mantissas + CLC / VLC cost of one BFU.
+ATDE_D UnitCost quant_unit(const float* in, int len, int bfu, int wl, signed char* m, float* ckey, unsigned char* cidx)
+{
+    const float mul = kMaxQuant[wl];
+    const float inv2 = __double2float_rn(__ddiv_rn(1.0, (double)fmul(mul, mul)));
     UnitCost u;
-    u.err = __fdiv_rn(e1, e2);
+    u.err = quant_mantissas(in, len, bfu > 18 /* LOSY_NAQ_START */, mul, inv2, m, ckey, cidx);
     // CLCEnc / VLCEnc bit counts (atrac3_bitstream.cpp:92-149)
     if (wl > 1) {
         u.clc = (unsigned)kClcLen[wl] * len;
@@ -310,8 +392,6 @@ ATDE_D UnitCost quant_unit(const float* in, int len, int bfu, int wl, signed cha
             v += kHuffBits[kVlcPairIdx[3 * (m[2 * j] + 1) + (m[2 * j + 1] + 1)]];
         u.vlc = v;
     }
-    if (m_out)
-        for (int j = 0; j < len; j++) m_out[j] = m[j];
     return u;
 }
 
@@ -332,8 +412,12 @@ ATDE_D void put_bits3(unsigned* words, int cap_bits, int pos, int n, unsigned va
 
 constexpr int kWordsPerCh = kMaxUnitBytes / 4 + 8;             // bitstream of one channel
 
+constexpr int kEaFirst = 288;                                  // first line of BFU 19 (BFUs > 18 re-round)
 struct PackShared {
     float sv[1024];                    // scaled spectrum of the channel
+    float ckey[1024 - kEaFirst];       // re-rounding candidates of the BFU being quantised: |delta| ...
+    unsigned char cidx[1024 - kEaFirst];   // ... and line offset inside the BFU
+    signed char mant[1024];            // mantissas of the unit quantised last, per BFU region
     unsigned words[kWordsPerCh];
     unsigned cache_cv[8][32];          // clc | vlc << 16, indexed [wordlen][bfu]
     float cache_err[8][32];
@@ -488,6 +572,8 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
     }
     const float fix_term = fmul(fsub(1.0f, spread), fix);
     unsigned cached = 0;                                         // bit w: (lane, w) is in the cache
+    float* ckey = sh.ckey + (start >= kEaFirst ? start - kEaFirst : 0);
+    unsigned char* cidx = sh.cidx + (start >= kEaFirst ? start - kEaFirst : 0);
 
     // CalcInitialNumBfu (:567-585)
     int num_bfu = g.bfu_idx_const ? g.bfu_idx_const : 32;
@@ -520,7 +606,7 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
                 for (;;) {
                     if (prec == 0) break;
                     if (!((cached >> prec) & 1u)) {
-                        const UnitCost u = quant_unit(sh.sv + start, len, lane, (int)prec, nullptr);
+                        const UnitCost u = quant_unit(sh.sv + start, len, lane, (int)prec, sh.mant + start, ckey, cidx);
                         sh.cache_cv[prec][lane] = u.clc | (u.vlc << 16);
                         sh.cache_err[prec][lane] = u.err;
                         cached |= 1u << prec;
@@ -660,8 +746,8 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
         if (lane >= d) inc += a;
     }
     if (in_use && prec) {
-        signed char m[128];
-        quant_unit(sh.sv + start, len, lane, (int)prec, m);
+        const signed char* m = sh.mant + start;
+        quant_unit(sh.sv + start, len, lane, (int)prec, sh.mant + start, ckey, cidx);
         int p = pos + (int)(inc - mybits);
         if (mode) {
             if (prec > 1u) {

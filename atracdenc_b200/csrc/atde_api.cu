@@ -397,8 +397,8 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
             e->launches += 3;
         }
         { KernelTimer kt(e, w.stream, 0); launch_mdct(g, b, w.stream); }
-        { KernelTimer kt(e, w.stream, 1); launch_loudness(g, b, w.stream); }
         { KernelTimer kt(e, w.stream, 5); launch_scale_tonal(g, b, w.stream); }
+        { KernelTimer kt(e, w.stream, 1); launch_loudness(g, b, w.stream); }
         { KernelTimer kt(e, w.stream, 2); launch_alloc_pack(g, b, w.stream); }
         e->launches += 4;
     }

@@ -199,17 +199,37 @@ ATDE_D float plateau_target(const float* in)
     return use_plateau ? level : in[n - 1];
 }
 
-constexpr int kGainThreads = 256;
+constexpr int kGainThreads = 128;
 
+// The 2048-point buffer is padded by 8 elements per 128 so that the stride-128 accesses of the
+// middle pass spread over all shared-memory banks.
+ATDE_D int gphys(int i) { return i + ((i >> 7) << 3); }
+
+// One (stream, channel, band, frame) per block.
+//
+// kiss_fftri(4096) = pre-processing + inverse complex FFT-2048 (4x4x4x4x4x2).  kissfft's decimation
+// in time is restated as a digit-reversed gather followed by the stages innermost first; the stages
+// are executed two at a time on registers (every butterfly keeps the library's exact operation
+// order, so regrouping them changes nothing numerically):
+//   pass 1  radix-2 (m=1) + radix-4 (m=2)   on the 8 consecutive slots of a group
+//   pass 2  radix-4 (m=8) + radix-4 (m=32)  on 16 slots  base + k + 8a + 32b
+//   pass 3  radix-4 (m=128) + radix-4 (m=512) on 16 slots k + 128a + 512b
+// Only input bins LowCutBin..256 and their mirrors are non-zero, which leaves two (for one group,
+// three) non-zero inputs per pass-1 group: slot 0 = tmpbuf[low], slot 7 = tmpbuf[1792 + low],
+// slot 2 = tmpbuf[256] (low == 0 only).  Pass 1 is written out for that case; adding or multiplying
+// by the structural zeros is exact, so the values equal the full transform's (up to the sign of zero,
+// which no consumer can see: the output is squared).
+// Only output samples [1024, 3072) are consumed (AnalyzeGain), i.e. complex slots [512, 1536).
 __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) cpx big[2048];          // inverse FFT buffer (also the real output, 4096 floats)
+    __shared__ __align__(16) cpx big[2048 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ __align__(16) cpx fwd[256];
     __shared__ __align__(16) cpx freq[257];
     __shared__ float micro[256];
     __shared__ float sgain[96];
     __shared__ double ek[257], ekh[257];
     __shared__ double esum2[2];
+    __shared__ float sstat[2];
 
     const DevTables* __restrict__ T = b.tab;
     const int f = blockIdx.x;
@@ -217,16 +237,17 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
     const int s = blockIdx.z;
     const float* __restrict__ in = b.bands + (((size_t)s * g.C + c) * 4 + band) * g.BL + 256 * (size_t)f;
     const int tid = threadIdx.x;
+    const cpx* __restrict__ tw = T->tw2048;
 
     // 1. Planck window, packed as the complex input of the half-size FFT, in digit-reversed order
     ATDE_PAR_FOR(o, 256) {
         const int j = T->perm256[o];
+        const float2 x = *reinterpret_cast<const float2*>(in + 2 * j);
         cpx z;
-        z.r = fmul(in[2 * j], T->planck[2 * j]);
-        z.i = fmul(in[2 * j + 1], T->planck[2 * j + 1]);
+        z.r = fmul(x.x, T->planck[2 * j]);
+        z.i = fmul(x.y, T->planck[2 * j + 1]);
         fwd[o] = z;
     }
-    ATDE_PAR_FOR(i, 2048) { big[i].r = 0.0f; big[i].i = 0.0f; }
     __syncthreads();
     // 2. forward complex FFT-256 = 4x4x4x4
     for (int st = 0; st < 4; st++) {
@@ -246,17 +267,17 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
             cpx f1k, f2k;
             f1k.r = fadd(fpk.r, fpnk.r); f1k.i = fadd(fpk.i, fpnk.i);
             f2k.r = fsub(fpk.r, fpnk.r); f2k.i = fsub(fpk.i, fpnk.i);
-            const cpx tw = cmul(f2k, T->super512[k - 1]);
+            const cpx t2 = cmul(f2k, T->super512[k - 1]);
             cpx a, bb;
-            a.r = fmul(fadd(f1k.r, tw.r), 0.5f);  a.i = fmul(fadd(f1k.i, tw.i), 0.5f);
-            bb.r = fmul(fsub(f1k.r, tw.r), 0.5f); bb.i = fmul(fsub(tw.i, f1k.i), 0.5f);
+            a.r = fmul(fadd(f1k.r, t2.r), 0.5f);  a.i = fmul(fadd(f1k.i, t2.i), 0.5f);
+            bb.r = fmul(fsub(f1k.r, t2.r), 0.5f); bb.i = fmul(fsub(t2.i, f1k.i), 0.5f);
             freq[k] = a;                       // k == 128 writes the same element twice: the second
             freq[256 - k] = bb;                // store (freqdata[ncfft-k]) wins, as in the reference
         }
     }
     __syncthreads();
-    // 2a. high-frequency energy ratio (upsampler.cpp:99-118): per-bin terms in parallel, then the two
-    //     sequential double sums on two threads while the others build the inverse FFT input.
+    // 2a. per-bin terms of the high-frequency energy ratio (upsampler.cpp:99-118); the two sequential
+    //     double sums are taken at the very end so that nothing waits for them.
     const int lcb = T->low_cut_bin;
     ATDE_PAR_FOR(k, 257) {
         const double r = (double)freq[k].r, i = (double)freq[k].i;
@@ -267,20 +288,15 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         ek[k] = e;
         ekh[k] = __dmul_rn(__dmul_rn(e, (double)H), (double)H);
     }
-    __syncthreads();
-    if (tid == kGainThreads - 1 || tid == kGainThreads - 33) {
-        const double* src = (tid == kGainThreads - 1) ? ek : ekh;
-        double a = 0.0;
-        for (int k = 0; k <= 256; k++) a = __dadd_rn(a, src[k]);
-        esum2[tid == kGainThreads - 1 ? 0 : 1] = a;
-    }
-    // 3/4a. inverse real FFT input: Y[k] = 8*X[k]*H[k]; kiss_fftri pre-processing (kiss_fftr.c:131-151)
-    //       with Y[2048-k] == 0 for every k that carries data.
-    ATDE_PAR_FOR(k, 257) {
-        if (k < lcb) continue;
+    // 3/4. inverse FFT input Y[k] = 8*X[k]*H[k] (Nyquist bin halved), kiss_fftri pre-processing
+    //      (kiss_fftr.c:131-151) with Y[2048-k] == 0, and pass 1 of the inverse FFT.
+    auto tmp_pair = [&](int k, cpx& lo, cpx& hi) {
+        // tmpbuf[k] and tmpbuf[2048-k] for 1 <= k <= 256; zero when the bin is cut
+        lo.r = lo.i = hi.r = hi.i = 0.0f;
+        if (k < lcb || k < 1) return;
         cpx fk;
         if (k == 256) {
-            if (lcb + 2 > 256) continue;
+            if (lcb + 2 > 256) return;
             fk.r = fmul(fmul(freq[256].r, 8.0f), 0.5f);
             fk.i = 0.0f;
         } else if (k >= lcb + 2) {
@@ -291,59 +307,111 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
             fk.r = fmul(fmul(freq[k].r, 8.0f), w);
             fk.i = fmul(fmul(freq[k].i, 8.0f), w);
         }
-        if (k == 0) {
-            // tmpbuf[0] = (Y[0].r + Y[2048].r, Y[0].r - Y[2048].r)
-            cpx z; z.r = fadd(fk.r, 0.0f); z.i = fsub(fk.r, 0.0f);
-            big[T->iperm2048[0]] = z;
-        } else {
-            // fnkc = conj(Y[2048-k]) = (0, -0)
-            cpx fek, tmp;
-            fek.r = fadd(fk.r, 0.0f);  fek.i = fadd(fk.i, -0.0f);
-            tmp.r = fsub(fk.r, 0.0f);  tmp.i = fsub(fk.i, -0.0f);
-            const cpx fok = cmul(tmp, T->super4096[k - 1]);
-            cpx lo, hi2;
-            lo.r = fadd(fek.r, fok.r);  lo.i = fadd(fek.i, fok.i);
-            hi2.r = fsub(fek.r, fok.r); hi2.i = fmul(fsub(fek.i, fok.i), -1.0f);
-            big[T->iperm2048[k]] = lo;
-            big[T->iperm2048[2048 - k]] = hi2;
+        // fnkc = conj(Y[2048-k]) = (0, -0):  fek = fk + fnkc, tmp = fk - fnkc
+        cpx fek, tp;
+        fek.r = fadd(fk.r, 0.0f);  fek.i = fadd(fk.i, -0.0f);
+        tp.r = fsub(fk.r, 0.0f);   tp.i = fsub(fk.i, -0.0f);
+        const cpx fok = cmul(tp, T->super4096[k - 1]);
+        lo.r = fadd(fek.r, fok.r);  lo.i = fadd(fek.i, fok.i);
+        hi.r = fsub(fek.r, fok.r);  hi.i = fmul(fsub(fek.i, fok.i), -1.0f);
+    };
+    for (int grp = tid; grp < 256; grp += kGainThreads) {
+        const int low = ((grp >> 6) & 3) | (((grp >> 4) & 3) << 2) | (((grp >> 2) & 3) << 4) | ((grp & 3) << 6);
+        cpx x0, x2, x7, dummy;
+        tmp_pair(low, x0, dummy);                        // slot 0: input index low (tmpbuf[0] is zero: bin 0 is cut)
+        tmp_pair(256 - low, dummy, x7);                  // slot 7: input index 1792 + low = 2048 - (256 - low)
+        x2.r = x2.i = 0.0f;
+        if (low == 0) { x0.r = x0.i = 0.0f; tmp_pair(256, x2, dummy); }   // slot 2: input index 256
+        if (lcb == 0 && low == 0) {
+            // bin 0 kept (not the encoder's configuration, kept for completeness): tmpbuf[0]
+            const float y0 = fmul(freq[0].r, 8.0f);
+            x0.r = fadd(y0, 0.0f); x0.i = fsub(y0, 0.0f);
         }
+        // radix-2, m = 1, twiddle tw[0]: (F0,F1) = (x0, x0); (F2,F3) = (x2, x2); (F6,F7) = (x7, -x7)
+        const cpx t7 = cmul(x7, tw[0]);
+        cpx F6, F7;
+        F7.r = fsub(0.0f, t7.r); F7.i = fsub(0.0f, t7.i);
+        F6.r = fadd(0.0f, t7.r); F6.i = fadd(0.0f, t7.i);
+        cpx o0, o1, o2, o3, o4, o5, o6, o7;
+        {   // radix-4, m = 2, k = 0: elements (x0, x2, 0, F6), twiddles tw[0]
+            cpx f0 = x0, f1 = x2, f2, f3 = F6;
+            f2.r = f2.i = 0.0f;
+            kf_bfly4<true>(f0, f1, f2, f3, tw[0], tw[0], tw[0]);
+            o0 = f0; o2 = f1; o4 = f2; o6 = f3;
+        }
+        {   // k = 1: elements (x0, x2, 0, F7), twiddles tw[256], tw[512], tw[768]
+            cpx f0 = x0, f1 = x2, f2, f3 = F7;
+            f2.r = f2.i = 0.0f;
+            kf_bfly4<true>(f0, f1, f2, f3, tw[256], tw[512], tw[768]);
+            o1 = f0; o3 = f1; o5 = f2; o7 = f3;
+        }
+        cpx* dst = big + gphys(8 * grp);
+        dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3; dst[4] = o4; dst[5] = o5; dst[6] = o6; dst[7] = o7;
     }
     __syncthreads();
-    const float hfr = (esum2[0] > 0.0) ? __double2float_rn(__ddiv_rn(esum2[1], esum2[0])) : 0.0f;
-    const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
-    if (hfr < 0.05f) {
-        // kHighFreqThreshold: CreateSubbandInfo only resets LastLevel and moves on (atrac3denc.cpp:319-327);
-        // nothing downstream reads the envelope of such a frame.
-        if (tid == 0) {
-            float4 st4;
-            st4.x = hfr; st4.y = 0.0f; st4.z = 0.0f; st4.w = 0.0f;
-            reinterpret_cast<float4*>(b.gstat)[item] = st4;
+    // pass 2: radix-4 m = 8 (fstride 64), then m = 32 (fstride 16)
+    {
+        const int k = tid & 7, base = (tid >> 3) << 7;
+        cpx x[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) x[a][q] = big[gphys(base + k + 8 * a + 32 * q)];
+        {
+            const cpx t1 = tw[64 * k], t2 = tw[128 * k], t3 = tw[192 * k];
+#pragma unroll
+            for (int q = 0; q < 4; q++) kf_bfly4<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3);
         }
-        return;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int kk = k + 8 * a;
+            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw[16 * kk], tw[32 * kk], tw[48 * kk]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) big[gphys(base + k + 8 * a + 32 * q)] = x[a][q];
     }
-    // 4b. inverse complex FFT-2048 = 4x4x4x4x4x2: radix-2 innermost, then m = 2, 8, 32, 128, 512
-    ATDE_PAR_FOR(v, 1024) kf_stage2(big, T->tw2048, v, 1, 1024);
     __syncthreads();
-    for (int st = 0; st < 5; st++) {
-        const int m = 2 << (2 * st);
-        ATDE_PAR_FOR(v, 512) kf_stage4<true>(big, T->tw2048, v, m, 512 / m);
-        __syncthreads();
+    // pass 3: radix-4 m = 128 (fstride 4), then m = 512 (fstride 1); keep slots [512, 1536), normalised
+    {
+        const int k = tid;
+        cpx x[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) x[a][q] = big[gphys(k + 128 * a + 512 * q)];
+        __syncthreads();                                  // every slot is in registers: big can be overwritten
+        {
+            const cpx t1 = tw[4 * k], t2 = tw[8 * k], t3 = tw[12 * k];
+#pragma unroll
+            for (int q = 0; q < 4; q++) kf_bfly4<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int kk = k + 128 * a;
+            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw[kk], tw[2 * kk], tw[3 * kk]);
+            // 5. normalise (norm = 1/4096); complex slot kk + 512q -> output samples 2*slot, 2*slot+1
+            cpx u, v;
+            u.r = fmul(x[a][1].r, 1.0f / 4096.0f); u.i = fmul(x[a][1].i, 1.0f / 4096.0f);
+            v.r = fmul(x[a][2].r, 1.0f / 4096.0f); v.i = fmul(x[a][2].i, 1.0f / 4096.0f);
+            big[kk] = u;                                  // slot 512 + kk
+            big[512 + kk] = v;                            // slot 1024 + kk
+        }
     }
-    // 5. normalise the analysis region [1024, 3072) (norm = 1/4096) and take the envelopes
-    float* sig = reinterpret_cast<float*>(big);
-    ATDE_PAR_FOR(i, 2048) sig[1024 + i] = fmul(sig[1024 + i], 1.0f / 4096.0f);
     __syncthreads();
     // AnalyzeGain(signal + 1024, 2048, 32, rms): 64-sample RMS, plus 8 micro-chunk RMS values each
+    const float* sig = reinterpret_cast<const float*>(big);       // sig[i] = output sample 1024 + i
     ATDE_PAR_FOR(q, 256) {
-        const float* p = sig + 1024 + 8 * q;
+        const float* p = sig + 8 * q;
         float a = 0.0f;
 #pragma unroll
         for (int i = 0; i < 8; i++) a = fadd(a, fmul(p[i], p[i]));
         micro[q] = __fsqrt_rn(__fdiv_rn(a, 8.0f));
     }
-    if (tid >= 64 && tid < 96) {
-        const int sf = tid - 64;
-        const float* p = sig + 1024 + 64 * sf;
+    if (tid >= 32 && tid < 64) {
+        const int sf = tid - 32;
+        const float* p = sig + 64 * sf;
         float a = 0.0f;
         for (int i = 0; i < 64; i++) a = fadd(a, fmul(p[i], p[i]));
         sgain[sf] = __fsqrt_rn(__fdiv_rn(a, 64.0f));
@@ -367,16 +435,27 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         sgain[32 + tid] = m[2];
         sgain[64 + tid] = m[6];
     }
-    __syncthreads();
-    ATDE_PAR_FOR(i, 96) b.gain[item * 96 + i] = sgain[i];
-    if (tid == 0) {
+    // the closing scalar work, spread over four warps: the two double chains, curHpfEnergy, the target
+    if (tid == 0 || tid == 32) {
+        const double* src = tid == 0 ? ek : ekh;
+        double a = 0.0;
+        for (int k = 0; k <= 256; k++) a = __dadd_rn(a, src[k]);
+        esum2[tid == 0 ? 0 : 1] = a;
+    } else if (tid == 64) {
         float cur = 0.0f;
         for (int i = 0; i < 32; i++) cur = fadd(cur, sgain[i]);
-        cur = __fdiv_rn(cur, 32.0f);
+        sstat[0] = __fdiv_rn(cur, 32.0f);
+    } else if (tid == 96) {
+        sstat[1] = plateau_target(sgain);
+    }
+    __syncthreads();
+    const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
+    ATDE_PAR_FOR(i, 96) b.gain[item * 96 + i] = sgain[i];
+    if (tid == 0) {
         float4 st4;
-        st4.x = hfr;
-        st4.y = cur;
-        st4.z = plateau_target(sgain);
+        st4.x = (esum2[0] > 0.0) ? __double2float_rn(__ddiv_rn(esum2[1], esum2[0])) : 0.0f;
+        st4.y = sstat[0];
+        st4.z = sstat[1];
         st4.w = sgain[31];
         reinterpret_cast<float4*>(b.gstat)[item] = st4;
     }

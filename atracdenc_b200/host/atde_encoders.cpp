@@ -53,9 +53,10 @@ void TBatchedEncoderBase::Flush()
 {
     if (!Staged)
         return;
-    const size_t units = Staged * Units;
+    // a look-ahead codec's first batch yields one frame less than it consumes
+    const size_t units = (size_t)atde_output_frames(Enc, (int64_t)Staged) * Units;
     Bytes.resize(units * UnitBytes + 8);
-    Sizes.resize(units);
+    Sizes.resize(units + 1);
     const size_t staged = Staged;
     Staged = 0;
     Check(atde_encode_batch(Enc, Stage.data(), 1, (int64_t)staged, Bytes.data(), Sizes.data()));
@@ -85,6 +86,42 @@ TAtrac1Encoder::TAtrac1Encoder(TCompressedOutputPtr&& aea, NAtrac1::TAtrac1Encod
 }
 
 TPCMEngine::TProcessLambda TAtrac1Encoder::GetLambda()
+{
+    return [this](float* data, const TPCMEngine::ProcessMeta& /*meta*/) { return Push(data); };
+}
+
+#ifndef ATDE_USE_REFERENCE_HEADERS
+namespace NAtrac3 {
+static const TContainerParams kContainerParams[8] = {        // atrac3.h:211-220
+    {66150, 192, true},   {93713, 272, true},   {104738, 304, false}, {132300, 384, false},
+    {146081, 424, false}, {176400, 512, false}, {264600, 768, false}, {352800, 1024, false}};
+const TContainerParams* GetContainerParamsForBitrate(uint32_t bitrate)
+{
+    if (bitrate == 0) bitrate = 132300;                      // LP2 by default (atrac3.cpp:45-51)
+    const TContainerParams* p = kContainerParams;
+    while (p != kContainerParams + 8 && p->Bitrate < bitrate) ++p;    // std::lower_bound
+    return p;
+}
+} // namespace NAtrac3
+#endif
+
+static atde_settings MakeAt3Settings(const NAtrac3::TAtrac3EncoderSettings& s)
+{
+    atde_settings c;
+    atde_default_settings(&c, ATDE_CODEC_ATRAC3, (int32_t)s.SourceChannels);
+    c.bitrate = s.ConteinerParams->Bitrate;                  // an exact table bitrate maps back to the same container
+    c.no_gain_control = s.NoGainControll;
+    c.no_tonal = s.NoTonalComponents;
+    c.bfu_idx_const = s.BfuIdxConst;
+    return c;
+}
+
+TAtrac3Encoder::TAtrac3Encoder(TCompressedOutputPtr&& oma, NAtrac3::TAtrac3EncoderSettings&& encoderSettings)
+    : TBatchedEncoderBase(std::move(oma), MakeAt3Settings(encoderSettings))
+{
+}
+
+TPCMEngine::TProcessLambda TAtrac3Encoder::GetLambda()
 {
     return [this](float* data, const TPCMEngine::ProcessMeta& /*meta*/) { return Push(data); };
 }

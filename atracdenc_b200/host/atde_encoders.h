@@ -2,8 +2,9 @@
 // libatde_b200.so (include/atde_b200.h).  Same class names, constructor signatures and lambda
 // semantics as
 //   NAtracDEnc::TAtrac1Encoder(TCompressedOutputPtr&&, NAtrac1::TAtrac1EncodeSettings&&)   src/atrac1denc.h:105
-// so `src/main.cpp`'s PrepareAtrac1Encoder / PCM loop (:292-340, :697-705) compile against it
-// unchanged.  Differences a caller can observe: WriteFrame calls are DEFERRED — frames are staged
+//   NAtracDEnc::TAtrac3Encoder(TCompressedOutputPtr&&, NAtrac3::TAtrac3EncoderSettings&&)  src/atrac3denc.h:131
+// so `src/main.cpp`'s PrepareAtrac1Encoder / PrepareAtrac3Encoder / PCM loop (:292-340, :342-470,
+// :697-705) compile against it unchanged.  Differences a caller can observe: WriteFrame calls are DEFERRED — frames are staged
 // and encoded on the GPU in batches; payload bytes, lengths and call order are identical, and
 // everything is flushed by Flush() or the destructor (the processor owns the container, and
 // main.cpp destroys the processor at scope exit).
@@ -11,6 +12,7 @@
 #include "atde_boundary.h"
 #include "../../include/atde_b200.h"
 
+#include <iosfwd>
 #include <stdexcept>
 
 namespace NAtracDEnc {
@@ -33,6 +35,33 @@ private:
     const uint32_t WindowMask = 0;
 };
 } // namespace NAtrac1
+
+namespace NAtrac3 {
+// src/atrac/at3/atrac3.h:33-37,211-220,260-277
+struct TContainerParams {
+    const uint32_t Bitrate;
+    const uint16_t FrameSz;
+    const bool Js;
+};
+const TContainerParams* GetContainerParamsForBitrate(uint32_t bitrate);   // TAtrac3Data::GetContainerParamsForBitrate
+struct TAtrac3EncoderSettings {
+    TAtrac3EncoderSettings(uint32_t bitrate, bool noGainControll, bool noTonalComponents, uint8_t sourceChannels,
+                           uint32_t bfuIdxConst, std::ostream* yamlLog = nullptr)
+        : ConteinerParams(GetContainerParamsForBitrate(bitrate))
+        , NoGainControll(noGainControll)
+        , NoTonalComponents(noTonalComponents)
+        , SourceChannels(sourceChannels)
+        , BfuIdxConst(bfuIdxConst)
+        , YamlLog(yamlLog)
+    { }
+    const TContainerParams* ConteinerParams;
+    const bool NoGainControll;
+    const bool NoTonalComponents;
+    const uint8_t SourceChannels;
+    const uint32_t BfuIdxConst;
+    std::ostream* YamlLog;   // accepted for signature compatibility; the GPU path does not produce the gain-control trace
+};
+} // namespace NAtrac3
 #endif
 
 // Common staging/flush machinery for all codecs.
@@ -60,6 +89,14 @@ private:
 class TAtrac1Encoder : public TBatchedEncoderBase {
 public:
     TAtrac1Encoder(TCompressedOutputPtr&& aea, NAtrac1::TAtrac1EncodeSettings&& settings);
+    TPCMEngine::TProcessLambda GetLambda() override;
+};
+
+// The first lambda call returns LOOK_AHEAD (src/atrac3denc.cpp:715-718), every later one PROCESSED;
+// one WriteFrame of exactly FrameSz bytes per PROCESSED call (src/atrac/at3/atrac3_bitstream.cpp:845).
+class TAtrac3Encoder : public TBatchedEncoderBase {
+public:
+    TAtrac3Encoder(TCompressedOutputPtr&& oma, NAtrac3::TAtrac3EncoderSettings&& encoderSettings);
     TPCMEngine::TProcessLambda GetLambda() override;
 };
 

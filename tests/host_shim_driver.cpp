@@ -1,6 +1,7 @@
 // tests/host_shim_driver.cpp — drives the C++ host shim exactly like src/main.cpp:697-716 drives
 // the reference's processors: TPCMEngine(4096) + memory reader + GetLambda() loop, capturing the
-// WriteFrame payloads to a file.  usage: driver <pcm.f32> <channels> <total_samples> <out.bin> <batch_frames>
+// WriteFrame payloads to a file.
+// usage: driver <pcm.f32> <channels> <total_samples> <out.bin> <batch_frames> [codec=1|3] [bitrate_kbit]
 #include "../atracdenc_b200/host/atde_encoders.h"
 #include <cstdio>
 #include <cstdlib>
@@ -48,13 +49,24 @@ int main(int argc, char** argv)
     fclose(f);
     try {
         TCompressedOutputPtr sink(new TFileSink(argv[4], ch));
-        std::unique_ptr<TAtrac1Encoder> proc(new TAtrac1Encoder(std::move(sink),
-            NAtrac1::TAtrac1EncodeSettings(0, NAtrac1::TAtrac1EncodeSettings::EWindowMode::EWM_AUTO, 0)));
+        const int codec = argc > 6 ? atoi(argv[6]) : 1;
+        const uint32_t kbit = argc > 7 ? (uint32_t)atoi(argv[7]) : 0;
+        std::unique_ptr<TBatchedEncoderBase> proc;
+        size_t step = 512;
+        if (codec == 1) {
+            proc.reset(new TAtrac1Encoder(std::move(sink),
+                NAtrac1::TAtrac1EncodeSettings(0, NAtrac1::TAtrac1EncodeSettings::EWindowMode::EWM_AUTO, 0)));
+        } else {
+            // src/main.cpp:671: TAtrac3EncoderSettings(bitrate * 1024, noGainControl, noTonalComponents, channels, bfuIdxConst)
+            proc.reset(new TAtrac3Encoder(std::move(sink),
+                NAtrac3::TAtrac3EncoderSettings(kbit * 1024, false, false, (uint8_t)ch, 0)));
+            step = 1024;
+        }
         proc->SetBatchFrames(atoi(argv[5]));
         TPCMEngine eng(4096, ch, TPCMEngine::TReaderPtr(new TMemReader(pcm, ch)));
         auto lambda = proc->GetLambda();
         try {
-            while (total > eng.ApplyProcess(512, lambda)) {}
+            while (total > eng.ApplyProcess(step, lambda)) {}
         } catch (const TNoDataToRead&) {}
         // processor destroyed here -> flushes the staged tail, as in main.cpp's scope exit
     } catch (const std::exception& e) {

@@ -23,10 +23,10 @@ def build_driver(so: Path, tag: str) -> Path:
     return out
 
 
-def run_driver(exe, pcm, channels, total, batch, tmp_path):
+def run_driver(exe, pcm, channels, total, batch, tmp_path, codec=1, kbit=0):
     src, dst = tmp_path / "in.f32", tmp_path / "out.bin"
     np.ascontiguousarray(pcm, np.float32).tofile(src)
-    subprocess.check_call([str(exe), str(src), str(channels), str(total), str(dst), str(batch)])
+    subprocess.check_call([str(exe), str(src), str(channels), str(total), str(dst), str(batch), str(codec), str(kbit)])
     raw = dst.read_bytes()
     sizes, payload, p = [], bytearray(), 0
     while p < len(raw):
@@ -43,8 +43,32 @@ def check(exe, tmp_path):
         assert np.array_equal(tl.pad_units(payload, sizes, 212), g["units"])
 
 
+def check_at3(exe, tmp_path, seconds=0.5):
+    """TAtrac3Encoder mirror under main.cpp's PCM pump (incl. the look-ahead drain at the end of the
+    input) against the reference encoder under the same pump."""
+    if tl.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    n = int(44100 * seconds)
+    pcm = tl.synth_rich((n + 1023) // 1024, 1024, 2, seed=61)[:n]
+    for kbit in (0, 64):
+        want, want_sizes = tl.ref_encode(3, 2, pcm.reshape(-1), total=n, bitrate_kbit=kbit)
+        for batch in (5, 4096):
+            payload, sizes = run_driver(exe, pcm, 2, n, batch, tmp_path, codec=3, kbit=kbit)
+            assert np.array_equal(sizes, want_sizes)
+            assert np.array_equal(payload, want)
+
+
 def test_host_shim_cpu_emulated(tmp_path):
     check(build_driver(tl.build_emu(), "emu"), tmp_path)
+
+
+def test_host_shim_at3_cpu_emulated(tmp_path):
+    check_at3(build_driver(tl.build_emu(), "emu"), tmp_path, seconds=0.3)
+
+
+@pytest.mark.gpu
+def test_host_shim_at3_gpu(tmp_path, gpu_lib):
+    check_at3(build_driver(ROOT / "atracdenc_b200" / "libatde_b200.so", "gpu"), tmp_path, seconds=3.0)
 
 
 @pytest.mark.gpu

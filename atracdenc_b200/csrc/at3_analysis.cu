@@ -509,25 +509,29 @@ struct Pts {
     int loc[8];
 };
 
-// BuildSubframeDivisors (atrac3denc.cpp:228-255)
+// BuildSubframeDivisors (atrac3denc.cpp:228-255): mean divisor of each 8-sample sub-frame.  Point i
+// holds its level up to sample 8*loc_i and ramps over the 8 samples of sub-frame loc_i, so a
+// sub-frame is either constant (sum of 8 equal powers of two, exact) or one point's ramp.
 ATDE_D void subframe_divisors(const DevTables* T, const Pts& p, float* out_div)
 {
-    float sd[256];
-    for (int i = 0; i < 256; i++) sd[i] = 1.0f;
-    int pos = 0;
+    int sf = 0;
     for (int i = 0; i < p.n; i++) {
-        const int last = p.loc[i] << 3;
-        float level = T->gain_level[p.level[i]];
-        const int inc = ((i + 1) < p.n ? p.level[i + 1] : 4) - p.level[i] + 15;
-        const float ginc = T->gain_interp[inc];
-        for (; pos < last && pos < 256; ++pos) sd[pos] = level;
-        for (; pos < last + 8 && pos < 256; ++pos) { sd[pos] = level; level = fmul(level, ginc); }
+        const float level0 = T->gain_level[p.level[i]];
+        for (; sf < p.loc[i] && sf < 32; ++sf) {
+            float sum = 0.0f;
+            for (int k = 0; k < 8; k++) sum = fadd(sum, level0);
+            out_div[sf] = __fdiv_rn(sum, 8.0f);
+        }
+        if (sf < 32 && sf == p.loc[i]) {
+            const int inc = ((i + 1) < p.n ? p.level[i + 1] : 4) - p.level[i] + 15;
+            const float ginc = T->gain_interp[inc];
+            float level = level0, sum = 0.0f;
+            for (int k = 0; k < 8; k++) { sum = fadd(sum, level); level = fmul(level, ginc); }
+            out_div[sf] = __fdiv_rn(sum, 8.0f);
+            ++sf;
+        }
     }
-    for (int sf = 0; sf < 32; sf++) {
-        float sum = 0.0f;
-        for (int k = 0; k < 8; k++) sum = fadd(sum, sd[sf * 8 + k]);
-        out_div[sf] = __fdiv_rn(sum, 8.0f);
-    }
+    for (; sf < 32; ++sf) out_div[sf] = 1.0f;
 }
 
 // CalcCurveEarlyMismatchScore (atrac3denc.cpp:259-297)

@@ -244,7 +244,7 @@ struct UnitCost {
 
 // Exact restatement with the complete candidate list and libstdc++'s sort order; only used when two
 // candidates that can actually be re-rounded share the same |delta| (see quant_unit).
-ATDE_D float quant_unit_exact(const float* in, int len, float mul, float inv2, signed char* m)
+ATDE_NOINLINE float quant_unit_exact(const float* in, int len, float mul, float inv2, signed char* m)
 {
     SortCand cand[128];
     int nc = 0;
@@ -328,14 +328,23 @@ ATDE_D float quant_mantissas(const float* in, int len, bool ea, float mul, float
     if (!ea || e2 == e1) return __fdiv_rn(e1, e2);
     const bool up = e2 < e1;
     const float lim = fsub(mul, 1.0f);
+    // A re-rounding moves e2 by d = (2|q| + 1) * inv2 (up) or (2|q| - 1) * inv2 (down) towards / past
+    // e1 and is accepted only if it lands closer, i.e. d < 2 * gap (up to rounding).  The gap only
+    // shrinks while the walk goes on, so a candidate with d >= 2 * gap0 + slack can never be accepted;
+    // `slack` (1e-4 relative to the energies involved, >> the few ulps the float updates can be off)
+    // keeps every borderline candidate in for the exact test.
+    const float gap0 = fabsf(fsub(e1, e2));
+    const float thr = fadd(fmul(2.0f, gap0), fmul(1e-4f, fadd(fadd(e1, e2), 1.0f)));
     int nc = 0;
     for (int j = 0; j < len; j++) {
         const float t = fmul(in[j], mul);
         const float delta = fsub(t, fadd(truncf(t), 0.5f));
         if (fabsf(delta) < 0.25f) {
-            const float aq = (float)abs((int)m[j]);
+            const int aqi = abs((int)m[j]);
+            const float aq = (float)aqi;
             const bool qual = up ? (aq < fabsf(t) && aq < lim) : (aq > fabsf(t));
-            if (qual) { ckey[nc] = fabsf(delta); cidx[nc] = (unsigned char)j; nc++; }
+            const float d = fmul((float)(up ? 2 * aqi + 1 : 2 * aqi - 1), inv2);
+            if (qual && d < thr) { ckey[nc] = fabsf(delta); cidx[nc] = (unsigned char)j; nc++; }
         }
     }
     float last = -1.0f;

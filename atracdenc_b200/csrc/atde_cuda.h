@@ -17,6 +17,7 @@
 #define ATDE_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define ATDE_HD __host__ __device__ __forceinline__
 #define ATDE_D __device__ __forceinline__
+#define ATDE_NOINLINE __device__ __noinline__
 #endif
 
 // Block-wide "parallel for": every phase between two __syncthreads() is a grid-stride loop over

@@ -27,6 +27,7 @@
 #define __align__(n) __attribute__((aligned(n)))
 #define ATDE_HD inline
 #define ATDE_D inline
+#define ATDE_NOINLINE inline
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {

@@ -297,112 +297,45 @@ ATDE_NOINLINE float quant_unit_exact(const float* in, int len, float mul, float 
     return __fdiv_rn(e1, e2);
 }
 
-// QuantMantisas (atrac_scale.cpp:40-130) of one BFU at one word length.
-//   in   scaled values of the BFU (shared memory)
-//   m    mantissas of the BFU (shared memory), written
-//   ckey / cidx   scratch for the BFU's re-rounding candidates (shared memory; BFUs > 18 only)
-//
-// The energy-aware branch of the reference sorts every candidate by |delta| and walks the sorted
-// list, re-rounding a value when that brings the quantised energy e2 closer to e1.  Restated here
-// without the full sort:
-//   * only candidates that pass the walk's own test (|m| < |t| && |m| < mul-1 when e2 < e1, |m| > |t|
-//     when e2 > e1 -- a static property of the element) can change anything, so only those are kept;
-//   * they are visited in ascending |delta| by repeated selection;
-//   * once e2 has reached or crossed e1 every later candidate is rejected (each step moves e2 by at
-//     least inv2 ~ 1e-3 in the same direction, far above the rounding error of the update), so the
-//     walk stops there.
-// With distinct |delta| among the visited candidates this is the reference's order exactly; if two
-// visited candidates tie, the library's sort order matters and quant_unit_exact redoes the block.
-ATDE_D float quant_mantissas(const float* in, int len, bool ea, float mul, float inv2, signed char* m,
-                             float* ckey, unsigned char* cidx)
+// ---- BFU geometry by 32-line row (atrac3.h:83-105): rows 0-1 hold four 8-line BFUs, rows 2-5 two
+//      16-line BFUs, rows 6-15 one 32-line BFU each, rows 16-23 half a 64-line BFU, rows 24-31 a
+//      quarter of a 128-line BFU.
+ATDE_D int elem_bfu(int i)
 {
-    float e1 = 0.0f, e2 = 0.0f;
-    for (int j = 0; j < len; j++) {
-        const float x = in[j];
-        const float t = fmul(x, mul);
-        e1 = fadd(e1, fmul(x, x));
-        const int q = __float2int_rn(t);
-        m[j] = (signed char)q;
-        e2 = fadd(e2, fmul((float)(q * q), inv2));
-    }
-    if (!ea || e2 == e1) return __fdiv_rn(e1, e2);
-    const bool up = e2 < e1;
-    const float lim = fsub(mul, 1.0f);
-    // A re-rounding moves e2 by d = (2|q| + 1) * inv2 (up) or (2|q| - 1) * inv2 (down) towards / past
-    // e1 and is accepted only if it lands closer, i.e. d < 2 * gap (up to rounding).  The gap only
-    // shrinks while the walk goes on, so a candidate with d >= 2 * gap0 + slack can never be accepted;
-    // `slack` (1e-4 relative to the energies involved, >> the few ulps the float updates can be off)
-    // keeps every borderline candidate in for the exact test.
-    const float gap0 = fabsf(fsub(e1, e2));
-    const float thr = fadd(fmul(2.0f, gap0), fmul(1e-4f, fadd(fadd(e1, e2), 1.0f)));
-    int nc = 0;
-    for (int j = 0; j < len; j++) {
-        const float t = fmul(in[j], mul);
-        const float delta = fsub(t, fadd(truncf(t), 0.5f));
-        if (fabsf(delta) < 0.25f) {
-            const int aqi = abs((int)m[j]);
-            const float aq = (float)aqi;
-            const bool qual = up ? (aq < fabsf(t) && aq < lim) : (aq > fabsf(t));
-            const float d = fmul((float)(up ? 2 * aqi + 1 : 2 * aqi - 1), inv2);
-            if (qual && d < thr) { ckey[nc] = fabsf(delta); cidx[nc] = (unsigned char)j; nc++; }
-        }
-    }
-    float last = -1.0f;
-    while (up ? (e2 < e1) : (e2 > e1)) {
-        float best = 2.0f;
-        int bi = -1, ties = 0;
-        for (int k = 0; k < nc; k++) {
-            const float key = ckey[k];
-            if (key > last) {
-                if (key < best) { best = key; bi = k; ties = 0; }
-                else if (key == best) ties++;
-            }
-        }
-        if (bi < 0) break;
-        if (ties) return quant_unit_exact(in, len, mul, inv2, m);
-        last = best;
-        const int j = cidx[bi];
-        const int q = m[j];
-        int q2 = q;
-        if (up) {
-            if (q > 0) q2++;
-            if (q < 0) q2--;
-            if (q == 0) q2 = fmul(in[j], mul) > 0.0f ? 1 : -1;
-        } else {
-            if (q > 0) q2--;
-            if (q < 0) q2++;
-        }
-        float ex = e2;
-        ex = fsub(ex, fmul((float)(q * q), inv2));
-        ex = fadd(ex, fmul((float)(q2 * q2), inv2));
-        if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) { m[j] = (signed char)q2; e2 = ex; }
-    }
-    return __fdiv_rn(e1, e2);
+    if (i < 64) return i >> 3;
+    if (i < 192) return 8 + ((i - 64) >> 4);
+    if (i < 512) return 16 + ((i - 192) >> 5);
+    if (i < 768) return 26 + ((i - 512) >> 6);
+    return 30 + ((i - 768) >> 7);
+}
+ATDE_D unsigned row_bfu_mask(int r)
+{
+    if (r < 2) return 0xFu << (4 * r);
+    if (r < 6) return 0x3u << (8 + 2 * (r - 2));
+    if (r < 16) return 1u << (16 + (r - 6));
+    if (r < 24) return 1u << (26 + ((r - 16) >> 1));
+    return 1u << (30 + ((r - 24) >> 2));
 }
 
-// TAt3SpecUnit::Provide (atrac3_bitstream.cpp:157-173): mantissas + CLC / VLC cost of one BFU.
-ATDE_D UnitCost quant_unit(const float* in, int len, int bfu, int wl, signed char* m, float* ckey, unsigned char* cidx)
+// rows (of 32 lines) touched by a set of BFUs
+ATDE_D unsigned rows_of_bfus(unsigned bm)
 {
-    const float mul = kMaxQuant[wl];
-    const float inv2 = __double2float_rn(__ddiv_rn(1.0, (double)fmul(mul, mul)));
-    UnitCost u;
-    u.err = quant_mantissas(in, len, bfu > 18 /* LOSY_NAQ_START */, mul, inv2, m, ckey, cidx);
-    // CLCEnc / VLCEnc bit counts (atrac3_bitstream.cpp:92-149)
-    if (wl > 1) {
-        u.clc = (unsigned)kClcLen[wl] * len;
-        unsigned v = 0;
-        const int off = kHuffOff[wl];
-        for (int j = 0; j < len; j++) v += kHuffBits[off + huff_index(m[j])];
-        u.vlc = v;
-    } else {
-        u.clc = 4u * len / 2;
-        unsigned v = 0;
-        for (int j = 0; j < len / 2; j++)
-            v += kHuffBits[kVlcPairIdx[3 * (m[2 * j] + 1) + (m[2 * j + 1] + 1)]];
-        u.vlc = v;
-    }
-    return u;
+    unsigned rows = ((bm & 0xFu) ? 1u : 0u) | ((bm & 0xF0u) ? 2u : 0u);
+    const unsigned p = (bm >> 8) & 0xFFu;                                  // BFUs 8..15: two per row
+    rows |= ((p & 0x03u) ? 1u << 2 : 0u) | ((p & 0x0Cu) ? 1u << 3 : 0u) | ((p & 0x30u) ? 1u << 4 : 0u) | ((p & 0xC0u) ? 1u << 5 : 0u);
+    rows |= ((bm >> 16) & 0x3FFu) << 6;                                    // BFUs 16..25: one row each
+    const unsigned q = (bm >> 26) & 0xFu;                                  // BFUs 26..29: two rows each
+    rows |= ((q & 1u) ? 0x3u << 16 : 0u) | ((q & 2u) ? 0x3u << 18 : 0u) | ((q & 4u) ? 0x3u << 20 : 0u) | ((q & 8u) ? 0x3u << 22 : 0u);
+    rows |= ((bm >> 30) & 1u) ? 0xFu << 24 : 0u;                           // BFUs 30, 31: four rows each
+    rows |= ((bm >> 31) & 1u) ? 0xFu << 28 : 0u;
+    return rows;
 }
+// (float)(1.0 / (mul * mul)) for MaxQuant[1..7] (atrac_scale.cpp:45), evaluated in double like the reference
+__device__ const float kInv2[8] = {0.0f, (float)(1.0 / 2.25), (float)(1.0 / 6.25), (float)(1.0 / 12.25), (float)(1.0 / 20.25),
+                                   (float)(1.0 / 56.25), (float)(1.0 / 240.25), (float)(1.0 / 992.25)};
+
+ATDE_D unsigned vlc_bits_of(int wl, int q) { return kHuffBits[kHuffOff[wl] + huff_index(q)]; }
+ATDE_D unsigned vlc_pair_bits(int qa, int qb) { return kHuffBits[kVlcPairIdx[3 * (qa + 1) + (qb + 1)]]; }
 
 // MSB-first bit field into a zeroed big-endian word array (value already masked to n bits);
 // fields that start beyond the buffer are dropped (the reference truncates with resize()).
@@ -419,14 +352,27 @@ ATDE_D void put_bits3(unsigned* words, int cap_bits, int pos, int n, unsigned va
     }
 }
 
+// sequential writer used by the header / tonal section (one lane, many call sites: kept out of line
+// so the hot search loop stays small in the instruction cache)
+ATDE_NOINLINE int put_seq(unsigned* words, int cap_bits, int pos, unsigned v, int n)
+{
+    put_bits3(words, cap_bits, pos, n, v & ((1u << n) - 1u));
+    return pos + n;
+}
+
 constexpr int kWordsPerCh = kMaxUnitBytes / 4 + 8;             // bitstream of one channel
 
 constexpr int kEaFirst = 288;                                  // first line of BFU 19 (BFUs > 18 re-round)
 struct PackShared {
     float sv[1024];                    // scaled spectrum of the channel
-    float ckey[1024 - kEaFirst];       // re-rounding candidates of the BFU being quantised: |delta| ...
-    unsigned char cidx[1024 - kEaFirst];   // ... and line offset inside the BFU
+    float pq[1024];                    // per line: q*q/mul^2 of the unit being quantised (energy chain input);
+                                       //   afterwards, per BFU region: |delta| of the re-rounding candidates
+    unsigned char hb[1024];            // per line: VLC bits (pairs: on the even line); afterwards: candidate line offsets
     signed char mant[1024];            // mantissas of the unit quantised last, per BFU region
+    unsigned char wl_now[32];          // word length being quantised per BFU (0 = not requested)
+    unsigned char walk_dir[32];        // 0 none, 1 e2 < e1 (round up), 2 e2 > e1 (round down)
+    float walk_thr[32];                // acceptance pre-filter per BFU
+    int walk_cnt[32];                  // candidates collected per BFU
     unsigned words[kWordsPerCh];
     unsigned cache_cv[8][32];          // clc | vlc << 16, indexed [wordlen][bfu]
     float cache_err[8][32];
@@ -436,6 +382,159 @@ struct PackShared {
     unsigned char prec[32];
     int hdr_bits;                      // header + gain info bits of this channel
 };
+
+// TAt3SpecUnit::Provide (atrac3_bitstream.cpp:157-173) = QuantMantisas (atrac_scale.cpp:40-130) + CLC /
+// VLC cost, for every BFU whose lane has `need` set, at that lane's word length `wl` — computed by the
+// whole warp together.  All 32 lanes must call it.  Phases:
+//   E   line-parallel: t = x*mul, q = rint(t), q*q/mul^2 and the VLC bits of every line of a requested BFU
+//   C   lane per BFU: the SEQUENTIAL energy sum e2 over the BFU's lines (the reference's order) + VLC sum
+//   E2  line-parallel, BFUs > 18 only (energy-aware re-rounding): collect the candidates that can
+//       change something into a compact per-BFU list
+//   W   lane per BFU: walk the candidates in ascending |delta|
+// The energy-aware branch of the reference sorts every candidate by |delta| and walks the sorted list,
+// re-rounding a value when that brings the quantised energy e2 closer to e1.  Restated without the sort:
+//   * only candidates that pass the walk's own test (|m| < |t| && |m| < mul-1 when e2 < e1, |m| > |t|
+//     when e2 > e1 -- a static property of the line) can change anything;
+//   * a re-rounding moves e2 by d = (2|q|+1)/mul^2 (up) or (2|q|-1)/mul^2 (down) and is accepted only if
+//     it lands closer to e1, i.e. d < 2*gap up to rounding; the gap only shrinks during the walk, so a
+//     candidate with d >= 2*gap0 + slack can never be accepted (slack = 1e-4 relative to the energies,
+//     far above the few ulps the float updates can be off) and is dropped;
+//   * the rest is visited in ascending |delta| by repeated selection, and the walk stops once e2 has
+//     reached or crossed e1 (every later candidate moves it further away by at least 1/mul^2 ~ 1e-3);
+//   * with distinct |delta| among the visited candidates this is the reference's order exactly; if two
+//     of them tie, the library's sort order matters and quant_unit_exact redoes the block.
+// Returns (for need lanes) clc | vlc << 16 and the energy ratio e1/e2.
+ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int start, int len, float e1, float& err_out)
+{
+    const unsigned nm = __ballot_sync(0xffffffffu, need);
+    sh.wl_now[lane] = need ? (unsigned char)wl : 0;
+    __syncwarp();
+    // ---- E ----
+    for (unsigned rows = rows_of_bfus(nm); rows; rows &= rows - 1) {
+        const int r = __ffs((int)rows) - 1;
+        const int i = 32 * r + lane;
+        const int w = sh.wl_now[elem_bfu(i)];
+        const float mul = kMaxQuant[w];
+        const float x = sh.sv[i];
+        const int q = __float2int_rn(fmul(x, mul));
+        const int qn = __shfl_down_sync(0xffffffffu, q, 1);
+        if (w) {
+            const float inv2 = kInv2[w];
+            sh.mant[i] = (signed char)q;
+            sh.pq[i] = fmul((float)(q * q), inv2);
+            sh.hb[i] = (unsigned char)(w > 1 ? vlc_bits_of(w, q) : ((lane & 1) ? 0u : vlc_pair_bits(q, qn)));
+        }
+    }
+    __syncwarp();
+    // ---- C ----
+    float e2 = 0.0f;
+    unsigned vlc = 0;
+    if (need) {
+        for (int j = 0; j < len; j++) {
+            e2 = fadd(e2, sh.pq[start + j]);
+            vlc += sh.hb[start + j];
+        }
+    }
+    const float mulw = kMaxQuant[need ? wl : 0];
+    const float inv2w = kInv2[need ? wl : 0];
+    bool used_exact = false;
+    float exact_err = 0.0f;
+    const bool walk = need && lane > 18 /* LOSY_NAQ_START */ && e2 != e1;
+    const unsigned wm = __ballot_sync(0xffffffffu, walk);
+    if (wm) {
+        // ---- E2 ----
+        const bool up = e2 < e1;
+        sh.walk_dir[lane] = walk ? (up ? 1 : 2) : 0;
+        sh.walk_thr[lane] = fadd(fmul(2.0f, fabsf(fsub(e1, e2))), fmul(1e-4f, fadd(fadd(e1, e2), 1.0f)));
+        sh.walk_cnt[lane] = 0;
+        __syncwarp();
+        for (unsigned rows = rows_of_bfus(wm); rows; rows &= rows - 1) {
+            const int r = __ffs((int)rows) - 1;
+            const int i = 32 * r + lane;
+            const int bf = elem_bfu(i);
+            const int dir = sh.walk_dir[bf];
+            if (dir) {
+                const int wq = sh.wl_now[bf];
+                const float mul = kMaxQuant[wq];
+                const float t = fmul(sh.sv[i], mul);
+                const float ad = fabsf(fsub(t, fadd(truncf(t), 0.5f)));
+                if (ad < 0.25f) {
+                    const int aqi = abs((int)sh.mant[i]);
+                    const float aq = (float)aqi;
+                    const bool qual = dir == 1 ? (aq < fabsf(t) && aq < fsub(mul, 1.0f)) : (aq > fabsf(t));
+                    const float d = fmul((float)(dir == 1 ? 2 * aqi + 1 : 2 * aqi - 1), kInv2[wq]);
+                    if (qual && d < sh.walk_thr[bf]) {
+                        const int b0 = kBlockStart[bf];
+                        const int slot = atomicAdd(&sh.walk_cnt[bf], 1);
+                        sh.pq[b0 + slot] = ad;                    // the chain inputs of this BFU are dead by now
+                        sh.hb[b0 + slot] = (unsigned char)(i - b0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- W ----
+        if (walk) {
+            int nc = sh.walk_cnt[lane];
+            float* ckey = sh.pq + start;
+            unsigned char* cidx = sh.hb + start;
+            signed char* m = sh.mant + start;
+            while ((up ? (e2 < e1) : (e2 > e1)) && nc > 0) {
+                // next candidate = smallest remaining |delta|; visited ones leave the list
+                float best = ckey[0];
+                int bi = 0, ties = 0;
+                for (int k = 1; k < nc; k++) {
+                    const float key = ckey[k];
+                    if (key < best) { best = key; bi = k; ties = 0; }
+                    else if (key == best) ties++;
+                }
+                if (ties) {
+                    // two visited candidates share |delta|: the reference's order is libstdc++'s
+                    const float er = quant_unit_exact(sh.sv + start, len, mulw, inv2w, m);
+                    unsigned v = 0;
+                    if (wl > 1) { for (int j = 0; j < len; j++) v += vlc_bits_of(wl, m[j]); }
+                    else { for (int j = 0; j < len / 2; j++) v += vlc_pair_bits(m[2 * j], m[2 * j + 1]); }
+                    vlc = v;
+                    exact_err = er;
+                    used_exact = true;
+                    break;
+                }
+                const int j = cidx[bi];
+                --nc;
+                ckey[bi] = ckey[nc];
+                cidx[bi] = cidx[nc];
+                const int q = m[j];
+                int q2 = q;
+                if (up) {
+                    if (q > 0) q2++;
+                    if (q < 0) q2--;
+                    if (q == 0) q2 = fmul(sh.sv[start + j], mulw) > 0.0f ? 1 : -1;
+                } else {
+                    if (q > 0) q2--;
+                    if (q < 0) q2++;
+                }
+                float ex = e2;
+                ex = fsub(ex, fmul((float)(q * q), inv2w));
+                ex = fadd(ex, fmul((float)(q2 * q2), inv2w));
+                if (fabsf(fsub(ex, e1)) < fabsf(fsub(e2, e1))) {
+                    if (wl > 1) {
+                        vlc += vlc_bits_of(wl, q2) - vlc_bits_of(wl, q);
+                    } else {
+                        const int other = m[j ^ 1];
+                        vlc += (j & 1) ? vlc_pair_bits(other, q2) - vlc_pair_bits(other, q)
+                                       : vlc_pair_bits(q2, other) - vlc_pair_bits(q, other);
+                    }
+                    m[j] = (signed char)q2;
+                    e2 = ex;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    err_out = used_exact ? exact_err : __fdiv_rn(e1, e2);
+    const unsigned clc = wl > 1 ? (unsigned)kClcLen[wl] * len : 4u * len / 2;
+    return clc | (vlc << 16);
+}
 
 // bits EncodeTonalComponents would emit for the current allocation (atrac3_bitstream.cpp:382-524),
 // warp-cooperative: lane t owns tonal block t.
@@ -581,8 +680,9 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
     }
     const float fix_term = fmul(fsub(1.0f, spread), fix);
     unsigned cached = 0;                                         // bit w: (lane, w) is in the cache
-    float* ckey = sh.ckey + (start >= kEaFirst ? start - kEaFirst : 0);
-    unsigned char* cidx = sh.cidx + (start >= kEaFirst ? start - kEaFirst : 0);
+    unsigned mant_wl = 0;                                        // word length whose mantissas sh.mant holds for this BFU
+    float e1 = 0.0f;                                             // QuantMantisas' e1: energy of the scaled values, sequential
+    for (int j = 0; j < len; j++) e1 = fadd(e1, fmul(sh.sv[start + j], sh.sv[start + j]));
 
     // CalcInitialNumBfu (:567-585)
     int num_bfu = g.bfu_idx_const ? g.bfu_idx_const : 32;
@@ -609,23 +709,32 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
             }
             if (lane < num_bfu && n_ton_mine && prec > 2u)
                 prec = max(2u, prec - (unsigned)min(n_ton_mine, 8));
-            // CalcSpecsBitsConsumption + ConsiderEnergyErr (:190-257): every BFU's trajectory is independent
+            // CalcSpecsBitsConsumption + ConsiderEnergyErr (:190-257): every BFU's bump chain is independent;
+            // missing (bfu, wordlen) units are quantised by the whole warp together
             unsigned cvb = 0;
-            if (lane < num_bfu) {
-                for (;;) {
-                    if (prec == 0) break;
-                    if (!((cached >> prec) & 1u)) {
-                        const UnitCost u = quant_unit(sh.sv + start, len, lane, (int)prec, sh.mant + start, ckey, cidx);
-                        sh.cache_cv[prec][lane] = u.clc | (u.vlc << 16);
-                        sh.cache_err[prec][lane] = u.err;
+            for (;;) {
+                const bool active = lane < num_bfu && prec != 0;
+                const bool need = active && !((cached >> prec) & 1u);
+                if (__any_sync(0xffffffffu, need)) {
+                    float er;
+                    const unsigned cv2 = compute_units(sh, lane, need, (int)prec, start, len, e1, er);
+                    if (need) {
+                        sh.cache_cv[prec][lane] = cv2;
+                        sh.cache_err[prec][lane] = er;
                         cached |= 1u << prec;
+                        mant_wl = prec;
                     }
-                    cvb = sh.cache_cv[prec][lane];
-                    if (lane >= 10) break;                       // BOOST_NAQ_END
-                    const float e = sh.cache_err[prec][lane];
-                    if (((e > 0.0f && e < 0.7f) || e > 1.2f) && prec < 7u) prec++;
-                    else break;
                 }
+                bool bump = false;
+                if (active) {
+                    cvb = sh.cache_cv[prec][lane];
+                    if (lane < 10) {                             // BOOST_NAQ_END
+                        const float e = sh.cache_err[prec][lane];
+                        bump = ((e > 0.0f && e < 0.7f) || e > 1.2f) && prec < 7u;
+                    }
+                }
+                if (bump) prec++;
+                if (!__any_sync(0xffffffffu, bump)) break;
             }
             const unsigned clc = warp_sum_u(prec ? (cvb & 0xffffu) : 0u);
             const unsigned vlc = warp_sum_u(prec ? (cvb >> 16) : 0u);
@@ -652,7 +761,7 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
     int pos = 0;
     if (lane == 0) {
         unsigned* W = sh.words;
-        auto put = [&](unsigned v, int n) { put_bits3(W, cap_bits, pos, n, v & ((1u << n) - 1u)); pos += n; };
+        auto put = [&](unsigned v, int n) { pos = put_seq(W, cap_bits, pos, v, n); };
         if (g.js && ch == 1) {
             put(0, 1); put(7, 3);
             for (int i = 0; i < 4; i++) put(3, 2);
@@ -754,9 +863,15 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
         const unsigned a = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += a;
     }
+    {
+        const bool redo = in_use && prec && mant_wl != prec;
+        if (__any_sync(0xffffffffu, redo)) {
+            float er;
+            compute_units(sh, lane, redo, (int)prec, start, len, e1, er);
+        }
+    }
     if (in_use && prec) {
         const signed char* m = sh.mant + start;
-        quant_unit(sh.sv + start, len, lane, (int)prec, sh.mant + start, ckey, cidx);
         int p = pos + (int)(inc - mybits);
         if (mode) {
             if (prec > 1u) {

@@ -1,8 +1,8 @@
 """CPU-only checks of two pieces of kernel logic that parity depends on, compiled for the host from
 the kernel sources (tests/cpuemu shim):
   * stdsort_dev.cuh  vs the real libstdc++ std::sort / std::partial_sort (tie order included)
-  * at3_pack.cu's quantiser (fast path with early termination, and the exact fallback) vs the
-    reference's own QuantMantisas linked from oracle/_ref."""
+  * at3_pack.cu's warp-cooperative quantiser (compute_units: fast walk with early termination and the
+    exact fallback, CLC/VLC costs) vs the reference's own QuantMantisas linked from oracle/_ref."""
 import subprocess
 from pathlib import Path
 
@@ -33,5 +33,5 @@ def test_quantiser_matches_reference(tmp_path):
         pytest.skip("oracle/_ref not built")
     ref_dir = ROOT / "oracle" / "_ref"
     exe = _build(tmp_path, "quant_check.cpp", [f"-L{ref_dir}", "-latde_ref", f"-Wl,-rpath,{ref_dir}"])
-    out = subprocess.check_output([str(exe), "60000"], text=True)
+    out = subprocess.check_output([str(exe), "500"], text=True)
     assert "mismatches=0" in out, out

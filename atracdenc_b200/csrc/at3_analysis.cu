@@ -780,12 +780,9 @@ ATDE_D float safe_energy_scale(float orig, float mod)
 
 __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) float cur[4][256];        // band samples of this frame, raw
-    __shared__ __align__(16) float curm[4][256];       // ... divided by the gain curve
-    __shared__ __align__(16) float prevw[4][256];      // stored half: window * modulated previous frame
-    __shared__ __align__(16) float pnext[4][2][256];   // previous frame: cur*win[i], (cur/div)*win[i] (for its NextOverlapScale)
+    __shared__ __align__(16) float tmp[4][512];        // MDCT input per band: stored half | windowed current frame
     __shared__ __align__(16) cpx fft[4][128];
-    __shared__ __align__(16) float sp[1024];
+    __shared__ __align__(16) float sq[7][256];         // squared terms of one band's energy sums (rare path)
     __shared__ float esum[4][8];
     __shared__ float sscale[4][4];
     __shared__ Curve scv[4][2];                        // [band][0] previous frame, [1] this frame
@@ -805,65 +802,85 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
         scv[band][which] = cv;
     }
     __syncthreads();
-    // ---- per-sample products; every sample is independent ----
+    // A band whose own curve is empty and whose overlap scale is 1 has every energy scale exactly 1.0
+    // (SafeEnergyScale(x, x)); the sequential energy sums only run for bands that touch a curve.
+    bool trivial[4];
+    bool all_trivial = true;
+#pragma unroll
+    for (int band = 0; band < 4; band++) {
+        trivial[band] = scv[band][1].n == 0 &&
+                        (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : scv[band][0].n == 0);
+        all_trivial = all_trivial && trivial[band];
+    }
+    // ---- MDCT input (atrac3denc.cpp:39-49): tmp[j] = stored half / scale, tmp[256+j] = win[255-j] * modulated cur ----
     ATDE_PAR_FOR(w, 1024) {
         const int band = w >> 8, i = w & 255;
         const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
-        const float x = bp[i];
         const Curve& cc = scv[band][1];
+        const float x = bp[i];
         const float xm = cc.n ? __fdiv_rn(x, curve_level(T, cc, i)) : x;
-        cur[band][i] = x;
-        curm[band][i] = xm;
+        float prev;
         if (f == 0) {
-            prevw[band][i] = b.prevhalf[(sc * 4 + band) * 256 + i];
+            prev = b.prevhalf[(sc * 4 + band) * 256 + i];
         } else {
-            const float y = bp[i - 256];
             const Curve& pc = scv[band][0];
-            const float ym = pc.n ? __fdiv_rn(y, curve_level(T, pc, i)) : y;
-            const float wi = T->encode_window[i];
-            prevw[band][i] = fmul(wi, ym);
-            pnext[band][0][i] = fmul(y, wi);
-            pnext[band][1][i] = fmul(ym, wi);
+            const float y = bp[i - 256];
+            prev = fmul(T->encode_window[i], pc.n ? __fdiv_rn(y, curve_level(T, pc, i)) : y);
         }
+        tmp[band][i] = cc.n ? __fdiv_rn(prev, T->gain_level[cc.level[0]]) : prev;
+        tmp[band][256 + i] = fmul(T->encode_window[255 - i], xm);
+        if (f == g.n_out - 1)                                 // the half this frame leaves behind (next batch)
+            b.prevhalf_out[(sc * 4 + band) * 256 + i] = fmul(T->encode_window[i], xm);
     }
-    __syncthreads();
-    // ---- energy chains of CalcGainEnergyScale: sequential sums, one thread per chain ----
-    //  chain 0 prevStored, 1 curOriginal, 2 curModulated, 3 nextOriginal, 4 nextModulated,
-    //  5/6 nextOriginal/nextModulated of the previous frame
-    //  A band whose own curve is empty and whose overlap scale is 1 has every scale exactly 1.0
-    //  (SafeEnergyScale(x, x)), so the chains only run for bands that touch a curve.
-    if (tid < 28) {
-        const int band = tid / 7, ch = tid % 7;
-        const bool cur_empty = scv[band][1].n == 0, prev_empty = scv[band][0].n == 0;
-        const bool trivial = cur_empty && (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : prev_empty);
-        float a = 0.0f;
-        bool run = !trivial;
-        // with an empty curve the modulated sums equal the original ones bit for bit
-        if ((ch == 2 || ch == 4) && cur_empty) run = false;
-        if (ch >= 5 && (f == 0 || prev_empty)) run = false;
-        if (run) {
-            if (ch == 0) {
-                for (int i = 0; i < 256; i++) { const float v = prevw[band][i]; a = fadd(a, fmul(v, v)); }
-            } else if (ch == 1 || ch == 2) {
-                const float* src = ch == 1 ? cur[band] : curm[band];
-                for (int i = 0; i < 256; i++) { const float v = fmul(src[i], T->encode_window[255 - i]); a = fadd(a, fmul(v, v)); }
-            } else if (ch == 3 || ch == 4) {
-                const float* src = ch == 3 ? cur[band] : curm[band];
-                for (int i = 0; i < 256; i++) { const float v = fmul(src[i], T->encode_window[i]); a = fadd(a, fmul(v, v)); }
-            } else {
-                const float* src = pnext[band][ch - 5];
-                for (int i = 0; i < 256; i++) { const float v = src[i]; a = fadd(a, fmul(v, v)); }
+    if (!all_trivial) {
+        // CalcGainEnergyScale's sequential sums (atrac3denc.cpp:189-216) for the bands that touch a curve:
+        // the squared terms are produced sample-parallel, seven threads then add them up in order.
+        //  0 prevStored  1 curOriginal  2 curModulated  3 nextOriginal  4 nextModulated
+        //  5/6 nextOriginal/nextModulated of the PREVIOUS frame (-> its NextOverlapScale)
+        for (int band = 0; band < 4; band++) {
+            if (trivial[band]) continue;
+            const Curve& cc = scv[band][1];
+            const Curve& pc = scv[band][0];
+            {
+                const int i = tid;
+                const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
+                const float x = bp[i];
+                const float xm = cc.n ? __fdiv_rn(x, curve_level(T, cc, i)) : x;
+                const float wi = T->encode_window[i], wr = T->encode_window[255 - i];
+                float prev, y = 0.0f, ym = 0.0f;
+                if (f == 0) {
+                    prev = b.prevhalf[(sc * 4 + band) * 256 + i];
+                } else {
+                    y = bp[i - 256];
+                    ym = pc.n ? __fdiv_rn(y, curve_level(T, pc, i)) : y;
+                    prev = fmul(wi, ym);
+                }
+                float v;
+                sq[0][i] = fmul(prev, prev);
+                v = fmul(x, wr);  sq[1][i] = fmul(v, v);
+                v = fmul(xm, wr); sq[2][i] = fmul(v, v);
+                v = fmul(x, wi);  sq[3][i] = fmul(v, v);
+                v = fmul(xm, wi); sq[4][i] = fmul(v, v);
+                v = fmul(y, wi);  sq[5][i] = fmul(v, v);
+                v = fmul(ym, wi); sq[6][i] = fmul(v, v);
             }
+            __syncthreads();
+            if (tid < 7) {
+                float a = 0.0f;
+                for (int i = 0; i < 256; i += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(&sq[tid][i]);
+                    a = fadd(a, q.x); a = fadd(a, q.y); a = fadd(a, q.z); a = fadd(a, q.w);
+                }
+                esum[band][tid] = a;
+            }
+            __syncthreads();
         }
-        esum[band][ch] = a;
     }
-    __syncthreads();
     if (tid < 4) {
         const int band = tid;
         const Curve& cc = scv[band][1];
         const bool cur_empty = cc.n == 0, prev_empty = scv[band][0].n == 0;
-        const bool trivial = cur_empty && (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : prev_empty);
-        if (trivial) {
+        if (trivial[band]) {
             sscale[band][0] = 1.0f; sscale[band][1] = 1.0f; sscale[band][2] = 1.0f; sscale[band][3] = 1.0f;
         } else {
             float pos_scale;                                       // PrevOverlapGainScale[channel][band]
@@ -884,30 +901,16 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
             sscale[band][3] = safe_energy_scale(nxt_orig, nxt_mod);
         }
     }
+    __syncthreads();
     // ---- MDCT-512 per band: fold + pre-twiddle into kissfft's gather order (mdct.h:56-76) ----
-    //   tmp[j]       = prevw[j] / scale           j < 256   (Modulate divides bufCur by GainLevel[first point])
-    //   tmp[256 + j] = win[255-j] * curm[j]
     ATDE_PAR_FOR(w, 512) {
         const int band = w >> 7, slot = w & 127;
-        const Curve& cc = scv[band][1];
-        const bool mod = cc.n != 0;
-        const float scale = mod ? T->gain_level[cc.level[0]] : 1.0f;
+        const float* in = tmp[band];
         const int i = T->perm128[slot];
         const int n = 2 * i;                                 // N = 512, n4 = 128, n34 = 384, n54 = 640
-        const int ia0 = 383 - n, ib0 = 128 + n;
-        const int ia1 = (n < 128) ? 384 + n : n - 128;
-        const int ib1 = (n < 128) ? 127 - n : 639 - n;
-        float v[4];
-        const int idx[4] = {ia0, ia1, ib0, ib1};
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int j = idx[q];
-            if (j < 256) v[q] = mod ? __fdiv_rn(prevw[band][j], scale) : prevw[band][j];
-            else v[q] = fmul(T->encode_window[255 - (j - 256)], curm[band][j - 256]);
-        }
         float r0, i0;
-        if (n < 128) { r0 = fadd(v[0], v[1]); i0 = fsub(v[2], v[3]); }
-        else         { r0 = fsub(v[0], v[1]); i0 = fadd(v[2], v[3]); }
+        if (n < 128) { r0 = fadd(in[383 - n], in[384 + n]); i0 = fsub(in[128 + n], in[127 - n]); }
+        else         { r0 = fsub(in[383 - n], in[n - 128]); i0 = fadd(in[128 + n], in[639 - n]); }
         const float cc2 = T->sincos512[n], ss = T->sincos512[n + 1];
         cpx X;
         X.r = fadd(fmul(r0, cc2), fmul(i0, ss));
@@ -929,7 +932,10 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
         }
         __syncthreads();
     }
-    // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55)
+    // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55); straight to global
+    const size_t unit = ((size_t)s * g.n_out + f) * g.C + c;
+    float* out = b.specs + unit * 1024;
+    float* sp = &tmp[0][0];                                  // the MDCT input is dead: reuse as the output tile
     ATDE_PAR_FOR(w, 512) {
         const int band = w >> 7, i = w & 127;
         const int n = 2 * i;
@@ -943,17 +949,9 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
         sp[band * 256 + pb] = vb;
     }
     __syncthreads();
-    const size_t unit = ((size_t)s * g.n_out + f) * g.C + c;
-    ATDE_PAR_FOR(i, 1024) b.specs[unit * 1024 + i] = sp[i];
+    ATDE_PAR_FOR(i, 1024) out[i] = sp[i];
     if (tid < 16) b.gscale[unit * 16 + tid] = sscale[tid >> 2][tid & 3];
-    if (f == g.n_out - 1) {
-        // state for the next batch: the half this frame leaves behind and its NextOverlapScale
-        ATDE_PAR_FOR(w, 1024) {
-            const int band = w >> 8, i = w & 255;
-            b.prevhalf_out[(sc * 4 + band) * 256 + i] = fmul(T->encode_window[i], curm[band][i]);
-        }
-        if (tid < 4) b.next_scale_out[sc * 4 + tid] = sscale[tid][3];
-    }
+    if (f == g.n_out - 1 && tid < 4) b.next_scale_out[sc * 4 + tid] = sscale[tid][3];
 }
 
 void launch_mdct(const Geometry& g, const Buffers& b, cudaStream_t st)

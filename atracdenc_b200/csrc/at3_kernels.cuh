@@ -115,6 +115,7 @@ void launch_gain_analysis(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_gain_scan(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_gain_curve(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_mdct(const Geometry& g, const Buffers& b, cudaStream_t st);
+void launch_loudterm(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_loudness(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_scale_tonal(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_alloc_pack(const Geometry& g, const Buffers& b, cudaStream_t st);

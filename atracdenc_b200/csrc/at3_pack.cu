@@ -73,6 +73,16 @@ ATDE_D int huff_index(int m)
 
 ATDE_D int bfu_band(int i) { return i >= 30 ? 3 : (i >= 26 ? 2 : (i >= 18 ? 1 : 0)); }     // BlocksPerBand {0,18,26,30,32}
 
+// BFU of spectral line i (atrac3.h:83-105)
+ATDE_D int elem_bfu_s(int i)
+{
+    if (i < 64) return i >> 3;
+    if (i < 192) return 8 + ((i - 64) >> 4);
+    if (i < 512) return 16 + ((i - 192) >> 5);
+    if (i < 768) return 26 + ((i - 512) >> 6);
+    return 30 + ((i - 768) >> 7);
+}
+
 ATDE_D unsigned warp_sum_u(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 
 // lower_bound over ScaleTable + TScaler::Scale (atrac_scale.cpp:141-172); writes the scaled values
@@ -103,6 +113,33 @@ ATDE_D int scale_block(const DevTables* T, float* v, int len, float& energy)
     return lo;
 }
 
+// TScaler::Scale split for the frame path: (1) per BFU, sequential — max |x|, scale factor index, energy
+// (len is a multiple of 8; 8 lines per trip keep the shared-memory loads off the dependent chain);
+// (2) per line, parallel — x / scale with the +-0.99999 clip.
+ATDE_D int scale_analyse(const DevTables* T, const float* v, int len, float& energy, float& scale)
+{
+    float mx = 0.0f, en = 0.0f;
+    for (int j = 0; j < len; j += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(v + j);
+        const float4 c = *reinterpret_cast<const float4*>(v + j + 4);
+        const float x[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            mx = fmaxf(mx, fabsf(x[k]));
+            en = fadd(en, fmul(x[k], x[k]));
+        }
+    }
+    if (mx > 1.0f) mx = 1.0f;
+    int lo = 0, hi = 63;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (T->scale_table[mid] < mx) lo = mid + 1; else hi = mid;
+    }
+    scale = T->scale_table[lo];
+    energy = en;
+    return lo;
+}
+
 // =====================================================================================
 // K7: tonal extraction + scaling, one warp per channel-frame
 // =====================================================================================
@@ -114,6 +151,7 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
     __shared__ float run_val[kScaleWarps][32][5];
     __shared__ short run_start[kScaleWarps][32];
     __shared__ signed char run_len[kScaleWarps][32];
+    __shared__ double lg_all[kScaleWarps][640];
 
     const DevTables* __restrict__ T = b.tab;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -128,29 +166,24 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
 
     const int start = kBlockStart[lane], len = kBlockStart[lane + 1] - kBlockStart[lane];
     TonalList* tl = b.tonal + unit;
-    if (lane == 0) {
-        // sce->Loudness (atrac3denc.cpp:811-820): l += e * Frame * curve, one sequential chain; runs
-        // on the lane that has no flatness work while lanes 8..28 do theirs
-        const float* gs = b.gscale + (size_t)unit * 16;
-        const float fr[4] = {gs[2], gs[6], gs[10], gs[14]};
-        float l = 0.0f;
-        for (int i = 0; i < 1024; i++) {
-            const float e = fmul(sv[i], sv[i]);
-            l = fadd(l, fmul(fmul(e, fr[i >> 8]), T->loud_curve[i]));
-        }
-        b.chloud[unit] = l;
-    }
-    __syncwarp();
     if (!g.no_tonal) {
+        // CalcSpectralFlatnessPerBfu: geometric / arithmetic mean of the line energies, in double.
+        // The logs of the 640 lines of BFUs 8..28 are taken line-parallel; the two sums stay sequential.
+        const double floor_d = (double)1e-12f;
+        double* lg = lg_all[wib];
+        for (int i = 64 + lane; i < 704; i += 32) {
+            const float ef = fmul(sv[i], sv[i]);
+            const double e = (double)fmaxf(0.0f, ef);
+            lg[i - 64] = g_log(e > floor_d ? e : floor_d);
+        }
+        __syncwarp();
         if (lane >= 8 && lane < 29) {
-            // CalcSpectralFlatnessPerBfu: geometric / arithmetic mean of the line energies, in double
-            const double floor_d = (double)1e-12f;
             double arith = 0.0, mean_log = 0.0;
             for (int i = 0; i < len; i++) {
                 const float ef = fmul(sv[start + i], sv[start + i]);
                 const double e = (double)fmaxf(0.0f, ef);
                 arith = __dadd_rn(arith, e);
-                mean_log = __dadd_rn(mean_log, g_log(e > floor_d ? e : floor_d));
+                mean_log = __dadd_rn(mean_log, lg[start - 64 + i]);
             }
             arith = __ddiv_rn(arith, (double)len);
             mean_log = __ddiv_rn(mean_log, (double)len);
@@ -180,7 +213,7 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
                 }
             }
         }
-        __syncwarp();                                            // lane 0 has finished reading the spectrum
+        __syncwarp();
         for (int n = 0; n < run_len[wib][lane]; n++) sv[run_start[wib][lane] + n] = 0.0f;
         __syncwarp();
         if (lane == 0) {
@@ -218,12 +251,65 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
         tl->n = 0;
     }
     // ScaleFrame on what is left of the spectrum
-    float en;
-    const int sfi = scale_block(T, sv + start, len, en);
+    float en, scale;
+    const int sfi = scale_analyse(T, sv + start, len, en, scale);
     b.sfi[(size_t)unit * 32 + lane] = (unsigned char)sfi;
     b.energy[(size_t)unit * 32 + lane] = en;
-    __syncwarp();
-    for (int i = lane; i < 1024; i += 32) gsp[i] = sv[i];
+    for (int i = lane; i < 1024; i += 32) {
+        const float sc = __shfl_sync(0xffffffffu, scale, elem_bfu_s(i));
+        float q = __fdiv_rn(sv[i], sc);
+        if (fabsf(q) >= 1.0f) q = (q > 0.0f) ? 0.99999f : -0.99999f;
+        gsp[i] = q;
+    }
+}
+
+// =====================================================================================
+// loudness term of every channel-frame (atrac3denc.cpp:811-820): l += e * Frame * curve over the 1024
+// lines in order -- one sequential chain per channel-frame, so ONE LANE per channel-frame; the
+// spectra are staged through shared memory in 32x32 tiles to keep the global reads coalesced.
+// =====================================================================================
+constexpr int kLoudWarps = 4;
+
+__global__ void __launch_bounds__(kLoudWarps * 32) at3_loudterm_kernel(Geometry g, Buffers b)
+{
+    __shared__ float tile_all[kLoudWarps][32][33];
+    const DevTables* __restrict__ T = b.tab;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long total = (long long)g.S * g.n_out * g.C;
+    const long long unit0 = ((long long)blockIdx.x * kLoudWarps + wib) * 32;
+    if (unit0 >= total) return;
+    float (*tile)[33] = tile_all[wib];
+    const long long mine = unit0 + lane;
+    const bool live = mine < total;
+    float fr[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    if (live) {
+        const float* gs = b.gscale + (size_t)mine * 16;
+        fr[0] = gs[2]; fr[1] = gs[6]; fr[2] = gs[10]; fr[3] = gs[14];
+    }
+    const int nrows = (int)min(32LL, total - unit0);
+    float l = 0.0f;
+    for (int t = 0; t < 32; t++) {
+        for (int r = 0; r < nrows; r++)
+            tile[r][lane] = b.specs[(size_t)(unit0 + r) * 1024 + 32 * t + lane];
+        __syncwarp();
+        const float f = fr[t >> 3];
+        if (live) {
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const float x = tile[lane][k];
+                l = fadd(l, fmul(fmul(fmul(x, x), f), T->loud_curve[32 * t + k]));
+            }
+        }
+        __syncwarp();
+    }
+    if (live) b.chloud[mine] = l;
+}
+
+void launch_loudterm(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    const long long total = (long long)g.S * g.n_out * g.C;
+    const long long per_block = kLoudWarps * 32;
+    ATDE_LAUNCH(at3_loudterm_kernel, (unsigned)((total + per_block - 1) / per_block), kLoudWarps * 32, 0, st, g, b);
 }
 
 void launch_scale_tonal(const Geometry& g, const Buffers& b, cudaStream_t st)
@@ -363,7 +449,7 @@ ATDE_NOINLINE int put_seq(unsigned* words, int cap_bits, int pos, unsigned v, in
 constexpr int kWordsPerCh = kMaxUnitBytes / 4 + 8;             // bitstream of one channel
 
 constexpr int kEaFirst = 288;                                  // first line of BFU 19 (BFUs > 18 re-round)
-struct PackShared {
+struct __align__(16) PackShared {
     float sv[1024];                    // scaled spectrum of the channel
     float pq[1024];                    // per line: q*q/mul^2 of the unit being quantised (energy chain input);
                                        //   afterwards, per BFU region: |delta| of the re-rounding candidates
@@ -430,9 +516,16 @@ ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int s
     float e2 = 0.0f;
     unsigned vlc = 0;
     if (need) {
-        for (int j = 0; j < len; j++) {
-            e2 = fadd(e2, sh.pq[start + j]);
-            vlc += sh.hb[start + j];
+        // 8 lines per trip (every BFU length is a multiple of 8): the loads stay off the dependent chain
+        for (int j = 0; j < len; j += 8) {
+            const float4 a = *reinterpret_cast<const float4*>(sh.pq + start + j);
+            const float4 c = *reinterpret_cast<const float4*>(sh.pq + start + j + 4);
+            const uint2 h = *reinterpret_cast<const uint2*>(sh.hb + start + j);
+            e2 = fadd(e2, a.x); e2 = fadd(e2, a.y); e2 = fadd(e2, a.z); e2 = fadd(e2, a.w);
+            e2 = fadd(e2, c.x); e2 = fadd(e2, c.y); e2 = fadd(e2, c.z); e2 = fadd(e2, c.w);
+            // byte sums: add the two words, then fold the four byte lanes (each lane <= 2*8 bits ... < 256)
+            const unsigned t2 = (h.x & 0x00ff00ffu) + ((h.x >> 8) & 0x00ff00ffu) + (h.y & 0x00ff00ffu) + ((h.y >> 8) & 0x00ff00ffu);
+            vlc += (t2 & 0xffffu) + (t2 >> 16);
         }
     }
     const float mulw = kMaxQuant[need ? wl : 0];
@@ -475,19 +568,22 @@ ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int s
         __syncwarp();
         // ---- W ----
         if (walk) {
-            int nc = sh.walk_cnt[lane];
-            float* ckey = sh.pq + start;
-            unsigned char* cidx = sh.hb + start;
+            const int nc = sh.walk_cnt[lane];
+            const float* ckey = sh.pq + start;
+            const unsigned char* cidx = sh.hb + start;
             signed char* m = sh.mant + start;
-            while ((up ? (e2 < e1) : (e2 > e1)) && nc > 0) {
-                // next candidate = smallest remaining |delta|; visited ones leave the list
-                float best = ckey[0];
-                int bi = 0, ties = 0;
-                for (int k = 1; k < nc; k++) {
+            float last = -1.0f;
+            while (up ? (e2 < e1) : (e2 > e1)) {
+                float best = 2.0f;
+                int bi = -1, ties = 0;
+                for (int k = 0; k < nc; k++) {
                     const float key = ckey[k];
-                    if (key < best) { best = key; bi = k; ties = 0; }
-                    else if (key == best) ties++;
+                    if (key > last) {
+                        if (key < best) { best = key; bi = k; ties = 0; }
+                        else if (key == best) ties++;
+                    }
                 }
+                if (bi < 0) break;
                 if (ties) {
                     // two visited candidates share |delta|: the reference's order is libstdc++'s
                     const float er = quant_unit_exact(sh.sv + start, len, mulw, inv2w, m);
@@ -499,10 +595,8 @@ ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int s
                     used_exact = true;
                     break;
                 }
+                last = best;
                 const int j = cidx[bi];
-                --nc;
-                ckey[bi] = ckey[nc];
-                cidx[bi] = cidx[nc];
                 const int q = m[j];
                 int q2 = q;
                 if (up) {
@@ -682,7 +776,12 @@ __global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers 
     unsigned cached = 0;                                         // bit w: (lane, w) is in the cache
     unsigned mant_wl = 0;                                        // word length whose mantissas sh.mant holds for this BFU
     float e1 = 0.0f;                                             // QuantMantisas' e1: energy of the scaled values, sequential
-    for (int j = 0; j < len; j++) e1 = fadd(e1, fmul(sh.sv[start + j], sh.sv[start + j]));
+    for (int j = 0; j < len; j += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(sh.sv + start + j);
+        const float4 c = *reinterpret_cast<const float4*>(sh.sv + start + j + 4);
+        e1 = fadd(e1, fmul(a.x, a.x)); e1 = fadd(e1, fmul(a.y, a.y)); e1 = fadd(e1, fmul(a.z, a.z)); e1 = fadd(e1, fmul(a.w, a.w));
+        e1 = fadd(e1, fmul(c.x, c.x)); e1 = fadd(e1, fmul(c.y, c.y)); e1 = fadd(e1, fmul(c.z, c.z)); e1 = fadd(e1, fmul(c.w, c.w));
+    }
 
     // CalcInitialNumBfu (:567-585)
     int num_bfu = g.bfu_idx_const ? g.bfu_idx_const : 32;

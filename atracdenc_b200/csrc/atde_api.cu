@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -397,10 +398,10 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
             e->launches += 3;
         }
         { KernelTimer kt(e, w.stream, 0); launch_mdct(g, b, w.stream); }
+        { KernelTimer kt(e, w.stream, 1); launch_loudterm(g, b, w.stream); launch_loudness(g, b, w.stream); }
         { KernelTimer kt(e, w.stream, 5); launch_scale_tonal(g, b, w.stream); }
-        { KernelTimer kt(e, w.stream, 1); launch_loudness(g, b, w.stream); }
         { KernelTimer kt(e, w.stream, 2); launch_alloc_pack(g, b, w.stream); }
-        e->launches += 4;
+        e->launches += 5;
     }
     launch_carry(g, b, w.stream);
     e->launches += 2;
@@ -605,7 +606,11 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
     const size_t out_per_stream = (size_t)n_out * e->units_per_frame * e->unit_bytes;
     const size_t units_per_stream = (size_t)n_out * e->units_per_frame;
     // chunk by streams so H2D of chunk k+1 overlaps compute of chunk k (two pipeline slots)
-    const size_t target_floats = (size_t)48 << 20;                              // ~192 MiB of PCM per chunk
+    size_t target_floats = (size_t)48 << 20;                                    // ~192 MiB of PCM per chunk
+    if (const char* env = getenv("ATDE_CHUNK_MIB")) {                           // tuning knob (MiB of PCM per chunk)
+        const long v = atol(env);
+        if (v > 0) target_floats = (size_t)v << 18;
+    }
     int chunk = (int)(target_floats / pcm_per_stream);
     if (chunk < 1) chunk = 1;
     if (chunk > S) chunk = S;

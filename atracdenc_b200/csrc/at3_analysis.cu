@@ -199,7 +199,8 @@ ATDE_D float plateau_target(const float* in)
     return use_plateau ? level : in[n - 1];
 }
 
-constexpr int kGainThreads = 128;
+constexpr int kGainThreads = 128;         // FFT threads
+constexpr int kGainBlock = kGainThreads + 32;   // + one helper warp for the double-precision hfr sums
 
 // The 2048-point buffer is padded by 8 elements per 128 so that the stride-128 accesses of the
 // middle pass spread over all shared-memory banks.
@@ -220,7 +221,7 @@ ATDE_D int gphys(int i) { return i + ((i >> 7) << 3); }
 // by the structural zeros is exact, so the values equal the full transform's (up to the sign of zero,
 // which no consumer can see: the output is squared).
 // Only output samples [1024, 3072) are consumed (AnalyzeGain), i.e. complex slots [512, 1536).
-__global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buffers b)
+__global__ void __launch_bounds__(kGainBlock) at3_gain_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) cpx big[2048 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ __align__(16) cpx fwd[256];
@@ -276,17 +277,31 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         }
     }
     __syncthreads();
-    // 2a. per-bin terms of the high-frequency energy ratio (upsampler.cpp:99-118); the two sequential
-    //     double sums are taken at the very end so that nothing waits for them.
+    // 2a. high-frequency energy ratio (upsampler.cpp:99-118): two SEQUENTIAL double sums over the 257
+    //     bins.  The helper warp takes them (per-bin terms lane-parallel, then both chains interleaved
+    //     on one lane) while the four FFT warps run the inverse transform; they only meet again at the
+    //     final barrier.
     const int lcb = T->low_cut_bin;
-    ATDE_PAR_FOR(k, 257) {
-        const double r = (double)freq[k].r, i = (double)freq[k].i;
-        const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
-        float H = 0.0f;
-        if (k >= lcb + 2) H = 1.0f;
-        else if (k >= lcb) H = T->hpf_h[k - lcb];
-        ek[k] = e;
-        ekh[k] = __dmul_rn(__dmul_rn(e, (double)H), (double)H);
+    if (tid >= kGainThreads) {
+        const int hl = tid - kGainThreads;
+        for (int k = hl; k < 257; k += 32) {
+            const double r = (double)freq[k].r, i = (double)freq[k].i;
+            const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
+            float H = 0.0f;
+            if (k >= lcb + 2) H = 1.0f;
+            else if (k >= lcb) H = T->hpf_h[k - lcb];
+            ek[k] = e;
+            ekh[k] = __dmul_rn(__dmul_rn(e, (double)H), (double)H);
+        }
+        __syncwarp();
+        if (hl == 0) {
+            double tot = 0.0, hi = 0.0;
+#pragma unroll 4
+            for (int k = 0; k <= 256; k++) { tot = __dadd_rn(tot, ek[k]); hi = __dadd_rn(hi, ekh[k]); }
+            esum2[0] = tot; esum2[1] = hi;
+        }
+        __syncthreads();                                      // the final barrier of the FFT warps
+        return;
     }
     // 3/4. inverse FFT input Y[k] = 8*X[k]*H[k] (Nyquist bin halved), kiss_fftri pre-processing
     //      (kiss_fftr.c:131-151) with Y[2048-k] == 0, and pass 1 of the inverse FFT.
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         cpx* dst = big + gphys(8 * grp);
         dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3; dst[4] = o4; dst[5] = o5; dst[6] = o6; dst[7] = o7;
     }
-    __syncthreads();
+    atde_named_barrier(1, kGainThreads);
     // pass 2: radix-4 m = 8 (fstride 64), then m = 32 (fstride 16)
     {
         const int k = tid & 7, base = (tid >> 3) << 7;
@@ -372,7 +387,7 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
 #pragma unroll
             for (int q = 0; q < 4; q++) big[gphys(base + k + 8 * a + 32 * q)] = x[a][q];
     }
-    __syncthreads();
+    atde_named_barrier(1, kGainThreads);
     // pass 3: radix-4 m = 128 (fstride 4), then m = 512 (fstride 1); keep slots [512, 1536), normalised
     {
         const int k = tid;
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int q = 0; q < 4; q++) x[a][q] = big[gphys(k + 128 * a + 512 * q)];
-        __syncthreads();                                  // every slot is in registers: big can be overwritten
+        atde_named_barrier(1, kGainThreads);                                  // every slot is in registers: big can be overwritten
         {
             const cpx t1 = tw[4 * k], t2 = tw[8 * k], t3 = tw[12 * k];
 #pragma unroll
@@ -399,10 +414,10 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
             big[512 + kk] = v;                            // slot 1024 + kk
         }
     }
-    __syncthreads();
+    atde_named_barrier(1, kGainThreads);
     // AnalyzeGain(signal + 1024, 2048, 32, rms): 64-sample RMS, plus 8 micro-chunk RMS values each
     const float* sig = reinterpret_cast<const float*>(big);       // sig[i] = output sample 1024 + i
-    ATDE_PAR_FOR(q, 256) {
+    for (int q = tid; q < 256; q += kGainThreads) {
         const float* p = sig + 8 * q;
         float a = 0.0f;
 #pragma unroll
@@ -416,7 +431,7 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         for (int i = 0; i < 64; i++) a = fadd(a, fmul(p[i], p[i]));
         sgain[sf] = __fsqrt_rn(__fdiv_rn(a, 64.0f));
     }
-    __syncthreads();
+    atde_named_barrier(1, kGainThreads);
     if (tid < 32) {
         float m[8];
 #pragma unroll
@@ -435,13 +450,8 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
         sgain[32 + tid] = m[2];
         sgain[64 + tid] = m[6];
     }
-    // the closing scalar work, spread over four warps: the two double chains, curHpfEnergy, the target
-    if (tid == 0 || tid == 32) {
-        const double* src = tid == 0 ? ek : ekh;
-        double a = 0.0;
-        for (int k = 0; k <= 256; k++) a = __dadd_rn(a, src[k]);
-        esum2[tid == 0 ? 0 : 1] = a;
-    } else if (tid == 64) {
+    // the closing scalar work: curHpfEnergy and the plateau target on two different warps
+    if (tid == 64) {
         float cur = 0.0f;
         for (int i = 0; i < 32; i++) cur = fadd(cur, sgain[i]);
         sstat[0] = __fdiv_rn(cur, 32.0f);
@@ -450,7 +460,7 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
     }
     __syncthreads();
     const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
-    ATDE_PAR_FOR(i, 96) b.gain[item * 96 + i] = sgain[i];
+    if (tid < 96) b.gain[item * 96 + tid] = sgain[tid];
     if (tid == 0) {
         float4 st4;
         st4.x = (esum2[0] > 0.0) ? __double2float_rn(__ddiv_rn(esum2[1], esum2[0])) : 0.0f;
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(kGainThreads) at3_gain_kernel(Geometry g, Buff
 void launch_gain_analysis(const Geometry& g, const Buffers& b, cudaStream_t st)
 {
     dim3 grid(g.n_out, g.C * kGainBands, g.S);
-    ATDE_LAUNCH(at3_gain_kernel, grid, kGainThreads, 0, st, g, b);
+    ATDE_LAUNCH(at3_gain_kernel, grid, kGainBlock, 0, st, g, b);
 }
 
 // =====================================================================================

@@ -18,6 +18,11 @@
 #define ATDE_HD __host__ __device__ __forceinline__
 #define ATDE_D __device__ __forceinline__
 #define ATDE_NOINLINE __device__ __noinline__
+// named barrier over `count` threads (a multiple of 32) of the block
+__device__ __forceinline__ void atde_named_barrier(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 #endif
 
 // Block-wide "parallel for": every phase between two __syncthreads() is a grid-stride loop over

@@ -45,6 +45,9 @@ namespace cuemu {
 struct BlockCtx {
     int nthreads, nwarps;
     pthread_barrier_t bar;
+    pthread_barrier_t named[8];     // bar.sync id, count (id 1..7), initialised on first use
+    int named_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    pthread_mutex_t named_mu = PTHREAD_MUTEX_INITIALIZER;
     std::vector<pthread_barrier_t> wbar;
     std::vector<uint64_t> xchg;   // [nwarps][32]
     explicit BlockCtx(int nt) : nthreads(nt), nwarps((nt + 31) / 32), wbar(nwarps), xchg((size_t)nwarps * 32)
@@ -58,6 +61,7 @@ struct BlockCtx {
     ~BlockCtx()
     {
         pthread_barrier_destroy(&bar);
+        for (int i = 0; i < 8; i++) if (named_count[i]) pthread_barrier_destroy(&named[i]);
         for (auto& b : wbar) pthread_barrier_destroy(&b);
     }
 };
@@ -87,6 +91,15 @@ extern thread_local dim3 blockDim, gridDim;
 static const int warpSize = 32;
 
 inline void __syncthreads() { pthread_barrier_wait(&cuemu::ctx->bar); }
+// named barrier over `count` threads of the block (PTX bar.sync id, count)
+inline void atde_named_barrier(int id, int count)
+{
+    cuemu::BlockCtx* c = cuemu::ctx;
+    pthread_mutex_lock(&c->named_mu);
+    if (!c->named_count[id]) { pthread_barrier_init(&c->named[id], nullptr, count); c->named_count[id] = count; }
+    pthread_mutex_unlock(&c->named_mu);
+    pthread_barrier_wait(&c->named[id]);
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::warp_barrier(); }
 inline void __threadfence_block() {}
 inline void __threadfence() {}

@@ -26,24 +26,30 @@
 namespace atde {
 namespace at3 {
 
-__constant__ float c_qmf3[48];        // QmfWindow, qmf.cpp:36-45
+__constant__ __align__(8) float c_qmf3[48];        // QmfWindow, qmf.cpp:36-45
 
 void upload_qmf_window(const float w[48]) { cudaMemcpyToSymbol(c_qmf3, w, 48 * sizeof(float)); }
 
 // 48-tap half-band split of one output pair (qmf.h:54-63): sequential sums, taps in order.
-// src[2j + 1 - 2i + 47 - 47]: caller passes src so that tap i reads src[2j + 48 - 2i] (even phase)
-// and src[2j + 48 - 2i + 1]... identical convention to at1_kernels.cu:qmf_pair.
-ATDE_D void qmf_pair3(const float* src, int j, float& lower, float& upper)
+// The source array is stored with the two samples of every pair SWAPPED (element k at index k^1), so
+// the 8-byte load at the even index e = 2j + 48 - 2i returns (src[e+1], src[e]) = (sample for W[2i],
+// sample for W[2i+1]); the two running sums (lower, upper) then advance with one packed multiply and
+// one packed add per tap pair.
+ATDE_D void qmf_pair3(const float* src_swapped, int j, f32x2 one, float& lower, float& upper)
 {
-    float lo = 0.0f, up = 0.0f;
+    f32x2 acc;
+    acc.x = 0.0f; acc.y = 0.0f;
 #pragma unroll
     for (int i = 0; i < 24; i++) {
-        const float2 v = *reinterpret_cast<const float2*>(src + 2 * j + 48 - 2 * i);
-        lo = fadd(lo, fmul(c_qmf3[2 * i], v.y));
-        up = fadd(up, fmul(c_qmf3[2 * i + 1], v.x));
+        const float2 v = *reinterpret_cast<const float2*>(src_swapped + 2 * j + 48 - 2 * i);
+        const float2 c = *reinterpret_cast<const float2*>(c_qmf3 + 2 * i);
+        f32x2 vv, cc;
+        vv.x = v.x; vv.y = v.y;
+        cc.x = c.x; cc.y = c.y;
+        acc = add2(acc, mul2(cc, vv), one);
     }
-    upper = fsub(lo, up);
-    lower = fadd(lo, up);
+    upper = fsub(acc.x, acc.y);
+    lower = fadd(acc.x, acc.y);
 }
 
 // =====================================================================================
@@ -86,25 +92,27 @@ __global__ void __launch_bounds__(256) at3_qmf_kernel(Geometry g, Buffers b)
     const int u0 = blockIdx.x * kQT;
     const int m0 = u0 - 128;
     const bool started = b.started[s] != 0;
+    f32x2 one;
+    one.x = g.one; one.y = g.one;
 
     for (int c = 0; c < g.C; c++) {
         ATDE_PAR_FOR(t, kQX) {
             const long long n = 4LL * m0 - 144 + t;
-            x[t] = fmul(virt_pcm(g, b, s, c, n, started), 0.25f);       // data / 4.0 (atrac3denc.cpp:704)
+            x[t ^ 1] = fmul(virt_pcm(g, b, s, c, n, started), 0.25f);   // data / 4.0 (atrac3denc.cpp:704); pairs swapped
         }
         __syncthreads();
         ATDE_PAR_FOR(j, kQS1) {
             float l, h;
-            qmf_pair3(x, j, l, h);
-            s1lo[j] = l;
-            s1hi[j] = h;
+            qmf_pair3(x, j, one, l, h);
+            s1lo[j ^ 1] = l;
+            s1hi[j ^ 1] = h;
         }
         __syncthreads();
         // Qmf2(Buf1) -> subs[0], subs[1];  Qmf3(Buf2) -> subs[3], subs[2]   (atrac3_qmf.h:37-41)
         ATDE_PAR_FOR(q2, 2 * kQT) {
             const int which = q2 >= kQT, q = q2 - which * kQT;
             float l, h;
-            qmf_pair3(which ? s1hi : s1lo, q, l, h);
+            qmf_pair3(which ? s1hi : s1lo, q, one, l, h);
             if (!which) { outb[c][0][q] = l; outb[c][1][q] = h; }
             else        { outb[c][3][q] = l; outb[c][2][q] = h; }
         }

@@ -77,6 +77,7 @@ struct Geometry {
     int frame_sz;                     // container frame size in bytes
     int no_gain, no_tonal;
     int bfu_idx_const;
+    float one;                        // 1.0f, opaque to the compiler (atde_cuda.h: add2)
 };
 
 struct Buffers {

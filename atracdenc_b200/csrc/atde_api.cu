@@ -350,6 +350,7 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
     g.no_gain = e->cfg.no_gain_control != 0;
     g.no_tonal = e->cfg.no_tonal != 0;
     g.bfu_idx_const = (int)e->cfg.bfu_idx_const;
+    g.one = 1.0f;
     const size_t units = (size_t)S * (size_t)(g.n_out > 0 ? g.n_out : 1) * C;
     const size_t items = (size_t)S * C * kGainBands * (size_t)(g.n_out > 0 ? g.n_out : 1);
     int rc;

@@ -48,4 +48,40 @@ ATDE_D cpx cmul(cpx a, cpx b)
     return m;
 }
 
+// ---- packed fp32 pairs (Blackwell FMUL2 / FFMA2): two IEEE-rn operations per issue slot ----
+// mul2 is a plain packed multiply.  add2 must stay an un-fused add: ptxas contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with --fmad=false, which would change the
+// rounding.  So add2 is spelled fma(a, ONE, b) with ONE = (1.0f, 1.0f) taken from a kernel parameter
+// (opaque to the compiler): a*1 + b rounds once, exactly like a + b, and nothing can be folded into it.
+struct f32x2 { float x, y; };
+#ifdef ATDE_CPU_EMU
+ATDE_D f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; r.x = fmul(a.x, b.x); r.y = fmul(a.y, b.y); return r; }
+ATDE_D f32x2 add2(f32x2 a, f32x2 b, f32x2 /*one*/) { f32x2 r; r.x = fadd(a.x, b.x); r.y = fadd(a.y, b.y); return r; }
+#else
+ATDE_D unsigned long long pack2(f32x2 a)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+ATDE_D f32x2 unpack2(unsigned long long v)
+{
+    f32x2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+ATDE_D f32x2 mul2(f32x2 a, f32x2 b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(r);
+}
+ATDE_D f32x2 add2(f32x2 a, f32x2 b, f32x2 one)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(one)), "l"(pack2(b)));
+    return unpack2(r);
+}
+#endif
+
 } // namespace atde

@@ -26,45 +26,78 @@
 namespace atde {
 namespace at3 {
 
-__constant__ __align__(8) float c_qmf3[48];        // QmfWindow, qmf.cpp:36-45
 
-void upload_qmf_window(const float w[48]) { cudaMemcpyToSymbol(c_qmf3, w, 48 * sizeof(float)); }
 
-// 48-tap half-band split of one output pair (qmf.h:54-63): sequential sums, taps in order.
-// The source array is stored with the two samples of every pair SWAPPED (element k at index k^1), so
-// the 8-byte load at the even index e = 2j + 48 - 2i returns (src[e+1], src[e]) = (sample for W[2i],
-// sample for W[2i+1]); the two running sums (lower, upper) then advance with one packed multiply and
-// one packed add per tap pair.
-ATDE_D void qmf_pair3(const float* src_swapped, int j, f32x2 one, float& lower, float& upper)
+// 48-tap half-band split (qmf.h:54-63), register-tiled: one thread task = kQR consecutive output
+// pairs j0 .. j0+kQR-1 of one source array.  Output j is
+//     lower = sum_{i=0..23} W[2i]   * src[2j + 49 - 2i]        (sequential, i ascending)
+//     upper = sum_{i=0..23} W[2i+1] * src[2j + 48 - 2i]
+// i.e. tap pair i multiplies the ALIGNED sample pair p = j + 24 - i = (src[2p], src[2p+1]) by
+// (W[2i+1], W[2i]); the two running sums advance with one packed multiply and one packed add per tap
+// pair.  The kQR outputs of a task share their sample pairs (31 distinct pairs for 8 outputs), which
+// are loaded once into registers: 16 x LDS.128 per 384 packed-math instructions instead of one
+// LDS.64 per tap pair — the kernel is bound by the FP32 pipe, not by shared-memory bandwidth.
+// Arrays are stored with one float4 of padding after every four (qphys) so that the 64-byte thread
+// stride of the task loads spreads over all banks.
+constexpr int kQR = 8;
+ATDE_HD int qphys(int e) { return e + ((e >> 4) << 2); }
+
+__constant__ __align__(8) float c_qmf3p[48];       // tap pairs (W[2i+1], W[2i])
+
+void upload_qmf_window(const float w[48])
 {
-    f32x2 acc;
-    acc.x = 0.0f; acc.y = 0.0f;
+    float p[48];
+    for (int i = 0; i < 24; i++) { p[2 * i] = w[2 * i + 1]; p[2 * i + 1] = w[2 * i]; }
+    cudaMemcpyToSymbol(c_qmf3p, p, 48 * sizeof(float));
+}
+
+// src: padded array; task: outputs 8*task .. 8*task+7.  lower[r] / upper[r] as TQmf::Analysis returns them.
+ATDE_D void qmf_task(const float* src, const float* cw, int task, f32x2 one, float* lower, float* upper)
+{
+    f32x2 xp[4 * kQR];                               // sample pairs 8*task .. 8*task+31
+    const float4* q = reinterpret_cast<const float4*>(src + qphys(2 * kQR * task));
+#pragma unroll
+    for (int u = 0; u < 2 * kQR; u++) {
+        const float4 v = q[u + (u >> 2)];
+        xp[2 * u].x = v.x; xp[2 * u].y = v.y;
+        xp[2 * u + 1].x = v.z; xp[2 * u + 1].y = v.w;
+    }
+    f32x2 acc[kQR];
+#pragma unroll
+    for (int r = 0; r < kQR; r++) { acc[r].x = 0.0f; acc[r].y = 0.0f; }
 #pragma unroll
     for (int i = 0; i < 24; i++) {
-        const float2 v = *reinterpret_cast<const float2*>(src_swapped + 2 * j + 48 - 2 * i);
-        const float2 c = *reinterpret_cast<const float2*>(c_qmf3 + 2 * i);
-        f32x2 vv, cc;
-        vv.x = v.x; vv.y = v.y;
+        const float2 c = *reinterpret_cast<const float2*>(cw + 2 * i);
+        f32x2 cc;
         cc.x = c.x; cc.y = c.y;
-        acc = add2(acc, mul2(cc, vv), one);
+#pragma unroll
+        for (int r = 0; r < kQR; r++) acc[r] = add2(acc[r], mul2(cc, xp[r + 24 - i]), one);
     }
-    upper = fsub(acc.x, acc.y);
-    lower = fadd(acc.x, acc.y);
+#pragma unroll
+    for (int r = 0; r < kQR; r++) {                  // acc.x = upper sum, acc.y = lower sum (qmf.h:60-62)
+        upper[r] = fsub(acc[r].y, acc[r].x);
+        lower[r] = fadd(acc[r].y, acc[r].x);
+    }
 }
 
 // =====================================================================================
 // K1: PCM -> four 11 kHz bands per channel (two QMF stages), optional M/S matrixing
 // =====================================================================================
-// One block = kQT consecutive band samples u of one stream (both channels).
+// One block = kQT consecutive band samples u of one stream; threads 0..127 work on channel 0,
+// threads 128..255 on channel 1.
 //   band sample u <-> m = u - 128 (sample m of the extended sequence, 256 per frame)
 //   stage-1 output index k (512 per frame) feeds stage 2: band m reads s1[2m-47 .. 2m+1]
 //   input sample n (1024 per frame): s1[k] reads x[2k-47 .. 2k+1]
 // Tile-local arrays (m0 = first band sample of the tile):
-//   s1[j] = stage-1 sample k = 2*m0 - 48 + j,  j in [0, 2*kQT + 48)     (tap read: s1[2q + 48 - 2i (+1)], q = m - m0)
-//   x[t]  = input sample n = 4*m0 - 144 + t,   t in [0, 4*kQT + 144)    (tap read: x[2j + 48 - 2i (+1)])
-constexpr int kQT = 512;
+//   s1[j] = stage-1 sample k = 2*m0 - 48 + j,  j in [0, kQS1 = 1024)  -> 128 tasks per channel
+//   x[t]  = input sample n = 4*m0 - 144 + t,   t in [0, kQX = 2096)
+//   stage 2: 488 outputs per half-band = 61 tasks each
+constexpr int kQT = 488;
 constexpr int kQS1 = 2 * kQT + 48;
-constexpr int kQX = 4 * kQT + 144;
+constexpr int kQX = 2 * kQS1 + 48;
+static_assert(kQS1 == 128 * kQR && kQT % kQR == 0, "tile geometry");
+constexpr int kQXP = kQX + (kQX / 16 + 1) * 4;       // padded sizes
+constexpr int kQS1P = kQS1 + (kQS1 / 16 + 1) * 4;
 
 ATDE_D float virt_pcm(const Geometry& g, const Buffers& b, int s, int c, long long n, bool started)
 {
@@ -81,54 +114,78 @@ ATDE_D float virt_pcm(const Geometry& g, const Buffers& b, int s, int c, long lo
     return b.pcm[((size_t)s * g.N * 1024 + (size_t)n) * g.C + c];
 }
 
-__global__ void __launch_bounds__(256) at3_qmf_kernel(Geometry g, Buffers b)
+__global__ void __launch_bounds__(256, 2) at3_qmf_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) float x[kQX];
-    __shared__ __align__(16) float s1lo[kQS1];
-    __shared__ __align__(16) float s1hi[kQS1];
-    __shared__ __align__(16) float outb[2][4][kQT];
+    __shared__ __align__(16) float xs[2][kQXP];          // input tile per channel; later the output tile
+    __shared__ __align__(16) float s1[2][2][kQS1P];      // [channel][lo, hi]
+    __shared__ __align__(8) float cw[48];
 
     const int s = blockIdx.y;
     const int u0 = blockIdx.x * kQT;
     const int m0 = u0 - 128;
     const bool started = b.started[s] != 0;
+    const int tid = threadIdx.x;
+    const int ch = tid >> 7, t7 = tid & 127;
     f32x2 one;
     one.x = g.one; one.y = g.one;
 
-    for (int c = 0; c < g.C; c++) {
+    if (tid < 48) cw[tid] = c_qmf3p[tid];
+    {
+        const long long n0 = 4LL * m0 - 144 - (started ? 1024 : 0);    // tile sample 0 as an index into b.pcm
+        const long long nlim = (long long)g.N * 1024;
         ATDE_PAR_FOR(t, kQX) {
-            const long long n = 4LL * m0 - 144 + t;
-            x[t ^ 1] = fmul(virt_pcm(g, b, s, c, n, started), 0.25f);   // data / 4.0 (atrac3denc.cpp:704); pairs swapped
+            const long long nn = n0 + t;
+            float v0, v1 = 0.0f;
+            if (nn >= 0 && nn < nlim) {
+                if (g.C == 2) {
+                    const float2 v = *reinterpret_cast<const float2*>(b.pcm + ((size_t)s * g.N * 1024 + (size_t)nn) * 2);
+                    v0 = v.x; v1 = v.y;
+                } else {
+                    v0 = b.pcm[(size_t)s * g.N * 1024 + (size_t)nn];
+                }
+            } else {
+                const long long n = 4LL * m0 - 144 + t;
+                v0 = virt_pcm(g, b, s, 0, n, started);
+                if (g.C == 2) v1 = virt_pcm(g, b, s, 1, n, started);
+            }
+            xs[0][qphys(t)] = fmul(v0, 0.25f);                   // data / 4.0 (atrac3denc.cpp:704)
+            xs[1][qphys(t)] = fmul(v1, 0.25f);
         }
-        __syncthreads();
-        ATDE_PAR_FOR(j, kQS1) {
-            float l, h;
-            qmf_pair3(x, j, one, l, h);
-            s1lo[j ^ 1] = l;
-            s1hi[j ^ 1] = h;
-        }
-        __syncthreads();
-        // Qmf2(Buf1) -> subs[0], subs[1];  Qmf3(Buf2) -> subs[3], subs[2]   (atrac3_qmf.h:37-41)
-        ATDE_PAR_FOR(q2, 2 * kQT) {
-            const int which = q2 >= kQT, q = q2 - which * kQT;
-            float l, h;
-            qmf_pair3(which ? s1hi : s1lo, q, one, l, h);
-            if (!which) { outb[c][0][q] = l; outb[c][1][q] = h; }
-            else        { outb[c][3][q] = l; outb[c][2][q] = h; }
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    if (ch < g.C) {
+        float lo[kQR], hi[kQR];
+        qmf_task(xs[ch], cw, t7, one, lo, hi);
+        float4* dl = reinterpret_cast<float4*>(&s1[ch][0][qphys(kQR * t7)]);
+        float4* dh = reinterpret_cast<float4*>(&s1[ch][1][qphys(kQR * t7)]);
+        dl[0] = make_float4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+        dh[0] = make_float4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+    }
+    __syncthreads();
+    // Qmf2(Buf1) -> subs[0], subs[1];  Qmf3(Buf2) -> subs[3], subs[2]   (atrac3_qmf.h:37-41)
+    float* outb = &xs[0][0];                                     // [channel][band][kQT], the input tile is dead
+    static_assert(2 * 4 * kQT <= 2 * kQXP, "output tile fits the input tile");
+    if (ch < g.C && t7 < 2 * (kQT / kQR)) {
+        const int which = t7 >= kQT / kQR, task = t7 - which * (kQT / kQR);
+        float lo[kQR], hi[kQR];
+        qmf_task(s1[ch][which], cw, task, one, lo, hi);
+        float* ol = outb + (ch * 4 + (which ? 3 : 0)) * kQT + kQR * task;
+        float* oh = outb + (ch * 4 + (which ? 2 : 1)) * kQT + kQR * task;
+#pragma unroll
+        for (int r = 0; r < kQR; r++) { ol[r] = lo[r]; oh[r] = hi[r]; }
+    }
+    __syncthreads();
     const int nvalid = min(kQT, g.BL - u0);
     ATDE_PAR_FOR(w, 4 * kQT) {
         const int band = w / kQT, q = w - band * kQT;
         if (q < nvalid) {
             if (g.js) {
-                const float l = outb[0][band][q], r = outb[1][band][q];
+                const float l = outb[band * kQT + q], r = outb[(4 + band) * kQT + q];
                 b.bands[(((size_t)s * 2 + 0) * 4 + band) * g.BL + u0 + q] = fmul(fadd(l, r), 0.5f);
                 b.bands[(((size_t)s * 2 + 1) * 4 + band) * g.BL + u0 + q] = fmul(fsub(l, r), 0.5f);
             } else {
                 for (int c = 0; c < g.C; c++)
-                    b.bands[(((size_t)s * g.C + c) * 4 + band) * g.BL + u0 + q] = outb[c][band][q];
+                    b.bands[(((size_t)s * g.C + c) * 4 + band) * g.BL + u0 + q] = outb[(c * 4 + band) * kQT + q];
             }
         }
     }

@@ -853,75 +853,77 @@ ATDE_D float safe_energy_scale(float orig, float mod)
     return (fabsf(sc) < inf && sc > 0.0f) ? sc : 1.0f;
 }
 
-__global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
+// One WARP per (stream, frame, channel); the four MDCT-512 of the unit run side by side, 8 lanes per
+// band, with no block-wide barrier.
+//   phase A  load the band samples of this and the previous frame (coalesced float4), divide by the
+//            gain curves, window, store the four 512-sample MDCT inputs to the warp's tile
+//   phase B  fold + pre-twiddle (mdct.h:56-76) straight into kissfft's gather order; lane k of a band
+//            owns gather blocks k and k+8 (8 consecutive slots each) and runs the two innermost stages
+//            (radix-2 m=1, radix-4 m=2) on registers
+//   exchange through the tile so that lane k holds elements k + 8a + 32b
+//   phase C  radix-4 m=8 over a, radix-4 m=32 over b on registers, post-twiddle (mdct.h:92-101),
+//            spectrum staged in the tile and written out as coalesced float4
+// Every butterfly keeps kissfft's operation order (kissfft_dev.cuh), so the regrouping is exact.
+constexpr int kMdctWarps = 4;
+constexpr int kMdctBandStride = 520;                 // floats; keeps float4 alignment, shifts banks by 8
+constexpr int kMdctXchStride = 152;                  // cpx per band in the exchange layout (16 blocks x 9, +8)
+constexpr int kMdctOutStride = 264;
+
+__global__ void __launch_bounds__(kMdctWarps * 32, 4) at3_mdct_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) float tmp[4][512];        // MDCT input per band: stored half | windowed current frame
-    __shared__ __align__(16) cpx fft[4][128];
-    __shared__ __align__(16) float sq[7][256];         // squared terms of one band's energy sums (rare path)
-    __shared__ float esum[4][8];
-    __shared__ float sscale[4][4];
-    __shared__ Curve scv[4][2];                        // [band][0] previous frame, [1] this frame
+    __shared__ __align__(16) float tile[kMdctWarps][4 * kMdctBandStride];
+    __shared__ __align__(16) float s_sincos[256];
+    __shared__ __align__(16) float s_win[256];
+    __shared__ __align__(16) cpx s_tw[128];
+    __shared__ Curve s_cv[kMdctWarps][4][2];         // [band][0] previous frame, [1] this frame
+    __shared__ float s_esum[kMdctWarps][4][8];
 
     const DevTables* __restrict__ T = b.tab;
-    const int f = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
-    const int tid = threadIdx.x;
-    const size_t sc = (size_t)s * g.C + c;
-
-    if (tid < 8) {
-        const int band = tid >> 1, which = tid & 1;
-        Curve cv;
-        cv.n = 0;
-        const int ff = f - 1 + which;
-        if (!g.no_gain && band < kGainBands && ff >= 0)
-            cv = b.curves[(sc * 4 + band) * g.n_out + ff];
-        scv[band][which] = cv;
-    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ATDE_PAR_FOR(i, 256) { s_sincos[i] = T->sincos512[i]; s_win[i] = T->encode_window[i]; }
+    ATDE_PAR_FOR(i, 128) s_tw[i] = T->tw128[i];
     __syncthreads();
-    // A band whose own curve is empty and whose overlap scale is 1 has every energy scale exactly 1.0
-    // (SafeEnergyScale(x, x)); the sequential energy sums only run for bands that touch a curve.
-    bool trivial[4];
-    bool all_trivial = true;
-#pragma unroll
-    for (int band = 0; band < 4; band++) {
-        trivial[band] = scv[band][1].n == 0 &&
-                        (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : scv[band][0].n == 0);
-        all_trivial = all_trivial && trivial[band];
-    }
-    // ---- MDCT input (atrac3denc.cpp:39-49): tmp[j] = stored half / scale, tmp[256+j] = win[255-j] * modulated cur ----
-    ATDE_PAR_FOR(w, 1024) {
-        const int band = w >> 8, i = w & 255;
-        const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
-        const Curve& cc = scv[band][1];
-        const float x = bp[i];
-        const float xm = cc.n ? __fdiv_rn(x, curve_level(T, cc, i)) : x;
-        float prev;
-        if (f == 0) {
-            prev = b.prevhalf[(sc * 4 + band) * 256 + i];
-        } else {
-            const Curve& pc = scv[band][0];
-            const float y = bp[i - 256];
-            prev = fmul(T->encode_window[i], pc.n ? __fdiv_rn(y, curve_level(T, pc, i)) : y);
+
+    float* tl = tile[warp];
+    const long long n_units = (long long)g.S * g.n_out * g.C;
+    for (long long unit = (long long)blockIdx.x * kMdctWarps + warp; unit < n_units;
+         unit += (long long)gridDim.x * kMdctWarps) {
+        const int c = (int)(unit % g.C);
+        const long long sf = unit / g.C;
+        const int f = (int)(sf % g.n_out), s = (int)(sf / g.n_out);
+        const size_t sc = (size_t)s * g.C + c;
+
+        __syncwarp();                                    // previous unit's tile reads are done
+        if (lane < 8) {
+            const int band = lane >> 1, which = lane & 1;
+            Curve cv;
+            cv.n = 0;
+            const int ff = f - 1 + which;
+            if (!g.no_gain && band < kGainBands && ff >= 0)
+                cv = b.curves[(sc * 4 + band) * g.n_out + ff];
+            s_cv[warp][band][which] = cv;
         }
-        tmp[band][i] = cc.n ? __fdiv_rn(prev, T->gain_level[cc.level[0]]) : prev;
-        tmp[band][256 + i] = fmul(T->encode_window[255 - i], xm);
-        if (f == g.n_out - 1)                                 // the half this frame leaves behind (next batch)
-            b.prevhalf_out[(sc * 4 + band) * 256 + i] = fmul(T->encode_window[i], xm);
-    }
-    if (!all_trivial) {
-        // CalcGainEnergyScale's sequential sums (atrac3denc.cpp:189-216) for the bands that touch a curve:
-        // the squared terms are produced sample-parallel, seven threads then add them up in order.
+        __syncwarp();
+        // A band whose own curve is empty and whose overlap scale is 1 has every energy scale exactly 1.0
+        // (SafeEnergyScale(x, x)); the sequential energy sums only run for bands that touch a curve.
+        bool trivial[4];
+#pragma unroll
+        for (int band = 0; band < 4; band++)
+            trivial[band] = s_cv[warp][band][1].n == 0 &&
+                            (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : s_cv[warp][band][0].n == 0);
+        // ---- CalcGainEnergyScale's sequential sums (atrac3denc.cpp:189-216), bands that touch a curve only:
+        // squared terms sample-parallel into the tile, seven lanes then add them up in order.
         //  0 prevStored  1 curOriginal  2 curModulated  3 nextOriginal  4 nextModulated
         //  5/6 nextOriginal/nextModulated of the PREVIOUS frame (-> its NextOverlapScale)
         for (int band = 0; band < 4; band++) {
             if (trivial[band]) continue;
-            const Curve& cc = scv[band][1];
-            const Curve& pc = scv[band][0];
-            {
-                const int i = tid;
-                const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
+            const Curve& cc = s_cv[warp][band][1];
+            const Curve& pc = s_cv[warp][band][0];
+            const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
+            for (int i = lane; i < 256; i += 32) {
                 const float x = bp[i];
                 const float xm = cc.n ? __fdiv_rn(x, curve_level(T, cc, i)) : x;
-                const float wi = T->encode_window[i], wr = T->encode_window[255 - i];
+                const float wi = s_win[i], wr = s_win[255 - i];
                 float prev, y = 0.0f, ym = 0.0f;
                 if (f == 0) {
                     prev = b.prevhalf[(sc * 4 + band) * 256 + i];
@@ -931,108 +933,177 @@ __global__ void __launch_bounds__(256) at3_mdct_kernel(Geometry g, Buffers b)
                     prev = fmul(wi, ym);
                 }
                 float v;
-                sq[0][i] = fmul(prev, prev);
-                v = fmul(x, wr);  sq[1][i] = fmul(v, v);
-                v = fmul(xm, wr); sq[2][i] = fmul(v, v);
-                v = fmul(x, wi);  sq[3][i] = fmul(v, v);
-                v = fmul(xm, wi); sq[4][i] = fmul(v, v);
-                v = fmul(y, wi);  sq[5][i] = fmul(v, v);
-                v = fmul(ym, wi); sq[6][i] = fmul(v, v);
+                tl[0 * 256 + i] = fmul(prev, prev);
+                v = fmul(x, wr);  tl[1 * 256 + i] = fmul(v, v);
+                v = fmul(xm, wr); tl[2 * 256 + i] = fmul(v, v);
+                v = fmul(x, wi);  tl[3 * 256 + i] = fmul(v, v);
+                v = fmul(xm, wi); tl[4 * 256 + i] = fmul(v, v);
+                v = fmul(y, wi);  tl[5 * 256 + i] = fmul(v, v);
+                v = fmul(ym, wi); tl[6 * 256 + i] = fmul(v, v);
             }
-            __syncthreads();
-            if (tid < 7) {
+            __syncwarp();
+            if (lane < 7) {
                 float a = 0.0f;
                 for (int i = 0; i < 256; i += 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(&sq[tid][i]);
+                    const float4 q = *reinterpret_cast<const float4*>(&tl[lane * 256 + i]);
                     a = fadd(a, q.x); a = fadd(a, q.y); a = fadd(a, q.z); a = fadd(a, q.w);
                 }
-                esum[band][tid] = a;
+                s_esum[warp][band][lane] = a;
             }
-            __syncthreads();
+            __syncwarp();
+        }
+        if (lane < 4) {
+            const int band = lane;
+            const Curve& cc = s_cv[warp][band][1];
+            const bool cur_empty = cc.n == 0, prev_empty = s_cv[warp][band][0].n == 0;
+            float sc0 = 1.0f, sc1 = 1.0f, sc2 = 1.0f, sc3 = 1.0f;
+            if (!trivial[band]) {
+                const float* es = s_esum[warp][band];
+                float pos_scale;                                       // PrevOverlapGainScale[channel][band]
+                if (f == 0) pos_scale = b.next_scale[sc * 4 + band];
+                else if (prev_empty) pos_scale = 1.0f;                 // SafeEnergyScale(e, e)
+                else pos_scale = safe_energy_scale(es[5], es[6]);
+                const float inf = __int_as_float(0x7f800000);
+                if (!(fabsf(pos_scale) < inf) || pos_scale <= 0.0f) pos_scale = 1.0f;
+                const float prev_div = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
+                const float prev_stored = es[0];
+                const float prev_orig = fmul(prev_stored, pos_scale);
+                const float prev_mod = __fdiv_rn(prev_stored, fmul(prev_div, prev_div));
+                const float cur_orig = es[1], cur_mod = cur_empty ? es[1] : es[2];
+                const float nxt_orig = es[3], nxt_mod = cur_empty ? es[3] : es[4];
+                sc0 = safe_energy_scale(prev_orig, prev_mod);
+                sc1 = safe_energy_scale(cur_orig, cur_mod);
+                sc2 = safe_energy_scale(fadd(prev_orig, cur_orig), fadd(prev_mod, cur_mod));
+                sc3 = safe_energy_scale(nxt_orig, nxt_mod);
+            }
+            *reinterpret_cast<float4*>(&b.gscale[(size_t)unit * 16 + band * 4]) = make_float4(sc0, sc1, sc2, sc3);
+            if (f == g.n_out - 1) b.next_scale_out[sc * 4 + band] = sc3;
+        }
+        // ---- phase A: MDCT input (atrac3denc.cpp:39-49): in[j] = stored half / scale, in[256+j] = win[255-j] * modulated cur
+#pragma unroll 1
+        for (int band = 0; band < 4; band++) {
+            // BL = 128 + 256 L: every band row and every frame inside it starts 16-byte aligned
+            const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
+            const Curve& cc = s_cv[warp][band][1];
+            const Curve& pc = s_cv[warp][band][0];
+            float* in = tl + band * kMdctBandStride;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i0 = 4 * (lane + 32 * h);
+                float x[4], y[4], pv[4], cu[4];
+                {
+                    const float4 q = *reinterpret_cast<const float4*>(bp + i0);
+                    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+                }
+                if (f == 0) {
+                    const float4 q = *reinterpret_cast<const float4*>(b.prevhalf + (sc * 4 + band) * 256 + i0);
+                    pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
+                } else {
+                    const float4 q = *reinterpret_cast<const float4*>(bp + i0 - 256);
+                    y[0] = q.x; y[1] = q.y; y[2] = q.z; y[3] = q.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int i = i0 + e;
+                    const float xm = cc.n ? __fdiv_rn(x[e], curve_level(T, cc, i)) : x[e];
+                    if (f != 0) pv[e] = fmul(s_win[i], pc.n ? __fdiv_rn(y[e], curve_level(T, pc, i)) : y[e]);
+                    if (cc.n) pv[e] = __fdiv_rn(pv[e], T->gain_level[cc.level[0]]);
+                    cu[e] = fmul(s_win[255 - i], xm);
+                    if (f == g.n_out - 1)                             // the half this frame leaves behind (next batch)
+                        b.prevhalf_out[(sc * 4 + band) * 256 + i] = fmul(s_win[i], xm);
+                }
+                *reinterpret_cast<float4*>(in + i0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                *reinterpret_cast<float4*>(in + 256 + i0) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+            }
+        }
+        __syncwarp();
+        // ---- phase B: fold + pre-twiddle + the two innermost FFT stages on gather blocks k and k+8
+        const int band = lane >> 3, k = lane & 7;
+        cpx e[4][4];                                       // after the exchange: element k + 8a + 32b
+        {
+            const float* in = tl + band * kMdctBandStride;
+            cpx v[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    // slot = 64h + 8k + j of the 4x4x4x2 digit reversal: i = d0 + 4 d1 + 16 d2 + 64 d3
+                    const int i = (2 * h + (k >> 2)) + 4 * (k & 3) + 16 * (j >> 1) + 64 * (j & 1);
+                    const int n = 2 * i;                         // N = 512, n4 = 128, n34 = 384, n54 = 640
+                    float r0, i0;
+                    if (n < 128) { r0 = fadd(in[383 - n], in[384 + n]); i0 = fsub(in[128 + n], in[127 - n]); }
+                    else         { r0 = fsub(in[383 - n], in[n - 128]); i0 = fadd(in[128 + n], in[639 - n]); }
+                    const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
+                    v[h][j].r = fadd(fmul(r0, cs.x), fmul(i0, cs.y));
+                    v[h][j].i = fsub(fmul(i0, cs.x), fmul(r0, cs.y));
+                }
+                // radix-2, m = 1 (fstride 64): pairs (2q, 2q+1), twiddle tw[0]
+#pragma unroll
+                for (int q = 0; q < 4; q++) kf_bfly2(v[h][2 * q], v[h][2 * q + 1], s_tw[0]);
+                // radix-4, m = 2 (fstride 16): elements kk + 2q, twiddles tw[16 kk q]
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++)
+                    kf_bfly4<false>(v[h][kk], v[h][kk + 2], v[h][kk + 4], v[h][kk + 6],
+                                    s_tw[16 * kk], s_tw[32 * kk], s_tw[48 * kk]);
+            }
+            __syncwarp();                                  // every lane has read its MDCT input
+            cpx* xch = reinterpret_cast<cpx*>(tl) + band * kMdctXchStride;
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) xch[(k + 8 * h) * 9 + j] = v[h][j];
+            __syncwarp();
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int bq = 0; bq < 4; bq++) e[a][bq] = xch[(a + 4 * bq) * 9 + k];
+        }
+        // ---- phase C: radix-4 m = 8 (fstride 4) over a, radix-4 m = 32 (fstride 1) over b
+        {
+            const cpx t1 = s_tw[4 * k], t2 = s_tw[8 * k], t3 = s_tw[12 * k];
+#pragma unroll
+            for (int bq = 0; bq < 4; bq++) kf_bfly4<false>(e[0][bq], e[1][bq], e[2][bq], e[3][bq], t1, t2, t3);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int v = k + 8 * a;
+            kf_bfly4<false>(e[a][0], e[a][1], e[a][2], e[a][3], s_tw[v], s_tw[2 * v], s_tw[3 * v]);
+        }
+        __syncwarp();                                      // exchange reads done: the tile becomes the output stage
+        // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55)
+        {
+            float* sp = tl + band * kMdctOutStride;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int bq = 0; bq < 4; bq++) {
+                    const int n = 2 * (k + 8 * a + 32 * bq);
+                    const cpx z = e[a][bq];
+                    const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
+                    const float va = fsub(fmul(-z.r, cs.x), fmul(z.i, cs.y));
+                    const float vb = fadd(fmul(-z.r, cs.y), fmul(z.i, cs.x));
+                    int pa = n, pb = 255 - n;
+                    if (band & 1) { pa = 255 - pa; pb = 255 - pb; }
+                    sp[pa] = va;
+                    sp[pb] = vb;
+                }
+        }
+        __syncwarp();
+        float4* out = reinterpret_cast<float4*>(b.specs + (size_t)unit * 1024);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int w = lane + 32 * q;                   // float4 index 0..255; band = w >> 6
+            out[w] = *reinterpret_cast<const float4*>(tl + (w >> 6) * kMdctOutStride + 4 * (w & 63));
         }
     }
-    if (tid < 4) {
-        const int band = tid;
-        const Curve& cc = scv[band][1];
-        const bool cur_empty = cc.n == 0, prev_empty = scv[band][0].n == 0;
-        if (trivial[band]) {
-            sscale[band][0] = 1.0f; sscale[band][1] = 1.0f; sscale[band][2] = 1.0f; sscale[band][3] = 1.0f;
-        } else {
-            float pos_scale;                                       // PrevOverlapGainScale[channel][band]
-            if (f == 0) pos_scale = b.next_scale[sc * 4 + band];
-            else if (prev_empty) pos_scale = 1.0f;                 // SafeEnergyScale(e, e)
-            else pos_scale = safe_energy_scale(esum[band][5], esum[band][6]);
-            const float inf = __int_as_float(0x7f800000);
-            if (!(fabsf(pos_scale) < inf) || pos_scale <= 0.0f) pos_scale = 1.0f;
-            const float prev_div = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
-            const float prev_stored = esum[band][0];
-            const float prev_orig = fmul(prev_stored, pos_scale);
-            const float prev_mod = __fdiv_rn(prev_stored, fmul(prev_div, prev_div));
-            const float cur_orig = esum[band][1], cur_mod = cur_empty ? esum[band][1] : esum[band][2];
-            const float nxt_orig = esum[band][3], nxt_mod = cur_empty ? esum[band][3] : esum[band][4];
-            sscale[band][0] = safe_energy_scale(prev_orig, prev_mod);
-            sscale[band][1] = safe_energy_scale(cur_orig, cur_mod);
-            sscale[band][2] = safe_energy_scale(fadd(prev_orig, cur_orig), fadd(prev_mod, cur_mod));
-            sscale[band][3] = safe_energy_scale(nxt_orig, nxt_mod);
-        }
-    }
-    __syncthreads();
-    // ---- MDCT-512 per band: fold + pre-twiddle into kissfft's gather order (mdct.h:56-76) ----
-    ATDE_PAR_FOR(w, 512) {
-        const int band = w >> 7, slot = w & 127;
-        const float* in = tmp[band];
-        const int i = T->perm128[slot];
-        const int n = 2 * i;                                 // N = 512, n4 = 128, n34 = 384, n54 = 640
-        float r0, i0;
-        if (n < 128) { r0 = fadd(in[383 - n], in[384 + n]); i0 = fsub(in[128 + n], in[127 - n]); }
-        else         { r0 = fsub(in[383 - n], in[n - 128]); i0 = fadd(in[128 + n], in[639 - n]); }
-        const float cc2 = T->sincos512[n], ss = T->sincos512[n + 1];
-        cpx X;
-        X.r = fadd(fmul(r0, cc2), fmul(i0, ss));
-        X.i = fsub(fmul(i0, cc2), fmul(r0, ss));
-        fft[band][slot] = X;
-    }
-    __syncthreads();
-    // FFT-128 = 4x4x4x2: radix-2 innermost (m = 1), then m = 2, 8, 32
-    {
-        const int band = tid >> 6, v = tid & 63;
-        kf_stage2(fft[band], T->tw128, v, 1, 64);
-    }
-    __syncthreads();
-    for (int st = 0; st < 3; st++) {
-        const int m = 2 << (2 * st);
-        if (tid < 128) {
-            const int band = tid >> 5, v = tid & 31;
-            kf_stage4<false>(fft[band], T->tw128, v, m, 32 / m);
-        }
-        __syncthreads();
-    }
-    // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55); straight to global
-    const size_t unit = ((size_t)s * g.n_out + f) * g.C + c;
-    float* out = b.specs + unit * 1024;
-    float* sp = &tmp[0][0];                                  // the MDCT input is dead: reuse as the output tile
-    ATDE_PAR_FOR(w, 512) {
-        const int band = w >> 7, i = w & 127;
-        const int n = 2 * i;
-        const cpx z = fft[band][i];
-        const float cc2 = T->sincos512[n], ss = T->sincos512[n + 1];
-        const float va = fsub(fmul(-z.r, cc2), fmul(z.i, ss));
-        const float vb = fadd(fmul(-z.r, ss), fmul(z.i, cc2));
-        int pa = n, pb = 255 - n;
-        if (band & 1) { pa = 255 - pa; pb = 255 - pb; }
-        sp[band * 256 + pa] = va;
-        sp[band * 256 + pb] = vb;
-    }
-    __syncthreads();
-    ATDE_PAR_FOR(i, 1024) out[i] = sp[i];
-    if (tid < 16) b.gscale[unit * 16 + tid] = sscale[tid >> 2][tid & 3];
-    if (f == g.n_out - 1 && tid < 4) b.next_scale_out[sc * 4 + tid] = sscale[tid][3];
 }
 
 void launch_mdct(const Geometry& g, const Buffers& b, cudaStream_t st)
 {
-    dim3 grid(g.n_out, g.C, g.S);
-    ATDE_LAUNCH(at3_mdct_kernel, grid, 256, 0, st, g, b);
+    const long long n_units = (long long)g.S * g.n_out * g.C;
+    long long blocks = (n_units + kMdctWarps - 1) / kMdctWarps;
+    if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;       // a few waves of resident blocks, warps stride over units
+    ATDE_LAUNCH(at3_mdct_kernel, (unsigned)blocks, kMdctWarps * 32, 0, st, g, b);
 }
 
 // =====================================================================================

@@ -114,7 +114,7 @@ ATDE_D float virt_pcm(const Geometry& g, const Buffers& b, int s, int c, long lo
     return b.pcm[((size_t)s * g.N * 1024 + (size_t)n) * g.C + c];
 }
 
-__global__ void __launch_bounds__(256, 2) at3_qmf_kernel(Geometry g, Buffers b)
+__global__ void __launch_bounds__(256, 4) at3_qmf_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) float xs[2][kQXP];          // input tile per channel; later the output tile
     __shared__ __align__(16) float s1[2][2][kQS1P];      // [channel][lo, hi]
@@ -133,6 +133,25 @@ __global__ void __launch_bounds__(256, 2) at3_qmf_kernel(Geometry g, Buffers b)
     {
         const long long n0 = 4LL * m0 - 144 - (started ? 1024 : 0);    // tile sample 0 as an index into b.pcm
         const long long nlim = (long long)g.N * 1024;
+        if (g.C == 2 && n0 >= 0 && n0 + kQX <= nlim) {
+            // interior tile: every load independent and in flight at once
+            const float2* src = reinterpret_cast<const float2*>(b.pcm + ((size_t)s * g.N * 1024 + (size_t)n0) * 2);
+            constexpr int kIters = (kQX + 255) / 256;
+            float2 v[kIters];
+#pragma unroll
+            for (int it = 0; it < kIters; it++) {
+                const int t = tid + 256 * it;
+                v[it] = t < kQX ? src[t] : make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int it = 0; it < kIters; it++) {
+                const int t = tid + 256 * it;
+                if (t < kQX) {
+                    xs[0][qphys(t)] = fmul(v[it].x, 0.25f);      // data / 4.0 (atrac3denc.cpp:704)
+                    xs[1][qphys(t)] = fmul(v[it].y, 0.25f);
+                }
+            }
+        } else
         ATDE_PAR_FOR(t, kQX) {
             const long long nn = n0 + t;
             float v0, v1 = 0.0f;
@@ -267,9 +286,13 @@ ATDE_D float plateau_target(const float* in)
 constexpr int kGainThreads = 128;         // FFT threads
 constexpr int kGainBlock = kGainThreads + 32;   // + one helper warp for the double-precision hfr sums
 
-// The 2048-point buffer is padded by 8 elements per 128 so that the stride-128 accesses of the
-// middle pass spread over all shared-memory banks.
-ATDE_D int gphys(int i) { return i + ((i >> 7) << 3); }
+// The 2048-point buffer is padded by one element per 8 (pass 1 stores 8 consecutive slots per thread:
+// a 9-element thread stride is conflict-free) and by 8 more per 128 (so the eight-lane groups of
+// pass 2, 128 slots apart, land on the other half of the banks).
+ATDE_D int gphys(int i) { return i + (i >> 3) + ((i >> 7) << 3); }
+// The real output signal is padded by 4 floats per 64 so that the 32 sequential 64-sample RMS sums
+// (one lane each, 64 floats apart) read different banks.
+ATDE_D int sphys(int j) { return j + ((j >> 6) << 2); }
 
 // One (stream, channel, band, frame) per block.
 //
@@ -286,9 +309,10 @@ ATDE_D int gphys(int i) { return i + ((i >> 7) << 3); }
 // by the structural zeros is exact, so the values equal the full transform's (up to the sign of zero,
 // which no consumer can see: the output is squared).
 // Only output samples [1024, 3072) are consumed (AnalyzeGain), i.e. complex slots [512, 1536).
-__global__ void __launch_bounds__(kGainBlock) at3_gain_kernel(Geometry g, Buffers b)
+__global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) cpx big[2048 + 128];    // inverse FFT buffer, padded; later the real output
+    __shared__ __align__(16) cpx big[2048 + 256 + 128];    // inverse FFT buffer, padded; later the real output
+    __shared__ __align__(8) cpx tw2c[15][8];         // pass-2 twiddles of lane group k, compact
     __shared__ __align__(16) cpx fwd[256];
     __shared__ __align__(16) cpx freq[257];
     __shared__ float micro[256];
@@ -305,6 +329,13 @@ __global__ void __launch_bounds__(kGainBlock) at3_gain_kernel(Geometry g, Buffer
     const int tid = threadIdx.x;
     const cpx* __restrict__ tw = T->tw2048;
 
+    if (tid < 120) {
+        const int j = tid >> 3, k = tid & 7;
+        int idx;
+        if (j < 3) idx = 64 * k * (j + 1);
+        else { const int a = (j - 3) / 3, q = (j - 3) % 3; idx = 16 * (k + 8 * a) * (q + 1); }
+        tw2c[j][k] = tw[idx];
+    }
     // 1. Planck window, packed as the complex input of the half-size FFT, in digit-reversed order
     ATDE_PAR_FOR(o, 256) {
         const int j = T->perm256[o];
@@ -438,15 +469,13 @@ __global__ void __launch_bounds__(kGainBlock) at3_gain_kernel(Geometry g, Buffer
 #pragma unroll
             for (int q = 0; q < 4; q++) x[a][q] = big[gphys(base + k + 8 * a + 32 * q)];
         {
-            const cpx t1 = tw[64 * k], t2 = tw[128 * k], t3 = tw[192 * k];
+            const cpx t1 = tw2c[0][k], t2 = tw2c[1][k], t3 = tw2c[2][k];      // tw[64k], tw[128k], tw[192k]
 #pragma unroll
             for (int q = 0; q < 4; q++) kf_bfly4<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3);
         }
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int kk = k + 8 * a;
-            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw[16 * kk], tw[32 * kk], tw[48 * kk]);
-        }
+        for (int a = 0; a < 4; a++)                                            // kk = k + 8a: tw[16kk], tw[32kk], tw[48kk]
+            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw2c[3 + 3 * a][k], tw2c[4 + 3 * a][k], tw2c[5 + 3 * a][k]);
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -475,15 +504,16 @@ __global__ void __launch_bounds__(kGainBlock) at3_gain_kernel(Geometry g, Buffer
             cpx u, v;
             u.r = fmul(x[a][1].r, 1.0f / 4096.0f); u.i = fmul(x[a][1].i, 1.0f / 4096.0f);
             v.r = fmul(x[a][2].r, 1.0f / 4096.0f); v.i = fmul(x[a][2].i, 1.0f / 4096.0f);
-            big[kk] = u;                                  // slot 512 + kk
-            big[512 + kk] = v;                            // slot 1024 + kk
+            float* sigw = reinterpret_cast<float*>(big);
+            *reinterpret_cast<cpx*>(sigw + sphys(2 * kk)) = u;            // slot 512 + kk  -> samples 1024 + 2kk, +1
+            *reinterpret_cast<cpx*>(sigw + sphys(1024 + 2 * kk)) = v;     // slot 1024 + kk -> samples 2048 + 2kk, +1
         }
     }
     atde_named_barrier(1, kGainThreads);
     // AnalyzeGain(signal + 1024, 2048, 32, rms): 64-sample RMS, plus 8 micro-chunk RMS values each
-    const float* sig = reinterpret_cast<const float*>(big);       // sig[i] = output sample 1024 + i
+    const float* sig = reinterpret_cast<const float*>(big);       // sig[sphys(i)] = output sample 1024 + i
     for (int q = tid; q < 256; q += kGainThreads) {
-        const float* p = sig + 8 * q;
+        const float* p = sig + sphys(8 * q);
         float a = 0.0f;
 #pragma unroll
         for (int i = 0; i < 8; i++) a = fadd(a, fmul(p[i], p[i]));
@@ -491,9 +521,13 @@ __global__ void __launch_bounds__(kGainBlock) at3_gain_kernel(Geometry g, Buffer
     }
     if (tid >= 32 && tid < 64) {
         const int sf = tid - 32;
-        const float* p = sig + 64 * sf;
+        const float* p = sig + sphys(64 * sf);
         float a = 0.0f;
-        for (int i = 0; i < 64; i++) a = fadd(a, fmul(p[i], p[i]));
+        for (int i = 0; i < 64; i += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(p + i);
+            a = fadd(a, fmul(q.x, q.x)); a = fadd(a, fmul(q.y, q.y));
+            a = fadd(a, fmul(q.z, q.z)); a = fadd(a, fmul(q.w, q.w));
+        }
         sgain[sf] = __fsqrt_rn(__fdiv_rn(a, 64.0f));
     }
     atde_named_barrier(1, kGainThreads);
@@ -843,6 +877,10 @@ ATDE_D float curve_level(const DevTables* T, const Curve& cv, int pos)
     return 1.0f;
 }
 
+// Out-of-line copy for the MDCT kernel: curves are rare there and the inlined loop, repeated per
+// sample slot, made the kernel overflow the instruction cache.
+ATDE_NOINLINE float curve_level_call(const DevTables* T, const Curve* cv, int pos) { return curve_level(T, *cv, pos); }
+
 // SafeEnergyScale (atrac3denc.cpp:143-152)
 ATDE_D float safe_energy_scale(float orig, float mod)
 {
@@ -853,25 +891,29 @@ ATDE_D float safe_energy_scale(float orig, float mod)
     return (fabsf(sc) < inf && sc > 0.0f) ? sc : 1.0f;
 }
 
-// One WARP per (stream, frame, channel); the four MDCT-512 of the unit run side by side, 8 lanes per
-// band, with no block-wide barrier.
+// One WARP per (stream, frame, channel), no block-wide barrier.  The unit's four MDCT-512 run as two
+// iterations of two bands, 16 lanes per band:
 //   phase A  load the band samples of this and the previous frame (coalesced float4), divide by the
-//            gain curves, window, store the four 512-sample MDCT inputs to the warp's tile
-//   phase B  fold + pre-twiddle (mdct.h:56-76) straight into kissfft's gather order; lane k of a band
-//            owns gather blocks k and k+8 (8 consecutive slots each) and runs the two innermost stages
+//            gain curves, window, store the two 512-sample MDCT inputs to the warp's tile
+//   phase B  fold + pre-twiddle (mdct.h:56-76) straight into kissfft's gather order; lane k16 of a band
+//            owns gather block k16 (8 consecutive slots) and runs the two innermost stages
 //            (radix-2 m=1, radix-4 m=2) on registers
-//   exchange through the tile so that lane k holds elements k + 8a + 32b
-//   phase C  radix-4 m=8 over a, radix-4 m=32 over b on registers, post-twiddle (mdct.h:92-101),
-//            spectrum staged in the tile and written out as coalesced float4
+//   exchange through the tile: lane (k, bp) takes elements k + 8a + 32b, a = 0..3, b = 2bp, 2bp+1
+//   phase C  radix-4 m=8 over a; lane pairs (k16, k16^8) swap halves by shuffle so that lane (k, ap)
+//            holds k + 8a + 32b, a = 2ap, 2ap+1, b = 0..3; radix-4 m=32 over b; post-twiddle
+//            (mdct.h:92-101); spectrum staged in the tile and written out as coalesced float4
 // Every butterfly keeps kissfft's operation order (kissfft_dev.cuh), so the regrouping is exact.
+// The loop body is kept small on purpose (two bands per iteration, rare gain-curve work out of line):
+// the fully unrolled four-band version missed the instruction cache on every warp.
 constexpr int kMdctWarps = 4;
 constexpr int kMdctBandStride = 520;                 // floats; keeps float4 alignment, shifts banks by 8
 constexpr int kMdctXchStride = 152;                  // cpx per band in the exchange layout (16 blocks x 9, +8)
 constexpr int kMdctOutStride = 264;
+constexpr int kMdctTile = 7 * 256;                   // floats per warp: the rare path's 7 x 256 squares is the largest user
 
-__global__ void __launch_bounds__(kMdctWarps * 32, 4) at3_mdct_kernel(Geometry g, Buffers b)
+__global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) float tile[kMdctWarps][4 * kMdctBandStride];
+    __shared__ __align__(16) float tile[kMdctWarps][kMdctTile];
     __shared__ __align__(16) float s_sincos[256];
     __shared__ __align__(16) float s_win[256];
     __shared__ __align__(16) cpx s_tw[128];
@@ -920,16 +962,17 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 4) at3_mdct_kernel(Geometry g
             const Curve& cc = s_cv[warp][band][1];
             const Curve& pc = s_cv[warp][band][0];
             const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
+#pragma unroll 1
             for (int i = lane; i < 256; i += 32) {
                 const float x = bp[i];
-                const float xm = cc.n ? __fdiv_rn(x, curve_level(T, cc, i)) : x;
+                const float xm = cc.n ? __fdiv_rn(x, curve_level_call(T, &cc, i)) : x;
                 const float wi = s_win[i], wr = s_win[255 - i];
                 float prev, y = 0.0f, ym = 0.0f;
                 if (f == 0) {
                     prev = b.prevhalf[(sc * 4 + band) * 256 + i];
                 } else {
                     y = bp[i - 256];
-                    ym = pc.n ? __fdiv_rn(y, curve_level(T, pc, i)) : y;
+                    ym = pc.n ? __fdiv_rn(y, curve_level_call(T, &pc, i)) : y;
                     prev = fmul(wi, ym);
                 }
                 float v;
@@ -979,14 +1022,19 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 4) at3_mdct_kernel(Geometry g
             *reinterpret_cast<float4*>(&b.gscale[(size_t)unit * 16 + band * 4]) = make_float4(sc0, sc1, sc2, sc3);
             if (f == g.n_out - 1) b.next_scale_out[sc * 4 + band] = sc3;
         }
+        float* const outp = b.specs + (size_t)unit * 1024;
+#pragma unroll 1
+        for (int bp2 = 0; bp2 < 2; bp2++) {                 // bands 2*bp2, 2*bp2 + 1
+        __syncwarp();                                       // the tile is free (rare path / previous iteration)
         // ---- phase A: MDCT input (atrac3denc.cpp:39-49): in[j] = stored half / scale, in[256+j] = win[255-j] * modulated cur
 #pragma unroll 1
-        for (int band = 0; band < 4; band++) {
+        for (int bb = 0; bb < 2; bb++) {
+            const int band = 2 * bp2 + bb;
             // BL = 128 + 256 L: every band row and every frame inside it starts 16-byte aligned
             const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
             const Curve& cc = s_cv[warp][band][1];
             const Curve& pc = s_cv[warp][band][0];
-            float* in = tl + band * kMdctBandStride;
+            float* in = tl + bb * kMdctBandStride;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int i0 = 4 * (lane + 32 * h);
@@ -1002,98 +1050,123 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 4) at3_mdct_kernel(Geometry g
                     const float4 q = *reinterpret_cast<const float4*>(bp + i0 - 256);
                     y[0] = q.x; y[1] = q.y; y[2] = q.z; y[3] = q.w;
                 }
+                if (cc.n | pc.n) {                                    // rare: gain modulation (gain_processor.h:87-121)
+#pragma unroll 1
+                    for (int e = 0; e < 4; e++) {
+                        const int i = i0 + e;
+                        if (cc.n) x[e] = __fdiv_rn(x[e], curve_level_call(T, &cc, i));
+                        if (f != 0 && pc.n) y[e] = __fdiv_rn(y[e], curve_level_call(T, &pc, i));
+                    }
+                }
+                const float4 wf = *reinterpret_cast<const float4*>(&s_win[i0]);          // win[i0 .. i0+3]
+                const float4 wb = *reinterpret_cast<const float4*>(&s_win[252 - i0]);    // win[255-i0-3 .. 255-i0]
+                const float wi[4] = {wf.x, wf.y, wf.z, wf.w}, wr[4] = {wb.w, wb.z, wb.y, wb.x};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const int i = i0 + e;
-                    const float xm = cc.n ? __fdiv_rn(x[e], curve_level(T, cc, i)) : x[e];
-                    if (f != 0) pv[e] = fmul(s_win[i], pc.n ? __fdiv_rn(y[e], curve_level(T, pc, i)) : y[e]);
-                    if (cc.n) pv[e] = __fdiv_rn(pv[e], T->gain_level[cc.level[0]]);
-                    cu[e] = fmul(s_win[255 - i], xm);
-                    if (f == g.n_out - 1)                             // the half this frame leaves behind (next batch)
-                        b.prevhalf_out[(sc * 4 + band) * 256 + i] = fmul(s_win[i], xm);
+                    if (f != 0) pv[e] = fmul(wi[e], y[e]);
+                    cu[e] = fmul(wr[e], x[e]);
+                }
+                if (cc.n) {
+                    const float d0 = T->gain_level[cc.level[0]];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) pv[e] = __fdiv_rn(pv[e], d0);
+                }
+                if (f == g.n_out - 1) {                               // the half this frame leaves behind (next batch)
+                    *reinterpret_cast<float4*>(b.prevhalf_out + (sc * 4 + band) * 256 + i0) =
+                        make_float4(fmul(wi[0], x[0]), fmul(wi[1], x[1]), fmul(wi[2], x[2]), fmul(wi[3], x[3]));
                 }
                 *reinterpret_cast<float4*>(in + i0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
                 *reinterpret_cast<float4*>(in + 256 + i0) = make_float4(cu[0], cu[1], cu[2], cu[3]);
             }
         }
         __syncwarp();
-        // ---- phase B: fold + pre-twiddle + the two innermost FFT stages on gather blocks k and k+8
-        const int band = lane >> 3, k = lane & 7;
-        cpx e[4][4];                                       // after the exchange: element k + 8a + 32b
+        // ---- phase B: fold + pre-twiddle + the two innermost FFT stages on gather block k16
+        const int bsel = lane >> 4, k16 = lane & 15, k = lane & 7, hp = (lane >> 3) & 1;
+        cpx e[4][2];                                       // after the exchange: element k + 8a + 32(2 hp + bb)
         {
-            const float* in = tl + band * kMdctBandStride;
-            cpx v[2][8];
+            const float* in = tl + bsel * kMdctBandStride;
+            cpx v[8];
+            // slot = 8 k16 + j of the 4x4x4x2 digit reversal: i = d0 + 4 d1 + 16 d2 + 64 d3
+            const int ibase = (k16 >> 2) + 4 * (k16 & 3);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    // slot = 64h + 8k + j of the 4x4x4x2 digit reversal: i = d0 + 4 d1 + 16 d2 + 64 d3
-                    const int i = (2 * h + (k >> 2)) + 4 * (k & 3) + 16 * (j >> 1) + 64 * (j & 1);
-                    const int n = 2 * i;                         // N = 512, n4 = 128, n34 = 384, n54 = 640
-                    float r0, i0;
-                    if (n < 128) { r0 = fadd(in[383 - n], in[384 + n]); i0 = fsub(in[128 + n], in[127 - n]); }
-                    else         { r0 = fsub(in[383 - n], in[n - 128]); i0 = fadd(in[128 + n], in[639 - n]); }
-                    const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
-                    v[h][j].r = fadd(fmul(r0, cs.x), fmul(i0, cs.y));
-                    v[h][j].i = fsub(fmul(i0, cs.x), fmul(r0, cs.y));
-                }
-                // radix-2, m = 1 (fstride 64): pairs (2q, 2q+1), twiddle tw[0]
-#pragma unroll
-                for (int q = 0; q < 4; q++) kf_bfly2(v[h][2 * q], v[h][2 * q + 1], s_tw[0]);
-                // radix-4, m = 2 (fstride 16): elements kk + 2q, twiddles tw[16 kk q]
-#pragma unroll
-                for (int kk = 0; kk < 2; kk++)
-                    kf_bfly4<false>(v[h][kk], v[h][kk + 2], v[h][kk + 4], v[h][kk + 6],
-                                    s_tw[16 * kk], s_tw[32 * kk], s_tw[48 * kk]);
+            for (int j = 0; j < 8; j++) {
+                const int n = 2 * (ibase + 16 * (j >> 1) + 64 * (j & 1));   // N = 512, n4 = 128, n34 = 384, n54 = 640
+                float r0, i0;
+                if ((j & 1) == 0) { r0 = fadd(in[383 - n], in[384 + n]); i0 = fsub(in[128 + n], in[127 - n]); }   // n < 128
+                else              { r0 = fsub(in[383 - n], in[n - 128]); i0 = fadd(in[128 + n], in[639 - n]); }
+                const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
+                v[j].r = fadd(fmul(r0, cs.x), fmul(i0, cs.y));
+                v[j].i = fsub(fmul(i0, cs.x), fmul(r0, cs.y));
             }
+            // radix-2, m = 1 (fstride 64): pairs (2q, 2q+1), twiddle tw[0]
+#pragma unroll
+            for (int q = 0; q < 4; q++) kf_bfly2(v[2 * q], v[2 * q + 1], s_tw[0]);
+            // radix-4, m = 2 (fstride 16): elements kk + 2q, twiddles tw[16 kk q]
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                kf_bfly4<false>(v[kk], v[kk + 2], v[kk + 4], v[kk + 6], s_tw[16 * kk], s_tw[32 * kk], s_tw[48 * kk]);
             __syncwarp();                                  // every lane has read its MDCT input
-            cpx* xch = reinterpret_cast<cpx*>(tl) + band * kMdctXchStride;
+            cpx* xch = reinterpret_cast<cpx*>(tl) + bsel * kMdctXchStride;
 #pragma unroll
-            for (int h = 0; h < 2; h++)
-#pragma unroll
-                for (int j = 0; j < 8; j++) xch[(k + 8 * h) * 9 + j] = v[h][j];
+            for (int j = 0; j < 8; j++) xch[k16 * 9 + j] = v[j];
             __syncwarp();
 #pragma unroll
             for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int bq = 0; bq < 4; bq++) e[a][bq] = xch[(a + 4 * bq) * 9 + k];
+                for (int bb = 0; bb < 2; bb++) e[a][bb] = xch[(a + 4 * (2 * hp + bb)) * 9 + k];
         }
-        // ---- phase C: radix-4 m = 8 (fstride 4) over a, radix-4 m = 32 (fstride 1) over b
+        // ---- phase C: radix-4 m = 8 (fstride 4) over a
         {
             const cpx t1 = s_tw[4 * k], t2 = s_tw[8 * k], t3 = s_tw[12 * k];
 #pragma unroll
-            for (int bq = 0; bq < 4; bq++) kf_bfly4<false>(e[0][bq], e[1][bq], e[2][bq], e[3][bq], t1, t2, t3);
+            for (int bb = 0; bb < 2; bb++) kf_bfly4<false>(e[0][bb], e[1][bb], e[2][bb], e[3][bb], t1, t2, t3);
         }
+        // lane pair swap: lane hp keeps a = 2hp + aa and receives the partner's b range for those a
+        cpx gq[2][4];                                      // element k + 8 (2 hp + aa) + 32 b
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int v = k + 8 * a;
-            kf_bfly4<false>(e[a][0], e[a][1], e[a][2], e[a][3], s_tw[v], s_tw[2 * v], s_tw[3 * v]);
+        for (int aa = 0; aa < 2; aa++)
+#pragma unroll
+            for (int bb = 0; bb < 2; bb++) {
+                const cpx keep = hp ? e[2 + aa][bb] : e[aa][bb];
+                const cpx send = hp ? e[aa][bb] : e[2 + aa][bb];
+                cpx recv;
+                recv.r = __shfl_xor_sync(0xffffffffu, send.r, 8);
+                recv.i = __shfl_xor_sync(0xffffffffu, send.i, 8);
+                gq[aa][bb] = hp ? recv : keep;
+                gq[aa][2 + bb] = hp ? keep : recv;
+            }
+        // radix-4 m = 32 (fstride 1) over b
+#pragma unroll
+        for (int aa = 0; aa < 2; aa++) {
+            const int v = k + 8 * (2 * hp + aa);
+            kf_bfly4<false>(gq[aa][0], gq[aa][1], gq[aa][2], gq[aa][3], s_tw[v], s_tw[2 * v], s_tw[3 * v]);
         }
         __syncwarp();                                      // exchange reads done: the tile becomes the output stage
         // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55)
         {
-            float* sp = tl + band * kMdctOutStride;
+            float* sp = tl + bsel * kMdctOutStride;
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int aa = 0; aa < 2; aa++)
 #pragma unroll
                 for (int bq = 0; bq < 4; bq++) {
-                    const int n = 2 * (k + 8 * a + 32 * bq);
-                    const cpx z = e[a][bq];
+                    const int n = 2 * (k + 8 * (2 * hp + aa) + 32 * bq);
+                    const cpx z = gq[aa][bq];
                     const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
                     const float va = fsub(fmul(-z.r, cs.x), fmul(z.i, cs.y));
                     const float vb = fadd(fmul(-z.r, cs.y), fmul(z.i, cs.x));
                     int pa = n, pb = 255 - n;
-                    if (band & 1) { pa = 255 - pa; pb = 255 - pb; }
+                    if (bsel) { pa = 255 - pa; pb = 255 - pb; }       // band 2*bp2 + bsel is odd iff bsel
                     sp[pa] = va;
                     sp[pb] = vb;
                 }
         }
         __syncwarp();
-        float4* out = reinterpret_cast<float4*>(b.specs + (size_t)unit * 1024);
+        float4* out = reinterpret_cast<float4*>(outp + 512 * bp2);
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int w = lane + 32 * q;                   // float4 index 0..255; band = w >> 6
+        for (int q = 0; q < 4; q++) {
+            const int w = lane + 32 * q;                   // float4 index 0..127; band within the pair = w >> 6
             out[w] = *reinterpret_cast<const float4*>(tl + (w >> 6) * kMdctOutStride + 4 * (w & 63));
+        }
         }
     }
 }

@@ -293,6 +293,18 @@ ATDE_D int gphys(int i) { return i + (i >> 3) + ((i >> 7) << 3); }
 // The real output signal is padded by 4 floats per 64 so that the 32 sequential 64-sample RMS sums
 // (one lane each, 64 floats apart) read different banks.
 ATDE_D int sphys(int j) { return j + ((j >> 6) << 2); }
+// Spectrum-sized arrays (forward FFT buffer, frequency bins, staged super-twiddles) are padded by one
+// element per 16: both the natural-order accesses and the base-4 digit-reversed ones (lane stride 64,
+// 16, 4 elements) then fall on 16 different bank pairs.
+ATDE_D int fq(int k) { return k + (k >> 4); }
+
+// One radix-4 butterfly of the forward FFT-256 on the padded buffer; F = first element, m = sub-length.
+ATDE_D void fwd_bfly(cpx* buf, int F, int m, cpx t1, cpx t2, cpx t3)
+{
+    cpx f0 = buf[fq(F)], f1 = buf[fq(F + m)], f2 = buf[fq(F + 2 * m)], f3 = buf[fq(F + 3 * m)];
+    kf_bfly4<false>(f0, f1, f2, f3, t1, t2, t3);
+    buf[fq(F)] = f0; buf[fq(F + m)] = f1; buf[fq(F + 2 * m)] = f2; buf[fq(F + 3 * m)] = f3;
+}
 
 // One (stream, channel, band, frame) per block.
 //
@@ -309,15 +321,16 @@ ATDE_D int sphys(int j) { return j + ((j >> 6) << 2); }
 // by the structural zeros is exact, so the values equal the full transform's (up to the sign of zero,
 // which no consumer can see: the output is squared).
 // Only output samples [1024, 3072) are consumed (AnalyzeGain), i.e. complex slots [512, 1536).
-__global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buffers b)
+__global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) cpx big[2048 + 256 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ __align__(8) cpx tw2c[15][8];         // pass-2 twiddles of lane group k, compact
-    __shared__ __align__(16) cpx fwd[256];
-    __shared__ __align__(16) cpx freq[257];
+    __shared__ __align__(16) cpx fwd[256 + 16];
+    __shared__ __align__(16) cpx freq[257 + 17];
+    __shared__ __align__(16) cpx sup[257 + 17];      // super4096[k - 1] at fq(k), k = 1..256
     __shared__ float micro[256];
     __shared__ float sgain[96];
-    __shared__ double ek[257], ekh[257];
+    __shared__ __align__(16) double2 ee[257];        // (|X_k|^2, |X_k H_k|^2)
     __shared__ double esum2[2];
     __shared__ float sstat[2];
 
@@ -329,38 +342,46 @@ __global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buf
     const int tid = threadIdx.x;
     const cpx* __restrict__ tw = T->tw2048;
 
-    if (tid < 120) {
-        const int j = tid >> 3, k = tid & 7;
-        int idx;
-        if (j < 3) idx = 64 * k * (j + 1);
-        else { const int a = (j - 3) / 3, q = (j - 3) % 3; idx = 16 * (k + 8 * a) * (q + 1); }
-        tw2c[j][k] = tw[idx];
-    }
-    // 1. Planck window, packed as the complex input of the half-size FFT, in digit-reversed order
-    ATDE_PAR_FOR(o, 256) {
-        const int j = T->perm256[o];
+    if (tid < 120) (&tw2c[0][0])[tid] = (&T->gtw2[0][0])[tid];
+    // the only super-twiddles kiss_fftri(4096) meets with a non-zero operand
+    for (int k = 1 + tid; k <= 256; k += kGainBlock) sup[fq(k)] = T->super4096[k - 1];
+    // 1. Planck window, packed as the complex input of the half-size FFT; loaded in natural order and
+    //    stored at its digit-reversed slot (base-4 reversal of 4 digits is an involution)
+    ATDE_PAR_FOR(j, 256) {
         const float2 x = *reinterpret_cast<const float2*>(in + 2 * j);
+        const float2 w = *reinterpret_cast<const float2*>(&T->planck[2 * j]);
         cpx z;
-        z.r = fmul(x.x, T->planck[2 * j]);
-        z.i = fmul(x.y, T->planck[2 * j + 1]);
-        fwd[o] = z;
+        z.r = fmul(x.x, w.x);
+        z.i = fmul(x.y, w.y);
+        const int o = ((j & 3) << 6) | (((j >> 2) & 3) << 4) | (((j >> 4) & 3) << 2) | (j >> 6);
+        fwd[fq(o)] = z;
     }
     __syncthreads();
-    // 2. forward complex FFT-256 = 4x4x4x4
-    for (int st = 0; st < 4; st++) {
-        const int m = 1 << (2 * st);
-        if (tid < 64) kf_stage4<false>(fwd, T->tw256, tid, m, 64 / m);
-        __syncthreads();
+    // 2. forward complex FFT-256 = 4x4x4x4, innermost stage first; the lane -> butterfly map of every
+    //    stage is chosen so that 16 consecutive lanes touch 16 different bank pairs
+    if (tid < 64) fwd_bfly(fwd, 4 * tid, 1, T->ftw[0][0][0], T->ftw[0][1][0], T->ftw[0][2][0]);
+    __syncthreads();
+    if (tid < 64) {
+        const int gq = tid & 15, k = tid >> 4;
+        fwd_bfly(fwd, 16 * gq + k, 4, T->ftw[1][0][k], T->ftw[1][1][k], T->ftw[1][2][k]);
     }
+    __syncthreads();
+    if (tid < 64) {
+        const int gq = tid >> 4, k = tid & 15;
+        fwd_bfly(fwd, 64 * gq + k, 16, T->ftw[2][0][k], T->ftw[2][1][k], T->ftw[2][2][k]);
+    }
+    __syncthreads();
+    if (tid < 64) fwd_bfly(fwd, tid, 64, T->ftw[3][0][tid], T->ftw[3][1][tid], T->ftw[3][2][tid]);
+    __syncthreads();
     // kiss_fftr post-processing (kiss_fftr.c:84-115)
     ATDE_PAR_FOR(k, 129) {
         if (k == 0) {
             const float tr = fwd[0].r, ti = fwd[0].i;
             freq[0].r = fadd(tr, ti);   freq[0].i = 0.0f;
-            freq[256].r = fsub(tr, ti); freq[256].i = 0.0f;
+            freq[fq(256)].r = fsub(tr, ti); freq[fq(256)].i = 0.0f;
         } else {
-            const cpx fpk = fwd[k];
-            cpx fpnk; fpnk.r = fwd[256 - k].r; fpnk.i = -fwd[256 - k].i;
+            const cpx fpk = fwd[fq(k)];
+            cpx fpnk; fpnk.r = fwd[fq(256 - k)].r; fpnk.i = -fwd[fq(256 - k)].i;
             cpx f1k, f2k;
             f1k.r = fadd(fpk.r, fpnk.r); f1k.i = fadd(fpk.i, fpnk.i);
             f2k.r = fsub(fpk.r, fpnk.r); f2k.i = fsub(fpk.i, fpnk.i);
@@ -368,8 +389,8 @@ __global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buf
             cpx a, bb;
             a.r = fmul(fadd(f1k.r, t2.r), 0.5f);  a.i = fmul(fadd(f1k.i, t2.i), 0.5f);
             bb.r = fmul(fsub(f1k.r, t2.r), 0.5f); bb.i = fmul(fsub(t2.i, f1k.i), 0.5f);
-            freq[k] = a;                       // k == 128 writes the same element twice: the second
-            freq[256 - k] = bb;                // store (freqdata[ncfft-k]) wins, as in the reference
+            freq[fq(k)] = a;                   // k == 128 writes the same element twice: the second
+            freq[fq(256 - k)] = bb;            // store (freqdata[ncfft-k]) wins, as in the reference
         }
     }
     __syncthreads();
@@ -381,19 +402,18 @@ __global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buf
     if (tid >= kGainThreads) {
         const int hl = tid - kGainThreads;
         for (int k = hl; k < 257; k += 32) {
-            const double r = (double)freq[k].r, i = (double)freq[k].i;
+            const double r = (double)freq[fq(k)].r, i = (double)freq[fq(k)].i;
             const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
             float H = 0.0f;
             if (k >= lcb + 2) H = 1.0f;
             else if (k >= lcb) H = T->hpf_h[k - lcb];
-            ek[k] = e;
-            ekh[k] = __dmul_rn(__dmul_rn(e, (double)H), (double)H);
+            ee[k] = make_double2(e, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
         }
         __syncwarp();
         if (hl == 0) {
             double tot = 0.0, hi = 0.0;
 #pragma unroll 4
-            for (int k = 0; k <= 256; k++) { tot = __dadd_rn(tot, ek[k]); hi = __dadd_rn(hi, ekh[k]); }
+            for (int k = 0; k <= 256; k++) { const double2 v = ee[k]; tot = __dadd_rn(tot, v.x); hi = __dadd_rn(hi, v.y); }
             esum2[0] = tot; esum2[1] = hi;
         }
         __syncthreads();                                      // the final barrier of the FFT warps
@@ -408,21 +428,21 @@ __global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buf
         cpx fk;
         if (k == 256) {
             if (lcb + 2 > 256) return;
-            fk.r = fmul(fmul(freq[256].r, 8.0f), 0.5f);
+            fk.r = fmul(fmul(freq[fq(256)].r, 8.0f), 0.5f);
             fk.i = 0.0f;
         } else if (k >= lcb + 2) {
-            fk.r = fmul(freq[k].r, 8.0f);
-            fk.i = fmul(freq[k].i, 8.0f);
+            fk.r = fmul(freq[fq(k)].r, 8.0f);
+            fk.i = fmul(freq[fq(k)].i, 8.0f);
         } else {
             const float w = T->hpf_h[k - lcb];
-            fk.r = fmul(fmul(freq[k].r, 8.0f), w);
-            fk.i = fmul(fmul(freq[k].i, 8.0f), w);
+            fk.r = fmul(fmul(freq[fq(k)].r, 8.0f), w);
+            fk.i = fmul(fmul(freq[fq(k)].i, 8.0f), w);
         }
         // fnkc = conj(Y[2048-k]) = (0, -0):  fek = fk + fnkc, tmp = fk - fnkc
         cpx fek, tp;
         fek.r = fadd(fk.r, 0.0f);  fek.i = fadd(fk.i, -0.0f);
         tp.r = fsub(fk.r, 0.0f);   tp.i = fsub(fk.i, -0.0f);
-        const cpx fok = cmul(tp, T->super4096[k - 1]);
+        const cpx fok = cmul(tp, sup[fq(k)]);
         lo.r = fadd(fek.r, fok.r);  lo.i = fadd(fek.i, fok.i);
         hi.r = fsub(fek.r, fok.r);  hi.i = fmul(fsub(fek.i, fok.i), -1.0f);
     };
@@ -492,14 +512,14 @@ __global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buf
             for (int q = 0; q < 4; q++) x[a][q] = big[gphys(k + 128 * a + 512 * q)];
         atde_named_barrier(1, kGainThreads);                                  // every slot is in registers: big can be overwritten
         {
-            const cpx t1 = tw[4 * k], t2 = tw[8 * k], t3 = tw[12 * k];
+            const cpx t1 = T->gtw3a[0][k], t2 = T->gtw3a[1][k], t3 = T->gtw3a[2][k];     // tw[4k], tw[8k], tw[12k]
 #pragma unroll
             for (int q = 0; q < 4; q++) kf_bfly4<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3);
         }
 #pragma unroll
         for (int a = 0; a < 4; a++) {
             const int kk = k + 128 * a;
-            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw[kk], tw[2 * kk], tw[3 * kk]);
+            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], T->gtw3b[a][0][k], T->gtw3b[a][1][k], T->gtw3b[a][2][k]);  // tw[kk], tw[2kk], tw[3kk]
             // 5. normalise (norm = 1/4096); complex slot kk + 512q -> output samples 2*slot, 2*slot+1
             cpx u, v;
             u.r = fmul(x[a][1].r, 1.0f / 4096.0f); u.i = fmul(x[a][1].i, 1.0f / 4096.0f);
@@ -512,7 +532,8 @@ __global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buf
     atde_named_barrier(1, kGainThreads);
     // AnalyzeGain(signal + 1024, 2048, 32, rms): 64-sample RMS, plus 8 micro-chunk RMS values each
     const float* sig = reinterpret_cast<const float*>(big);       // sig[sphys(i)] = output sample 1024 + i
-    for (int q = tid; q < 256; q += kGainThreads) {
+    for (int l = tid; l < 256; l += kGainThreads) {
+        const int q = (l & ~12) | ((l & 4) << 1) | ((l & 8) >> 1);    // bits 2 and 3 swapped: conflict-free float4 reads
         const float* p = sig + sphys(8 * q);
         float a = 0.0f;
 #pragma unroll

@@ -250,6 +250,25 @@ int build_at3_tables(atde_encoder* e)
     memcpy(h->super4096, s4096.data(), sizeof(h->super4096));
     const auto p2048 = kiss_perm(2048);
     for (int o = 0; o < 2048; o++) h->iperm2048[p2048[o]] = (unsigned short)o;
+    memset(h->ftw, 0, sizeof(h->ftw));
+    for (int st = 0; st < 4; st++) {
+        const int m = 1 << (2 * st), fstride = 64 / m;
+        for (int q = 0; q < 3; q++)
+            for (int k = 0; k < m; k++) memcpy(&h->ftw[st][q][k], &tw256[(size_t)(q + 1) * k * fstride], sizeof(at3::DevTables::ftw[0][0][0]));
+    }
+    for (int k = 0; k < 8; k++) {
+        for (int q = 0; q < 3; q++) {
+            memcpy(&h->gtw2[q][k], &tw2048[(size_t)64 * k * (q + 1)], sizeof(h->gtw2[0][0]));
+            for (int a = 0; a < 4; a++)
+                memcpy(&h->gtw2[3 + 3 * a + q][k], &tw2048[(size_t)16 * (k + 8 * a) * (q + 1)], sizeof(h->gtw2[0][0]));
+        }
+    }
+    for (int k = 0; k < 128; k++)
+        for (int q = 0; q < 3; q++) {
+            memcpy(&h->gtw3a[q][k], &tw2048[(size_t)4 * k * (q + 1)], sizeof(h->gtw3a[0][0]));
+            for (int a = 0; a < 4; a++)
+                memcpy(&h->gtw3b[a][q][k], &tw2048[(size_t)(k + 128 * a) * (q + 1)], sizeof(h->gtw3b[0][0][0]));
+        }
 
     cudaError_t ce = cudaMalloc(&e->d_at3_tab, sizeof(at3::DevTables));
     if (ce == cudaSuccess) ce = cudaMemcpy(e->d_at3_tab, h, sizeof(at3::DevTables), cudaMemcpyHostToDevice);

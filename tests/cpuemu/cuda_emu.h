@@ -40,6 +40,8 @@ struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct __attribute__((aligned(16))) double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace cuemu {
 struct BlockCtx {

@@ -34,7 +34,7 @@ struct DevTables {
     cpx tw128[128];                   // forward kissfft twiddles, MDCT-512's 128-point FFT
     unsigned char perm128[128];
     // gain control: TSpectralUpsampler (transient_spectral_upsampler.cpp)
-    float planck[512];                // Planck-taper window, eps = 0.15
+    alignas(16) float planck[512];    // Planck-taper window, eps = 0.15 (read as float2)
     float hpf_h[2];                   // raised-cosine H at LowCutBin, LowCutBin+1
     int low_cut_bin;
     cpx tw256[256];                   // forward, kiss_fftr(512) -> complex FFT-256

@@ -1,0 +1,358 @@
+// at3p_kernels.cu — ATRAC3plus encode path on sm_100a: PQF analysis, MDCT-256 x16, frame packer.
+// See at3p_kernels.cuh for the reference chain and what is still missing (GHA).
+//
+// Bit-exactness rules are the ones of the other codecs: un-fused IEEE fp32 in the
+// reference's operation order, doubles where the reference uses doubles (the PQF accumulators),
+// kissfft restated stage by stage, tables computed on the host with the reference's expressions.
+#include "at3p_kernels.cuh"
+#include "kissfft_dev.cuh"
+#include "host_tables.h"
+#include "at3p_tables_gen.h"
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace atde {
+namespace at3p {
+
+__constant__ float c_fir[kPqfProto];       // analysis prototype, atrac3plus_pqf.c:59-78
+__constant__ float c_dct_sc[16];           // TMIDCT<32>(32 * 128 * 512) pre/post twiddles, mdct.cpp:63-66
+__constant__ cpx c_tw8[8];                 // forward kissfft twiddles of the 8-point FFT
+
+// =====================================================================================
+// host tables
+// =====================================================================================
+static DevTables* g_dev_tables = nullptr;
+static std::once_flag g_tables_once;
+
+static float bits_to_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+
+static void build_tables()
+{
+    DevTables* h = new DevTables();
+    memset(h, 0, sizeof(*h));
+    const auto sc = mdct_sincos(256, 1.0f);
+    memcpy(h->sincos256, sc.data(), sizeof(h->sincos256));
+    for (int i = 0; i < 128; i++)                                     // at3p_mdct.cpp:36-40
+        h->sine_win[i] = 2.0 * sinf((i + 0.5) * (M_PI / (2.0 * 128)));
+    const auto tw = kiss_twiddles(64, false);
+    memcpy(h->tw64, tw.data(), sizeof(h->tw64));
+    for (int i = 0; i < 64; i++) h->scale_table[i] = bits_to_float(kAt3pScaleBits[i]);
+    for (int i = 0; i < 8; i++) h->inv_mant[i] = bits_to_float(kAt3pInvMantBits[i]);
+    memcpy(h->spec_tab, kAt3pSpecTab, sizeof(h->spec_tab));
+    memcpy(h->vlc_off, kAt3pVlcOff, sizeof(h->vlc_off));
+    static_assert(sizeof(kAt3pVlc) == sizeof(DevTables::vlc), "generated VLC table size");
+    memcpy(h->vlc, kAt3pVlc, sizeof(h->vlc));
+    memcpy(h->wl_vlc, kAt3pWlVlc, sizeof(h->wl_vlc));
+    memcpy(h->tone_bands_vlc, kAt3pToneBandsVlc, sizeof(h->tone_bands_vlc));
+    memcpy(h->qu_to_subband, kAt3pQuToSubband, sizeof(h->qu_to_subband));
+    memcpy(h->sb_to_powgrps, kAt3pSbToPowGrps, sizeof(h->sb_to_powgrps));
+
+    float fir[kPqfProto];
+    for (int i = 0; i < kPqfProto; i++) fir[i] = bits_to_float(kAt3pFirBits[i]);
+    // atde_create_dct4_16(128 * 512.0): TMIDCT<32>(32 * 65536) -> CalcSinCos(32, 32 * 65536 / 2)
+    const auto dsc = mdct_sincos(32, 1048576.0f);
+    const auto tw8 = kiss_twiddles(8, false);
+    DevTables* d = nullptr;
+    if (cudaMalloc(&d, sizeof(DevTables)) == cudaSuccess &&
+        cudaMemcpy(d, h, sizeof(DevTables), cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpyToSymbol(c_fir, fir, sizeof(fir)) == cudaSuccess &&
+        cudaMemcpyToSymbol(c_dct_sc, dsc.data(), 16 * sizeof(float)) == cudaSuccess &&
+        cudaMemcpyToSymbol(c_tw8, tw8.data(), 8 * sizeof(cpx)) == cudaSuccess)
+        g_dev_tables = d;
+    delete h;
+}
+
+const DevTables* device_tables()
+{
+    std::call_once(g_tables_once, build_tables);
+    return g_dev_tables;
+}
+
+// =====================================================================================
+// P1: PQF analysis, at3plus_pqf_do_analyse (atrac3plus_pqf.c:80-147)
+// =====================================================================================
+// One block per (frame, stream): threads 0..127 = output position i of channel 0, 128..255 of
+// channel 1.  Position i reads the 384 samples x[0..383] = buf[16 i ..] (buf = 368 history samples |
+// the frame) and produces one sample of each of the 16 subbands:
+//   vectoring  y[t] = sum_{j<12} (double)(fir[12 t + j] * x[32 j + t]),  t < 32  (float product, double sum)
+//   matrixing  yy[k] = (float)(y[k + 8] + y[7 - k]),  yy[k + 8] = (float)(y[k + 16] + y[31 - k])
+//              res = DCT-IV-16(yy) (TMIDCT<32> + 8-point kissfft);  out[sb][i] = res[15 - sb]
+// The tile is padded by one float per 16 so that the 16-float stride between lanes is conflict-free.
+constexpr int kPqfTile = kFrame + kPqfOverlap;                       // 2416
+ATDE_HD int pphys(int e) { return e + (e >> 4); }
+constexpr int kPqfTilePad = kPqfTile + kPqfTile / 16 + 1;
+
+// out[i] = -Buf[i + 8] of TMIDCT<32> (mdct.cpp:73-81, mdct.h:117-180) on 16 inputs.
+ATDE_D void dct4_16(const float* in, float* out)
+{
+    cpx v[8];                                       // FFT input in kissfft's gather order
+    // 8 = 4 x 2: slot = 2 d0 + d1 holds input d0 + 4 d1
+#pragma unroll
+    for (int slot = 0; slot < 8; slot++) {
+        const int idx = (slot >> 1) + 4 * (slot & 1);
+        const int n = 2 * idx;
+        const float r0 = in[n], i0 = in[15 - n];
+        const float c = c_dct_sc[n], s = c_dct_sc[n + 1];
+        // xr = -2.0 * (i0 * s + r0 * c); xi = -2.0 * (i0 * c - r0 * s): the float sums, doubled and negated exactly
+        v[slot].r = fmul(-2.0f, fadd(fmul(i0, s), fmul(r0, c)));
+        v[slot].i = fmul(-2.0f, fsub(fmul(i0, c), fmul(r0, s)));
+    }
+    // radix-2, m = 1 (fstride 4), twiddle tw[0]
+#pragma unroll
+    for (int q = 0; q < 4; q++) kf_bfly2(v[2 * q], v[2 * q + 1], c_tw8[0]);
+    // radix-4, m = 2 (fstride 1): elements k + 2q, twiddles tw[k], tw[2k], tw[3k]
+#pragma unroll
+    for (int k = 0; k < 2; k++) kf_bfly4<false>(v[k], v[k + 2], v[k + 4], v[k + 6], c_tw8[k], c_tw8[2 * k], c_tw8[3 * k]);
+    float buf[32];
+#pragma unroll
+    for (int h = 0; h < 8; h++) {
+        const int n = 2 * h;
+        const float r0 = v[h].r, i0 = v[h].i;
+        const float c = c_dct_sc[n], s = c_dct_sc[n + 1];
+        const float r1 = fadd(fmul(r0, c), fmul(i0, s));
+        const float i1 = fsub(fmul(r0, s), fmul(i0, c));
+        if (n < 8) { buf[23 - n] = r1; buf[24 + n] = r1; buf[8 + n] = i1; buf[7 - n] = -i1; }
+        else       { buf[23 - n] = r1; buf[n - 8] = -r1; buf[8 + n] = i1; buf[39 - n] = i1; }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = -buf[i + 8];
+}
+
+__global__ void __launch_bounds__(256) at3p_pqf_kernel(const float* __restrict__ pcm, float* __restrict__ bands,
+                                                        int S, int C, int F)
+{
+    __shared__ float xs[2][kPqfTilePad];
+    const int f = blockIdx.x, s = blockIdx.y;
+    const int tid = threadIdx.x;
+    const long long n0 = (long long)f * kFrame - kPqfOverlap;        // tile sample 0 within the stream
+    const float* src = pcm + (size_t)s * F * kFrame * C;
+    ATDE_PAR_FOR(t, kPqfTile) {
+        const long long n = n0 + t;
+        float v0 = 0.0f, v1 = 0.0f;
+        if (n >= 0) {
+            if (C == 2) {
+                const float2 v = *reinterpret_cast<const float2*>(src + (size_t)n * 2);
+                v0 = v.x; v1 = v.y;
+            } else {
+                v0 = src[n];
+            }
+        }
+        xs[0][pphys(t)] = v0;
+        xs[1][pphys(t)] = v1;
+    }
+    __syncthreads();
+    const int ch = tid >> 7, i = tid & 127;
+    if (ch >= C) return;
+    const float* x = xs[ch];
+    const int base = 16 * i;
+    float yy[16];
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        // four accumulator chains at once: y[k+8], y[7-k], y[k+16], y[31-k]
+        const int t0 = k + 8, t1 = 7 - k, t2 = k + 16, t3 = 31 - k;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            a0 = __dadd_rn(a0, (double)fmul(c_fir[12 * t0 + j], x[pphys(base + 32 * j + t0)]));
+            a1 = __dadd_rn(a1, (double)fmul(c_fir[12 * t1 + j], x[pphys(base + 32 * j + t1)]));
+            a2 = __dadd_rn(a2, (double)fmul(c_fir[12 * t2 + j], x[pphys(base + 32 * j + t2)]));
+            a3 = __dadd_rn(a3, (double)fmul(c_fir[12 * t3 + j], x[pphys(base + 32 * j + t3)]));
+        }
+        const float lo = __double2float_rn(__dadd_rn(a0, a1));
+        const float hi = __double2float_rn(__dadd_rn(a2, a3));
+        // yy[k], yy[k + 8] without dynamic register indexing
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (q == k) { yy[q] = lo; yy[q + 8] = hi; }
+    }
+    float res[16];
+    dct4_16(yy, res);
+    float* out = bands + (((size_t)s * C + ch) * F + f) * kFrame + i;
+#pragma unroll
+    for (int sb = 0; sb < 16; sb++) out[sb * kSbSamples] = res[15 - sb];
+}
+
+void launch_pqf(const float* pcm, float* bands, int S, int C, int F, cudaStream_t st)
+{
+    dim3 grid(F, S);
+    ATDE_LAUNCH(at3p_pqf_kernel, grid, 256, 0, st, pcm, bands, S, C, F);
+}
+
+// =====================================================================================
+// P4: TAt3pMDCT::Do with sine windows (at3p_mdct.cpp:52-96), TMDCT<256> (mdct.h:51-104)
+// =====================================================================================
+// One WARP per (stream, frame, channel); two iterations of eight subbands, four lanes per band.
+//   phase A  in[j] = win[j] * prev[j] (the overlap half the previous frame left behind, recomputed from
+//            the previous frame's samples), in[128 + j] = win[127 - j] * cur[j]
+//   phase B  fold + pre-twiddle into kissfft's gather order (64 = 4 x 4 x 4); lane k4 owns slots
+//            16 k4 .. 16 k4 + 15 and runs the stages m = 1 and m = 4 on registers
+//   exchange through the tile; phase C: stage m = 16 on elements k + 16 q, k = k4 + 4 c; post-twiddle;
+//            odd bands reversed (SwapArray); staged and written as coalesced float4
+constexpr int kPmWarps = 4;
+constexpr int kPmBandStride = 264;                   // floats per band in the tile (256 + 8)
+constexpr int kPmXchStride = 68;                     // cpx per band in the exchange layout: 4 lanes x 17, and 68 = 4 mod 16 spreads the bands
+constexpr int kPmOutStride = 136;                    // floats per band in the output stage (128 + 8)
+
+__global__ void __launch_bounds__(kPmWarps * 32, 6) at3p_mdct_kernel(const DevTables* __restrict__ T,
+                                                                      const float* __restrict__ resid,
+                                                                      float* __restrict__ specs, int S, int C, int F)
+{
+    __shared__ __align__(16) float tile[kPmWarps][8 * kPmBandStride];
+    __shared__ __align__(16) float s_sincos[128];
+    __shared__ __align__(16) float s_win[128];
+    __shared__ __align__(16) cpx s_tw[64];
+    ATDE_PAR_FOR(i, 128) { s_sincos[i] = T->sincos256[i]; s_win[i] = T->sine_win[i]; }
+    ATDE_PAR_FOR(i, 64) s_tw[i] = T->tw64[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tl = tile[warp];
+    const long long n_units = (long long)S * F * C;
+    for (long long unit = (long long)blockIdx.x * kPmWarps + warp; unit < n_units;
+         unit += (long long)gridDim.x * kPmWarps) {
+        const int c = (int)(unit % C);
+        const long long sf = unit / C;
+        const int f = (int)(sf % F), s = (int)(sf / F);
+        const float* cur = resid + (((size_t)s * C + c) * F + f) * kFrame;
+        float* const outp = specs + (size_t)unit * kFrame;
+#pragma unroll 1
+        for (int it = 0; it < 2; it++) {                     // subbands 8 it .. 8 it + 7
+            __syncwarp();
+            // ---- phase A ----
+#pragma unroll
+            for (int h = 0; h < 8; h++) {
+                const int w = lane + 32 * h;                 // float4 index within the 8 x 128 samples
+                const int band = w >> 5, i0 = 4 * (w & 31);
+                const float4 x = *reinterpret_cast<const float4*>(cur + (8 * it + band) * kSbSamples + i0);
+                float4 y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (f > 0) y = *reinterpret_cast<const float4*>(cur - kFrame + (8 * it + band) * kSbSamples + i0);
+                const float4 wf = *reinterpret_cast<const float4*>(&s_win[i0]);
+                const float4 wb = *reinterpret_cast<const float4*>(&s_win[124 - i0]);
+                float* in = tl + band * kPmBandStride;
+                *reinterpret_cast<float4*>(in + i0) =
+                    make_float4(fmul(wf.x, y.x), fmul(wf.y, y.y), fmul(wf.z, y.z), fmul(wf.w, y.w));
+                *reinterpret_cast<float4*>(in + 128 + i0) =
+                    make_float4(fmul(wb.w, x.x), fmul(wb.z, x.y), fmul(wb.y, x.z), fmul(wb.x, x.w));
+            }
+            __syncwarp();
+            // ---- phase B ----
+            const int band = lane >> 2, k4 = lane & 3;
+            cpx e[4][4];                                     // after the exchange: element (k4 + 4 c) + 16 q -> e[c][q]
+            {
+                const float* in = tl + band * kPmBandStride;
+                cpx v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    // slot 16 k4 + j of the 4x4x4 digit reversal: i = d0 + 4 d1 + 16 d2
+                    const int n = 2 * (k4 + 4 * (j >> 2) + 16 * (j & 3));    // N = 256, n4 = 64, n34 = 192, n54 = 320
+                    float r0, i0;
+                    if ((j & 3) < 2) { r0 = fadd(in[191 - n], in[192 + n]); i0 = fsub(in[64 + n], in[63 - n]); }   // n < 64
+                    else             { r0 = fsub(in[191 - n], in[n - 64]);  i0 = fadd(in[64 + n], in[319 - n]); }
+                    const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
+                    v[j].r = fadd(fmul(r0, cs.x), fmul(i0, cs.y));
+                    v[j].i = fsub(fmul(i0, cs.x), fmul(r0, cs.y));
+                }
+                // radix-4, m = 1 (fstride 16): elements 4 g + q, twiddles tw[0]
+#pragma unroll
+                for (int gq = 0; gq < 4; gq++)
+                    kf_bfly4<false>(v[4 * gq], v[4 * gq + 1], v[4 * gq + 2], v[4 * gq + 3], s_tw[0], s_tw[0], s_tw[0]);
+                // radix-4, m = 4 (fstride 4): elements k + 4 q, twiddles tw[4 k q']
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    kf_bfly4<false>(v[k], v[k + 4], v[k + 8], v[k + 12], s_tw[4 * k], s_tw[8 * k], s_tw[12 * k]);
+                __syncwarp();                                // every lane has read its MDCT input
+                cpx* xch = reinterpret_cast<cpx*>(tl) + band * kPmXchStride;
+#pragma unroll
+                for (int j = 0; j < 16; j++) xch[17 * k4 + j] = v[j];         // 17-element lane stride: conflict-free
+                __syncwarp();
+#pragma unroll
+                for (int cq = 0; cq < 4; cq++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) e[cq][q] = xch[17 * q + (k4 + 4 * cq)];   // element (k4 + 4cq) + 16 q
+            }
+            // ---- phase C: radix-4, m = 16 (fstride 1) ----
+#pragma unroll
+            for (int cq = 0; cq < 4; cq++) {
+                const int k = k4 + 4 * cq;
+                kf_bfly4<false>(e[cq][0], e[cq][1], e[cq][2], e[cq][3], s_tw[k], s_tw[2 * k], s_tw[3 * k]);
+            }
+            __syncwarp();
+            {
+                float* sp = tl + band * kPmOutStride;
+#pragma unroll
+                for (int cq = 0; cq < 4; cq++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int n = 2 * (k4 + 4 * cq + 16 * q);
+                        const cpx z = e[cq][q];
+                        const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
+                        const float va = fsub(fmul(-z.r, cs.x), fmul(z.i, cs.y));
+                        const float vb = fadd(fmul(-z.r, cs.y), fmul(z.i, cs.x));
+                        int pa = n, pb = 127 - n;
+                        if (band & 1) { pa = 127 - pa; pb = 127 - pb; }       // SwapArray for odd subbands (8 it is even)
+                        sp[pa] = va;
+                        sp[pb] = vb;
+                    }
+            }
+            __syncwarp();
+            float4* out = reinterpret_cast<float4*>(outp + 1024 * it);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int w = lane + 32 * q;                 // float4 index; band = w >> 5
+                out[w] = *reinterpret_cast<const float4*>(tl + (w >> 5) * kPmOutStride + 4 * (w & 31));
+            }
+        }
+    }
+}
+
+void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, int C, int F, cudaStream_t st)
+{
+    const long long n_units = (long long)S * F * C;
+    long long blocks = (n_units + kPmWarps - 1) / kPmWarps;
+    if (blocks > 148 * 6 * 4) blocks = 148 * 6 * 4;
+    ATDE_LAUNCH(at3p_mdct_kernel, (unsigned)blocks, kPmWarps * 32, 0, st, T, resid, specs, S, C, F);
+}
+
+} // namespace at3p
+} // namespace atde
+
+// =====================================================================================
+// Stage entry points (host buffers in, host buffers out).  ATRAC3plus is not reachable through
+// atde_create() until the GHA stage exists; these let tests/ drive each finished kernel against the
+// reference's taps (oracle/ref_harness_at3p.cpp).  Declared in at3p_stage_api.h, not in include/.
+// =====================================================================================
+namespace {
+template <class T> struct ScopedDev {
+    T* p = nullptr;
+    ~ScopedDev() { if (p) cudaFree(p); }
+    bool alloc(size_t n) { return cudaMalloc(&p, n * sizeof(T)) == cudaSuccess; }
+};
+} // namespace
+
+extern "C" int atde_at3p_stage_pqf(const float* pcm, int S, int C, int F, float* bands)
+{
+    using namespace atde::at3p;
+    if (!device_tables()) return -2;
+    const size_t n = (size_t)S * C * F * kFrame;
+    ScopedDev<float> d_in, d_out;
+    if (!d_in.alloc(n) || !d_out.alloc(n)) return -3;
+    if (cudaMemcpy(d_in.p, pcm, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    launch_pqf(d_in.p, d_out.p, S, C, F, nullptr);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+    return cudaMemcpy(bands, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int atde_at3p_stage_mdct(const float* resid, int S, int C, int F, float* specs)
+{
+    using namespace atde::at3p;
+    const DevTables* T = device_tables();
+    if (!T) return -2;
+    const size_t n = (size_t)S * C * F * kFrame;
+    ScopedDev<float> d_in, d_out;
+    if (!d_in.alloc(n) || !d_out.alloc(n)) return -3;
+    if (cudaMemcpy(d_in.p, resid, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    launch_mdct(T, d_in.p, d_out.p, S, C, F, nullptr);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+    return cudaMemcpy(specs, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}

@@ -1,0 +1,68 @@
+// at3p_kernels.cuh — device-side interface of the ATRAC3plus encode path (at3p_kernels.cu).
+//
+// Reference chain: at3plus_pqf_do_analyse (src/atrac/atrac3plus_pqf/atrac3plus_pqf.c:130-147)
+// -> IGhaProcessor::DoAnalize (src/atrac/at3p/at3p_gha.cpp:692) -> TAt3pMDCT::Do (src/atrac/at3p/at3p_mdct.cpp:52-96)
+// -> TScaler<NAt3p::TScaleTable>::ScaleFrame (src/atrac/atrac_scale.cpp:141-188)
+// -> TAt3PBitStream::WriteFrame (src/atrac/at3p/at3p_bitstream.cpp:703-726), driven by
+// TAt3PEnc::TImpl::EncodeFrame (src/atrac/at3p/at3p.cpp:88-194).
+//
+// Built so far: the PQF analysis filterbank, the 16-band MDCT-256 and the frame packer (scale,
+// quantise, code-table choice, tonal block, bit writer).  The GHA tone extraction between the
+// filterbank and the MDCT is not built yet; until it is, ATRAC3plus is not reachable through
+// atde_create() and these kernels are exercised stage by stage against the reference's taps.
+#pragma once
+#include "atde_cuda.h"
+
+namespace atde {
+namespace at3p {
+
+constexpr int kFrame = 2048;          // samples per channel-frame (src/atrac3p.h:61)
+constexpr int kSubbands = 16;
+constexpr int kSbSamples = 128;
+constexpr int kPqfProto = 384;        // prototype length (atrac3plus_pqf.c:42)
+constexpr int kPqfOverlap = kPqfProto - kSubbands;   // 368 history samples (atrac3plus_pqf.c:45)
+constexpr int kQuantUnits = 32;
+constexpr int kFrameBytes = 2048;     // at3p.cpp:41: BitStream(out, 2048)
+constexpr int kMaxWaves = 48;         // at3p_gha.cpp:611
+
+// Device tables, built on the host by build_tables() with the reference's expressions
+struct DevTables {
+    alignas(16) float sincos256[128]; // TMDCT<256>(1)   (mdct.cpp:25-36)
+    alignas(16) float sine_win[128];  // SineWin128      (at3p_mdct.cpp:36-40)
+    alignas(16) cpx tw64[64];         // forward kissfft twiddles of the 64-point FFT
+    alignas(16) float scale_table[64];// NAt3p::TScaleTable::ScaleTable (at3p_tables.cpp:42-70)
+    float inv_mant[8];                // 1 / atrac3p_mant_tab[wl] (at3p_tables.cpp:28-38)
+    unsigned char spec_tab[56][4];    // group_size, num_coeffs, bits, is_signed (ff/atrac3plus_data.h:1427)
+    unsigned vlc_off[57];
+    unsigned vlc[7812];               // code | len << 16 of THuffTables::VlcSpecs[0..55]
+    unsigned wl_vlc[4][8];            // THuffTables::WordLens
+    unsigned tone_bands_vlc[16];      // THuffTables::NumToneBands
+    unsigned char qu_to_subband[32];
+    unsigned char sb_to_powgrps[16];
+};
+
+// Flattened TAt3PGhaData (src/atrac/at3p/at3p_gha.h:29-66): what the tonal-block writer consumes.
+struct ToneBlock {
+    int present;                      // a non-null block with NumToneBands > 0
+    int num_tone_bands;
+    int second_is_leader;
+    int tone_sharing[16];
+    int n_sb[2];
+    int sb[2][16][4];                 // WaveIndex, WaveNums, Envelope.first, Envelope.second
+    int n_params[2];
+    int params[2][64][4];             // FreqIndex, AmpSf, AmpIndex, PhaseIndex
+};
+
+const DevTables* device_tables();     // builds + uploads on first use; nullptr on failure
+
+// pcm [S][F*2048][C] interleaved -> bands [S][C][F][16][128]; every stream starts with a zero history
+void launch_pqf(const float* pcm, float* bands, int S, int C, int F, cudaStream_t st);
+// resid [S][C][F][16][128] (already scaled to the MDCT's input range) -> specs [S][F][C][2048];
+// every stream starts with a zero overlap history
+void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, int C, int F, cudaStream_t st);
+// specs [U][C][2048], tones [U] -> frames [U][2048]
+void launch_pack(const DevTables* T, const float* specs, const ToneBlock* tones, unsigned char* frames,
+                 int units, int C, cudaStream_t st);
+
+} // namespace at3p
+} // namespace atde

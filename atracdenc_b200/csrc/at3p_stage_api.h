@@ -1,0 +1,17 @@
+/* at3p_stage_api.h — stage-level entry points of the ATRAC3plus kernels (host buffers in/out).
+ * NOT part of the drop-in boundary (include/atde_b200.h): ATRAC3plus cannot be created through
+ * atde_create() until the GHA stage exists.  tests/ uses these to check every finished kernel
+ * against the reference's taps.  All return 0 on success, -2 on a CUDA error, -3 on allocation failure. */
+#pragma once
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* at3plus_pqf_do_analyse (src/atrac/atrac3plus_pqf/atrac3plus_pqf.c:130-147) over F frames of S fresh
+ * streams: pcm [S][F*2048][C] interleaved -> bands [S][C][F][16][128]. */
+int atde_at3p_stage_pqf(const float* pcm, int S, int C, int F, float* bands);
+/* TAt3pMDCT::Do, sine windows (src/atrac/at3p/at3p_mdct.cpp:52-96), fresh history:
+ * resid [S][C][F][16][128] -> specs [S][F][C][2048]. */
+int atde_at3p_stage_mdct(const float* resid, int S, int C, int F, float* specs);
+#ifdef __cplusplus
+}
+#endif

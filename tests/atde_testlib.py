@@ -253,3 +253,52 @@ def synth_rich(n_frames, frame_samples, channels, seed=1, kind="mix"):
         if channels == 2:
             x[n // 2:, 1] = 0.9 * x[n // 2:, 0] + 0.01 * rng.uniform(-1, 1, n - n // 2)   # correlated half: M/S budget shift
     return quantise(np.clip(x, -1, 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# ATRAC3plus reference taps (oracle/ref_harness_at3p.cpp)
+AT3P_GHA_REC = np.dtype([
+    ("present", np.int32), ("num_tone_bands", np.int32), ("second_is_leader", np.int32),
+    ("tone_sharing", np.int32, (16,)), ("n_sb", np.int32, (2,)), ("sb", np.int32, (2, 16, 4)),
+    ("n_params", np.int32, (2,)), ("params", np.int32, (2, 64, 4)),
+])
+
+
+def ref_at3p_pqf(x):
+    """at3plus_pqf_do_analyse over whole frames of one channel, fresh context -> [F][2048]."""
+    lib = ref_lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    F = x.size // 2048
+    out = np.zeros((F, 2048), np.float32)
+    lib.ref_at3p_pqf(x.ctypes.data_as(P), ctypes.c_long(F), out.ctypes.data_as(P))
+    return out
+
+
+def ref_at3p_mdct(bands):
+    """TAt3pMDCT::Do (sine windows, fresh history) over [F][2048] -> [F][2048]."""
+    lib = ref_lib()
+    bands = np.ascontiguousarray(bands, dtype=np.float32)
+    F = bands.shape[0]
+    out = np.zeros((F, 2048), np.float32)
+    lib.ref_at3p_mdct(bands.ctypes.data_as(P), ctypes.c_long(F), out.ctypes.data_as(P))
+    return out
+
+
+def ref_at3p_stages(channels, pcm, gha_flags=-1):
+    """Drives TAt3PEnc frame by frame; per output frame: the PQF-domain frames, the work buffer
+    before / after the tone filter, the GHA result of that call, the spectra and the frame bytes."""
+    lib = ref_lib()
+    assert lib.ref_at3p_gha_rec_size() == AT3P_GHA_REC.itemsize
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    F = pcm.size // channels // 2048
+    z = lambda: np.zeros((F, channels, 2048), np.float32)
+    cur, nxt, win, wout, specs = z(), z(), z(), z(), z()
+    gha = np.zeros(F, AT3P_GHA_REC)
+    frames = np.zeros((F, 2048), np.uint8)
+    lib.ref_at3p_stages.restype = ctypes.c_long
+    k = lib.ref_at3p_stages(channels, pcm.ctypes.data_as(P), ctypes.c_long(F), gha_flags,
+                            cur.ctypes.data_as(P), nxt.ctypes.data_as(P), win.ctypes.data_as(P),
+                            wout.ctypes.data_as(P), gha.ctypes.data_as(P), specs.ctypes.data_as(P),
+                            frames.ctypes.data_as(P))
+    return dict(n=k, pqf_cur=cur[:k], pqf_next=nxt[:k], work_in=win[:k], work_out=wout[:k], gha=gha[:k],
+                specs=specs[:k], frames=frames[:k])

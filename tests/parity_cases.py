@@ -351,3 +351,68 @@ def check_at3_errors(lib):
     enc = ab.Encoder(ab.CODEC_ATRAC3, 2, bitrate=64 * 1024, lib=lib)
     assert enc.unit_bytes == 192
     enc.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# ATRAC3plus, stage by stage (the GHA stage is not built yet: atracdenc_b200/csrc/at3p_stage_api.h)
+def _at3p_signal(S, F, C, seed):
+    kinds = ("mix", "tones", "steps", None)
+    streams = []
+    for s in range(S):
+        kind = kinds[s % len(kinds)]
+        streams.append(tl.synth_streams(1, F, 2048, C, seed=seed + s)[0] if kind is None
+                       else tl.synth_rich(F, 2048, C, seed=seed + s, kind=kind))
+    return np.stack(streams)                                       # [S][F*2048][C]
+
+
+def at3p_stage_pqf(lib, pcm, S, C, F):
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    out = np.zeros((S, C, F, 2048), np.float32)
+    rc = lib.atde_at3p_stage_pqf(pcm.ctypes.data_as(tl.P), S, C, F, out.ctypes.data_as(tl.P))
+    assert rc == 0, f"atde_at3p_stage_pqf -> {rc}"
+    return out
+
+
+def at3p_stage_mdct(lib, resid, S, C, F):
+    resid = np.ascontiguousarray(resid, dtype=np.float32)
+    out = np.zeros((S, F, C, 2048), np.float32)
+    rc = lib.atde_at3p_stage_mdct(resid.ctypes.data_as(tl.P), S, C, F, out.ctypes.data_as(tl.P))
+    assert rc == 0, f"atde_at3p_stage_mdct -> {rc}"
+    return out
+
+
+def check_at3p_pqf(lib, S=3, F=6, C=2, seed=900):
+    """PQF analysis bit-exact against at3plus_pqf_do_analyse (fresh context per stream and channel)."""
+    pcm = _at3p_signal(S, F, C, seed)
+    got = at3p_stage_pqf(lib, pcm, S, C, F)
+    if tl.ref_lib() is None:
+        return 0
+    for s in range(S):
+        for c in range(C):
+            want = tl.ref_at3p_pqf(pcm[s, :, c])
+            bad = np.argwhere(got[s, c].view(np.uint32) != want.view(np.uint32))
+            assert bad.size == 0, f"stream {s} ch {c}: first differing (frame, index) = {bad[:4].tolist()}"
+    return S
+
+
+def check_at3p_mdct(lib, S=2, F=6, C=2, seed=910):
+    """MDCT bit-exact against TAt3pMDCT::Do fed with the residual the reference encoder produced
+    (work buffer after the tone filter, scaled like at3p.cpp:150-153)."""
+    if tl.ref_lib() is None:
+        return 0
+    pcm = _at3p_signal(S, F + 1, C, seed)
+    resid = np.zeros((S, C, F, 2048), np.float32)
+    want = np.zeros((S, F, C, 2048), np.float32)
+    for s in range(S):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        assert st["n"] == F
+        # tmp[i] = x[i] / (32768.0 / 1.122018): double division, rounded to float on the store
+        r = (st["work_out"].astype(np.float64) / (32768.0 / 1.122018)).astype(np.float32)
+        resid[s] = r.transpose(1, 0, 2)
+        want[s] = st["specs"]
+        for c in range(C):                                           # the harness' own MDCT entry agrees with the encoder's
+            assert np.array_equal(tl.ref_at3p_mdct(r[:, c]).view(np.uint32), st["specs"][:, c].view(np.uint32))
+    got = at3p_stage_mdct(lib, resid, S, C, F)
+    bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+    assert bad.size == 0, f"first differing (stream, frame, ch, line) = {bad[:4].tolist()}"
+    return S

@@ -1,0 +1,13 @@
+"""CPU-only: the ATRAC3plus stage kernels compiled against the pthread CUDA shim (tests/cpuemu),
+checked against the reference's taps (oracle/_ref).  The GPU suite repeats these on hardware."""
+import parity_cases as pc
+
+
+def test_pqf(emu_lib):
+    pc.check_at3p_pqf(emu_lib, S=2, F=3, C=2)
+    pc.check_at3p_pqf(emu_lib, S=1, F=2, C=1, seed=905)
+
+
+def test_mdct(emu_lib):
+    pc.check_at3p_mdct(emu_lib, S=2, F=4, C=2)
+    pc.check_at3p_mdct(emu_lib, S=1, F=3, C=1, seed=915)

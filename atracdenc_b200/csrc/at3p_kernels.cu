@@ -39,7 +39,8 @@ static void build_tables()
     const auto tw = kiss_twiddles(64, false);
     memcpy(h->tw64, tw.data(), sizeof(h->tw64));
     for (int i = 0; i < 64; i++) h->scale_table[i] = bits_to_float(kAt3pScaleBits[i]);
-    for (int i = 0; i < 8; i++) h->inv_mant[i] = bits_to_float(kAt3pInvMantBits[i]);
+    h->inv_mant[0] = 0.0f;
+    for (int i = 1; i < 8; i++) h->inv_mant[i] = 1.0f / bits_to_float(kAt3pMantTabBits[i]);   // TUnit::Multiplier, at3p_bitstream.cpp:365-368
     memcpy(h->spec_tab, kAt3pSpecTab, sizeof(h->spec_tab));
     memcpy(h->vlc_off, kAt3pVlcOff, sizeof(h->vlc_off));
     static_assert(sizeof(kAt3pVlc) == sizeof(DevTables::vlc), "generated VLC table size");
@@ -314,6 +315,382 @@ void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, in
     ATDE_LAUNCH(at3p_mdct_kernel, (unsigned)blocks, kPmWarps * 32, 0, st, T, resid, specs, S, C, F);
 }
 
+// =====================================================================================
+// P5: TScaler<NAt3p::TScaleTable>::ScaleFrame (atrac_scale.cpp:141-188) + TAt3PBitStream::WriteFrame
+//     (at3p_bitstream.cpp:703-726) with its five part encoders (:98-701)
+// =====================================================================================
+// One WARP per frame (both channels).  The reference's allocation is static: word length per quant unit
+// from TConfigure's table (:106-112), so a unit's mantissas, its best code table and its bit cost do
+// not depend on how many units are finally coded; the only search is TTonalComponentEncoder's
+// "drop units until the frame fits" loop (:596-609), evaluated here for every candidate count at once.
+__constant__ unsigned char c_alloc[32] = {7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7,
+                                          7, 6, 6, 6, 6, 6, 6, 6, 6, 6, 5, 5, 4, 3, 2, 1};      // at3p_bitstream.cpp:106-112
+__constant__ unsigned short c_qu_start[33] = {0, 16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256, 288, 320, 352,
+                                              384, 448, 512, 576, 640, 704, 768, 896, 1024, 1152, 1280, 1408, 1536,
+                                              1664, 1792, 1920, 2048};                            // at3p_tables.h:66-72
+constexpr int kPackWarps = 4;
+constexpr int kFrameBits = kFrameBytes * 8;
+constexpr int kAllocBits = kFrameBits - 3;           // FrameSzToAllocBits, at3p_bitstream.cpp:441
+
+struct __align__(16) PackSm {
+    signed char mant[2][kFrame];
+    unsigned words[kFrameBytes / 4 + 4];
+    unsigned twords[96];                             // the tonal part's own buffer (TDumper::Buf), <= 3072 bits
+    unsigned short qbits[2][32];                     // bits of the cheapest code table per unit
+    unsigned char qtab[2][32];
+    unsigned char sfi[2][32];
+};
+
+ATDE_D void put_bits(unsigned* words, int cap_bits, int pos, int n, unsigned val)
+{
+    if (n <= 0 || pos + n > cap_bits) return;
+    const int w = pos >> 5, off = pos & 31;
+    const int room = 32 - off;
+    if (n <= room) {
+        atomicOr(&words[w], val << (room - n));
+    } else {
+        atomicOr(&words[w], val >> (n - room));
+        atomicOr(&words[w + 1], val << (32 - (n - room)));
+    }
+}
+
+// TBitStream::Write keeps the low n bits of the value (bitstream.cpp:49)
+ATDE_NOINLINE int put_field(unsigned* words, int cap_bits, int pos, unsigned v, int n)
+{
+    put_bits(words, cap_bits, pos, n, n >= 32 ? v : (v & ((1u << n) - 1u)));
+    return pos + n;
+}
+
+// One VLC symbol of TQuantUnitsEncoder::EncodeQuSpectra (:283-343): optional group flag, code, sign bits.
+ATDE_D unsigned spec_symbol(const DevTables* T, int tab, const signed char* m, int s, int& nbits)
+{
+    const int g = T->spec_tab[tab][0], nc = T->spec_tab[tab][1], bits = T->spec_tab[tab][2], sgn = T->spec_tab[tab][3];
+    unsigned val = 0, signs = 0;
+    int nsign = 0;
+    for (int i = 0; i < nc; i++) {
+        int t = m[s * nc + i];
+        if (!sgn && t != 0) {
+            signs = (signs << 1) | (t < 0 ? 1u : 0u);
+            nsign++;
+            if (t < 0) t = -t;
+        } else {
+            t &= (1 << bits) - 1;
+        }
+        val |= (unsigned)t << (bits * i);
+    }
+    const unsigned e = T->vlc[T->vlc_off[tab] + (val & 255u)];
+    unsigned out = e & 0xffffu;
+    int n = (int)(e >> 16);
+    out = (out << nsign) | signs;
+    n += nsign;
+    if (g != 1 && (s % g) == 0) { out |= 1u << n; n++; }
+    nbits = n;
+    return out;
+}
+
+ATDE_D int first_set_bit(unsigned x) { return x ? 31 - __clz((int)x) : 0; }   // util.h:65-76
+
+// TTonalComponentEncoder::WriteTonalBlock (:465-594) into the part's own buffer; one lane.  Returns bits used.
+ATDE_D int write_tonal_block(const DevTables* T, unsigned* w, int cap, int pos, int channels, const ToneBlock* tb)
+{
+    pos = put_field(w, cap, pos, 1, 1);                                          // GHA amplitude mode 1
+    const unsigned tbv = T->tone_bands_vlc[tb->num_tone_bands - 1];
+    pos = put_field(w, cap, pos, tbv & 0xffffu, (int)(tbv >> 16));
+    const int ntb = tb->num_tone_bands;
+    auto flags = [&](const int* fl, int nfl) {                                   // WriteSubbandFlags (:444-463)
+        int sum = 0;
+        for (int i = 0; i < nfl; i++) sum += fl[i] ? 1 : 0;
+        if (sum == 0) {
+            pos = put_field(w, cap, pos, 0, 1);
+        } else if (sum == nfl) {
+            pos = put_field(w, cap, pos, 1, 1);
+            pos = put_field(w, cap, pos, 0, 1);
+        } else {
+            pos = put_field(w, cap, pos, 1, 1);
+            pos = put_field(w, cap, pos, 1, 1);
+            for (int i = 0; i < nfl; i++) pos = put_field(w, cap, pos, fl[i] ? 1 : 0, 1);
+        }
+    };
+    if (channels == 2) {
+        flags(tb->tone_sharing, ntb);
+        flags(&tb->second_is_leader, 1);
+        pos = put_field(w, cap, pos, 0, 1);
+    }
+    for (int ch = 0; ch < channels; ch++) {
+        if (ch) pos = put_field(w, cap, pos, 0, 1);                              // each channel has its own envelope
+        for (int i = 0; i < ntb; i++) {
+            if (ch && tb->tone_sharing[i]) continue;
+            const unsigned e0 = (unsigned)tb->sb[ch][i][2], e1 = (unsigned)tb->sb[ch][i][3];
+            if (e0 != 0xffffffffu) { pos = put_field(w, cap, pos, 1, 1); pos = put_field(w, cap, pos, e0, 5); }
+            else pos = put_field(w, cap, pos, 0, 1);
+            if (e1 != 0xffffffffu) { pos = put_field(w, cap, pos, 1, 1); pos = put_field(w, cap, pos, e1, 5); }
+            else pos = put_field(w, cap, pos, 0, 1);
+        }
+        pos = put_field(w, cap, pos, 0, ch + 1);                                 // num waves mode
+        for (int i = 0; i < ntb; i++) {
+            if (ch && tb->tone_sharing[i]) continue;
+            pos = put_field(w, cap, pos, (unsigned)tb->sb[ch][i][1], 4);
+        }
+        if (ch) pos = put_field(w, cap, pos, 0, 1);                              // frequencies coded independently
+        for (int i = 0; i < ntb; i++) {
+            if (ch && tb->tone_sharing[i]) continue;
+            const int nw = tb->sb[ch][i][1];
+            if (nw == 0) continue;
+            const int (*prm)[4] = &tb->params[ch][tb->sb[ch][i][0]];
+            // CreateFreqBitPack (:39-96): ascending vs descending delta coding, fewer bits wins (ties: descending)
+            int bits_asc = 10, bits_desc = 10;
+            {
+                unsigned prev = (unsigned)prm[0][0] & 1023u;
+                for (int k = 1; k < nw; k++) {
+                    bits_asc += prev < 512 ? 10 : first_set_bit(1023 - prev) + 1;
+                    prev = (unsigned)prm[k][0] & 1023u;
+                }
+                prev = (unsigned)prm[nw - 1][0] & 1023u;
+                for (int k = nw - 2; k >= 0; k--) {
+                    bits_desc += first_set_bit(prev) + 1;
+                    prev = (unsigned)prm[k][0] & 1023u;
+                }
+            }
+            const bool asc = nw == 1 || bits_asc < bits_desc;
+            if (nw > 1) pos = put_field(w, cap, pos, asc ? 0 : 1, 1);
+            if (asc) {
+                unsigned prev = (unsigned)prm[0][0] & 1023u;
+                pos = put_field(w, cap, pos, prev, 10);
+                for (int k = 1; k < nw; k++) {
+                    const unsigned cur = (unsigned)prm[k][0] & 1023u;
+                    if (prev < 512) {
+                        pos = put_field(w, cap, pos, cur, 10);
+                    } else {
+                        const int bq = first_set_bit(1023 - prev) + 1;
+                        pos = put_field(w, cap, pos, (cur - (1024u - (1u << bq))) & 0xffffu, bq);
+                    }
+                    prev = cur;
+                }
+            } else {
+                unsigned prev = (unsigned)prm[nw - 1][0] & 1023u;
+                pos = put_field(w, cap, pos, prev, 10);
+                for (int k = nw - 2; k >= 0; k--) {
+                    const unsigned cur = (unsigned)prm[k][0] & 1023u;
+                    pos = put_field(w, cap, pos, cur, first_set_bit(prev) + 1);
+                    prev = cur;
+                }
+            }
+        }
+        pos = put_field(w, cap, pos, 0, ch + 1);                                 // amplitude mode
+        for (int i = 0; i < ntb; i++) {
+            if (ch && tb->tone_sharing[i]) continue;
+            const int nw = tb->sb[ch][i][1];
+            for (int k = 0; k < nw; k++) pos = put_field(w, cap, pos, (unsigned)tb->params[ch][tb->sb[ch][i][0] + k][1], 6);
+        }
+        for (int i = 0; i < ntb; i++) {
+            if (ch && tb->tone_sharing[i]) continue;
+            const int nw = tb->sb[ch][i][1];
+            for (int k = 0; k < nw; k++) pos = put_field(w, cap, pos, (unsigned)tb->params[ch][tb->sb[ch][i][0] + k][3], 5);
+        }
+    }
+    return pos;
+}
+
+ATDE_D unsigned warp_incl_scan(unsigned v, int lane)
+{
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned a = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += a;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTables* __restrict__ T,
+                                                                     const float* __restrict__ specs,
+                                                                     const ToneBlock* __restrict__ tones,
+                                                                     unsigned char* __restrict__ frames, int units, int C)
+{
+    __shared__ PackSm sm[kPackWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * kPackWarps + warp;
+    if (unit >= units) return;
+    PackSm& sh = sm[warp];
+    for (int i = lane; i < kFrameBytes / 4 + 4; i += 32) sh.words[i] = 0;
+    for (int i = lane; i < 96; i += 32) sh.twords[i] = 0;
+
+    // ---- TScaler::Scale per quant unit + the fixed-word-length quantiser (QuantMantisas, ea = false)
+    for (int ch = 0; ch < C; ch++) {
+        const float* x = specs + ((size_t)unit * C + ch) * kFrame;
+        for (int qu = 0; qu < kQuantUnits; qu++) {
+            const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
+            float mx = 0.0f;
+            for (int i = lane; i < len; i += 32) mx = fmaxf(mx, fabsf(x[start + i]));
+            for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            if (mx > 1.0f) mx = 1.0f;                                  // MAX_SCALE
+            int lo = 0, hi = 63;                                       // lower_bound over the ascending table
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (T->scale_table[mid] < mx) lo = mid + 1; else hi = mid;
+            }
+            const float sf = T->scale_table[lo];
+            const float mul = T->inv_mant[c_alloc[qu]];
+            for (int i = lane; i < len; i += 32) {
+                float v = __fdiv_rn(x[start + i], sf);
+                if (fabsf(v) >= 1.0f) v = v > 0.0f ? 0.99999f : -0.99999f;
+                sh.mant[ch][start + i] = (signed char)__float2int_rn(fmul(v, mul));
+            }
+            if (lane == 0) sh.sfi[ch][qu] = (unsigned char)lo;
+        }
+    }
+    __syncwarp();
+    // ---- TUnit::GetOrCompute (:370-397): cheapest of the 8 code tables per unit; lane = (table, quarter)
+    {
+        const int ti = lane >> 2, sub = lane & 3;
+        for (int ch = 0; ch < C; ch++)
+            for (int qu = 0; qu < kQuantUnits; qu++) {
+                const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
+                const int tab = c_alloc[qu] - 1 + 7 * ti;
+                const int nsym = len / T->spec_tab[tab][1];
+                unsigned bits = 0;
+                for (int sidx = sub; sidx < nsym; sidx += 4) {
+                    int nb;
+                    spec_symbol(T, tab, sh.mant[ch] + start, sidx, nb);
+                    bits += (unsigned)nb;
+                }
+                bits += __shfl_xor_sync(0xffffffffu, bits, 1);
+                bits += __shfl_xor_sync(0xffffffffu, bits, 2);
+                unsigned key = bits * 8u + (unsigned)ti;                 // first minimum wins (t < consumed)
+                for (int d = 4; d < 32; d <<= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d));
+                if (lane == 0) { sh.qbits[ch][qu] = (unsigned short)(key >> 3); sh.qtab[ch][qu] = (unsigned char)(key & 7u); }
+            }
+    }
+    __syncwarp();
+    // ---- TTonalComponentEncoder::Encode (:611-669), once: its buffer survives the Repeat rounds
+    const ToneBlock* tb = tones + unit;
+    int tonal_bits = 0;
+    if (lane == 0) {
+        unsigned* w = sh.twords;
+        const int cap = 96 * 32;
+        int p = 0;
+        if (C == 2) p = put_field(w, cap, p, 0, 2);                      // swap_channels, negate_coeffs
+        for (int ch = 0; ch < C; ch++) p = put_field(w, cap, p, 0, 1);   // every window is a sine window (at3p.cpp:161)
+        for (int ch = 0; ch < C; ch++) p = put_field(w, cap, p, 0, 1);   // no gain compensation
+        if (tb->present && tb->num_tone_bands) {
+            p = put_field(w, cap, p, 1, 1);
+            p = write_tonal_block(T, w, cap, p, C, tb);
+        } else {
+            p = put_field(w, cap, p, 0, 1);
+        }
+        p = put_field(w, cap, p, 0, 1);                                  // no noise info
+        p = put_field(w, cap, p, 3, 2);                                  // terminator
+        tonal_bits = p;
+    }
+    tonal_bits = __shfl_sync(0xffffffffu, tonal_bits, 0);
+    // ---- how many quant units fit: 32, else 28, 27, ... (:596-609).  Lane l evaluates n = l + 1.
+    int num_qu;
+    {
+        const int n = lane + 1;
+        // word-length part (:164-246): deltas of the static table
+        int maxd = 0;
+        for (int i = 1; i < n; i++) maxd |= abs((int)c_alloc[i] - (int)c_alloc[i - 1]);
+        const int t0 = maxd >= 3 ? 2 : (maxd == 2 ? 1 : 0), t1 = maxd >= 3 ? 3 : t0;
+        int wl_idx = 0;
+        unsigned wl_best = 0xffffffffu;
+        for (int t = t0; t <= t1; t++) {
+            unsigned sum = 0;
+            for (int i = 1; i < n; i++) sum += T->wl_vlc[t][((int)c_alloc[i] - (int)c_alloc[i - 1]) & 7] >> 16;
+            if (sum < wl_best) { wl_best = sum; wl_idx = t; }
+        }
+        unsigned total = 6;                                              // TConfigure: units - 1 (5), mute flag (1)
+        total += 2 + 2 + 2 + 2 + 3 + wl_best;
+        if (C == 2) total += 2 + 2 + 2 + (unsigned)n * (T->wl_vlc[0][0] >> 16);
+        total += (unsigned)C * (2 + 6 * (unsigned)n);                    // TSfIdxEncoder (:248-270)
+        total += 1 + (unsigned)C * (1 + 2 + 1 + 3 * (unsigned)n);        // EncodeCodeTab (:272-295)
+        const unsigned q0 = warp_incl_scan(sh.qbits[0][lane], lane);
+        const unsigned q1 = C == 2 ? warp_incl_scan(sh.qbits[1][lane], lane) : 0u;
+        total += q0 + q1;
+        total += (unsigned)C * 4u * T->sb_to_powgrps[T->qu_to_subband[n - 1]];
+        total += (unsigned)tonal_bits;
+        const bool fits = total <= (unsigned)kAllocBits;
+        const unsigned fm = __ballot_sync(0xffffffffu, fits);
+        if (fm >> 31) num_qu = 32;
+        else {
+            const unsigned low = fm & 0x0fffffffu;                       // candidates 28 .. 1
+            num_qu = low ? 32 - __clz((int)low) : 1;
+        }
+        // the chosen count's word-length table index is needed by the writer
+        wl_idx = __shfl_sync(0xffffffffu, wl_idx, num_qu - 1);
+        // ---- write: header + parts in Dump order (encode.cpp:116-119)
+        unsigned* w = sh.words;
+        int p = 0;
+        if (lane == 0) {
+            p = put_field(w, kFrameBits, p, 0, 1);
+            p = put_field(w, kFrameBits, p, (unsigned)(C - 1), 2);
+            p = put_field(w, kFrameBits, p, (unsigned)(num_qu - 1), 5);
+            p = put_field(w, kFrameBits, p, 0, 1);
+            p = put_field(w, kFrameBits, p, 3, 2);
+            p = put_field(w, kFrameBits, p, 0, 2);
+            p = put_field(w, kFrameBits, p, 0, 2);
+            p = put_field(w, kFrameBits, p, (unsigned)wl_idx, 2);
+            p = put_field(w, kFrameBits, p, c_alloc[0], 3);
+            for (int i = 1; i < num_qu; i++) {
+                const unsigned e = T->wl_vlc[wl_idx][((int)c_alloc[i] - (int)c_alloc[i - 1]) & 7];
+                p = put_field(w, kFrameBits, p, e & 0xffffu, (int)(e >> 16));
+            }
+            if (C == 2) {
+                p = put_field(w, kFrameBits, p, 1, 2);
+                p = put_field(w, kFrameBits, p, 0, 2);
+                p = put_field(w, kFrameBits, p, 0, 2);
+                const unsigned e = T->wl_vlc[0][0];
+                for (int i = 0; i < num_qu; i++) p = put_field(w, kFrameBits, p, e & 0xffffu, (int)(e >> 16));
+            }
+        }
+        p = __shfl_sync(0xffffffffu, p, 0);
+        for (int ch = 0; ch < C; ch++) {                                 // scale factor indices
+            if (lane < num_qu) put_bits(w, kFrameBits, p + 2 + 6 * lane, 6, sh.sfi[ch][lane]);
+            p += 2 + 6 * num_qu;
+        }
+        p += 1;                                                          // use full table = 1
+        if (lane == 0) put_bits(w, kFrameBits, p - 1, 1, 1u);
+        for (int ch = 0; ch < C; ch++) {
+            if (lane < num_qu) put_bits(w, kFrameBits, p + 4 + 3 * lane, 3, sh.qtab[ch][lane]);
+            p += 4 + 3 * num_qu;
+        }
+        for (int ch = 0; ch < C; ch++) {
+            for (int qu = 0; qu < num_qu; qu++) {
+                const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
+                const int tab = c_alloc[qu] - 1 + 7 * sh.qtab[ch][qu];
+                const int nsym = len / T->spec_tab[tab][1];
+                for (int s0 = 0; s0 < nsym; s0 += 32) {
+                    const int sidx = s0 + lane;
+                    int nb = 0;
+                    unsigned code = 0;
+                    if (sidx < nsym) code = spec_symbol(T, tab, sh.mant[ch] + start, sidx, nb);
+                    const unsigned inc = warp_incl_scan((unsigned)nb, lane);
+                    put_bits(w, kFrameBits, p + (int)(inc - (unsigned)nb), nb, code);
+                    p += (int)__shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
+            const int npow = T->sb_to_powgrps[T->qu_to_subband[num_qu - 1]];
+            if (lane < npow) put_bits(w, kFrameBits, p + 4 * lane, 4, 15u);
+            p += 4 * npow;
+        }
+        // the tonal part's buffer, appended bit-exactly
+        for (int i = lane; i * 32 < tonal_bits; i += 32) {
+            const int nb = min(32, tonal_bits - 32 * i);
+            put_bits(w, kFrameBits, p + 32 * i, nb, sh.twords[i] >> (32 - nb));
+        }
+    }
+    __syncwarp();
+    unsigned char* out = frames + (size_t)unit * kFrameBytes;
+    for (int i = lane; i < kFrameBytes / 4; i += 32) {
+        const unsigned v = sh.words[i];
+        reinterpret_cast<unsigned*>(out)[i] = __byte_perm(v, 0, 0x0123);   // big-endian words -> byte stream
+    }
+}
+
+void launch_pack(const DevTables* T, const float* specs, const ToneBlock* tones, unsigned char* frames,
+                 int units, int C, cudaStream_t st)
+{
+    ATDE_LAUNCH(at3p_pack_kernel, (unsigned)((units + kPackWarps - 1) / kPackWarps), kPackWarps * 32, 0, st,
+                T, specs, tones, frames, units, C);
+}
+
 } // namespace at3p
 } // namespace atde
 
@@ -355,4 +732,23 @@ extern "C" int atde_at3p_stage_mdct(const float* resid, int S, int C, int F, flo
     launch_mdct(T, d_in.p, d_out.p, S, C, F, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     return cudaMemcpy(specs, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int atde_at3p_tone_block_size(void) { return (int)sizeof(atde::at3p::ToneBlock); }
+
+extern "C" int atde_at3p_stage_pack(const float* specs, const void* tones, int units, int C, unsigned char* frames)
+{
+    using namespace atde::at3p;
+    const DevTables* T = device_tables();
+    if (!T) return -2;
+    const size_t n = (size_t)units * C * kFrame;
+    ScopedDev<float> d_in;
+    ScopedDev<ToneBlock> d_t;
+    ScopedDev<unsigned char> d_out;
+    if (!d_in.alloc(n) || !d_t.alloc((size_t)units) || !d_out.alloc((size_t)units * kFrameBytes)) return -3;
+    if (cudaMemcpy(d_in.p, specs, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    if (cudaMemcpy(d_t.p, tones, (size_t)units * sizeof(ToneBlock), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    launch_pack(T, d_in.p, d_t.p, d_out.p, units, C, nullptr);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+    return cudaMemcpy(frames, d_out.p, (size_t)units * kFrameBytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }

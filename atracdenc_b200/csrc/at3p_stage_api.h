@@ -12,6 +12,11 @@ int atde_at3p_stage_pqf(const float* pcm, int S, int C, int F, float* bands);
 /* TAt3pMDCT::Do, sine windows (src/atrac/at3p/at3p_mdct.cpp:52-96), fresh history:
  * resid [S][C][F][16][128] -> specs [S][F][C][2048]. */
 int atde_at3p_stage_mdct(const float* resid, int S, int C, int F, float* specs);
+/* TScaler::ScaleFrame + TAt3PBitStream::WriteFrame (src/atrac/at3p/at3p_bitstream.cpp:703-726):
+ * specs [U][C][2048], tones [U] flattened TAt3PGhaData (atde_at3p_tone_block_size() bytes each, layout of
+ * at3p_kernels.cuh:ToneBlock) -> frames [U][2048]. */
+int atde_at3p_stage_pack(const float* specs, const void* tones, int units, int C, unsigned char* frames);
+int atde_at3p_tone_block_size(void);
 #ifdef __cplusplus
 }
 #endif

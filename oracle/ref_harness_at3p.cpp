@@ -159,6 +159,49 @@ long ref_at3p_stages(int channels, const float* pcm, long n_frames, int gha_flag
     return produced;
 }
 
+/* TScaler<NAt3p::TScaleTable>::ScaleFrame + TAt3PBitStream::WriteFrame on caller-supplied spectra and
+ * tone data (the tail of EncodeFrame, at3p.cpp:163-168): specs [U][C][2048], tones [U] -> frames [U][2048]. */
+long ref_at3p_pack(int channels, const float* specs, const at3p_gha_rec* tones, long units, unsigned char* frames)
+{
+    std::vector<uint8_t> bytes;
+    TNullOut3p out(channels, &bytes);
+    TAt3PBitStream bs(&out, 2048);
+    TScaler<NAt3p::TScaleTable> scaler;
+    for (long u = 0; u < units; u++) {
+        std::vector<TAt3PBitStream::TSingleChannelElement> sces(channels);
+        for (int c = 0; c < channels; c++) {
+            std::vector<float> sp(specs + ((size_t)u * channels + c) * 2048, specs + ((size_t)u * channels + c + 1) * 2048);
+            sces[c].ScaledBlocks = scaler.ScaleFrame(sp, NAt3p::TScaleTable::TBlockSizeMod());
+        }
+        TAt3PGhaData d;
+        const at3p_gha_rec& r = tones[u];
+        const TAt3PGhaData* p = nullptr;
+        if (r.present && r.num_tone_bands) {
+            d.NumToneBands = (uint8_t)r.num_tone_bands;
+            d.SecondIsLeader = r.second_is_leader != 0;
+            for (int i = 0; i < 16; i++) d.ToneSharing[i] = r.tone_sharing[i] != 0;
+            for (int ch = 0; ch < channels; ch++) {
+                d.Waves[ch].WaveSbInfos.resize(r.n_sb[ch]);
+                for (int i = 0; i < r.n_sb[ch]; i++) {
+                    d.Waves[ch].WaveSbInfos[i].WaveIndex = (size_t)r.sb[ch][i][0];
+                    d.Waves[ch].WaveSbInfos[i].WaveNums = (size_t)r.sb[ch][i][1];
+                    d.Waves[ch].WaveSbInfos[i].Envelope = {(uint32_t)r.sb[ch][i][2], (uint32_t)r.sb[ch][i][3]};
+                }
+                d.Waves[ch].WaveParams.resize(r.n_params[ch]);
+                for (int i = 0; i < r.n_params[ch]; i++)
+                    d.Waves[ch].WaveParams[i] = TAt3PGhaData::TWaveParam{(uint32_t)r.params[ch][i][0], (uint32_t)r.params[ch][i][1],
+                                                                         (uint32_t)r.params[ch][i][2], (uint32_t)r.params[ch][i][3]};
+            }
+            p = &d;
+        }
+        const size_t before = bytes.size();
+        bs.WriteFrame(channels, p, sces);
+        if (bytes.size() - before != 2048) return -1;
+        memcpy(frames + (size_t)u * 2048, bytes.data() + before, 2048);
+    }
+    return units;
+}
+
 /* at3plus_pqf_do_analyse (src/atrac/atrac3plus_pqf/atrac3plus_pqf.c:130-147) over n_frames frames of
  * one channel, fresh context: out[f][2048] (16 subbands x 128). */
 void ref_at3p_pqf(const float* pcm, long n_frames, float* out)

@@ -302,3 +302,16 @@ def ref_at3p_stages(channels, pcm, gha_flags=-1):
                             frames.ctypes.data_as(P))
     return dict(n=k, pqf_cur=cur[:k], pqf_next=nxt[:k], work_in=win[:k], work_out=wout[:k], gha=gha[:k],
                 specs=specs[:k], frames=frames[:k])
+
+
+def ref_at3p_pack(channels, specs, tones):
+    """ScaleFrame + TAt3PBitStream::WriteFrame on caller-supplied spectra [U][C][2048] and tone records."""
+    lib = ref_lib()
+    specs = np.ascontiguousarray(specs, dtype=np.float32)
+    tones = np.ascontiguousarray(tones)
+    U = specs.shape[0]
+    out = np.zeros((U, 2048), np.uint8)
+    lib.ref_at3p_pack.restype = ctypes.c_long
+    k = lib.ref_at3p_pack(channels, specs.ctypes.data_as(P), tones.ctypes.data_as(P), ctypes.c_long(U), out.ctypes.data_as(P))
+    assert k == U
+    return out

@@ -416,3 +416,59 @@ def check_at3p_mdct(lib, S=2, F=6, C=2, seed=910):
     bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
     assert bad.size == 0, f"first differing (stream, frame, ch, line) = {bad[:4].tolist()}"
     return S
+
+
+def at3p_stage_pack(lib, specs, tones, C):
+    specs = np.ascontiguousarray(specs, dtype=np.float32)
+    tones = np.ascontiguousarray(tones)
+    assert lib.atde_at3p_tone_block_size() == tl.AT3P_GHA_REC.itemsize
+    U = specs.shape[0]
+    out = np.zeros((U, 2048), np.uint8)
+    rc = lib.atde_at3p_stage_pack(specs.ctypes.data_as(tl.P), tones.ctypes.data_as(tl.P), U, C, out.ctypes.data_as(tl.P))
+    assert rc == 0, f"atde_at3p_stage_pack -> {rc}"
+    return out
+
+
+def check_at3p_pack(lib, S=2, F=6, C=2, seed=920, loud=False):
+    """Frame packer (scale, quantise, code-table choice, tonal block, bit writer) bit-exact against
+    TAt3PBitStream::WriteFrame, fed with the spectra and the tone data of the reference encoder: the
+    frame written in call t carries the GHA result of call t-1 (`delay`, at3p.cpp:127-131,186-190)."""
+    if tl.ref_lib() is None:
+        return 0
+    pcm = _at3p_signal(S, F + 1, C, seed)
+    if loud:
+        pcm = tl.quantise(np.clip(pcm.astype(np.float64) * 12.0, -1.0, 1.0))       # forces the unit-dropping loop
+    for s in range(S):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        assert st["n"] == F
+        tones = np.zeros(F, tl.AT3P_GHA_REC)
+        tones[1:] = st["gha"][:-1]
+        got = at3p_stage_pack(lib, st["specs"], tones, C)
+        bad = np.argwhere((got != st["frames"]).any(-1))
+        assert bad.size == 0, f"stream {s}: first differing frames {bad[:4].ravel().tolist()}, " \
+                              f"first byte {np.argwhere(got[bad[0, 0]] != st['frames'][bad[0, 0]])[:3].ravel().tolist()}"
+    return S
+
+
+def check_at3p_pack_random(lib, U=12, C=2, seed=940):
+    """Packer on random spectra of growing level: walks TTonalComponentEncoder's unit-dropping loop well
+    below 28 units, which no natural signal reaches; tone data borrowed from a real encode."""
+    if tl.ref_lib() is None:
+        return 0
+    rng = np.random.default_rng(seed)
+    st = tl.ref_at3p_stages(C, _at3p_signal(1, 5, C, seed)[0].reshape(-1))
+    tones = np.zeros(U, tl.AT3P_GHA_REC)
+    specs = np.zeros((U, C, 2048), np.float32)
+    for u in range(U):
+        level = 10.0 ** rng.uniform(-4, 0)
+        specs[u] = rng.uniform(-level, level, (C, 2048)) * (rng.uniform(0, 1, (C, 2048)) < rng.uniform(0.05, 1.0))
+        if u % 3:
+            tones[u] = st["gha"][u % st["n"]]
+    specs[U - 1] = 0.0
+    specs[0, 0, 5] = 1.0                                              # == MAX_SCALE: last table entry, value clipped to 0.99999
+    want = tl.ref_at3p_pack(C, specs, tones)
+    got = at3p_stage_pack(lib, specs, tones, C)
+    nq = sorted({int(f[0] & 0x1f) + 1 for f in want})
+    bad = np.argwhere((got != want).any(-1))
+    assert bad.size == 0, f"differing frames {bad[:4].ravel().tolist()} (unit counts seen: {nq})"
+    return nq

@@ -11,3 +11,15 @@ def test_pqf(emu_lib):
 def test_mdct(emu_lib):
     pc.check_at3p_mdct(emu_lib, S=2, F=4, C=2)
     pc.check_at3p_mdct(emu_lib, S=1, F=3, C=1, seed=915)
+
+
+def test_pack(emu_lib):
+    pc.check_at3p_pack(emu_lib, S=3, F=5, C=2)
+    pc.check_at3p_pack(emu_lib, S=1, F=4, C=1, seed=925)
+    pc.check_at3p_pack(emu_lib, S=1, F=4, C=2, seed=930, loud=True)
+
+
+def test_pack_random_spectra(emu_lib):
+    nq = pc.check_at3p_pack_random(emu_lib, U=10, C=2)
+    assert nq == 0 or min(nq) < 28
+    pc.check_at3p_pack_random(emu_lib, U=6, C=1, seed=950)

@@ -15,3 +15,15 @@ def test_pqf(gpu_lib):
 def test_mdct(gpu_lib):
     pc.check_at3p_mdct(gpu_lib, S=6, F=20, C=2)
     pc.check_at3p_mdct(gpu_lib, S=2, F=9, C=1, seed=915)
+
+
+def test_pack(gpu_lib):
+    pc.check_at3p_pack(gpu_lib, S=6, F=20, C=2)
+    pc.check_at3p_pack(gpu_lib, S=2, F=9, C=1, seed=925)
+    pc.check_at3p_pack(gpu_lib, S=2, F=9, C=2, seed=930, loud=True)
+
+
+def test_pack_random_spectra(gpu_lib):
+    nq = pc.check_at3p_pack_random(gpu_lib, U=40, C=2)
+    assert nq == 0 or min(nq) < 28
+    pc.check_at3p_pack_random(gpu_lib, U=20, C=1, seed=950)

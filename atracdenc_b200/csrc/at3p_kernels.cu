@@ -49,6 +49,12 @@ static void build_tables()
     memcpy(h->tone_bands_vlc, kAt3pToneBandsVlc, sizeof(h->tone_bands_vlc));
     memcpy(h->qu_to_subband, kAt3pQuToSubband, sizeof(h->qu_to_subband));
     memcpy(h->sb_to_powgrps, kAt3pSbToPowGrps, sizeof(h->sb_to_powgrps));
+    {   // ff_atrac3p_init_dsp_static (ff/atrac3plusdsp.c:49-66), same expressions and types
+        const double twopi = 2 * M_PI;
+        for (int i = 0; i < 2048; i++) h->sine_table[i] = sin(twopi * i / 2048);
+        for (int i = 0; i < 256; i++) h->hann_window[i] = (1.0f - cos(twopi * i / 256.0f)) * 0.5f;
+        for (int i = 0; i < 64; i++) h->amp_sf_tab[i] = exp2f((i - 3) / 4.0f);
+    }
 
     float fir[kPqfProto];
     for (int i = 0; i < kPqfProto; i++) fir[i] = bits_to_float(kAt3pFirBits[i]);
@@ -178,6 +184,124 @@ void launch_pqf(const float* pcm, float* bands, int S, int C, int F, cudaStream_
 {
     dim3 grid(F, S);
     ATDE_LAUNCH(at3p_pqf_kernel, grid, 256, 0, st, pcm, bands, S, C, F);
+}
+
+// =====================================================================================
+// P3: tone filter — TGhaProcessorBase::ApplyFilter (at3p_gha.cpp:581-687) + ff_atrac3p_generate_tones
+//     (ff/atrac3plusdsp.c:130-204) + the MDCT input scaling of EncodeFrame (at3p.cpp:147-153)
+// =====================================================================================
+// The reference keeps two frames of tone parameters in Atrac3pChanUnitCtx; what it subtracts from the
+// frame being encoded is a function of three consecutive GHA results only:
+//   tb_next  the result of this call (tones_info),  tb_now  of the previous call (tones_info_prev),
+//   tb_old   of the call before (its pending envelope enters tones_now->curr_env, computed one call earlier).
+struct WaveGroup {                    // Atrac3pWavesData after ApplyFilter's sharing / leader swaps
+    int num_wavs, src_ch, first;      // waves = tb->params[src_ch][first ..]
+    int has_start, start_pos, has_stop, stop_pos;    // pend_env
+};
+
+ATDE_D WaveGroup resolve_group(const ToneBlock* tb, int C, int ch, int sb)
+{
+    WaveGroup g = {0, 0, 0, 0, 0, 0, 0};
+    if (!tb->present || sb >= tb->num_tone_bands) return g;           // memset-zero state
+    int c = ch;
+    if (C == 2 && tb->second_is_leader) c = 1 - c;                    // std::swap(channels[0], channels[1])
+    if (c == 1 && tb->tone_sharing[sb]) c = 0;                        // channels[1] = channels[0]
+    g.num_wavs = tb->sb[c][sb][1];
+    g.src_ch = c;
+    g.first = tb->sb[c][sb][0];
+    const unsigned e0 = (unsigned)tb->sb[c][sb][2], e1 = (unsigned)tb->sb[c][sb][3];
+    g.has_start = e0 != 0xffffffffu; g.start_pos = g.has_start ? (int)e0 : -1;
+    g.has_stop = e1 != 0xffffffffu;  g.stop_pos = g.has_stop ? (int)e1 : 32;
+    return g;
+}
+
+struct Envelope { int has_start, start_pos, has_stop, stop_pos; };
+
+// curr_env of `next` given the pending envelopes of `now` and `next` (atrac3plusdsp.c:141-166)
+ATDE_D Envelope current_envelope(const WaveGroup& now, const WaveGroup& next)
+{
+    Envelope e;
+    if (next.has_start && next.start_pos < next.stop_pos) { e.has_start = 1; e.start_pos = next.start_pos + 32; }
+    else if (now.has_start) { e.has_start = 1; e.start_pos = now.start_pos; }
+    else { e.has_start = 0; e.start_pos = 0; }
+    if (now.has_stop && now.stop_pos >= e.start_pos) { e.has_stop = 1; e.stop_pos = now.stop_pos; }
+    else if (next.has_stop) { e.has_stop = 1; e.stop_pos = next.stop_pos + 32; }
+    else { e.has_stop = 0; e.stop_pos = 64; }
+    return e;
+}
+
+// sample i of waves_synth (atrac3plusdsp.c:79-128), amplitude_mode = 1, no phase inversion
+ATDE_D float synth_sample(const DevTables* T, const ToneBlock* tb, const WaveGroup& g, const Envelope& env, int reg_offset, int i)
+{
+    float v = 0.0f;
+    for (int wn = 0; wn < g.num_wavs; wn++) {
+        const int* prm = tb->params[g.src_ch][g.first + wn];
+        const double amp = (double)fmul(T->amp_sf_tab[prm[1]], 1.0f);
+        const int inc = prm[0];
+        const int pos = ((((prm[3] & 0x1f) << 6) - (reg_offset ^ 128) * inc) + i * inc) & 2047;
+        v = __double2float_rn(__dadd_rn((double)v, __dmul_rn((double)T->sine_table[pos], amp)));
+    }
+    if (env.has_start) {
+        const int pos = (env.start_pos << 2) - reg_offset;
+        if (pos > 0 && pos <= 128) {
+            if (i < pos) v = 0.0f;
+            if ((!env.has_stop || env.start_pos != env.stop_pos) && i >= pos && i < pos + 4)
+                v = fmul(v, T->hann_window[32 * (i - pos)]);
+        }
+    }
+    if (env.has_stop) {
+        const int pos = ((env.stop_pos + 1) << 2) - reg_offset;
+        if (pos > 0 && pos <= 128) {
+            if (i >= pos - 4 && i < pos) v = fmul(v, T->hann_window[96 - 32 * (i - (pos - 4))]);
+            if (i >= pos) v = 0.0f;
+        }
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(128) at3p_tone_filter_kernel(const DevTables* __restrict__ T, const float* __restrict__ bands,
+                                                                const ToneBlock* __restrict__ tb_old,
+                                                                const ToneBlock* __restrict__ tb_now,
+                                                                const ToneBlock* __restrict__ tb_next,
+                                                                float* __restrict__ resid, int units, int C)
+{
+    const int u = blockIdx.x / C, ch = blockIdx.x % C, i = threadIdx.x;
+    const ToneBlock* old = tb_old + u;
+    const ToneBlock* now = tb_now + u;
+    const ToneBlock* next = tb_next + u;
+    const float* in = bands + ((size_t)u * C + ch) * kFrame;
+    float* out = resid + ((size_t)u * C + ch) * kFrame;
+    const bool any = now->present || next->present;                    // tones_present || prev tones_present
+    for (int sb = 0; sb < kSubbands; sb++) {
+        float x = in[sb * kSbSamples + i];
+        if (sb < 8 && any) {
+            const WaveGroup gn = resolve_group(now, C, ch, sb), gx = resolve_group(next, C, ch, sb);
+            if (gn.num_wavs || gx.num_wavs) {
+                const Envelope env_next = current_envelope(gn, gx);
+                const Envelope env_now = current_envelope(resolve_group(old, C, ch, sb), gn);   // what the previous call left
+                const bool reg1 = env_now.stop_pos >= 32, reg2 = env_next.start_pos < 32;
+                float w1 = 0.0f, w2 = 0.0f;
+                if (gn.num_wavs && reg1) w1 = synth_sample(T, now, gn, env_now, 128, i);
+                if (gx.num_wavs && reg2) w2 = synth_sample(T, next, gx, env_next, 0, i);
+                if (gn.num_wavs && gx.num_wavs && reg1 && reg2) {
+                    w1 = fmul(w1, T->hann_window[128 + i]);
+                    w2 = fmul(w2, T->hann_window[i]);
+                } else {
+                    if (gn.num_wavs && !env_now.has_stop) w1 = fmul(w1, T->hann_window[128 + i]);
+                    if (gx.num_wavs && !env_next.has_start) w2 = fmul(w2, T->hann_window[i]);
+                }
+                x = fsub(x, fadd(w1, w2));
+            }
+        }
+        // tmp[i] = x[i] / (32768.0 / 1.122018)  (at3p.cpp:150-153): double division, rounded to float on the store
+        out[sb * kSbSamples + i] = __double2float_rn(__ddiv_rn((double)x, 32768.0 / 1.122018));
+    }
+}
+
+void launch_tone_filter(const DevTables* T, const float* bands, const ToneBlock* tb_old, const ToneBlock* tb_now,
+                        const ToneBlock* tb_next, float* resid, int units, int C, cudaStream_t st)
+{
+    ATDE_LAUNCH(at3p_tone_filter_kernel, (unsigned)(units * C), 128, 0, st, T, bands, tb_old, tb_now, tb_next, resid, units, C);
 }
 
 // =====================================================================================
@@ -751,4 +875,25 @@ extern "C" int atde_at3p_stage_pack(const float* specs, const void* tones, int u
     launch_pack(T, d_in.p, d_t.p, d_out.p, units, C, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     return cudaMemcpy(frames, d_out.p, (size_t)units * kFrameBytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int atde_at3p_stage_tone_filter(const float* bands, const void* tb_old, const void* tb_now, const void* tb_next,
+                                           int units, int C, float* resid)
+{
+    using namespace atde::at3p;
+    const DevTables* T = device_tables();
+    if (!T) return -2;
+    const size_t n = (size_t)units * C * kFrame;
+    ScopedDev<float> d_in, d_out;
+    ScopedDev<ToneBlock> d_t[3];
+    const void* src[3] = {tb_old, tb_now, tb_next};
+    if (!d_in.alloc(n) || !d_out.alloc(n)) return -3;
+    for (int k = 0; k < 3; k++) {
+        if (!d_t[k].alloc((size_t)units)) return -3;
+        if (cudaMemcpy(d_t[k].p, src[k], (size_t)units * sizeof(ToneBlock), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    }
+    if (cudaMemcpy(d_in.p, bands, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    launch_tone_filter(T, d_in.p, d_t[0].p, d_t[1].p, d_t[2].p, d_out.p, units, C, nullptr);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+    return cudaMemcpy(resid, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }

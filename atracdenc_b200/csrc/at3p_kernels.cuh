@@ -39,6 +39,10 @@ struct DevTables {
     unsigned tone_bands_vlc[16];      // THuffTables::NumToneBands
     unsigned char qu_to_subband[32];
     unsigned char sb_to_powgrps[16];
+    // tone synthesis (ff/atrac3plusdsp.c:49-66)
+    alignas(16) float sine_table[2048];
+    float hann_window[256];
+    float amp_sf_tab[64];
 };
 
 // Flattened TAt3PGhaData (src/atrac/at3p/at3p_gha.h:29-66): what the tonal-block writer consumes.
@@ -57,6 +61,11 @@ const DevTables* device_tables();     // builds + uploads on first use; nullptr 
 
 // pcm [S][F*2048][C] interleaved -> bands [S][C][F][16][128]; every stream starts with a zero history
 void launch_pqf(const float* pcm, float* bands, int S, int C, int F, cudaStream_t st);
+// Tone filter + MDCT input scaling (TGhaProcessorBase::ApplyFilter, at3p_gha.cpp:581-687;
+// ff_atrac3p_generate_tones, ff/atrac3plusdsp.c:130-204; at3p.cpp:147-153): for unit u, frame bands
+// [U][C][16][128] minus the tones of tb_now[u] / tb_next[u] (envelopes also need tb_old[u]) -> resid, same layout
+void launch_tone_filter(const DevTables* T, const float* bands, const ToneBlock* tb_old, const ToneBlock* tb_now,
+                        const ToneBlock* tb_next, float* resid, int units, int C, cudaStream_t st);
 // resid [S][C][F][16][128] (already scaled to the MDCT's input range) -> specs [S][F][C][2048];
 // every stream starts with a zero overlap history
 void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, int C, int F, cudaStream_t st);

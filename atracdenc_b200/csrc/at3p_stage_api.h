@@ -17,6 +17,11 @@ int atde_at3p_stage_mdct(const float* resid, int S, int C, int F, float* specs);
  * at3p_kernels.cuh:ToneBlock) -> frames [U][2048]. */
 int atde_at3p_stage_pack(const float* specs, const void* tones, int units, int C, unsigned char* frames);
 int atde_at3p_tone_block_size(void);
+/* TGhaProcessorBase::ApplyFilter + ff_atrac3p_generate_tones + the MDCT input scaling (at3p_gha.cpp:581-687,
+ * ff/atrac3plusdsp.c:130-204, at3p.cpp:147-153): bands [U][C][2048] minus the tones of three consecutive GHA
+ * results per unit (two calls ago, previous call, this call) -> resid [U][C][2048]. */
+int atde_at3p_stage_tone_filter(const float* bands, const void* tb_old, const void* tb_now, const void* tb_next,
+                                int units, int C, float* resid);
 #ifdef __cplusplus
 }
 #endif

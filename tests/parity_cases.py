@@ -472,3 +472,59 @@ def check_at3p_pack_random(lib, U=12, C=2, seed=940):
     bad = np.argwhere((got != want).any(-1))
     assert bad.size == 0, f"differing frames {bad[:4].ravel().tolist()} (unit counts seen: {nq})"
     return nq
+
+
+def at3p_stage_tone_filter(lib, bands, old, now, nxt, C):
+    bands = np.ascontiguousarray(bands, dtype=np.float32)
+    U = bands.shape[0]
+    out = np.zeros((U, C, 2048), np.float32)
+    a = [np.ascontiguousarray(t) for t in (old, now, nxt)]
+    rc = lib.atde_at3p_stage_tone_filter(bands.ctypes.data_as(tl.P), a[0].ctypes.data_as(tl.P), a[1].ctypes.data_as(tl.P),
+                                         a[2].ctypes.data_as(tl.P), U, C, out.ctypes.data_as(tl.P))
+    assert rc == 0, f"atde_at3p_stage_tone_filter -> {rc}"
+    return out
+
+
+def _shift(recs, k):
+    out = np.zeros_like(recs)
+    if k < len(recs):
+        out[k:] = recs[:len(recs) - k]
+    return out
+
+
+def check_at3p_tone_filter(lib, S=2, F=8, C=2, seed=960):
+    """Tone subtraction + MDCT input scaling bit-exact against the work buffer TGhaProcessorBase::ApplyFilter
+    leaves behind, fed with the reference's own GHA results of three consecutive calls."""
+    if tl.ref_lib() is None:
+        return 0
+    pcm = _at3p_signal(S, F + 1, C, seed)
+    for s in range(S):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        want = (st["work_out"].astype(np.float64) / (32768.0 / 1.122018)).astype(np.float32)
+        got = at3p_stage_tone_filter(lib, st["work_in"], _shift(st["gha"], 2), _shift(st["gha"], 1), st["gha"], C)
+        bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+        assert bad.size == 0, f"stream {s}: first differing (frame, ch, sample) = {bad[:4].tolist()}"
+        assert np.abs(st["work_out"] - st["work_in"]).max() > 1.0          # tones were actually subtracted
+    return S
+
+
+def check_at3p_chain_after_gha(lib, S=2, F=8, C=2, seed=970):
+    """PCM -> PQF -> [reference GHA results] -> tone filter -> MDCT -> packer == the reference's frames:
+    everything of the ATRAC3plus path except the tone search itself, chained on the device kernels."""
+    if tl.ref_lib() is None:
+        return 0
+    pcm = _at3p_signal(S, F + 1, C, seed)
+    bands = at3p_stage_pqf(lib, pcm, S, C, F + 1)                        # [S][C][F+1][2048]
+    for s in range(S):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        assert st["n"] == F
+        # output o encodes PQF frame o-1 (zeros for o = 0): at3p.cpp:113-121,181-185
+        work = np.zeros((F, C, 2048), np.float32)
+        work[1:] = bands[s].transpose(1, 0, 2)[:F - 1]
+        assert np.array_equal(work, st["work_in"])
+        resid = at3p_stage_tone_filter(lib, work, _shift(st["gha"], 2), _shift(st["gha"], 1), st["gha"], C)
+        specs = at3p_stage_mdct(lib, resid.transpose(1, 0, 2)[None], 1, C, F)[0]      # [F][C][2048]
+        frames = at3p_stage_pack(lib, specs, _shift(st["gha"], 1), C)
+        bad = np.argwhere((frames != st["frames"]).any(-1))
+        assert bad.size == 0, f"stream {s}: differing frames {bad[:4].ravel().tolist()}"
+    return S

@@ -23,3 +23,12 @@ def test_pack_random_spectra(emu_lib):
     nq = pc.check_at3p_pack_random(emu_lib, U=10, C=2)
     assert nq == 0 or min(nq) < 28
     pc.check_at3p_pack_random(emu_lib, U=6, C=1, seed=950)
+
+
+def test_tone_filter(emu_lib):
+    pc.check_at3p_tone_filter(emu_lib, S=3, F=6, C=2)
+    pc.check_at3p_tone_filter(emu_lib, S=1, F=5, C=1, seed=965)
+
+
+def test_chain_after_gha(emu_lib):
+    pc.check_at3p_chain_after_gha(emu_lib, S=2, F=5, C=2)

@@ -27,3 +27,13 @@ def test_pack_random_spectra(gpu_lib):
     nq = pc.check_at3p_pack_random(gpu_lib, U=40, C=2)
     assert nq == 0 or min(nq) < 28
     pc.check_at3p_pack_random(gpu_lib, U=20, C=1, seed=950)
+
+
+def test_tone_filter(gpu_lib):
+    pc.check_at3p_tone_filter(gpu_lib, S=8, F=24, C=2)
+    pc.check_at3p_tone_filter(gpu_lib, S=3, F=12, C=1, seed=965)
+
+
+def test_chain_after_gha(gpu_lib):
+    pc.check_at3p_chain_after_gha(gpu_lib, S=6, F=20, C=2)
+    pc.check_at3p_chain_after_gha(gpu_lib, S=2, F=10, C=1, seed=975)

@@ -6,6 +6,7 @@
 // kissfft restated stage by stage, tables computed on the host with the reference's expressions.
 #include "at3p_kernels.cuh"
 #include "kissfft_dev.cuh"
+#include "glibc_trig.cuh"
 #include "host_tables.h"
 #include "at3p_tables_gen.h"
 
@@ -896,4 +897,33 @@ extern "C" int atde_at3p_stage_tone_filter(const float* bands, const void* tb_ol
     launch_tone_filter(T, d_in.p, d_t[0].p, d_t[1].p, d_t[2].p, d_out.p, units, C, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     return cudaMemcpy(resid, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+
+// ---- device libm replicas under test (tests/test_gpu_math.py) ----
+namespace {
+__global__ void trig_kernel(int fn, const double* x, double* y, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    if (fn == 0) y[i] = atde::g_sin(v);
+    else if (fn == 1) y[i] = atde::g_cos(v);
+    else if (fn == 2) y[i] = atde::g_atan(v);
+    else {
+        float s, c;
+        atde::g_sincosf((float)v, s, c);
+        y[i] = fn == 3 ? (double)s : (double)c;
+    }
+}
+} // namespace
+
+/* fn: 0 sin, 1 cos, 2 atan (double in, double out); 3 sinf, 4 cosf of sincosf((float)x) widened to double */
+extern "C" int atde_at3p_debug_trig(int fn, const double* x, double* y, long long n)
+{
+    ScopedDev<double> dx, dy;
+    if (n <= 0 || !dx.alloc((size_t)n) || !dy.alloc((size_t)n)) return -3;
+    if (cudaMemcpy(dx.p, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    ATDE_LAUNCH(trig_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t) nullptr, fn, (const double*)dx.p, dy.p, n);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+    return cudaMemcpy(y, dy.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }

@@ -175,6 +175,7 @@ inline int __double2int_rz(double x) { return (int)x; }
 inline float __int2float_rn(int x) { return (float)x; }
 inline float __uint2float_rn(unsigned x) { return (float)x; }
 inline double __int2double_rn(int x) { return (double)x; }
+inline double __ll2double_rn(long long x) { return (double)x; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }

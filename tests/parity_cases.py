@@ -528,3 +528,45 @@ def check_at3p_chain_after_gha(lib, S=2, F=8, C=2, seed=970):
         bad = np.argwhere((frames != st["frames"]).any(-1))
         assert bad.size == 0, f"stream {s}: differing frames {bad[:4].ravel().tolist()}"
     return S
+
+
+def check_trig_replicas(lib, n=2000000, seed=77):
+    """Device replicas of glibc sin / cos / atan / sincosf against the live libm of the box, on the argument
+    ranges the tone search visits (phases up to ~2^9, ratios of any magnitude) and beyond."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    rng = np.random.default_rng(seed)
+    xs = np.concatenate([
+        rng.uniform(-4, 4, n // 4), rng.uniform(0, 420, n // 4).astype(np.float32).astype(np.float64),
+        np.ldexp(rng.uniform(0.5, 1, n // 4), rng.integers(-40, 26, n // 4)) * rng.choice([-1, 1], n // 4),
+        rng.uniform(-1e8, 1e8, n // 4), np.array([0.0, -0.0, 0.126, 0.855469, 2.426265, 1e-300, np.pi, np.pi / 2]),
+    ])
+    xs = np.ascontiguousarray(xs[np.abs(xs) < 105414000.0])
+    def dev(fn, x):
+        y = np.empty_like(x)
+        rc = lib.atde_at3p_debug_trig(fn, x.ctypes.data_as(tl.P), y.ctypes.data_as(tl.P), ctypes.c_longlong(x.size))
+        assert rc == 0
+        return y
+    for fn, name in ((0, "sin"), (1, "cos"), (2, "atan")):
+        f = getattr(libm, name)
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_double]
+        x = xs if name != "atan" else np.concatenate([xs, np.ldexp(rng.uniform(0.5, 1, n // 4), rng.integers(-60, 70, n // 4))])
+        x = np.ascontiguousarray(x[:: max(1, x.size // 60000)])            # the ctypes loop is the slow part
+        want = np.array([f(float(v)) for v in x])
+        got = dev(fn, x)
+        bad = np.argwhere(want.view(np.uint64) != got.view(np.uint64))
+        assert bad.size == 0, (name, x[bad[:3].ravel()], want[bad[:3].ravel()], got[bad[:3].ravel()])
+    # sincosf: numpy has no glibc sinf; go through libm.sincosf
+    sc = libm.sincosf
+    sc.restype = None
+    sc.argtypes = [ctypes.c_float, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    xf = np.concatenate([rng.uniform(-420, 420, 20000), np.ldexp(rng.uniform(0.5, 1, 20000), rng.integers(-30, 60, 20000))]).astype(np.float32)
+    s, c = ctypes.c_float(), ctypes.c_float()
+    ws, wc = np.empty(xf.size, np.float32), np.empty(xf.size, np.float32)
+    for i, v in enumerate(xf):
+        sc(float(v), ctypes.byref(s), ctypes.byref(c))
+        ws[i], wc[i] = s.value, c.value
+    xd = np.ascontiguousarray(xf.astype(np.float64))
+    assert np.array_equal(dev(3, xd).astype(np.float32).view(np.uint32), ws.view(np.uint32))
+    assert np.array_equal(dev(4, xd).astype(np.float32).view(np.uint32), wc.view(np.uint32))

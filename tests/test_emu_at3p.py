@@ -32,3 +32,8 @@ def test_tone_filter(emu_lib):
 
 def test_chain_after_gha(emu_lib):
     pc.check_at3p_chain_after_gha(emu_lib, S=2, F=5, C=2)
+
+
+def test_trig_replicas_match_libm(emu_lib):
+    """glibc_trig.cuh (compiled for the host by the emulator build) against the live libm."""
+    pc.check_trig_replicas(emu_lib, n=200000)

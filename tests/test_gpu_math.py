@@ -26,3 +26,9 @@ def test_device_math_matches_libm(gpu_lib, fn, name):
     assert rc == 0, gpu_lib.atde_last_error()
     want = _live(name, x)
     assert np.array_equal(want.view(np.uint32), y.view(np.uint32))
+
+
+def test_device_trig_matches_libm(gpu_lib):
+    """glibc_trig.cuh on the device: sin / cos / atan (double) and sincosf against the live libm."""
+    import parity_cases as pc
+    pc.check_trig_replicas(gpu_lib)

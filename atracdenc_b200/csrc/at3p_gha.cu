@@ -1,0 +1,848 @@
+// at3p_gha.cu — ATRAC3plus tone search on sm_100a (first, correctness-first version).
+//
+// Replaces TSubbandGhaProcessor::AnalyzeChannels / DoRound (src/atrac/at3p/at3p_gha.cpp:732-953),
+// CheckResuidalAndApply (:492-579), CheckNextFrame (:780-813), PsyPreCheck (:955-973), FillResultBuf /
+// FillFolowerRes / AdjustEnvelope (:1499-1664) and libgha's gha_analyze_one / gha_adjust_info_newton_md /
+// sle_solve (src/lib/libgha/src/gha.c:141-470, sle.c:9-60).
+//
+// Parallel structure.  A frame's search is a sequence of rounds; in a round every (channel, subband)
+// re-fits its tones (Newton) and extracts one more.  The reference walks them in order, but a
+// (channel, subband) step only reads that subband's own tones and samples; the order matters only for
+// the shared tone budget (48) and for the "too close to a neighbour" test, which look at the other
+// subbands' state.  So: one THREAD per (channel, subband) computes its step from the state at the start
+// of the round into a staging area (kGhaTask = 16 threads per frame, two frames per warp); then one
+// lane per frame commits the 16 staged steps in the reference's order, applying the budget and the
+// neighbour tests against the partially committed state, exactly as the sequential code would see it.
+// All arithmetic is the reference's: un-fused doubles / floats in its operation order, glibc's
+// sin / cos / atan / sincosf restated (glibc_trig.cuh), kissfft restated (kissfft_dev.cuh).
+// Across frames the only carried state is the previous valid result's stop envelopes
+// (ResultBufHistory), scanned per stream by at3p_gha_result_kernel.
+#include "at3p_kernels.cuh"
+#include "kissfft_dev.cuh"
+#include "glibc_trig.cuh"
+#include "host_tables.h"
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace atde {
+namespace at3p {
+
+constexpr int kGhaSb = 8;                 // SUBBANDS, at3p_gha.cpp:216
+constexpr int kGhaTask = 16;              // (channel, subband) tasks per frame
+constexpr int kMaxDim = 16;               // tones per subband: SubbandDone counts to 15, +1 being fitted
+constexpr unsigned kEmpty = 0xffffffffu;  // TAt3PGhaData::EMPTY_POINT
+constexpr unsigned kInit = 0xfffffffeu;   // TAt3PGhaData::INIT
+constexpr double kPi = 3.14159265358979323846;
+
+struct GhaTables {
+    float window[128];                    // gha_init_window, gha.c:41-56
+    cpx tw64[64];                         // forward, kiss_fftr(128) -> FFT-64
+    cpx super128[32];
+    cpx tw128i[128];                      // inverse, kiss_fftri(256) -> FFT-128
+    cpx super256i[64];
+    float subband_ath[kGhaSb];            // FillSubbandAth, at3p_gha.cpp:453-465
+    float amp_sf_tab[64];                 // CreateAmpSfTab, :467-474
+    float sine_tab[2048];                 // :281-283
+};
+
+struct GhaInfo { float frequency, phase, magnitude; };
+
+// TChannelData of one (channel, subband), at3p_gha.cpp:225-247
+struct SbState {
+    int n;                                // tones of this subband in GhaInfos, ascending key
+    unsigned key[kMaxDim];
+    GhaInfo info[kMaxDim];
+    unsigned env_first, env_second;
+    int gapless, done;                    // done == 16: MarkSubbandDone
+    float max_mag, last_res_energy;
+    unsigned last_added;
+};
+
+// what one step wants to do, applied (or dropped) by the commit pass
+struct Staged {
+    int part1;                            // 0 no tones, 1 fit ok (replace tones), 2 failed: erase last added, mark done
+    int n_new;
+    GhaInfo fit[kMaxDim];                 // re-fitted tones, sorted by frequency
+    unsigned env_first, env_second;       // CheckResuidalAndApply's writes (also on its error paths)
+    float last_res_energy;
+    int gapless;
+    int resid_valid;                      // the staged residual replaces Buf
+    int analyzed;
+    GhaInfo found;                        // gha_analyze_one on the (new) residual
+    int psy_ok;
+    float max_mag;
+};
+
+// per-frame raw search result, consumed by the per-stream result pass
+struct GhaFrameOut {
+    int total_tones;
+    int n[2][kGhaSb];
+    unsigned key[2][kGhaSb][kMaxDim];
+    GhaInfo info[2][kGhaSb][kMaxDim];
+    unsigned env[2][kGhaSb][2];
+};
+
+struct TaskScratch {                      // global memory, one per resident task thread
+    float buf[128];                       // Buf[sb]: residual so far
+    float buf_new[128];
+    float tmp[128];                       // libgha's ctx->tmp_buf (the Repeat call of gha_adjust_info reads its stale tail)
+    float s[kMaxDim][128], c[kMaxDim][128];
+    cpx fa[64];
+    cpx fout[65];
+    cpx fb[128];
+};
+
+static GhaTables* g_gha_tables = nullptr;
+static std::once_flag g_gha_once;
+
+static void build_gha_tables()
+{
+    GhaTables* h = new GhaTables();
+    memset(h, 0, sizeof(*h));
+    {
+        const size_t size = 128, n = size + 1, half = size / 2;
+        for (size_t i = 0; i < half; i++) {
+            h->window[i] = sinf(M_PI * (i + 1) / n);
+            h->window[i] *= h->window[i];
+        }
+        for (size_t i = half; i < size; i++) h->window[i] = h->window[size - 1 - i];
+    }
+    const auto t64 = kiss_twiddles(64, false);
+    memcpy(h->tw64, t64.data(), sizeof(h->tw64));
+    const auto s128 = kiss_super_twiddles(128, false);
+    memcpy(h->super128, s128.data(), sizeof(h->super128));
+    const auto t128 = kiss_twiddles(128, true);
+    memcpy(h->tw128i, t128.data(), sizeof(h->tw128i));
+    const auto s256 = kiss_super_twiddles(256, true);
+    memcpy(h->super256i, s256.data(), sizeof(h->super256i));
+    {
+        const auto ath = calc_ath(16 * 1024, 44100);
+        for (size_t sb = 0; sb < (size_t)kGhaSb; sb++) {
+            float m = 999.;
+            for (size_t f = sb * 1024, i = 0; i < 1024; f++, i++) m = fmin(m, ath[f]);
+            h->subband_ath[sb] = pow(10, 0.1 * (m + 90));
+        }
+    }
+    for (int i = 0; i < 64; i++) h->amp_sf_tab[i] = exp2f((i - 3) / 4.0f);
+    for (int i = 0; i < 2048; i++) h->sine_tab[i] = sin(2 * M_PI * i / 2048);
+    GhaTables* d = nullptr;
+    if (cudaMalloc(&d, sizeof(GhaTables)) == cudaSuccess &&
+        cudaMemcpy(d, h, sizeof(GhaTables), cudaMemcpyHostToDevice) == cudaSuccess)
+        g_gha_tables = d;
+    delete h;
+}
+
+const GhaTables* gha_tables()
+{
+    std::call_once(g_gha_once, build_gha_tables);
+    return g_gha_tables;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+ATDE_D double dmul(double a, double b) { return __dmul_rn(a, b); }
+ATDE_D double dadd(double a, double b) { return __dadd_rn(a, b); }
+ATDE_D double dsub(double a, double b) { return __dsub_rn(a, b); }
+ATDE_D double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+ATDE_D float d2f(double a) { return __double2float_rn(a); }
+
+// GhaFreqToIndex (at3p_gha.cpp:50-53): lrintf(1024.0f * (f / M_PI)) & 1023 | sb << 10
+ATDE_D unsigned freq_to_index(float f, unsigned sb)
+{
+    const float v = d2f(dmul(1024.0, ddiv((double)f, kPi)));
+    return ((unsigned)__float2int_rn(v) & 1023u) | (sb << 10);
+}
+// GhaPhaseToIndex (:55-58): lrintf(32.0 * (p / (2 * M_PI))) & 31
+ATDE_D unsigned phase_to_index(float p)
+{
+    const float v = d2f(dmul(32.0, ddiv((double)p, 2 * kPi)));
+    return (unsigned)__float2int_rn(v) & 31u;
+}
+// AmplitudeToSf (:1666-1673): upper_bound - 1, clamped at 0
+ATDE_D unsigned amplitude_to_sf(const GhaTables* G, float amp)
+{
+    int lo = 0, hi = 64;                                 // first element > amp
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (amp < G->amp_sf_tab[mid]) hi = mid; else lo = mid + 1;
+    }
+    return (unsigned)(lo > 0 ? lo - 1 : 0);
+}
+
+// in-place kissfft on a buffer already in gather order; radix-4 stages with sub-lengths m0, 4 m0, ...
+template <bool INVERSE>
+ATDE_D void fft_stages4(cpx* buf, const cpx* tw, int n, int m0)
+{
+    for (int m = m0; m < n; m *= 4) {
+        const int fstride = n / (4 * m);
+        for (int v = 0; v < n / 4; v++) kf_stage4<INVERSE>(buf, tw, v, m, fstride);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gha_analyze_one (gha.c:404-431) with upsample = 1
+// ---------------------------------------------------------------------------------------------
+ATDE_D GhaInfo analyze_one(const GhaTables* G, const float* pcm, TaskScratch* ws)
+{
+    float* tmp = ws->tmp;
+    for (int i = 0; i < 128; i++) tmp[i] = fmul(pcm[i], G->window[i]);
+    // kiss_fftr(128): FFT-64 of the packed pairs (64 = 4 x 4 x 4: slot 16 d0 + 4 d1 + d2 holds input d0 + 4 d1 + 16 d2)
+    cpx* fa = ws->fa;
+    for (int slot = 0; slot < 64; slot++) {
+        const int j = (slot >> 4) + 4 * ((slot >> 2) & 3) + 16 * (slot & 3);
+        fa[slot].r = tmp[2 * j];
+        fa[slot].i = tmp[2 * j + 1];
+    }
+    fft_stages4<false>(fa, G->tw64, 64, 1);
+    cpx* fo = ws->fout;                                   // freqdata[0..64]; [65..128] stay zero (calloc)
+    {
+        const float tr = fa[0].r, ti = fa[0].i;
+        fo[0].r = fadd(tr, ti);  fo[0].i = 0.0f;
+        fo[64].r = fsub(tr, ti); fo[64].i = 0.0f;
+        for (int k = 1; k <= 32; k++) {
+            const cpx fpk = fa[k];
+            cpx fpnk; fpnk.r = fa[64 - k].r; fpnk.i = -fa[64 - k].i;
+            cpx f1k, f2k;
+            f1k.r = fadd(fpk.r, fpnk.r); f1k.i = fadd(fpk.i, fpnk.i);
+            f2k.r = fsub(fpk.r, fpnk.r); f2k.i = fsub(fpk.i, fpnk.i);
+            const cpx t2 = cmul(f2k, G->super128[k - 1]);
+            fo[k].r = fmul(fadd(f1k.r, t2.r), 0.5f);
+            fo[k].i = fmul(fadd(f1k.i, t2.i), 0.5f);
+            fo[64 - k].r = fmul(fsub(f1k.r, t2.r), 0.5f);
+            fo[64 - k].i = fmul(fsub(t2.i, f1k.i), 0.5f);
+        }
+    }
+    // gha_estimate_bin (:141-157)
+    int bin = 0;
+    {
+        float mx = 0.0f;
+        for (int i = 0; i < 65; i++) {
+            const float t = fadd(fmul(fo[i].r, fo[i].r), fmul(fo[i].i, fo[i].i));
+            if (t > mx) { mx = t; bin = i; }
+        }
+    }
+    // resample_fft (:159-166): kiss_fftri(256) of the zero-extended spectrum, then / 128
+    cpx* fb = ws->fb;                                     // gather order of 128 = 4 x 4 x 4 x 2
+    {
+        auto freq = [&](int k) { cpx z; if (k <= 64) z = fo[k]; else { z.r = 0.0f; z.i = 0.0f; } return z; };
+        auto put = [&](int idx, cpx v) {
+            // input index d0 + 4 d1 + 16 d2 + 64 d3 sits at slot 32 d0 + 8 d1 + 2 d2 + d3
+            const int slot = ((idx & 3) << 5) | (((idx >> 2) & 3) << 3) | (((idx >> 4) & 3) << 1) | (idx >> 6);
+            fb[slot] = v;
+        };
+        cpx t0;
+        t0.r = fadd(freq(0).r, freq(128).r);
+        t0.i = fsub(freq(0).r, freq(128).r);
+        put(0, t0);
+        for (int k = 1; k <= 64; k++) {
+            const cpx fk = freq(k);
+            cpx fnkc; fnkc.r = freq(128 - k).r; fnkc.i = -freq(128 - k).i;
+            cpx fek, tp;
+            fek.r = fadd(fk.r, fnkc.r); fek.i = fadd(fk.i, fnkc.i);
+            tp.r = fsub(fk.r, fnkc.r);  tp.i = fsub(fk.i, fnkc.i);
+            const cpx fok = cmul(tp, G->super256i[k - 1]);
+            cpx a, bq;
+            a.r = fadd(fek.r, fok.r); a.i = fadd(fek.i, fok.i);
+            bq.r = fsub(fek.r, fok.r); bq.i = fmul(fsub(fek.i, fok.i), -1.0f);
+            put(k, a);
+            put(128 - k, bq);                             // k == 64 overwrites, as in the reference
+        }
+        for (int v = 0; v < 64; v++) kf_stage2(fb, G->tw128i, v, 1, 64);
+        fft_stages4<true>(fb, G->tw128i, 128, 2);
+    }
+    float* res = reinterpret_cast<float*>(fb);            // 256 reals
+    for (int i = 0; i < 256; i++) res[i] = __fdiv_rn(res[i], 128.0f);
+    // gha_search_omega_newton (:173-236) on the 256 resampled points
+    GhaInfo out;
+    {
+        double omega = ddiv(dmul((double)(bin * 2), kPi), 256.0);
+        for (int loop = 0; loop <= 7; loop++) {
+            double Xr = 0, Xi = 0, dXr = 0, dXi = 0, ddXr = 0, ddXs = 0;
+            const double a = g_cos(omega), b = g_sin(omega);
+            double c = 1.0, s = 0.0;
+            for (int n = 0; n < 256; n++) {
+                const double p = (double)res[n], dn = (double)n;
+                const double cm = dmul(p, c), sm = dmul(p, s);
+                Xr = dadd(Xr, cm);
+                Xi = dadd(Xi, sm);
+                const double tc = dmul(dn, cm), ts = dmul(dn, sm);
+                dXr = dsub(dXr, ts);
+                dXi = dadd(dXi, tc);
+                ddXr = dsub(ddXr, dmul(dn, tc));
+                ddXs = dsub(ddXs, dmul(dn, ts));
+                const double nc = dsub(dmul(a, c), dmul(b, s));
+                const double ns = dadd(dmul(b, c), dmul(a, s));
+                c = nc; s = ns;
+            }
+            const double F = dadd(dmul(Xr, dXr), dmul(Xi, dXi));
+            const double G2 = dadd(dmul(Xr, Xr), dmul(Xi, Xi));
+            const double dF = dadd(dadd(dadd(dmul(Xr, ddXr), dmul(dXr, dXr)), dmul(Xi, ddXs)), dmul(dXi, dXi));
+            const double dw = ddiv(F, dsub(dF, ddiv(dmul(F, F), G2)));
+            omega = dsub(omega, dw);
+            if (omega < 0) omega = dmul(omega, -1.0);
+            while (omega > kPi * 2.0) omega = dsub(omega, kPi * 2.0);
+            if (omega > kPi) omega = dsub(kPi * 2.0, omega);
+            if (loop == 7) {
+                out.frequency = d2f(omega);
+                out.phase = d2f(dsub(kPi / 2, g_atan(ddiv(Xi, Xr))));
+                if (Xr < 0) out.phase = d2f(dadd((double)out.phase, kPi));
+            }
+        }
+        out.frequency = d2f(dmul((double)out.frequency, 2.0));
+    }
+    // gha_generate_sine (:238-244) + gha_estimate_magnitude (:246-257)
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < 128; i++) {
+        const float arg = fadd(fmul(out.frequency, (float)i), out.phase);
+        const float r = d2f(g_sin((double)arg));
+        tmp[i] = r;
+        t1 = dadd(t1, (double)fmul(pcm[i], r));
+        t2 = dadd(t2, (double)fmul(r, r));
+    }
+    out.magnitude = d2f(ddiv(t1, t2));
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sle_solve (sle.c:9-60) on one dim x (dim+1) block.  The reference solves the 3dim system at once, but
+// gha_adjust_info_newton_md overwrites the coupling blocks with never-written (zero) entries
+// (gha.c:341-343), which leaves three independent blocks; rows of the other blocks carry exact zeros
+// in this block's columns, never win a pivot search and are skipped by the |t| < eps test.
+// ---------------------------------------------------------------------------------------------
+ATDE_D int sle_block(double* a, int n, double* x)
+{
+    const int col = n + 1;
+    const double eps = (double)0.00001f;
+    for (int k = 0; k < n; k++) {
+        double mx = fabs(a[col * k + k]);
+        int index = k;
+        for (int i = k + 1; i < n; i++) {
+            const double t = fabs(a[col * i + k]);
+            if (t > mx) { mx = t; index = i; }
+        }
+        if (mx < eps) return -1;
+        if (index != k)
+            for (int i = 0; i < col; i++) { const double t = a[col * k + i]; a[col * k + i] = a[col * index + i]; a[col * index + i] = t; }
+        for (int i = k; i < n; i++) {
+            const double t = a[col * i + k];
+            if (fabs(t) < eps) continue;
+            for (int j = 0; j < col; j++) a[i * col + j] = ddiv(a[i * col + j], t);
+            if (i != k)
+                for (int j = 0; j < col; j++) a[i * col + j] = dsub(a[i * col + j], a[k * col + j]);
+        }
+    }
+    for (int k = n - 1; k >= 0; k--) {
+        x[k] = a[col * k + n];
+        for (int i = 0; i < k; i++) a[col * i + n] = dsub(a[col * i + n], dmul(a[col * i + k], x[k]));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gha_adjust_info_newton_md (gha.c:259-402); leaves the last loop's residual in ws->tmp[0..sz)
+// ---------------------------------------------------------------------------------------------
+ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskScratch* ws)
+{
+    float* tmp = ws->tmp;
+    double M[kMaxDim * (kMaxDim + 1)];
+    double fx[3][kMaxDim];
+    for (int loop = 0; loop < 7; loop++) {
+        for (int n = 0; n < sz; n++) tmp[n] = pcm[n];
+        for (int k = 0; k < dim; k++) {
+            const float fr = info[k].frequency, ph = info[k].phase, mg = info[k].magnitude;
+            for (int n = 0; n < sz; n++) {
+                const float t = fadd(fmul(fr, (float)n), ph);
+                float s, c;
+                g_sincosf(t, s, c);
+                tmp[n] = fsub(tmp[n], fmul(mg, s));
+                ws->s[k][n] = s;
+                ws->c[k][n] = c;
+            }
+        }
+        // three blocks: A (ba = -s), w (bw = -A n c), p (bp = -A c); right-hand sides from the residual
+        for (int blk = 0; blk < 3; blk++) {
+            const int col = dim + 1;
+            for (int i = 0; i < dim; i++) {
+                const double Ai = (double)info[i].magnitude;
+                for (int j = 0; j < dim; j++) {
+                    const double Aj = (double)info[j].magnitude;
+                    double acc = 0.0;
+                    if (blk == 0) {
+                        for (int n = 0; n < sz; n++)
+                            acc = dadd(acc, dmul(-(double)ws->s[i][n], -(double)ws->s[j][n]));
+                    } else if (blk == 1) {
+                        if (i == j) {
+                            for (int n = 0; n < sz; n++) {
+                                const double dn = (double)n, c = (double)ws->c[i][n], s = (double)ws->s[i][n];
+                                const double bw = dmul(dmul(-Ai, dn), c);
+                                const double bww = dmul(dmul(dmul(Ai, dn), dn), s);
+                                acc = dadd(acc, dadd(dmul((double)tmp[n], bww), dmul(bw, bw)));
+                            }
+                        } else {
+                            for (int n = 0; n < sz; n++) {
+                                const double dn = (double)n;
+                                const double bwi = dmul(dmul(-Ai, dn), (double)ws->c[i][n]);
+                                const double bwj = dmul(dmul(-Aj, dn), (double)ws->c[j][n]);
+                                acc = dadd(acc, dmul(bwi, bwj));
+                            }
+                        }
+                    } else {
+                        if (i == j) {
+                            for (int n = 0; n < sz; n++) {
+                                const double bp = dmul(-Ai, (double)ws->c[i][n]);
+                                const float bpp = d2f(dmul(Ai, (double)ws->s[i][n]));
+                                acc = dadd(acc, dadd((double)fmul(tmp[n], bpp), dmul(bp, bp)));
+                            }
+                        } else {
+                            for (int n = 0; n < sz; n++) {
+                                const double bpi = dmul(-Ai, (double)ws->c[i][n]);
+                                const double bpj = dmul(-Aj, (double)ws->c[j][n]);
+                                acc = dadd(acc, dmul(bpi, bpj));
+                            }
+                        }
+                    }
+                    M[i * col + j] = dmul(acc, 2.0);
+                }
+                double r = 0.0;
+                for (int n = 0; n < sz; n++) {
+                    float bf;
+                    if (blk == 0) bf = -ws->s[i][n];
+                    else if (blk == 1) bf = d2f(dmul(dmul(-Ai, (double)n), (double)ws->c[i][n]));
+                    else bf = d2f(dmul(-Ai, (double)ws->c[i][n]));
+                    r = dadd(r, (double)fmul(tmp[n], bf));
+                }
+                M[i * col + dim] = dmul(r, 2.0);
+            }
+            for (int i = 0; i < dim; i++) fx[blk][i] = 0.0;
+            if (sle_block(M, dim, fx[blk])) return -1;
+        }
+        for (int k = 0; k < dim; k++) {
+            info[k].magnitude = d2f(dsub((double)info[k].magnitude, dmul(fx[0][k], 0.8)));
+            info[k].frequency = d2f(dsub((double)info[k].frequency, dmul(fx[1][k], 0.8)));
+            info[k].phase = d2f(dsub((double)info[k].phase, dmul(fx[2][k], 0.8)));
+        }
+        for (int k = 0; k < dim; k++) {
+            if (info[k].magnitude < 0) {
+                info[k].magnitude = fmul(info[k].magnitude, -1.0f);
+                info[k].phase = d2f(dadd((double)info[k].phase, kPi));
+            }
+            if (info[k].magnitude > 32768.0f) info[k].magnitude = d2f(dmul(32768.0, 0.5));
+        }
+        for (int k = 0; k < dim; k++) {
+            if (info[k].frequency < 0) {
+                info[k].frequency = fmul(info[k].frequency, -1.0f);
+                info[k].phase = d2f(dsub(2 * kPi, (double)info[k].phase));
+            }
+            while ((double)info[k].frequency > kPi * 2.0) info[k].frequency = d2f(dsub((double)info[k].frequency, kPi * 2.0));
+            if ((double)info[k].frequency > kPi) info[k].frequency = d2f(dsub(2 * kPi, (double)info[k].frequency));
+        }
+        for (int k = 0; k < dim; k++) {
+            while ((double)info[k].phase > kPi * 2.0) info[k].phase = d2f(dsub((double)info[k].phase, kPi * 2));
+            while (info[k].phase < 0) info[k].phase = d2f(dadd((double)info[k].phase, kPi * 2));
+        }
+    }
+    return 0;
+}
+
+// GenWaves (at3p_gha.cpp:476-490) over the 64 look-ahead samples + the energy test of CheckNextFrame (:780-813)
+ATDE_D bool check_next_frame(const GhaTables* G, const float* next_src, const GhaInfo* tones, int n)
+{
+    float buf[64];
+    for (int i = 0; i < 64; i++) buf[i] = 0.0f;
+    for (int w = 0; w < n; w++) {
+        const float amp = G->amp_sf_tab[amplitude_to_sf(G, tones[w].magnitude)];
+        const int inc = (int)freq_to_index(tones[w].frequency, 0);
+        int pos = ((int)((phase_to_index(tones[w].phase) & 0x1f) << 6) + (0 ^ 128) * inc) & 2047;
+        for (int i = 0; i < 64; i++) {
+            buf[i] = fadd(buf[i], fmul(G->sine_tab[pos], amp));
+            pos = (pos + inc) & 2047;
+        }
+    }
+    float before = 0.0f, after = 0.0f;
+    for (int i = 0; i < 64; i++) {
+        before = fadd(before, fmul(next_src[i], next_src[i]));
+        const float t = fsub(next_src[i], buf[i]);
+        after = fadd(after, fmul(t, t));
+    }
+    return after < before;
+}
+
+// One (channel, subband) step of DoRound computed from the start-of-round state into `st`.
+ATDE_D void task_step(const GhaTables* G, const SbState& sbs, int sb, const float* src, const float* next_src,
+                      TaskScratch* ws, Staged& st)
+{
+    st.part1 = 0; st.n_new = 0; st.resid_valid = 0; st.analyzed = 0; st.psy_ok = 0;
+    st.env_first = sbs.env_first; st.env_second = sbs.env_second;
+    st.last_res_energy = sbs.last_res_energy; st.gapless = sbs.gapless; st.max_mag = sbs.max_mag;
+    const float* analysis_src = ws->buf;
+    if (sbs.n > 0) {
+        const int dim = sbs.n;
+        GhaInfo tmp_info[kMaxDim];
+        for (int i = 0; i < dim; i++) tmp_info[i] = sbs.info[i];
+        // do { gha_adjust_info(...) } while (Repeat)   (at3p_gha.cpp:840-846, CheckResuidalAndApply :492-579)
+        int status = 1;                                  // 0 Error, 1 Ok, 2 Repeat
+        int frame_sz = 0;
+        for (int call = 0; call < 2; call++) {
+            const int sz = (frame_sz && frame_sz < 128) ? frame_sz : 128;
+            if (adjust_newton(src, tmp_info, dim, sz, ws) < 0) { status = 0; break; }
+            // the callback reads 128 samples: beyond sz they are what the previous (full-size) call left in
+            // tmp_buf, which is exactly what ws->tmp still holds there
+            float res_energy = 0.0f;
+            unsigned start = 0, cur_start = 0, count = 0, len = 0;
+            bool found = false;
+            for (int i = 0; i < 128; i += 4) {
+                float ein = 0.0f, eout = 0.0f;
+                for (int j = 0; j < 4; j++) {
+                    ein = fadd(ein, fmul(src[i + j], src[i + j]));
+                    eout = fadd(eout, fmul(ws->tmp[i + j], ws->tmp[i + j]));
+                }
+                ein = __fsqrt_rn(__fdiv_rn(ein, 4.0f));
+                eout = __fsqrt_rn(__fdiv_rn(eout, 4.0f));
+                res_energy = fadd(res_energy, eout);
+                if (__fdiv_rn(ein, eout) < 1.0f) {
+                    count = 0; found = false; cur_start = (unsigned)i + 4;
+                } else {
+                    count++;
+                    if (count > len) { len = count; if (!found) { start = cur_start; found = true; } }
+                }
+            }
+            if (len < 4) { status = 0; break; }
+            const unsigned end = start + len * 4;
+            if (status != 2 && end != 128) {
+                frame_sz = (int)end; status = 2;
+                continue;
+            }
+            if (st.last_res_energy == 0.0f) {               // static_cast<bool>(x) == false
+                st.last_res_energy = res_energy;
+            } else if (st.last_res_energy < fmul(res_energy, 1.05f)) {
+                status = 0; break;
+            } else {
+                st.last_res_energy = res_energy;
+            }
+            st.env_first = start;
+            if (st.env_second == kEmpty && end != 128) { status = 0; break; }
+            st.env_second = end;
+            status = 1;
+            for (int i = 0; i < 128; i++) ws->buf_new[i] = ws->tmp[i];
+            st.resid_valid = 1;
+            break;
+        }
+        bool ok = status == 1;                          // (the second call never asks for another repeat)
+        if (ok) {
+            // std::sort by frequency (unique result unless two frequencies are equal, which the duplicate test rejects)
+            for (int i = 1; i < dim; i++) {
+                const GhaInfo v = tmp_info[i];
+                int j = i - 1;
+                while (j >= 0 && v.frequency < tmp_info[j].frequency) { tmp_info[j + 1] = tmp_info[j]; j--; }
+                tmp_info[j + 1] = v;
+            }
+            bool dup = false;
+            unsigned idx1 = freq_to_index(tmp_info[0].frequency, (unsigned)sb);
+            for (int i = 1; i < dim; i++) {
+                const unsigned idx2 = freq_to_index(tmp_info[i].frequency, (unsigned)sb);
+                if (idx2 == idx1) { dup = true; break; }
+                idx1 = idx2;
+            }
+            if (dup) ok = false;
+            if (ok && (st.env_second == 128u || st.env_second == kEmpty)) {
+                const bool cont = check_next_frame(G, next_src, tmp_info, dim);
+                if (st.gapless && !cont) ok = false;
+                else if (st.env_second == 128u && cont) { st.env_second = kEmpty; st.gapless = 1; }
+            }
+        }
+        if (!ok) { st.part1 = 2; return; }
+        st.part1 = 1;
+        st.n_new = dim;
+        for (int i = 0; i < dim; i++) {
+            st.fit[i] = tmp_info[i];
+            st.max_mag = fmaxf(st.max_mag, tmp_info[i].magnitude);
+        }
+        if (st.resid_valid) analysis_src = ws->buf_new;
+    }
+    st.found = analyze_one(G, analysis_src, ws);
+    st.analyzed = 1;
+    // PsyPreCheck (:955-973)
+    const float mg = st.found.magnitude;
+    st.psy_ok = !(mg != mg) && fmul(mg, mg) > G->subband_ath[sb] && mg > __fdiv_rn(st.max_mag, 10.0f);
+}
+
+// map<uint32_t, gha_info> of one channel = the eight per-subband lists; helpers for the commit pass
+ATDE_D void sb_erase_key(SbState& s, unsigned key)
+{
+    for (int i = 0; i < s.n; i++)
+        if (s.key[i] == key) {
+            for (int j = i; j + 1 < s.n; j++) { s.key[j] = s.key[j + 1]; s.info[j] = s.info[j + 1]; }
+            s.n--;
+            return;
+        }
+}
+ATDE_D bool sb_insert(SbState& s, unsigned key, const GhaInfo& v)     // map::insert: keeps the old element on a key clash
+{
+    int pos = 0;
+    while (pos < s.n && s.key[pos] < key) pos++;
+    if (pos < s.n && s.key[pos] == key) return false;
+    if (s.n >= kMaxDim) return false;
+    for (int j = s.n; j > pos; j--) { s.key[j] = s.key[j - 1]; s.info[j] = s.info[j - 1]; }
+    s.key[pos] = key; s.info[pos] = v; s.n++;
+    return true;
+}
+
+constexpr int kGhaThreads = 64;           // 4 frames per block
+
+__global__ void __launch_bounds__(kGhaThreads) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
+                                                                       const float* __restrict__ bands,
+                                                                       int S, int C, int F, TaskScratch* scratch,
+                                                                       GhaFrameOut* out)
+{
+    // bands [S][C][F][2048]; frame (s, f) analyses bands[s][c][f] with look-ahead bands[s][c][f+1] (zeros past the end)
+    __shared__ SbState state[kGhaThreads / kGhaTask][2][kGhaSb];
+    __shared__ Staged staged[kGhaThreads / kGhaTask][kGhaTask];
+    __shared__ int s_total[kGhaThreads / kGhaTask], s_go[kGhaThreads / kGhaTask];
+    __shared__ unsigned char s_adopt[kGhaThreads / kGhaTask][kGhaTask];
+    const int slot = threadIdx.x / kGhaTask, t = threadIdx.x % kGhaTask;
+    const int ch = t >> 3, sb = t & 7;
+    const long long n_frames = (long long)S * F;
+    TaskScratch* ws = scratch + (size_t)blockIdx.x * kGhaThreads + threadIdx.x;
+    for (long long base = (long long)blockIdx.x * (kGhaThreads / kGhaTask); base < n_frames;
+         base += (long long)gridDim.x * (kGhaThreads / kGhaTask)) {
+        const long long frame = base + slot;
+        const bool live = frame < n_frames && ch < C;
+        const int s = live ? (int)(frame / F) : 0, f = live ? (int)(frame % F) : 0;
+        const float* src = bands + (((size_t)s * C + (live ? ch : 0)) * F + f) * kFrame + sb * kSbSamples;
+        const bool has_next = f + 1 < F;
+        float next_src[64];
+        SbState& me = state[slot][ch][sb];
+        if (live) {
+            for (int i = 0; i < 128; i++) ws->buf[i] = src[i];
+            for (int i = 0; i < 64; i++) next_src[i] = has_next ? src[kFrame + i] : 0.0f;
+            me.n = 0;
+            // pair<> Envelopes[SUBBANDS] = {{INIT, INIT}}: only element 0 gets INIT, the rest are value-initialised
+            me.env_first = sb == 0 ? kInit : 0u;
+            me.env_second = sb == 0 ? kInit : 0u;
+            me.gapless = 0; me.done = 0; me.max_mag = 0.0f; me.last_res_energy = 0.0f; me.last_added = 0;
+        } else {
+            me.n = 0; me.done = 16;
+        }
+        if (t == 0) { s_total[slot] = 0; s_go[slot] = frame < n_frames; }
+        s_adopt[slot][t] = 0;
+        __syncthreads();
+        for (;;) {
+            bool any_go = false;
+            for (int q = 0; q < kGhaThreads / kGhaTask; q++) any_go |= s_go[q] != 0;
+            if (!any_go) break;
+            __syncthreads();
+            Staged& st = staged[slot][t];
+            const bool run = live && s_go[slot] && me.done != 16;
+            if (run) task_step(G, me, sb, src, next_src, ws, st);
+            __syncthreads();
+            if (t == 0 && s_go[slot]) {
+                // commit in the reference's order: channel 0 subbands 0..7, then channel 1
+                int total = s_total[slot];
+                bool progress[2] = {false, false};
+                for (int c2 = 0; c2 < C; c2++) {
+                    bool prog = false;
+                    for (int b2 = 0; b2 < kGhaSb; b2++) {
+                        SbState& z = state[slot][c2][b2];
+                        if (z.done == 16) continue;
+                        if (total >= 48) { prog = false; break; }          // return false
+                        const Staged& g = staged[slot][c2 * 8 + b2];
+                        if (g.part1 != 0) {
+                            // what CheckResuidalAndApply / the look-ahead test wrote, also on their failure paths
+                            z.env_first = g.env_first; z.env_second = g.env_second;
+                            z.last_res_energy = g.last_res_energy; z.gapless = g.gapless;
+                            if (g.part1 == 2) {                            // :866-871, :899-910: drop the last added tone, done
+                                sb_erase_key(z, z.last_added);
+                                total--;
+                                z.done = 16;
+                                continue;
+                            }
+                            z.n = 0;                                       // :888-897: replace the subband's tones
+                            for (int i = 0; i < g.n_new; i++) {
+                                z.max_mag = fmaxf(z.max_mag, g.fit[i].magnitude);
+                                sb_insert(z, freq_to_index(g.fit[i].frequency, (unsigned)b2), g.fit[i]);
+                            }
+                            if (g.resid_valid) s_adopt[slot][c2 * 8 + b2] = 1;
+                        }
+                        const unsigned fi = freq_to_index(g.found.frequency, (unsigned)b2);
+                        if (!g.psy_ok) { z.done = 16; continue; }
+                        if (z.done == 0) {
+                            sb_insert(z, fi, g.found);
+                            z.last_added = fi;
+                        } else {
+                            // lower_bound over the channel's whole map
+                            unsigned next_key = 0, prev_key = 0;
+                            bool has_nxt = false, has_prev = false;
+                            for (int b3 = 0; b3 < kGhaSb; b3++) {
+                                const SbState& y = state[slot][c2][b3];
+                                for (int i = 0; i < y.n; i++) {
+                                    if (y.key[i] >= fi) { if (!has_nxt) { has_nxt = true; next_key = y.key[i]; } }
+                                    else { has_prev = true; prev_key = y.key[i]; }
+                                }
+                            }
+                            if (has_nxt && (next_key == fi || next_key - fi < 20u)) { z.done = 16; continue; }
+                            if (has_prev && fi - prev_key < 20u) { z.done = 16; continue; }
+                            if (z.done == 15) { z.done = 16; continue; }
+                            sb_insert(z, fi, g.found);
+                            z.last_added = fi;
+                        }
+                        z.done++;
+                        total++;
+                        prog = true;
+                    }
+                    progress[c2] = prog;
+                }
+                s_total[slot] = total;
+                s_go[slot] = (progress[0] || progress[1]) && total < 48;
+            }
+            __syncthreads();
+            // adopt the staged residual where the callback accepted it and the step was committed
+            if (s_adopt[slot][t]) {
+                s_adopt[slot][t] = 0;
+                for (int i = 0; i < 128; i++) ws->buf[i] = ws->buf_new[i];
+            }
+            __syncthreads();
+        }
+        if (frame < n_frames && live) {
+            GhaFrameOut& o = out[frame];
+            if (t == 0) o.total_tones = s_total[slot];
+            o.n[ch][sb] = me.n;
+            for (int i = 0; i < me.n; i++) { o.key[ch][sb][i] = me.key[i]; o.info[ch][sb][i] = me.info[i]; }
+            o.env[ch][sb][0] = me.env_first; o.env[ch][sb][1] = me.env_second;
+        }
+        __syncthreads();
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// FillResultBuf / FillFolowerRes / AdjustEnvelope (at3p_gha.cpp:1499-1664) + the ResultBufHistory carry:
+// one thread per stream walks its frames in order.
+// ---------------------------------------------------------------------------------------------
+struct GhaHistory {                       // what later frames read of ResultBufHistory
+    int n_sb[2];
+    unsigned env_second[2][16];
+};
+
+ATDE_D void adjust_envelope(int* env /*[2]*/, unsigned src_first, unsigned src_second, unsigned history)
+{
+    if (src_first == 0 && history == kEmpty) env[0] = (int)kEmpty;
+    else env[0] = (int)(src_first / 4);
+    if (src_second == kEmpty) env[1] = (int)kEmpty;
+    else env[1] = (int)((src_second - 1) / 4);
+}
+
+__global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const GhaFrameOut* __restrict__ in,
+                                       int S, int C, int F, GhaHistory* hist_state, ToneBlock* out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    GhaHistory h = hist_state[s];
+    for (int f = 0; f < F; f++) {
+        const GhaFrameOut& o = in[(size_t)s * F + f];
+        ToneBlock& tb = out[(size_t)s * F + f];
+        tb.present = 0; tb.num_tone_bands = 0; tb.second_is_leader = 0;
+        tb.n_sb[0] = tb.n_sb[1] = 0; tb.n_params[0] = tb.n_params[1] = 0;
+        for (int i = 0; i < 16; i++) tb.tone_sharing[i] = 0;
+        if (o.total_tones == 0) continue;                      // DoAnalize returns nullptr, history untouched
+        int used[2] = {0, 0};
+        for (int ch = 0; ch < C; ch++)
+            for (int sb = 0; sb < kGhaSb; sb++) if (o.n[ch][sb] > 0) used[ch] = sb + 1;
+        const int leader = used[1] > used[0] ? 1 : 0;
+        const int ntb = used[leader];
+        tb.present = 1; tb.second_is_leader = leader; tb.num_tone_bands = ntb;
+        tb.n_sb[0] = ntb;
+        if (C == 2) tb.n_sb[1] = ntb;
+        for (int ch = 0; ch < 2; ch++)
+            for (int sb = 0; sb < 16; sb++) { tb.sb[ch][sb][0] = 0; tb.sb[ch][sb][1] = 0; tb.sb[ch][sb][2] = (int)kEmpty; tb.sb[ch][sb][3] = (int)kEmpty; }
+        int np0 = 0, np1 = 0;
+        const int fol = 1 - leader;
+        for (int sb = 0; sb < ntb; sb++) {
+            const int index = np0;
+            for (int i = 0; i < o.n[leader][sb]; i++) {
+                int* prm = tb.params[0][np0++];
+                prm[0] = (int)(o.key[leader][sb][i] & 1023u);
+                prm[1] = (int)amplitude_to_sf(G, o.info[leader][sb][i].magnitude);
+                prm[2] = 1;
+                prm[3] = (int)phase_to_index(o.info[leader][sb][i].phase);
+                tb.sb[0][sb][1]++;
+            }
+            if (tb.sb[0][sb][1] > 0) {
+                tb.sb[0][sb][0] = index;
+                const unsigned hs = h.n_sb[0] > sb ? h.env_second[0][sb] : kInit;
+                adjust_envelope(&tb.sb[0][sb][2], o.env[leader][sb][0], o.env[leader][sb][1], hs);
+            }
+            if (C == 2) {
+                const unsigned hs = h.n_sb[1] > sb ? h.env_second[1][sb] : kInit;
+                unsigned mode = 0;
+                int added = 0;
+                for (int i = 0; i < o.n[fol][sb]; i++) {
+                    const unsigned key = o.key[fol][sb][i];
+                    bool in_leader = false;
+                    for (int j = 0; j < o.n[leader][sb]; j++) in_leader |= o.key[leader][sb][j] == key;
+                    mode |= in_leader ? 1u : 2u;
+                    int* prm = tb.params[1][np1++];
+                    prm[0] = (int)(key & 1023u);
+                    prm[1] = (int)amplitude_to_sf(G, o.info[fol][sb][i].magnitude);
+                    prm[2] = 1;
+                    prm[3] = (int)phase_to_index(o.info[fol][sb][i].phase);
+                    added++;
+                }
+                if (mode == 0) { tb.tone_sharing[sb] = 0; tb.sb[1][sb][1] = 0; }
+                else if (mode == 1) { tb.tone_sharing[sb] = 1; np1 -= added; }
+                else {
+                    tb.tone_sharing[sb] = 0;
+                    tb.sb[1][sb][0] = np1 - added;
+                    tb.sb[1][sb][1] = added;
+                    adjust_envelope(&tb.sb[1][sb][2], o.env[fol][sb][0], o.env[fol][sb][1], hs);
+                }
+            }
+        }
+        tb.n_params[0] = np0; tb.n_params[1] = np1;
+        // ResultBufHistory = ResultBuf
+        h.n_sb[0] = ntb;
+        h.n_sb[1] = C == 2 ? ntb : h.n_sb[1];
+        for (int ch = 0; ch < C; ch++)
+            for (int sb = 0; sb < ntb; sb++) h.env_second[ch][sb] = (unsigned)tb.sb[ch][sb][3];
+    }
+    hist_state[s] = h;
+}
+
+} // namespace at3p
+} // namespace atde
+
+// ---- stage entry: the whole tone search on fresh streams (tests/) ----
+extern "C" int atde_at3p_stage_gha(const float* bands, int S, int C, int F, void* tones)
+{
+    using namespace atde::at3p;
+    const GhaTables* G = gha_tables();
+    if (!G) return -2;
+    const size_t n = (size_t)S * C * F * kFrame;
+    float* d_bands = nullptr;
+    TaskScratch* d_scr = nullptr;
+    GhaFrameOut* d_out = nullptr;
+    GhaHistory* d_hist = nullptr;
+    ToneBlock* d_tb = nullptr;
+    const long long n_frames = (long long)S * F;
+    int blocks = (int)((n_frames + 3) / 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    int rc = 0;
+    if (cudaMalloc(&d_bands, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&d_scr, (size_t)blocks * kGhaThreads * sizeof(TaskScratch)) != cudaSuccess ||
+        cudaMalloc(&d_out, (size_t)n_frames * sizeof(GhaFrameOut)) != cudaSuccess ||
+        cudaMalloc(&d_hist, (size_t)S * sizeof(GhaHistory)) != cudaSuccess ||
+        cudaMalloc(&d_tb, (size_t)n_frames * sizeof(ToneBlock)) != cudaSuccess) rc = -3;
+    if (!rc && (cudaMemcpy(d_bands, bands, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemset(d_hist, 0, (size_t)S * sizeof(GhaHistory)) != cudaSuccess ||
+                cudaMemset(d_out, 0, (size_t)n_frames * sizeof(GhaFrameOut)) != cudaSuccess)) rc = -2;
+    if (!rc) {
+        ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, (cudaStream_t) nullptr, G, (const float*)d_bands, S, C, F, d_scr, d_out);
+        ATDE_LAUNCH(at3p_gha_result_kernel, (unsigned)((S + 63) / 64), 64, 0, (cudaStream_t) nullptr, G, (const GhaFrameOut*)d_out, S, C, F, d_hist, d_tb);
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = -2;
+    }
+    if (!rc && cudaMemcpy(tones, d_tb, (size_t)n_frames * sizeof(ToneBlock), cudaMemcpyDeviceToHost) != cudaSuccess) rc = -2;
+    cudaFree(d_bands); cudaFree(d_scr); cudaFree(d_out); cudaFree(d_hist); cudaFree(d_tb);
+    return rc;
+}

@@ -22,6 +22,9 @@ int atde_at3p_tone_block_size(void);
  * results per unit (two calls ago, previous call, this call) -> resid [U][C][2048]. */
 int atde_at3p_stage_tone_filter(const float* bands, const void* tb_old, const void* tb_now, const void* tb_next,
                                 int units, int C, float* resid);
+/* IGhaProcessor::DoAnalize without the filter (src/atrac/at3p/at3p_gha.cpp:692-743): bands [S][C][F][2048] of fresh
+ * streams (frame f looks ahead into frame f+1; zeros past the end) -> tones [S][F] (ToneBlock records). */
+int atde_at3p_stage_gha(const float* bands, int S, int C, int F, void* tones);
 /* device replicas of glibc sin / cos / atan / sincosf (glibc_trig.cuh); fn: 0 sin, 1 cos, 2 atan, 3 sinf, 4 cosf */
 int atde_at3p_debug_trig(int fn, const double* x, double* y, long long n);
 #ifdef __cplusplus

@@ -570,3 +570,78 @@ def check_trig_replicas(lib, n=2000000, seed=77):
     xd = np.ascontiguousarray(xf.astype(np.float64))
     assert np.array_equal(dev(3, xd).astype(np.float32).view(np.uint32), ws.view(np.uint32))
     assert np.array_equal(dev(4, xd).astype(np.float32).view(np.uint32), wc.view(np.uint32))
+
+
+def at3p_stage_gha(lib, bands, S, C, F):
+    bands = np.ascontiguousarray(bands, dtype=np.float32)
+    assert lib.atde_at3p_tone_block_size() == tl.AT3P_GHA_REC.itemsize
+    out = np.zeros((S, F), tl.AT3P_GHA_REC)
+    rc = lib.atde_at3p_stage_gha(bands.ctypes.data_as(tl.P), S, C, F, out.ctypes.data_as(tl.P))
+    assert rc == 0, f"atde_at3p_stage_gha -> {rc}"
+    return out
+
+
+def _tone_records_equal(got, want, C):
+    """Compares the meaningful fields of two flattened TAt3PGhaData records (the reference leaves stale
+    ToneSharing flags / wave slots beyond NumToneBands behind)."""
+    if int(got["present"]) != int(want["present"]):
+        return "present"
+    if not want["present"]:
+        return None
+    for k in ("num_tone_bands", "second_is_leader"):
+        if int(got[k]) != int(want[k]):
+            return k
+    ntb = int(want["num_tone_bands"])
+    if C == 2 and not np.array_equal(got["tone_sharing"][:ntb] != 0, want["tone_sharing"][:ntb] != 0):
+        return "tone_sharing"
+    for ch in range(C):
+        if int(got["n_sb"][ch]) != int(want["n_sb"][ch]):
+            return f"n_sb[{ch}]"
+        for sb in range(ntb):
+            if ch == 1 and want["tone_sharing"][sb]:
+                continue
+            g, w = got["sb"][ch][sb], want["sb"][ch][sb]
+            if int(g[1]) != int(w[1]) or (int(w[1]) and int(g[0]) != int(w[0])) or (int(w[1]) and not np.array_equal(g[2:], w[2:])):
+                return f"sb[{ch}][{sb}] {g.tolist()} vs {w.tolist()}"
+            n, i0 = int(w[1]), int(w[0])
+            if not np.array_equal(got["params"][ch][i0:i0 + n], want["params"][ch][i0:i0 + n]):
+                return f"params[{ch}] sb {sb}: {got['params'][ch][i0:i0 + n].tolist()} vs {want['params'][ch][i0:i0 + n].tolist()}"
+    return None
+
+
+def check_at3p_gha(lib, S=2, F=4, C=2, seed=980):
+    """The tone search (DoAnalize without the filter) against the reference's GHA results, frame by frame."""
+    if tl.ref_lib() is None:
+        return 0
+    pcm = _at3p_signal(S, F + 1, C, seed)
+    bands = at3p_stage_pqf(lib, pcm, S, C, F + 1)
+    got = at3p_stage_gha(lib, bands, S, C, F + 1)
+    for s in range(S):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        assert st["n"] == F
+        for f in range(F):
+            why = _tone_records_equal(got[s, f], st["gha"][f], C)
+            assert why is None, f"stream {s} frame {f}: {why}"
+    return S
+
+
+def check_at3p_full_chain(lib, S=2, F=6, C=2, seed=990):
+    """PCM -> PQF -> tone search -> tone filter -> MDCT -> packer, every stage on the device kernels,
+    == the frames of the reference encoder (fresh streams)."""
+    if tl.ref_lib() is None:
+        return 0
+    pcm = _at3p_signal(S, F + 1, C, seed)
+    bands = at3p_stage_pqf(lib, pcm, S, C, F + 1)                        # [S][C][F+1][2048]
+    tones = at3p_stage_gha(lib, bands, S, C, F + 1)                      # [S][F+1]; call o+1 analyses frame o
+    for s in range(S):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        assert st["n"] == F
+        gha = tones[s, :F]
+        work = np.zeros((F, C, 2048), np.float32)                        # output o encodes PQF frame o-1
+        work[1:] = bands[s].transpose(1, 0, 2)[:F - 1]
+        resid = at3p_stage_tone_filter(lib, work, _shift(gha, 2), _shift(gha, 1), gha, C)
+        specs = at3p_stage_mdct(lib, resid.transpose(1, 0, 2)[None], 1, C, F)[0]
+        frames = at3p_stage_pack(lib, specs, _shift(gha, 1), C)
+        bad = np.argwhere((frames != st["frames"]).any(-1))
+        assert bad.size == 0, f"stream {s}: differing frames {bad[:4].ravel().tolist()}"
+    return S

@@ -37,3 +37,12 @@ def test_chain_after_gha(emu_lib):
 def test_trig_replicas_match_libm(emu_lib):
     """glibc_trig.cuh (compiled for the host by the emulator build) against the live libm."""
     pc.check_trig_replicas(emu_lib, n=200000)
+
+
+def test_gha_search(emu_lib):
+    pc.check_at3p_gha(emu_lib, S=2, F=3, C=2)
+
+
+def test_full_chain(emu_lib):
+    pc.check_at3p_full_chain(emu_lib, S=2, F=5, C=2)
+    pc.check_at3p_full_chain(emu_lib, S=1, F=4, C=1, seed=995)

@@ -37,3 +37,13 @@ def test_tone_filter(gpu_lib):
 def test_chain_after_gha(gpu_lib):
     pc.check_at3p_chain_after_gha(gpu_lib, S=6, F=20, C=2)
     pc.check_at3p_chain_after_gha(gpu_lib, S=2, F=10, C=1, seed=975)
+
+
+def test_gha_search(gpu_lib):
+    pc.check_at3p_gha(gpu_lib, S=8, F=16, C=2)
+    pc.check_at3p_gha(gpu_lib, S=3, F=10, C=1, seed=985)
+
+
+def test_full_chain(gpu_lib):
+    pc.check_at3p_full_chain(gpu_lib, S=6, F=16, C=2)
+    pc.check_at3p_full_chain(gpu_lib, S=2, F=8, C=1, seed=995)

@@ -594,10 +594,10 @@ constexpr int kGhaThreads = 64;           // 4 frames per block
 
 __global__ void __launch_bounds__(kGhaThreads) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
                                                                        const float* __restrict__ bands,
-                                                                       int S, int C, int F, TaskScratch* scratch,
+                                                                       int S, int C, int F, int L, int j0, TaskScratch* scratch,
                                                                        GhaFrameOut* out)
 {
-    // bands [S][C][F][2048]; frame (s, f) analyses bands[s][c][f] with look-ahead bands[s][c][f+1] (zeros past the end)
+    // bands [S][C][L][2048]; analysis (s, f), f < F, reads frame j0 + f with look-ahead frame j0 + f + 1 (zeros past L)
     __shared__ SbState state[kGhaThreads / kGhaTask][2][kGhaSb];
     __shared__ Staged staged[kGhaThreads / kGhaTask][kGhaTask];
     __shared__ int s_total[kGhaThreads / kGhaTask], s_go[kGhaThreads / kGhaTask];
@@ -611,8 +611,8 @@ __global__ void __launch_bounds__(kGhaThreads) at3p_gha_search_kernel(const GhaT
         const long long frame = base + slot;
         const bool live = frame < n_frames && ch < C;
         const int s = live ? (int)(frame / F) : 0, f = live ? (int)(frame % F) : 0;
-        const float* src = bands + (((size_t)s * C + (live ? ch : 0)) * F + f) * kFrame + sb * kSbSamples;
-        const bool has_next = f + 1 < F;
+        const float* src = bands + (((size_t)s * C + (live ? ch : 0)) * L + j0 + f) * kFrame + sb * kSbSamples;
+        const bool has_next = j0 + f + 1 < L;
         float next_src[64];
         SbState& me = state[slot][ch][sb];
         if (live) {
@@ -735,14 +735,14 @@ ATDE_D void adjust_envelope(int* env /*[2]*/, unsigned src_first, unsigned src_s
 }
 
 __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const GhaFrameOut* __restrict__ in,
-                                       int S, int C, int F, GhaHistory* hist_state, ToneBlock* out)
+                                       int S, int C, int F, GhaHistory* hist_state, ToneBlock* out, int out_stride, int out_off)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     GhaHistory h = hist_state[s];
     for (int f = 0; f < F; f++) {
         const GhaFrameOut& o = in[(size_t)s * F + f];
-        ToneBlock& tb = out[(size_t)s * F + f];
+        ToneBlock& tb = out[(size_t)s * out_stride + out_off + f];
         tb.present = 0; tb.num_tone_bands = 0; tb.second_is_leader = 0;
         tb.n_sb[0] = tb.n_sb[1] = 0; tb.n_params[0] = tb.n_params[1] = 0;
         for (int i = 0; i < 16; i++) tb.tone_sharing[i] = 0;
@@ -810,6 +810,27 @@ __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const Gh
     hist_state[s] = h;
 }
 
+size_t gha_scratch_bytes(int blocks) { return (size_t)blocks * kGhaThreads * sizeof(TaskScratch); }
+size_t gha_frame_out_bytes() { return sizeof(GhaFrameOut); }
+size_t gha_history_bytes() { return sizeof(GhaHistory); }
+int gha_blocks_for(long long n_analyses)
+{
+    long long b = (n_analyses + kGhaThreads / kGhaTask - 1) / (kGhaThreads / kGhaTask);
+    if (b > 148 * 8) b = 148 * 8;
+    return (int)(b < 1 ? 1 : b);
+}
+void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)
+{
+    ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
+                (TaskScratch*)scratch, (GhaFrameOut*)frame_out);
+}
+void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_state, ToneBlock* tones, int stride, int off, cudaStream_t st)
+{
+    ATDE_LAUNCH(at3p_gha_result_kernel, (unsigned)((S + 63) / 64), 64, 0, st, gha_tables(), (const GhaFrameOut*)frame_out, S, C, nA,
+                (GhaHistory*)hist_state, tones, stride, off);
+}
+bool gha_tables_ready() { return gha_tables() != nullptr; }
+
 } // namespace at3p
 } // namespace atde
 
@@ -838,8 +859,8 @@ extern "C" int atde_at3p_stage_gha(const float* bands, int S, int C, int F, void
                 cudaMemset(d_hist, 0, (size_t)S * sizeof(GhaHistory)) != cudaSuccess ||
                 cudaMemset(d_out, 0, (size_t)n_frames * sizeof(GhaFrameOut)) != cudaSuccess)) rc = -2;
     if (!rc) {
-        ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, (cudaStream_t) nullptr, G, (const float*)d_bands, S, C, F, d_scr, d_out);
-        ATDE_LAUNCH(at3p_gha_result_kernel, (unsigned)((S + 63) / 64), 64, 0, (cudaStream_t) nullptr, G, (const GhaFrameOut*)d_out, S, C, F, d_hist, d_tb);
+        ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, (cudaStream_t) nullptr, G, (const float*)d_bands, S, C, F, F, 0, d_scr, d_out);
+        ATDE_LAUNCH(at3p_gha_result_kernel, (unsigned)((S + 63) / 64), 64, 0, (cudaStream_t) nullptr, G, (const GhaFrameOut*)d_out, S, C, F, d_hist, d_tb, F, 0);
         if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = -2;
     }
     if (!rc && cudaMemcpy(tones, d_tb, (size_t)n_frames * sizeof(ToneBlock), cudaMemcpyDeviceToHost) != cudaSuccess) rc = -2;

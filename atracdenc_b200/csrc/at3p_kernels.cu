@@ -128,8 +128,8 @@ ATDE_D void dct4_16(const float* in, float* out)
     for (int i = 0; i < 16; i++) out[i] = -buf[i + 8];
 }
 
-__global__ void __launch_bounds__(256) at3p_pqf_kernel(const float* __restrict__ pcm, float* __restrict__ bands,
-                                                        int S, int C, int F)
+__global__ void __launch_bounds__(256) at3p_pqf_kernel(const float* __restrict__ pcm, const float* __restrict__ pcm_tail,
+                                                        float* __restrict__ bands, int S, int C, int F, int L, int joff)
 {
     __shared__ float xs[2][kPqfTilePad];
     const int f = blockIdx.x, s = blockIdx.y;
@@ -146,6 +146,10 @@ __global__ void __launch_bounds__(256) at3p_pqf_kernel(const float* __restrict__
             } else {
                 v0 = src[n];
             }
+        } else if (pcm_tail) {                                        // the last 368 samples of the previous batch
+            const float* tl = pcm_tail + ((size_t)s * kPqfOverlap + (size_t)(n + kPqfOverlap)) * C;
+            v0 = tl[0];
+            if (C == 2) v1 = tl[1];
         }
         xs[0][pphys(t)] = v0;
         xs[1][pphys(t)] = v1;
@@ -176,15 +180,15 @@ __global__ void __launch_bounds__(256) at3p_pqf_kernel(const float* __restrict__
     }
     float res[16];
     dct4_16(yy, res);
-    float* out = bands + (((size_t)s * C + ch) * F + f) * kFrame + i;
+    float* out = bands + (((size_t)s * C + ch) * L + joff + f) * kFrame + i;
 #pragma unroll
     for (int sb = 0; sb < 16; sb++) out[sb * kSbSamples] = res[15 - sb];
 }
 
-void launch_pqf(const float* pcm, float* bands, int S, int C, int F, cudaStream_t st)
+void launch_pqf(const float* pcm, const float* pcm_tail, float* bands, int S, int C, int F, int L, int joff, cudaStream_t st)
 {
     dim3 grid(F, S);
-    ATDE_LAUNCH(at3p_pqf_kernel, grid, 256, 0, st, pcm, bands, S, C, F);
+    ATDE_LAUNCH(at3p_pqf_kernel, grid, 256, 0, st, pcm, pcm_tail, bands, S, C, F, L, joff);
 }
 
 // =====================================================================================
@@ -264,14 +268,17 @@ __global__ void __launch_bounds__(128) at3p_tone_filter_kernel(const DevTables* 
                                                                 const ToneBlock* __restrict__ tb_old,
                                                                 const ToneBlock* __restrict__ tb_now,
                                                                 const ToneBlock* __restrict__ tb_next,
-                                                                float* __restrict__ resid, int units, int C)
+                                                                float* __restrict__ resid, int units, int C, FilterLayout lay)
 {
     const int u = blockIdx.x / C, ch = blockIdx.x % C, i = threadIdx.x;
-    const ToneBlock* old = tb_old + u;
-    const ToneBlock* now = tb_now + u;
-    const ToneBlock* next = tb_next + u;
-    const float* in = bands + ((size_t)u * C + ch) * kFrame;
-    float* out = resid + ((size_t)u * C + ch) * kFrame;
+    // unit u = (stream s, output q); flat layout: fo = units, everything indexed by u
+    const int s = u / lay.fo, q = u % lay.fo;
+    const size_t ti = (size_t)s * lay.tone_stride + q;
+    const ToneBlock* old = tb_old + ti;
+    const ToneBlock* now = tb_now + ti;
+    const ToneBlock* next = tb_next + ti;
+    const float* in = bands + (((size_t)s * C + ch) * lay.in_frames + lay.in_off + q) * kFrame;
+    float* out = resid + (((size_t)s * C + ch) * lay.out_frames + lay.out_off + q) * kFrame;
     const bool any = now->present || next->present;                    // tones_present || prev tones_present
     for (int sb = 0; sb < kSubbands; sb++) {
         float x = in[sb * kSbSamples + i];
@@ -300,9 +307,9 @@ __global__ void __launch_bounds__(128) at3p_tone_filter_kernel(const DevTables* 
 }
 
 void launch_tone_filter(const DevTables* T, const float* bands, const ToneBlock* tb_old, const ToneBlock* tb_now,
-                        const ToneBlock* tb_next, float* resid, int units, int C, cudaStream_t st)
+                        const ToneBlock* tb_next, float* resid, int units, int C, const FilterLayout& lay, cudaStream_t st)
 {
-    ATDE_LAUNCH(at3p_tone_filter_kernel, (unsigned)(units * C), 128, 0, st, T, bands, tb_old, tb_now, tb_next, resid, units, C);
+    ATDE_LAUNCH(at3p_tone_filter_kernel, (unsigned)(units * C), 128, 0, st, T, bands, tb_old, tb_now, tb_next, resid, units, C, lay);
 }
 
 // =====================================================================================
@@ -322,7 +329,7 @@ constexpr int kPmOutStride = 136;                    // floats per band in the o
 
 __global__ void __launch_bounds__(kPmWarps * 32, 6) at3p_mdct_kernel(const DevTables* __restrict__ T,
                                                                       const float* __restrict__ resid,
-                                                                      float* __restrict__ specs, int S, int C, int F)
+                                                                      float* __restrict__ specs, int S, int C, int F, int lead)
 {
     __shared__ __align__(16) float tile[kPmWarps][8 * kPmBandStride];
     __shared__ __align__(16) float s_sincos[128];
@@ -340,7 +347,8 @@ __global__ void __launch_bounds__(kPmWarps * 32, 6) at3p_mdct_kernel(const DevTa
         const int c = (int)(unit % C);
         const long long sf = unit / C;
         const int f = (int)(sf % F), s = (int)(sf / F);
-        const float* cur = resid + (((size_t)s * C + c) * F + f) * kFrame;
+        // resid [S][C][lead + F][2048]: with lead = 1 frame 0 is the residual the previous batch ended with
+        const float* cur = resid + (((size_t)s * C + c) * (F + lead) + f + lead) * kFrame;
         float* const outp = specs + (size_t)unit * kFrame;
 #pragma unroll 1
         for (int it = 0; it < 2; it++) {                     // subbands 8 it .. 8 it + 7
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(kPmWarps * 32, 6) at3p_mdct_kernel(const DevTa
                 const int band = w >> 5, i0 = 4 * (w & 31);
                 const float4 x = *reinterpret_cast<const float4*>(cur + (8 * it + band) * kSbSamples + i0);
                 float4 y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (f > 0) y = *reinterpret_cast<const float4*>(cur - kFrame + (8 * it + band) * kSbSamples + i0);
+                if (f + lead > 0) y = *reinterpret_cast<const float4*>(cur - kFrame + (8 * it + band) * kSbSamples + i0);
                 const float4 wf = *reinterpret_cast<const float4*>(&s_win[i0]);
                 const float4 wb = *reinterpret_cast<const float4*>(&s_win[124 - i0]);
                 float* in = tl + band * kPmBandStride;
@@ -432,12 +440,12 @@ __global__ void __launch_bounds__(kPmWarps * 32, 6) at3p_mdct_kernel(const DevTa
     }
 }
 
-void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, int C, int F, cudaStream_t st)
+void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, int C, int F, int lead, cudaStream_t st)
 {
     const long long n_units = (long long)S * F * C;
     long long blocks = (n_units + kPmWarps - 1) / kPmWarps;
     if (blocks > 148 * 6 * 4) blocks = 148 * 6 * 4;
-    ATDE_LAUNCH(at3p_mdct_kernel, (unsigned)blocks, kPmWarps * 32, 0, st, T, resid, specs, S, C, F);
+    ATDE_LAUNCH(at3p_mdct_kernel, (unsigned)blocks, kPmWarps * 32, 0, st, T, resid, specs, S, C, F, lead);
 }
 
 // =====================================================================================
@@ -628,7 +636,8 @@ ATDE_D unsigned warp_incl_scan(unsigned v, int lane)
 __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTables* __restrict__ T,
                                                                      const float* __restrict__ specs,
                                                                      const ToneBlock* __restrict__ tones,
-                                                                     unsigned char* __restrict__ frames, int units, int C)
+                                                                     unsigned char* __restrict__ frames, int units, int C,
+                                                                     int fo, int tone_stride)
 {
     __shared__ PackSm sm[kPackWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -686,7 +695,7 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
     }
     __syncwarp();
     // ---- TTonalComponentEncoder::Encode (:611-669), once: its buffer survives the Repeat rounds
-    const ToneBlock* tb = tones + unit;
+    const ToneBlock* tb = tones + (size_t)(unit / fo) * tone_stride + unit % fo;   // unit = (stream, output)
     int tonal_bits = 0;
     if (lane == 0) {
         unsigned* w = sh.twords;
@@ -810,10 +819,10 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
 }
 
 void launch_pack(const DevTables* T, const float* specs, const ToneBlock* tones, unsigned char* frames,
-                 int units, int C, cudaStream_t st)
+                 int units, int C, int fo, int tone_stride, cudaStream_t st)
 {
     ATDE_LAUNCH(at3p_pack_kernel, (unsigned)((units + kPackWarps - 1) / kPackWarps), kPackWarps * 32, 0, st,
-                T, specs, tones, frames, units, C);
+                T, specs, tones, frames, units, C, fo, tone_stride);
 }
 
 } // namespace at3p
@@ -840,7 +849,7 @@ extern "C" int atde_at3p_stage_pqf(const float* pcm, int S, int C, int F, float*
     ScopedDev<float> d_in, d_out;
     if (!d_in.alloc(n) || !d_out.alloc(n)) return -3;
     if (cudaMemcpy(d_in.p, pcm, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
-    launch_pqf(d_in.p, d_out.p, S, C, F, nullptr);
+    launch_pqf(d_in.p, nullptr, d_out.p, S, C, F, F, 0, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     return cudaMemcpy(bands, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
@@ -854,7 +863,7 @@ extern "C" int atde_at3p_stage_mdct(const float* resid, int S, int C, int F, flo
     ScopedDev<float> d_in, d_out;
     if (!d_in.alloc(n) || !d_out.alloc(n)) return -3;
     if (cudaMemcpy(d_in.p, resid, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
-    launch_mdct(T, d_in.p, d_out.p, S, C, F, nullptr);
+    launch_mdct(T, d_in.p, d_out.p, S, C, F, 0, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     return cudaMemcpy(specs, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
@@ -873,7 +882,7 @@ extern "C" int atde_at3p_stage_pack(const float* specs, const void* tones, int u
     if (!d_in.alloc(n) || !d_t.alloc((size_t)units) || !d_out.alloc((size_t)units * kFrameBytes)) return -3;
     if (cudaMemcpy(d_in.p, specs, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
     if (cudaMemcpy(d_t.p, tones, (size_t)units * sizeof(ToneBlock), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
-    launch_pack(T, d_in.p, d_t.p, d_out.p, units, C, nullptr);
+    launch_pack(T, d_in.p, d_t.p, d_out.p, units, C, 1, 1, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     return cudaMemcpy(frames, d_out.p, (size_t)units * kFrameBytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
@@ -894,7 +903,10 @@ extern "C" int atde_at3p_stage_tone_filter(const float* bands, const void* tb_ol
         if (cudaMemcpy(d_t[k].p, src[k], (size_t)units * sizeof(ToneBlock), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
     }
     if (cudaMemcpy(d_in.p, bands, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
-    launch_tone_filter(T, d_in.p, d_t[0].p, d_t[1].p, d_t[2].p, d_out.p, units, C, nullptr);
+    // flat test layout [U][C][2048]: one "stream" per unit with a single frame
+    FilterLayout lay;
+    lay.fo = 1; lay.tone_stride = 1; lay.in_frames = 1; lay.in_off = 0; lay.out_frames = 1; lay.out_off = 0;
+    launch_tone_filter(T, d_in.p, d_t[0].p, d_t[1].p, d_t[2].p, d_out.p, units, C, lay, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     return cudaMemcpy(resid, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }

@@ -59,19 +59,54 @@ struct ToneBlock {
 
 const DevTables* device_tables();     // builds + uploads on first use; nullptr on failure
 
+// where a unit's data lives when the kernels run inside the streaming pipeline (at3p_pipeline.cu):
+// unit = (stream s, output q), q < fo
+struct FilterLayout {
+    int fo;                           // outputs per stream
+    int tone_stride;                  // ToneBlock records per stream; the three tone pointers are pre-offset
+    int in_frames, in_off;            // bands  [S][C][in_frames][2048], unit frame = in_off + q
+    int out_frames, out_off;          // resid  [S][C][out_frames][2048], unit frame = out_off + q
+};
+
 // pcm [S][F*2048][C] interleaved -> bands [S][C][F][16][128]; every stream starts with a zero history
-void launch_pqf(const float* pcm, float* bands, int S, int C, int F, cudaStream_t st);
+// pcm_tail: [S][368][C] samples preceding the batch (nullptr = zeros); bands [S][C][L][2048], frame f lands at joff + f
+void launch_pqf(const float* pcm, const float* pcm_tail, float* bands, int S, int C, int F, int L, int joff, cudaStream_t st);
 // Tone filter + MDCT input scaling (TGhaProcessorBase::ApplyFilter, at3p_gha.cpp:581-687;
 // ff_atrac3p_generate_tones, ff/atrac3plusdsp.c:130-204; at3p.cpp:147-153): for unit u, frame bands
 // [U][C][16][128] minus the tones of tb_now[u] / tb_next[u] (envelopes also need tb_old[u]) -> resid, same layout
 void launch_tone_filter(const DevTables* T, const float* bands, const ToneBlock* tb_old, const ToneBlock* tb_now,
-                        const ToneBlock* tb_next, float* resid, int units, int C, cudaStream_t st);
+                        const ToneBlock* tb_next, float* resid, int units, int C, const FilterLayout& lay, cudaStream_t st);
 // resid [S][C][F][16][128] (already scaled to the MDCT's input range) -> specs [S][F][C][2048];
 // every stream starts with a zero overlap history
-void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, int C, int F, cudaStream_t st);
+void launch_mdct(const DevTables* T, const float* resid, float* specs, int S, int C, int F, int lead, cudaStream_t st);
 // specs [U][C][2048], tones [U] -> frames [U][2048]
+// tones of unit (s, q) = tones[s * tone_stride + q]
 void launch_pack(const DevTables* T, const float* specs, const ToneBlock* tones, unsigned char* frames,
-                 int units, int C, cudaStream_t st);
+                 int units, int C, int fo, int tone_stride, cudaStream_t st);
+
+// tone search (at3p_gha.cu)
+bool gha_tables_ready();
+size_t gha_scratch_bytes(int blocks);
+size_t gha_frame_out_bytes();
+size_t gha_history_bytes();
+int gha_blocks_for(long long n_analyses);
+// analyses (s, f), f < nA, of band frames j0 + f (look-ahead j0 + f + 1) of bands [S][C][L][2048] -> frame_out [S][nA]
+void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st);
+// per-stream FillResultBuf + history carry: frame_out [S][nA] -> tones[s * stride + off + f]
+void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_state, ToneBlock* tones, int stride, int off, cudaStream_t st);
+
+// streaming pipeline (at3p_pipeline.cu): the body of TAt3PEnc::TImpl::EncodeFrame for S streams x N calls
+struct StreamState;                   // per-handle carried state
+StreamState* pipeline_create(int C);
+void pipeline_destroy(StreamState*);
+void pipeline_reset(StreamState*);
+// Encodes N new frames per stream (d_pcm [S][N*2048][C]) continuing streams s0 .. s0+S-1 of `total_streams`;
+// writes n_out = N (N - 1 on the first batch) frames per stream to d_out [S][n_out][2048].  Returns 0 or a
+// negative status with *err set.
+int pipeline_run(StreamState*, const float* d_pcm, int s0, int S, int total_streams, long long N, bool started,
+                 unsigned char* d_out, cudaStream_t st, int slot, long long* launches, const char** err);
+// call once per batch after every chunk was enqueued
+void pipeline_commit(StreamState*);
 
 } // namespace at3p
 } // namespace atde

@@ -6,6 +6,7 @@
 #include "atde_cuda.h"
 #include "at1_kernels.cuh"
 #include "at3_kernels.cuh"
+#include "at3p_kernels.cuh"
 #include "glibc_math.cuh"
 #include "host_tables.h"
 
@@ -89,6 +90,7 @@ struct atde_encoder {
     atde::at1::DevTables* d_at1_tab = nullptr;
     atde::at3::DevTables* d_at3_tab = nullptr;
     int at3_js = 0;
+    atde::at3p::StreamState* at3p = nullptr;    // ATRAC3plus: carried stream state + workspaces (at3p_pipeline.cu)
     // ATRAC3 stream state beyond hist / loud_state / started
     DevBuf<float> prevhalf, next_scale, ctx;
     Workspace ws[2];
@@ -449,6 +451,13 @@ int ensure_state(atde_encoder* e, int S)
     int rc;
     const int C = e->cfg.channels;
     const bool at3 = e->cfg.codec == ATDE_CODEC_ATRAC3;
+    if (e->cfg.codec == ATDE_CODEC_ATRAC3PLUS) {              // carried state lives in at3p_pipeline.cu
+        atde::at3p::pipeline_reset(e->at3p);
+        e->streams_started = false;
+        e->n_state_streams = S;
+        e->have_state = true;
+        return 0;
+    }
     if ((rc = e->hist.ensure((size_t)S * e->frame_samples * C * (at3 ? 2 : 1)))) return rc;
     if ((rc = e->loud_state.ensure(S))) return rc;
     if ((rc = e->started.ensure(S))) return rc;
@@ -494,11 +503,13 @@ int atde_create(const atde_settings* s, atde_encoder** out)
     if (!s || !out) return fail(ATDE_ERR_INVALID, "null argument");
     *out = nullptr;
     if (s->channels < 1 || s->channels > 2) return fail(ATDE_ERR_INVALID, "channels must be 1 or 2");
-    if (s->codec != ATDE_CODEC_ATRAC1 && s->codec != ATDE_CODEC_ATRAC3)
+    if (s->codec != ATDE_CODEC_ATRAC1 && s->codec != ATDE_CODEC_ATRAC3 && s->codec != ATDE_CODEC_ATRAC3PLUS)
         return fail(ATDE_ERR_UNSUPPORTED, "codec %d is not built yet", s->codec);
     const At3Container* cont = nullptr;
     if (s->codec == ATDE_CODEC_ATRAC1) {
         if (s->bfu_idx_const > 8) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..8");
+    } else if (s->codec == ATDE_CODEC_ATRAC3PLUS) {
+        // TAt3PEnc::TSettings defaults only (UseGha = GHA_ENABLED, src/atrac3p.h:34-57); no tunables in the ABI yet
     } else {
         if (s->bfu_idx_const > 32) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..32");
         cont = at3_container_for(s->bitrate);
@@ -518,6 +529,13 @@ int atde_create(const atde_settings* s, atde_encoder** out)
         e->units_per_frame = s->channels;
         e->unit_bytes = atde::at1::kUnitBytes;
         e->lookahead = 0;
+    } else if (s->codec == ATDE_CODEC_ATRAC3PLUS) {
+        e->frame_samples = atde::at3p::kFrame;
+        e->units_per_frame = 1;
+        e->unit_bytes = atde::at3p::kFrameBytes;
+        e->lookahead = 1;
+        e->at3p = atde::at3p::pipeline_create(s->channels);
+        if (!e->at3p) { delete e; return fail(ATDE_ERR_NOMEM, "host alloc"); }
     } else {
         e->frame_samples = 1024;
         e->units_per_frame = 1;
@@ -529,7 +547,10 @@ int atde_create(const atde_settings* s, atde_encoder** out)
         cudaError_t ce = cudaStreamCreateWithFlags(&e->ws[i].stream, cudaStreamNonBlocking);
         if (ce != cudaSuccess) { delete e; return fail(ATDE_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
     }
-    int rc = s->codec == ATDE_CODEC_ATRAC1 ? build_at1_tables(e) : build_at3_tables(e);
+    int rc = 0;
+    if (s->codec == ATDE_CODEC_ATRAC1) rc = build_at1_tables(e);
+    else if (s->codec == ATDE_CODEC_ATRAC3) rc = build_at3_tables(e);
+    else if (!atde::at3p::device_tables() || !atde::at3p::gha_tables_ready()) rc = fail(ATDE_ERR_CUDA, "ATRAC3plus table upload failed");
     if (rc) { atde_destroy(e); return rc; }
     *out = e;
     return 0;
@@ -546,6 +567,7 @@ void atde_destroy(atde_encoder* e)
     }
     e->hist.release(); e->loud_state.release(); e->started.release();
     e->prevhalf.release(); e->next_scale.release(); e->ctx.release();
+    atde::at3p::pipeline_destroy(e->at3p);
     if (e->d_at1_tab) cudaFree(e->d_at1_tab);
     if (e->d_at3_tab) cudaFree(e->d_at3_tab);
     for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -567,6 +589,7 @@ int atde_reset(atde_encoder* e)
     e->have_state = false;
     e->n_state_streams = 0;
     e->streams_started = false;
+    atde::at3p::pipeline_reset(e->at3p);
     return 0;
 }
 
@@ -595,6 +618,16 @@ int atde_encode_batch_device(atde_encoder* e, const float* d_pcm, int32_t S, int
     int rc = ensure_state(e, S);
     if (rc) return rc;
     e->last_S = S; e->last_F = F;
+    if (e->cfg.codec == ATDE_CODEC_ATRAC3PLUS) {
+        const bool started = e->streams_started;
+        e->last_out = F - (started ? 0 : 1);
+        const char* why = "";
+        rc = atde::at3p::pipeline_run(e->at3p, d_pcm, 0, S, S, F, started, d_out, e->ws[0].stream, 0, &e->launches, &why);
+        if (rc) return fail(rc == -3 ? ATDE_ERR_NOMEM : ATDE_ERR_CUDA, "ATRAC3plus pipeline: %s (%s)", why, cudaGetErrorString(cudaGetLastError()));
+        atde::at3p::pipeline_commit(e->at3p);
+        e->streams_started = true;
+        return 0;
+    }
     if (e->cfg.codec == ATDE_CODEC_ATRAC3) {
         const bool started = e->streams_started;
         e->last_out = F - (started ? 0 : 1);
@@ -618,7 +651,8 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
     if (rc) return rc;
     e->last_S = S; e->last_F = F;
     const int C = e->cfg.channels;
-    const bool at3 = e->cfg.codec == ATDE_CODEC_ATRAC3;
+    const bool at3p = e->cfg.codec == ATDE_CODEC_ATRAC3PLUS;
+    const bool at3 = e->cfg.codec == ATDE_CODEC_ATRAC3 || at3p;      // one-frame look-ahead, fixed-size units
     const bool started = e->streams_started;
     const long long n_out = F - ((at3 && !started) ? 1 : 0);
     e->last_out = n_out;
@@ -643,7 +677,11 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
         if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return rc;
         CK(cudaMemcpyAsync(w.pcm.p, pcm + (size_t)s0 * pcm_per_stream, (size_t)n * pcm_per_stream * sizeof(float),
                            cudaMemcpyHostToDevice, w.stream));
-        if (at3) rc = run_at3(e, w, w.pcm.p, s0, n, F, started, w.out.p);
+        if (at3p) {
+            const char* why = "";
+            rc = atde::at3p::pipeline_run(e->at3p, w.pcm.p, s0, n, S, F, started, w.out.p, w.stream, slot, &e->launches, &why);
+            if (rc) return fail(rc == -3 ? ATDE_ERR_NOMEM : ATDE_ERR_CUDA, "ATRAC3plus pipeline: %s (%s)", why, cudaGetErrorString(cudaGetLastError()));
+        } else if (at3) rc = run_at3(e, w, w.pcm.p, s0, n, F, started, w.out.p);
         else rc = run_at1(e, w, w.pcm.p, s0, n, F, w.out.p, sizes ? w.sizes.p : nullptr);
         if (rc) return rc;
         if (out_per_stream)
@@ -657,6 +695,7 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
     CK(cudaStreamSynchronize(e->ws[1].stream));
     if (sizes && at3)                                  // every WriteFrame payload is exactly FrameSz bytes
         for (size_t i = 0; i < (size_t)S * units_per_stream; i++) sizes[i] = e->unit_bytes;
+    if (at3p) atde::at3p::pipeline_commit(e->at3p);
     e->streams_started = true;
     return 0;
 }

@@ -645,3 +645,39 @@ def check_at3p_full_chain(lib, S=2, F=6, C=2, seed=990):
         bad = np.argwhere((frames != st["frames"]).any(-1))
         assert bad.size == 0, f"stream {s}: differing frames {bad[:4].ravel().tolist()}"
     return S
+
+
+# ---------------------------------------------------------------------------------------------
+# ATRAC3plus through the C ABI (atde_create(ATDE_CODEC_ATRAC3PLUS))
+def check_at3p_vs_oracle(lib, S=3, F=7, C=2, seed=1200):
+    """Whole ATRAC3plus encoder through atde_encode_batch == the reference encoder's frames."""
+    pcm = _at3p_signal(S, F, C, seed)
+    enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
+    assert (enc.frame_samples, enc.units_per_frame, enc.unit_bytes, enc.lookahead) == (2048, 1, 2048, 1)
+    out = enc.encode(pcm, S)
+    enc.close()
+    assert out.shape == (S, F - 1, 1, 2048)
+    if tl.ref_lib() is None:
+        return 0
+    for s in range(S):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        assert st["n"] == F - 1
+        bad = np.argwhere((out[s, :, 0] != st["frames"]).any(-1))
+        assert bad.size == 0, f"stream {s}: differing frames {bad[:4].ravel().tolist()}"
+    return S
+
+
+def check_at3p_batch_split_invariance(lib, S=2, F=9, C=2, cuts=(1, 3, 2), seed=1300):
+    """Streams continue across calls (carried PQF history, two PQF frames, MDCT overlap, the last two GHA
+    results, envelope history): the pieces must equal one batch."""
+    pcm = _at3p_signal(S, F, C, seed)
+    enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
+    whole = enc.encode(pcm, S)
+    enc.reset()
+    parts, pos = [], 0
+    for n in list(cuts) + [F - sum(cuts)]:
+        parts.append(enc.encode(pcm[:, pos * 2048:(pos + n) * 2048], S))
+        pos += n
+    enc.close()
+    assert [p.shape[1] for p in parts] == [cuts[0] - 1] + list(cuts[1:]) + [F - sum(cuts)]
+    assert np.array_equal(np.concatenate(parts, axis=1), whole)

@@ -46,3 +46,13 @@ def test_gha_search(emu_lib):
 def test_full_chain(emu_lib):
     pc.check_at3p_full_chain(emu_lib, S=2, F=5, C=2)
     pc.check_at3p_full_chain(emu_lib, S=1, F=4, C=1, seed=995)
+
+
+def test_encoder_vs_oracle(emu_lib):
+    pc.check_at3p_vs_oracle(emu_lib, S=3, F=6, C=2)
+    pc.check_at3p_vs_oracle(emu_lib, S=1, F=5, C=1, seed=1210)
+
+
+def test_encoder_batch_split_invariance(emu_lib):
+    pc.check_at3p_batch_split_invariance(emu_lib, S=2, F=9, C=2)
+    pc.check_at3p_batch_split_invariance(emu_lib, S=1, F=7, C=1, cuts=(2, 1, 1), seed=1310)

@@ -47,3 +47,13 @@ def test_gha_search(gpu_lib):
 def test_full_chain(gpu_lib):
     pc.check_at3p_full_chain(gpu_lib, S=6, F=16, C=2)
     pc.check_at3p_full_chain(gpu_lib, S=2, F=8, C=1, seed=995)
+
+
+def test_encoder_vs_oracle(gpu_lib):
+    assert pc.check_at3p_vs_oracle(gpu_lib, S=8, F=24, C=2) in (0, 8)
+    pc.check_at3p_vs_oracle(gpu_lib, S=3, F=12, C=1, seed=1210)
+
+
+def test_encoder_batch_split_invariance(gpu_lib):
+    pc.check_at3p_batch_split_invariance(gpu_lib, S=4, F=20, C=2, cuts=(1, 7, 4))
+    pc.check_at3p_batch_split_invariance(gpu_lib, S=2, F=9, C=1, cuts=(2, 1, 3), seed=1310)

@@ -126,4 +126,23 @@ TPCMEngine::TProcessLambda TAtrac3Encoder::GetLambda()
     return [this](float* data, const TPCMEngine::ProcessMeta& /*meta*/) { return Push(data); };
 }
 
+static atde_settings MakeAt3pSettings(int channels, const TAt3PEnc::TSettings& s)
+{
+    if (s.UseGha != TAt3PEnc::TSettings::GHA_ENABLED)
+        throw std::runtime_error("atde_b200: only the default ATRAC3plus GHA settings are built (ghadbg=7)");
+    atde_settings c;
+    atde_default_settings(&c, ATDE_CODEC_ATRAC3PLUS, (int32_t)channels);
+    return c;
+}
+
+TAt3PEnc::TAt3PEnc(TCompressedOutputPtr&& out, int channels, TSettings settings)
+    : TBatchedEncoderBase(std::move(out), MakeAt3pSettings(channels, settings))
+{
+}
+
+TPCMEngine::TProcessLambda TAt3PEnc::GetLambda()
+{
+    return [this](float* data, const TPCMEngine::ProcessMeta& /*meta*/) { return Push(data); };
+}
+
 } // namespace NAtracDEnc

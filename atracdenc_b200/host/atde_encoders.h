@@ -3,6 +3,7 @@
 // semantics as
 //   NAtracDEnc::TAtrac1Encoder(TCompressedOutputPtr&&, NAtrac1::TAtrac1EncodeSettings&&)   src/atrac1denc.h:105
 //   NAtracDEnc::TAtrac3Encoder(TCompressedOutputPtr&&, NAtrac3::TAtrac3EncoderSettings&&)  src/atrac3denc.h:131
+//   NAtracDEnc::TAt3PEnc(TCompressedOutputPtr&&, int channels, TSettings)                  src/atrac3p.h:59
 // so `src/main.cpp`'s PrepareAtrac1Encoder / PrepareAtrac3Encoder / PCM loop (:292-340, :342-470,
 // :697-705) compile against it unchanged.  Differences a caller can observe: WriteFrame calls are DEFERRED — frames are staged
 // and encoded on the GPU in batches; payload bytes, lengths and call order are identical, and
@@ -98,6 +99,25 @@ class TAtrac3Encoder : public TBatchedEncoderBase {
 public:
     TAtrac3Encoder(TCompressedOutputPtr&& oma, NAtrac3::TAtrac3EncoderSettings&& encoderSettings);
     TPCMEngine::TProcessLambda GetLambda() override;
+};
+
+// ATRAC3plus (src/atrac3p.h:28-71).  The first lambda call returns LOOK_AHEAD (at3p.cpp:109-111), every
+// later one PROCESSED with one WriteFrame of 2048 bytes (at3p_bitstream.cpp:724-725).  Only the default
+// GHA settings (UseGha = GHA_ENABLED, subband refinement) are built; any other mask throws.
+class TAt3PEnc : public TBatchedEncoderBase {
+public:
+    struct TSettings {
+        enum GhaProcessingFlags : uint8_t {
+            GHA_PASS_INPUT = 1, GHA_WRITE_TONAL = 1 << 1, GHA_WRITE_RESIUDAL = 1 << 2, GHA_WIDEBAND = 1 << 3,
+            GHA_ENABLED = GHA_PASS_INPUT | GHA_WRITE_TONAL | GHA_WRITE_RESIUDAL
+        };
+        uint8_t UseGha;
+        uint8_t WidebandRefineMode;
+        TSettings() : UseGha(GHA_ENABLED), WidebandRefineMode(0) {}
+    };
+    TAt3PEnc(TCompressedOutputPtr&& out, int channels, TSettings settings);
+    TPCMEngine::TProcessLambda GetLambda() override;
+    static constexpr int NumSamples = 2048;
 };
 
 } // namespace NAtracDEnc

@@ -1,7 +1,7 @@
 // tests/host_shim_driver.cpp — drives the C++ host shim exactly like src/main.cpp:697-716 drives
 // the reference's processors: TPCMEngine(4096) + memory reader + GetLambda() loop, capturing the
 // WriteFrame payloads to a file.
-// usage: driver <pcm.f32> <channels> <total_samples> <out.bin> <batch_frames> [codec=1|3] [bitrate_kbit]
+// usage: driver <pcm.f32> <channels> <total_samples> <out.bin> <batch_frames> [codec=1|3|4] [bitrate_kbit]
 #include "../atracdenc_b200/host/atde_encoders.h"
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +56,10 @@ int main(int argc, char** argv)
         if (codec == 1) {
             proc.reset(new TAtrac1Encoder(std::move(sink),
                 NAtrac1::TAtrac1EncodeSettings(0, NAtrac1::TAtrac1EncodeSettings::EWindowMode::EWM_AUTO, 0)));
+        } else if (codec == 4) {
+            // src/main.cpp:478-482: TAt3PEnc(std::move(out), channels, settings)
+            proc.reset(new TAt3PEnc(std::move(sink), (int)ch, TAt3PEnc::TSettings()));
+            step = 2048;
         } else {
             // src/main.cpp:671: TAtrac3EncoderSettings(bitrate * 1024, noGainControl, noTonalComponents, channels, bfuIdxConst)
             proc.reset(new TAtrac3Encoder(std::move(sink),

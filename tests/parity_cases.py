@@ -344,7 +344,7 @@ def check_at3_errors(lib):
     with pytest.raises(ab.AtdeError):
         ab.Encoder(ab.CODEC_ATRAC3, 2, bitrate=400 * 1024, lib=lib)      # beyond the largest container
     with pytest.raises(ab.AtdeError):
-        ab.Encoder(ab.CODEC_ATRAC3PLUS, 2, lib=lib)
+        ab.Encoder(2, 2, lib=lib)                                        # no such codec
     enc = ab.Encoder(ab.CODEC_ATRAC3, 2, lib=lib)
     assert (enc.frame_samples, enc.units_per_frame, enc.unit_bytes, enc.lookahead) == (1024, 1, 384, 1)
     enc.close()

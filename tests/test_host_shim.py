@@ -43,6 +43,19 @@ def check(exe, tmp_path):
         assert np.array_equal(tl.pad_units(payload, sizes, 212), g["units"])
 
 
+def check_at3p(exe, tmp_path, seconds=0.6):
+    """TAt3PEnc mirror under main.cpp's PCM pump (incl. the look-ahead drain) against the reference."""
+    if tl.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    n = int(44100 * seconds)
+    pcm = tl.synth_rich((n + 2047) // 2048, 2048, 2, seed=71)[:n]
+    want, want_sizes = tl.ref_encode(4, 2, pcm.reshape(-1), total=n)
+    for batch in (3, 4096):
+        payload, sizes = run_driver(exe, pcm, 2, n, batch, tmp_path, codec=4)
+        assert np.array_equal(sizes, want_sizes)
+        assert np.array_equal(payload, want)
+
+
 def check_at3(exe, tmp_path, seconds=0.5):
     """TAtrac3Encoder mirror under main.cpp's PCM pump (incl. the look-ahead drain at the end of the
     input) against the reference encoder under the same pump."""
@@ -74,3 +87,12 @@ def test_host_shim_at3_gpu(tmp_path, gpu_lib):
 @pytest.mark.gpu
 def test_host_shim_gpu(tmp_path, gpu_lib):
     check(build_driver(ROOT / "atracdenc_b200" / "libatde_b200.so", "gpu"), tmp_path)
+
+
+def test_host_shim_at3p_cpu_emulated(tmp_path):
+    check_at3p(build_driver(tl.build_emu(), "emu"), tmp_path, seconds=0.4)
+
+
+@pytest.mark.gpu
+def test_host_shim_at3p_gpu(tmp_path, gpu_lib):
+    check_at3p(build_driver(ROOT / "atracdenc_b200" / "libatde_b200.so", "gpu"), tmp_path, seconds=2.0)

@@ -103,8 +103,16 @@ void pipeline_reset(StreamState*);
 // Encodes N new frames per stream (d_pcm [S][N*2048][C]) continuing streams s0 .. s0+S-1 of `total_streams`;
 // writes n_out = N (N - 1 on the first batch) frames per stream to d_out [S][n_out][2048].  Returns 0 or a
 // negative status with *err set.
+// optional per-kernel event timing supplied by the API layer; kinds: 0 PQF + MDCT, 2 scale/quantise/pack,
+// 3 tone search, 4 tone filter
+struct Profiler {
+    void* ctx = nullptr;
+    int (*begin)(void* ctx, cudaStream_t st, int kind) = nullptr;
+    void (*end)(void* ctx, cudaStream_t st, int idx) = nullptr;
+};
 int pipeline_run(StreamState*, const float* d_pcm, int s0, int S, int total_streams, long long N, bool started,
-                 unsigned char* d_out, cudaStream_t st, int slot, long long* launches, const char** err);
+                 unsigned char* d_out, cudaStream_t st, int slot, long long* launches, const char** err,
+                 const Profiler* prof = nullptr);
 // call once per batch after every chunk was enqueued
 void pipeline_commit(StreamState*);
 

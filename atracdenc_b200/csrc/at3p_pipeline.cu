@@ -83,8 +83,14 @@ void pipeline_commit(StreamState* st)
 #define PCK(call) do { if ((call) != cudaSuccess) { *err = #call; return -2; } } while (0)
 
 int pipeline_run(StreamState* st, const float* d_pcm, int s0, int S, int total, long long N64, bool started,
-                 unsigned char* d_out, cudaStream_t cs, int slot, long long* launches, const char** err)
+                 unsigned char* d_out, cudaStream_t cs, int slot, long long* launches, const char** err,
+                 const Profiler* prof)
 {
+    struct Scope {
+        const Profiler* p; cudaStream_t s; int idx = -1;
+        Scope(const Profiler* p_, cudaStream_t s_, int kind) : p(p_), s(s_) { if (p && p->begin) idx = p->begin(p->ctx, s, kind); }
+        ~Scope() { if (p && p->end && idx >= 0) p->end(p->ctx, s, idx); }
+    };
     const DevTables* T = device_tables();
     if (!T || !gha_tables_ready()) { *err = "ATRAC3plus table upload failed"; return -2; }
     const int C = st->C, N = (int)N64;
@@ -131,16 +137,19 @@ int pipeline_run(StreamState* st, const float* d_pcm, int s0, int S, int total, 
                           2 * sizeof(ToneBlock), (size_t)S, cudaMemcpyDeviceToDevice, cs));
     PCK(cudaMemcpy2DAsync(w.resid.p, (size_t)(nA + 1) * kFrame * sizeof(float), resid_prev, kFrame * sizeof(float),
                           kFrame * sizeof(float), (size_t)S * C, cudaMemcpyDeviceToDevice, cs));
-    launch_pqf(d_pcm, pcm_tail, w.bands.p, S, C, N, L, 2, cs);
+    { Scope sc(prof, cs, 0); launch_pqf(d_pcm, pcm_tail, w.bands.p, S, C, N, L, 2, cs); }
     *launches += 1;
     if (nA > 0) {
-        launch_gha_search(w.bands.p, S, C, nA, L, jA0, w.scratch.p, w.frame_out.p, gha_blocks, cs);
-        launch_gha_result(w.frame_out.p, S, C, nA, gha_hist, w.tones.p, TS, 2, cs);
+        {
+            Scope sc(prof, cs, 3);
+            launch_gha_search(w.bands.p, S, C, nA, L, jA0, w.scratch.p, w.frame_out.p, gha_blocks, cs);
+            launch_gha_result(w.frame_out.p, S, C, nA, gha_hist, w.tones.p, TS, 2, cs);
+        }
         FilterLayout lay;
         lay.fo = nA; lay.tone_stride = TS; lay.in_frames = L; lay.in_off = jW0; lay.out_frames = nA + 1; lay.out_off = 1;
-        launch_tone_filter(T, w.bands.p, w.tones.p, w.tones.p + 1, w.tones.p + 2, w.resid.p, S * nA, C, lay, cs);
-        launch_mdct(T, w.resid.p, w.specs.p, S, C, nA, 1, cs);
-        launch_pack(T, w.specs.p, w.tones.p + 1, d_out, S * nA, C, nA, TS, cs);
+        { Scope sc(prof, cs, 4); launch_tone_filter(T, w.bands.p, w.tones.p, w.tones.p + 1, w.tones.p + 2, w.resid.p, S * nA, C, lay, cs); }
+        { Scope sc(prof, cs, 0); launch_mdct(T, w.resid.p, w.specs.p, S, C, nA, 1, cs); }
+        { Scope sc(prof, cs, 2); launch_pack(T, w.specs.p, w.tones.p + 1, d_out, S * nA, C, nA, TS, cs); }
         *launches += 5;
     }
     // carry out

@@ -297,6 +297,26 @@ struct KernelTimer {
     ~KernelTimer() { if (idx >= 0) cudaEventRecord(e->ev_pool[idx].b, st); }
 };
 
+int at3p_prof_begin(void* ctx, cudaStream_t st, int kind)
+{
+    atde_encoder* e = (atde_encoder*)ctx;
+    if (!e->profiling) return -1;
+    if (e->ev_used == e->ev_pool.size()) {
+        atde_encoder::EvPair p;
+        if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return -1;
+        e->ev_pool.push_back(p);
+    }
+    const int idx = (int)e->ev_used++;
+    e->ev_pool[idx].kind = kind;
+    cudaEventRecord(e->ev_pool[idx].a, st);
+    return idx;
+}
+void at3p_prof_end(void* ctx, cudaStream_t st, int idx)
+{
+    atde_encoder* e = (atde_encoder*)ctx;
+    if (idx >= 0) cudaEventRecord(e->ev_pool[idx].b, st);
+}
+
 // Runs the ATRAC1 pipeline for `S` streams x F frames whose PCM is at d_pcm (device), first
 // stream index s0 inside the handle's state arrays.
 int run_at1(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, long long F,
@@ -622,7 +642,9 @@ int atde_encode_batch_device(atde_encoder* e, const float* d_pcm, int32_t S, int
         const bool started = e->streams_started;
         e->last_out = F - (started ? 0 : 1);
         const char* why = "";
-        rc = atde::at3p::pipeline_run(e->at3p, d_pcm, 0, S, S, F, started, d_out, e->ws[0].stream, 0, &e->launches, &why);
+        atde::at3p::Profiler prof;
+        prof.ctx = e; prof.begin = at3p_prof_begin; prof.end = at3p_prof_end;
+        rc = atde::at3p::pipeline_run(e->at3p, d_pcm, 0, S, S, F, started, d_out, e->ws[0].stream, 0, &e->launches, &why, &prof);
         if (rc) return fail(rc == -3 ? ATDE_ERR_NOMEM : ATDE_ERR_CUDA, "ATRAC3plus pipeline: %s (%s)", why, cudaGetErrorString(cudaGetLastError()));
         atde::at3p::pipeline_commit(e->at3p);
         e->streams_started = true;
@@ -679,7 +701,9 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
                            cudaMemcpyHostToDevice, w.stream));
         if (at3p) {
             const char* why = "";
-            rc = atde::at3p::pipeline_run(e->at3p, w.pcm.p, s0, n, S, F, started, w.out.p, w.stream, slot, &e->launches, &why);
+            atde::at3p::Profiler prof;
+            prof.ctx = e; prof.begin = at3p_prof_begin; prof.end = at3p_prof_end;
+            rc = atde::at3p::pipeline_run(e->at3p, w.pcm.p, s0, n, S, F, started, w.out.p, w.stream, slot, &e->launches, &why, &prof);
             if (rc) return fail(rc == -3 ? ATDE_ERR_NOMEM : ATDE_ERR_CUDA, "ATRAC3plus pipeline: %s (%s)", why, cudaGetErrorString(cudaGetLastError()));
         } else if (at3) rc = run_at3(e, w, w.pcm.p, s0, n, F, started, w.out.p);
         else rc = run_at1(e, w, w.pcm.p, s0, n, F, w.out.p, sizes ? w.sizes.p : nullptr);

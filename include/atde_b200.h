@@ -7,11 +7,13 @@
  *   - the frame-processor lambdas returned by IProcessor::GetLambda()  (src/pcmengin.h:195-199)
  *       TAtrac1Encoder::GetLambda   src/atrac1denc.cpp:180-255
  *       TAtrac3Encoder::GetLambda   src/atrac3denc.cpp:679-867
+ *       TAt3PEnc::GetLambda         src/atrac/at3p/at3p.cpp:202-206 (TImpl::EncodeFrame :88-194)
  *   - and, on the output side, produces exactly the byte vectors those lambdas hand to
  *       ICompressedOutput::WriteFrame(std::vector<char>)             (src/compressed_io.h:56-59)
  *     in the same order (ATRAC1: one 212-byte sound unit per channel per frame, channel 0 first,
  *     src/atrac/at1/atrac1_bitalloc.cpp:406; ATRAC3: one FrameSz-byte unit per frame,
- *     src/atrac/at3/atrac3_bitstream.cpp:845).
+ *     src/atrac/at3/atrac3_bitstream.cpp:845; ATRAC3plus: one 2048-byte unit per frame,
+ *     src/atrac/at3p/at3p_bitstream.cpp:724-725).
  *
  * Unit of work: a batch of S independent streams x F consecutive frames.  A "stream" is what
  * the reference calls one encoder instance.  Streams continue across calls (the handle keeps
@@ -42,7 +44,7 @@ typedef enum {
 typedef enum {
     ATDE_CODEC_ATRAC1 = 1,      /* -e atrac1        src/main.cpp:635-655 */
     ATDE_CODEC_ATRAC3 = 3,      /* -e atrac3 / atrac3_lp4  src/main.cpp:657-678 */
-    ATDE_CODEC_ATRAC3PLUS = 4   /* -e atrac3plus    src/main.cpp:679-686 */
+    ATDE_CODEC_ATRAC3PLUS = 4   /* -e atrac3plus    src/main.cpp:679-686; TAt3PEnc::TSettings defaults (GHA_ENABLED) only */
 } atde_codec;
 
 /* Mirrors the reference's settings objects field by field. */
@@ -67,7 +69,7 @@ typedef struct atde_encoder atde_encoder;
  * TAtrac3EncoderSettings(0, false, false, channels, 0)). */
 void atde_default_settings(atde_settings* s, int32_t codec, int32_t channels);
 
-/* Construct / destroy an encoder (== constructing TAtrac1Encoder / TAtrac3Encoder). */
+/* Construct / destroy an encoder (== constructing TAtrac1Encoder / TAtrac3Encoder / TAt3PEnc). */
 int atde_create(const atde_settings* s, atde_encoder** out);
 void atde_destroy(atde_encoder* e);
 
@@ -77,7 +79,7 @@ int atde_units_per_frame(const atde_encoder* e);   /* WriteFrame calls per lambd
 int atde_unit_bytes(const atde_encoder* e);        /* bytes stored per unit in `out` (container frame size) */
 int atde_lookahead_frames(const atde_encoder* e);  /* lambda calls that return LOOK_AHEAD before output starts (0 / 1) */
 /* Output frames per stream the NEXT batch of n_frames input frames will produce: n_frames, except
- * that the first batch of an ATRAC3 stream yields n_frames - 1 (the reference's first lambda call
+ * that the first batch of an ATRAC3 / ATRAC3plus stream yields n_frames - 1 (the reference's first lambda call
  * only fills the look-ahead buffer and returns LOOK_AHEAD, src/atrac3denc.cpp:715-718). */
 int64_t atde_output_frames(const atde_encoder* e, int64_t n_frames);
 

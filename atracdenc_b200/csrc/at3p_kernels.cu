@@ -831,7 +831,7 @@ void launch_pack(const DevTables* T, const float* specs, const ToneBlock* tones,
 // =====================================================================================
 // Stage entry points (host buffers in, host buffers out).  ATRAC3plus is not reachable through
 // atde_create() until the GHA stage exists; these let tests/ drive each finished kernel against the
-// reference's taps (oracle/ref_harness_at3p.cpp).  Declared in at3p_stage_api.h, not in include/.
+// reference's taps.  Declared in at3p_stage_api.h, not in include/.
 // =====================================================================================
 namespace {
 template <class T> struct ScopedDev {

@@ -367,7 +367,8 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
             const int col = dim + 1;
             for (int i = 0; i < dim; i++) {
                 const double Ai = (double)info[i].magnitude;
-                for (int j = 0; j < dim; j++) {
+                // M[i][j] and M[j][i] are the same sum of commutative products in the same order: compute j >= i, mirror
+                for (int j = i; j < dim; j++) {
                     const double Aj = (double)info[j].magnitude;
                     double acc = 0.0;
                     if (blk == 0) {
@@ -405,6 +406,7 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
                         }
                     }
                     M[i * col + j] = dmul(acc, 2.0);
+                    M[j * col + i] = M[i * col + j];
                 }
                 double r = 0.0;
                 for (int n = 0; n < sz; n++) {
@@ -592,7 +594,7 @@ ATDE_D bool sb_insert(SbState& s, unsigned key, const GhaInfo& v)     // map::in
 
 constexpr int kGhaThreads = 64;           // 4 frames per block
 
-__global__ void __launch_bounds__(kGhaThreads) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
+__global__ void __launch_bounds__(kGhaThreads, 8) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
                                                                        const float* __restrict__ bands,
                                                                        int S, int C, int F, int L, int j0, TaskScratch* scratch,
                                                                        GhaFrameOut* out)
@@ -816,7 +818,7 @@ size_t gha_history_bytes() { return sizeof(GhaHistory); }
 int gha_blocks_for(long long n_analyses)
 {
     long long b = (n_analyses + kGhaThreads / kGhaTask - 1) / (kGhaThreads / kGhaTask);
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > 148 * 8) b = 148 * 8;                     // one resident wave (launch bounds: 8 blocks per SM)
     return (int)(b < 1 ? 1 : b);
 }
 void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)

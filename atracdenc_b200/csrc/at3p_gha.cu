@@ -84,9 +84,7 @@ struct GhaFrameOut {
     unsigned env[2][kGhaSb][2];
 };
 
-struct TaskScratch {                      // global memory, one per resident task thread
-    float buf[128];                       // Buf[sb]: residual so far
-    float buf_new[128];
+struct TaskScratch {                      // global memory, one per resident thread: transient within a step
     float tmp[128];                       // libgha's ctx->tmp_buf (the Repeat call of gha_adjust_info reads its stale tail)
     float s[kMaxDim][128], c[kMaxDim][128];
     cpx fa[64];
@@ -474,12 +472,12 @@ ATDE_D bool check_next_frame(const GhaTables* G, const float* next_src, const Gh
 
 // One (channel, subband) step of DoRound computed from the start-of-round state into `st`.
 ATDE_D void task_step(const GhaTables* G, const SbState& sbs, int sb, const float* src, const float* next_src,
-                      TaskScratch* ws, Staged& st)
+                      const float* buf, float* buf_new, TaskScratch* ws, Staged& st)
 {
     st.part1 = 0; st.n_new = 0; st.resid_valid = 0; st.analyzed = 0; st.psy_ok = 0;
     st.env_first = sbs.env_first; st.env_second = sbs.env_second;
     st.last_res_energy = sbs.last_res_energy; st.gapless = sbs.gapless; st.max_mag = sbs.max_mag;
-    const float* analysis_src = ws->buf;
+    const float* analysis_src = buf;
     if (sbs.n > 0) {
         const int dim = sbs.n;
         GhaInfo tmp_info[kMaxDim];
@@ -528,7 +526,7 @@ ATDE_D void task_step(const GhaTables* G, const SbState& sbs, int sb, const floa
             if (st.env_second == kEmpty && end != 128) { status = 0; break; }
             st.env_second = end;
             status = 1;
-            for (int i = 0; i < 128; i++) ws->buf_new[i] = ws->tmp[i];
+            for (int i = 0; i < 128; i++) buf_new[i] = ws->tmp[i];
             st.resid_valid = 1;
             break;
         }
@@ -562,7 +560,7 @@ ATDE_D void task_step(const GhaTables* G, const SbState& sbs, int sb, const floa
             st.fit[i] = tmp_info[i];
             st.max_mag = fmaxf(st.max_mag, tmp_info[i].magnitude);
         }
-        if (st.resid_valid) analysis_src = ws->buf_new;
+        if (st.resid_valid) analysis_src = buf_new;
     }
     st.found = analyze_one(G, analysis_src, ws);
     st.analyzed = 1;
@@ -592,65 +590,91 @@ ATDE_D bool sb_insert(SbState& s, unsigned key, const GhaInfo& v)     // map::in
     return true;
 }
 
-constexpr int kGhaThreads = 64;           // 4 frames per block
+// The search kernel.  A block works on kGhaFB frames at a time.  Every round it compacts the (frame, channel,
+// subband) steps that still have work into a list and spreads that list over its threads — subbands and
+// frames need very different numbers of rounds, and a fixed step-per-lane mapping left three quarters of
+// the lanes idle — then one thread per frame commits that frame's staged steps in the reference's order.
+constexpr int kGhaFB = 32;                // frames per block batch
+constexpr int kGhaThreads = 128;
+constexpr int kGhaItems = kGhaFB * kGhaTask;
 
-__global__ void __launch_bounds__(kGhaThreads, 8) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
+struct ItemState {                        // global memory, per (frame slot, channel, subband) of a block
+    float buf[128];                       // Buf[sb]: residual so far
+    float buf_new[128];                   // staged residual of the running step
+    SbState sb;
+    Staged st;
+};
+
+__device__ float g_zero64[64];            // look-ahead of the last frame of a stage-test run
+
+__global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
                                                                        const float* __restrict__ bands,
-                                                                       int S, int C, int F, int L, int j0, TaskScratch* scratch,
-                                                                       GhaFrameOut* out)
+                                                                       int S, int C, int F, int L, int j0, TaskScratch* tscr,
+                                                                       ItemState* items_g, GhaFrameOut* out)
 {
     // bands [S][C][L][2048]; analysis (s, f), f < F, reads frame j0 + f with look-ahead frame j0 + f + 1 (zeros past L)
-    __shared__ SbState state[kGhaThreads / kGhaTask][2][kGhaSb];
-    __shared__ Staged staged[kGhaThreads / kGhaTask][kGhaTask];
-    __shared__ int s_total[kGhaThreads / kGhaTask], s_go[kGhaThreads / kGhaTask];
-    __shared__ unsigned char s_adopt[kGhaThreads / kGhaTask][kGhaTask];
-    const int slot = threadIdx.x / kGhaTask, t = threadIdx.x % kGhaTask;
-    const int ch = t >> 3, sb = t & 7;
+    __shared__ int s_total[kGhaFB], s_go[kGhaFB];
+    __shared__ unsigned short s_list[kGhaItems];
+    __shared__ unsigned char s_adopt[kGhaItems];
+    __shared__ int s_n;
+    const int tid = threadIdx.x;
     const long long n_frames = (long long)S * F;
-    TaskScratch* ws = scratch + (size_t)blockIdx.x * kGhaThreads + threadIdx.x;
-    for (long long base = (long long)blockIdx.x * (kGhaThreads / kGhaTask); base < n_frames;
-         base += (long long)gridDim.x * (kGhaThreads / kGhaTask)) {
-        const long long frame = base + slot;
-        const bool live = frame < n_frames && ch < C;
-        const int s = live ? (int)(frame / F) : 0, f = live ? (int)(frame % F) : 0;
-        const float* src = bands + (((size_t)s * C + (live ? ch : 0)) * L + j0 + f) * kFrame + sb * kSbSamples;
-        const bool has_next = j0 + f + 1 < L;
-        float next_src[64];
-        SbState& me = state[slot][ch][sb];
-        if (live) {
-            for (int i = 0; i < 128; i++) ws->buf[i] = src[i];
-            for (int i = 0; i < 64; i++) next_src[i] = has_next ? src[kFrame + i] : 0.0f;
+    TaskScratch* ws = tscr + (size_t)blockIdx.x * kGhaThreads + tid;
+    ItemState* items = items_g + (size_t)blockIdx.x * kGhaItems;
+    for (long long base = (long long)blockIdx.x * kGhaFB; base < n_frames; base += (long long)gridDim.x * kGhaFB) {
+        for (int idx = tid; idx < kGhaItems; idx += kGhaThreads) {
+            const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+            const bool live = base + fs < n_frames && ch < C;
+            SbState& me = items[idx].sb;
             me.n = 0;
             // pair<> Envelopes[SUBBANDS] = {{INIT, INIT}}: only element 0 gets INIT, the rest are value-initialised
             me.env_first = sb == 0 ? kInit : 0u;
             me.env_second = sb == 0 ? kInit : 0u;
-            me.gapless = 0; me.done = 0; me.max_mag = 0.0f; me.last_res_energy = 0.0f; me.last_added = 0;
-        } else {
-            me.n = 0; me.done = 16;
+            me.gapless = 0; me.done = live ? 0 : 16; me.max_mag = 0.0f; me.last_res_energy = 0.0f; me.last_added = 0;
+            s_adopt[idx] = 0;
         }
-        if (t == 0) { s_total[slot] = 0; s_go[slot] = frame < n_frames; }
-        s_adopt[slot][t] = 0;
+        for (int w = tid; w < kGhaItems * 32; w += kGhaThreads) {        // Buf[sb] = the subband's samples (float4 granules)
+            const int idx = w >> 5, q = w & 31;
+            const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+            const long long frame = base + fs;
+            if (frame < n_frames && ch < C) {
+                const int s = (int)(frame / F), f = (int)(frame % F);
+                const float* src = bands + (((size_t)s * C + ch) * L + j0 + f) * kFrame + sb * kSbSamples;
+                reinterpret_cast<float4*>(items[idx].buf)[q] = reinterpret_cast<const float4*>(src)[q];
+            }
+        }
+        if (tid < kGhaFB) { s_total[tid] = 0; s_go[tid] = base + tid < n_frames; }
         __syncthreads();
         for (;;) {
-            bool any_go = false;
-            for (int q = 0; q < kGhaThreads / kGhaTask; q++) any_go |= s_go[q] != 0;
-            if (!any_go) break;
+            if (tid == 0) s_n = 0;
             __syncthreads();
-            Staged& st = staged[slot][t];
-            const bool run = live && s_go[slot] && me.done != 16;
-            if (run) task_step(G, me, sb, src, next_src, ws, st);
+            for (int idx = tid; idx < kGhaItems; idx += kGhaThreads)
+                if (s_go[idx >> 4] && items[idx].sb.done != 16) s_list[atomicAdd(&s_n, 1)] = (unsigned short)idx;
             __syncthreads();
-            if (t == 0 && s_go[slot]) {
+            const int n_list = s_n;
+            if (n_list == 0) break;
+            for (int it = tid; it < n_list; it += kGhaThreads) {
+                const int idx = s_list[it];
+                const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+                const long long frame = base + fs;
+                const int s = (int)(frame / F), f = (int)(frame % F);
+                const float* src = bands + (((size_t)s * C + ch) * L + j0 + f) * kFrame + sb * kSbSamples;
+                const float* next_src = j0 + f + 1 < L ? src + kFrame : g_zero64;
+                task_step(G, items[idx].sb, sb, src, next_src, items[idx].buf, items[idx].buf_new, ws, items[idx].st);
+            }
+            __syncthreads();
+            if (tid < kGhaFB && s_go[tid]) {
                 // commit in the reference's order: channel 0 subbands 0..7, then channel 1
-                int total = s_total[slot];
+                const int fs = tid;
+                int total = s_total[fs];
                 bool progress[2] = {false, false};
                 for (int c2 = 0; c2 < C; c2++) {
                     bool prog = false;
                     for (int b2 = 0; b2 < kGhaSb; b2++) {
-                        SbState& z = state[slot][c2][b2];
+                        SbState& z = items[fs * 16 + c2 * 8 + b2].sb;
                         if (z.done == 16) continue;
                         if (total >= 48) { prog = false; break; }          // return false
-                        const Staged& g = staged[slot][c2 * 8 + b2];
+                        const Staged& g = items[fs * 16 + c2 * 8 + b2].st;
                         if (g.part1 != 0) {
                             // what CheckResuidalAndApply / the look-ahead test wrote, also on their failure paths
                             z.env_first = g.env_first; z.env_second = g.env_second;
@@ -666,7 +690,7 @@ __global__ void __launch_bounds__(kGhaThreads, 8) at3p_gha_search_kernel(const G
                                 z.max_mag = fmaxf(z.max_mag, g.fit[i].magnitude);
                                 sb_insert(z, freq_to_index(g.fit[i].frequency, (unsigned)b2), g.fit[i]);
                             }
-                            if (g.resid_valid) s_adopt[slot][c2 * 8 + b2] = 1;
+                            if (g.resid_valid) s_adopt[fs * 16 + c2 * 8 + b2] = 1;
                         }
                         const unsigned fi = freq_to_index(g.found.frequency, (unsigned)b2);
                         if (!g.psy_ok) { z.done = 16; continue; }
@@ -678,7 +702,7 @@ __global__ void __launch_bounds__(kGhaThreads, 8) at3p_gha_search_kernel(const G
                             unsigned next_key = 0, prev_key = 0;
                             bool has_nxt = false, has_prev = false;
                             for (int b3 = 0; b3 < kGhaSb; b3++) {
-                                const SbState& y = state[slot][c2][b3];
+                                const SbState& y = items[fs * 16 + c2 * 8 + b3].sb;
                                 for (int i = 0; i < y.n; i++) {
                                     if (y.key[i] >= fi) { if (!has_nxt) { has_nxt = true; next_key = y.key[i]; } }
                                     else { has_prev = true; prev_key = y.key[i]; }
@@ -696,28 +720,34 @@ __global__ void __launch_bounds__(kGhaThreads, 8) at3p_gha_search_kernel(const G
                     }
                     progress[c2] = prog;
                 }
-                s_total[slot] = total;
-                s_go[slot] = (progress[0] || progress[1]) && total < 48;
+                s_total[fs] = total;
+                s_go[fs] = (progress[0] || progress[1]) && total < 48;
             }
             __syncthreads();
             // adopt the staged residual where the callback accepted it and the step was committed
-            if (s_adopt[slot][t]) {
-                s_adopt[slot][t] = 0;
-                for (int i = 0; i < 128; i++) ws->buf[i] = ws->buf_new[i];
+            for (int w = tid; w < n_list * 32; w += kGhaThreads) {
+                const int idx = s_list[w >> 5], q = w & 31;
+                if (s_adopt[idx])
+                    reinterpret_cast<float4*>(items[idx].buf)[q] = reinterpret_cast<const float4*>(items[idx].buf_new)[q];
             }
             __syncthreads();
+            for (int it = tid; it < n_list; it += kGhaThreads) s_adopt[s_list[it]] = 0;
         }
-        if (frame < n_frames && live) {
-            GhaFrameOut& o = out[frame];
-            if (t == 0) o.total_tones = s_total[slot];
-            o.n[ch][sb] = me.n;
-            for (int i = 0; i < me.n; i++) { o.key[ch][sb][i] = me.key[i]; o.info[ch][sb][i] = me.info[i]; }
-            o.env[ch][sb][0] = me.env_first; o.env[ch][sb][1] = me.env_second;
+        for (int idx = tid; idx < kGhaItems; idx += kGhaThreads) {
+            const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+            const long long frame = base + fs;
+            if (frame < n_frames && ch < C) {
+                const SbState& me = items[idx].sb;
+                GhaFrameOut& o = out[frame];
+                if (t == 0) o.total_tones = s_total[fs];
+                o.n[ch][sb] = me.n;
+                for (int i = 0; i < me.n; i++) { o.key[ch][sb][i] = me.key[i]; o.info[ch][sb][i] = me.info[i]; }
+                o.env[ch][sb][0] = me.env_first; o.env[ch][sb][1] = me.env_second;
+            }
         }
         __syncthreads();
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // FillResultBuf / FillFolowerRes / AdjustEnvelope (at3p_gha.cpp:1499-1664) + the ResultBufHistory carry:
@@ -812,19 +842,20 @@ __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const Gh
     hist_state[s] = h;
 }
 
-size_t gha_scratch_bytes(int blocks) { return (size_t)blocks * kGhaThreads * sizeof(TaskScratch); }
+static size_t gha_thread_scratch_bytes(int blocks) { return ((size_t)blocks * kGhaThreads * sizeof(TaskScratch) + 255) / 256 * 256; }
+size_t gha_scratch_bytes(int blocks) { return gha_thread_scratch_bytes(blocks) + (size_t)blocks * kGhaItems * sizeof(ItemState); }
 size_t gha_frame_out_bytes() { return sizeof(GhaFrameOut); }
 size_t gha_history_bytes() { return sizeof(GhaHistory); }
 int gha_blocks_for(long long n_analyses)
 {
-    long long b = (n_analyses + kGhaThreads / kGhaTask - 1) / (kGhaThreads / kGhaTask);
-    if (b > 148 * 8) b = 148 * 8;                     // one resident wave (launch bounds: 8 blocks per SM)
+    long long b = (n_analyses + kGhaFB - 1) / kGhaFB;
+    if (b > 148 * 4) b = 148 * 4;                     // one resident wave (launch bounds: 4 blocks per SM)
     return (int)(b < 1 ? 1 : b);
 }
 void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)
 {
     ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
-                (TaskScratch*)scratch, (GhaFrameOut*)frame_out);
+                (TaskScratch*)scratch, (ItemState*)((unsigned char*)scratch + gha_thread_scratch_bytes(blocks)), (GhaFrameOut*)frame_out);
 }
 void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_state, ToneBlock* tones, int stride, int off, cudaStream_t st)
 {
@@ -840,29 +871,25 @@ bool gha_tables_ready() { return gha_tables() != nullptr; }
 extern "C" int atde_at3p_stage_gha(const float* bands, int S, int C, int F, void* tones)
 {
     using namespace atde::at3p;
-    const GhaTables* G = gha_tables();
-    if (!G) return -2;
+    if (!gha_tables_ready()) return -2;
     const size_t n = (size_t)S * C * F * kFrame;
     float* d_bands = nullptr;
-    TaskScratch* d_scr = nullptr;
-    GhaFrameOut* d_out = nullptr;
-    GhaHistory* d_hist = nullptr;
+    unsigned char *d_scr = nullptr, *d_out = nullptr, *d_hist = nullptr;
     ToneBlock* d_tb = nullptr;
     const long long n_frames = (long long)S * F;
-    int blocks = (int)((n_frames + 3) / 4);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    const int blocks = gha_blocks_for(n_frames);
     int rc = 0;
     if (cudaMalloc(&d_bands, n * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&d_scr, (size_t)blocks * kGhaThreads * sizeof(TaskScratch)) != cudaSuccess ||
-        cudaMalloc(&d_out, (size_t)n_frames * sizeof(GhaFrameOut)) != cudaSuccess ||
-        cudaMalloc(&d_hist, (size_t)S * sizeof(GhaHistory)) != cudaSuccess ||
+        cudaMalloc(&d_scr, gha_scratch_bytes(blocks)) != cudaSuccess ||
+        cudaMalloc(&d_out, (size_t)n_frames * gha_frame_out_bytes()) != cudaSuccess ||
+        cudaMalloc(&d_hist, (size_t)S * gha_history_bytes()) != cudaSuccess ||
         cudaMalloc(&d_tb, (size_t)n_frames * sizeof(ToneBlock)) != cudaSuccess) rc = -3;
     if (!rc && (cudaMemcpy(d_bands, bands, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
-                cudaMemset(d_hist, 0, (size_t)S * sizeof(GhaHistory)) != cudaSuccess ||
-                cudaMemset(d_out, 0, (size_t)n_frames * sizeof(GhaFrameOut)) != cudaSuccess)) rc = -2;
+                cudaMemset(d_hist, 0, (size_t)S * gha_history_bytes()) != cudaSuccess ||
+                cudaMemset(d_out, 0, (size_t)n_frames * gha_frame_out_bytes()) != cudaSuccess)) rc = -2;
     if (!rc) {
-        ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, (cudaStream_t) nullptr, G, (const float*)d_bands, S, C, F, F, 0, d_scr, d_out);
-        ATDE_LAUNCH(at3p_gha_result_kernel, (unsigned)((S + 63) / 64), 64, 0, (cudaStream_t) nullptr, G, (const GhaFrameOut*)d_out, S, C, F, d_hist, d_tb, F, 0);
+        launch_gha_search(d_bands, S, C, F, F, 0, d_scr, d_out, blocks, nullptr);
+        launch_gha_result(d_out, S, C, F, d_hist, d_tb, F, 0, nullptr);
         if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = -2;
     }
     if (!rc && cudaMemcpy(tones, d_tb, (size_t)n_frames * sizeof(ToneBlock), cudaMemcpyDeviceToHost) != cudaSuccess) rc = -2;

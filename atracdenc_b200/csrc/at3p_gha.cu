@@ -598,7 +598,7 @@ constexpr int kGhaFB = 32;                // frames per block batch
 constexpr int kGhaThreads = 128;
 constexpr int kGhaItems = kGhaFB * kGhaTask;
 
-struct ItemState {                        // global memory, per (frame slot, channel, subband) of a block
+struct alignas(16) ItemState {            // global memory, per (frame slot, channel, subband) of a block; float4 copies
     float buf[128];                       // Buf[sb]: residual so far
     float buf_new[128];                   // staged residual of the running step
     SbState sb;

@@ -84,7 +84,9 @@ struct GhaFrameOut {
     unsigned env[2][kGhaSb][2];
 };
 
-struct TaskScratch {                      // global memory, one per resident thread: transient within a step
+struct TaskScratch {                      // LOCAL memory (the kernel's stack frame): transient within a step; the hardware
+                                          // interleaves local memory across the lanes of a warp, so lanes walking their own
+                                          // arrays in step touch one line per access instead of 32
     float tmp[128];                       // libgha's ctx->tmp_buf (the Repeat call of gha_adjust_info reads its stale tail)
     float s[kMaxDim][128], c[kMaxDim][128];
     cpx fa[64];
@@ -609,7 +611,7 @@ __device__ float g_zero64[64];            // look-ahead of the last frame of a s
 
 __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
                                                                        const float* __restrict__ bands,
-                                                                       int S, int C, int F, int L, int j0, TaskScratch* tscr,
+                                                                       int S, int C, int F, int L, int j0,
                                                                        ItemState* items_g, GhaFrameOut* out)
 {
     // bands [S][C][L][2048]; analysis (s, f), f < F, reads frame j0 + f with look-ahead frame j0 + f + 1 (zeros past L)
@@ -619,7 +621,8 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
     __shared__ int s_n;
     const int tid = threadIdx.x;
     const long long n_frames = (long long)S * F;
-    TaskScratch* ws = tscr + (size_t)blockIdx.x * kGhaThreads + tid;
+    TaskScratch scratch_local;
+    TaskScratch* ws = &scratch_local;
     ItemState* items = items_g + (size_t)blockIdx.x * kGhaItems;
     for (long long base = (long long)blockIdx.x * kGhaFB; base < n_frames; base += (long long)gridDim.x * kGhaFB) {
         for (int idx = tid; idx < kGhaItems; idx += kGhaThreads) {
@@ -842,8 +845,7 @@ __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const Gh
     hist_state[s] = h;
 }
 
-static size_t gha_thread_scratch_bytes(int blocks) { return ((size_t)blocks * kGhaThreads * sizeof(TaskScratch) + 255) / 256 * 256; }
-size_t gha_scratch_bytes(int blocks) { return gha_thread_scratch_bytes(blocks) + (size_t)blocks * kGhaItems * sizeof(ItemState); }
+size_t gha_scratch_bytes(int blocks) { return (size_t)blocks * kGhaItems * sizeof(ItemState); }
 size_t gha_frame_out_bytes() { return sizeof(GhaFrameOut); }
 size_t gha_history_bytes() { return sizeof(GhaHistory); }
 int gha_blocks_for(long long n_analyses)
@@ -855,7 +857,7 @@ int gha_blocks_for(long long n_analyses)
 void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)
 {
     ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
-                (TaskScratch*)scratch, (ItemState*)((unsigned char*)scratch + gha_thread_scratch_bytes(blocks)), (GhaFrameOut*)frame_out);
+                (ItemState*)scratch, (GhaFrameOut*)frame_out);
 }
 void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_state, ToneBlock* tones, int stride, int off, cudaStream_t st)
 {

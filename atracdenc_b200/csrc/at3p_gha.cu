@@ -472,15 +472,17 @@ ATDE_D bool check_next_frame(const GhaTables* G, const float* next_src, const Gh
     return after < before;
 }
 
-// One (channel, subband) step of DoRound computed from the start-of-round state into `st`.
-ATDE_D void task_step(const GhaTables* G, const SbState& sbs, int sb, const float* src, const float* next_src,
-                      const float* buf, float* buf_new, TaskScratch* ws, Staged& st)
+// One (channel, subband) step of DoRound computed from the start-of-round state into `st`, in two halves so
+// that the kernel can run each half over a list of its own (every lane of a warp then executes the same code).
+// First half: re-fit the subband's tones (nothing to do without tones).  Returns false when the step ends
+// here (the fit failed: the commit pass drops the last added tone and closes the subband).
+ATDE_D bool task_fit(const GhaTables* G, const SbState& sbs, int sb, const float* src, const float* next_src,
+                     float* buf_new, TaskScratch* ws, Staged& st)
 {
     st.part1 = 0; st.n_new = 0; st.resid_valid = 0; st.analyzed = 0; st.psy_ok = 0;
     st.env_first = sbs.env_first; st.env_second = sbs.env_second;
     st.last_res_energy = sbs.last_res_energy; st.gapless = sbs.gapless; st.max_mag = sbs.max_mag;
-    const float* analysis_src = buf;
-    if (sbs.n > 0) {
+    {
         const int dim = sbs.n;
         GhaInfo tmp_info[kMaxDim];
         for (int i = 0; i < dim; i++) tmp_info[i] = sbs.info[i];
@@ -555,15 +557,21 @@ ATDE_D void task_step(const GhaTables* G, const SbState& sbs, int sb, const floa
                 else if (st.env_second == 128u && cont) { st.env_second = kEmpty; st.gapless = 1; }
             }
         }
-        if (!ok) { st.part1 = 2; return; }
+        if (!ok) { st.part1 = 2; return false; }
         st.part1 = 1;
         st.n_new = dim;
         for (int i = 0; i < dim; i++) {
             st.fit[i] = tmp_info[i];
             st.max_mag = fmaxf(st.max_mag, tmp_info[i].magnitude);
         }
-        if (st.resid_valid) analysis_src = buf_new;
     }
+    return true;
+}
+
+// Second half: extract the next tone from the residual (the staged one if the fit just replaced it).
+ATDE_D void task_analyze(const GhaTables* G, int sb, const float* buf, const float* buf_new, TaskScratch* ws, Staged& st)
+{
+    const float* analysis_src = st.resid_valid ? buf_new : buf;
     st.found = analyze_one(G, analysis_src, ws);
     st.analyzed = 1;
     // PsyPreCheck (:955-973)
@@ -616,9 +624,10 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
 {
     // bands [S][C][L][2048]; analysis (s, f), f < F, reads frame j0 + f with look-ahead frame j0 + f + 1 (zeros past L)
     __shared__ int s_total[kGhaFB], s_go[kGhaFB];
-    __shared__ unsigned short s_list[kGhaItems];
+    __shared__ unsigned short s_list[kGhaItems];      // steps with work this round, then: steps to analyse
+    __shared__ unsigned short s_fit[kGhaItems];       // steps with tones to re-fit, grouped by tone count
     __shared__ unsigned char s_adopt[kGhaItems];
-    __shared__ int s_n;
+    __shared__ int s_n, s_nfit, s_cnt[kMaxDim + 1], s_off[kMaxDim + 1];
     const int tid = threadIdx.x;
     const long long n_frames = (long long)S * F;
     TaskScratch scratch_local;
@@ -649,21 +658,59 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
         if (tid < kGhaFB) { s_total[tid] = 0; s_go[tid] = base + tid < n_frames; }
         __syncthreads();
         for (;;) {
-            if (tid == 0) s_n = 0;
+            if (tid == 0) { s_n = 0; s_nfit = 0; }
+            if (tid <= kMaxDim) s_cnt[tid] = 0;
+            __syncthreads();
+            // steps with work; those with tones are counted per tone count (a counting sort keeps warps homogeneous)
+            int my_active = 0;
+            for (int idx = tid; idx < kGhaItems; idx += kGhaThreads)
+                if (s_go[idx >> 4] && items[idx].sb.done != 16) {
+                    my_active++;
+                    const int n = items[idx].sb.n;
+                    if (n > 0) atomicAdd(&s_cnt[n], 1);
+                }
+            if (my_active) atomicAdd(&s_n, my_active);
+            __syncthreads();
+            if (s_n == 0) break;
+            if (tid == 0) {
+                int acc = 0;
+                for (int d = kMaxDim; d >= 1; d--) { s_off[d] = acc; acc += s_cnt[d]; }     // largest fits first
+                s_nfit = acc;
+            }
             __syncthreads();
             for (int idx = tid; idx < kGhaItems; idx += kGhaThreads)
-                if (s_go[idx >> 4] && items[idx].sb.done != 16) s_list[atomicAdd(&s_n, 1)] = (unsigned short)idx;
+                if (s_go[idx >> 4] && items[idx].sb.done != 16 && items[idx].sb.n > 0)
+                    s_fit[atomicAdd(&s_off[items[idx].sb.n], 1)] = (unsigned short)idx;
+            if (tid == 0) s_n = 0;
             __syncthreads();
-            const int n_list = s_n;
-            if (n_list == 0) break;
-            for (int it = tid; it < n_list; it += kGhaThreads) {
-                const int idx = s_list[it];
+            // first half: fits
+            const int n_fit = s_nfit;
+            for (int it = tid; it < n_fit; it += kGhaThreads) {
+                const int idx = s_fit[it];
                 const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
                 const long long frame = base + fs;
                 const int s = (int)(frame / F), f = (int)(frame % F);
                 const float* src = bands + (((size_t)s * C + ch) * L + j0 + f) * kFrame + sb * kSbSamples;
                 const float* next_src = j0 + f + 1 < L ? src + kFrame : g_zero64;
-                task_step(G, items[idx].sb, sb, src, next_src, items[idx].buf, items[idx].buf_new, ws, items[idx].st);
+                if (task_fit(G, items[idx].sb, sb, src, next_src, items[idx].buf_new, ws, items[idx].st))
+                    s_list[atomicAdd(&s_n, 1)] = (unsigned short)idx;
+            }
+            // steps without tones go straight to the analysis
+            for (int idx = tid; idx < kGhaItems; idx += kGhaThreads)
+                if (s_go[idx >> 4] && items[idx].sb.done != 16 && items[idx].sb.n == 0) {
+                    Staged& st = items[idx].st;
+                    const SbState& sbs = items[idx].sb;
+                    st.part1 = 0; st.n_new = 0; st.resid_valid = 0; st.analyzed = 0; st.psy_ok = 0;
+                    st.env_first = sbs.env_first; st.env_second = sbs.env_second;
+                    st.last_res_energy = sbs.last_res_energy; st.gapless = sbs.gapless; st.max_mag = sbs.max_mag;
+                    s_list[atomicAdd(&s_n, 1)] = (unsigned short)idx;
+                }
+            __syncthreads();
+            // second half: analyses
+            const int n_list = s_n;
+            for (int it = tid; it < n_list; it += kGhaThreads) {
+                const int idx = s_list[it];
+                task_analyze(G, idx & 7, items[idx].buf, items[idx].buf_new, ws, items[idx].st);
             }
             __syncthreads();
             if (tid < kGhaFB && s_go[tid]) {

@@ -604,7 +604,7 @@ ATDE_D bool sb_insert(SbState& s, unsigned key, const GhaInfo& v)     // map::in
 // subband) steps that still have work into a list and spreads that list over its threads — subbands and
 // frames need very different numbers of rounds, and a fixed step-per-lane mapping left three quarters of
 // the lanes idle — then one thread per frame commits that frame's staged steps in the reference's order.
-constexpr int kGhaFB = 32;                // frames per block batch
+constexpr int kGhaFB = 64;                // frames per block batch
 constexpr int kGhaThreads = 128;
 constexpr int kGhaItems = kGhaFB * kGhaTask;
 
@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
     __shared__ unsigned short s_fit[kGhaItems];       // steps with tones to re-fit, grouped by tone count
     __shared__ unsigned char s_adopt[kGhaItems];
     __shared__ int s_n, s_nfit, s_cnt[kMaxDim + 1], s_off[kMaxDim + 1];
+    __shared__ int s_next;                            // dynamic work fetch: warps take 32 list entries at a time
     const int tid = threadIdx.x;
     const long long n_frames = (long long)S * F;
     TaskScratch scratch_local;
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
         if (tid < kGhaFB) { s_total[tid] = 0; s_go[tid] = base + tid < n_frames; }
         __syncthreads();
         for (;;) {
-            if (tid == 0) { s_n = 0; s_nfit = 0; }
+            if (tid == 0) { s_n = 0; s_nfit = 0; s_next = 0; }
             if (tid <= kMaxDim) s_cnt[tid] = 0;
             __syncthreads();
             // steps with work; those with tones are counted per tone count (a counting sort keeps warps homogeneous)
@@ -685,7 +686,15 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
             __syncthreads();
             // first half: fits
             const int n_fit = s_nfit;
-            for (int it = tid; it < n_fit; it += kGhaThreads) {
+            for (;;) {
+                // the list is sorted by tone count, largest first: a warp's 32 entries cost about the same, and the
+                // expensive ones start first
+                int it0 = 0;
+                if ((tid & 31) == 0) it0 = atomicAdd(&s_next, 32);
+                it0 = __shfl_sync(0xffffffffu, it0, 0);
+                if (it0 >= n_fit) break;
+                const int it = it0 + (tid & 31);
+                if (it >= n_fit) continue;
                 const int idx = s_fit[it];
                 const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
                 const long long frame = base + fs;
@@ -706,9 +715,17 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
                     s_list[atomicAdd(&s_n, 1)] = (unsigned short)idx;
                 }
             __syncthreads();
+            if (tid == 0) s_next = 0;
+            __syncthreads();
             // second half: analyses
             const int n_list = s_n;
-            for (int it = tid; it < n_list; it += kGhaThreads) {
+            for (;;) {
+                int it0 = 0;
+                if ((tid & 31) == 0) it0 = atomicAdd(&s_next, 32);
+                it0 = __shfl_sync(0xffffffffu, it0, 0);
+                if (it0 >= n_list) break;
+                const int it = it0 + (tid & 31);
+                if (it >= n_list) continue;
                 const int idx = s_list[it];
                 task_analyze(G, idx & 7, items[idx].buf, items[idx].buf_new, ws, items[idx].st);
             }

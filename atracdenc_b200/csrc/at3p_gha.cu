@@ -347,7 +347,7 @@ ATDE_D int sle_block(double* a, int n, double* x)
 ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskScratch* ws)
 {
     float* tmp = ws->tmp;
-    double M[kMaxDim * (kMaxDim + 1)];
+    double M[3][kMaxDim * (kMaxDim + 1)];
     double fx[3][kMaxDim];
     for (int loop = 0; loop < 7; loop++) {
         for (int n = 0; n < sz; n++) tmp[n] = pcm[n];
@@ -362,64 +362,49 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
                 ws->c[k][n] = c;
             }
         }
-        // three blocks: A (ba = -s), w (bw = -A n c), p (bp = -A c); right-hand sides from the residual
-        for (int blk = 0; blk < 3; blk++) {
+        // three blocks: A (ba = -s), w (bw = -A n c), p (bp = -A c); right-hand sides from the residual.
+        // One pass over n per tone builds its three diagonal entries and right-hand sides, one pass per tone
+        // pair the three off-diagonal entries (each accumulator still adds its terms in the order n = 0, 1, ...).
+        {
             const int col = dim + 1;
             for (int i = 0; i < dim; i++) {
                 const double Ai = (double)info[i].magnitude;
-                // M[i][j] and M[j][i] are the same sum of commutative products in the same order: compute j >= i, mirror
-                for (int j = i; j < dim; j++) {
-                    const double Aj = (double)info[j].magnitude;
-                    double acc = 0.0;
-                    if (blk == 0) {
-                        for (int n = 0; n < sz; n++)
-                            acc = dadd(acc, dmul(-(double)ws->s[i][n], -(double)ws->s[j][n]));
-                    } else if (blk == 1) {
-                        if (i == j) {
-                            for (int n = 0; n < sz; n++) {
-                                const double dn = (double)n, c = (double)ws->c[i][n], s = (double)ws->s[i][n];
-                                const double bw = dmul(dmul(-Ai, dn), c);
-                                const double bww = dmul(dmul(dmul(Ai, dn), dn), s);
-                                acc = dadd(acc, dadd(dmul((double)tmp[n], bww), dmul(bw, bw)));
-                            }
-                        } else {
-                            for (int n = 0; n < sz; n++) {
-                                const double dn = (double)n;
-                                const double bwi = dmul(dmul(-Ai, dn), (double)ws->c[i][n]);
-                                const double bwj = dmul(dmul(-Aj, dn), (double)ws->c[j][n]);
-                                acc = dadd(acc, dmul(bwi, bwj));
-                            }
-                        }
-                    } else {
-                        if (i == j) {
-                            for (int n = 0; n < sz; n++) {
-                                const double bp = dmul(-Ai, (double)ws->c[i][n]);
-                                const float bpp = d2f(dmul(Ai, (double)ws->s[i][n]));
-                                acc = dadd(acc, dadd((double)fmul(tmp[n], bpp), dmul(bp, bp)));
-                            }
-                        } else {
-                            for (int n = 0; n < sz; n++) {
-                                const double bpi = dmul(-Ai, (double)ws->c[i][n]);
-                                const double bpj = dmul(-Aj, (double)ws->c[j][n]);
-                                acc = dadd(acc, dmul(bpi, bpj));
-                            }
-                        }
-                    }
-                    M[i * col + j] = dmul(acc, 2.0);
-                    M[j * col + i] = M[i * col + j];
-                }
-                double r = 0.0;
+                double aa = 0.0, ww = 0.0, pp = 0.0, ra = 0.0, rw = 0.0, rp = 0.0;
                 for (int n = 0; n < sz; n++) {
-                    float bf;
-                    if (blk == 0) bf = -ws->s[i][n];
-                    else if (blk == 1) bf = d2f(dmul(dmul(-Ai, (double)n), (double)ws->c[i][n]));
-                    else bf = d2f(dmul(-Ai, (double)ws->c[i][n]));
-                    r = dadd(r, (double)fmul(tmp[n], bf));
+                    const float sf = ws->s[i][n], t = tmp[n];
+                    const double dn = (double)n, c = (double)ws->c[i][n], sd = (double)sf, td = (double)t;
+                    aa = dadd(aa, dmul(-sd, -sd));
+                    const double bw = dmul(dmul(-Ai, dn), c);
+                    const double bww = dmul(dmul(dmul(Ai, dn), dn), sd);
+                    ww = dadd(ww, dadd(dmul(td, bww), dmul(bw, bw)));
+                    const double bp = dmul(-Ai, c);
+                    const float bpp = d2f(dmul(Ai, sd));
+                    pp = dadd(pp, dadd((double)fmul(t, bpp), dmul(bp, bp)));
+                    ra = dadd(ra, (double)fmul(t, -sf));
+                    rw = dadd(rw, (double)fmul(t, d2f(bw)));
+                    rp = dadd(rp, (double)fmul(t, d2f(bp)));
                 }
-                M[i * col + dim] = dmul(r, 2.0);
+                M[0][i * col + i] = dmul(aa, 2.0); M[1][i * col + i] = dmul(ww, 2.0); M[2][i * col + i] = dmul(pp, 2.0);
+                M[0][i * col + dim] = dmul(ra, 2.0); M[1][i * col + dim] = dmul(rw, 2.0); M[2][i * col + dim] = dmul(rp, 2.0);
+                // M[i][j] and M[j][i] are the same sum of commutative products in the same order: compute j > i, mirror
+                for (int j = i + 1; j < dim; j++) {
+                    const double Aj = (double)info[j].magnitude;
+                    double xa = 0.0, xw = 0.0, xp = 0.0;
+                    for (int n = 0; n < sz; n++) {
+                        const double dn = (double)n, ci = (double)ws->c[i][n], cj = (double)ws->c[j][n];
+                        xa = dadd(xa, dmul(-(double)ws->s[i][n], -(double)ws->s[j][n]));
+                        xw = dadd(xw, dmul(dmul(dmul(-Ai, dn), ci), dmul(dmul(-Aj, dn), cj)));
+                        xp = dadd(xp, dmul(dmul(-Ai, ci), dmul(-Aj, cj)));
+                    }
+                    M[0][i * col + j] = M[0][j * col + i] = dmul(xa, 2.0);
+                    M[1][i * col + j] = M[1][j * col + i] = dmul(xw, 2.0);
+                    M[2][i * col + j] = M[2][j * col + i] = dmul(xp, 2.0);
+                }
             }
-            for (int i = 0; i < dim; i++) fx[blk][i] = 0.0;
-            if (sle_block(M, dim, fx[blk])) return -1;
+            for (int blk = 0; blk < 3; blk++) {
+                for (int i = 0; i < dim; i++) fx[blk][i] = 0.0;
+                if (sle_block(M[blk], dim, fx[blk])) return -1;
+            }
         }
         for (int k = 0; k < dim; k++) {
             info[k].magnitude = d2f(dsub((double)info[k].magnitude, dmul(fx[0][k], 0.8)));
@@ -604,7 +589,7 @@ ATDE_D bool sb_insert(SbState& s, unsigned key, const GhaInfo& v)     // map::in
 // subband) steps that still have work into a list and spreads that list over its threads — subbands and
 // frames need very different numbers of rounds, and a fixed step-per-lane mapping left three quarters of
 // the lanes idle — then one thread per frame commits that frame's staged steps in the reference's order.
-constexpr int kGhaFB = 64;                // frames per block batch
+constexpr int kGhaFB = 64;                // most frames per block batch (the launch picks fb <= kGhaFB)
 constexpr int kGhaThreads = 128;
 constexpr int kGhaItems = kGhaFB * kGhaTask;
 
@@ -619,7 +604,7 @@ __device__ float g_zero64[64];            // look-ahead of the last frame of a s
 
 __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
                                                                        const float* __restrict__ bands,
-                                                                       int S, int C, int F, int L, int j0,
+                                                                       int S, int C, int F, int L, int j0, int fb,
                                                                        ItemState* items_g, GhaFrameOut* out)
 {
     // bands [S][C][L][2048]; analysis (s, f), f < F, reads frame j0 + f with look-ahead frame j0 + f + 1 (zeros past L)
@@ -630,12 +615,13 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
     __shared__ int s_n, s_nfit, s_cnt[kMaxDim + 1], s_off[kMaxDim + 1];
     __shared__ int s_next;                            // dynamic work fetch: warps take 32 list entries at a time
     const int tid = threadIdx.x;
+    const int n_items = fb * kGhaTask;                // steps of this block's batch
     const long long n_frames = (long long)S * F;
     TaskScratch scratch_local;
     TaskScratch* ws = &scratch_local;
     ItemState* items = items_g + (size_t)blockIdx.x * kGhaItems;
-    for (long long base = (long long)blockIdx.x * kGhaFB; base < n_frames; base += (long long)gridDim.x * kGhaFB) {
-        for (int idx = tid; idx < kGhaItems; idx += kGhaThreads) {
+    for (long long base = (long long)blockIdx.x * fb; base < n_frames; base += (long long)gridDim.x * fb) {
+        for (int idx = tid; idx < n_items; idx += kGhaThreads) {
             const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
             const bool live = base + fs < n_frames && ch < C;
             SbState& me = items[idx].sb;
@@ -646,7 +632,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
             me.gapless = 0; me.done = live ? 0 : 16; me.max_mag = 0.0f; me.last_res_energy = 0.0f; me.last_added = 0;
             s_adopt[idx] = 0;
         }
-        for (int w = tid; w < kGhaItems * 32; w += kGhaThreads) {        // Buf[sb] = the subband's samples (float4 granules)
+        for (int w = tid; w < n_items * 32; w += kGhaThreads) {        // Buf[sb] = the subband's samples (float4 granules)
             const int idx = w >> 5, q = w & 31;
             const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
             const long long frame = base + fs;
@@ -656,7 +642,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
                 reinterpret_cast<float4*>(items[idx].buf)[q] = reinterpret_cast<const float4*>(src)[q];
             }
         }
-        if (tid < kGhaFB) { s_total[tid] = 0; s_go[tid] = base + tid < n_frames; }
+        if (tid < fb) { s_total[tid] = 0; s_go[tid] = base + tid < n_frames; }
         __syncthreads();
         for (;;) {
             if (tid == 0) { s_n = 0; s_nfit = 0; s_next = 0; }
@@ -664,7 +650,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
             __syncthreads();
             // steps with work; those with tones are counted per tone count (a counting sort keeps warps homogeneous)
             int my_active = 0;
-            for (int idx = tid; idx < kGhaItems; idx += kGhaThreads)
+            for (int idx = tid; idx < n_items; idx += kGhaThreads)
                 if (s_go[idx >> 4] && items[idx].sb.done != 16) {
                     my_active++;
                     const int n = items[idx].sb.n;
@@ -679,7 +665,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
                 s_nfit = acc;
             }
             __syncthreads();
-            for (int idx = tid; idx < kGhaItems; idx += kGhaThreads)
+            for (int idx = tid; idx < n_items; idx += kGhaThreads)
                 if (s_go[idx >> 4] && items[idx].sb.done != 16 && items[idx].sb.n > 0)
                     s_fit[atomicAdd(&s_off[items[idx].sb.n], 1)] = (unsigned short)idx;
             if (tid == 0) s_n = 0;
@@ -705,7 +691,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
                     s_list[atomicAdd(&s_n, 1)] = (unsigned short)idx;
             }
             // steps without tones go straight to the analysis
-            for (int idx = tid; idx < kGhaItems; idx += kGhaThreads)
+            for (int idx = tid; idx < n_items; idx += kGhaThreads)
                 if (s_go[idx >> 4] && items[idx].sb.done != 16 && items[idx].sb.n == 0) {
                     Staged& st = items[idx].st;
                     const SbState& sbs = items[idx].sb;
@@ -730,7 +716,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
                 task_analyze(G, idx & 7, items[idx].buf, items[idx].buf_new, ws, items[idx].st);
             }
             __syncthreads();
-            if (tid < kGhaFB && s_go[tid]) {
+            if (tid < fb && s_go[tid]) {
                 // commit in the reference's order: channel 0 subbands 0..7, then channel 1
                 const int fs = tid;
                 int total = s_total[fs];
@@ -800,7 +786,7 @@ __global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const G
             __syncthreads();
             for (int it = tid; it < n_list; it += kGhaThreads) s_adopt[s_list[it]] = 0;
         }
-        for (int idx = tid; idx < kGhaItems; idx += kGhaThreads) {
+        for (int idx = tid; idx < n_items; idx += kGhaThreads) {
             const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
             const long long frame = base + fs;
             if (frame < n_frames && ch < C) {
@@ -912,16 +898,25 @@ __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const Gh
 size_t gha_scratch_bytes(int blocks) { return (size_t)blocks * kGhaItems * sizeof(ItemState); }
 size_t gha_frame_out_bytes() { return sizeof(GhaFrameOut); }
 size_t gha_history_bytes() { return sizeof(GhaHistory); }
+// frames per block batch: as many as keep one resident wave of blocks (4 per SM) busy, at most kGhaFB
+static int gha_fb_for(long long n_analyses)
+{
+    long long fb = (n_analyses + 148 * 4 - 1) / (148 * 4);
+    if (fb < 8) fb = 8;
+    if (fb > kGhaFB) fb = kGhaFB;
+    return (int)fb;
+}
 int gha_blocks_for(long long n_analyses)
 {
-    long long b = (n_analyses + kGhaFB - 1) / kGhaFB;
+    const int fb = gha_fb_for(n_analyses);
+    long long b = (n_analyses + fb - 1) / fb;
     if (b > 148 * 4) b = 148 * 4;                     // one resident wave (launch bounds: 4 blocks per SM)
     return (int)(b < 1 ? 1 : b);
 }
 void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)
 {
     ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
-                (ItemState*)scratch, (GhaFrameOut*)frame_out);
+                gha_fb_for((long long)S * nA), (ItemState*)scratch, (GhaFrameOut*)frame_out);
 }
 void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_state, ToneBlock* tones, int stride, int off, cudaStream_t st)
 {

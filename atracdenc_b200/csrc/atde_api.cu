@@ -687,6 +687,7 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
         const long v = atol(env);
         if (v > 0) target_floats = (size_t)v << 18;
     }
+    if (at3p) target_floats *= 4;                                               // the tone search wants many frames per launch
     int chunk = (int)(target_floats / pcm_per_stream);
     if (chunk < 1) chunk = 1;
     if (chunk > S) chunk = S;

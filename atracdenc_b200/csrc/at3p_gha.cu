@@ -92,6 +92,7 @@ struct TaskScratch {                      // LOCAL memory (the kernel's stack fr
     cpx fa[64];
     cpx fout[65];
     cpx fb[128];
+    double resd[256];                     // the resampled signal widened once for the eight Newton sweeps
 };
 
 static GhaTables* g_gha_tables = nullptr;
@@ -254,7 +255,7 @@ ATDE_D GhaInfo analyze_one(const GhaTables* G, const float* pcm, TaskScratch* ws
         fft_stages4<true>(fb, G->tw128i, 128, 2);
     }
     float* res = reinterpret_cast<float*>(fb);            // 256 reals
-    for (int i = 0; i < 256; i++) res[i] = __fdiv_rn(res[i], 128.0f);
+    for (int i = 0; i < 256; i++) ws->resd[i] = (double)__fdiv_rn(res[i], 128.0f);
     // gha_search_omega_newton (:173-236) on the 256 resampled points
     GhaInfo out;
     {
@@ -262,9 +263,9 @@ ATDE_D GhaInfo analyze_one(const GhaTables* G, const float* pcm, TaskScratch* ws
         for (int loop = 0; loop <= 7; loop++) {
             double Xr = 0, Xi = 0, dXr = 0, dXi = 0, ddXr = 0, ddXs = 0;
             const double a = g_cos(omega), b = g_sin(omega);
-            double c = 1.0, s = 0.0;
-            for (int n = 0; n < 256; n++) {
-                const double p = (double)res[n], dn = (double)n;
+            double c = 1.0, s = 0.0, dn = 0.0;
+            for (int n = 0; n < 256; n++, dn += 1.0) {      // dn == (double)n exactly
+                const double p = ws->resd[n];
                 const double cm = dmul(p, c), sm = dmul(p, s);
                 Xr = dadd(Xr, cm);
                 Xi = dadd(Xi, sm);
@@ -295,8 +296,9 @@ ATDE_D GhaInfo analyze_one(const GhaTables* G, const float* pcm, TaskScratch* ws
     }
     // gha_generate_sine (:238-244) + gha_estimate_magnitude (:246-257)
     double t1 = 0, t2 = 0;
-    for (int i = 0; i < 128; i++) {
-        const float arg = fadd(fmul(out.frequency, (float)i), out.phase);
+    float fi = 0.0f;
+    for (int i = 0; i < 128; i++, fi += 1.0f) {
+        const float arg = fadd(fmul(out.frequency, fi), out.phase);
         const float r = d2f(g_sin((double)arg));
         tmp[i] = r;
         t1 = dadd(t1, (double)fmul(pcm[i], r));
@@ -353,8 +355,9 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
         for (int n = 0; n < sz; n++) tmp[n] = pcm[n];
         for (int k = 0; k < dim; k++) {
             const float fr = info[k].frequency, ph = info[k].phase, mg = info[k].magnitude;
-            for (int n = 0; n < sz; n++) {
-                const float t = fadd(fmul(fr, (float)n), ph);
+            float fn = 0.0f;                                 // == (float)n exactly
+            for (int n = 0; n < sz; n++, fn += 1.0f) {
+                const float t = fadd(fmul(fr, fn), ph);
                 float s, c;
                 g_sincosf(t, s, c);
                 tmp[n] = fsub(tmp[n], fmul(mg, s));
@@ -369,10 +372,10 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
             const int col = dim + 1;
             for (int i = 0; i < dim; i++) {
                 const double Ai = (double)info[i].magnitude;
-                double aa = 0.0, ww = 0.0, pp = 0.0, ra = 0.0, rw = 0.0, rp = 0.0;
-                for (int n = 0; n < sz; n++) {
+                double aa = 0.0, ww = 0.0, pp = 0.0, ra = 0.0, rw = 0.0, rp = 0.0, dn = 0.0;
+                for (int n = 0; n < sz; n++, dn += 1.0) {
                     const float sf = ws->s[i][n], t = tmp[n];
-                    const double dn = (double)n, c = (double)ws->c[i][n], sd = (double)sf, td = (double)t;
+                    const double c = (double)ws->c[i][n], sd = (double)sf, td = (double)t;
                     aa = dadd(aa, dmul(-sd, -sd));
                     const double bw = dmul(dmul(-Ai, dn), c);
                     const double bww = dmul(dmul(dmul(Ai, dn), dn), sd);
@@ -389,9 +392,9 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
                 // M[i][j] and M[j][i] are the same sum of commutative products in the same order: compute j > i, mirror
                 for (int j = i + 1; j < dim; j++) {
                     const double Aj = (double)info[j].magnitude;
-                    double xa = 0.0, xw = 0.0, xp = 0.0;
-                    for (int n = 0; n < sz; n++) {
-                        const double dn = (double)n, ci = (double)ws->c[i][n], cj = (double)ws->c[j][n];
+                    double xa = 0.0, xw = 0.0, xp = 0.0, dn = 0.0;
+                    for (int n = 0; n < sz; n++, dn += 1.0) {
+                        const double ci = (double)ws->c[i][n], cj = (double)ws->c[j][n];
                         xa = dadd(xa, dmul(-(double)ws->s[i][n], -(double)ws->s[j][n]));
                         xw = dadd(xw, dmul(dmul(dmul(-Ai, dn), ci), dmul(dmul(-Aj, dn), cj)));
                         xp = dadd(xp, dmul(dmul(-Ai, ci), dmul(-Aj, cj)));

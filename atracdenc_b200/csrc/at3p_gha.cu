@@ -92,7 +92,6 @@ struct TaskScratch {                      // LOCAL memory (the kernel's stack fr
     cpx fa[64];
     cpx fout[65];
     cpx fb[128];
-    double resd[256];                     // the resampled signal widened once for the eight Newton sweeps
 };
 
 static GhaTables* g_gha_tables = nullptr;
@@ -255,7 +254,7 @@ ATDE_D GhaInfo analyze_one(const GhaTables* G, const float* pcm, TaskScratch* ws
         fft_stages4<true>(fb, G->tw128i, 128, 2);
     }
     float* res = reinterpret_cast<float*>(fb);            // 256 reals
-    for (int i = 0; i < 256; i++) ws->resd[i] = (double)__fdiv_rn(res[i], 128.0f);
+    for (int i = 0; i < 256; i++) res[i] = __fdiv_rn(res[i], 128.0f);
     // gha_search_omega_newton (:173-236) on the 256 resampled points
     GhaInfo out;
     {
@@ -265,7 +264,7 @@ ATDE_D GhaInfo analyze_one(const GhaTables* G, const float* pcm, TaskScratch* ws
             const double a = g_cos(omega), b = g_sin(omega);
             double c = 1.0, s = 0.0, dn = 0.0;
             for (int n = 0; n < 256; n++, dn += 1.0) {      // dn == (double)n exactly
-                const double p = ws->resd[n];
+                const double p = (double)res[n];
                 const double cm = dmul(p, c), sm = dmul(p, s);
                 Xr = dadd(Xr, cm);
                 Xi = dadd(Xi, sm);
@@ -343,6 +342,29 @@ ATDE_D int sle_block(double* a, int n, double* x)
     return 0;
 }
 
+// The end of one Newton loop for one tone (gha.c:348-399): damped step, then the sign / range repairs.  The
+// reference runs the four repair loops one after the other over all tones; they only touch their own tone, so
+// doing all four for tone k before tone k+1 gives the same values.
+ATDE_D void newton_update(GhaInfo& t, double da, double dw, double dp)
+{
+    t.magnitude = d2f(dsub((double)t.magnitude, dmul(da, 0.8)));
+    t.frequency = d2f(dsub((double)t.frequency, dmul(dw, 0.8)));
+    t.phase = d2f(dsub((double)t.phase, dmul(dp, 0.8)));
+    if (t.magnitude < 0) {
+        t.magnitude = fmul(t.magnitude, -1.0f);
+        t.phase = d2f(dadd((double)t.phase, kPi));
+    }
+    if (t.magnitude > 32768.0f) t.magnitude = d2f(dmul(32768.0, 0.5));
+    if (t.frequency < 0) {
+        t.frequency = fmul(t.frequency, -1.0f);
+        t.phase = d2f(dsub(2 * kPi, (double)t.phase));
+    }
+    while ((double)t.frequency > kPi * 2.0) t.frequency = d2f(dsub((double)t.frequency, kPi * 2.0));
+    if ((double)t.frequency > kPi) t.frequency = d2f(dsub(2 * kPi, (double)t.frequency));
+    while ((double)t.phase > kPi * 2.0) t.phase = d2f(dsub((double)t.phase, kPi * 2));
+    while (t.phase < 0) t.phase = d2f(dadd((double)t.phase, kPi * 2));
+}
+
 // ---------------------------------------------------------------------------------------------
 // gha_adjust_info_newton_md (gha.c:259-402); leaves the last loop's residual in ws->tmp[0..sz)
 // ---------------------------------------------------------------------------------------------
@@ -409,30 +431,82 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
                 if (sle_block(M[blk], dim, fx[blk])) return -1;
             }
         }
-        for (int k = 0; k < dim; k++) {
-            info[k].magnitude = d2f(dsub((double)info[k].magnitude, dmul(fx[0][k], 0.8)));
-            info[k].frequency = d2f(dsub((double)info[k].frequency, dmul(fx[1][k], 0.8)));
-            info[k].phase = d2f(dsub((double)info[k].phase, dmul(fx[2][k], 0.8)));
+        for (int k = 0; k < dim; k++) newton_update(info[k], fx[0][k], fx[1][k], fx[2][k]);
+    }
+    return 0;
+}
+
+// The same fit for 1..3 tones — by far the most frequent sizes — with one pass over the samples per Newton
+// loop: every sample's sin/cos pairs, the residual and all matrix terms are produced together and the
+// accumulators live in registers, so the [tone][sample] sin/cos arrays (the bulk of the local-memory traffic of
+// the general version) are never stored.  Every accumulator still adds its terms in the order n = 0, 1, ...
+template <int DIM>
+ATDE_D int adjust_newton_small(const float* pcm, GhaInfo* info, int sz, TaskScratch* ws)
+{
+    float* tmp = ws->tmp;
+    constexpr int col = DIM + 1;
+    for (int loop = 0; loop < 7; loop++) {
+        double aa[DIM], ww[DIM], pp[DIM], ra[DIM], rw[DIM], rp[DIM];
+        double xa[DIM][DIM], xw[DIM][DIM], xp[DIM][DIM];             // only j > i used
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+            aa[i] = ww[i] = pp[i] = ra[i] = rw[i] = rp[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < DIM; j++) xa[i][j] = xw[i][j] = xp[i][j] = 0.0;
         }
-        for (int k = 0; k < dim; k++) {
-            if (info[k].magnitude < 0) {
-                info[k].magnitude = fmul(info[k].magnitude, -1.0f);
-                info[k].phase = d2f(dadd((double)info[k].phase, kPi));
+        float fn = 0.0f;
+        double dn = 0.0;
+        for (int n = 0; n < sz; n++, fn += 1.0f, dn += 1.0) {
+            float sf[DIM], cf[DIM];
+            float t = pcm[n];
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                g_sincosf(fadd(fmul(info[k].frequency, fn), info[k].phase), sf[k], cf[k]);
+                t = fsub(t, fmul(info[k].magnitude, sf[k]));
             }
-            if (info[k].magnitude > 32768.0f) info[k].magnitude = d2f(dmul(32768.0, 0.5));
-        }
-        for (int k = 0; k < dim; k++) {
-            if (info[k].frequency < 0) {
-                info[k].frequency = fmul(info[k].frequency, -1.0f);
-                info[k].phase = d2f(dsub(2 * kPi, (double)info[k].phase));
+            tmp[n] = t;
+            const double td = (double)t;
+            double bw[DIM], bp[DIM];
+#pragma unroll
+            for (int i = 0; i < DIM; i++) {
+                const double Ai = (double)info[i].magnitude, c = (double)cf[i], sd = (double)sf[i];
+                aa[i] = dadd(aa[i], dmul(-sd, -sd));
+                bw[i] = dmul(dmul(-Ai, dn), c);
+                const double bww = dmul(dmul(dmul(Ai, dn), dn), sd);
+                ww[i] = dadd(ww[i], dadd(dmul(td, bww), dmul(bw[i], bw[i])));
+                bp[i] = dmul(-Ai, c);
+                const float bpp = d2f(dmul(Ai, sd));
+                pp[i] = dadd(pp[i], dadd((double)fmul(t, bpp), dmul(bp[i], bp[i])));
+                ra[i] = dadd(ra[i], (double)fmul(t, -sf[i]));
+                rw[i] = dadd(rw[i], (double)fmul(t, d2f(bw[i])));
+                rp[i] = dadd(rp[i], (double)fmul(t, d2f(bp[i])));
             }
-            while ((double)info[k].frequency > kPi * 2.0) info[k].frequency = d2f(dsub((double)info[k].frequency, kPi * 2.0));
-            if ((double)info[k].frequency > kPi) info[k].frequency = d2f(dsub(2 * kPi, (double)info[k].frequency));
+#pragma unroll
+            for (int i = 0; i < DIM; i++)
+#pragma unroll
+                for (int j = i + 1; j < DIM; j++) {
+                    xa[i][j] = dadd(xa[i][j], dmul(-(double)sf[i], -(double)sf[j]));
+                    xw[i][j] = dadd(xw[i][j], dmul(bw[i], bw[j]));
+                    xp[i][j] = dadd(xp[i][j], dmul(bp[i], bp[j]));
+                }
         }
-        for (int k = 0; k < dim; k++) {
-            while ((double)info[k].phase > kPi * 2.0) info[k].phase = d2f(dsub((double)info[k].phase, kPi * 2));
-            while (info[k].phase < 0) info[k].phase = d2f(dadd((double)info[k].phase, kPi * 2));
+        double M[3][DIM * col], fx[3][DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+            M[0][i * col + i] = dmul(aa[i], 2.0); M[1][i * col + i] = dmul(ww[i], 2.0); M[2][i * col + i] = dmul(pp[i], 2.0);
+            M[0][i * col + DIM] = dmul(ra[i], 2.0); M[1][i * col + DIM] = dmul(rw[i], 2.0); M[2][i * col + DIM] = dmul(rp[i], 2.0);
+#pragma unroll
+            for (int j = i + 1; j < DIM; j++) {
+                M[0][i * col + j] = M[0][j * col + i] = dmul(xa[i][j], 2.0);
+                M[1][i * col + j] = M[1][j * col + i] = dmul(xw[i][j], 2.0);
+                M[2][i * col + j] = M[2][j * col + i] = dmul(xp[i][j], 2.0);
+            }
         }
+        for (int blk = 0; blk < 3; blk++) {
+            for (int i = 0; i < DIM; i++) fx[blk][i] = 0.0;
+            if (sle_block(M[blk], DIM, fx[blk])) return -1;
+        }
+        for (int k = 0; k < DIM; k++) newton_update(info[k], fx[0][k], fx[1][k], fx[2][k]);
     }
     return 0;
 }
@@ -479,7 +553,12 @@ ATDE_D bool task_fit(const GhaTables* G, const SbState& sbs, int sb, const float
         int frame_sz = 0;
         for (int call = 0; call < 2; call++) {
             const int sz = (frame_sz && frame_sz < 128) ? frame_sz : 128;
-            if (adjust_newton(src, tmp_info, dim, sz, ws) < 0) { status = 0; break; }
+            int ar;
+            if (dim == 1) ar = adjust_newton_small<1>(src, tmp_info, sz, ws);
+            else if (dim == 2) ar = adjust_newton_small<2>(src, tmp_info, sz, ws);
+            else if (dim == 3) ar = adjust_newton_small<3>(src, tmp_info, sz, ws);
+            else ar = adjust_newton(src, tmp_info, dim, sz, ws);
+            if (ar < 0) { status = 0; break; }
             // the callback reads 128 samples: beyond sz they are what the previous (full-size) call left in
             // tmp_buf, which is exactly what ws->tmp still holds there
             float res_energy = 0.0f;

@@ -893,27 +893,31 @@ struct GhaHistory {                       // what later frames read of ResultBuf
     unsigned env_second[2][16];
 };
 
-ATDE_D void adjust_envelope(int* env /*[2]*/, unsigned src_first, unsigned src_second, unsigned history)
+constexpr unsigned kNeedHist = 0xfffffffdu;   // envelope start that depends on the previous valid result (patched by the history pass)
+
+ATDE_D void adjust_envelope(int* env /*[2]*/, unsigned src_first, unsigned src_second)
 {
-    if (src_first == 0 && history == kEmpty) env[0] = (int)kEmpty;
+    // AdjustEnvelope(.., history): first = (src.first == 0 && history == EMPTY) ? EMPTY : src.first / 4
+    if (src_first == 0) env[0] = (int)kNeedHist;
     else env[0] = (int)(src_first / 4);
     if (src_second == kEmpty) env[1] = (int)kEmpty;
     else env[1] = (int)((src_second - 1) / 4);
 }
 
+// One thread per frame: everything of FillResultBuf that does not look at ResultBufHistory.
 __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const GhaFrameOut* __restrict__ in,
-                                       int S, int C, int F, GhaHistory* hist_state, ToneBlock* out, int out_stride, int out_off)
+                                       int S, int C, int F, ToneBlock* out, int out_stride, int out_off)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    GhaHistory h = hist_state[s];
-    for (int f = 0; f < F; f++) {
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= (long long)S * F) return;
+    const int s = (int)(gi / F), f = (int)(gi % F);
+    {
         const GhaFrameOut& o = in[(size_t)s * F + f];
         ToneBlock& tb = out[(size_t)s * out_stride + out_off + f];
         tb.present = 0; tb.num_tone_bands = 0; tb.second_is_leader = 0;
         tb.n_sb[0] = tb.n_sb[1] = 0; tb.n_params[0] = tb.n_params[1] = 0;
         for (int i = 0; i < 16; i++) tb.tone_sharing[i] = 0;
-        if (o.total_tones == 0) continue;                      // DoAnalize returns nullptr, history untouched
+        if (o.total_tones == 0) return;                        // DoAnalize returns nullptr, history untouched
         int used[2] = {0, 0};
         for (int ch = 0; ch < C; ch++)
             for (int sb = 0; sb < kGhaSb; sb++) if (o.n[ch][sb] > 0) used[ch] = sb + 1;
@@ -938,11 +942,9 @@ __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const Gh
             }
             if (tb.sb[0][sb][1] > 0) {
                 tb.sb[0][sb][0] = index;
-                const unsigned hs = h.n_sb[0] > sb ? h.env_second[0][sb] : kInit;
-                adjust_envelope(&tb.sb[0][sb][2], o.env[leader][sb][0], o.env[leader][sb][1], hs);
+                adjust_envelope(&tb.sb[0][sb][2], o.env[leader][sb][0], o.env[leader][sb][1]);
             }
             if (C == 2) {
-                const unsigned hs = h.n_sb[1] > sb ? h.env_second[1][sb] : kInit;
                 unsigned mode = 0;
                 int added = 0;
                 for (int i = 0; i < o.n[fol][sb]; i++) {
@@ -963,17 +965,53 @@ __global__ void at3p_gha_result_kernel(const GhaTables* __restrict__ G, const Gh
                     tb.tone_sharing[sb] = 0;
                     tb.sb[1][sb][0] = np1 - added;
                     tb.sb[1][sb][1] = added;
-                    adjust_envelope(&tb.sb[1][sb][2], o.env[fol][sb][0], o.env[fol][sb][1], hs);
+                    adjust_envelope(&tb.sb[1][sb][2], o.env[fol][sb][0], o.env[fol][sb][1]);
                 }
             }
         }
         tb.n_params[0] = np0; tb.n_params[1] = np1;
-        // ResultBufHistory = ResultBuf
-        h.n_sb[0] = ntb;
-        h.n_sb[1] = C == 2 ? ntb : h.n_sb[1];
-        for (int ch = 0; ch < C; ch++)
-            for (int sb = 0; sb < ntb; sb++) h.env_second[ch][sb] = (unsigned)tb.sb[ch][sb][3];
     }
+}
+
+// ResultBufHistory is the previous NON-NULL result; what later frames read of it (WaveSbInfos.size() and the stop
+// envelopes) does not depend on history itself, so the carry is a look-back, not a recurrence: one thread per
+// frame finds its predecessor (inside the batch, else the carried state) and settles the envelope starts that
+// were waiting for it.
+__global__ void at3p_gha_history_kernel(int S, int C, int F, const GhaHistory* hist_state, ToneBlock* out, int out_stride, int out_off)
+{
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= (long long)S * F) return;
+    const int s = (int)(gi / F), f = (int)(gi % F);
+    ToneBlock* row = out + (size_t)s * out_stride + out_off;
+    ToneBlock& tb = row[f];
+    if (!tb.present) return;
+    int g = f - 1;
+    while (g >= 0 && !row[g].present) g--;
+    for (int ch = 0; ch < C; ch++)
+        for (int sb = 0; sb < tb.num_tone_bands; sb++) {
+            if ((unsigned)tb.sb[ch][sb][2] != kNeedHist) continue;
+            unsigned hs = kInit;
+            if (g >= 0) { if (row[g].n_sb[ch] > sb) hs = (unsigned)row[g].sb[ch][sb][3]; }
+            else if (hist_state[s].n_sb[ch] > sb) hs = hist_state[s].env_second[ch][sb];
+            tb.sb[ch][sb][2] = hs == kEmpty ? (int)kEmpty : 0;
+        }
+}
+
+// after the look-backs: the last non-null result of the batch becomes the carried history
+__global__ void at3p_gha_history_commit_kernel(int S, int C, int F, GhaHistory* hist_state, const ToneBlock* out, int out_stride, int out_off)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const ToneBlock* row = out + (size_t)s * out_stride + out_off;
+    int g = F - 1;
+    while (g >= 0 && !row[g].present) g--;
+    if (g < 0) return;
+    GhaHistory h = hist_state[s];
+    const int ntb = row[g].num_tone_bands;
+    h.n_sb[0] = ntb;
+    if (C == 2) h.n_sb[1] = ntb;
+    for (int ch = 0; ch < C; ch++)
+        for (int sb = 0; sb < ntb; sb++) h.env_second[ch][sb] = (unsigned)row[g].sb[ch][sb][3];
     hist_state[s] = h;
 }
 
@@ -1002,8 +1040,12 @@ void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, 
 }
 void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_state, ToneBlock* tones, int stride, int off, cudaStream_t st)
 {
-    ATDE_LAUNCH(at3p_gha_result_kernel, (unsigned)((S + 63) / 64), 64, 0, st, gha_tables(), (const GhaFrameOut*)frame_out, S, C, nA,
-                (GhaHistory*)hist_state, tones, stride, off);
+    const long long n = (long long)S * nA;
+    ATDE_LAUNCH(at3p_gha_result_kernel, (unsigned)((n + 63) / 64), 64, 0, st, gha_tables(), (const GhaFrameOut*)frame_out, S, C, nA,
+                tones, stride, off);
+    ATDE_LAUNCH(at3p_gha_history_kernel, (unsigned)((n + 63) / 64), 64, 0, st, S, C, nA, (const GhaHistory*)hist_state, tones, stride, off);
+    ATDE_LAUNCH(at3p_gha_history_commit_kernel, (unsigned)((S + 63) / 64), 64, 0, st, S, C, nA, (GhaHistory*)hist_state,
+                (const ToneBlock*)tones, stride, off);
 }
 bool gha_tables_ready() { return gha_tables() != nullptr; }
 

@@ -47,7 +47,7 @@ class AtdeError(RuntimeError):
 
 def load_library(path: os.PathLike | str | None = None) -> ctypes.CDLL:
     """Loads the C-ABI library and declares the prototypes of include/atde_b200.h."""
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("ATDE_LIB", LIB_PATH))   # ATDE_LIB: A/B a differently built library
     if not p.exists():
         raise AtdeError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)")

@@ -673,6 +673,9 @@ ATDE_D bool sb_insert(SbState& s, unsigned key, const GhaInfo& v)     // map::in
 // the lanes idle — then one thread per frame commits that frame's staged steps in the reference's order.
 constexpr int kGhaFB = 64;                // most frames per block batch (the launch picks fb <= kGhaFB)
 constexpr int kGhaThreads = 128;
+#ifndef ATDE_GHA_MINBLOCKS
+#define ATDE_GHA_MINBLOCKS 4              // resident blocks per SM the register budget is capped for
+#endif
 constexpr int kGhaItems = kGhaFB * kGhaTask;
 
 struct alignas(16) ItemState {            // global memory, per (frame slot, channel, subband) of a block; float4 copies
@@ -684,7 +687,7 @@ struct alignas(16) ItemState {            // global memory, per (frame slot, cha
 
 __device__ float g_zero64[64];            // look-ahead of the last frame of a stage-test run
 
-__global__ void __launch_bounds__(kGhaThreads, 4) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
+__global__ void __launch_bounds__(kGhaThreads, ATDE_GHA_MINBLOCKS) at3p_gha_search_kernel(const GhaTables* __restrict__ G,
                                                                        const float* __restrict__ bands,
                                                                        int S, int C, int F, int L, int j0, int fb,
                                                                        ItemState* items_g, GhaFrameOut* out)
@@ -1021,7 +1024,7 @@ size_t gha_history_bytes() { return sizeof(GhaHistory); }
 // frames per block batch: as many as keep one resident wave of blocks (4 per SM) busy, at most kGhaFB
 static int gha_fb_for(long long n_analyses)
 {
-    long long fb = (n_analyses + 148 * 4 - 1) / (148 * 4);
+    long long fb = (n_analyses + 148 * ATDE_GHA_MINBLOCKS - 1) / (148 * ATDE_GHA_MINBLOCKS);
     if (fb < 8) fb = 8;
     if (fb > kGhaFB) fb = kGhaFB;
     return (int)fb;
@@ -1030,7 +1033,7 @@ int gha_blocks_for(long long n_analyses)
 {
     const int fb = gha_fb_for(n_analyses);
     long long b = (n_analyses + fb - 1) / fb;
-    if (b > 148 * 4) b = 148 * 4;                     // one resident wave (launch bounds: 4 blocks per SM)
+    if (b > 148 * ATDE_GHA_MINBLOCKS) b = 148 * ATDE_GHA_MINBLOCKS;       // one resident wave
     return (int)(b < 1 ? 1 : b);
 }
 void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)

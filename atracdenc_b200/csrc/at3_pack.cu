@@ -671,7 +671,10 @@ ATDE_D unsigned tonal_bits(const PackShared& sh, int n_ton, int lane, unsigned p
     return 5u + (tcsgn ? 2u : 0u) + sum;
 }
 
-__global__ void __launch_bounds__(64) at3_alloc_pack_kernel(Geometry g, Buffers b)
+#ifndef ATDE_PACK_MINBLOCKS
+#define ATDE_PACK_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel(Geometry g, Buffers b)
 {
     __shared__ PackShared shm[2];
     __shared__ int s_shift;

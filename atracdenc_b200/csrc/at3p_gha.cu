@@ -888,6 +888,243 @@ __global__ void __launch_bounds__(kGhaThreads, ATDE_GHA_MINBLOCKS) at3p_gha_sear
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same search without block-wide rounds.  Frames are independent, and inside a frame the only ordering is
+// "all steps of a round, then the commit, then the next round" — so a frame advances on its own: every step
+// decrements its frame's counter when it finishes, the thread that brings it to zero commits the frame and
+// queues the next round's steps.  Warps pull up to 32 steps at a time from five queues (analyses; fits of 1, 2, 3
+// and >= 4 tones, so that a warp's lanes run the same code).  No barrier inside a batch: the tail rounds of
+// slow frames overlap with the busy rounds of others.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGhaQ = 5;
+struct DynShared {
+    unsigned short q[kGhaQ][kGhaItems];   // rings of step ids, 0xffff = empty slot
+    int head[kGhaQ], tail[kGhaQ];
+    int pending[kGhaFB], total[kGhaFB];
+    unsigned char cur[kGhaItems];         // which of the step's two residual buffers is Buf[sb]
+    int active_frames;
+};
+
+ATDE_D int vload(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+ATDE_D void dyn_push(DynShared& sh, int qi, int id)
+{
+    const int pos = atomicAdd(&sh.tail[qi], 1);
+    *reinterpret_cast<volatile unsigned short*>(&sh.q[qi][pos & (kGhaItems - 1)]) = (unsigned short)id;
+}
+
+// queue the steps of frame slot fs's next round; returns false if there is none (every subband closed)
+ATDE_D bool dyn_start_round(DynShared& sh, ItemState* items, int fs)
+{
+    int pend = 0;
+    for (int t = 0; t < kGhaTask; t++) pend += items[fs * 16 + t].sb.done != 16;
+    if (pend == 0) return false;
+    sh.pending[fs] = pend;
+    __threadfence_block();
+    for (int t = 0; t < kGhaTask; t++) {
+        const int idx = fs * 16 + t;
+        const SbState& sbs = items[idx].sb;
+        if (sbs.done == 16) continue;
+        if (sbs.n == 0) {
+            Staged& st = items[idx].st;
+            st.part1 = 0; st.n_new = 0; st.resid_valid = 0; st.analyzed = 0; st.psy_ok = 0;
+            st.env_first = sbs.env_first; st.env_second = sbs.env_second;
+            st.last_res_energy = sbs.last_res_energy; st.gapless = sbs.gapless; st.max_mag = sbs.max_mag;
+            __threadfence_block();
+            dyn_push(sh, 0, idx);
+        } else {
+            dyn_push(sh, sbs.n < 4 ? sbs.n : 4, idx);
+        }
+    }
+    return true;
+}
+
+// the commit pass of one frame (the reference's order: channel 0 subbands 0..7, then channel 1); returns `go`
+ATDE_D bool dyn_commit(DynShared& sh, ItemState* items, int fs, int C)
+{
+    int total = sh.total[fs];
+    bool progress[2] = {false, false};
+    for (int c2 = 0; c2 < C; c2++) {
+        bool prog = false;
+        for (int b2 = 0; b2 < kGhaSb; b2++) {
+            const int idx = fs * 16 + c2 * 8 + b2;
+            SbState& z = items[idx].sb;
+            if (z.done == 16) continue;
+            if (total >= 48) { prog = false; break; }                      // return false
+            const Staged& g = items[idx].st;
+            if (g.part1 != 0) {
+                z.env_first = g.env_first; z.env_second = g.env_second;
+                z.last_res_energy = g.last_res_energy; z.gapless = g.gapless;
+                if (g.part1 == 2) {
+                    sb_erase_key(z, z.last_added);
+                    total--;
+                    z.done = 16;
+                    continue;
+                }
+                z.n = 0;
+                for (int i = 0; i < g.n_new; i++) {
+                    z.max_mag = fmaxf(z.max_mag, g.fit[i].magnitude);
+                    sb_insert(z, freq_to_index(g.fit[i].frequency, (unsigned)b2), g.fit[i]);
+                }
+                if (g.resid_valid) sh.cur[idx] ^= 1;                      // the staged residual becomes Buf[sb]
+            }
+            const unsigned fi = freq_to_index(g.found.frequency, (unsigned)b2);
+            if (!g.psy_ok) { z.done = 16; continue; }
+            if (z.done == 0) {
+                sb_insert(z, fi, g.found);
+                z.last_added = fi;
+            } else {
+                unsigned next_key = 0, prev_key = 0;
+                bool has_nxt = false, has_prev = false;
+                for (int b3 = 0; b3 < kGhaSb; b3++) {
+                    const SbState& y = items[fs * 16 + c2 * 8 + b3].sb;
+                    for (int i = 0; i < y.n; i++) {
+                        if (y.key[i] >= fi) { if (!has_nxt) { has_nxt = true; next_key = y.key[i]; } }
+                        else { has_prev = true; prev_key = y.key[i]; }
+                    }
+                }
+                if (has_nxt && (next_key == fi || next_key - fi < 20u)) { z.done = 16; continue; }
+                if (has_prev && fi - prev_key < 20u) { z.done = 16; continue; }
+                if (z.done == 15) { z.done = 16; continue; }
+                sb_insert(z, fi, g.found);
+                z.last_added = fi;
+            }
+            z.done++;
+            total++;
+            prog = true;
+        }
+        progress[c2] = prog;
+    }
+    sh.total[fs] = total;
+    return (progress[0] || progress[1]) && total < 48;
+}
+
+// a step of frame slot fs has finished; the last one of the round commits and moves the frame on
+ATDE_D void dyn_step_done(DynShared& sh, ItemState* items, int fs, int C)
+{
+    __threadfence_block();
+    if (atomicSub(&sh.pending[fs], 1) != 1) return;
+    __threadfence_block();
+    const bool go = dyn_commit(sh, items, fs, C);
+    __threadfence_block();
+    if (!go || !dyn_start_round(sh, items, fs)) atomicSub(&sh.active_frames, 1);
+}
+
+__global__ void __launch_bounds__(kGhaThreads, ATDE_GHA_MINBLOCKS) at3p_gha_search_dyn_kernel(const GhaTables* __restrict__ G,
+                                                                       const float* __restrict__ bands,
+                                                                       int S, int C, int F, int L, int j0, int fb,
+                                                                       ItemState* items_g, GhaFrameOut* out)
+{
+    __shared__ DynShared sh;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n_items = fb * kGhaTask;
+    const long long n_frames = (long long)S * F;
+    TaskScratch scratch_local;
+    TaskScratch* ws = &scratch_local;
+    ItemState* items = items_g + (size_t)blockIdx.x * kGhaItems;
+    for (int i = tid; i < kGhaQ * kGhaItems; i += kGhaThreads) (&sh.q[0][0])[i] = 0xffffu;
+    if (tid < kGhaQ) { sh.head[tid] = 0; sh.tail[tid] = 0; }
+    __syncthreads();
+    for (long long base = (long long)blockIdx.x * fb; base < n_frames; base += (long long)gridDim.x * fb) {
+        for (int idx = tid; idx < n_items; idx += kGhaThreads) {
+            const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+            const bool live = base + fs < n_frames && ch < C;
+            SbState& me = items[idx].sb;
+            me.n = 0;
+            me.env_first = sb == 0 ? kInit : 0u;               // Envelopes[SUBBANDS] = {{INIT, INIT}}: element 0 only
+            me.env_second = sb == 0 ? kInit : 0u;
+            me.gapless = 0; me.done = live ? 0 : 16; me.max_mag = 0.0f; me.last_res_energy = 0.0f; me.last_added = 0;
+            sh.cur[idx] = 0;
+        }
+        for (int w = tid; w < n_items * 32; w += kGhaThreads) {
+            const int idx = w >> 5, q = w & 31;
+            const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+            const long long frame = base + fs;
+            if (frame < n_frames && ch < C) {
+                const int s = (int)(frame / F), f = (int)(frame % F);
+                const float* src = bands + (((size_t)s * C + ch) * L + j0 + f) * kFrame + sb * kSbSamples;
+                reinterpret_cast<float4*>(items[idx].buf)[q] = reinterpret_cast<const float4*>(src)[q];
+            }
+        }
+        if (tid == 0) {
+            long long nf = n_frames - base;
+            sh.active_frames = (int)(nf < fb ? nf : fb);
+        }
+        if (tid < fb) sh.total[tid] = 0;
+        __syncthreads();
+        if (tid < fb && base + tid < n_frames)
+            if (!dyn_start_round(sh, items, tid)) atomicSub(&sh.active_frames, 1);
+        __syncthreads();
+        for (;;) {
+            int qi = -1, h0 = 0, take = 0;
+            if (lane == 0) {
+                for (;;) {
+                    int best = -1, bestn = 0;
+                    for (int k = 0; k < kGhaQ; k++) {
+                        const int n = vload(&sh.tail[k]) - vload(&sh.head[k]);
+                        if (n > bestn) { bestn = n; best = k; }
+                    }
+                    if (best >= 0) {
+                        const int h = vload(&sh.head[best]);
+                        const int n = vload(&sh.tail[best]) - h;
+                        if (n <= 0) continue;
+                        const int tk = n < 32 ? n : 32;
+                        if (atomicCAS(&sh.head[best], h, h + tk) == h) { qi = best; h0 = h; take = tk; break; }
+                        continue;
+                    }
+                    if (vload(&sh.active_frames) <= 0) { qi = -2; break; }
+                    __nanosleep(100);                       // steps of other warps are still running
+                }
+            }
+            qi = __shfl_sync(0xffffffffu, qi, 0);
+            h0 = __shfl_sync(0xffffffffu, h0, 0);
+            take = __shfl_sync(0xffffffffu, take, 0);
+            if (qi == -2) break;
+            if (lane < take) {
+                volatile unsigned short* slot = &sh.q[qi][(h0 + lane) & (kGhaItems - 1)];
+                unsigned id;
+                while ((id = *slot) == 0xffffu) __nanosleep(20);
+                *slot = 0xffffu;
+                __threadfence_block();
+                const int idx = (int)id;
+                const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+                float* bcur = sh.cur[idx] ? items[idx].buf_new : items[idx].buf;
+                float* bnew = sh.cur[idx] ? items[idx].buf : items[idx].buf_new;
+                if (qi == 0) {
+                    task_analyze(G, sb, bcur, bnew, ws, items[idx].st);
+                    dyn_step_done(sh, items, fs, C);
+                } else {
+                    const long long frame = base + fs;
+                    const int s = (int)(frame / F), f = (int)(frame % F);
+                    const float* src = bands + (((size_t)s * C + ch) * L + j0 + f) * kFrame + sb * kSbSamples;
+                    const float* next_src = j0 + f + 1 < L ? src + kFrame : g_zero64;
+                    if (task_fit(G, items[idx].sb, sb, src, next_src, bnew, ws, items[idx].st)) {
+                        __threadfence_block();
+                        dyn_push(sh, 0, idx);
+                    } else {
+                        dyn_step_done(sh, items, fs, C);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n_items; idx += kGhaThreads) {
+            const int fs = idx >> 4, t = idx & 15, ch = t >> 3, sb = t & 7;
+            const long long frame = base + fs;
+            if (frame < n_frames && ch < C) {
+                const SbState& me = items[idx].sb;
+                GhaFrameOut& o = out[frame];
+                if (t == 0) o.total_tones = sh.total[fs];
+                o.n[ch][sb] = me.n;
+                for (int i = 0; i < me.n; i++) { o.key[ch][sb][i] = me.key[i]; o.info[ch][sb][i] = me.info[i]; }
+                o.env[ch][sb][0] = me.env_first; o.env[ch][sb][1] = me.env_second;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FillResultBuf / FillFolowerRes / AdjustEnvelope (at3p_gha.cpp:1499-1664) + the ResultBufHistory carry:
 // one thread per stream walks its frames in order.
 // ---------------------------------------------------------------------------------------------
@@ -1038,8 +1275,13 @@ int gha_blocks_for(long long n_analyses)
 }
 void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)
 {
+#ifndef ATDE_GHA_ROUNDS
+    ATDE_LAUNCH(at3p_gha_search_dyn_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
+                gha_fb_for((long long)S * nA), (ItemState*)scratch, (GhaFrameOut*)frame_out);
+#else   // the barrier-per-round version, kept for A/B runs
     ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
                 gha_fb_for((long long)S * nA), (ItemState*)scratch, (GhaFrameOut*)frame_out);
+#endif
 }
 void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_state, ToneBlock* tones, int stride, int off, cudaStream_t st)
 {

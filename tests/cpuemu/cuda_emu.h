@@ -8,6 +8,7 @@
 //
 // Supported subset = what the kernels use.  Warp collectives must be called by all 32 lanes.
 #pragma once
+#include <sched.h>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -207,6 +208,9 @@ inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, 
 inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicSub(int* p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicCAS(int* p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+inline void __nanosleep(unsigned) { sched_yield(); }
 inline int atomicMax(int* p, int v)
 {
     int old = __atomic_load_n(p, __ATOMIC_RELAXED);

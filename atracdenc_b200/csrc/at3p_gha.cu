@@ -888,6 +888,7 @@ __global__ void __launch_bounds__(kGhaThreads, ATDE_GHA_MINBLOCKS) at3p_gha_sear
 }
 
 // ---------------------------------------------------------------------------------------------
+// EXPERIMENT (not launched unless built with -DATDE_GHA_DYNAMIC; see launch_gha_search).
 // The same search without block-wide rounds.  Frames are independent, and inside a frame the only ordering is
 // "all steps of a round, then the commit, then the next round" — so a frame advances on its own: every step
 // decrements its frame's counter when it finishes, the thread that brings it to zero commits the frame and
@@ -1275,10 +1276,12 @@ int gha_blocks_for(long long n_analyses)
 }
 void launch_gha_search(const float* bands, int S, int C, int nA, int L, int j0, void* scratch, void* frame_out, int blocks, cudaStream_t st)
 {
-#ifndef ATDE_GHA_ROUNDS
+#ifdef ATDE_GHA_DYNAMIC
+    // the barrier-free per-frame scheduler: exact, but measured slower on B200 (137 ms vs 104 ms per 62,720 frames):
+    // warps often find fewer than 32 ready steps and a commit holds its whole warp; kept for the next round of work
     ATDE_LAUNCH(at3p_gha_search_dyn_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
                 gha_fb_for((long long)S * nA), (ItemState*)scratch, (GhaFrameOut*)frame_out);
-#else   // the barrier-per-round version, kept for A/B runs
+#else
     ATDE_LAUNCH(at3p_gha_search_kernel, (unsigned)blocks, kGhaThreads, 0, st, gha_tables(), bands, S, C, nA, L, j0,
                 gha_fb_for((long long)S * nA), (ItemState*)scratch, (GhaFrameOut*)frame_out);
 #endif

@@ -671,11 +671,14 @@ ATDE_D bool sb_insert(SbState& s, unsigned key, const GhaInfo& v)     // map::in
 // subband) steps that still have work into a list and spreads that list over its threads — subbands and
 // frames need very different numbers of rounds, and a fixed step-per-lane mapping left three quarters of
 // the lanes idle — then one thread per frame commits that frame's staged steps in the reference's order.
-constexpr int kGhaFB = 128;               // most frames per block batch (the launch picks fb <= kGhaFB)
-constexpr int kGhaThreads = 128;
-#ifndef ATDE_GHA_MINBLOCKS
-#define ATDE_GHA_MINBLOCKS 4              // resident blocks per SM the register budget is capped for
+#ifndef ATDE_GHA_THREADS
+#define ATDE_GHA_THREADS 256
 #endif
+#ifndef ATDE_GHA_MINBLOCKS
+#define ATDE_GHA_MINBLOCKS 2              // resident blocks per SM the register budget is capped for (128 registers)
+#endif
+constexpr int kGhaThreads = ATDE_GHA_THREADS;
+constexpr int kGhaFB = kGhaThreads;       // most frames per block batch (one committing thread per frame); the launch picks fb <= kGhaFB
 constexpr int kGhaItems = kGhaFB * kGhaTask;
 
 struct alignas(16) ItemState {            // global memory, per (frame slot, channel, subband) of a block; float4 copies

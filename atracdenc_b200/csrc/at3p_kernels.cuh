@@ -6,10 +6,9 @@
 // -> TAt3PBitStream::WriteFrame (src/atrac/at3p/at3p_bitstream.cpp:703-726), driven by
 // TAt3PEnc::TImpl::EncodeFrame (src/atrac/at3p/at3p.cpp:88-194).
 //
-// Built so far: the PQF analysis filterbank, the 16-band MDCT-256 and the frame packer (scale,
-// quantise, code-table choice, tonal block, bit writer).  The GHA tone extraction between the
-// filterbank and the MDCT is not built yet; until it is, ATRAC3plus is not reachable through
-// atde_create() and these kernels are exercised stage by stage against the reference's taps.
+// Kernels: the PQF analysis filterbank, the tone filter, the 16-band MDCT-256 and the frame packer
+// (scale, quantise, code-table choice, tonal block, bit writer) in at3p_kernels.cu; the GHA tone
+// search in at3p_gha.cu; at3p_pipeline.cu strings them together behind atde_create(codec 4).
 #pragma once
 #include "atde_cuda.h"
 

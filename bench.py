@@ -43,10 +43,9 @@ WORKLOADS = {
                                      settings="LP4 66150 bit/s joint stereo, gain control + tonal components on",
                                      desc="ATRAC3 LP4 (66 kbps, joint-stereo) encode, 1.25*10^6 frames per GPU "
                                           "(BASELINE.json configs[3] is this shard on each of 8 GPUs)"),
-    # BASELINE.json configs[4] asks for 10^6 frames; the first (correctness-first) tone-search kernel makes a
-    # step of that size take tens of seconds, so the default shard is 256 streams x 245 frames (62,720 frames);
-    # --streams / --frames scale it up.
-    "atrac3plus_stereo": dict(codec=4, step=2048, S=256, F=245, alg_bytes=32768, kbit=0,
+    # BASELINE.json configs[4] asks for 10^6 frames; the default shard is 1024 streams x 245 frames (250,880
+    # frames, ~20 GB of HBM with the per-batch workspaces); --streams / --frames scale it.
+    "atrac3plus_stereo": dict(codec=4, step=2048, S=1024, F=245, alg_bytes=32768, kbit=0,
                               kernel="at3p_pqf_kernel + at3p_mdct_kernel (16-band PQF, MDCT-256 x16)",
                               settings="reference defaults: GHA_ENABLED (pass input, write tonal, write residual)",
                               desc="ATRAC3PLUS encode, synthetic stereo batch (BASELINE.json configs[4], reduced shard)"),

@@ -436,6 +436,10 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
     return 0;
 }
 
+#ifndef ATDE_GHA_NEWTON_UNROLL
+#define ATDE_GHA_NEWTON_UNROLL 1
+#endif
+constexpr int kNewtonUnroll = ATDE_GHA_NEWTON_UNROLL;   // sample-loop unroll of the register-resident Newton fits
 // The same fit for 1..3 tones — by far the most frequent sizes — with one pass over the samples per Newton
 // loop: every sample's sin/cos pairs, the residual and all matrix terms are produced together and the
 // accumulators live in registers, so the [tone][sample] sin/cos arrays (the bulk of the local-memory traffic of
@@ -456,6 +460,7 @@ ATDE_D int adjust_newton_small(const float* pcm, GhaInfo* info, int sz, TaskScra
         }
         float fn = 0.0f;
         double dn = 0.0;
+#pragma unroll kNewtonUnroll
         for (int n = 0; n < sz; n++, fn += 1.0f, dn += 1.0) {
             float sf[DIM], cf[DIM];
             float t = pcm[n];

@@ -437,7 +437,7 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
 }
 
 #ifndef ATDE_GHA_NEWTON_UNROLL
-#define ATDE_GHA_NEWTON_UNROLL 1
+#define ATDE_GHA_NEWTON_UNROLL 2
 #endif
 constexpr int kNewtonUnroll = ATDE_GHA_NEWTON_UNROLL;   // sample-loop unroll of the register-resident Newton fits
 // The same fit for 1..3 tones — by far the most frequent sizes — with one pass over the samples per Newton

@@ -17,6 +17,15 @@
 #include "glibc_math.cuh"
 #include "stdsort_dev.cuh"
 
+// The allocation / pack kernel is bound by instruction fetch, not by arithmetic (16 warps per SM, each in a
+// different phase of a long program): loops the compiler would unroll are kept rolled so that the program
+// executed per frame stays small (183 -> 141 ms per 10^6 frames for the first three, see profiles/README.md).
+#ifdef ATDE_PACK_UNROLLED
+#define ATDE_ROLLED
+#else
+#define ATDE_ROLLED _Pragma("unroll 1")
+#endif
+
 namespace atde {
 namespace at3 {
 
@@ -490,7 +499,7 @@ struct __align__(16) PackShared {
 //   * with distinct |delta| among the visited candidates this is the reference's order exactly; if two
 //     of them tie, the library's sort order matters and quant_unit_exact redoes the block.
 // Returns (for need lanes) clc | vlc << 16 and the energy ratio e1/e2.
-ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int start, int len, float e1, float& err_out)
+ATDE_NOINLINE unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int start, int len, float e1, float& err_out)
 {
     const unsigned nm = __ballot_sync(0xffffffffu, need);
     sh.wl_now[lane] = need ? (unsigned char)wl : 0;
@@ -517,6 +526,7 @@ ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int s
     unsigned vlc = 0;
     if (need) {
         // 8 lines per trip (every BFU length is a multiple of 8): the loads stay off the dependent chain
+#pragma unroll 1
         for (int j = 0; j < len; j += 8) {
             const float4 a = *reinterpret_cast<const float4*>(sh.pq + start + j);
             const float4 c = *reinterpret_cast<const float4*>(sh.pq + start + j + 4);
@@ -576,6 +586,7 @@ ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int s
             while (up ? (e2 < e1) : (e2 > e1)) {
                 float best = 2.0f;
                 int bi = -1, ties = 0;
+#pragma unroll 2
                 for (int k = 0; k < nc; k++) {
                     const float key = ckey[k];
                     if (key > last) {
@@ -588,8 +599,13 @@ ATDE_D unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int s
                     // two visited candidates share |delta|: the reference's order is libstdc++'s
                     const float er = quant_unit_exact(sh.sv + start, len, mulw, inv2w, m);
                     unsigned v = 0;
-                    if (wl > 1) { for (int j = 0; j < len; j++) v += vlc_bits_of(wl, m[j]); }
-                    else { for (int j = 0; j < len / 2; j++) v += vlc_pair_bits(m[2 * j], m[2 * j + 1]); }
+                                        if (wl > 1) {
+                        ATDE_ROLLED
+                        for (int j = 0; j < len; j++) v += vlc_bits_of(wl, m[j]);
+                    } else {
+                        ATDE_ROLLED
+                        for (int j = 0; j < len / 2; j++) v += vlc_pair_bits(m[2 * j], m[2 * j + 1]);
+                    }
                     vlc = v;
                     exact_err = er;
                     used_exact = true;
@@ -646,6 +662,7 @@ ATDE_D unsigned tonal_bits(const PackShared& sh, int n_ton, int lane, unsigned p
     bool leader = active;
     int start_val = 0, limiter = 0, nsub = 0;
     unsigned flags = 0, bits = 0;
+    ATDE_ROLLED
     for (int j = 0; j < n_ton; j++) {
         const int kj = __shfl_sync(0xffffffffu, key, j);
         const int pj = __shfl_sync(0xffffffffu, pos, j);
@@ -697,9 +714,11 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     if (lane < n_ton) {
         const TonalBlock& tb = tl->b[lane];
         sh.ton_pos[lane] = tb.pos; sh.ton_bfu[lane] = tb.bfu; sh.ton_len[lane] = tb.len; sh.ton_sfi[lane] = tb.sfi;
+        ATDE_ROLLED
         for (int q = 2; q < 8; q++) {
             unsigned v = 0;
             const int off = kHuffOff[q];
+            ATDE_ROLLED
             for (int z = 0; z < tb.len; z++)
                 v += kHuffBits[off + huff_index(__float2int_rn(fmul(tb.val[z], kMaxQuant[q])))];
             sh.ton_vlc[lane][q] = (unsigned char)v;
@@ -758,14 +777,17 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     const float sfi_term = __fdiv_rn(sfi_corr, xdiv);
     const float fix = (float)kFixedAlloc[lane];
     int n_ton_mine = 0;                                          // tonal blocks whose first line is in this BFU
+    ATDE_ROLLED
     for (int t = 0; t < n_ton; t++) n_ton_mine += (sh.ton_bfu[t] == lane);
     // AnalizeScaleFactorSpread (atrac_psy_common.cpp:105-124): sequential float sums
     float spread;
     {
         float sacc = 0.0f;
+        ATDE_ROLLED
         for (int i = 0; i < 32; i++) sacc = fadd(sacc, (float)__shfl_sync(0xffffffffu, sfi, i));
         sacc = __fdiv_rn(sacc, 32.0f);
         float sigma = 0.0f;
+        ATDE_ROLLED
         for (int i = 0; i < 32; i++) {
             float t = fsub((float)__shfl_sync(0xffffffffu, sfi, i), sacc);
             t = fmul(t, t);
@@ -779,6 +801,7 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     unsigned cached = 0;                                         // bit w: (lane, w) is in the cache
     unsigned mant_wl = 0;                                        // word length whose mantissas sh.mant holds for this BFU
     float e1 = 0.0f;                                             // QuantMantisas' e1: energy of the scaled values, sequential
+    ATDE_ROLLED
     for (int j = 0; j < len; j += 8) {
         const float4 a = *reinterpret_cast<const float4*>(sh.sv + start + j);
         const float4 c = *reinterpret_cast<const float4*>(sh.sv + start + j + 4);
@@ -872,12 +895,15 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
             put(0x28, 6);
         }
         put(3, 2);                                               // numQmfBand - 1
+        ATDE_ROLLED
         for (int band = 0; band < 4; band++) {
             put(cv[band].n, 3);
+            ATDE_ROLLED
             for (int i = 0; i < cv[band].n; i++) { put(cv[band].level[i], 4); put(cv[band].loc[i], 5); }
         }
         // EncodeTonalComponents (:382-524)
         int order[kMaxTonal], keys[kMaxTonal], na = 0;
+        ATDE_ROLLED
         for (int t = 0; t < n_ton; t++) {
             if (sh.ton_bfu[t] >= num_bfu) continue;
             const int quant = max(2, min((int)sh.prec[sh.ton_bfu[t]] + 4, 7));
@@ -885,8 +911,10 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         }
         // count subgroups first (tcsgn is written ahead of them)
         int tcsgn = 0;
+        ATDE_ROLLED
         for (int key = 16; key < 64; key++) {
             int startv = 0, limiter = 0; bool open = false;
+            ATDE_ROLLED
             for (int a = 0; a < na; a++) {
                 if (keys[a] != key) continue;
                 const int p = sh.ton_pos[order[a]];
@@ -900,8 +928,10 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         put((unsigned)tcsgn, 5);
         if (tcsgn) {
             put(0, 2);
+            ATDE_ROLLED
             for (int key = 16; key < 64; key++) {
                 int mem[kMaxTonal], nm = 0;
+                ATDE_ROLLED
                 for (int a = 0; a < na; a++) if (keys[a] == key) mem[nm++] = order[a];
                 if (!nm) continue;
                 const int quant = key >> 3, coded = key & 7;
@@ -916,23 +946,30 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
                         a1++;
                     }
                     unsigned char cnt[16];
+                    ATDE_ROLLED
                     for (int j = 0; j < 16; j++) cnt[j] = 0;
+                    ATDE_ROLLED
                     for (int a = a0; a < a1; a++) cnt[sh.ton_pos[mem[a]] >> 6]++;
                     unsigned bandf = 0;
+                    ATDE_ROLLED
                     for (int j = 0; j < 16; j++) if (cnt[j]) bandf |= 1u << (j >> 2);
+                    ATDE_ROLLED
                     for (int j = 0; j < 4; j++) put((bandf >> j) & 1u, 1);
                     put((unsigned)(coded - 1), 3);
                     put((unsigned)quant, 3);
                     int lastp = a0;
+                    ATDE_ROLLED
                     for (int j = 0; j < 16; j++) {
                         if (!((bandf >> (j >> 2)) & 1u)) continue;
                         put(cnt[j], 3);
+                        ATDE_ROLLED
                         for (int k = lastp; k < lastp + cnt[j]; k++) {
                             const int t = mem[k];
                             put(sh.ton_sfi[t], 6);
                             put((unsigned)(sh.ton_pos[t] - j * 64), 6);
                             const TonalBlock& tb = tl->b[t];
                             const int off = kHuffOff[quant];
+                            ATDE_ROLLED
                             for (int z = 0; z < tb.len; z++) {
                                 const int hi = huff_index(__float2int_rn(fmul(tb.val[z], kMaxQuant[quant])));
                                 put(kHuffCode[off + hi], kHuffBits[off + hi]);
@@ -978,8 +1015,10 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         if (mode) {
             if (prec > 1u) {
                 const int nb = kClcLen[prec];
+                ATDE_ROLLED
                 for (int j = 0; j < len; j++) { put_bits3(sh.words, cap_bits, p, nb, (unsigned)m[j] & ((1u << nb) - 1u)); p += nb; }
             } else {
+                ATDE_ROLLED
                 for (int j = 0; j < len / 2; j++) {
                     const unsigned code = ((unsigned)kClcIdx[m[2 * j] + 2] << 2) | kClcIdx[m[2 * j + 1] + 2];
                     put_bits3(sh.words, cap_bits, p, 4, code); p += 4;
@@ -988,11 +1027,13 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         } else {
             const int off = kHuffOff[prec];
             if (prec > 1u) {
+                ATDE_ROLLED
                 for (int j = 0; j < len; j++) {
                     const int hi = huff_index(m[j]);
                     put_bits3(sh.words, cap_bits, p, kHuffBits[off + hi], kHuffCode[off + hi]); p += kHuffBits[off + hi];
                 }
             } else {
+                ATDE_ROLLED
                 for (int j = 0; j < len / 2; j++) {
                     const int hi = kVlcPairIdx[3 * (m[2 * j] + 1) + (m[2 * j + 1] + 1)];
                     put_bits3(sh.words, cap_bits, p, kHuffBits[hi], kHuffCode[hi]); p += kHuffBits[hi];

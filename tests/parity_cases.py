@@ -681,3 +681,32 @@ def check_at3p_batch_split_invariance(lib, S=2, F=9, C=2, cuts=(1, 3, 2), seed=1
     enc.close()
     assert [p.shape[1] for p in parts] == [cuts[0] - 1] + list(cuts[1:]) + [F - sum(cuts)]
     assert np.array_equal(np.concatenate(parts, axis=1), whole)
+
+
+def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700):
+    """atde_encode_batch() splits the streams of a batch into chunks (a short first one, then equal ones, on two
+    pipeline slots).  Forced down to four streams per chunk (1 + 4 + 4 + ...), the result must equal the
+    single-chunk batch, also on the continuation batch that starts from carried state."""
+    import os
+    step = {ab.CODEC_ATRAC1: 512, ab.CODEC_ATRAC3: 1024, ab.CODEC_ATRAC3PLUS: 2048}[codec]
+    rng = np.random.default_rng(seed)
+    pcm = np.stack([tl.synth_rich(2 * F, step, C, seed=seed + s, kind=("mix", "tones", "steps")[s % 3]) for s in range(S)])
+    pcm = (pcm * rng.uniform(0.2, 1.0, size=(S, 1, 1))).astype(np.float32)
+    old = os.environ.pop("ATDE_CHUNK_STREAMS", None)
+    try:
+        outs = []
+        for streams in (None, "4"):
+            if streams:
+                os.environ["ATDE_CHUNK_STREAMS"] = streams
+            enc = ab.Encoder(codec, C, lib=lib)
+            a = enc.encode(pcm[:, :F * step], S, want_sizes=True)
+            b = enc.encode(pcm[:, F * step:], S, want_sizes=True)
+            enc.close()
+            outs.append((a, b))
+        for (x, xs), (y, ys) in zip(outs[0], outs[1]):
+            assert np.array_equal(xs, ys)
+            assert np.array_equal(x, y)
+    finally:
+        os.environ.pop("ATDE_CHUNK_STREAMS", None)
+        if old is not None:
+            os.environ["ATDE_CHUNK_STREAMS"] = old

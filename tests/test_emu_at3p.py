@@ -56,3 +56,10 @@ def test_encoder_vs_oracle(emu_lib):
 def test_encoder_batch_split_invariance(emu_lib):
     pc.check_at3p_batch_split_invariance(emu_lib, S=2, F=9, C=2)
     pc.check_at3p_batch_split_invariance(emu_lib, S=1, F=7, C=1, cuts=(2, 1, 1), seed=1310)
+
+
+def test_host_chunking(emu_lib):
+    import atracdenc_b200 as ab
+    pc.check_host_chunking(emu_lib, ab.CODEC_ATRAC1, S=11, F=4)
+    pc.check_host_chunking(emu_lib, ab.CODEC_ATRAC3, S=11, F=3)
+    pc.check_host_chunking(emu_lib, ab.CODEC_ATRAC3PLUS, S=10, F=2)

@@ -57,3 +57,10 @@ def test_encoder_vs_oracle(gpu_lib):
 def test_encoder_batch_split_invariance(gpu_lib):
     pc.check_at3p_batch_split_invariance(gpu_lib, S=4, F=20, C=2, cuts=(1, 7, 4))
     pc.check_at3p_batch_split_invariance(gpu_lib, S=2, F=9, C=1, cuts=(2, 1, 3), seed=1310)
+
+
+def test_host_chunking(gpu_lib):
+    import atracdenc_b200 as ab
+    pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC1, S=11, F=4)
+    pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC3, S=11, F=3)
+    pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC3PLUS, S=10, F=2)

@@ -681,10 +681,14 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
     const size_t pcm_per_stream = (size_t)F * e->frame_samples * C;            // floats
     const size_t out_per_stream = (size_t)n_out * e->units_per_frame * e->unit_bytes;
     const size_t units_per_stream = (size_t)n_out * e->units_per_frame;
-    // chunk by streams so H2D of chunk k+1 overlaps compute of chunk k (two pipeline slots).  Large chunks keep
-    // the kernels efficient (measured on the 10^6-frame ATRAC3 batch: 96 MiB 351 ms, 192 MiB 326 ms, 384 MiB
-    // 294 ms, 1 GiB 286 ms per step); the first chunk is a quarter of the size so the device starts early.
-    size_t target_floats = (size_t)192 << 20;                                   // ~768 MiB of PCM per chunk
+    // chunk by streams so H2D of chunk k+1 overlaps compute of chunk k (two pipeline slots).  The compute-bound
+    // codecs want large chunks (kernel tails; measured on the 10^6-frame ATRAC3 batch: 96 MiB 351 ms, 192 MiB
+    // 326 ms, 384 MiB 294 ms, 1 GiB 286 ms per step), ATRAC1 is bound by the H2D copy and wants a short last
+    // chunk.  The first chunk is a quarter of the size so the device starts early; the rest is split evenly.
+    // (Not for ATRAC3plus: its tone search has a long per-launch tail that the next chunk's kernels fill, and
+    // 191 + 191 + ... + 69 streams measured 350 ms per 250,880 frames against 373 ms with the short first chunk
+    // and 494 ms with seven equal ones.)
+    size_t target_floats = (size_t)(at3 ? 192 : 48) << 20;                      // ~768 / ~192 MiB of PCM per chunk
     if (const char* env = getenv("ATDE_CHUNK_MIB")) {                           // tuning knob (MiB of PCM per chunk)
         const long v = atol(env);
         if (v > 0) target_floats = (size_t)v << 18;
@@ -696,7 +700,11 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
     }
     if (chunk < 1) chunk = 1;
     if (chunk > S) chunk = S;
-    const int first = chunk >= 4 && chunk < S ? chunk / 4 : chunk;
+    const int first = !at3p && chunk >= 4 && chunk < S ? chunk / 4 : chunk;
+    if (!at3p && first < S) {
+        const int rest = S - first, pieces = (rest + chunk - 1) / chunk;
+        chunk = (rest + pieces - 1) / pieces;
+    }
     int slot = 0;
     for (int s0 = 0, n = first; s0 < S; s0 += n, n = chunk, slot ^= 1) {
         if (n > S - s0) n = S - s0;

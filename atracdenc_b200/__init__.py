@@ -25,7 +25,7 @@ TAP_BANDS, TAP_CURVES, TAP_GSCALE, TAP_ENERGY, TAP_TONAL, TAP_GAIN = 7, 8, 9, 10
 
 EXPORTS = [
     "atde_default_settings", "atde_create", "atde_destroy", "atde_frame_samples",
-    "atde_units_per_frame", "atde_unit_bytes", "atde_lookahead_frames", "atde_output_frames", "atde_encode_batch",
+    "atde_units_per_frame", "atde_unit_bytes", "atde_lookahead_frames", "atde_output_frames", "atde_encode_batch", "atde_encode_batch_i16",
     "atde_encode_batch_device", "atde_sync", "atde_reset", "atde_cuda_stream",
     "atde_launch_count", "atde_set_profiling", "atde_kernel_times", "atde_debug_tap", "atde_debug_math", "atde_last_error", "atde_version",
 ]
@@ -65,6 +65,7 @@ def load_library(path: os.PathLike | str | None = None) -> ctypes.CDLL:
     lib.atde_output_frames.argtypes = [vp, i64]
     lib.atde_output_frames.restype = i64
     lib.atde_encode_batch.argtypes = [vp, vp, i32, i64, vp, vp]
+    lib.atde_encode_batch_i16.argtypes = [vp, vp, i32, i64, vp, vp]
     lib.atde_encode_batch_device.argtypes = [vp, vp, i32, i64, vp, vp]
     lib.atde_cuda_stream.argtypes = [vp]
     lib.atde_cuda_stream.restype = vp
@@ -134,6 +135,25 @@ class Encoder:
             self.h, pcm.ctypes.data, n_streams, F, out.ctypes.data,
             sizes.ctypes.data if want_sizes else None))
         return (out, sizes) if want_sizes else out
+
+    def encode_i16(self, pcm: np.ndarray, n_streams: int, want_sizes: bool = False):
+        """Like encode(), from int16 PCM [S][F*frame_samples][C] (converted on the device, value / 32768)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        per_stream = pcm.size // n_streams
+        assert per_stream * n_streams == pcm.size
+        F = per_stream // (self.frame_samples * self.channels)
+        assert F * self.frame_samples * self.channels == per_stream, "whole frames only"
+        Fo = self.output_frames(F)
+        out = np.empty((n_streams, Fo, self.units_per_frame, self.unit_bytes), dtype=np.uint8)
+        sizes = np.empty((n_streams, Fo, self.units_per_frame), dtype=np.int32) if want_sizes else None
+        self._check(self.lib.atde_encode_batch_i16(
+            self.h, pcm.ctypes.data, n_streams, F, out.ctypes.data,
+            sizes.ctypes.data if want_sizes else None))
+        return (out, sizes) if want_sizes else out
+
+    def encode_ptr_i16(self, pcm_ptr: int, n_streams: int, n_frames: int, out_ptr: int, sizes_ptr: int = 0):
+        """Host-pointer variant of encode_i16 (pinned buffers owned by the caller)."""
+        self._check(self.lib.atde_encode_batch_i16(self.h, pcm_ptr, n_streams, n_frames, out_ptr, sizes_ptr or None))
 
     def output_frames(self, n_frames: int) -> int:
         """Output frames per stream the next batch of n_frames will produce (ATRAC3's first batch: n-1)."""

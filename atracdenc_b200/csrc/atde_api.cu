@@ -60,6 +60,7 @@ template <class T> struct DevBuf {
 // Per-chunk scratch (one per pipeline slot)
 struct Workspace {
     DevBuf<float> pcm;              // host path only
+    DevBuf<short> pcm16;            // host path, int16 ingest only
     DevBuf<float> specs;
     DevBuf<unsigned char> masks;
     DevBuf<float> chloud;
@@ -75,7 +76,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     void release()
     {
-        pcm.release(); specs.release(); masks.release(); chloud.release(); loud.release();
+        pcm.release(); pcm16.release(); specs.release(); masks.release(); chloud.release(); loud.release();
         out.release(); sizes.release(); tap_sfi.release(); tap_wl.release();
         bands.release(); gain.release(); gstat.release(); gprev.release(); gscale.release();
         energy.release(); hist_tmp.release(); curves.release(); tonal.release(); sfi.release();
@@ -505,6 +506,31 @@ int ensure_state(atde_encoder* e, int S)
 
 } // namespace
 
+namespace {
+// int16 PCM -> the normalised float the reference's reader hands to the PCM engine: libsndfile's sf_readf_float
+// on a PCM_16 file multiplies by 1.0 / 0x8000 (src/pcm_io_sndfile.cpp:111-113 -> SndfileHandle::readf(float*)),
+// exact in fp32.  8 samples per thread (one 16-byte load, two 16-byte stores).
+__global__ void pcm_i16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out, long long n)
+{
+    const long long n8 = n >> 3;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+        const int w[4] = {(int)v.x, (int)v.y, (int)v.z, (int)v.w};
+        float f[8];
+        for (int k = 0; k < 4; k++) {
+            f[2 * k] = __fmul_rn((float)(short)(w[k] & 0xffff), 1.0f / 32768.0f);
+            f[2 * k + 1] = __fmul_rn((float)(short)(w[k] >> 16), 1.0f / 32768.0f);
+        }
+        reinterpret_cast<float4*>(out)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __fmul_rn((float)in[i], 1.0f / 32768.0f);
+}
+
+} // namespace
+
 extern "C" {
 
 const char* atde_last_error(void) { return g_err.c_str(); }
@@ -663,9 +689,22 @@ int atde_encode_batch_device(atde_encoder* e, const float* d_pcm, int32_t S, int
     return rc;
 }
 
+static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* pcm16, int32_t S, int64_t F, uint8_t* out, int32_t* sizes);
+
 int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
 {
     if (!e || !pcm || !out) return fail(ATDE_ERR_INVALID, "null argument");
+    return encode_batch_host(e, pcm, nullptr, S, F, out, sizes);
+}
+
+int atde_encode_batch_i16(atde_encoder* e, const int16_t* pcm, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
+{
+    if (!e || !pcm || !out) return fail(ATDE_ERR_INVALID, "null argument");
+    return encode_batch_host(e, nullptr, pcm, S, F, out, sizes);
+}
+
+static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* pcm16, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
+{
     if (S <= 0 || F <= 0) return fail(ATDE_ERR_INVALID, "empty batch (S=%d, F=%lld)", S, (long long)F);
     if (F > (1 << 21)) return fail(ATDE_ERR_INVALID, "too many frames per stream in one batch");
     CK(cudaSetDevice(e->cfg.device));
@@ -712,8 +751,17 @@ int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t S, int64_t F, u
         if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) return rc;
         if ((rc = w.out.ensure((size_t)n * out_per_stream + 1))) return rc;
         if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return rc;
-        CK(cudaMemcpyAsync(w.pcm.p, pcm + (size_t)s0 * pcm_per_stream, (size_t)n * pcm_per_stream * sizeof(float),
-                           cudaMemcpyHostToDevice, w.stream));
+        if (pcm16) {
+            const size_t cnt = (size_t)n * pcm_per_stream;
+            if ((rc = w.pcm16.ensure(cnt + 8))) return rc;
+            CK(cudaMemcpyAsync(w.pcm16.p, pcm16 + (size_t)s0 * pcm_per_stream, cnt * sizeof(short), cudaMemcpyHostToDevice, w.stream));
+            const unsigned blocks = (unsigned)std::min<size_t>((cnt / 8 + 255) / 256 + 1, (size_t)148 * 16);
+            ATDE_LAUNCH(pcm_i16_to_f32_kernel, blocks, 256, 0, w.stream, (const short*)w.pcm16.p, w.pcm.p, (long long)cnt);
+            e->launches += 1;
+        } else {
+            CK(cudaMemcpyAsync(w.pcm.p, pcm + (size_t)s0 * pcm_per_stream, (size_t)n * pcm_per_stream * sizeof(float),
+                               cudaMemcpyHostToDevice, w.stream));
+        }
         if (at3p) {
             const char* why = "";
             atde::at3p::Profiler prof;

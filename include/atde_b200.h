@@ -101,6 +101,14 @@ int64_t atde_output_frames(const atde_encoder* e, int64_t n_frames);
 int atde_encode_batch(atde_encoder* e, const float* pcm, int32_t n_streams, int64_t n_frames,
                       uint8_t* out, int32_t* sizes);
 
+/* Same, from interleaved 16-bit PCM [S][F*frame_samples][channels] (what a WAV file holds): half the host->device
+ * bytes.  The samples are converted on the device the way the reference's reader converts them before the PCM
+ * engine sees them — libsndfile's sf_readf_float on a PCM_16 file, value * (1 / 0x8000)
+ * (src/pcm_io_sndfile.cpp:111-113, src/wav.cpp:46-61) — so the result equals atde_encode_batch() on those
+ * floats.  SURVEY.md 8(f) rank 2. */
+int atde_encode_batch_i16(atde_encoder* e, const int16_t* pcm, int32_t n_streams, int64_t n_frames,
+                          uint8_t* out, int32_t* sizes);
+
 /* Same, with pcm/out/sizes already resident in DEVICE memory of the handle's GPU; enqueued on the
  * handle's stream, returns without synchronising (use atde_sync). */
 int atde_encode_batch_device(atde_encoder* e, const float* d_pcm, int32_t n_streams, int64_t n_frames,

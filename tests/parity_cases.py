@@ -710,3 +710,22 @@ def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700):
         os.environ.pop("ATDE_CHUNK_STREAMS", None)
         if old is not None:
             os.environ["ATDE_CHUNK_STREAMS"] = old
+
+
+def check_i16_ingest(lib, codec, C=2, S=3, F=5, seed=1800):
+    """atde_encode_batch_i16 == atde_encode_batch on the floats the reference's reader would produce
+    (libsndfile: int16 * (1 / 0x8000)), across a continuation batch; extreme sample values included."""
+    step = {ab.CODEC_ATRAC1: 512, ab.CODEC_ATRAC3: 1024, ab.CODEC_ATRAC3PLUS: 2048}[codec]
+    pcm = np.stack([tl.synth_rich(2 * F, step, C, seed=seed + s, kind=("mix", "tones", "steps")[s % 3]) for s in range(S)])
+    q = np.clip(np.rint(pcm * 32768.0), -32768, 32767).astype(np.int16)
+    q[0, :4, :] = np.array([[-32768, 32767], [32767, -32768], [0, -1], [1, 0]], np.int16)[:, :C]
+    f = (q.astype(np.float32) * np.float32(1.0 / 32768.0)).astype(np.float32)
+    enc = ab.Encoder(codec, C, lib=lib)
+    a1, s1 = enc.encode(f[:, :F * step], S, want_sizes=True)
+    a2, s2 = enc.encode(f[:, F * step:], S, want_sizes=True)
+    enc.reset()
+    b1, t1 = enc.encode_i16(q[:, :F * step], S, want_sizes=True)
+    b2, t2 = enc.encode_i16(q[:, F * step:], S, want_sizes=True)
+    enc.close()
+    assert np.array_equal(s1, t1) and np.array_equal(s2, t2)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)

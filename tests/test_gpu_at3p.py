@@ -64,3 +64,11 @@ def test_host_chunking(gpu_lib):
     pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC1, S=11, F=4)
     pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC3, S=11, F=3)
     pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC3PLUS, S=10, F=2)
+
+
+def test_i16_ingest(gpu_lib):
+    import atracdenc_b200 as ab
+    pc.check_i16_ingest(gpu_lib, ab.CODEC_ATRAC1, S=3, F=5)
+    pc.check_i16_ingest(gpu_lib, ab.CODEC_ATRAC1, C=1, S=2, F=3, seed=1810)
+    pc.check_i16_ingest(gpu_lib, ab.CODEC_ATRAC3, S=3, F=4)
+    pc.check_i16_ingest(gpu_lib, ab.CODEC_ATRAC3PLUS, S=2, F=3)

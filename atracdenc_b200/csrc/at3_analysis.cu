@@ -898,9 +898,36 @@ ATDE_D float curve_level(const DevTables* T, const Curve& cv, int pos)
     return 1.0f;
 }
 
-// Out-of-line copy for the MDCT kernel: curves are rare there and the inlined loop, repeated per
-// sample slot, made the kernel overflow the instruction cache.
-ATDE_NOINLINE float curve_level_call(const DevTables* T, const Curve* cv, int pos) { return curve_level(T, *cv, pos); }
+
+// The same divisors for all 256 positions of a band at once, by a whole warp: lane g owns positions 8g .. 8g+7,
+// which lie in one 8-sample step of the curve.  curve_level() picks the first point i with pos < 8 loc[i] + 8,
+// i.e. g <= loc[i]; left of the ramp (g < loc[i]) the level is constant, inside it (g == loc[i]) it is
+// level * ginc^r built by r successive multiplications, exactly the chain of the per-sample loop.
+ATDE_D void curve_levels_warp(const DevTables* T, const Curve& cv, int lane, float* dst)
+{
+    float v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = 1.0f;
+    for (int i = 0; i < cv.n; i++) {
+        const int loc = cv.loc[i];
+        if (lane <= loc) {
+            float level = T->gain_level[cv.level[i]];
+            float ginc = 1.0f;
+            if (lane == loc) {
+                const int inc = ((i + 1) < cv.n ? (int)cv.level[i + 1] : 4) - (int)cv.level[i] + 15;
+                ginc = T->gain_interp[inc];
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                v[r] = level;
+                if (lane == loc) level = fmul(level, ginc);
+            }
+            break;
+        }
+    }
+    *reinterpret_cast<float4*>(dst + 8 * lane) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 8 * lane + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
 
 // SafeEnergyScale (atrac3denc.cpp:143-152)
 ATDE_D float safe_energy_scale(float orig, float mod)
@@ -924,13 +951,16 @@ ATDE_D float safe_energy_scale(float orig, float mod)
 //            holds k + 8a + 32b, a = 2ap, 2ap+1, b = 0..3; radix-4 m=32 over b; post-twiddle
 //            (mdct.h:92-101); spectrum staged in the tile and written out as coalesced float4
 // Every butterfly keeps kissfft's operation order (kissfft_dev.cuh), so the regrouping is exact.
-// The loop body is kept small on purpose (two bands per iteration, rare gain-curve work out of line):
-// the fully unrolled four-band version missed the instruction cache on every warp.
+// The loop body is kept small on purpose (two bands per iteration): the fully unrolled four-band version missed
+// the instruction cache on every warp.  Gain-curve divisors are built once per band by the whole warp
+// (curve_levels_warp) instead of per sample: the per-sample curve walk was 28 % of this kernel's instructions
+// and 45 % of its stall samples on the bench signal (ncu v6).
 constexpr int kMdctWarps = 4;
 constexpr int kMdctBandStride = 520;                 // floats; keeps float4 alignment, shifts banks by 8
 constexpr int kMdctXchStride = 152;                  // cpx per band in the exchange layout (16 blocks x 9, +8)
 constexpr int kMdctOutStride = 264;
-constexpr int kMdctTile = 7 * 256;                   // floats per warp: the rare path's 7 x 256 squares is the largest user
+constexpr int kMdctLevels = 2 * kMdctBandStride;     // floats: divisor tables of the band in work (its own curve, the previous frame's)
+constexpr int kMdctTile = kMdctLevels + 512;         // floats per warp: two MDCT inputs (or 7 x 128 energy terms) + the two tables
 
 __global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g, Buffers b)
 {
@@ -983,37 +1013,49 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g
             const Curve& cc = s_cv[warp][band][1];
             const Curve& pc = s_cv[warp][band][0];
             const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
-#pragma unroll 1
-            for (int i = lane; i < 256; i += 32) {
-                const float x = bp[i];
-                const float xm = cc.n ? __fdiv_rn(x, curve_level_call(T, &cc, i)) : x;
-                const float wi = s_win[i], wr = s_win[255 - i];
-                float prev, y = 0.0f, ym = 0.0f;
-                if (f == 0) {
-                    prev = b.prevhalf[(sc * 4 + band) * 256 + i];
-                } else {
-                    y = bp[i - 256];
-                    ym = pc.n ? __fdiv_rn(y, curve_level_call(T, &pc, i)) : y;
-                    prev = fmul(wi, ym);
-                }
-                float v;
-                tl[0 * 256 + i] = fmul(prev, prev);
-                v = fmul(x, wr);  tl[1 * 256 + i] = fmul(v, v);
-                v = fmul(xm, wr); tl[2 * 256 + i] = fmul(v, v);
-                v = fmul(x, wi);  tl[3 * 256 + i] = fmul(v, v);
-                v = fmul(xm, wi); tl[4 * 256 + i] = fmul(v, v);
-                v = fmul(y, wi);  tl[5 * 256 + i] = fmul(v, v);
-                v = fmul(ym, wi); tl[6 * 256 + i] = fmul(v, v);
-            }
+            float* lv_c = tl + kMdctLevels;
+            float* lv_p = lv_c + 256;
             __syncwarp();
-            if (lane < 7) {
-                float a = 0.0f;
-                for (int i = 0; i < 256; i += 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(&tl[lane * 256 + i]);
-                    a = fadd(a, q.x); a = fadd(a, q.y); a = fadd(a, q.z); a = fadd(a, q.w);
+            if (cc.n) curve_levels_warp(T, cc, lane, lv_c);
+            if (f != 0 && pc.n) curve_levels_warp(T, pc, lane, lv_p);
+            __syncwarp();
+            float a = 0.0f;                                    // lane < 7: running sum of term `lane`
+#pragma unroll 1
+            for (int half = 0; half < 256; half += 128) {
+#pragma unroll 1
+                for (int j = lane; j < 128; j += 32) {
+                    const int i = half + j;
+                    const float x = bp[i];
+                    const float xm = cc.n ? __fdiv_rn(x, lv_c[i]) : x;
+                    const float wi = s_win[i], wr = s_win[255 - i];
+                    float prev, y = 0.0f, ym = 0.0f;
+                    if (f == 0) {
+                        prev = b.prevhalf[(sc * 4 + band) * 256 + i];
+                    } else {
+                        y = bp[i - 256];
+                        ym = pc.n ? __fdiv_rn(y, lv_p[i]) : y;
+                        prev = fmul(wi, ym);
+                    }
+                    float v;
+                    tl[0 * 128 + j] = fmul(prev, prev);
+                    v = fmul(x, wr);  tl[1 * 128 + j] = fmul(v, v);
+                    v = fmul(xm, wr); tl[2 * 128 + j] = fmul(v, v);
+                    v = fmul(x, wi);  tl[3 * 128 + j] = fmul(v, v);
+                    v = fmul(xm, wi); tl[4 * 128 + j] = fmul(v, v);
+                    v = fmul(y, wi);  tl[5 * 128 + j] = fmul(v, v);
+                    v = fmul(ym, wi); tl[6 * 128 + j] = fmul(v, v);
                 }
-                s_esum[warp][band][lane] = a;
+                __syncwarp();
+                if (lane < 7) {
+#pragma unroll 4
+                    for (int j = 0; j < 128; j += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(&tl[lane * 128 + j]);
+                        a = fadd(a, q.x); a = fadd(a, q.y); a = fadd(a, q.z); a = fadd(a, q.w);
+                    }
+                }
+                __syncwarp();
             }
+            if (lane < 7) s_esum[warp][band][lane] = a;
             __syncwarp();
         }
         if (lane < 4) {
@@ -1056,6 +1098,14 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g
             const Curve& cc = s_cv[warp][band][1];
             const Curve& pc = s_cv[warp][band][0];
             float* in = tl + bb * kMdctBandStride;
+            float* lv_c = tl + kMdctLevels;
+            float* lv_p = lv_c + 256;
+            if (cc.n | pc.n) {                                        // divisor tables of this band (rare)
+                __syncwarp();
+                if (cc.n) curve_levels_warp(T, cc, lane, lv_c);
+                if (f != 0 && pc.n) curve_levels_warp(T, pc, lane, lv_p);
+                __syncwarp();
+            }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int i0 = 4 * (lane + 32 * h);
@@ -1071,13 +1121,13 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g
                     const float4 q = *reinterpret_cast<const float4*>(bp + i0 - 256);
                     y[0] = q.x; y[1] = q.y; y[2] = q.z; y[3] = q.w;
                 }
-                if (cc.n | pc.n) {                                    // rare: gain modulation (gain_processor.h:87-121)
-#pragma unroll 1
-                    for (int e = 0; e < 4; e++) {
-                        const int i = i0 + e;
-                        if (cc.n) x[e] = __fdiv_rn(x[e], curve_level_call(T, &cc, i));
-                        if (f != 0 && pc.n) y[e] = __fdiv_rn(y[e], curve_level_call(T, &pc, i));
-                    }
+                if (cc.n) {                                           // gain modulation (gain_processor.h:87-121)
+                    const float4 d = *reinterpret_cast<const float4*>(lv_c + i0);
+                    x[0] = __fdiv_rn(x[0], d.x); x[1] = __fdiv_rn(x[1], d.y); x[2] = __fdiv_rn(x[2], d.z); x[3] = __fdiv_rn(x[3], d.w);
+                }
+                if (f != 0 && pc.n) {
+                    const float4 d = *reinterpret_cast<const float4*>(lv_p + i0);
+                    y[0] = __fdiv_rn(y[0], d.x); y[1] = __fdiv_rn(y[1], d.y); y[2] = __fdiv_rn(y[2], d.z); y[3] = __fdiv_rn(y[3], d.w);
                 }
                 const float4 wf = *reinterpret_cast<const float4*>(&s_win[i0]);          // win[i0 .. i0+3]
                 const float4 wb = *reinterpret_cast<const float4*>(&s_win[252 - i0]);    // win[255-i0-3 .. 255-i0]

@@ -959,6 +959,7 @@ constexpr int kMdctWarps = 4;
 constexpr int kMdctBandStride = 520;                 // floats; keeps float4 alignment, shifts banks by 8
 constexpr int kMdctXchStride = 152;                  // cpx per band in the exchange layout (16 blocks x 9, +8)
 constexpr int kMdctOutStride = 264;
+constexpr int kMdctTermStride = 132;                 // floats between the seven energy-term rows: the seven summing lanes hit 28 different banks
 constexpr int kMdctLevels = 2 * kMdctBandStride;     // floats: divisor tables of the band in work (its own curve, the previous frame's)
 constexpr int kMdctTile = kMdctLevels + 512;         // floats per warp: two MDCT inputs (or 7 x 128 energy terms) + the two tables
 
@@ -1037,19 +1038,19 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g
                         prev = fmul(wi, ym);
                     }
                     float v;
-                    tl[0 * 128 + j] = fmul(prev, prev);
-                    v = fmul(x, wr);  tl[1 * 128 + j] = fmul(v, v);
-                    v = fmul(xm, wr); tl[2 * 128 + j] = fmul(v, v);
-                    v = fmul(x, wi);  tl[3 * 128 + j] = fmul(v, v);
-                    v = fmul(xm, wi); tl[4 * 128 + j] = fmul(v, v);
-                    v = fmul(y, wi);  tl[5 * 128 + j] = fmul(v, v);
-                    v = fmul(ym, wi); tl[6 * 128 + j] = fmul(v, v);
+                    tl[0 * kMdctTermStride + j] = fmul(prev, prev);
+                    v = fmul(x, wr);  tl[1 * kMdctTermStride + j] = fmul(v, v);
+                    v = fmul(xm, wr); tl[2 * kMdctTermStride + j] = fmul(v, v);
+                    v = fmul(x, wi);  tl[3 * kMdctTermStride + j] = fmul(v, v);
+                    v = fmul(xm, wi); tl[4 * kMdctTermStride + j] = fmul(v, v);
+                    v = fmul(y, wi);  tl[5 * kMdctTermStride + j] = fmul(v, v);
+                    v = fmul(ym, wi); tl[6 * kMdctTermStride + j] = fmul(v, v);
                 }
                 __syncwarp();
                 if (lane < 7) {
 #pragma unroll 4
                     for (int j = 0; j < 128; j += 4) {
-                        const float4 q = *reinterpret_cast<const float4*>(&tl[lane * 128 + j]);
+                        const float4 q = *reinterpret_cast<const float4*>(&tl[lane * kMdctTermStride + j]);
                         a = fadd(a, q.x); a = fadd(a, q.y); a = fadd(a, q.z); a = fadd(a, q.w);
                     }
                 }

@@ -154,13 +154,18 @@ ATDE_D int scale_analyse(const DevTables* T, const float* v, int len, float& ene
 // =====================================================================================
 constexpr int kScaleWarps = 4;
 
+// Padded index of the per-line log table: lanes 8..28 walk their BFUs (16 / 32 / 64 lines apart) in lock step,
+// which without padding puts up to ten doubles of one access into the same bank (38 % of the kernel's
+// shared-memory wavefronts, ncu v6); one pad per 16 and one per 256 leaves 1.25 wavefronts per access.
+ATDE_D int lgp(int p) { return p + (p >> 4) + (p >> 8); }
+
 __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) float sv_all[kScaleWarps][1024];
     __shared__ float run_val[kScaleWarps][32][5];
     __shared__ short run_start[kScaleWarps][32];
     __shared__ signed char run_len[kScaleWarps][32];
-    __shared__ double lg_all[kScaleWarps][640];
+    __shared__ double lg_all[kScaleWarps][688];         // 640 logs, padded: see lgp()
 
     const DevTables* __restrict__ T = b.tab;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -183,16 +188,23 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
         for (int i = 64 + lane; i < 704; i += 32) {
             const float ef = fmul(sv[i], sv[i]);
             const double e = (double)fmaxf(0.0f, ef);
-            lg[i - 64] = g_log(e > floor_d ? e : floor_d);
+            lg[lgp(i - 64)] = g_log(e > floor_d ? e : floor_d);
         }
         __syncwarp();
         if (lane >= 8 && lane < 29) {
             double arith = 0.0, mean_log = 0.0;
-            for (int i = 0; i < len; i++) {
-                const float ef = fmul(sv[start + i], sv[start + i]);
-                const double e = (double)fmaxf(0.0f, ef);
-                arith = __dadd_rn(arith, e);
-                mean_log = __dadd_rn(mean_log, lg[start - 64 + i]);
+            // (these BFUs are 16, 32 or 64 lines long; one 16-byte load per four lines: the lanes' lines are 16 / 32 /
+            // 64 floats apart, so scalar loads would take nine shared-memory wavefronts each)
+            for (int i = 0; i < len; i += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(sv + start + i);
+                const float x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float ef = fmul(x[k], x[k]);
+                    const double e = (double)fmaxf(0.0f, ef);
+                    arith = __dadd_rn(arith, e);
+                    mean_log = __dadd_rn(mean_log, lg[lgp(start - 64 + i + k)]);
+                }
             }
             arith = __ddiv_rn(arith, (double)len);
             mean_log = __ddiv_rn(mean_log, (double)len);

@@ -1000,17 +1000,18 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g
         __syncwarp();
         // A band whose own curve is empty and whose overlap scale is 1 has every energy scale exactly 1.0
         // (SafeEnergyScale(x, x)); the sequential energy sums only run for bands that touch a curve.
-        bool trivial[4];
+        unsigned trivial = 0;                              // bit per band (a mask, so that the band loop below stays rolled)
 #pragma unroll
         for (int band = 0; band < 4; band++)
-            trivial[band] = s_cv[warp][band][1].n == 0 &&
-                            (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : s_cv[warp][band][0].n == 0);
+            if (s_cv[warp][band][1].n == 0 &&
+                (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : s_cv[warp][band][0].n == 0)) trivial |= 1u << band;
         // ---- CalcGainEnergyScale's sequential sums (atrac3denc.cpp:189-216), bands that touch a curve only:
         // squared terms sample-parallel into the tile, seven lanes then add them up in order.
         //  0 prevStored  1 curOriginal  2 curModulated  3 nextOriginal  4 nextModulated
         //  5/6 nextOriginal/nextModulated of the PREVIOUS frame (-> its NextOverlapScale)
+#pragma unroll 1
         for (int band = 0; band < 4; band++) {
-            if (trivial[band]) continue;
+            if ((trivial >> band) & 1u) continue;
             const Curve& cc = s_cv[warp][band][1];
             const Curve& pc = s_cv[warp][band][0];
             const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
@@ -1064,7 +1065,7 @@ __global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g
             const Curve& cc = s_cv[warp][band][1];
             const bool cur_empty = cc.n == 0, prev_empty = s_cv[warp][band][0].n == 0;
             float sc0 = 1.0f, sc1 = 1.0f, sc2 = 1.0f, sc3 = 1.0f;
-            if (!trivial[band]) {
+            if (!((trivial >> band) & 1u)) {
                 const float* es = s_esum[warp][band];
                 float pos_scale;                                       // PrevOverlapGainScale[channel][band]
                 if (f == 0) pos_scale = b.next_scale[sc * 4 + band];

@@ -1,8 +1,12 @@
 // tests/host_shim_driver.cpp — drives the C++ host shim exactly like src/main.cpp:697-716 drives
 // the reference's processors: TPCMEngine(4096) + memory reader + GetLambda() loop, capturing the
 // WriteFrame payloads to a file.
-// usage: driver <pcm.f32> <channels> <total_samples> <out.bin> <batch_frames> [codec=1|3|4] [bitrate_kbit]
+// usage: driver <pcm.f32> <channels> <total_samples> <out.bin> <batch_frames> [codec=1|3|4] [bitrate_kbit] [container]
+// With a container name (aea, raw, oma, riff, rm) the output goes through this repo's container writers, created
+// with the arguments main.cpp passes (src/main.cpp:312-326, :380-410, :438-462): the result is a whole file.
 #include "../atracdenc_b200/host/atde_encoders.h"
+#include "../atracdenc_b200/host/atde_containers.h"
+#include <string>
 #include <cstdio>
 #include <cstdlib>
 
@@ -48,9 +52,28 @@ int main(int argc, char** argv)
     if (fread(pcm.data(), 4, pcm.size(), f) != pcm.size()) return 4;
     fclose(f);
     try {
-        TCompressedOutputPtr sink(new TFileSink(argv[4], ch));
         const int codec = argc > 6 ? atoi(argv[6]) : 1;
         const uint32_t kbit = argc > 7 ? (uint32_t)atoi(argv[7]) : 0;
+        const std::string cont = argc > 8 ? argv[8] : "";
+        TCompressedOutputPtr sink;
+        if (cont.empty()) {
+            sink.reset(new TFileSink(argv[4], ch));
+        } else if (codec == 1) {
+            const uint64_t numFrames = ch * total / 512;
+            sink = cont == "raw" ? CreateRawOutput(argv[4], ch, 212) : CreateAeaOutput(argv[4], "test", ch, (uint32_t)numFrames);
+        } else if (codec == 3) {
+            const uint64_t numFrames = total / 1024;
+            const NAtrac3::TContainerParams* cp = NAtrac3::GetContainerParamsForBitrate(kbit * 1024);
+            if (cont == "riff") sink = CreateAt3Output(argv[4], 2, (uint32_t)numFrames, cp->FrameSz, cp->Js);
+            else if (cont == "raw") sink = CreateRawOutput(argv[4], ch);
+            else if (cont == "rm") sink = CreateRmOutput(argv[4], "test", ch, (uint32_t)numFrames, cp->FrameSz, cp->Js);
+            else sink.reset(new TOma(argv[4], "test", ch, (int32_t)numFrames, OMAC_ID_ATRAC3, cp->FrameSz, cp->Js));
+        } else {
+            const uint64_t numFrames = total / 2048;
+            if (cont == "riff") sink = CreateAt3POutput(argv[4], ch, (uint32_t)numFrames, 2048);
+            else if (cont == "raw") sink = CreateRawOutput(argv[4], ch);
+            else sink.reset(new TOma(argv[4], "test", ch, (int32_t)numFrames, OMAC_ID_ATRAC3PLUS, 2048, false));
+        }
         std::unique_ptr<TBatchedEncoderBase> proc;
         size_t step = 512;
         if (codec == 1) {

@@ -904,6 +904,7 @@ __global__ void __launch_bounds__(kGhaThreads, ATDE_GHA_MINBLOCKS) at3p_gha_sear
 // and >= 4 tones, so that a warp's lanes run the same code).  No barrier inside a batch: the tail rounds of
 // slow frames overlap with the busy rounds of others.
 // ---------------------------------------------------------------------------------------------
+#ifdef ATDE_GHA_DYNAMIC
 constexpr int kGhaQ = 5;
 struct DynShared {
     unsigned short q[kGhaQ][kGhaItems];   // rings of step ids, 0xffff = empty slot
@@ -1132,6 +1133,7 @@ __global__ void __launch_bounds__(kGhaThreads, ATDE_GHA_MINBLOCKS) at3p_gha_sear
         __syncthreads();
     }
 }
+#endif // ATDE_GHA_DYNAMIC
 
 // ---------------------------------------------------------------------------------------------
 // FillResultBuf / FillFolowerRes / AdjustEnvelope (at3p_gha.cpp:1499-1664) + the ResultBufHistory carry:

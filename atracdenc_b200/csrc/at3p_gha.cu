@@ -436,6 +436,11 @@ ATDE_D int adjust_newton(const float* pcm, GhaInfo* info, int dim, int sz, TaskS
     return 0;
 }
 
+#ifndef ATDE_GHA_SMALL_MAX
+#define ATDE_GHA_SMALL_MAX 3              // fits of up to this many tones keep every accumulator in registers
+                                          // (measured per 250,880 frames: 3 -> 253 ms; 2 -> 279 ms; 3 blocks per SM at
+                                          //  80 registers -> 287 ms with 3, 300 ms with 2)
+#endif
 #ifndef ATDE_GHA_NEWTON_UNROLL
 #define ATDE_GHA_NEWTON_UNROLL 2
 #endif
@@ -561,7 +566,9 @@ ATDE_D bool task_fit(const GhaTables* G, const SbState& sbs, int sb, const float
             int ar;
             if (dim == 1) ar = adjust_newton_small<1>(src, tmp_info, sz, ws);
             else if (dim == 2) ar = adjust_newton_small<2>(src, tmp_info, sz, ws);
+#if ATDE_GHA_SMALL_MAX >= 3
             else if (dim == 3) ar = adjust_newton_small<3>(src, tmp_info, sz, ws);
+#endif
             else ar = adjust_newton(src, tmp_info, dim, sz, ws);
             if (ar < 0) { status = 0; break; }
             // the callback reads 128 samples: beyond sz they are what the previous (full-size) call left in

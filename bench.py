@@ -273,6 +273,7 @@ def run_ours(args):
     same = bool(torch.equal(h_out.view(-1)[: S * fo * units * ub], dev_bytes))
 
     # ---- the same through the int16 ingest entry point: half the H2D bytes ----
+    del h_pcm                                                           # its pinned block is reused for the int16 copy
     h_pcm16 = torch.empty((S, F * step, C), dtype=torch.int16, pin_memory=True)
     h_pcm16.copy_(torch.round(d_pcm * 32768.0).to(torch.int16))        # the synthetic PCM is int16-quantised: exact
     enc.reset()

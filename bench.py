@@ -43,12 +43,11 @@ WORKLOADS = {
                                      settings="LP4 66150 bit/s joint stereo, gain control + tonal components on",
                                      desc="ATRAC3 LP4 (66 kbps, joint-stereo) encode, 1.25*10^6 frames per GPU "
                                           "(BASELINE.json configs[3] is this shard on each of 8 GPUs)"),
-    # BASELINE.json configs[4] asks for 10^6 frames; the default shard is 1024 streams x 245 frames (250,880
-    # frames, ~20 GB of HBM with the per-batch workspaces); --streams / --frames scale it.
-    "atrac3plus_stereo": dict(codec=4, step=2048, S=1024, F=245, alg_bytes=32768, kbit=0,
+    # BASELINE.json configs[4]: 10^6 frames (1024 streams x 977 frames; ~75 GB of HBM with the per-batch workspaces)
+    "atrac3plus_stereo": dict(codec=4, step=2048, S=1024, F=977, alg_bytes=32768, kbit=0,
                               kernel="at3p_pqf_kernel + at3p_mdct_kernel (16-band PQF, MDCT-256 x16)",
                               settings="reference defaults: GHA_ENABLED (pass input, write tonal, write residual)",
-                              desc="ATRAC3PLUS encode, synthetic stereo batch (BASELINE.json configs[4], reduced shard)"),
+                              desc="ATRAC3PLUS encode, 10^6-frame synthetic stereo batch (BASELINE.json configs[4])"),
 }
 DEFAULT_WORKLOAD = "atrac3_lp2_stereo_1e6"
 KIND_NAMES = ["qmf_mdct", "loudness_scan", "alloc_quant_pack", "gain_envelope", "gain_curve", "tonal_scale"]

@@ -728,6 +728,12 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     // 191 + 191 + ... + 69 streams measured 350 ms per 250,880 frames against 373 ms with the short first chunk
     // and 494 ms with seven equal ones.)
     size_t target_floats = (size_t)(at3 ? 192 : 48) << 20;                      // ~768 / ~192 MiB of PCM per chunk
+    if (at3p) {
+        // every tone-search launch ends in a ~14 ms tail: aim at about five chunks per batch, 768 MiB .. 3 GiB each
+        // (10^6-frame batch: 21 chunks of 768 MiB 1479 ms per step against 1188 ms device-resident)
+        const size_t fifth = (size_t)S * pcm_per_stream / 5;
+        target_floats = fifth < ((size_t)192 << 20) ? ((size_t)192 << 20) : fifth > ((size_t)768 << 20) ? ((size_t)768 << 20) : fifth;
+    }
     if (const char* env = getenv("ATDE_CHUNK_MIB")) {                           // tuning knob (MiB of PCM per chunk)
         const long v = atol(env);
         if (v > 0) target_floats = (size_t)v << 18;

@@ -749,7 +749,8 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         for (int band = 0; band < 4; band++) hb += 3 + 9 * cv[band].n;
         sh.hdr_bits = hb;
     }
-    __syncthreads();
+    if (g.js) __syncthreads();                  // the byte shift below reads both channels' header sizes
+    else __syncwarp();                          // otherwise the two channel warps never meet
     // ---- byte budget of this channel ----
     int shift_bytes = 0;
     if (g.js) {
@@ -1053,21 +1054,25 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- frame assembly (:826-843): channel 0 bytes, then channel 1 (byte-reversed when joint stereo);
-    //      mono without JS duplicates the half frame ----
+    //      mono without JS duplicates the half frame.  Every warp places its own channel's bytes (the split
+    //      point is known since the byte-shift barrier), so a fast channel does not wait for the other one ----
     unsigned char* dst = b.out + (size_t)frame * g.frame_sz;
     const int n0 = half + shift_bytes;
-    for (int i = threadIdx.x; i < g.frame_sz; i += blockDim.x) {
-        int chn, q;
-        if (i < n0) { chn = 0; q = i; }
-        else if (g.C == 2) {
-            chn = 1;
-            q = i - n0;
-            if (g.js) q = (g.frame_sz - n0 - 1) - q;
-        } else { chn = 0; q = i - n0; }
-        const unsigned w = shm[chn].words[q >> 2];
-        dst[i] = (unsigned char)(w >> (24 - 8 * (q & 3)));
+    if (g.C == 2) {
+        const int lo = ch == 0 ? 0 : n0, hi = ch == 0 ? n0 : g.frame_sz;
+        for (int i = lo + lane; i < hi; i += 32) {
+            const int q = ch == 0 ? i : (g.js ? (g.frame_sz - n0 - 1) - (i - n0) : i - n0);
+            const unsigned w = sh.words[q >> 2];
+            dst[i] = (unsigned char)(w >> (24 - 8 * (q & 3)));
+        }
+    } else {
+        for (int i = lane; i < g.frame_sz; i += 32) {
+            const int q = i < n0 ? i : i - n0;
+            const unsigned w = sh.words[q >> 2];
+            dst[i] = (unsigned char)(w >> (24 - 8 * (q & 3)));
+        }
     }
 }
 

@@ -79,6 +79,7 @@ struct Geometry {
     int n_out;                        // = L - 1 output frames
     int BL;                           // band buffer length per (s,c,band) = 128 + 256*L
     int js;                           // joint stereo (container Js flag and C == 2)
+    int js_mono;                      // container Js flag with ONE input channel: an empty second element is written
     int frame_sz;                     // container frame size in bytes
     int no_gain, no_tonal;
     int bfu_idx_const;

@@ -769,6 +769,14 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         __syncthreads();
         shift_bytes = s_shift;
     }
+    if (g.js_mono) {
+        // Mono input in a joint-stereo container (atrac3denc.cpp:843-849): the second element is EMPTY — one QMF
+        // band, no gain points, no blocks: WriteJsParams + 3 (14 bits), numQmfBand - 1 (2), gain count (3) = 19
+        // header bits, then an empty tonal section (5), numBfu - 1 = 0 (5), coding mode 1 (1), precision 0 (3) —
+        // and CalcMSBytesShift hands the first element everything the second cannot use (:750-752).
+        const int used = (6 + sh.hdr_bits) + (6 + 19);
+        shift_bytes = half - (int)(1u + ((unsigned)used - 1u) / 8u);
+    }
     const int my_bytes = (ch == 0) ? half + shift_bytes : half - shift_bytes;
     int to_alloc = -6 - sh.hdr_bits + 8 * my_bytes;
     const unsigned target = (unsigned)(unsigned short)max(1, to_alloc);
@@ -1066,6 +1074,19 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
             const int q = ch == 0 ? i : (g.js ? (g.frame_sz - n0 - 1) - (i - n0) : i - n0);
             const unsigned w = sh.words[q >> 2];
             dst[i] = (unsigned char)(w >> (24 - 8 * (q & 3)));
+        }
+    } else if (g.js_mono) {
+        // the empty element's 33 bits 0 111 11111111 11 00 000 00000 00000 1 000, zero-padded, byte-reversed at the frame end
+        for (int i = lane; i < g.frame_sz; i += 32) {
+            unsigned char v;
+            if (i < n0) {
+                const unsigned w = sh.words[i >> 2];
+                v = (unsigned char)(w >> (24 - 8 * (i & 3)));
+            } else {
+                const int q = (g.frame_sz - 1) - i;
+                v = q == 0 ? 0x7F : q == 1 ? 0xFC : q == 3 ? 0x04 : 0x00;
+            }
+            dst[i] = v;
         }
     } else {
         for (int i = lane; i < g.frame_sz; i += 32) {

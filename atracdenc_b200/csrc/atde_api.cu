@@ -388,6 +388,7 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
     g.n_out = g.L - 1;
     g.BL = 128 + 256 * g.L;
     g.js = e->at3_js && C == 2;
+    g.js_mono = e->at3_js && C == 1;
     g.frame_sz = e->unit_bytes;
     g.no_gain = e->cfg.no_gain_control != 0;
     g.no_tonal = e->cfg.no_tonal != 0;
@@ -560,8 +561,6 @@ int atde_create(const atde_settings* s, atde_encoder** out)
         if (s->bfu_idx_const > 32) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..32");
         cont = at3_container_for(s->bitrate);
         if (!cont) return fail(ATDE_ERR_INVALID, "bitrate %u is above the largest ATRAC3 container (352800)", s->bitrate);
-        if (cont->js && s->channels == 1)
-            return fail(ATDE_ERR_UNSUPPORTED, "joint-stereo containers with mono input are not built yet");
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)

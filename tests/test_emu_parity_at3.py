@@ -24,6 +24,13 @@ def test_vs_oracle_mono_lp2(emu_lib):
     pc.check_at3_vs_oracle(emu_lib, S=2, F=7, C=1, kbit=0, seed=300)
 
 
+def test_vs_oracle_mono_in_joint_stereo_container(emu_lib):
+    """Mono input at LP4 / 94 kbit: the reference writes an empty second element and gives the first one all the
+    bytes the second cannot use (atrac3denc.cpp:843-849, atrac3_bitstream.cpp:750-752)."""
+    pc.check_at3_vs_oracle(emu_lib, S=3, F=8, C=1, kbit=64, seed=320)
+    pc.check_at3_vs_oracle(emu_lib, S=1, F=6, C=1, kbit=90, seed=330, kinds=("steps",))
+
+
 def test_vs_oracle_flags(emu_lib):
     pc.check_at3_vs_oracle(emu_lib, S=1, F=7, C=2, kbit=0, seed=400, kinds=("mix",), no_gain=1)
     pc.check_at3_vs_oracle(emu_lib, S=1, F=7, C=2, kbit=0, seed=401, kinds=("tones",), no_tonal=1)

@@ -18,7 +18,7 @@ def test_golden_lp4(gpu_lib):
     pc.check_at3_golden(gpu_lib, "at3_lp4_js_stereo.npz")
 
 
-@pytest.mark.parametrize("kbit,C", [(0, 2), (64, 2), (0, 1), (128, 2), (94, 2)])
+@pytest.mark.parametrize("kbit,C", [(0, 2), (64, 2), (0, 1), (128, 2), (94, 2), (64, 1), (90, 1)])
 def test_vs_oracle(gpu_lib, kbit, C):
     """LP2, LP4 (joint stereo), mono LP2, and two more containers (132300 via 128 kbit request;
     104738 non-JS via 94*1024=96256)."""

@@ -37,7 +37,7 @@ class Settings(ctypes.Structure):
         ("bfu_idx_const", ctypes.c_uint32), ("window_mode", ctypes.c_int32),
         ("window_mask", ctypes.c_uint32), ("bitrate", ctypes.c_uint32),
         ("no_gain_control", ctypes.c_int32), ("no_tonal", ctypes.c_int32),
-        ("device", ctypes.c_int32), ("reserved", ctypes.c_int32 * 7),
+        ("device", ctypes.c_int32), ("gha_flags", ctypes.c_uint32), ("reserved", ctypes.c_int32 * 6),
     ]
 
 
@@ -86,12 +86,14 @@ class Encoder:
 
     def __init__(self, codec: int, channels: int, *, bfu_idx_const: int = 0, window_mode: int = 1,
                  window_mask: int = 0, bitrate: int = 0, no_gain_control: bool = False,
-                 no_tonal: bool = False, device: int = 0, lib: ctypes.CDLL | None = None):
+                 no_tonal: bool = False, device: int = 0, lib: ctypes.CDLL | None = None, gha_flags: int | None = None):
         self.lib = lib or load_library()
         s = Settings()
         self.lib.atde_default_settings(ctypes.byref(s), codec, channels)
         s.bfu_idx_const, s.window_mode, s.window_mask = bfu_idx_const, window_mode, window_mask
         s.bitrate, s.no_gain_control, s.no_tonal, s.device = bitrate, int(no_gain_control), int(no_tonal), device
+        if gha_flags is not None:
+            s.gha_flags = gha_flags
         h = ctypes.c_void_p()
         self._check(self.lib.atde_create(ctypes.byref(s), ctypes.byref(h)))
         self.h = h

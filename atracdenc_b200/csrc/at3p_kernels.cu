@@ -277,11 +277,12 @@ __global__ void __launch_bounds__(128) at3p_tone_filter_kernel(const DevTables* 
     const ToneBlock* old = tb_old + ti;
     const ToneBlock* now = tb_now + ti;
     const ToneBlock* next = tb_next + ti;
-    const float* in = bands + (((size_t)s * C + ch) * lay.in_frames + lay.in_off + q) * kFrame;
+    // bands == nullptr: GHA_PASS_INPUT is off — the work buffer starts from zeros (at3p.cpp:165-169)
+    const float* in = bands ? bands + (((size_t)s * C + ch) * lay.in_frames + lay.in_off + q) * kFrame : nullptr;
     float* out = resid + (((size_t)s * C + ch) * lay.out_frames + lay.out_off + q) * kFrame;
     const bool any = now->present || next->present;                    // tones_present || prev tones_present
     for (int sb = 0; sb < kSubbands; sb++) {
-        float x = in[sb * kSbSamples + i];
+        float x = in ? in[sb * kSbSamples + i] : 0.0f;
         if (sb < 8 && any) {
             const WaveGroup gn = resolve_group(now, C, ch, sb), gx = resolve_group(next, C, ch, sb);
             if (gn.num_wavs || gx.num_wavs) {
@@ -695,7 +696,8 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
     }
     __syncwarp();
     // ---- TTonalComponentEncoder::Encode (:611-669), once: its buffer survives the Repeat rounds
-    const ToneBlock* tb = tones + (size_t)(unit / fo) * tone_stride + unit % fo;   // unit = (stream, output)
+    // tones == nullptr: GHA_WRITE_TONAL is off — `delay` never holds a tone block (at3p.cpp:173-177)
+    const ToneBlock* tb = tones ? tones + (size_t)(unit / fo) * tone_stride + unit % fo : nullptr;   // unit = (stream, output)
     int tonal_bits = 0;
     if (lane == 0) {
         unsigned* w = sh.twords;
@@ -704,7 +706,7 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
         if (C == 2) p = put_field(w, cap, p, 0, 2);                      // swap_channels, negate_coeffs
         for (int ch = 0; ch < C; ch++) p = put_field(w, cap, p, 0, 1);   // every window is a sine window (at3p.cpp:161)
         for (int ch = 0; ch < C; ch++) p = put_field(w, cap, p, 0, 1);   // no gain compensation
-        if (tb->present && tb->num_tone_bands) {
+        if (tb && tb->present && tb->num_tone_bands) {
             p = put_field(w, cap, p, 1, 1);
             p = write_tonal_block(T, w, cap, p, C, tb);
         } else {

@@ -96,7 +96,7 @@ void launch_gha_result(const void* frame_out, int S, int C, int nA, void* hist_s
 
 // streaming pipeline (at3p_pipeline.cu): the body of TAt3PEnc::TImpl::EncodeFrame for S streams x N calls
 struct StreamState;                   // per-handle carried state
-StreamState* pipeline_create(int C);
+StreamState* pipeline_create(int C, int gha_flags = 7);   // gha_flags: TAt3PEnc::TSettings::UseGha (bits 0..2)
 void pipeline_destroy(StreamState*);
 void pipeline_reset(StreamState*);
 // Encodes N new frames per stream (d_pcm [S][N*2048][C]) continuing streams s0 .. s0+S-1 of `total_streams`;

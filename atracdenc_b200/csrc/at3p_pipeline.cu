@@ -36,6 +36,7 @@ template <class T> struct Buf {
 
 struct StreamState {
     int C = 0;
+    int gha_flags = 7;                   // TAt3PEnc::TSettings::UseGha: 1 pass input, 2 write tonal, 4 write residual
     int n_streams = 0;                   // the carried arrays are sized (and zeroed) for this many streams
     long long calls = 0;                 // lambda calls every stream has seen
     long long pending = 0;               // calls of the batch being enqueued
@@ -51,10 +52,10 @@ struct StreamState {
     } w[2];
 };
 
-StreamState* pipeline_create(int C)
+StreamState* pipeline_create(int C, int gha_flags)
 {
     StreamState* st = new (std::nothrow) StreamState();
-    if (st) st->C = C;
+    if (st) { st->C = C; st->gha_flags = gha_flags; }
     return st;
 }
 
@@ -147,9 +148,13 @@ int pipeline_run(StreamState* st, const float* d_pcm, int s0, int S, int total, 
         }
         FilterLayout lay;
         lay.fo = nA; lay.tone_stride = TS; lay.in_frames = L; lay.in_off = jW0; lay.out_frames = nA + 1; lay.out_off = 1;
-        { Scope sc(prof, cs, 4); launch_tone_filter(T, w.bands.p, w.tones.p, w.tones.p + 1, w.tones.p + 2, w.resid.p, S * nA, C, lay, cs); }
+        // the debug masks of `--advanced ghadbg=` (at3p.cpp:143-177): without PASS_INPUT the tones are subtracted from
+        // zeros, without WRITE_RESIUDAL the MDCT sees zeros, without WRITE_TONAL no tone block is written
+        const bool pass_input = st->gha_flags & 1, write_tonal = st->gha_flags & 2, write_resid = st->gha_flags & 4;
+        { Scope sc(prof, cs, 4); launch_tone_filter(T, pass_input ? w.bands.p : nullptr, w.tones.p, w.tones.p + 1, w.tones.p + 2, w.resid.p, S * nA, C, lay, cs); }
+        if (!write_resid) PCK(cudaMemsetAsync(w.resid.p, 0, (size_t)S * C * (nA + 1) * kFrame * sizeof(float), cs));
         { Scope sc(prof, cs, 0); launch_mdct(T, w.resid.p, w.specs.p, S, C, nA, 1, cs); }
-        { Scope sc(prof, cs, 2); launch_pack(T, w.specs.p, w.tones.p + 1, d_out, S * nA, C, nA, TS, cs); }
+        { Scope sc(prof, cs, 2); launch_pack(T, w.specs.p, write_tonal ? w.tones.p + 1 : nullptr, d_out, S * nA, C, nA, TS, cs); }
         *launches += 5;
     }
     // carry out

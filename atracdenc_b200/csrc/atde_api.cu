@@ -543,6 +543,7 @@ void atde_default_settings(atde_settings* s, int32_t codec, int32_t channels)
     s->codec = codec;
     s->channels = channels;
     s->window_mode = 1;
+    s->gha_flags = 7;                       // TAt3PEnc::TSettings(): UseGha = GHA_ENABLED
 }
 
 int atde_create(const atde_settings* s, atde_encoder** out)
@@ -556,7 +557,9 @@ int atde_create(const atde_settings* s, atde_encoder** out)
     if (s->codec == ATDE_CODEC_ATRAC1) {
         if (s->bfu_idx_const > 8) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..8");
     } else if (s->codec == ATDE_CODEC_ATRAC3PLUS) {
-        // TAt3PEnc::TSettings defaults only (UseGha = GHA_ENABLED, src/atrac3p.h:34-57); no tunables in the ABI yet
+        // TAt3PEnc::TSettings (src/atrac3p.h:29-57): the three processing flags; the wideband experiment is not built
+        if (s->gha_flags & ~7u)
+            return fail(ATDE_ERR_UNSUPPORTED, "ATRAC3plus GHA_WIDEBAND (gha_flags bit 3) is not built");
     } else {
         if (s->bfu_idx_const > 32) return fail(ATDE_ERR_INVALID, "bfu_idx_const must be 0..32");
         cont = at3_container_for(s->bitrate);
@@ -579,7 +582,7 @@ int atde_create(const atde_settings* s, atde_encoder** out)
         e->units_per_frame = 1;
         e->unit_bytes = atde::at3p::kFrameBytes;
         e->lookahead = 1;
-        e->at3p = atde::at3p::pipeline_create(s->channels);
+        e->at3p = atde::at3p::pipeline_create(s->channels, (int)s->gha_flags);
         if (!e->at3p) { delete e; return fail(ATDE_ERR_NOMEM, "host alloc"); }
     } else {
         e->frame_samples = 1024;

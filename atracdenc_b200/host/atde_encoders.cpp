@@ -128,10 +128,11 @@ TPCMEngine::TProcessLambda TAtrac3Encoder::GetLambda()
 
 static atde_settings MakeAt3pSettings(int channels, const TAt3PEnc::TSettings& s)
 {
-    if (s.UseGha != TAt3PEnc::TSettings::GHA_ENABLED)
-        throw std::runtime_error("atde_b200: only the default ATRAC3plus GHA settings are built (ghadbg=7)");
+    if (s.UseGha & ~(unsigned)TAt3PEnc::TSettings::GHA_ENABLED)
+        throw std::runtime_error("atde_b200: the ATRAC3plus GHA_WIDEBAND experiment is not built");
     atde_settings c;
     atde_default_settings(&c, ATDE_CODEC_ATRAC3PLUS, (int32_t)channels);
+    c.gha_flags = s.UseGha;
     return c;
 }
 

@@ -102,8 +102,8 @@ public:
 };
 
 // ATRAC3plus (src/atrac3p.h:28-71).  The first lambda call returns LOOK_AHEAD (at3p.cpp:109-111), every
-// later one PROCESSED with one WriteFrame of 2048 bytes (at3p_bitstream.cpp:724-725).  Only the default
-// GHA settings (UseGha = GHA_ENABLED, subband refinement) are built; any other mask throws.
+// later one PROCESSED with one WriteFrame of 2048 bytes (at3p_bitstream.cpp:724-725).  The three
+// processing flags of UseGha (`ghadbg`) are honoured; GHA_WIDEBAND (an opt-in experiment) throws.
 class TAt3PEnc : public TBatchedEncoderBase {
 public:
     struct TSettings {

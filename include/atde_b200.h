@@ -44,7 +44,7 @@ typedef enum {
 typedef enum {
     ATDE_CODEC_ATRAC1 = 1,      /* -e atrac1        src/main.cpp:635-655 */
     ATDE_CODEC_ATRAC3 = 3,      /* -e atrac3 / atrac3_lp4  src/main.cpp:657-678 */
-    ATDE_CODEC_ATRAC3PLUS = 4   /* -e atrac3plus    src/main.cpp:679-686; TAt3PEnc::TSettings defaults (GHA_ENABLED) only */
+    ATDE_CODEC_ATRAC3PLUS = 4   /* -e atrac3plus    src/main.cpp:679-686; TAt3PEnc::TSettings incl. the ghadbg masks, no GHA_WIDEBAND */
 } atde_codec;
 
 /* Mirrors the reference's settings objects field by field. */
@@ -60,7 +60,11 @@ typedef struct {
     int32_t no_gain_control;    /* --nogaincontrol */
     int32_t no_tonal;           /* --notonal */
     int32_t device;             /* CUDA device ordinal */
-    int32_t reserved[7];
+    /* NAtracDEnc::TAt3PEnc::TSettings::UseGha (src/atrac3p.h:29-47; `--advanced ghadbg=N`): bit 0 GHA_PASS_INPUT,
+     * bit 1 GHA_WRITE_TONAL, bit 2 GHA_WRITE_RESIUDAL; atde_default_settings sets GHA_ENABLED (7).  Bit 3
+     * (GHA_WIDEBAND, an opt-in experiment of the reference) is refused. */
+    uint32_t gha_flags;
+    int32_t reserved[6];
 } atde_settings;
 
 typedef struct atde_encoder atde_encoder;

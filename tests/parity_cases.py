@@ -727,3 +727,27 @@ def check_i16_ingest(lib, codec, C=2, S=3, F=5, seed=1800):
     enc.close()
     assert np.array_equal(s1, t1) and np.array_equal(s2, t2)
     assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+
+
+def check_at3p_gha_masks(lib, masks=(0, 1, 2, 3, 4, 5, 6), S=2, F=6, C=2, seed=1900):
+    """TAt3PEnc::TSettings::UseGha other than GHA_ENABLED (`--advanced ghadbg=N`, at3p.cpp:143-177): without
+    PASS_INPUT the tones are subtracted from zeros, without WRITE_RESIUDAL the MDCT sees zeros, without WRITE_TONAL
+    no tone block is written.  Frames against the reference run with the same mask, across two batches."""
+    import pytest
+    pcm = _at3p_signal(S, F, C, seed)
+    with pytest.raises(ab.AtdeError):
+        ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib, gha_flags=8 | 7)          # GHA_WIDEBAND: not built
+    if tl.ref_lib() is None:
+        return 0
+    for mask in masks:
+        enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib, gha_flags=mask)
+        a = enc.encode(pcm[:, :3 * 2048], S)
+        b = enc.encode(pcm[:, 3 * 2048:], S)
+        enc.close()
+        out = np.concatenate([a, b], axis=1)
+        for s in range(S):
+            st = tl.ref_at3p_stages(C, pcm[s].reshape(-1), gha_flags=mask)
+            assert st["n"] == F - 1
+            bad = np.argwhere((out[s, :, 0] != st["frames"]).any(-1))
+            assert bad.size == 0, f"mask {mask} stream {s}: differing frames {bad[:4].ravel().tolist()}"
+    return len(masks)

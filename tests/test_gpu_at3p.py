@@ -72,3 +72,7 @@ def test_i16_ingest(gpu_lib):
     pc.check_i16_ingest(gpu_lib, ab.CODEC_ATRAC1, C=1, S=2, F=3, seed=1810)
     pc.check_i16_ingest(gpu_lib, ab.CODEC_ATRAC3, S=3, F=4)
     pc.check_i16_ingest(gpu_lib, ab.CODEC_ATRAC3PLUS, S=2, F=3)
+
+
+def test_gha_debug_masks(gpu_lib):
+    pc.check_at3p_gha_masks(gpu_lib, S=3, F=9)

@@ -751,3 +751,59 @@ def check_at3p_gha_masks(lib, masks=(0, 1, 2, 3, 4, 5, 6), S=2, F=6, C=2, seed=1
             bad = np.argwhere((out[s, :, 0] != st["frames"]).any(-1))
             assert bad.size == 0, f"mask {mask} stream {s}: differing frames {bad[:4].ravel().tolist()}"
     return len(masks)
+
+
+def check_at3p_edge_inputs(lib, C=2, F=5):
+    """Silence, full-scale DC, Nyquist, one impulse, a loud pure sine, two sines either side of a PQF subband
+    edge, a sine that stops mid-frame; and a one-frame first batch (no output) followed by the rest."""
+    n = F * 2048
+    t = np.arange(n, dtype=np.float64)
+    def chans(x):
+        x = np.asarray(x, np.float32)
+        return np.stack([x, (x * np.float32(0.5) if C == 2 else x)][:C], axis=1) if x.ndim == 1 else x
+    sine = lambda f, a=0.5: (a * np.sin(2 * np.pi * f / 44100.0 * t))
+    stop = sine(1000.0, 0.7); stop[2 * 2048 + 700:] = 0.0
+    cases = {
+        "silence": np.zeros((n, C), np.float32),
+        "full_scale_dc": np.full((n, C), 32767 / 32768, np.float32),
+        "nyquist": chans(np.tile(np.array([1.0, -1.0]), n // 2) * (32767 / 32768)),
+        "impulse": np.zeros((n, C), np.float32),
+        "sine_1k": chans(sine(1000.0, 0.9)),
+        "sines_at_subband_edge": chans(sine(1378.125 - 20.0, 0.4) + sine(1378.125 + 20.0, 0.4)),
+        "sine_stops": chans(stop),
+    }
+    cases["impulse"][3000, 0] = -1.0
+    checked = 0
+    for name, x in cases.items():
+        x = tl.quantise(np.ascontiguousarray(x, np.float32))
+        enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
+        out = enc.encode(x, 1)
+        enc.close()
+        assert out.shape == (1, F - 1, 1, 2048), name
+        if tl.ref_lib() is not None:
+            st = tl.ref_at3p_stages(C, x.reshape(-1))
+            bad = np.argwhere((out[0, :, 0] != st["frames"]).any(-1))
+            assert bad.size == 0, f"{name}: differing frames {bad[:4].ravel().tolist()}"
+            checked += 1
+    x = tl.quantise(np.ascontiguousarray(cases["sine_stops"], np.float32))
+    enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
+    first = enc.encode(x[:2048], 1)
+    assert first.shape[1] == 0
+    rest = enc.encode(x[2048:], 1)
+    enc.close()
+    if tl.ref_lib() is not None:
+        assert np.array_equal(rest[0, :, 0], tl.ref_at3p_stages(C, x.reshape(-1))["frames"])
+    return checked
+
+
+def check_at3p_stream_independence(lib, C=2, F=5):
+    pcm = _at3p_signal(4, F, C, 2100)
+    enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
+    batch = enc.encode(pcm, 4)
+    enc.reset()
+    rev = enc.encode(pcm[::-1].copy(), 4)
+    enc.reset()
+    one = enc.encode(pcm[2:3].copy(), 1)
+    enc.close()
+    assert np.array_equal(batch, rev[::-1])
+    assert np.array_equal(batch[2:3], one)

@@ -75,3 +75,13 @@ def test_i16_ingest(emu_lib):
 
 def test_gha_debug_masks(emu_lib):
     pc.check_at3p_gha_masks(emu_lib, masks=(0, 3, 5, 6), S=2, F=5)
+
+
+def test_edge_inputs(emu_lib):
+    pc.check_at3p_edge_inputs(emu_lib, C=2, F=4)
+    pc.check_at3p_edge_inputs(emu_lib, C=1, F=4)
+
+
+def test_mono_and_stream_independence(emu_lib):
+    pc.check_at3p_vs_oracle(emu_lib, S=2, F=4, C=1, seed=2200)
+    pc.check_at3p_stream_independence(emu_lib, F=4)

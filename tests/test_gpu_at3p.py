@@ -76,3 +76,50 @@ def test_i16_ingest(gpu_lib):
 
 def test_gha_debug_masks(gpu_lib):
     pc.check_at3p_gha_masks(gpu_lib, S=3, F=9)
+
+
+def test_edge_inputs(gpu_lib):
+    pc.check_at3p_edge_inputs(gpu_lib, C=2, F=9)
+    pc.check_at3p_edge_inputs(gpu_lib, C=1, F=9)
+
+
+def test_mono_and_stream_independence(gpu_lib):
+    pc.check_at3p_vs_oracle(gpu_lib, S=2, F=9, C=1, seed=2200)
+    pc.check_at3p_stream_independence(gpu_lib, F=9)
+
+
+def test_full_size_properties(gpu_lib):
+    """A quarter of BASELINE.json configs[4] on one GPU (1024 streams x 245 frames), device-resident:
+    (a) replicated streams give replicated bitstreams, (b) the 16 distinct streams match the reference,
+    (c) the batch is reproducible after atde_reset(), (d) the host entry point gives the same bytes."""
+    import numpy as np
+    import torch
+    import atde_testlib as tl
+    import atracdenc_b200 as ab
+    S, F, C = 1024, 245, 2
+    base = np.stack([tl.synth_rich(F, 2048, C, seed=9500 + s, kind=("mix", "tones", "steps")[s % 3]) if s % 4
+                     else tl.synth_streams(1, F, 2048, C, seed=9500 + s)[0] for s in range(16)])
+    d_base = torch.from_numpy(base).cuda()
+    d_pcm = d_base.repeat(S // 16, 1, 1).contiguous()          # stream s == stream s % 16
+    enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=gpu_lib)
+    fo, ub = enc.output_frames(F), enc.unit_bytes
+    d_out = torch.empty((S, fo, ub), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
+    enc.sync()
+    out = d_out.cpu().numpy()
+    assert (out.reshape(S // 16, 16, fo, ub) == out[:16]).all()
+    if tl.ref_lib() is not None:
+        for s in range(0, 16, 3):
+            want = tl.ref_at3p_stages(C, base[s].reshape(-1))["frames"]
+            bad = np.argwhere((out[s] != want).any(-1))
+            assert bad.size == 0, (s, bad[:4, 0].tolist())
+    enc.reset()
+    d_out2 = torch.empty_like(d_out)
+    enc.encode_device(d_pcm.data_ptr(), S, F, d_out2.data_ptr())
+    enc.sync()
+    assert torch.equal(d_out, d_out2)
+    enc.reset()
+    host = enc.encode(np.ascontiguousarray(d_pcm[:64].cpu().numpy()), 64)
+    enc.close()
+    assert np.array_equal(host[:, :, 0], out[:64])

@@ -46,6 +46,16 @@ def main():
         assert np.array_equal(pcm16.astype(np.float32) / np.float32(32768), xs)
         np.savez_compressed(HERE / name, pcm=pcm16, frames=frames, kbit=kbit)
         print(name, frames.shape)
+    # ATRAC3plus (default GHA settings), stereo and mono: tones (tone blocks, envelopes), level steps, noise;
+    # frames straight from TAt3PEnc's lambda.  PCM stored as the int16 it was quantised from.
+    for name, C in (("at3p_stereo.npz", 2), ("at3p_mono.npz", 1)):
+        F = 10
+        xs = np.stack([tl.synth_rich(F, 2048, C, seed=0xA7AC + 16 + i, kind=k) for i, k in enumerate(("mix", "tones", "steps"))])
+        frames = np.stack([tl.ref_at3p_stages(C, x.reshape(-1))["frames"] for x in xs])
+        pcm16 = np.rint(xs * 32768).astype(np.int16)
+        assert np.array_equal(pcm16.astype(np.float32) / np.float32(32768), xs)
+        np.savez_compressed(HERE / name, pcm=pcm16, frames=frames)
+        print(name, frames.shape)
 
 
 if __name__ == "__main__":

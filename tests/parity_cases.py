@@ -807,3 +807,20 @@ def check_at3p_stream_independence(lib, C=2, F=5):
     enc.close()
     assert np.array_equal(batch, rev[::-1])
     assert np.array_equal(batch[2:3], one)
+
+
+def check_at3p_golden(lib, name, max_frames=None):
+    """Committed reference output (tests/golden/make_golden.py): works on a box without oracle/_ref."""
+    g = np.load(GOLDEN / name)
+    pcm = g["pcm"].astype(np.float32) / np.float32(32768)            # stored as int16
+    frames = g["frames"]
+    S, F, C = pcm.shape[0], pcm.shape[1] // 2048, pcm.shape[2]
+    if max_frames:
+        F = min(F, max_frames)
+        pcm = pcm[:, :F * 2048]
+    enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
+    out = enc.encode(pcm, S)
+    enc.close()
+    assert out.shape == (S, F - 1, 1, 2048)
+    bad = np.argwhere((out[:, :, 0] != frames[:, :F - 1]).any(-1))
+    assert bad.size == 0, f"first differing (stream, frame) = {bad[:4].tolist()}"

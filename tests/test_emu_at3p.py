@@ -85,3 +85,8 @@ def test_edge_inputs(emu_lib):
 def test_mono_and_stream_independence(emu_lib):
     pc.check_at3p_vs_oracle(emu_lib, S=2, F=4, C=1, seed=2200)
     pc.check_at3p_stream_independence(emu_lib, F=4)
+
+
+def test_golden(emu_lib):
+    pc.check_at3p_golden(emu_lib, "at3p_stereo.npz", max_frames=5)
+    pc.check_at3p_golden(emu_lib, "at3p_mono.npz", max_frames=5)

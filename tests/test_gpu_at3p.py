@@ -123,3 +123,8 @@ def test_full_size_properties(gpu_lib):
     host = enc.encode(np.ascontiguousarray(d_pcm[:64].cpu().numpy()), 64)
     enc.close()
     assert np.array_equal(host[:, :, 0], out[:64])
+
+
+def test_golden(gpu_lib):
+    pc.check_at3p_golden(gpu_lib, "at3p_stereo.npz")
+    pc.check_at3p_golden(gpu_lib, "at3p_mono.npz")

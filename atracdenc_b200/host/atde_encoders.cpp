@@ -1,74 +1,40 @@
 // atde_encoders.cpp — see atde_encoders.h.  Pure host C++ over the C ABI; no CUDA types here.
 #include "atde_encoders.h"
 
+#include <atomic>
+#include <iostream>
 #include <string>
 
 namespace NAtracDEnc {
 
-static void Check(int rc)
-{
-    // C-ABI status -> the exception type main.cpp already catches (src/main.cpp:709-720)
-    if (rc < 0)
-        throw std::runtime_error(std::string("atde_b200: ") + atde_last_error());
-}
+#ifdef ATDE_USE_REFERENCE_HEADERS
+namespace NAtdeMirror {
+#endif
+
+static std::atomic<int> g_flush_failures{0};
 
 TBatchedEncoderBase::TBatchedEncoderBase(TCompressedOutputPtr&& out, const atde_settings& settings)
     : Out(std::move(out))
+    , Batcher(settings)
 {
-    Check(atde_create(&settings, &Enc));
-    Channels = settings.channels;
-    FrameSamples = atde_frame_samples(Enc);
-    Units = atde_units_per_frame(Enc);
-    UnitBytes = atde_unit_bytes(Enc);
-    LookAhead = atde_lookahead_frames(Enc);
 }
 
 TBatchedEncoderBase::~TBatchedEncoderBase()
 {
     try {
         Flush();
+    } catch (const std::exception& ex) {
+        // destructors must not throw.  In the reference this error would have left the lambda and reached
+        // main.cpp's catch (exit code 1): make it visible — callers that need the exception call Flush() first.
+        g_flush_failures++;
+        std::cerr << "atde_b200: final flush failed, " << Batcher.Pending() << " staged frame(s) lost: " << ex.what() << std::endl;
     } catch (...) {
-        // destructors must not throw; a failed flush loses the staged tail exactly like an
-        // exception escaping the reference's lambda would have
-    }
-    atde_destroy(Enc);
-}
-
-TPCMEngine::EProcessResult TBatchedEncoderBase::Push(const float* data)
-{
-    // the PCM pointer is only valid during the call (it points into TPCMEngine's buffer): copy
-    const size_t n = (size_t)FrameSamples * Channels;
-    if (Stage.size() < BatchFrames * n)
-        Stage.resize(BatchFrames * n);
-    memcpy(&Stage[Staged * n], data, n * sizeof(float));
-    Staged++;
-    const bool lookAhead = Calls < (uint64_t)LookAhead;
-    Calls++;
-    if (Staged == BatchFrames)
-        Flush();
-    return lookAhead ? TPCMEngine::EProcessResult::LOOK_AHEAD : TPCMEngine::EProcessResult::PROCESSED;
-}
-
-void TBatchedEncoderBase::Flush()
-{
-    if (!Staged)
-        return;
-    // a look-ahead codec's first batch yields one frame less than it consumes
-    const size_t units = (size_t)atde_output_frames(Enc, (int64_t)Staged) * Units;
-    Bytes.resize(units * UnitBytes + 8);
-    Sizes.resize(units + 1);
-    const size_t staged = Staged;
-    Staged = 0;
-    Check(atde_encode_batch(Enc, Stage.data(), 1, (int64_t)staged, Bytes.data(), Sizes.data()));
-    for (size_t u = 0; u < units; u++) {
-        // same bytes, same length, same order as the reference's WriteFrame calls; payload bytes
-        // beyond the container frame size are the bit writer's zero growth slack
-        const char* p = reinterpret_cast<const char*>(&Bytes[u * UnitBytes]);
-        std::vector<char> frame((size_t)Sizes[u], 0);
-        memcpy(frame.data(), p, (size_t)Sizes[u] < (size_t)UnitBytes ? (size_t)Sizes[u] : (size_t)UnitBytes);
-        Out->WriteFrame(std::move(frame));
+        g_flush_failures++;
+        std::cerr << "atde_b200: final flush failed, " << Batcher.Pending() << " staged frame(s) lost" << std::endl;
     }
 }
+
+int TBatchedEncoderBase::FlushFailures() { return g_flush_failures.load(); }
 
 static atde_settings MakeAt1Settings(size_t channels, const NAtrac1::TAtrac1EncodeSettings& s)
 {
@@ -145,5 +111,14 @@ TPCMEngine::TProcessLambda TAt3PEnc::GetLambda()
 {
     return [this](float* data, const TPCMEngine::ProcessMeta& /*meta*/) { return Push(data); };
 }
+
+void TAt3PEnc::ParseAdvancedOpt(const char* opt, TSettings& settings)
+{
+    ParseAt3pAdvancedOpt(opt, settings.UseGha, settings.WidebandRefineMode);
+}
+
+#ifdef ATDE_USE_REFERENCE_HEADERS
+} // namespace NAtdeMirror
+#endif
 
 } // namespace NAtracDEnc

@@ -4,19 +4,31 @@
 //   NAtracDEnc::TAtrac1Encoder(TCompressedOutputPtr&&, NAtrac1::TAtrac1EncodeSettings&&)   src/atrac1denc.h:105
 //   NAtracDEnc::TAtrac3Encoder(TCompressedOutputPtr&&, NAtrac3::TAtrac3EncoderSettings&&)  src/atrac3denc.h:131
 //   NAtracDEnc::TAt3PEnc(TCompressedOutputPtr&&, int channels, TSettings)                  src/atrac3p.h:59
-// so `src/main.cpp`'s PrepareAtrac1Encoder / PrepareAtrac3Encoder / PCM loop (:292-340, :342-470,
-// :697-705) compile against it unchanged.  Differences a caller can observe: WriteFrame calls are DEFERRED — frames are staged
-// and encoded on the GPU in batches; payload bytes, lengths and call order are identical, and
-// everything is flushed by Flush() or the destructor (the processor owns the container, and
-// main.cpp destroys the processor at scope exit).
+// for programs built WITHOUT the atracdenc tree (this repo's tests, a batch transcoder over the library).  Inside the
+// atracdenc tree the reference's own class declarations are kept and atde_reference_dropin.cpp supplies their
+// member functions instead — this header is not used there.
+// Differences a caller can observe: WriteFrame calls are DEFERRED — frames are staged and encoded on the GPU in
+// batches; payload bytes, lengths and call order are identical, and everything is flushed by Flush() or the
+// destructor (the processor owns the container).  Call Flush() before destruction to get errors as exceptions; a
+// failure inside the destructor is reported on stderr and through TBatchedEncoderBase::FlushFailures().
 #pragma once
-#include "atde_boundary.h"
-#include "../../include/atde_b200.h"
+#include "atde_batcher.h"
 
 #include <iosfwd>
 #include <stdexcept>
 
+#ifdef ATDE_USE_REFERENCE_HEADERS
+#include "atrac/at1/atrac1.h"                  // NAtrac1::TAtrac1EncodeSettings
+#include "atrac/at3/atrac3.h"                  // NAtrac3::TAtrac3EncoderSettings, TContainerParams
+#endif
+
 namespace NAtracDEnc {
+
+#ifdef ATDE_USE_REFERENCE_HEADERS
+// Built next to the reference's headers the mirror classes live in their own namespace: the reference's
+// atrac1denc.h / atrac3denc.h / atrac3p.h declare classes of the same names.
+namespace NAtdeMirror {
+#endif
 
 #ifndef ATDE_USE_REFERENCE_HEADERS
 namespace NAtrac1 {
@@ -70,21 +82,17 @@ class TBatchedEncoderBase : public IProcessor {
 public:
     ~TBatchedEncoderBase() override;
     // Encode and deliver everything staged so far (idempotent).
-    void Flush();
+    // Throws std::runtime_error on failure and keeps the staged frames (a later call retries them).
+    void Flush() { Batcher.Flush(*Out); }
     // Frames staged before a batch is sent to the GPU (default 4096; tests use small values).
-    void SetBatchFrames(size_t n) { BatchFrames = n ? n : 1; }
+    void SetBatchFrames(size_t n) { Batcher.SetBatchFrames(n); }
+    // Number of destructors (process-wide) whose final flush failed: the frames were lost and the error printed.
+    static int FlushFailures();
 protected:
     TBatchedEncoderBase(TCompressedOutputPtr&& out, const atde_settings& settings);
-    TPCMEngine::EProcessResult Push(const float* data);
+    TPCMEngine::EProcessResult Push(const float* data) { return Batcher.Push(data, *Out); }
     TCompressedOutputPtr Out;
-    atde_encoder* Enc = nullptr;
-    int Channels = 0, FrameSamples = 0, Units = 0, UnitBytes = 0, LookAhead = 0;
-private:
-    std::vector<float> Stage;       // [BatchFrames][FrameSamples][Channels]
-    std::vector<uint8_t> Bytes;
-    std::vector<int32_t> Sizes;
-    size_t Staged = 0, BatchFrames = 4096;
-    uint64_t Calls = 0;
+    TFrameBatcher Batcher;
 };
 
 class TAtrac1Encoder : public TBatchedEncoderBase {
@@ -118,6 +126,12 @@ public:
     TAt3PEnc(TCompressedOutputPtr&& out, int channels, TSettings settings);
     TPCMEngine::TProcessLambda GetLambda() override;
     static constexpr int NumSamples = 2048;
+    // src/atrac/at3p/at3p.cpp:224-284 (called at src/main.cpp:480)
+    static void ParseAdvancedOpt(const char* opt, TSettings& settings);
 };
+
+#ifdef ATDE_USE_REFERENCE_HEADERS
+} // namespace NAtdeMirror
+#endif
 
 } // namespace NAtracDEnc

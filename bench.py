@@ -173,6 +173,63 @@ def cpu_reference_rate(wl, streams_per_core=8, frames=977):
                 unit="frames/s")
 
 
+# ------------------------------------------------------------------------------------------------
+# parity at benchmark scale: the bench's OWN device-generated PCM through the reference encoder
+def _verify_worker(args):
+    path, shape, idxs, codec, C, kbit, n_out, unit_bytes = args
+    import numpy as np
+    import atde_testlib as tl
+    pcm = np.load(path, mmap_mode="r")
+    res = []
+    for i in idxs:
+        x = np.ascontiguousarray(pcm[i]).reshape(-1)
+        payload, sizes = tl.ref_encode(codec, C, x, bitrate_kbit=kbit)
+        if codec == 1:                                   # WriteFrame payloads of varying length: the container pads to 212
+            units = tl.pad_units(payload, sizes, unit_bytes)[:n_out]
+        else:                                            # fixed-size frames; what follows n_out is the engine's drain
+            units = payload[:n_out * unit_bytes].reshape(n_out, unit_bytes)
+        res.append((i, np.ascontiguousarray(units)))
+    return res
+
+
+def verify_against_reference(wl, sample_pcm, sample_out, world=1):
+    """Every unit of `sample_out` ([n][units][unit_bytes], this library's output for the streams `sample_pcm`
+    [n][samples][C]) against the reference encoder (oracle/_ref: src/main.cpp:697-716's loop over the same PCM),
+    one process per host core.  Returns the `parity` object of the bench line."""
+    import multiprocessing as mp
+    import tempfile
+    import numpy as np
+    import atde_testlib as tl
+    if tl.ref_lib() is None:
+        return {"checked": False, "why": "oracle/_ref/libatde_ref.so did not travel"}
+    n, n_units, ub = sample_out.shape
+    C = sample_pcm.shape[2]
+    cores = max(1, (os.cpu_count() or 1) // max(1, world))
+    t0 = time.perf_counter()
+    with tempfile.TemporaryDirectory(prefix="atde_verify_") as td:
+        path = os.path.join(td, "pcm.npy")
+        np.save(path, sample_pcm)
+        jobs = [(path, sample_pcm.shape, list(range(k, n, cores)), wl["codec"], C, wl["kbit"], n_units, ub)
+                for k in range(min(cores, n))]
+        with mp.get_context("spawn").Pool(len(jobs)) as pool:
+            parts = pool.map(_verify_worker, jobs)
+    bad_units, bad_streams, first = 0, 0, None
+    for part in parts:
+        for i, want in part:
+            diff = (want != sample_out[i]).any(-1)
+            k = int(diff.sum())
+            if k:
+                bad_units += k
+                bad_streams += 1
+                if first is None:
+                    first = {"sample_stream": int(i), "unit": int(np.argmax(diff))}
+    upf = 2 if wl["codec"] == 1 else 1
+    return {"checked": True, "frames_checked": int(n * n_units // upf), "units_checked": int(n * n_units),
+            "streams_checked": int(n), "mismatches": int(bad_units), "mismatching_streams": int(bad_streams),
+            "first_mismatch": first, "oracle": "oracle/_ref (unmodified reference, src/main.cpp's PCM loop)",
+            "host_processes": len(jobs), "seconds": round(time.perf_counter() - t0, 2)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -239,40 +296,41 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(enc.cuda_stream, device=torch.device("cuda", local))
     torch.cuda.synchronize()
 
-    # ---- device-resident loop: `value` ----
-    for _ in range(args.warmup):
-        enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
-    enc.sync()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = enc.launch_count
-    enc.set_profiling(True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
-    e1.record(stream)
-    enc.sync()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    kms, kcnt = enc.kernel_times(6)
-    enc.set_profiling(False)
-    launches = enc.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    if not args.verify_only:
+        # ---- device-resident loop: `value` ----
+        for _ in range(args.warmup):
+            enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
+        enc.sync()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = enc.launch_count
+        enc.set_profiling(True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
+        e1.record(stream)
+        enc.sync()
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        kms, kcnt = enc.kernel_times(6)
+        enc.set_profiling(False)
+        launches = enc.launch_count - launches0
+        clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end loop through the host API: `e2e` ----
-    enc.reset()
-    for _ in range(max(1, args.warmup // 2)):
-        enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
-    torch.cuda.synchronize()
-    host_ms = (time.perf_counter() - t0) * 1000.0
-    barrier()
+        # ---- end-to-end loop through the host API: `e2e` ----
+        enc.reset()
+        for _ in range(max(1, args.warmup // 2)):
+            enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
+        torch.cuda.synchronize()
+        host_ms = (time.perf_counter() - t0) * 1000.0
+        barrier()
     # host and device entry points must agree byte for byte from the same (fresh) stream state
     enc.reset()
     fo = enc.output_frames(F)
@@ -282,6 +340,35 @@ def run_ours(args):
     enc.reset()
     enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
     same = bool(torch.equal(h_out.view(-1)[: S * fo * units * ub], dev_bytes))
+
+    # ---- parity at benchmark scale: a fixed 1-in-`stride` sample of THIS batch's streams through the reference ----
+    parity = None
+    if args.verify_stride > 0:
+        import hashlib
+        ids = list(range(0, S, args.verify_stride))
+        idt = torch.tensor(ids, device="cuda")
+        sample_pcm = d_pcm.index_select(0, idt).cpu().numpy()
+        sample_out = dev_bytes.view(S, fo * units, ub).index_select(0, idt.cpu()).numpy()
+        parity = verify_against_reference(wl, sample_pcm, sample_out, world)
+        parity["sample"] = f"streams 0, {args.verify_stride}, 2*{args.verify_stride}, ... of the {S} streams of this rank's batch"
+        parity["batch_output_sha256"] = hashlib.sha256(dev_bytes.numpy().tobytes()).hexdigest()[:16]
+        del sample_pcm, sample_out
+        if world > 1:
+            pv = torch.tensor([parity.get("frames_checked", 0), parity.get("mismatches", -1 if not parity["checked"] else 0)],
+                              dtype=torch.int64, device="cuda")
+            allp = [torch.zeros_like(pv) for _ in range(world)]
+            dist.all_gather(allp, pv)
+            parity["per_rank"] = [{"frames_checked": int(a[0]), "mismatches": int(a[1])} for a in allp]
+            parity["frames_checked"] = int(sum(int(a[0]) for a in allp))
+            parity["mismatches"] = int(sum(int(a[1]) for a in allp))
+    if args.verify_only:
+        if rank == 0:
+            print(json.dumps({"workload": wl["desc"], "n_gpus": world, "streams_per_gpu": S, "frames_per_stream": F,
+                              "host_and_device_outputs_equal": same, "parity": parity}), flush=True)
+        enc.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- the same through the int16 ingest entry point: half the H2D bytes ----
     del h_pcm                                                           # its pinned block is reused for the int16 copy
@@ -327,7 +414,10 @@ def run_ours(args):
             "config": {"workload": wl["desc"], "streams_per_gpu": S, "frames_per_stream": F, "channels": C,
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                        "l2_policy": f"inputs larger than L2 ({S * F * step * C * 4 / 2**20:.0f} MiB PCM per step)",
-                       "settings": wl["settings"]},
+                       "settings": wl["settings"],
+                       "signal": "per stream: uniform noise 0.025 FS + sine 0.03 FS at 100*(1 + s mod 160) Hz, x10 (+20 dB) "
+                                 "64-sample burst at the start of every 7th frame, every 61st stream silent, int16-quantised; "
+                                 "amplitudes are 1/10 of SURVEY.md 8(d)'s proposal (0.25 / 0.3), which clips under the bursts"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": wl["kernel"], "peak_source": f"of {peak_kind}",
@@ -344,6 +434,7 @@ def run_ours(args):
                         "note": "atde_encode_batch_i16: int16 PCM in, converted on the device"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(wl, streams_per_core=8 if wl["codec"] == 1 else 4)
@@ -363,6 +454,11 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU (debug)")
     ap.add_argument("--frames", type=int, default=0, help="override frames per stream (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify-stride", type=int, default=8,
+                    help="parity: every k-th stream of the batch goes through the reference encoder on the host cores "
+                         "(default 8: >= 1.2*10^5 frames of the 10^6-frame batches; 1 = every frame; 0 = off)")
+    ap.add_argument("--verify", dest="verify_only", action="store_true",
+                    help="only generate the batch, encode it once and verify it against the reference (no timing)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

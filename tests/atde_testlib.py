@@ -45,6 +45,21 @@ def ref_lib():
     return _ref
 
 
+def require_ref(what="this check"):
+    """Parity against the reference needs oracle/_ref.  Without it the calling test is SKIPPED with a reason
+    (never a pass); under ATDE_REQUIRE_REF=1 — set by tests/conftest.py on a box with a GPU, where the prebuilt
+    oracle/_ref must have travelled with the snapshot — it is a hard failure."""
+    lib = ref_lib()
+    if lib is not None:
+        return lib
+    import os
+    msg = f"oracle/_ref/libatde_ref.so is missing: {what} cannot be compared with the reference"
+    if os.environ.get("ATDE_REQUIRE_REF") == "1":
+        raise AssertionError(msg + " (ATDE_REQUIRE_REF=1)")
+    import pytest
+    pytest.skip(msg)
+
+
 def port_lib():
     """The plain-C restatement in oracle/*.c."""
     global _port

@@ -11,6 +11,17 @@ for p in (str(ROOT), str(ROOT / "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # On a box with a GPU the prebuilt oracle/_ref must have travelled with the snapshot: a parity test that cannot
+    # reach the reference FAILS there instead of being skipped (atde_testlib.require_ref).  Opt out with
+    # ATDE_REQUIRE_REF=0.
+    import os
+    if "ATDE_REQUIRE_REF" not in os.environ:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                os.environ["ATDE_REQUIRE_REF"] = "1"
+        except Exception:
+            pass
 
 
 @pytest.fixture(scope="session")

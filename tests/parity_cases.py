@@ -72,8 +72,7 @@ def check_at1_vs_oracle(lib, S, F, C, seed=1, **settings):
 
 def check_at1_stage_taps(lib, S=2, F=12, C=2):
     """Intermediates against the reference's own sub-objects (needs oracle/_ref)."""
-    if tl.ref_lib() is None:
-        return False
+    tl.require_ref()
     pcm = tl.synth_streams(S, F, 512, C, seed=3)
     enc = ab.Encoder(ab.CODEC_ATRAC1, C, lib=lib)
     enc.arm_taps()
@@ -172,9 +171,8 @@ def check_errors(lib):
 # through TAtrac3Encoder::GetLambda by oracle/ref_harness_at3.cpp); where it did not travel, the
 # committed fixtures under tests/golden/ (generated from it by make_golden.py) are the pin.
 def oracle_at3(C, pcm_stream, kbit=0, no_gain=0, no_tonal=0):
-    """Reference frames [Fo][FrameSz] for one stream, or None without oracle/_ref."""
-    if tl.ref_lib() is None:
-        return None
+    """Reference frames [Fo][FrameSz] for one stream (skips / fails the calling test without oracle/_ref)."""
+    tl.require_ref()
     return tl.ref_at3_stages(C, pcm_stream, kbit, no_gain, no_tonal)[2]
 
 
@@ -213,8 +211,6 @@ def check_at3_vs_oracle(lib, S, F, C, kbit=0, seed=1, kinds=("mix", "tones", "st
     checked = 0
     for s in range(S):
         want = oracle_at3(C, pcm[s].reshape(-1), kbit, **flags)
-        if want is None:
-            continue
         bad = np.argwhere((out[s, :, 0] != want).any(-1))
         assert bad.size == 0, f"stream {s} ({kinds[s % len(kinds)]}): first differing frames {bad[:4, 0].tolist()}"
         checked += 1
@@ -223,8 +219,7 @@ def check_at3_vs_oracle(lib, S, F, C, kbit=0, seed=1, kinds=("mix", "tones", "st
 
 def check_at3_stage_taps(lib, C=2, F=12, kbit=0, seed=21, kind="mix"):
     """Intermediates against the reference's own sub-objects (needs oracle/_ref)."""
-    if tl.ref_lib() is None:
-        return False
+    tl.require_ref()
     pcm = tl.synth_rich(F, 1024, C, seed=seed, kind=kind)[None]
     recs, tracked, frames = tl.ref_at3_stages(C, pcm[0].reshape(-1), kbit)
     Fo = F - 1
@@ -262,8 +257,7 @@ def check_at3_stage_taps(lib, C=2, F=12, kbit=0, seed=21, kind="mix"):
 def check_at3_main_loop(lib, C=2, kbit=0, seconds=0.4):
     """Through src/main.cpp's PCM pump (TPCMEngine(4096) + look-ahead): the frames the reference CLI
     would hand to WriteFrame for a WAV of `seconds`, against ours on the frames the lambda received."""
-    if tl.ref_lib() is None:
-        return False
+    tl.require_ref()
     n = int(44100 * seconds)
     pcm = tl.synth_rich((n + 1023) // 1024, 1024, C, seed=31)[:n]
     payload, sizes = tl.ref_encode(3, C, pcm.reshape(-1), total=n, bitrate_kbit=kbit)
@@ -323,17 +317,15 @@ def check_at3_edge_inputs(lib, kbit=0):
         out = enc.encode(x, 1)
         enc.close()
         want = oracle_at3(2, x.reshape(-1), kbit)
-        if want is not None:
-            assert np.array_equal(out[0, :, 0], want), name
-            checked += 1
+        assert np.array_equal(out[0, :, 0], want), name
+        checked += 1
     enc = _at3_enc(lib, 2, kbit)
     first = enc.encode(cases["impulse"][:1024], 1)
     assert first.shape[1] == 0
     rest = enc.encode(cases["impulse"][1024:], 1)
     enc.close()
     want = oracle_at3(2, cases["impulse"].reshape(-1), kbit)
-    if want is not None:
-        assert np.array_equal(rest[0, :, 0], want)
+    assert np.array_equal(rest[0, :, 0], want)
     return checked
 
 
@@ -383,8 +375,7 @@ def check_at3p_pqf(lib, S=3, F=6, C=2, seed=900):
     """PQF analysis bit-exact against at3plus_pqf_do_analyse (fresh context per stream and channel)."""
     pcm = _at3p_signal(S, F, C, seed)
     got = at3p_stage_pqf(lib, pcm, S, C, F)
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     for s in range(S):
         for c in range(C):
             want = tl.ref_at3p_pqf(pcm[s, :, c])
@@ -396,8 +387,7 @@ def check_at3p_pqf(lib, S=3, F=6, C=2, seed=900):
 def check_at3p_mdct(lib, S=2, F=6, C=2, seed=910):
     """MDCT bit-exact against TAt3pMDCT::Do fed with the residual the reference encoder produced
     (work buffer after the tone filter, scaled like at3p.cpp:150-153)."""
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     pcm = _at3p_signal(S, F + 1, C, seed)
     resid = np.zeros((S, C, F, 2048), np.float32)
     want = np.zeros((S, F, C, 2048), np.float32)
@@ -431,8 +421,7 @@ def check_at3p_pack(lib, S=2, F=6, C=2, seed=920, loud=False):
     """Frame packer (scale, quantise, code-table choice, tonal block, bit writer) bit-exact against
     TAt3PBitStream::WriteFrame, fed with the spectra and the tone data of the reference encoder: the
     frame written in call t carries the GHA result of call t-1 (`delay`, at3p.cpp:127-131,186-190)."""
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     pcm = _at3p_signal(S, F + 1, C, seed)
     if loud:
         pcm = tl.quantise(np.clip(pcm.astype(np.float64) * 12.0, -1.0, 1.0))       # forces the unit-dropping loop
@@ -451,8 +440,7 @@ def check_at3p_pack(lib, S=2, F=6, C=2, seed=920, loud=False):
 def check_at3p_pack_random(lib, U=12, C=2, seed=940):
     """Packer on random spectra of growing level: walks TTonalComponentEncoder's unit-dropping loop well
     below 28 units, which no natural signal reaches; tone data borrowed from a real encode."""
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     rng = np.random.default_rng(seed)
     st = tl.ref_at3p_stages(C, _at3p_signal(1, 5, C, seed)[0].reshape(-1))
     tones = np.zeros(U, tl.AT3P_GHA_REC)
@@ -493,8 +481,7 @@ def _shift(recs, k):
 def check_at3p_tone_filter(lib, S=2, F=8, C=2, seed=960):
     """Tone subtraction + MDCT input scaling bit-exact against the work buffer TGhaProcessorBase::ApplyFilter
     leaves behind, fed with the reference's own GHA results of three consecutive calls."""
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     pcm = _at3p_signal(S, F + 1, C, seed)
     for s in range(S):
         st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
@@ -509,8 +496,7 @@ def check_at3p_tone_filter(lib, S=2, F=8, C=2, seed=960):
 def check_at3p_chain_after_gha(lib, S=2, F=8, C=2, seed=970):
     """PCM -> PQF -> [reference GHA results] -> tone filter -> MDCT -> packer == the reference's frames:
     everything of the ATRAC3plus path except the tone search itself, chained on the device kernels."""
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     pcm = _at3p_signal(S, F + 1, C, seed)
     bands = at3p_stage_pqf(lib, pcm, S, C, F + 1)                        # [S][C][F+1][2048]
     for s in range(S):
@@ -609,8 +595,7 @@ def _tone_records_equal(got, want, C):
 
 def check_at3p_gha(lib, S=2, F=4, C=2, seed=980):
     """The tone search (DoAnalize without the filter) against the reference's GHA results, frame by frame."""
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     pcm = _at3p_signal(S, F + 1, C, seed)
     bands = at3p_stage_pqf(lib, pcm, S, C, F + 1)
     got = at3p_stage_gha(lib, bands, S, C, F + 1)
@@ -626,8 +611,7 @@ def check_at3p_gha(lib, S=2, F=4, C=2, seed=980):
 def check_at3p_full_chain(lib, S=2, F=6, C=2, seed=990):
     """PCM -> PQF -> tone search -> tone filter -> MDCT -> packer, every stage on the device kernels,
     == the frames of the reference encoder (fresh streams)."""
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     pcm = _at3p_signal(S, F + 1, C, seed)
     bands = at3p_stage_pqf(lib, pcm, S, C, F + 1)                        # [S][C][F+1][2048]
     tones = at3p_stage_gha(lib, bands, S, C, F + 1)                      # [S][F+1]; call o+1 analyses frame o
@@ -655,8 +639,7 @@ def check_at3p_vs_oracle(lib, S=3, F=7, C=2, seed=1200):
     out = enc.encode(pcm, S)
     enc.close()
     assert out.shape == (S, F - 1, 1, 2048)
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     for s in range(S):
         st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
         assert st["n"] == F - 1
@@ -737,8 +720,7 @@ def check_at3p_gha_masks(lib, masks=(0, 1, 2, 3, 4, 5, 6), S=2, F=6, C=2, seed=1
     pcm = _at3p_signal(S, F, C, seed)
     with pytest.raises(ab.AtdeError):
         ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib, gha_flags=8 | 7)          # GHA_WIDEBAND: not built
-    if tl.ref_lib() is None:
-        return 0
+    tl.require_ref()
     for mask in masks:
         enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib, gha_flags=mask)
         a = enc.encode(pcm[:, :3 * 2048], S)
@@ -774,25 +756,24 @@ def check_at3p_edge_inputs(lib, C=2, F=5):
     }
     cases["impulse"][3000, 0] = -1.0
     checked = 0
+    tl.require_ref()
     for name, x in cases.items():
         x = tl.quantise(np.ascontiguousarray(x, np.float32))
         enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
         out = enc.encode(x, 1)
         enc.close()
         assert out.shape == (1, F - 1, 1, 2048), name
-        if tl.ref_lib() is not None:
-            st = tl.ref_at3p_stages(C, x.reshape(-1))
-            bad = np.argwhere((out[0, :, 0] != st["frames"]).any(-1))
-            assert bad.size == 0, f"{name}: differing frames {bad[:4].ravel().tolist()}"
-            checked += 1
+        st = tl.ref_at3p_stages(C, x.reshape(-1))
+        bad = np.argwhere((out[0, :, 0] != st["frames"]).any(-1))
+        assert bad.size == 0, f"{name}: differing frames {bad[:4].ravel().tolist()}"
+        checked += 1
     x = tl.quantise(np.ascontiguousarray(cases["sine_stops"], np.float32))
     enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=lib)
     first = enc.encode(x[:2048], 1)
     assert first.shape[1] == 0
     rest = enc.encode(x[2048:], 1)
     enc.close()
-    if tl.ref_lib() is not None:
-        assert np.array_equal(rest[0, :, 0], tl.ref_at3p_stages(C, x.reshape(-1))["frames"])
+    assert np.array_equal(rest[0, :, 0], tl.ref_at3p_stages(C, x.reshape(-1))["frames"])
     return checked
 
 

@@ -109,11 +109,11 @@ def test_full_size_properties(gpu_lib):
     enc.sync()
     out = d_out.cpu().numpy()
     assert (out.reshape(S // 16, 16, fo, ub) == out[:16]).all()
-    if tl.ref_lib() is not None:
-        for s in range(0, 16, 3):
-            want = tl.ref_at3p_stages(C, base[s].reshape(-1))["frames"]
-            bad = np.argwhere((out[s] != want).any(-1))
-            assert bad.size == 0, (s, bad[:4, 0].tolist())
+    tl.require_ref()
+    for s in range(0, 16, 3):
+        want = tl.ref_at3p_stages(C, base[s].reshape(-1))["frames"]
+        bad = np.argwhere((out[s] != want).any(-1))
+        assert bad.size == 0, (s, bad[:4, 0].tolist())
     enc.reset()
     d_out2 = torch.empty_like(d_out)
     enc.encode_device(d_pcm.data_ptr(), S, F, d_out2.data_ptr())

@@ -23,7 +23,7 @@ def test_vs_oracle(gpu_lib, kbit, C):
     """LP2, LP4 (joint stereo), mono LP2, and two more containers (132300 via 128 kbit request;
     104738 non-JS via 94*1024=96256)."""
     n = pc.check_at3_vs_oracle(gpu_lib, S=8, F=48, C=C, kbit=kbit, seed=1000 + kbit)
-    assert n == 8 or tl.ref_lib() is None
+    assert n == 8
 
 
 def test_vs_oracle_flags(gpu_lib):
@@ -66,7 +66,7 @@ def test_long_streams_against_oracle(gpu_lib):
     """64 streams x 200 frames per mode (25 k stereo frames): every stream against the reference."""
     for kbit in (0, 64):
         n = pc.check_at3_vs_oracle(gpu_lib, S=64, F=200, C=2, kbit=kbit, seed=5000 + kbit)
-        assert n == 64 or tl.ref_lib() is None
+        assert n == 64
 
 
 @pytest.mark.parametrize("kbit", [0, 64])
@@ -75,6 +75,7 @@ def test_full_size_properties(gpu_lib, kbit):
     device-resident: (a) replicated streams give replicated bitstreams, (b) the 16 distinct streams
     match the reference, (c) the batch is reproducible after atde_reset()."""
     import torch
+    tl.require_ref("test_full_size_properties (b)")
     S, F, C = 1024, 977, 2
     base = np.stack([tl.synth_rich(F, 1024, C, seed=9000 + s, kind=("mix", "tones", "steps")[s % 3]) if s % 4
                      else tl.synth_streams(1, F, 1024, C, seed=9000 + s)[0] for s in range(16)])
@@ -89,11 +90,10 @@ def test_full_size_properties(gpu_lib, kbit):
     out = d_out.cpu().numpy()
     assert np.array_equal(out[:16], out[16:32]) and np.array_equal(out[:16], out[-16:])
     assert (out.reshape(S // 16, 16, fo, ub) == out[:16]).all()
-    if tl.ref_lib() is not None:
-        for s in range(16):
-            want = pc.oracle_at3(C, base[s].reshape(-1), kbit)
-            bad = np.argwhere((out[s] != want).any(-1))
-            assert bad.size == 0, (s, bad[:4, 0].tolist())
+    for s in range(16):
+        want = pc.oracle_at3(C, base[s].reshape(-1), kbit)
+        bad = np.argwhere((out[s] != want).any(-1))
+        assert bad.size == 0, (s, bad[:4, 0].tolist())
     enc.reset()
     d_out2 = torch.empty_like(d_out)
     enc.encode_device(d_pcm.data_ptr(), S, F, d_out2.data_ptr())

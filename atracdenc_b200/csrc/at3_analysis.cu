@@ -247,44 +247,43 @@ ATDE_D void median_filter1(const float* in, float* out, int n)
     }
 }
 
-// FindPlateau (transient_detector.cpp:175-262) + target selection (:286-299); in[] has 32 entries.
-ATDE_D float plateau_target(const float* in)
+// FindPlateau (transient_detector.cpp:175-262) + target selection (:286-299) over the 32 sub-frame levels:
+//   filt = MedianFilter<1>(in); best = max over j of min(filt[j..j+2]) (first j wins), the run is extended while
+//   filt >= best; "release" if the frame ends far below the plateau; the plateau is the target unless it is released,
+//   negligible or below 0.4 of the frame's maximum — then the last level is.
+// By a whole warp: lane i holds in[i] (all values >= 0: they are RMS levels, so their bit patterns order
+// like the floats and redux.sync finds maxima).  Every lane returns the target.
+ATDE_D float plateau_target_warp(float a, int lane)
 {
-    const int n = 32, minc = 3;
-    float max_raw = 0.0f;
-    for (int i = 0; i < n; i++) max_raw = fmaxf(max_raw, in[i]);
-    float filt[32];
-    median_filter1(in, filt, n);
-    float best = 0.0f;
-    int best_end = -1;
-    for (int j = 0; j + minc <= n; j++) {
-        float mv = filt[j];
-        for (int k = 1; k < minc; k++) mv = fminf(mv, filt[j + k]);
-        if (mv > best) { best = mv; best_end = j + minc - 1; }
-    }
-    float level = best;
+    const unsigned full = 0xffffffffu;
+    const float left = __shfl_up_sync(full, a, 1), right = __shfl_down_sync(full, a, 1);
+    const float filt = lane == 0 ? fmaxf(a, right) : (lane == 31 ? fmaxf(left, a) : median3(left, a, right));
+    const float max_raw = __uint_as_float(__reduce_max_sync(full, __float_as_uint(a)));
+    const float f1 = __shfl_down_sync(full, filt, 1), f2 = __shfl_down_sync(full, filt, 2);
+    const float mv = lane <= 29 ? fminf(fminf(filt, f1), f2) : 0.0f;
+    const float best = __uint_as_float(__reduce_max_sync(full, __float_as_uint(mv)));      // 0 when no run is above 0
+    const float last = __shfl_sync(full, a, 31);
     bool release = false;
+    float level = best;
     if (best < 1e-6f) {
         level = 0.0f;
     } else {
-        while (best_end + 1 < n && filt[best_end + 1] >= best) ++best_end;
-        if (best_end < n - 1) {
-            if (in[n - 1] < fmul(best, 0.1f)) {
-                release = true;
-            } else {
-                bool any_high = false;
-                for (int i = best_end + 1; i < n; i++)
-                    if (in[i] >= fmul(best, 0.7f)) { any_high = true; break; }
-                release = !any_high && (in[n - 1] < fmul(best, 0.5f));
-            }
+        // first run that reaches the maximum (the serial scan only replaces on '>'), extended while filt >= best
+        int best_end = __ffs((int)__ballot_sync(full, lane <= 29 && mv == best)) - 1 + 2;
+        const unsigned below = ~__ballot_sync(full, filt >= best) & (best_end >= 31 ? 0u : (full << (best_end + 1)));
+        best_end = below ? __ffs((int)below) - 2 : 31;
+        const unsigned high = __ballot_sync(full, a >= fmul(best, 0.7f));
+        if (best_end < 31) {
+            if (last < fmul(best, 0.1f)) release = true;
+            else release = !(high & (full << (best_end + 1))) && (last < fmul(best, 0.5f));
         }
     }
     const bool use_plateau = level > 1e-6f && !release && level >= fmul(max_raw, 0.4f);
-    return use_plateau ? level : in[n - 1];
+    return use_plateau ? level : last;
 }
 
-constexpr int kGainThreads = 128;         // FFT threads
-constexpr int kGainBlock = kGainThreads + 32;   // + one helper warp for the double-precision hfr sums
+constexpr int kGainThreads = 128;         // threads per block
+constexpr int kGainBlock = kGainThreads;
 
 // The 2048-point buffer is padded by one element per 8 (pass 1 stores 8 consecutive slots per thread:
 // a 9-element thread stride is conflict-free) and by 8 more per 128 (so the eight-lane groups of
@@ -298,12 +297,14 @@ ATDE_D int sphys(int j) { return j + ((j >> 6) << 2); }
 // 16, 4 elements) then fall on 16 different bank pairs.
 ATDE_D int fq(int k) { return k + (k >> 4); }
 
-// One radix-4 butterfly of the forward FFT-256 on the padded buffer; F = first element, m = sub-length.
-ATDE_D void fwd_bfly(cpx* buf, int F, int m, cpx t1, cpx t2, cpx t3)
+// One radix-4 butterfly of the forward FFT-256 on the padded buffer: elements p, p + d, p + 2d, p + 3d in PADDED
+// coordinates (the callers fold fq() into p and d: every stage touches elements whose padding is an affine function of
+// the butterfly number, so the addresses are base + constant and need no per-access index arithmetic).
+ATDE_D void fwd_bfly(cpx* buf, int p, int d, cpx t1, cpx t2, cpx t3)
 {
-    cpx f0 = buf[fq(F)], f1 = buf[fq(F + m)], f2 = buf[fq(F + 2 * m)], f3 = buf[fq(F + 3 * m)];
+    cpx f0 = buf[p], f1 = buf[p + d], f2 = buf[p + 2 * d], f3 = buf[p + 3 * d];
     kf_bfly4<false>(f0, f1, f2, f3, t1, t2, t3);
-    buf[fq(F)] = f0; buf[fq(F + m)] = f1; buf[fq(F + 2 * m)] = f2; buf[fq(F + 3 * m)] = f3;
+    buf[p] = f0; buf[p + d] = f1; buf[p + 2 * d] = f2; buf[p + 3 * d] = f3;
 }
 
 // One (stream, channel, band, frame) per block.
@@ -321,7 +322,7 @@ ATDE_D void fwd_bfly(cpx* buf, int F, int m, cpx t1, cpx t2, cpx t3)
 // by the structural zeros is exact, so the values equal the full transform's (up to the sign of zero,
 // which no consumer can see: the output is squared).
 // Only output samples [1024, 3072) are consumed (AnalyzeGain), i.e. complex slots [512, 1536).
-__global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buffers b)
+__global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) cpx big[2048 + 256 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ __align__(8) cpx tw2c[15][8];         // pass-2 twiddles of lane group k, compact
@@ -330,8 +331,7 @@ __global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buf
     __shared__ __align__(16) cpx sup[257 + 17];      // super4096[k - 1] at fq(k), k = 1..256
     __shared__ float micro[256];
     __shared__ float sgain[96];
-    __shared__ __align__(16) double2 ee[257];        // (|X_k|^2, |X_k H_k|^2)
-    __shared__ double esum2[2];
+    __shared__ double esum_part[kGainThreads / 32][2];   // per-warp partial sums of (|X_k|^2, |X_k H_k|^2)
     __shared__ float sstat[2];
 
     const DevTables* __restrict__ T = b.tab;
@@ -359,19 +359,20 @@ __global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buf
     __syncthreads();
     // 2. forward complex FFT-256 = 4x4x4x4, innermost stage first; the lane -> butterfly map of every
     //    stage is chosen so that 16 consecutive lanes touch 16 different bank pairs
-    if (tid < 64) fwd_bfly(fwd, 4 * tid, 1, T->ftw[0][0][0], T->ftw[0][1][0], T->ftw[0][2][0]);
+    //    (padded addresses: element F + m q of a butterfly lies at fq(F) + q * (m + m / 16))
+    if (tid < 64) fwd_bfly(fwd, 4 * tid + (tid >> 2), 1, T->ftw[0][0][0], T->ftw[0][1][0], T->ftw[0][2][0]);
     __syncthreads();
     if (tid < 64) {
         const int gq = tid & 15, k = tid >> 4;
-        fwd_bfly(fwd, 16 * gq + k, 4, T->ftw[1][0][k], T->ftw[1][1][k], T->ftw[1][2][k]);
+        fwd_bfly(fwd, 17 * gq + k, 4, T->ftw[1][0][k], T->ftw[1][1][k], T->ftw[1][2][k]);
     }
     __syncthreads();
     if (tid < 64) {
         const int gq = tid >> 4, k = tid & 15;
-        fwd_bfly(fwd, 64 * gq + k, 16, T->ftw[2][0][k], T->ftw[2][1][k], T->ftw[2][2][k]);
+        fwd_bfly(fwd, 68 * gq + k, 17, T->ftw[2][0][k], T->ftw[2][1][k], T->ftw[2][2][k]);
     }
     __syncthreads();
-    if (tid < 64) fwd_bfly(fwd, tid, 64, T->ftw[3][0][tid], T->ftw[3][1][tid], T->ftw[3][2][tid]);
+    if (tid < 64) fwd_bfly(fwd, tid + (tid >> 4), 68, T->ftw[3][0][tid], T->ftw[3][1][tid], T->ftw[3][2][tid]);
     __syncthreads();
     // kiss_fftr post-processing (kiss_fftr.c:84-115)
     ATDE_PAR_FOR(k, 129) {
@@ -394,30 +395,32 @@ __global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buf
         }
     }
     __syncthreads();
-    // 2a. high-frequency energy ratio (upsampler.cpp:99-118): two SEQUENTIAL double sums over the 257
-    //     bins.  The helper warp takes them (per-bin terms lane-parallel, then both chains interleaved
-    //     on one lane) while the four FFT warps run the inverse transform; they only meet again at the
-    //     final barrier.
+    // 2a. high-frequency energy ratio (upsampler.cpp:99-118).  The reference adds the 257 per-bin energies (and the
+    //     HPF-weighted ones) SEQUENTIALLY in double and hands float(hi / tot) to the curve builder, where the value is
+    //     only ever COMPARED with kHighFreqThreshold = 0.05f and with 0.3f (atrac3denc.cpp:352,431).  Here the two sums
+    //     are taken as a tree over the block — any summation order of 257 non-negative doubles agrees with the
+    //     sequential one to 257 * 2^-53 relative, the ratio to ~1.2e-13 — and a result that lands within 1e-7
+    //     (relative) of one of the two thresholds, where the float rounding of the ratio could decide a comparison
+    //     differently, is recomputed with the reference's sequential loop at the end of the kernel.
     const int lcb = T->low_cut_bin;
-    if (tid >= kGainThreads) {
-        const int hl = tid - kGainThreads;
-        for (int k = hl; k < 257; k += 32) {
-            const double r = (double)freq[fq(k)].r, i = (double)freq[fq(k)].i;
+    {
+        double tot = 0.0, hi = 0.0;
+        for (int k = tid; k < 257; k += kGainThreads) {
+            const cpx z = freq[fq(k)];
+            const double r = (double)z.r, i = (double)z.i;
             const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
             float H = 0.0f;
             if (k >= lcb + 2) H = 1.0f;
             else if (k >= lcb) H = T->hpf_h[k - lcb];
-            ee[k] = make_double2(e, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
+            tot = __dadd_rn(tot, e);
+            hi = __dadd_rn(hi, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
         }
-        __syncwarp();
-        if (hl == 0) {
-            double tot = 0.0, hi = 0.0;
-#pragma unroll 4
-            for (int k = 0; k <= 256; k++) { const double2 v = ee[k]; tot = __dadd_rn(tot, v.x); hi = __dadd_rn(hi, v.y); }
-            esum2[0] = tot; esum2[1] = hi;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            tot = __dadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, d));
+            hi = __dadd_rn(hi, __shfl_xor_sync(0xffffffffu, hi, d));
         }
-        __syncthreads();                                      // the final barrier of the FFT warps
-        return;
+        if ((tid & 31) == 0) { esum_part[tid >> 5][0] = tot; esum_part[tid >> 5][1] = hi; }
     }
     // 3/4. inverse FFT input Y[k] = 8*X[k]*H[k] (Nyquist bin halved), kiss_fftri pre-processing
     //      (kiss_fftr.c:131-151) with Y[2048-k] == 0, and pass 1 of the inverse FFT.
@@ -482,12 +485,14 @@ __global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buf
     atde_named_barrier(1, kGainThreads);
     // pass 2: radix-4 m = 8 (fstride 64), then m = 32 (fstride 16)
     {
-        const int k = tid & 7, base = (tid >> 3) << 7;
+        // gphys(base + k + 8a + 32q) = gphys(base + k) + 9a + 36q  (k < 8, base a multiple of 128)
+        const int k = tid & 7;
+        cpx* const bg = big + gphys(((tid >> 3) << 7) + k);
         cpx x[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) x[a][q] = big[gphys(base + k + 8 * a + 32 * q)];
+            for (int q = 0; q < 4; q++) x[a][q] = bg[9 * a + 36 * q];
         {
             const cpx t1 = tw2c[0][k], t2 = tw2c[1][k], t3 = tw2c[2][k];      // tw[64k], tw[128k], tw[192k]
 #pragma unroll
@@ -499,17 +504,19 @@ __global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buf
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) big[gphys(base + k + 8 * a + 32 * q)] = x[a][q];
+            for (int q = 0; q < 4; q++) bg[9 * a + 36 * q] = x[a][q];
     }
     atde_named_barrier(1, kGainThreads);
     // pass 3: radix-4 m = 128 (fstride 4), then m = 512 (fstride 1); keep slots [512, 1536), normalised
     {
+        // gphys(k + 128a + 512q) = k + k / 8 + 152a + 608q  (k < 128)
         const int k = tid;
+        const cpx* const bg = big + k + (k >> 3);
         cpx x[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) x[a][q] = big[gphys(k + 128 * a + 512 * q)];
+            for (int q = 0; q < 4; q++) x[a][q] = bg[152 * a + 608 * q];
         atde_named_barrier(1, kGainThreads);                                  // every slot is in registers: big can be overwritten
         {
             const cpx t1 = T->gtw3a[0][k], t2 = T->gtw3a[1][k], t3 = T->gtw3a[2][k];     // tw[4k], tw[8k], tw[12k]
@@ -518,15 +525,15 @@ __global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buf
         }
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-            const int kk = k + 128 * a;
             kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], T->gtw3b[a][0][k], T->gtw3b[a][1][k], T->gtw3b[a][2][k]);  // tw[kk], tw[2kk], tw[3kk]
             // 5. normalise (norm = 1/4096); complex slot kk + 512q -> output samples 2*slot, 2*slot+1
             cpx u, v;
             u.r = fmul(x[a][1].r, 1.0f / 4096.0f); u.i = fmul(x[a][1].i, 1.0f / 4096.0f);
             v.r = fmul(x[a][2].r, 1.0f / 4096.0f); v.i = fmul(x[a][2].i, 1.0f / 4096.0f);
-            float* sigw = reinterpret_cast<float*>(big);
-            *reinterpret_cast<cpx*>(sigw + sphys(2 * kk)) = u;            // slot 512 + kk  -> samples 1024 + 2kk, +1
-            *reinterpret_cast<cpx*>(sigw + sphys(1024 + 2 * kk)) = v;     // slot 1024 + kk -> samples 2048 + 2kk, +1
+            // sphys(2kk) = 2k + 4 (k / 32) + 272a;  sphys(1024 + 2kk) = that + 1088
+            float* sigw = reinterpret_cast<float*>(big) + 2 * k + 4 * (k >> 5);
+            *reinterpret_cast<cpx*>(sigw + 272 * a) = u;                  // slot 512 + kk  -> samples 1024 + 2kk, +1
+            *reinterpret_cast<cpx*>(sigw + 272 * a + 1088) = v;           // slot 1024 + kk -> samples 2048 + 2kk, +1
         }
     }
     atde_named_barrier(1, kGainThreads);
@@ -575,15 +582,35 @@ __global__ void __launch_bounds__(kGainBlock, 6) at3_gain_kernel(Geometry g, Buf
         float cur = 0.0f;
         for (int i = 0; i < 32; i++) cur = fadd(cur, sgain[i]);
         sstat[0] = __fdiv_rn(cur, 32.0f);
-    } else if (tid == 96) {
-        sstat[1] = plateau_target(sgain);
+    } else if (tid >= 96) {
+        const float tgt = plateau_target_warp(sgain[tid - 96], tid - 96);
+        if (tid == 96) sstat[1] = tgt;
     }
     __syncthreads();
     const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
     if (tid < 96) b.gain[item * 96 + tid] = sgain[tid];
     if (tid == 0) {
+        double tot = __dadd_rn(__dadd_rn(esum_part[0][0], esum_part[1][0]), __dadd_rn(esum_part[2][0], esum_part[3][0]));
+        double hi = __dadd_rn(__dadd_rn(esum_part[0][1], esum_part[1][1]), __dadd_rn(esum_part[2][1], esum_part[3][1]));
+        if (tot > 0.0) {
+            const double ratio = __ddiv_rn(hi, tot);
+            const double t1 = (double)0.05f, t2 = (double)0.3f;
+            if (fabs(ratio - t1) <= t1 * 1e-7 || fabs(ratio - t2) <= t2 * 1e-7) {
+                // too close to a decision threshold for a reordered sum: the reference's loop, bin by bin
+                tot = 0.0; hi = 0.0;
+                for (int k = 0; k <= 256; k++) {
+                    const double r = (double)freq[fq(k)].r, i = (double)freq[fq(k)].i;
+                    const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
+                    float H = 0.0f;
+                    if (k >= lcb + 2) H = 1.0f;
+                    else if (k >= lcb) H = T->hpf_h[k - lcb];
+                    tot = __dadd_rn(tot, e);
+                    hi = __dadd_rn(hi, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
+                }
+            }
+        }
         float4 st4;
-        st4.x = (esum2[0] > 0.0) ? __double2float_rn(__ddiv_rn(esum2[1], esum2[0])) : 0.0f;
+        st4.x = (tot > 0.0) ? __double2float_rn(__ddiv_rn(hi, tot)) : 0.0f;
         st4.y = sstat[0];
         st4.z = sstat[1];
         st4.w = sgain[31];
@@ -939,317 +966,401 @@ ATDE_D float safe_energy_scale(float orig, float mod)
     return (fabsf(sc) < inf && sc > 0.0f) ? sc : 1.0f;
 }
 
-// One WARP per (stream, frame, channel), no block-wide barrier.  The unit's four MDCT-512 run as two
-// iterations of two bands, 16 lanes per band:
-//   phase A  load the band samples of this and the previous frame (coalesced float4), divide by the
-//            gain curves, window, store the two 512-sample MDCT inputs to the warp's tile
-//   phase B  fold + pre-twiddle (mdct.h:56-76) straight into kissfft's gather order; lane k16 of a band
-//            owns gather block k16 (8 consecutive slots) and runs the two innermost stages
-//            (radix-2 m=1, radix-4 m=2) on registers
-//   exchange through the tile: lane (k, bp) takes elements k + 8a + 32b, a = 0..3, b = 2bp, 2bp+1
-//   phase C  radix-4 m=8 over a; lane pairs (k16, k16^8) swap halves by shuffle so that lane (k, ap)
-//            holds k + 8a + 32b, a = 2ap, 2ap+1, b = 0..3; radix-4 m=32 over b; post-twiddle
-//            (mdct.h:92-101); spectrum staged in the tile and written out as coalesced float4
+// One WARP walks a RUN of consecutive frames of one (stream, channel); the band samples come in by bulk
+// asynchronous copies (1-D TMA) and the spectra leave the same way:
+//   ring    per band two 256-sample slots: the previous frame's samples (already gain-modulated) and this frame's.
+//           While frame f is transformed, lane 0 has the copy engine fetch frame f+1 into the slots frame f-1
+//           just vacated (cp.async.bulk + mbarrier); nothing is read twice and the warp never waits on a load it
+//           issued itself.  (The first frame of a stream takes the carried, already windowed half instead.)
+//   energy  bands that touch a gain curve: CalcGainEnergyScale's sequential sums (atrac3denc.cpp:189-216) from the ring,
+//           then the frame's samples are divided by the curve IN PLACE — the next frame needs them modulated too —
+//           and the overlap scale is handed on in a register.
+//   fold    all four MDCT-512 at once, 8 lanes per band, 16 complex points per lane: window (atrac3denc.cpp:39-49),
+//           fold + pre-twiddle (mdct.h:56-76) straight from the ring into kissfft's gather order; radix-2 m=1 and
+//           radix-4 m=2 on registers
+//   exchange through the warp's tile (padded 1 per 16: conflict-free both ways)
+//   finish  radix-4 m=8 and m=32 on registers, post-twiddle (mdct.h:92-101), odd bands reversed
+//           (atrac3denc.cpp:53-55), spectrum staged in the tile and stored with cp.async.bulk
 // Every butterfly keeps kissfft's operation order (kissfft_dev.cuh), so the regrouping is exact.
-// The loop body is kept small on purpose (two bands per iteration): the fully unrolled four-band version missed
-// the instruction cache on every warp.  Gain-curve divisors are built once per band by the whole warp
-// (curve_levels_warp) instead of per sample: the per-sample curve walk was 28 % of this kernel's instructions
-// and 45 % of its stall samples on the bench signal (ncu v6).
-constexpr int kMdctWarps = 4;
-constexpr int kMdctBandStride = 520;                 // floats; keeps float4 alignment, shifts banks by 8
-constexpr int kMdctXchStride = 152;                  // cpx per band in the exchange layout (16 blocks x 9, +8)
-constexpr int kMdctOutStride = 264;
-constexpr int kMdctTermStride = 132;                 // floats between the seven energy-term rows: the seven summing lanes hit 28 different banks
-constexpr int kMdctLevels = 2 * kMdctBandStride;     // floats: divisor tables of the band in work (its own curve, the previous frame's)
-constexpr int kMdctTile = kMdctLevels + 512;         // floats per warp: two MDCT inputs (or 7 x 128 energy terms) + the two tables
+constexpr int kMdWarps = 4;
+#ifndef ATDE_MD_RUN
+#define ATDE_MD_RUN 16                               // (the CPU-emulation build uses 3 so that tiny batches cross run boundaries)
+#endif
+constexpr int kMdRun = ATDE_MD_RUN;                  // frames a warp walks before it takes the next item
+constexpr int kMdRingBand = 2 * 256 + 8;             // floats per band: two slots; +8 spreads the bands over the banks
+constexpr int kMdRingFloats = 4 * kMdRingBand;       // 2080
+constexpr int kMdXchBand = 136;                      // cpx per band in the exchange layout (128 + 1 per 16)
+constexpr int kMdOutBand = 2 * kMdXchBand;           // floats per band in the output layout (272: 16-byte aligned rows)
+constexpr int kMdTileFloats = 4 * kMdOutBand;        // 1088 (exchange / output / energy-term scratch)
+constexpr int kMdTermStride = 132;                   // floats between energy-term rows
 
-__global__ void __launch_bounds__(kMdctWarps * 32, 7) at3_mdct_kernel(Geometry g, Buffers b)
+struct MdWarpShared {
+    float ring[kMdRingFloats];
+    float tile[kMdTileFloats];
+    Curve cv[4][2];                                  // [band][0] previous frame, [1] this frame
+    float esum[4][8];                                // energy sums 0..4; [5] = divisor of the stored half (d0), [6] = overlap scale
+    mbar_t bar;
+    unsigned long long pad_;
+};
+struct MdBlockShared {
+    float sincos[256];
+    float win[256];
+    float ones[256];
+    cpx tw[128];
+    MdWarpShared w[kMdWarps];
+};
+
+__global__ void __launch_bounds__(kMdWarps * 32, 4) at3_mdct_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) float tile[kMdctWarps][kMdctTile];
-    __shared__ __align__(16) float s_sincos[256];
-    __shared__ __align__(16) float s_win[256];
-    __shared__ __align__(16) cpx s_tw[128];
-    __shared__ Curve s_cv[kMdctWarps][4][2];         // [band][0] previous frame, [1] this frame
-    __shared__ float s_esum[kMdctWarps][4][8];
+    ATDE_DYN_SMEM(smem_raw);
+    MdBlockShared& sh = *reinterpret_cast<MdBlockShared*>(smem_raw);
 
     const DevTables* __restrict__ T = b.tab;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ATDE_PAR_FOR(i, 256) { s_sincos[i] = T->sincos512[i]; s_win[i] = T->encode_window[i]; }
-    ATDE_PAR_FOR(i, 128) s_tw[i] = T->tw128[i];
+    ATDE_PAR_FOR(i, 256) { sh.sincos[i] = T->sincos512[i]; sh.win[i] = T->encode_window[i]; sh.ones[i] = 1.0f; }
+    ATDE_PAR_FOR(i, 128) sh.tw[i] = T->tw128[i];
+    MdWarpShared& ws = sh.w[warp];
+    if (lane == 0) mbar_init(&ws.bar, 1);
+    async_proxy_fence();
     __syncthreads();
 
-    float* tl = tile[warp];
-    const long long n_units = (long long)g.S * g.n_out * g.C;
-    for (long long unit = (long long)blockIdx.x * kMdctWarps + warp; unit < n_units;
-         unit += (long long)gridDim.x * kMdctWarps) {
-        const int c = (int)(unit % g.C);
-        const long long sf = unit / g.C;
-        const int f = (int)(sf % g.n_out), s = (int)(sf / g.n_out);
-        const size_t sc = (size_t)s * g.C + c;
+    float* const ring = ws.ring;
+    float* const tile = ws.tile;
+    unsigned phase = 0;                                  // parity of the barrier phase the next wait looks at
+    const int runs = (g.n_out + kMdRun - 1) / kMdRun;
+    const long long n_items = (long long)g.S * g.C * runs;
+    const int bnd = lane >> 3, L = lane & 7;             // fold / FFT ownership: band, lane within the band
 
-        __syncwarp();                                    // previous unit's tile reads are done
-        if (lane < 8) {
-            const int band = lane >> 1, which = lane & 1;
-            Curve cv;
-            cv.n = 0;
-            const int ff = f - 1 + which;
-            if (!g.no_gain && band < kGainBands && ff >= 0)
-                cv = b.curves[(sc * 4 + band) * g.n_out + ff];
-            s_cv[warp][band][which] = cv;
-        }
-        __syncwarp();
-        // A band whose own curve is empty and whose overlap scale is 1 has every energy scale exactly 1.0
-        // (SafeEnergyScale(x, x)); the sequential energy sums only run for bands that touch a curve.
-        unsigned trivial = 0;                              // bit per band (a mask, so that the band loop below stays rolled)
+    for (long long item = (long long)blockIdx.x * kMdWarps + warp; item < n_items; item += (long long)gridDim.x * kMdWarps) {
+        const int run = (int)(item % runs);
+        const size_t sc = (size_t)(item / runs);
+        const int c = (int)(sc % g.C), s = (int)(sc / g.C);
+        const int f0 = run * kMdRun, f1 = min(f0 + kMdRun, g.n_out);
+        const float* const brow = b.bands + sc * 4 * g.BL + 128;          // band q, frame f: brow + q BL + 256 f
+        const bool gain = !g.no_gain;
+
+        // ---- prologue: stored half + first frame into the ring ----
+        if (lane == 0) bulk_store_wait_read();           // the previous item's spectrum has left the tile
+        async_proxy_fence();
+        __syncwarp();                                    // ... and nobody still reads the ring
+        if (lane == 0) {
+            mbar_expect_tx(&ws.bar, (f0 > 0 ? 8u : 4u) * 1024u);
 #pragma unroll
-        for (int band = 0; band < 4; band++)
-            if (s_cv[warp][band][1].n == 0 &&
-                (f == 0 ? b.next_scale[sc * 4 + band] == 1.0f : s_cv[warp][band][0].n == 0)) trivial |= 1u << band;
-        // ---- CalcGainEnergyScale's sequential sums (atrac3denc.cpp:189-216), bands that touch a curve only:
-        // squared terms sample-parallel into the tile, seven lanes then add them up in order.
-        //  0 prevStored  1 curOriginal  2 curModulated  3 nextOriginal  4 nextModulated
-        //  5/6 nextOriginal/nextModulated of the PREVIOUS frame (-> its NextOverlapScale)
-#pragma unroll 1
-        for (int band = 0; band < 4; band++) {
-            if ((trivial >> band) & 1u) continue;
-            const Curve& cc = s_cv[warp][band][1];
-            const Curve& pc = s_cv[warp][band][0];
-            const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
-            float* lv_c = tl + kMdctLevels;
-            float* lv_p = lv_c + 256;
+            for (int q = 0; q < 4; q++) {
+                if (f0 > 0) bulk_g2s(ring + q * kMdRingBand, brow + (size_t)q * g.BL + 256 * (size_t)(f0 - 1), 1024, &ws.bar);
+                bulk_g2s(ring + q * kMdRingBand + 256, brow + (size_t)q * g.BL + 256 * (size_t)f0, 1024, &ws.bar);
+            }
+        }
+        if (f0 == 0) {                                   // the carried half is windowed + modulated already
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    *reinterpret_cast<float4*>(ring + q * kMdRingBand + 4 * (lane + 32 * h)) =
+                        *reinterpret_cast<const float4*>(b.prevhalf + (sc * 4 + q) * 256 + 4 * (lane + 32 * h));
+        }
+        // gain curves: lane q < 3 carries band q's curve of the frame in work and of the one before
+        Curve cc, pc;
+        cc.n = 0; pc.n = 0;
+        if (gain && lane < kGainBands) {
+            const Curve* cp = b.curves + (sc * 4 + lane) * g.n_out;
+            cc = cp[f0];
+            if (f0 > 0) pc = cp[f0 - 1];
+        }
+        float pos_scale = 1.0f;                          // lane q < 4: PrevOverlapGainScale[channel][q]
+        if (f0 == 0 && lane < 4) pos_scale = b.next_scale[sc * 4 + lane];
+        mbar_wait(&ws.bar, phase);
+        phase ^= 1u;
+        if (f0 > 0) {
+            // the stored half of a run that starts inside the stream: the previous frame's samples, modulated by ITS
+            // curve; its NextOverlapScale = SafeEnergyScale(sum (y w)^2, sum (ym w)^2) (atrac3denc.cpp:205-216)
+            if (lane < 4) ws.cv[lane][0] = pc;
             __syncwarp();
-            if (cc.n) curve_levels_warp(T, cc, lane, lv_c);
-            if (f != 0 && pc.n) curve_levels_warp(T, pc, lane, lv_p);
-            __syncwarp();
-            float a = 0.0f;                                    // lane < 7: running sum of term `lane`
 #pragma unroll 1
-            for (int half = 0; half < 256; half += 128) {
-#pragma unroll 1
-                for (int j = lane; j < 128; j += 32) {
-                    const int i = half + j;
-                    const float x = bp[i];
-                    const float xm = cc.n ? __fdiv_rn(x, lv_c[i]) : x;
-                    const float wi = s_win[i], wr = s_win[255 - i];
-                    float prev, y = 0.0f, ym = 0.0f;
-                    if (f == 0) {
-                        prev = b.prevhalf[(sc * 4 + band) * 256 + i];
-                    } else {
-                        y = bp[i - 256];
-                        ym = pc.n ? __fdiv_rn(y, lv_p[i]) : y;
-                        prev = fmul(wi, ym);
-                    }
-                    float v;
-                    tl[0 * kMdctTermStride + j] = fmul(prev, prev);
-                    v = fmul(x, wr);  tl[1 * kMdctTermStride + j] = fmul(v, v);
-                    v = fmul(xm, wr); tl[2 * kMdctTermStride + j] = fmul(v, v);
-                    v = fmul(x, wi);  tl[3 * kMdctTermStride + j] = fmul(v, v);
-                    v = fmul(xm, wi); tl[4 * kMdctTermStride + j] = fmul(v, v);
-                    v = fmul(y, wi);  tl[5 * kMdctTermStride + j] = fmul(v, v);
-                    v = fmul(ym, wi); tl[6 * kMdctTermStride + j] = fmul(v, v);
-                }
+            for (int q = 0; q < kGainBands; q++) {
+                const Curve& pcv = ws.cv[q][0];
+                if (pcv.n == 0) continue;
+                float* P = ring + q * kMdRingBand;
+                float* lv = tile + 2 * kMdTermStride;
                 __syncwarp();
-                if (lane < 7) {
+                curve_levels_warp(T, pcv, lane, lv);
+                __syncwarp();
+                float a = 0.0f;
+#pragma unroll 1
+                for (int half = 0; half < 256; half += 128) {
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const int j = lane + 32 * t, i = half + j;
+                        const float y = P[i];
+                        const float ym = __fdiv_rn(y, lv[i]);
+                        const float wi = sh.win[i];
+                        float v;
+                        v = fmul(y, wi);  tile[0 * kMdTermStride + j] = fmul(v, v);
+                        v = fmul(ym, wi); tile[1 * kMdTermStride + j] = fmul(v, v);
+                        P[i] = ym;
+                    }
+                    __syncwarp();
+                    if (lane < 2) {
 #pragma unroll 4
-                    for (int j = 0; j < 128; j += 4) {
-                        const float4 q = *reinterpret_cast<const float4*>(&tl[lane * kMdctTermStride + j]);
-                        a = fadd(a, q.x); a = fadd(a, q.y); a = fadd(a, q.z); a = fadd(a, q.w);
+                        for (int j = 0; j < 128; j += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(&tile[lane * kMdTermStride + j]);
+                            a = fadd(a, t4.x); a = fadd(a, t4.y); a = fadd(a, t4.z); a = fadd(a, t4.w);
+                        }
+                    }
+                    __syncwarp();
+                }
+                const float e_org = __shfl_sync(0xffffffffu, a, 0);
+                const float e_mod = __shfl_sync(0xffffffffu, a, 1);
+                if (lane == q) {
+                    float ps = safe_energy_scale(e_org, e_mod);
+                    const float inf = __int_as_float(0x7f800000);
+                    if (!(fabsf(ps) < inf) || ps <= 0.0f) ps = 1.0f;
+                    pos_scale = ps;
+                }
+            }
+        }
+
+        int par = 0;                                     // ring slot of the stored half
+#pragma unroll 1
+        for (int f = f0; f < f1; f++) {
+            const size_t unit = ((size_t)s * g.n_out + f) * g.C + c;
+            if (f != f0) {
+                mbar_wait(&ws.bar, phase);               // frame f's samples have landed
+                phase ^= 1u;
+            }
+            Curve nc;                                    // next frame's curve, fetched early
+            nc.n = 0;
+            if (gain && lane < kGainBands && f + 1 < f1) nc = b.curves[(sc * 4 + lane) * g.n_out + f + 1];
+            if (lane == 0) bulk_store_wait_read();       // the previous frame's spectrum has left the tile
+            if (lane < 4) {
+                ws.cv[lane][1] = cc;
+                ws.esum[lane][6] = pos_scale;
+                ws.esum[lane][5] = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
+            }
+            __syncwarp();
+            // A band whose own curve is empty and whose overlap scale is 1 has every energy scale exactly 1.0
+            // (SafeEnergyScale(x, x)); the sequential energy sums only run for bands that touch a curve.
+            unsigned trivial = 0, curved = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (ws.cv[q][1].n) curved |= 1u << q;
+                else if (ws.esum[q][6] == 1.0f) trivial |= 1u << q;
+            }
+            const float* wprev = (f == 0) ? sh.ones : sh.win;      // window of the stored half (applied already at f == 0)
+            // ---- CalcGainEnergyScale's sequential sums, bands that touch a curve only:
+            //  0 prevStored  1 curOriginal  2 curModulated  3 nextOriginal  4 nextModulated
+#pragma unroll 1
+            for (int q = 0; q < 4; q++) {
+                if ((trivial >> q) & 1u) continue;
+                const bool has = (curved >> q) & 1u;
+                const float* P = ring + q * kMdRingBand + 256 * par;
+                float* X = ring + q * kMdRingBand + 256 * (par ^ 1);
+                float* lv = tile + 5 * kMdTermStride;
+                __syncwarp();
+                if (has) curve_levels_warp(T, ws.cv[q][1], lane, lv);
+                __syncwarp();
+                float a = 0.0f;                                    // lane < 5: running sum of term `lane`
+#pragma unroll 1
+                for (int half = 0; half < 256; half += 128) {
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const int j = lane + 32 * t, i = half + j;
+                        const float x = X[i];
+                        const float xm = has ? __fdiv_rn(x, lv[i]) : x;
+                        const float wi = sh.win[i], wr = sh.win[255 - i];
+                        const float prev = fmul(wprev[i], P[i]);
+                        float v;
+                        tile[0 * kMdTermStride + j] = fmul(prev, prev);
+                        v = fmul(x, wr);  tile[1 * kMdTermStride + j] = fmul(v, v);
+                        v = fmul(xm, wr); tile[2 * kMdTermStride + j] = fmul(v, v);
+                        v = fmul(x, wi);  tile[3 * kMdTermStride + j] = fmul(v, v);
+                        v = fmul(xm, wi); tile[4 * kMdTermStride + j] = fmul(v, v);
+                        if (has) X[i] = xm;                        // gain modulation (gain_processor.h:87-121), in place
+                    }
+                    __syncwarp();
+                    if (lane < 5) {
+#pragma unroll 4
+                        for (int j = 0; j < 128; j += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(&tile[lane * kMdTermStride + j]);
+                            a = fadd(a, t4.x); a = fadd(a, t4.y); a = fadd(a, t4.z); a = fadd(a, t4.w);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (lane < 5) ws.esum[q][lane] = a;
+            }
+            __syncwarp();
+            if (lane < 4) {
+                const int q = lane;
+                const bool cur_empty = cc.n == 0;
+                float sc0 = 1.0f, sc1 = 1.0f, sc2 = 1.0f, sc3 = 1.0f;
+                if (!((trivial >> q) & 1u)) {
+                    const float* es = ws.esum[q];
+                    const float prev_div = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
+                    const float prev_stored = es[0];
+                    const float prev_orig = fmul(prev_stored, pos_scale);
+                    const float prev_mod = __fdiv_rn(prev_stored, fmul(prev_div, prev_div));
+                    const float cur_orig = es[1], cur_mod = cur_empty ? es[1] : es[2];
+                    const float nxt_orig = es[3], nxt_mod = cur_empty ? es[3] : es[4];
+                    sc0 = safe_energy_scale(prev_orig, prev_mod);
+                    sc1 = safe_energy_scale(cur_orig, cur_mod);
+                    sc2 = safe_energy_scale(fadd(prev_orig, cur_orig), fadd(prev_mod, cur_mod));
+                    sc3 = safe_energy_scale(nxt_orig, nxt_mod);
+                }
+                *reinterpret_cast<float4*>(&b.gscale[unit * 16 + q * 4]) = make_float4(sc0, sc1, sc2, sc3);
+                if (f == g.n_out - 1) b.next_scale_out[sc * 4 + q] = sc3;
+                // PrevOverlapGainScale for the next frame (atrac3denc.cpp:781-786)
+                float ps = sc3;
+                const float inf = __int_as_float(0x7f800000);
+                if (!(fabsf(ps) < inf) || ps <= 0.0f) ps = 1.0f;
+                pos_scale = ps;
+            }
+            if (f == g.n_out - 1) {                                // the half this frame leaves behind (next batch)
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int i0 = 4 * (lane + 32 * h);
+                        const float4 x4 = *reinterpret_cast<const float4*>(ring + q * kMdRingBand + 256 * (par ^ 1) + i0);
+                        const float4 w4 = *reinterpret_cast<const float4*>(&sh.win[i0]);
+                        *reinterpret_cast<float4*>(b.prevhalf_out + (sc * 4 + q) * 256 + i0) =
+                            make_float4(fmul(w4.x, x4.x), fmul(w4.y, x4.y), fmul(w4.z, x4.z), fmul(w4.w, x4.w));
+                    }
+            }
+            __syncwarp();                                          // ring modulated, tile free, esum[.][5] visible
+            const float* wfold = wprev;
+            if (curved) {
+                // some band has a curve: its stored half is divided by the curve's first level (atrac3denc.cpp:46-47).
+                // Done here, on the windowed values and in place (the slot is dead after this frame), so that the fold
+                // below carries no division; bands without a curve divide by 1.0f, which changes nothing.
+#pragma unroll 1
+                for (int q = 0; q < 4; q++) {
+                    float* P = ring + q * kMdRingBand + 256 * par;
+                    const float d0 = ws.esum[q][5];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int i0 = 4 * (lane + 32 * h);
+                        const float4 p4 = *reinterpret_cast<const float4*>(P + i0);
+                        const float4 w4 = *reinterpret_cast<const float4*>(wprev + i0);
+                        *reinterpret_cast<float4*>(P + i0) =
+                            make_float4(__fdiv_rn(fmul(w4.x, p4.x), d0), __fdiv_rn(fmul(w4.y, p4.y), d0),
+                                        __fdiv_rn(fmul(w4.z, p4.z), d0), __fdiv_rn(fmul(w4.w, p4.w), d0));
                     }
                 }
+                wfold = sh.ones;
                 __syncwarp();
             }
-            if (lane < 7) s_esum[warp][band][lane] = a;
-            __syncwarp();
-        }
-        if (lane < 4) {
-            const int band = lane;
-            const Curve& cc = s_cv[warp][band][1];
-            const bool cur_empty = cc.n == 0, prev_empty = s_cv[warp][band][0].n == 0;
-            float sc0 = 1.0f, sc1 = 1.0f, sc2 = 1.0f, sc3 = 1.0f;
-            if (!((trivial >> band) & 1u)) {
-                const float* es = s_esum[warp][band];
-                float pos_scale;                                       // PrevOverlapGainScale[channel][band]
-                if (f == 0) pos_scale = b.next_scale[sc * 4 + band];
-                else if (prev_empty) pos_scale = 1.0f;                 // SafeEnergyScale(e, e)
-                else pos_scale = safe_energy_scale(es[5], es[6]);
-                const float inf = __int_as_float(0x7f800000);
-                if (!(fabsf(pos_scale) < inf) || pos_scale <= 0.0f) pos_scale = 1.0f;
-                const float prev_div = cc.n ? T->gain_level[cc.level[0]] : 1.0f;
-                const float prev_stored = es[0];
-                const float prev_orig = fmul(prev_stored, pos_scale);
-                const float prev_mod = __fdiv_rn(prev_stored, fmul(prev_div, prev_div));
-                const float cur_orig = es[1], cur_mod = cur_empty ? es[1] : es[2];
-                const float nxt_orig = es[3], nxt_mod = cur_empty ? es[3] : es[4];
-                sc0 = safe_energy_scale(prev_orig, prev_mod);
-                sc1 = safe_energy_scale(cur_orig, cur_mod);
-                sc2 = safe_energy_scale(fadd(prev_orig, cur_orig), fadd(prev_mod, cur_mod));
-                sc3 = safe_energy_scale(nxt_orig, nxt_mod);
-            }
-            *reinterpret_cast<float4*>(&b.gscale[(size_t)unit * 16 + band * 4]) = make_float4(sc0, sc1, sc2, sc3);
-            if (f == g.n_out - 1) b.next_scale_out[sc * 4 + band] = sc3;
-        }
-        float* const outp = b.specs + (size_t)unit * 1024;
+
+            // ---- fold + pre-twiddle + the two innermost FFT stages: lane (bnd, L) owns gather blocks 2L, 2L + 1 ----
+            cpx e[4][4];                                           // after the exchange: element L + 8a + 32b
+            {
+                const float* P = ring + bnd * kMdRingBand + 256 * par;
+                const float* X = ring + bnd * kMdRingBand + 256 * (par ^ 1);
+                cpx* xch = reinterpret_cast<cpx*>(tile) + bnd * kMdXchBand;
 #pragma unroll 1
-        for (int bp2 = 0; bp2 < 2; bp2++) {                 // bands 2*bp2, 2*bp2 + 1
-        __syncwarp();                                       // the tile is free (rare path / previous iteration)
-        // ---- phase A: MDCT input (atrac3denc.cpp:39-49): in[j] = stored half / scale, in[256+j] = win[255-j] * modulated cur
-#pragma unroll 1
-        for (int bb = 0; bb < 2; bb++) {
-            const int band = 2 * bp2 + bb;
-            // BL = 128 + 256 L: every band row and every frame inside it starts 16-byte aligned
-            const float* bp = b.bands + (sc * 4 + band) * g.BL + 128 + 256 * (size_t)f;
-            const Curve& cc = s_cv[warp][band][1];
-            const Curve& pc = s_cv[warp][band][0];
-            float* in = tl + bb * kMdctBandStride;
-            float* lv_c = tl + kMdctLevels;
-            float* lv_p = lv_c + 256;
-            if (cc.n | pc.n) {                                        // divisor tables of this band (rare)
-                __syncwarp();
-                if (cc.n) curve_levels_warp(T, cc, lane, lv_c);
-                if (f != 0 && pc.n) curve_levels_warp(T, pc, lane, lv_p);
-                __syncwarp();
+                for (int h = 0; h < 2; h++) {                      // (rolled: the kernel is instruction-fetch sensitive)
+                    const int blk = 2 * L + h;
+                    // slot = 8 blk + j of the 4x4x4x2 digit reversal: i = d0 + 4 d1 + 16 d2 + 64 d3
+                    const int ibase = (blk >> 2) + 4 * (blk & 3);
+                    cpx v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int n = 2 * (ibase + 16 * (j >> 1) + 64 * (j & 1));   // N = 512, n4 = 128, n34 = 384, n54 = 640
+                        float r0, i0;
+                        if ((j & 1) == 0) {                        // n < 128: r0 = in[383-n] + in[384+n], i0 = in[128+n] - in[127-n]
+                            const float wa = sh.win[128 + n], wb = sh.win[127 - n];
+                            const float p1 = fmul(wfold[128 + n], P[128 + n]), p2 = fmul(wfold[127 - n], P[127 - n]);
+                            r0 = fadd(fmul(wa, X[127 - n]), fmul(wb, X[128 + n]));
+                            i0 = fsub(p1, p2);
+                        } else {                                   // r0 = in[383-n] - in[n-128], i0 = in[128+n] + in[639-n]
+                            const float wa = sh.win[383 - n], wb = sh.win[n - 128];
+                            const float p1 = fmul(wfold[383 - n], P[383 - n]), p2 = fmul(wfold[n - 128], P[n - 128]);
+                            r0 = fsub(p1, p2);
+                            i0 = fadd(fmul(wa, X[n - 128]), fmul(wb, X[383 - n]));
+                        }
+                        const float2 cs = *reinterpret_cast<const float2*>(&sh.sincos[n]);
+                        v[j].r = fadd(fmul(r0, cs.x), fmul(i0, cs.y));
+                        v[j].i = fsub(fmul(i0, cs.x), fmul(r0, cs.y));
+                    }
+                    // radix-2, m = 1 (fstride 64): pairs (2q, 2q+1), twiddle tw[0]
+#pragma unroll
+                    for (int q = 0; q < 4; q++) kf_bfly2(v[2 * q], v[2 * q + 1], sh.tw[0]);
+                    // radix-4, m = 2 (fstride 16): elements kk + 2q, twiddles tw[16 kk q]
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++)
+                        kf_bfly4<false>(v[kk], v[kk + 2], v[kk + 4], v[kk + 6], sh.tw[16 * kk], sh.tw[32 * kk], sh.tw[48 * kk]);
+                    // element 8 blk + j at padded index 17 L + 8 h + j (one pad per 16 elements)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) xch[17 * L + 8 * h + j] = v[j];
+                }
+                async_proxy_fence();
+                __syncwarp();                                      // every lane is done with the ring's stored-half slots
+                if (lane == 0 && f + 1 < f1) {                     // fetch frame f+1 into them while this one is transformed
+                    mbar_expect_tx(&ws.bar, 4096u);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        bulk_g2s(ring + q * kMdRingBand + 256 * par, brow + (size_t)q * g.BL + 256 * (size_t)(f + 1), 1024, &ws.bar);
+                }
+                // element L + 8a + 32b at padded index L + 8a + (a >> 1) + 34 b
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) e[a][q] = xch[L + 8 * a + (a >> 1) + 34 * q];
+            }
+            // ---- radix-4 m = 8 (fstride 4) over a, radix-4 m = 32 (fstride 1) over b ----
+            {
+                const cpx t1 = sh.tw[4 * L], t2 = sh.tw[8 * L], t3 = sh.tw[12 * L];
+#pragma unroll
+                for (int q = 0; q < 4; q++) kf_bfly4<false>(e[0][q], e[1][q], e[2][q], e[3][q], t1, t2, t3);
             }
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int i0 = 4 * (lane + 32 * h);
-                float x[4], y[4], pv[4], cu[4];
-                {
-                    const float4 q = *reinterpret_cast<const float4*>(bp + i0);
-                    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-                }
-                if (f == 0) {
-                    const float4 q = *reinterpret_cast<const float4*>(b.prevhalf + (sc * 4 + band) * 256 + i0);
-                    pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
-                } else {
-                    const float4 q = *reinterpret_cast<const float4*>(bp + i0 - 256);
-                    y[0] = q.x; y[1] = q.y; y[2] = q.z; y[3] = q.w;
-                }
-                if (cc.n) {                                           // gain modulation (gain_processor.h:87-121)
-                    const float4 d = *reinterpret_cast<const float4*>(lv_c + i0);
-                    x[0] = __fdiv_rn(x[0], d.x); x[1] = __fdiv_rn(x[1], d.y); x[2] = __fdiv_rn(x[2], d.z); x[3] = __fdiv_rn(x[3], d.w);
-                }
-                if (f != 0 && pc.n) {
-                    const float4 d = *reinterpret_cast<const float4*>(lv_p + i0);
-                    y[0] = __fdiv_rn(y[0], d.x); y[1] = __fdiv_rn(y[1], d.y); y[2] = __fdiv_rn(y[2], d.z); y[3] = __fdiv_rn(y[3], d.w);
-                }
-                const float4 wf = *reinterpret_cast<const float4*>(&s_win[i0]);          // win[i0 .. i0+3]
-                const float4 wb = *reinterpret_cast<const float4*>(&s_win[252 - i0]);    // win[255-i0-3 .. 255-i0]
-                const float wi[4] = {wf.x, wf.y, wf.z, wf.w}, wr[4] = {wb.w, wb.z, wb.y, wb.x};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    if (f != 0) pv[e] = fmul(wi[e], y[e]);
-                    cu[e] = fmul(wr[e], x[e]);
-                }
-                if (cc.n) {
-                    const float d0 = T->gain_level[cc.level[0]];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) pv[e] = __fdiv_rn(pv[e], d0);
-                }
-                if (f == g.n_out - 1) {                               // the half this frame leaves behind (next batch)
-                    *reinterpret_cast<float4*>(b.prevhalf_out + (sc * 4 + band) * 256 + i0) =
-                        make_float4(fmul(wi[0], x[0]), fmul(wi[1], x[1]), fmul(wi[2], x[2]), fmul(wi[3], x[3]));
-                }
-                *reinterpret_cast<float4*>(in + i0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                *reinterpret_cast<float4*>(in + 256 + i0) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+            for (int a = 0; a < 4; a++) {
+                const int v = L + 8 * a;
+                kf_bfly4<false>(e[a][0], e[a][1], e[a][2], e[a][3], sh.tw[v], sh.tw[2 * v], sh.tw[3 * v]);
             }
-        }
-        __syncwarp();
-        // ---- phase B: fold + pre-twiddle + the two innermost FFT stages on gather block k16
-        const int bsel = lane >> 4, k16 = lane & 15, k = lane & 7, hp = (lane >> 3) & 1;
-        cpx e[4][2];                                       // after the exchange: element k + 8a + 32(2 hp + bb)
-        {
-            const float* in = tl + bsel * kMdctBandStride;
-            cpx v[8];
-            // slot = 8 k16 + j of the 4x4x4x2 digit reversal: i = d0 + 4 d1 + 16 d2 + 64 d3
-            const int ibase = (k16 >> 2) + 4 * (k16 & 3);
+            __syncwarp();                                          // exchange reads done: the tile becomes the output stage
+            // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55)
+            {
+                float* sp = tile + bnd * kMdOutBand;
+                const bool odd = bnd & 1;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int n = 2 * (ibase + 16 * (j >> 1) + 64 * (j & 1));   // N = 512, n4 = 128, n34 = 384, n54 = 640
-                float r0, i0;
-                if ((j & 1) == 0) { r0 = fadd(in[383 - n], in[384 + n]); i0 = fsub(in[128 + n], in[127 - n]); }   // n < 128
-                else              { r0 = fsub(in[383 - n], in[n - 128]); i0 = fadd(in[128 + n], in[639 - n]); }
-                const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
-                v[j].r = fadd(fmul(r0, cs.x), fmul(i0, cs.y));
-                v[j].i = fsub(fmul(i0, cs.x), fmul(r0, cs.y));
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int n = 2 * (L + 8 * a + 32 * q);
+                        const cpx z = e[a][q];
+                        const float2 cs = *reinterpret_cast<const float2*>(&sh.sincos[n]);
+                        const float va = fsub(fmul(-z.r, cs.x), fmul(z.i, cs.y));
+                        const float vb = fadd(fmul(-z.r, cs.y), fmul(z.i, cs.x));
+                        sp[odd ? 255 - n : n] = va;
+                        sp[odd ? n : 255 - n] = vb;
+                    }
             }
-            // radix-2, m = 1 (fstride 64): pairs (2q, 2q+1), twiddle tw[0]
-#pragma unroll
-            for (int q = 0; q < 4; q++) kf_bfly2(v[2 * q], v[2 * q + 1], s_tw[0]);
-            // radix-4, m = 2 (fstride 16): elements kk + 2q, twiddles tw[16 kk q]
-#pragma unroll
-            for (int kk = 0; kk < 2; kk++)
-                kf_bfly4<false>(v[kk], v[kk + 2], v[kk + 4], v[kk + 6], s_tw[16 * kk], s_tw[32 * kk], s_tw[48 * kk]);
-            __syncwarp();                                  // every lane has read its MDCT input
-            cpx* xch = reinterpret_cast<cpx*>(tl) + bsel * kMdctXchStride;
-#pragma unroll
-            for (int j = 0; j < 8; j++) xch[k16 * 9 + j] = v[j];
+            async_proxy_fence();                                   // generic-proxy stores -> visible to the copy engine
             __syncwarp();
+            if (lane == 0) {
+                float* outp = b.specs + unit * 1024;
 #pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int bb = 0; bb < 2; bb++) e[a][bb] = xch[(a + 4 * (2 * hp + bb)) * 9 + k];
-        }
-        // ---- phase C: radix-4 m = 8 (fstride 4) over a
-        {
-            const cpx t1 = s_tw[4 * k], t2 = s_tw[8 * k], t3 = s_tw[12 * k];
-#pragma unroll
-            for (int bb = 0; bb < 2; bb++) kf_bfly4<false>(e[0][bb], e[1][bb], e[2][bb], e[3][bb], t1, t2, t3);
-        }
-        // lane pair swap: lane hp keeps a = 2hp + aa and receives the partner's b range for those a
-        cpx gq[2][4];                                      // element k + 8 (2 hp + aa) + 32 b
-#pragma unroll
-        for (int aa = 0; aa < 2; aa++)
-#pragma unroll
-            for (int bb = 0; bb < 2; bb++) {
-                const cpx keep = hp ? e[2 + aa][bb] : e[aa][bb];
-                const cpx send = hp ? e[aa][bb] : e[2 + aa][bb];
-                cpx recv;
-                recv.r = __shfl_xor_sync(0xffffffffu, send.r, 8);
-                recv.i = __shfl_xor_sync(0xffffffffu, send.i, 8);
-                gq[aa][bb] = hp ? recv : keep;
-                gq[aa][2 + bb] = hp ? keep : recv;
+                for (int q = 0; q < 4; q++) bulk_s2g(outp + 256 * q, tile + q * kMdOutBand, 1024);
+                bulk_store_commit();
             }
-        // radix-4 m = 32 (fstride 1) over b
-#pragma unroll
-        for (int aa = 0; aa < 2; aa++) {
-            const int v = k + 8 * (2 * hp + aa);
-            kf_bfly4<false>(gq[aa][0], gq[aa][1], gq[aa][2], gq[aa][3], s_tw[v], s_tw[2 * v], s_tw[3 * v]);
-        }
-        __syncwarp();                                      // exchange reads done: the tile becomes the output stage
-        // post-twiddle (mdct.h:92-101); odd bands reversed (atrac3denc.cpp:53-55)
-        {
-            float* sp = tl + bsel * kMdctOutStride;
-#pragma unroll
-            for (int aa = 0; aa < 2; aa++)
-#pragma unroll
-                for (int bq = 0; bq < 4; bq++) {
-                    const int n = 2 * (k + 8 * (2 * hp + aa) + 32 * bq);
-                    const cpx z = gq[aa][bq];
-                    const float2 cs = *reinterpret_cast<const float2*>(&s_sincos[n]);
-                    const float va = fsub(fmul(-z.r, cs.x), fmul(z.i, cs.y));
-                    const float vb = fadd(fmul(-z.r, cs.y), fmul(z.i, cs.x));
-                    int pa = n, pb = 255 - n;
-                    if (bsel) { pa = 255 - pa; pb = 255 - pb; }       // band 2*bp2 + bsel is odd iff bsel
-                    sp[pa] = va;
-                    sp[pb] = vb;
-                }
-        }
-        __syncwarp();
-        float4* out = reinterpret_cast<float4*>(outp + 512 * bp2);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int w = lane + 32 * q;                   // float4 index 0..127; band within the pair = w >> 6
-            out[w] = *reinterpret_cast<const float4*>(tl + (w >> 6) * kMdctOutStride + 4 * (w & 63));
-        }
+            par ^= 1;
+            pc = cc;
+            cc = nc;
         }
     }
+    if (lane == 0) bulk_store_wait_all();                          // the last spectrum is in global memory before the block retires
 }
 
 void launch_mdct(const Geometry& g, const Buffers& b, cudaStream_t st)
 {
-    const long long n_units = (long long)g.S * g.n_out * g.C;
-    long long blocks = (n_units + kMdctWarps - 1) / kMdctWarps;
-    if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;       // a few waves of resident blocks, warps stride over units
-    ATDE_LAUNCH(at3_mdct_kernel, (unsigned)blocks, kMdctWarps * 32, 0, st, g, b);
+    const int runs = (g.n_out + kMdRun - 1) / kMdRun;
+    const long long n_items = (long long)g.S * g.C * runs;
+    long long blocks = (n_items + kMdWarps - 1) / kMdWarps;
+    if (blocks > 148 * 4) blocks = 148 * 4;               // persistent: every block resident (4 per SM), warps stride over items
+    cudaFuncSetAttribute(at3_mdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MdBlockShared));
+    ATDE_LAUNCH(at3_mdct_kernel, (unsigned)blocks, kMdWarps * 32, sizeof(MdBlockShared), st, g, b);
 }
 
 // =====================================================================================

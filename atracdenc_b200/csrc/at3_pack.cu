@@ -415,6 +415,15 @@ ATDE_D int elem_bfu(int i)
     if (i < 768) return 26 + ((i - 512) >> 6);
     return 30 + ((i - 768) >> 7);
 }
+// BFU of line 32 r + lane: the row index is warp-uniform, so the branches are too
+ATDE_D int row_bfu(int r, int lane)
+{
+    if (r < 2) return 4 * r + (lane >> 3);
+    if (r < 6) return 4 + 2 * r + (lane >> 4);
+    if (r < 16) return 10 + r;
+    if (r < 24) return 26 + ((r - 16) >> 1);
+    return 30 + ((r - 24) >> 2);
+}
 ATDE_D unsigned row_bfu_mask(int r)
 {
     if (r < 2) return 0xFu << (4 * r);
@@ -469,20 +478,19 @@ ATDE_NOINLINE int put_seq(unsigned* words, int cap_bits, int pos, unsigned v, in
 
 constexpr int kWordsPerCh = kMaxUnitBytes / 4 + 8;             // bitstream of one channel
 
-constexpr int kEaFirst = 288;                                  // first line of BFU 19 (BFUs > 18 re-round)
 struct __align__(16) PackShared {
     float sv[1024];                    // scaled spectrum of the channel
     float pq[1024];                    // per line: q*q/mul^2 of the unit being quantised (energy chain input);
-                                       //   afterwards, per BFU region: |delta| of the re-rounding candidates
+                                       //   afterwards, per BFU region: |delta| of the re-rounding candidates;
+                                       //   once the allocation is final: the channel's bitstream words (kWordsPerCh)
     unsigned char hb[1024];            // per line: VLC bits (pairs: on the even line); afterwards: candidate line offsets
     signed char mant[1024];            // mantissas of the unit quantised last, per BFU region
     unsigned char wl_now[32];          // word length being quantised per BFU (0 = not requested)
     unsigned char walk_dir[32];        // 0 none, 1 e2 < e1 (round up), 2 e2 > e1 (round down)
     float walk_thr[32];                // acceptance pre-filter per BFU
     int walk_cnt[32];                  // candidates collected per BFU
-    unsigned words[kWordsPerCh];
-    unsigned cache_cv[8][32];          // clc | vlc << 16, indexed [wordlen][bfu]
-    float cache_err[8][32];
+    unsigned short cache_vlc[8][32];   // VLC bits of the unit, indexed [wordlen][bfu] (the CLC bits are len * kClcLen[wordlen])
+    float cache_err[8][10];            // energy ratio e1 / e2; only BFUs < 10 (BOOST_NAQ_END) ever look at it
     unsigned short ton_pos[kMaxTonal];
     unsigned char ton_bfu[kMaxTonal], ton_len[kMaxTonal], ton_sfi[kMaxTonal];
     unsigned char ton_vlc[kMaxTonal][8];   // VLC bits of the block's mantissas at quantiser 2..7
@@ -511,16 +519,23 @@ struct __align__(16) PackShared {
 //   * with distinct |delta| among the visited candidates this is the reference's order exactly; if two
 //     of them tie, the library's sort order matters and quant_unit_exact redoes the block.
 // Returns (for need lanes) clc | vlc << 16 and the energy ratio e1/e2.
+#ifdef ATDE_PACK_STATS
+long long g_stats[64];
+struct StatsPrinter { ~StatsPrinter() { fprintf(stderr, "compute_units calls %lld, units %lld, walkers %lld, frames*ch %lld, bisect iters %lld\n", g_stats[0], g_stats[1], g_stats[2], g_stats[3], g_stats[4]); for (int q = 0; q < 32; q++) fprintf(stderr, "%lld ", g_stats[8 + q]); fprintf(stderr, "\n"); } } g_stats_printer;
+#endif
 ATDE_NOINLINE unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int start, int len, float e1, float& err_out)
 {
     const unsigned nm = __ballot_sync(0xffffffffu, need);
+#ifdef ATDE_PACK_STATS
+    if (lane == 0) { g_stats[0]++; g_stats[1] += __popc(nm); g_stats[2] += __popc(nm >> 19); for (int q = 0; q < 32; q++) if ((nm >> q) & 1u) g_stats[8 + q]++; }
+#endif
     sh.wl_now[lane] = need ? (unsigned char)wl : 0;
     __syncwarp();
     // ---- E ----
     for (unsigned rows = rows_of_bfus(nm); rows; rows &= rows - 1) {
         const int r = __ffs((int)rows) - 1;
         const int i = 32 * r + lane;
-        const int w = sh.wl_now[elem_bfu(i)];
+        const int w = sh.wl_now[row_bfu(r, lane)];
         const float mul = kMaxQuant[w];
         const float x = sh.sv[i];
         const int q = __float2int_rn(fmul(x, mul));
@@ -566,7 +581,7 @@ ATDE_NOINLINE unsigned compute_units(PackShared& sh, int lane, bool need, int wl
         for (unsigned rows = rows_of_bfus(wm); rows; rows &= rows - 1) {
             const int r = __ffs((int)rows) - 1;
             const int i = 32 * r + lane;
-            const int bf = elem_bfu(i);
+            const int bf = row_bfu(r, lane);
             const int dir = sh.walk_dir[bf];
             if (dir) {
                 const int wq = sh.wl_now[bf];
@@ -588,30 +603,66 @@ ATDE_NOINLINE unsigned compute_units(PackShared& sh, int lane, bool need, int wl
             }
         }
         __syncwarp();
+        // ---- S ---- sort every walking BFU's candidate list by |delta| (rank by counting, the whole warp on one list at a
+        //      time: the walk below then visits candidates in order instead of searching the minimum again at every step).
+        //      Equal keys keep their list order; the walk falls back to the exact restatement before it would visit them.
+        for (unsigned bm = wm; bm; bm &= bm - 1) {
+            const int bf = __ffs((int)bm) - 1;
+            const int nc = sh.walk_cnt[bf];
+            if (nc < 2) continue;
+            const int b0 = kBlockStart[bf];
+            float* ck = sh.pq + b0;
+            unsigned char* ci = sh.hb + b0;
+            if (nc <= 32) {
+                const bool mine = lane < nc;
+                const float key = mine ? ck[lane] : 0.0f;
+                const unsigned char idx = mine ? ci[lane] : 0;
+                int rank = 0;
+                ATDE_ROLLED
+                for (int k = 0; k < nc; k++) {
+                    const float kk = ck[k];
+                    rank += (kk < key || (kk == key && k < lane)) ? 1 : 0;
+                }
+                __syncwarp();
+                if (mine) { ck[rank] = key; ci[rank] = idx; }
+            } else {                                               // up to 128 candidates: four slots per lane
+                float key[4];
+                unsigned char idx[4];
+                int rank[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) {
+                    const int sl = lane + 32 * rr;
+                    key[rr] = sl < nc ? ck[sl] : 0.0f;
+                    idx[rr] = sl < nc ? ci[sl] : 0;
+                    rank[rr] = 0;
+                }
+                ATDE_ROLLED
+                for (int k = 0; k < nc; k++) {
+                    const float kk = ck[k];
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++)
+                        rank[rr] += (kk < key[rr] || (kk == key[rr] && k < lane + 32 * rr)) ? 1 : 0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++)
+                    if (lane + 32 * rr < nc) { ck[rank[rr]] = key[rr]; ci[rank[rr]] = idx[rr]; }
+            }
+        }
+        __syncwarp();
         // ---- W ----
         if (walk) {
             const int nc = sh.walk_cnt[lane];
             const float* ckey = sh.pq + start;
             const unsigned char* cidx = sh.hb + start;
             signed char* m = sh.mant + start;
-            float last = -1.0f;
-            while (up ? (e2 < e1) : (e2 > e1)) {
-                float best = 2.0f;
-                int bi = -1, ties = 0;
-#pragma unroll 2
-                for (int k = 0; k < nc; k++) {
-                    const float key = ckey[k];
-                    if (key > last) {
-                        if (key < best) { best = key; bi = k; ties = 0; }
-                        else if (key == best) ties++;
-                    }
-                }
-                if (bi < 0) break;
-                if (ties) {
-                    // two visited candidates share |delta|: the reference's order is libstdc++'s
+            int k = 0;
+            while ((up ? (e2 < e1) : (e2 > e1)) && k < nc) {
+                if (k + 1 < nc && ckey[k + 1] == ckey[k]) {
+                    // two candidates that would be visited share |delta|: the reference's order is libstdc++'s
                     const float er = quant_unit_exact(sh.sv + start, len, mulw, inv2w, m);
                     unsigned v = 0;
-                                        if (wl > 1) {
+                    if (wl > 1) {
                         ATDE_ROLLED
                         for (int j = 0; j < len; j++) v += vlc_bits_of(wl, m[j]);
                     } else {
@@ -623,8 +674,8 @@ ATDE_NOINLINE unsigned compute_units(PackShared& sh, int lane, bool need, int wl
                     used_exact = true;
                     break;
                 }
-                last = best;
-                const int j = cidx[bi];
+                const int j = cidx[k];
+                k++;
                 const int q = m[j];
                 int q2 = q;
                 if (up) {
@@ -701,7 +752,7 @@ ATDE_D unsigned tonal_bits(const PackShared& sh, int n_ton, int lane, unsigned p
 }
 
 #ifndef ATDE_PACK_MINBLOCKS
-#define ATDE_PACK_MINBLOCKS 1
+#define ATDE_PACK_MINBLOCKS 9          // 23.5 KB of shared memory per block: nine blocks (18 warps) per SM, <= 113 registers
 #endif
 __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel(Geometry g, Buffers b)
 {
@@ -720,7 +771,6 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     // ---- load; header + gain info size of both channels (WriteSoundUnit, :771-804) ----
     const float* gsp = b.specs + (size_t)unit * 1024;
     for (int i = lane; i < 1024; i += 32) sh.sv[i] = gsp[i];
-    for (int i = lane; i < kWordsPerCh; i += 32) sh.words[i] = 0;
     const TonalList* tl = b.tonal + unit;
     const int n_ton = g.no_tonal ? 0 : tl->n;
     if (lane < n_ton) {
@@ -840,11 +890,17 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     }
     num_bfu = max(1, num_bfu);
 
+#ifdef ATDE_PACK_STATS
+    if (lane == 0) g_stats[3]++;
+#endif
     unsigned prec = 0;
     unsigned mode = 1;
     for (;;) {                                                   // TConfigure: ba.Start(target, -8, 20)
         float mn = -8.0f, mx = 20.0f, last = 20.0f;
         for (;;) {                                               // TAlloc::Encode
+#ifdef ATDE_PACK_STATS
+            if (lane == 0) g_stats[4]++;
+#endif
             const bool exhausted = mx <= mn;
             const float shift = exhausted ? last : __double2float_rn(__ddiv_rn((double)fadd(mx, mn), 2.0));
             // CalcBitsAllocation (:272-336)
@@ -865,15 +921,15 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
                     float er;
                     const unsigned cv2 = compute_units(sh, lane, need, (int)prec, start, len, e1, er);
                     if (need) {
-                        sh.cache_cv[prec][lane] = cv2;
-                        sh.cache_err[prec][lane] = er;
+                        sh.cache_vlc[prec][lane] = (unsigned short)(cv2 >> 16);
+                        if (lane < 10) sh.cache_err[prec][lane] = er;
                         cached |= 1u << prec;
                         mant_wl = prec;
                     }
                 }
                 bool bump = false;
                 if (active) {
-                    cvb = sh.cache_cv[prec][lane];
+                    cvb = ((prec > 1u ? (unsigned)kClcLen[prec] : 2u) * (unsigned)len) | ((unsigned)sh.cache_vlc[prec][lane] << 16);
                     if (lane < 10) {                             // BOOST_NAQ_END
                         const float e = sh.cache_err[prec][lane];
                         bump = ((e > 0.0f && e < 0.7f) || e > 1.2f) && prec < 7u;
@@ -903,10 +959,24 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     sh.prec[lane] = (unsigned char)prec;
     __syncwarp();
 
-    // ---- write the channel's sound unit ----
+    // ---- mantissas of the final allocation (units whose last quantisation was at another word length are redone;
+    //      the procedure is deterministic, so they come out as they were costed) ----
+    const bool in_use = lane < num_bfu;
+    {
+        const bool redo = in_use && prec && mant_wl != prec;
+        if (__any_sync(0xffffffffu, redo)) {
+            float er;
+            compute_units(sh, lane, redo, (int)prec, start, len, e1, er);
+        }
+    }
+    // ---- write the channel's sound unit; the bitstream words take over the quantiser's scratch ----
+    unsigned* const words = reinterpret_cast<unsigned*>(sh.pq);
+    __syncwarp();
+    for (int i = lane; i < kWordsPerCh; i += 32) words[i] = 0;
+    __syncwarp();
     int pos = 0;
     if (lane == 0) {
-        unsigned* W = sh.words;
+        unsigned* W = words;
         auto put = [&](unsigned v, int n) { pos = put_seq(W, cap_bits, pos, v, n); };
         if (g.js && ch == 1) {
             put(0, 1); put(7, 3);
@@ -1007,59 +1077,51 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     }
     pos = __shfl_sync(0xffffffffu, pos, 0);
     // precisions, scale factor indices, mantissas (EncodeSpecs :541-564)
-    const bool in_use = lane < num_bfu;
-    if (in_use) put_bits3(sh.words, cap_bits, pos + 3 * lane, 3, prec);
+    if (in_use) put_bits3(words, cap_bits, pos + 3 * lane, 3, prec);
     pos += 3 * num_bfu;
     const unsigned nzmask = __ballot_sync(0xffffffffu, in_use && prec != 0);
-    if (in_use && prec) put_bits3(sh.words, cap_bits, pos + 6 * __popc(nzmask & ((1u << lane) - 1u)), 6, (unsigned)sfi);
+    if (in_use && prec) put_bits3(words, cap_bits, pos + 6 * __popc(nzmask & ((1u << lane) - 1u)), 6, (unsigned)sfi);
     pos += 6 * __popc(nzmask);
-    unsigned mybits = 0;
-    if (in_use && prec) {
-        const unsigned cvb = sh.cache_cv[prec][lane];
-        mybits = mode ? (cvb & 0xffffu) : (cvb >> 16);
-    }
-    unsigned inc = mybits;
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned a = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += a;
-    }
+    // Mantissas, line-parallel: BFUs follow each other in line order and unused ones contribute no bits, so the bit
+    // position of a line is the running sum of the code lengths of all lines before it (a warp scan per 32-line row).
+    sh.wl_now[lane] = (in_use ? (unsigned char)prec : 0);
+    __syncwarp();
     {
-        const bool redo = in_use && prec && mant_wl != prec;
-        if (__any_sync(0xffffffffu, redo)) {
-            float er;
-            compute_units(sh, lane, redo, (int)prec, start, len, e1, er);
-        }
-    }
-    if (in_use && prec) {
-        const signed char* m = sh.mant + start;
-        int p = pos + (int)(inc - mybits);
-        if (mode) {
-            if (prec > 1u) {
-                const int nb = kClcLen[prec];
-                ATDE_ROLLED
-                for (int j = 0; j < len; j++) { put_bits3(sh.words, cap_bits, p, nb, (unsigned)m[j] & ((1u << nb) - 1u)); p += nb; }
-            } else {
-                ATDE_ROLLED
-                for (int j = 0; j < len / 2; j++) {
-                    const unsigned code = ((unsigned)kClcIdx[m[2 * j] + 2] << 2) | kClcIdx[m[2 * j + 1] + 2];
-                    put_bits3(sh.words, cap_bits, p, 4, code); p += 4;
+        int base = pos;
+        for (unsigned rows = rows_of_bfus(nzmask); rows; rows &= rows - 1) {
+            const int r = __ffs((int)rows) - 1;
+            const int i = 32 * r + lane;
+            const int p = sh.wl_now[row_bfu(r, lane)];
+            const int m = sh.mant[i];
+            const int mn = __shfl_down_sync(0xffffffffu, m, 1);
+            unsigned nb = 0, code = 0;
+            if (p > 1) {
+                if (mode) {
+                    nb = kClcLen[p];
+                    code = (unsigned)m & ((1u << nb) - 1u);
+                } else {
+                    const int hi = kHuffOff[p] + huff_index(m);
+                    nb = kHuffBits[hi];
+                    code = kHuffCode[hi];
+                }
+            } else if (p == 1 && !(lane & 1)) {                  // word length 1 codes pairs of lines
+                if (mode) {
+                    nb = 4;
+                    code = ((unsigned)kClcIdx[m + 2] << 2) | kClcIdx[mn + 2];
+                } else {
+                    const int hi = kVlcPairIdx[3 * (m + 1) + (mn + 1)];
+                    nb = kHuffBits[hi];
+                    code = kHuffCode[hi];
                 }
             }
-        } else {
-            const int off = kHuffOff[prec];
-            if (prec > 1u) {
-                ATDE_ROLLED
-                for (int j = 0; j < len; j++) {
-                    const int hi = huff_index(m[j]);
-                    put_bits3(sh.words, cap_bits, p, kHuffBits[off + hi], kHuffCode[off + hi]); p += kHuffBits[off + hi];
-                }
-            } else {
-                ATDE_ROLLED
-                for (int j = 0; j < len / 2; j++) {
-                    const int hi = kVlcPairIdx[3 * (m[2 * j] + 1) + (m[2 * j + 1] + 1)];
-                    put_bits3(sh.words, cap_bits, p, kHuffBits[hi], kHuffCode[hi]); p += kHuffBits[hi];
-                }
+            unsigned incl = nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
             }
+            if (nb) put_bits3(words, cap_bits, base + (int)(incl - nb), (int)nb, code);
+            base += (int)__shfl_sync(0xffffffffu, incl, 31);
         }
     }
     __syncwarp();
@@ -1072,7 +1134,7 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         const int lo = ch == 0 ? 0 : n0, hi = ch == 0 ? n0 : g.frame_sz;
         for (int i = lo + lane; i < hi; i += 32) {
             const int q = ch == 0 ? i : (g.js ? (g.frame_sz - n0 - 1) - (i - n0) : i - n0);
-            const unsigned w = sh.words[q >> 2];
+            const unsigned w = words[q >> 2];
             dst[i] = (unsigned char)(w >> (24 - 8 * (q & 3)));
         }
     } else if (g.js_mono) {
@@ -1080,7 +1142,7 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
         for (int i = lane; i < g.frame_sz; i += 32) {
             unsigned char v;
             if (i < n0) {
-                const unsigned w = sh.words[i >> 2];
+                const unsigned w = words[i >> 2];
                 v = (unsigned char)(w >> (24 - 8 * (i & 3)));
             } else {
                 const int q = (g.frame_sz - 1) - i;
@@ -1091,7 +1153,7 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
     } else {
         for (int i = lane; i < g.frame_sz; i += 32) {
             const int q = i < n0 ? i : i - n0;
-            const unsigned w = sh.words[q >> 2];
+            const unsigned w = words[q >> 2];
             dst[i] = (unsigned char)(w >> (24 - 8 * (q & 3)));
         }
     }

@@ -94,10 +94,12 @@ struct TaskScratch {                      // LOCAL memory (the kernel's stack fr
     cpx fb[128];
 };
 
-static GhaTables* g_gha_tables = nullptr;
-static std::once_flag g_gha_once;
+// per CUDA device, like at3p_kernels.cu:device_tables()
+constexpr int kMaxGhaDevices = 64;
+static GhaTables* g_gha_tables[kMaxGhaDevices] = {};
+static std::mutex g_gha_mu;
 
-static void build_gha_tables()
+static GhaTables* build_gha_tables()
 {
     GhaTables* h = new GhaTables();
     memset(h, 0, sizeof(*h));
@@ -129,15 +131,22 @@ static void build_gha_tables()
     for (int i = 0; i < 2048; i++) h->sine_tab[i] = sin(2 * M_PI * i / 2048);
     GhaTables* d = nullptr;
     if (cudaMalloc(&d, sizeof(GhaTables)) == cudaSuccess &&
-        cudaMemcpy(d, h, sizeof(GhaTables), cudaMemcpyHostToDevice) == cudaSuccess)
-        g_gha_tables = d;
+        cudaMemcpy(d, h, sizeof(GhaTables), cudaMemcpyHostToDevice) == cudaSuccess) {
+        delete h;
+        return d;
+    }
+    if (d) cudaFree(d);
     delete h;
+    return nullptr;
 }
 
 const GhaTables* gha_tables()
 {
-    std::call_once(g_gha_once, build_gha_tables);
-    return g_gha_tables;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxGhaDevices) return nullptr;
+    std::lock_guard<std::mutex> lock(g_gha_mu);
+    if (!g_gha_tables[dev]) g_gha_tables[dev] = build_gha_tables();
+    return g_gha_tables[dev];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,12 +24,16 @@ __constant__ cpx c_tw8[8];                 // forward kissfft twiddles of the 8-
 // =====================================================================================
 // host tables
 // =====================================================================================
-static DevTables* g_dev_tables = nullptr;
-static std::once_flag g_tables_once;
+// One table set (and one upload of the __constant__ symbols) per CUDA DEVICE: a process may create ATRAC3plus encoders
+// on several GPUs (atde_settings::device), and both a cudaMalloc'ed table and a __constant__ symbol belong to the
+// device that was current when they were written.  A failed upload is not cached: the next call tries again.
+constexpr int kMaxDevices = 64;
+static DevTables* g_dev_tables[kMaxDevices] = {};
+static std::mutex g_tables_mu;
 
 static float bits_to_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 
-static void build_tables()
+static DevTables* build_tables()
 {
     DevTables* h = new DevTables();
     memset(h, 0, sizeof(*h));
@@ -67,15 +71,22 @@ static void build_tables()
         cudaMemcpy(d, h, sizeof(DevTables), cudaMemcpyHostToDevice) == cudaSuccess &&
         cudaMemcpyToSymbol(c_fir, fir, sizeof(fir)) == cudaSuccess &&
         cudaMemcpyToSymbol(c_dct_sc, dsc.data(), 16 * sizeof(float)) == cudaSuccess &&
-        cudaMemcpyToSymbol(c_tw8, tw8.data(), 8 * sizeof(cpx)) == cudaSuccess)
-        g_dev_tables = d;
+        cudaMemcpyToSymbol(c_tw8, tw8.data(), 8 * sizeof(cpx)) == cudaSuccess) {
+        delete h;
+        return d;
+    }
+    if (d) cudaFree(d);
     delete h;
+    return nullptr;
 }
 
 const DevTables* device_tables()
 {
-    std::call_once(g_tables_once, build_tables);
-    return g_dev_tables;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    std::lock_guard<std::mutex> lock(g_tables_mu);
+    if (!g_dev_tables[dev]) g_dev_tables[dev] = build_tables();
+    return g_dev_tables[dev];
 }
 
 // =====================================================================================

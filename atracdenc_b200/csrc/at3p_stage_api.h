@@ -1,7 +1,6 @@
 /* at3p_stage_api.h — stage-level entry points of the ATRAC3plus kernels (host buffers in/out).
- * NOT part of the drop-in boundary (include/atde_b200.h): ATRAC3plus cannot be created through
- * atde_create() until the GHA stage exists.  tests/ uses these to check every finished kernel
- * against the reference's taps.  All return 0 on success, -2 on a CUDA error, -3 on allocation failure. */
+ * NOT part of the drop-in boundary (include/atde_b200.h; the product path is atde_create(ATDE_CODEC_ATRAC3PLUS)).
+ * tests/ uses these to check every kernel of the ATRAC3plus chain on its own against the reference's taps.  All return 0 on success, -2 on a CUDA error, -3 on allocation failure. */
 #pragma once
 #ifdef __cplusplus
 extern "C" {

@@ -713,6 +713,9 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     int rc = ensure_state(e, S);
     if (rc) return rc;
     e->last_S = S; e->last_F = F;
+    // atde_encode_batch_device() only enqueues on slot 0's stream: what it still has in flight must be done before
+    // slot 1's stream touches the carried stream state
+    CK(cudaStreamSynchronize(e->ws[0].stream));
     const int C = e->cfg.channels;
     const bool at3p = e->cfg.codec == ATDE_CODEC_ATRAC3PLUS;
     const bool at3 = e->cfg.codec == ATDE_CODEC_ATRAC3 || at3p;      // one-frame look-ahead, fixed-size units
@@ -752,22 +755,40 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
         const int rest = S - first, pieces = (rest + chunk - 1) / chunk;
         chunk = (rest + pieces - 1) / pieces;
     }
+    // A failure inside the loop must not return while earlier chunks' copies still use the caller's buffers, and it
+    // leaves the carried stream state half advanced: drain both pipeline slots and invalidate the state
+    // (the next batch needs atde_reset()).
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(e->ws[0].stream);
+        cudaStreamSynchronize(e->ws[1].stream);
+        e->have_state = false;
+        e->n_state_streams = 0;
+        e->streams_started = false;
+        atde::at3p::pipeline_reset(e->at3p);
+        return code;
+    };
+#define CKB(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return bail(fail(ATDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
     int slot = 0;
     for (int s0 = 0, n = first; s0 < S; s0 += n, n = chunk, slot ^= 1) {
         if (n > S - s0) n = S - s0;
         Workspace& w = e->ws[slot];
-        if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) return rc;
-        if ((rc = w.out.ensure((size_t)n * out_per_stream + 1))) return rc;
-        if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return rc;
+        if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) return bail(rc);
+        if ((rc = w.out.ensure((size_t)n * out_per_stream + 1))) return bail(rc);
+        if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return bail(rc);
         if (pcm16) {
             const size_t cnt = (size_t)n * pcm_per_stream;
-            if ((rc = w.pcm16.ensure(cnt + 8))) return rc;
-            CK(cudaMemcpyAsync(w.pcm16.p, pcm16 + (size_t)s0 * pcm_per_stream, cnt * sizeof(short), cudaMemcpyHostToDevice, w.stream));
+            if ((rc = w.pcm16.ensure(cnt + 8))) return bail(rc);
+            CKB(cudaMemcpyAsync(w.pcm16.p, pcm16 + (size_t)s0 * pcm_per_stream, cnt * sizeof(short), cudaMemcpyHostToDevice, w.stream));
             const unsigned blocks = (unsigned)std::min<size_t>((cnt / 8 + 255) / 256 + 1, (size_t)148 * 16);
             ATDE_LAUNCH(pcm_i16_to_f32_kernel, blocks, 256, 0, w.stream, (const short*)w.pcm16.p, w.pcm.p, (long long)cnt);
             e->launches += 1;
         } else {
-            CK(cudaMemcpyAsync(w.pcm.p, pcm + (size_t)s0 * pcm_per_stream, (size_t)n * pcm_per_stream * sizeof(float),
+            CKB(cudaMemcpyAsync(w.pcm.p, pcm + (size_t)s0 * pcm_per_stream, (size_t)n * pcm_per_stream * sizeof(float),
                                cudaMemcpyHostToDevice, w.stream));
         }
         if (at3p) {
@@ -775,19 +796,20 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
             atde::at3p::Profiler prof;
             prof.ctx = e; prof.begin = at3p_prof_begin; prof.end = at3p_prof_end;
             rc = atde::at3p::pipeline_run(e->at3p, w.pcm.p, s0, n, S, F, started, w.out.p, w.stream, slot, &e->launches, &why, &prof);
-            if (rc) return fail(rc == -3 ? ATDE_ERR_NOMEM : ATDE_ERR_CUDA, "ATRAC3plus pipeline: %s (%s)", why, cudaGetErrorString(cudaGetLastError()));
+            if (rc) return bail(fail(rc == -3 ? ATDE_ERR_NOMEM : ATDE_ERR_CUDA, "ATRAC3plus pipeline: %s (%s)", why, cudaGetErrorString(cudaGetLastError())));
         } else if (at3) rc = run_at3(e, w, w.pcm.p, s0, n, F, started, w.out.p);
         else rc = run_at1(e, w, w.pcm.p, s0, n, F, w.out.p, sizes ? w.sizes.p : nullptr);
-        if (rc) return rc;
+        if (rc) return bail(rc);
         if (out_per_stream)
-            CK(cudaMemcpyAsync(out + (size_t)s0 * out_per_stream, w.out.p, (size_t)n * out_per_stream,
+            CKB(cudaMemcpyAsync(out + (size_t)s0 * out_per_stream, w.out.p, (size_t)n * out_per_stream,
                                cudaMemcpyDeviceToHost, w.stream));
         if (sizes && !at3)
-            CK(cudaMemcpyAsync(sizes + (size_t)s0 * units_per_stream, w.sizes.p, (size_t)n * units_per_stream * sizeof(int),
+            CKB(cudaMemcpyAsync(sizes + (size_t)s0 * units_per_stream, w.sizes.p, (size_t)n * units_per_stream * sizeof(int),
                                cudaMemcpyDeviceToHost, w.stream));
     }
     CK(cudaStreamSynchronize(e->ws[0].stream));
     CK(cudaStreamSynchronize(e->ws[1].stream));
+#undef CKB
     if (sizes && at3)                                  // every WriteFrame payload is exactly FrameSz bytes
         for (size_t i = 0; i < (size_t)S * units_per_stream; i++) sizes[i] = e->unit_bytes;
     if (at3p) atde::at3p::pipeline_commit(e->at3p);

@@ -31,7 +31,7 @@ __device__ __forceinline__ void atde_named_barrier(int id, int count)
 
 namespace atde {
 
-struct cpx { float r, i; };
+struct __align__(8) cpx { float r, i; };   // 8-byte aligned: one 64-bit load / store per element
 
 // Un-fused IEEE fp32 helpers.  With -fmad=false plain operators would do, but spelling the
 // rounding out keeps the parity contract visible and survives a stray build flag.
@@ -82,6 +82,75 @@ ATDE_D f32x2 add2(f32x2 a, f32x2 b, f32x2 one)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(one)), "l"(pack2(b)));
     return unpack2(r);
 }
+#endif
+
+// ---- bulk asynchronous copies (1-D TMA, `cp.async.bulk`) with mbarrier completion ----
+// Global -> shared: ONE lane arms the barrier with the byte count and issues the copies; the copy engine moves the
+// tile while the warp computes; every consumer waits on the barrier's phase parity.  Shared -> global: the writers
+// make their generic-proxy stores visible to the async proxy (async_proxy_fence), one lane issues the copy and commits
+// the group; bulk_store_wait_read() tells when the shared source may be overwritten.  Addresses and sizes are
+// multiples of 16 bytes.  SASS: UBLKCP (bulk copy), SYNCS (mbarrier).
+//
+// ATDE_DYN_SMEM(name): the block's dynamic shared memory as `unsigned char* name`.
+#ifdef ATDE_CPU_EMU
+#define ATDE_DYN_SMEM(name) unsigned char* name = cuemu::dyn_smem
+struct mbar_t { volatile unsigned phase; volatile unsigned pending; };
+ATDE_D void mbar_init(mbar_t* b, int /*arrivals*/) { b->phase = 0; b->pending = 0; }
+ATDE_D void mbar_expect_tx(mbar_t* b, unsigned bytes) { b->pending = bytes; }
+ATDE_D void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t* b)
+{
+    memcpy(dst, src, bytes);
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    b->pending -= bytes;
+    if (b->pending == 0) { __atomic_thread_fence(__ATOMIC_SEQ_CST); b->phase = b->phase + 1; }
+}
+ATDE_D void mbar_wait(mbar_t* b, unsigned parity)
+{
+    while ((b->phase & 1u) == parity) sched_yield();
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+ATDE_D void async_proxy_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+ATDE_D void bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
+ATDE_D void bulk_store_commit() {}
+ATDE_D void bulk_store_wait_read() {}
+ATDE_D void bulk_store_wait_all() {}
+#else
+#define ATDE_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+typedef unsigned long long mbar_t;
+ATDE_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+ATDE_D void mbar_init(mbar_t* b, int arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(arrivals) : "memory");
+}
+ATDE_D void mbar_expect_tx(mbar_t* b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+ATDE_D void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+ATDE_D void mbar_wait(mbar_t* b, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+ATDE_D void async_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+ATDE_D void bulk_s2g(void* dst, const void* src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+ATDE_D void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+ATDE_D void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+ATDE_D void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 #endif
 
 } // namespace atde

@@ -144,6 +144,16 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v)
     cuemu::warp_barrier();
     return r;
 }
+inline unsigned __reduce_max_sync(unsigned, unsigned v)
+{
+    uint64_t* s = cuemu::warp_slots();
+    s[cuemu::lin_tid & 31] = v;
+    cuemu::warp_barrier();
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r = (unsigned)s[i] > r ? (unsigned)s[i] : r;
+    cuemu::warp_barrier();
+    return r;
+}
 inline int __reduce_add_sync(unsigned m, int v) { return (int)__reduce_add_sync(m, (unsigned)v); }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }

@@ -28,6 +28,8 @@ EXPORTS = [
     "atde_units_per_frame", "atde_unit_bytes", "atde_lookahead_frames", "atde_output_frames", "atde_encode_batch", "atde_encode_batch_i16",
     "atde_encode_batch_device", "atde_sync", "atde_reset", "atde_cuda_stream",
     "atde_launch_count", "atde_set_profiling", "atde_kernel_times", "atde_debug_tap", "atde_debug_math", "atde_last_error", "atde_version",
+    "atde_create_group", "atde_destroy_group", "atde_group_size", "atde_group_encode_batch", "atde_group_encode_batch_i16",
+    "atde_group_output_frames", "atde_group_reset",
 ]
 
 
@@ -76,6 +78,15 @@ def load_library(path: os.PathLike | str | None = None) -> ctypes.CDLL:
     lib.atde_debug_tap.argtypes = [vp, i32, vp, ctypes.c_size_t]
     lib.atde_debug_tap.restype = i64
     lib.atde_debug_math.argtypes = [i32, i32, vp, vp, i64]
+    lib.atde_create_group.argtypes = [ctypes.POINTER(Settings), ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+    lib.atde_destroy_group.argtypes = [vp]
+    lib.atde_destroy_group.restype = None
+    lib.atde_group_size.argtypes = [vp]
+    lib.atde_group_encode_batch.argtypes = [vp, vp, i32, i64, vp, vp]
+    lib.atde_group_encode_batch_i16.argtypes = [vp, vp, i32, i64, vp, vp]
+    lib.atde_group_output_frames.argtypes = [vp, i64]
+    lib.atde_group_output_frames.restype = i64
+    lib.atde_group_reset.argtypes = [vp]
     lib.atde_last_error.restype = ctypes.c_char_p
     lib.atde_version.restype = ctypes.c_char_p
     return lib
@@ -193,3 +204,63 @@ class Encoder:
         buf = np.empty(shape, dtype=dtype)
         self._check(self.lib.atde_debug_tap(self.h, what, buf.ctypes.data, buf.nbytes))
         return buf
+
+
+class EncoderGroup:
+    """atde_create_group: one member per device, a batch's streams sharded contiguously over the members, members run
+    concurrently (one host thread per device).  Host buffers only."""
+
+    def __init__(self, codec: int, channels: int, devices, *, bitrate: int = 0, lib: ctypes.CDLL | None = None, **kw):
+        self.lib = lib or load_library()
+        s = Settings()
+        self.lib.atde_default_settings(ctypes.byref(s), codec, channels)
+        s.bitrate = bitrate
+        for k, v in kw.items():
+            setattr(s, k, int(v))
+        devs = (ctypes.c_int32 * len(devices))(*devices)
+        h = ctypes.c_void_p()
+        rc = self.lib.atde_create_group(ctypes.byref(s), devs, len(devices), ctypes.byref(h))
+        if rc < 0:
+            raise AtdeError(f"atde error {rc}: {self.lib.atde_last_error().decode()}")
+        self.h, self.channels = h, channels
+        probe = Encoder(codec, channels, bitrate=bitrate, device=devices[0], lib=self.lib)
+        self.frame_samples, self.units_per_frame, self.unit_bytes = probe.frame_samples, probe.units_per_frame, probe.unit_bytes
+        probe.close()
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise AtdeError(f"atde error {rc}: {self.lib.atde_last_error().decode()}")
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.atde_destroy_group(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def size(self) -> int:
+        return self._check(self.lib.atde_group_size(self.h))
+
+    def reset(self):
+        self._check(self.lib.atde_group_reset(self.h))
+
+    def output_frames(self, n_frames: int) -> int:
+        return self._check(self.lib.atde_group_output_frames(self.h, n_frames))
+
+    def encode(self, pcm: np.ndarray, n_streams: int, want_sizes: bool = False):
+        i16 = pcm.dtype == np.int16
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16 if i16 else np.float32)
+        per_stream = pcm.size // n_streams
+        F = per_stream // (self.frame_samples * self.channels)
+        assert F * self.frame_samples * self.channels * n_streams == pcm.size, "whole frames only"
+        Fo = self.output_frames(F)
+        out = np.empty((n_streams, Fo, self.units_per_frame, self.unit_bytes), dtype=np.uint8)
+        sizes = np.empty((n_streams, Fo, self.units_per_frame), dtype=np.int32) if want_sizes else None
+        fn = self.lib.atde_group_encode_batch_i16 if i16 else self.lib.atde_group_encode_batch
+        self._check(fn(self.h, pcm.ctypes.data, n_streams, F, out.ctypes.data, sizes.ctypes.data if want_sizes else None))
+        return (out, sizes) if want_sizes else out
+
+    def encode_ptr(self, pcm_ptr: int, n_streams: int, n_frames: int, out_ptr: int, i16: bool = False):
+        fn = self.lib.atde_group_encode_batch_i16 if i16 else self.lib.atde_group_encode_batch
+        self._check(fn(self.h, pcm_ptr, n_streams, n_frames, out_ptr, None))

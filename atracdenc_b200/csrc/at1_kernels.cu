@@ -21,13 +21,19 @@
 #include "at1_kernels.cuh"
 #include "kissfft_dev.cuh"
 #include "glibc_math.cuh"
+#include "qmf_dev.cuh"
 
 namespace atde {
 namespace at1 {
 
-__constant__ float c_qmf[48];        // QmfWindow, qmf.cpp:36-45 (uniform-index reads -> constant bank)
+__constant__ __align__(8) float c_qmf1p[48];   // QmfWindow (qmf.cpp:36-45) as tap pairs (W[2i+1], W[2i]), see qmf_dev.cuh
 
-void upload_qmf_window(const float w[48]) { cudaMemcpyToSymbol(c_qmf, w, 48 * sizeof(float)); }
+void upload_qmf_window(const float w[48])
+{
+    float p[48];
+    for (int i = 0; i < 24; i++) { p[2 * i] = w[2 * i + 1]; p[2 * i + 1] = w[2 * i]; }
+    cudaMemcpyToSymbol(c_qmf1p, p, 48 * sizeof(float));
+}
 
 // ---- BFU geometry, atrac1.h:89-104 ----
 __device__ const unsigned char kSpecsPerBlock[kMaxBfus] = {
@@ -76,26 +82,12 @@ struct BandView {
     int size;            // 128 / 128 / 256
 };
 
-// 48-tap half-band split of one output pair (qmf.h:54-63): sequential sums, taps in order.
-ATDE_D void qmf_pair(const float* src, int j, float& lower, float& upper)
+// HPF input sample: band sample k (k may reach -20 into the previous frame), spectrum-inverted for the mid/hi bands
+// (InvertSpectr, util.h:51-63: even indices negated).  `flip` is the sign-bit mask of the EVEN samples (0 for the low
+// band); negation is exact, so flipping the bit equals the reference's multiplication by -1.
+ATDE_D float hpf_in(const float* band0, int k, unsigned flip)
 {
-    float lo = 0.0f, up = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 24; i++) {
-        const float2 v = *reinterpret_cast<const float2*>(src + 2 * j + 48 - 2 * i);
-        lo = fadd(lo, fmul(c_qmf[2 * i], v.y));
-        up = fadd(up, fmul(c_qmf[2 * i + 1], v.x));
-    }
-    upper = fsub(lo, up);
-    lower = fadd(lo, up);
-}
-
-// HPF input sample: band sample k (k may reach -20 into the previous frame), spectrum-inverted
-// for the mid/hi bands (InvertSpectr, util.h:51-63: even indices negated).
-ATDE_D float hpf_in(const float* band0, int k, bool invert)
-{
-    const float v = band0[k];
-    return (invert && !(k & 1)) ? -v : v;
+    return __uint_as_float(__float_as_uint(band0[k]) ^ ((k & 1) ? 0u : flip));
 }
 
 // MDCT input sample tmp[j] of TAtrac1MDCT::Mdct (atrac1denc.cpp:80-90), built on the fly.
@@ -120,27 +112,40 @@ ATDE_D float mdct_in_short(const float* band0, const float* W, int j, int kb)
     return fmul(W[63 - j], band0[32 * kb + (j - 32)]);
 }
 
-__global__ void __launch_bounds__(256) at1_analysis_kernel(AnalysisParams p)
+// Stage-1 tasks of 9 output pairs (kNS1 = 1152 = 128 x 9: one task per thread), stage-2 tasks of 5 (111 tasks cover
+// kNS2 = 552 and three scratch outputs).  Odd task sizes keep the 64-bit loads conflict-free (qmf_dev.cuh).
+constexpr int kQ1 = 9, kQ2 = 5;
+constexpr int kAnaThreads = 128;
+static_assert(kNS1 == kAnaThreads * kQ1, "stage-1 tasks fill the block exactly");
+constexpr int kNS2T = ((kNS2 + kQ2 - 1) / kQ2) * kQ2;           // 555
+
+__global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisParams p)
 {
-    __shared__ __align__(16) float x[kNX];          // input tile; later HPF output; later FFT buffer
-    __shared__ __align__(16) float s1lo[kNS1];
+    __shared__ __align__(16) float x[kNX + 8];      // input tile; later HPF output; later FFT buffer
+    __shared__ __align__(16) float s1lo[kNS1 + 8];  // (+8: the three scratch outputs of stage 2 read past kNS1)
     __shared__ __align__(16) float s1hi[kNS1];
-    __shared__ __align__(16) float lo[kNS2];
-    __shared__ __align__(16) float mi[kNS2];
+    __shared__ __align__(16) float lo[kNS2T + 1];
+    __shared__ __align__(16) float mi[kNS2T + 1];
     __shared__ __align__(16) float sp[kTile * 512];
     __shared__ float ener[kNEner];
     __shared__ float W[32];
+    __shared__ __align__(8) float cw[48];
     __shared__ unsigned char smask[kTile];
 
     const int s = blockIdx.y;
+    const int c = blockIdx.z;                              // one block per channel: the channels never meet
     const int t0 = blockIdx.x * kTile;
     const int C = p.C, F = p.F;
     const DevTables* __restrict__ T = p.tab;
     const bool fresh = !(p.started && p.started[s]);       // stream starts at frame 0 of this batch
+    f32x2 one;
+    one.x = p.one; one.y = p.one;
 
     ATDE_PAR_FOR(i, 32) W[i] = T->sine_window[i];
+    ATDE_PAR_FOR(i, 48) cw[i] = c_qmf1p[i];
+    ATDE_PAR_FOR(i, 8) { x[kNX + i] = 0.0f; s1lo[kNS1 + i] = 0.0f; }
 
-    for (int c = 0; c < C; c++) {
+    {
         // ---- load input tile with halo ----
         const float* __restrict__ pcm = p.pcm + (size_t)s * F * 512 * C + c;
         ATDE_PAR_FOR(k, kNX) {
@@ -154,20 +159,20 @@ __global__ void __launch_bounds__(256) at1_analysis_kernel(AnalysisParams p)
             x[k] = v;
         }
         __syncthreads();
-        // ---- QMF stage 1: full band -> (low+mid, hi) ----
-        ATDE_PAR_FOR(j, kNS1) {
-            float l, u;
-            qmf_pair(x, j, l, u);
-            s1lo[j] = l;
-            s1hi[j] = u;
+        // ---- QMF stage 1: full band -> (low+mid, hi); thread t owns outputs 9t .. 9t+8 ----
+        {
+            float l[kQ1], u[kQ1];
+            qmf_task64<kQ1>(x, cw, kQ1 * (int)threadIdx.x, one, l, u);
+#pragma unroll
+            for (int r = 0; r < kQ1; r++) { s1lo[kQ1 * threadIdx.x + r] = l[r]; s1hi[kQ1 * threadIdx.x + r] = u[r]; }
         }
         __syncthreads();
         // ---- QMF stage 2: (low+mid) -> (low, mid) ----
-        ATDE_PAR_FOR(j, kNS2) {
-            float l, u;
-            qmf_pair(s1lo, j, l, u);
-            lo[j] = l;
-            mi[j] = u;
+        if (threadIdx.x < kNS2T / kQ2) {
+            float l[kQ2], u[kQ2];
+            qmf_task64<kQ2>(s1lo, cw, kQ2 * (int)threadIdx.x, one, l, u);
+#pragma unroll
+            for (int r = 0; r < kQ2; r++) { lo[kQ2 * threadIdx.x + r] = l[r]; mi[kQ2 * threadIdx.x + r] = u[r]; }
         }
         __syncthreads();
 
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(256) at1_analysis_kernel(AnalysisParams p)
                 if (q < 16) { tl = -1; i = size - 16 + q; }
                 else { tl = (q - 16) / size; i = (q - 16) - tl * size; }
                 const float* fr = band0[b] + tl * size;          // sample 0 of that frame
-                const bool inv = b != 0;
+                const unsigned inv = b != 0 ? 0x80000000u : 0u;
                 // inBuf[w] = frame sample (w - 20); inBuf[size + 20] is never written by the reference => 0
                 const float c0 = -8.65163e-18 * 2.0, c1 = -0.00851586 * 2.0, c2 = -6.74764e-18 * 2.0,
                             c3 = 0.0209036 * 2.0, c4 = -3.36639e-17 * 2.0, c5 = -0.0438162 * 2.0,
@@ -348,31 +353,58 @@ __global__ void __launch_bounds__(256) at1_analysis_kernel(AnalysisParams p)
             out[pb] = vb;
         }
         __syncthreads();
-        // ---- store spectra, masks; loudness term (sequential sum, atrac1denc.cpp:235-240) ----
+        // ---- store spectra and masks (the loudness term has its own kernel: it is one sequential sum per frame) ----
         ATDE_PAR_FOR(u, kTile * 512) {
             const int tl = u >> 9, i = u & 511;
             if (t0 + tl < F)
                 p.specs[(((size_t)s * F + t0 + tl) * C + c) * 512 + i] = sp[u];
         }
         ATDE_PAR_FOR(tl, kTile) {
-            if (t0 + tl < F) {
-                const float* q = sp + tl * 512;
-                float l = 0.0f;
-                for (int i = 0; i < 512; i++)
-                    l = fadd(l, fmul(fmul(q[i], q[i]), T->loud_curve[i]));
-                const size_t o = ((size_t)s * F + t0 + tl) * C + c;
-                p.chloud[o] = l;
-                p.masks[o] = smask[tl];
+            if (t0 + tl < F) p.masks[((size_t)s * F + t0 + tl) * C + c] = smask[tl];
+        }
+    }
+}
+
+// Loudness term of every channel-frame (atrac1denc.cpp:235-240): l += spec^2 * curve over the 512 lines in order — one
+// sequential chain per channel-frame, so ONE LANE per channel-frame; the spectra are staged through shared memory in
+// 32x32 tiles to keep the global reads coalesced.
+constexpr int kLoudWarps = 4;
+__global__ void __launch_bounds__(kLoudWarps * 32) at1_loudterm_kernel(AnalysisParams p)
+{
+    __shared__ float tile_all[kLoudWarps][32][33];
+    const DevTables* __restrict__ T = p.tab;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long total = (long long)p.S * p.F * p.C;
+    const long long unit0 = ((long long)blockIdx.x * kLoudWarps + wib) * 32;
+    if (unit0 >= total) return;
+    float (*tile)[33] = tile_all[wib];
+    const long long mine = unit0 + lane;
+    const bool live = mine < total;
+    const int nrows = (int)min(32LL, total - unit0);
+    float l = 0.0f;
+    for (int t = 0; t < 16; t++) {
+        for (int r = 0; r < nrows; r++)
+            tile[r][lane] = p.specs[(size_t)(unit0 + r) * 512 + 32 * t + lane];
+        __syncwarp();
+        if (live) {
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const float v = tile[lane][k];
+                l = fadd(l, fmul(fmul(v, v), T->loud_curve[32 * t + k]));
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
+    if (live) p.chloud[mine] = l;
 }
 
 void launch_analysis(const AnalysisParams& p, cudaStream_t st)
 {
-    dim3 grid((p.F + kTile - 1) / kTile, p.S);
-    ATDE_LAUNCH(at1_analysis_kernel, grid, 256, 0, st, p);
+    dim3 grid((p.F + kTile - 1) / kTile, p.S, p.C);
+    ATDE_LAUNCH(at1_analysis_kernel, grid, kAnaThreads, 0, st, p);
+    const long long total = (long long)p.S * p.F * p.C;
+    const long long per_block = kLoudWarps * 32;
+    ATDE_LAUNCH(at1_loudterm_kernel, (unsigned)((total + per_block - 1) / per_block), kLoudWarps * 32, 0, st, p);
 }
 
 // =====================================================================================

@@ -35,6 +35,7 @@ struct AnalysisParams {
     int F;
     int window_auto;             // EWM_AUTO
     int window_mask;             // used when !window_auto
+    float one;                   // 1.0f, opaque to the compiler (atde_cuda.h: add2)
 };
 
 struct LoudnessParams {

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -344,6 +345,7 @@ int run_at1(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
     a.S = S; a.C = C; a.F = (int)F;
     a.window_auto = e->cfg.window_mode == 1;
     a.window_mask = (int)e->cfg.window_mask;
+    a.one = 1.0f;
     { KernelTimer kt(e, w.stream, 0); launch_analysis(a, w.stream); }
 
     LoudnessParams l;
@@ -370,7 +372,7 @@ int run_at1(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
     c.started = e->started.p + s0;
     c.S = S; c.C = C; c.F = (int)F;
     launch_carry(c, w.stream);
-    e->launches += 4;
+    e->launches += 5;
     CK(cudaGetLastError());
     return 0;
 }
@@ -881,6 +883,110 @@ int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* dst, size_t capacity
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return (int64_t)bytes;
+}
+
+// ---- encoder groups: one member per device, streams sharded contiguously, members run concurrently ----
+struct atde_group {
+    std::vector<atde_encoder*> members;
+};
+
+static void group_range(int S, int n, int r, int* lo, int* hi)
+{
+    const int base = S / n, extra = S % n;
+    *lo = r * base + (r < extra ? r : extra);
+    *hi = *lo + base + (r < extra ? 1 : 0);
+}
+
+int atde_create_group(const atde_settings* s, const int32_t* devices, int32_t n_devices, atde_group** out)
+{
+    if (!s || !devices || !out || n_devices <= 0) return fail(ATDE_ERR_INVALID, "bad group arguments");
+    *out = nullptr;
+    atde_group* g = new (std::nothrow) atde_group();
+    if (!g) return fail(ATDE_ERR_NOMEM, "host alloc");
+    for (int r = 0; r < n_devices; r++) {
+        atde_settings m = *s;
+        m.device = devices[r];
+        atde_encoder* e = nullptr;
+        const int rc = atde_create(&m, &e);
+        if (rc) {
+            const std::string why = g_err;
+            atde_destroy_group(g);
+            return fail(rc, "group member %d (device %d): %s", r, devices[r], why.c_str());
+        }
+        g->members.push_back(e);
+    }
+    *out = g;
+    return 0;
+}
+
+void atde_destroy_group(atde_group* g)
+{
+    if (!g) return;
+    for (atde_encoder* e : g->members) atde_destroy(e);
+    delete g;
+}
+
+int atde_group_size(const atde_group* g) { return g ? (int)g->members.size() : ATDE_ERR_INVALID; }
+
+int64_t atde_group_output_frames(const atde_group* g, int64_t n_frames)
+{
+    if (!g || g->members.empty()) return ATDE_ERR_INVALID;
+    return atde_output_frames(g->members[0], n_frames);
+}
+
+int atde_group_reset(atde_group* g)
+{
+    if (!g) return fail(ATDE_ERR_INVALID, "null group");
+    for (atde_encoder* e : g->members) {
+        const int rc = atde_reset(e);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int group_encode(atde_group* g, const float* pcm, const int16_t* pcm16, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
+{
+    if (!g || (!pcm && !pcm16) || !out) return fail(ATDE_ERR_INVALID, "null argument");
+    const int n = (int)g->members.size();
+    if (S < n) return fail(ATDE_ERR_INVALID, "a group of %d members needs at least %d streams per batch (got %d)", n, n, S);
+    if (F <= 0) return fail(ATDE_ERR_INVALID, "empty batch");
+    const atde_encoder* e0 = g->members[0];
+    const int64_t fo = atde_output_frames(e0, F);
+    const size_t pcm_per_stream = (size_t)F * e0->frame_samples * e0->cfg.channels;
+    const size_t units_per_stream = (size_t)fo * e0->units_per_frame;
+    const size_t out_per_stream = units_per_stream * e0->unit_bytes;
+    std::vector<int> rcs(n, 0);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> workers;
+    workers.reserve(n);
+    for (int r = 0; r < n; r++) {
+#ifdef ATDE_CPU_EMU
+        // (the CPU-emulation shim of the tests runs one kernel at a time: members take turns there)
+        if (!workers.empty()) { workers.back().join(); workers.pop_back(); }
+#endif
+        workers.emplace_back([&, r]() {
+            int lo, hi;
+            group_range(S, n, r, &lo, &hi);
+            rcs[r] = encode_batch_host(g->members[r], pcm ? pcm + (size_t)lo * pcm_per_stream : nullptr,
+                                       pcm16 ? pcm16 + (size_t)lo * pcm_per_stream : nullptr, hi - lo, F,
+                                       out + (size_t)lo * out_per_stream, sizes ? sizes + (size_t)lo * units_per_stream : nullptr);
+            if (rcs[r]) errs[r] = g_err;                     // g_err is per thread: hand the text to the caller's thread
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int r = 0; r < n; r++)
+        if (rcs[r]) return fail(rcs[r], "group member %d: %s", r, errs[r].c_str());
+    return 0;
+}
+
+int atde_group_encode_batch(atde_group* g, const float* pcm, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
+{
+    return group_encode(g, pcm, nullptr, S, F, out, sizes);
+}
+
+int atde_group_encode_batch_i16(atde_group* g, const int16_t* pcm, int32_t S, int64_t F, uint8_t* out, int32_t* sizes)
+{
+    return group_encode(g, nullptr, pcm, S, F, out, sizes);
 }
 
 } // extern "C"

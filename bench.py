@@ -253,26 +253,44 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def bind_host_cores(local, world):
+    """Pins this rank's host threads (and therefore the first touch of its pinned staging buffers) to an equal share
+    of the cores NVML reports as local to its GPU.  Returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = [c for c in range(ncpu) if (words[c // 64] >> (c % 64)) & 1]
+        # GPUs that share this affinity mask split it evenly
+        n_gpu = pynvml.nvmlDeviceGetCount()
+        peers = []
+        for g in range(min(n_gpu, max(world, 1))):
+            w2 = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), (ncpu + 63) // 64)
+            if list(w2) == list(words):
+                peers.append(g)
+        allowed = sorted(os.sched_getaffinity(0))
+        near = [c for c in near if c in allowed] or allowed
+        k = peers.index(local) if local in peers else 0
+        share = max(1, len(near) // max(1, len(peers)))
+        mine = near[k * share:(k + 1) * share] or near
+        os.sched_setaffinity(0, mine)
+        return {"gpu_local_cores": f"{near[0]}-{near[-1]}", "gpus_sharing_them": len(peers), "bound_to": f"{mine[0]}-{mine[-1]}"}
+    except Exception as ex:                                             # no NVML / not permitted: run unbound
+        return {"bound_to": None, "why": str(ex)[:80]}
+
+
+def measure_workload(name, args, env, *, steps, warmup, verify_stride, with_i16=True, verify_only=False):
+    """One workload on this rank's GPU: device-resident loop (`value`), host-buffer loop through the C ABI (`e2e`, float
+    and int16 ingest), parity of a stream sample against the reference.  Returns the pieces of the JSON line (rank 0)
+    or None (other ranks)."""
     import torch
     import torch.distributed as dist
     import atracdenc_b200 as ab
+    rank, world, local, barrier = env["rank"], env["world"], env["local"], env["barrier"]
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS[name]
     S, F, step, C = args.streams or wl["S"], args.frames or wl["F"], wl["step"], 2
     enc = ab.Encoder(wl["codec"], C, bitrate=wl["kbit"] * 1024, device=local)
     units, ub = enc.units_per_frame, enc.unit_bytes
@@ -295,10 +313,12 @@ def run_ours(args):
     h_out = host_empty((S, F, units, ub), torch.uint8)
     stream = torch.cuda.ExternalStream(enc.cuda_stream, device=torch.device("cuda", local))
     torch.cuda.synchronize()
+    dev_ms = host_ms = host16_ms = 0.0
+    kms, kcnt, launches, clocks = [0.0] * 6, [0] * 6, 0, None
 
-    if not args.verify_only:
+    if not verify_only:
         # ---- device-resident loop: `value` ----
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
         enc.sync()
         sampler = ClockSampler(local)
@@ -309,7 +329,7 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             enc.encode_device(d_pcm.data_ptr(), S, F, d_out.data_ptr())
         e1.record(stream)
         enc.sync()
@@ -322,11 +342,11 @@ def run_ours(args):
 
         # ---- end-to-end loop through the host API: `e2e` ----
         enc.reset()
-        for _ in range(max(1, args.warmup // 2)):
+        for _ in range(max(1, warmup // 2)):
             enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             enc.encode_ptr(h_pcm.data_ptr(), S, F, h_out.data_ptr())
         torch.cuda.synchronize()
         host_ms = (time.perf_counter() - t0) * 1000.0
@@ -343,74 +363,79 @@ def run_ours(args):
 
     # ---- parity at benchmark scale: a fixed 1-in-`stride` sample of THIS batch's streams through the reference ----
     parity = None
-    if args.verify_stride > 0:
+    if verify_stride > 0:
         import hashlib
-        ids = list(range(0, S, args.verify_stride))
+        ids = list(range(0, S, verify_stride))
         idt = torch.tensor(ids, device="cuda")
         sample_pcm = d_pcm.index_select(0, idt).cpu().numpy()
         sample_out = dev_bytes.view(S, fo * units, ub).index_select(0, idt.cpu()).numpy()
         parity = verify_against_reference(wl, sample_pcm, sample_out, world)
-        parity["sample"] = f"streams 0, {args.verify_stride}, 2*{args.verify_stride}, ... of the {S} streams of this rank's batch"
+        parity["sample"] = f"streams 0, {verify_stride}, 2*{verify_stride}, ... of the {S} streams of this rank's batch"
         parity["batch_output_sha256"] = hashlib.sha256(dev_bytes.numpy().tobytes()).hexdigest()[:16]
         del sample_pcm, sample_out
         if world > 1:
-            pv = torch.tensor([parity.get("frames_checked", 0), parity.get("mismatches", -1 if not parity["checked"] else 0)],
+            pv = torch.tensor([parity.get("frames_checked", 0), parity.get("mismatches", 0) if parity["checked"] else -1],
                               dtype=torch.int64, device="cuda")
             allp = [torch.zeros_like(pv) for _ in range(world)]
             dist.all_gather(allp, pv)
             parity["per_rank"] = [{"frames_checked": int(a[0]), "mismatches": int(a[1])} for a in allp]
             parity["frames_checked"] = int(sum(int(a[0]) for a in allp))
             parity["mismatches"] = int(sum(int(a[1]) for a in allp))
-    if args.verify_only:
-        if rank == 0:
-            print(json.dumps({"workload": wl["desc"], "n_gpus": world, "streams_per_gpu": S, "frames_per_stream": F,
-                              "host_and_device_outputs_equal": same, "parity": parity}), flush=True)
+    if verify_only:
         enc.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return {"workload": wl["desc"], "n_gpus": world, "streams_per_gpu": S, "frames_per_stream": F,
+                "host_and_device_outputs_equal": same, "parity": parity} if rank == 0 else None
 
     # ---- the same through the int16 ingest entry point: half the H2D bytes ----
-    del h_pcm                                                           # its pinned block is reused for the int16 copy
-    h_pcm16 = host_empty((S, F * step, C), torch.int16)
-    h_pcm16.copy_(torch.round(d_pcm * 32768.0).to(torch.int16))        # the synthetic PCM is int16-quantised: exact
-    enc.reset()
-    enc.encode_ptr_i16(h_pcm16.data_ptr(), S, F, h_out.data_ptr())
-    same16 = bool(torch.equal(h_out.view(-1)[: S * fo * units * ub], dev_bytes))
-    for _ in range(max(1, args.warmup // 2)):
+    same16 = None
+    if with_i16:
+        del h_pcm                                                       # its pinned block is reused for the int16 copy
+        h_pcm16 = host_empty((S, F * step, C), torch.int16)
+        h_pcm16.copy_(torch.round(d_pcm * 32768.0).to(torch.int16))    # the synthetic PCM is int16-quantised: exact
+        enc.reset()
         enc.encode_ptr_i16(h_pcm16.data_ptr(), S, F, h_out.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        enc.encode_ptr_i16(h_pcm16.data_ptr(), S, F, h_out.data_ptr())
-    torch.cuda.synchronize()
-    host16_ms = (time.perf_counter() - t0) * 1000.0
-    barrier()
+        same16 = bool(torch.equal(h_out.view(-1)[: S * fo * units * ub], dev_bytes))
+        for _ in range(max(1, warmup // 2)):
+            enc.encode_ptr_i16(h_pcm16.data_ptr(), S, F, h_out.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            enc.encode_ptr_i16(h_pcm16.data_ptr(), S, F, h_out.data_ptr())
+        torch.cuda.synchronize()
+        host16_ms = (time.perf_counter() - t0) * 1000.0
+        barrier()
+        del h_pcm16
 
     t = torch.tensor([dev_ms, host_ms, host16_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, host_ms, host16_ms = float(t[0]), float(t[1]), float(t[2])
 
+    # ---- the optional exchange step at the edges: NCCL scatter of PCM shards from rank 0, gather of
+    #      the bitstream shards onto rank 0, timed on the device; not part of `value` (the path itself has no collective)
+    collective = None
+    if world > 1 and env.get("collectives") and name == DEFAULT_WORKLOAD:
+        collective = measure_collectives(torch, dist, env, d_pcm, d_out[:, :fo].contiguous(), S)
+
+    res = None
     if rank == 0:
         frames_total = S * F * world
-        value = frames_total * args.steps / (dev_ms / 1000.0)
-        e2e = frames_total * args.steps / (host_ms / 1000.0)
+        value = frames_total * steps / (dev_ms / 1000.0)
+        e2e = frames_total * steps / (host_ms / 1000.0)
         peak, peak_kind = read_peak()
-        k1_ms = kms[0] / max(1, args.steps)          # per step: ATRAC3 launches two kernels of kind 0 (QMF, MDCT)
+        k1_ms = kms[0] / max(1, steps)               # per step: ATRAC3 launches two kernels of kind 0 (QMF, MDCT)
         alg_bytes = wl["alg_bytes"] * S * F
         achieved = alg_bytes / (k1_ms / 1000.0) / 1e9 if k1_ms > 0 else None
         traffic = None
-        tp = ROOT / "profiles" / f"traffic_{args.workload}.json"
+        tp = ROOT / "profiles" / f"traffic_{name}.json"
         if tp.exists():
             try:
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        h2d = S * F * step * C * 4
+        res = {
+            "value": value, "ms_per_step": dev_ms / steps, "steps": steps, "warmup": warmup,
             "config": {"workload": wl["desc"], "streams_per_gpu": S, "frames_per_stream": F, "channels": C,
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                        "l2_policy": f"inputs larger than L2 ({S * F * step * C * 4 / 2**20:.0f} MiB PCM per step)",
@@ -423,23 +448,134 @@ def run_ours(args):
                          "kernel": wl["kernel"], "peak_source": f"of {peak_kind}",
                          "kernel_ms": k1_ms, "alg_bytes_per_launch": alg_bytes,
                          "kernel_share_of_step": (kms[0] / dev_ms) if dev_ms else None,
-                         "kernels_ms_per_step": {(KIND_NAMES_AT3P if wl["codec"] == 4 else KIND_NAMES)[k]: kms[k] / max(1, args.steps)
+                         "kernels_ms_per_step": {(KIND_NAMES_AT3P if wl["codec"] == 4 else KIND_NAMES)[k]: kms[k] / max(1, steps)
                                                  for k in range(6) if kcnt[k]}},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": S * F * step * C * 4,
-                    "d2h_bytes_per_step": S * F * units * ub, "ms_per_step": host_ms / args.steps,
-                    "host_and_device_outputs_equal": same, "host_buffers": host_kind},
-            "e2e_i16": {"value": frames_total * args.steps / (host16_ms / 1000.0), "unit": "frames/s",
-                        "h2d_bytes_per_step": S * F * step * C * 2, "d2h_bytes_per_step": S * F * units * ub,
-                        "ms_per_step": host16_ms / args.steps, "outputs_equal_float_path": same16,
-                        "note": "atde_encode_batch_i16: int16 PCM in, converted on the device"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "parity": parity,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": S * F * units * ub, "ms_per_step": host_ms / steps,
+                    "host_and_device_outputs_equal": same, "host_buffers": host_kind,
+                    "h2d_GBps_aggregate": world * h2d / (host_ms / steps / 1000.0) / 1e9,
+                    "host_binding": env.get("binding")},
+            "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_rate(wl, streams_per_core=8 if wl["codec"] == 1 else 4)
-        print(json.dumps(line), flush=True)
+        if with_i16:
+            res["e2e"]["i16"] = {"value": frames_total * steps / (host16_ms / 1000.0), "unit": "frames/s",
+                                 "h2d_bytes_per_step": h2d // 2, "d2h_bytes_per_step": S * F * units * ub,
+                                 "ms_per_step": host16_ms / steps, "outputs_equal_float_path": same16,
+                                 "note": "atde_encode_batch_i16: int16 PCM in (what a WAV file holds), converted on the device"}
+        if collective:
+            res["collective_ms"] = collective
+            res["value_with_collectives"] = frames_total / ((dev_ms / steps + collective["scatter_pcm_ms"] + collective["gather_units_ms"]) / 1000.0)
     enc.close()
+    del d_pcm, d_out, h_out
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_collectives(torch, dist, env, d_pcm, d_units, S):
+    """atracdenc_b200.sharding.scatter_pcm / gather_units over NCCL (NVLink): rank 0 holds the whole job's PCM on its
+    GPU, every rank receives its stream shard, encodes (not timed here), and rank 0 collects the bitstream shards."""
+    from atracdenc_b200 import sharding
+    rank, world = env["rank"], env["world"]
+    dev = d_pcm.device
+    try:
+        full = None
+        if rank == 0:
+            full = torch.empty((world * S,) + tuple(d_pcm.shape[1:]), dtype=d_pcm.dtype, device=dev)
+            for r in range(world):
+                full[r * S:(r + 1) * S].copy_(d_pcm)
+        torch.cuda.synchronize(); dist.barrier()
+        times = []
+        for it in range(3):                                             # first pass warms NCCL's channels up
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            dist.barrier(); torch.cuda.synchronize()
+            e0.record()
+            mine = sharding.scatter_pcm(full, world * S, tuple(d_pcm.shape[1:]), d_pcm.dtype, dev, src=0)
+            e1.record()
+            got = sharding.gather_units(d_units, world * S, dst=0)
+            e2.record()
+            torch.cuda.synchronize(); dist.barrier()
+            times.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
+        t = torch.tensor(times[1:], dtype=torch.float64, device=dev).mean(0)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = torch.tensor([1 if (rank != 0 or bool(torch.equal(mine, d_pcm))) else 0], device=dev)
+        if rank == 0:
+            ok[0] = int(bool(torch.equal(mine, d_pcm)) and tuple(got.shape) == (world * S,) + tuple(d_units.shape[1:])
+                        and bool(torch.equal(got[:S], d_units)))
+        else:
+            full0 = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        sb = (world - 1) * d_pcm.numel() * d_pcm.element_size()
+        gb = (world - 1) * d_units.numel()
+        del full, mine, got
+        torch.cuda.empty_cache()
+        return {"scatter_pcm_ms": float(t[0]), "gather_units_ms": float(t[1]), "scatter_bytes": sb, "gather_bytes": gb,
+                "scatter_GBps_rank0_egress": sb / (float(t[0]) / 1000.0) / 1e9, "gather_GBps_rank0_ingress": gb / max(1e-9, float(t[1]) / 1000.0) / 1e9,
+                "payload_ok": bool(int(ok[0])), "backend": "nccl (torch.distributed send/recv)",
+                "what": "rank 0 -> every rank: its PCM shard; every rank -> rank 0: its bitstream shard (atracdenc_b200/sharding.py)"}
+    except RuntimeError as ex:                                          # e.g. not enough HBM on rank 0 for the whole job's PCM
+        return {"error": str(ex)[:200]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    binding = bind_host_cores(local, world) if not args.no_bind else {"bound_to": None, "why": "--no-bind"}
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    env = {"rank": rank, "world": world, "local": local, "barrier": barrier, "binding": binding,
+           "collectives": not args.no_collectives}
+    if args.verify_only:
+        r = measure_workload(args.workload, args, env, steps=0, warmup=0, verify_stride=args.verify_stride or 8, verify_only=True)
+        if rank == 0:
+            print(json.dumps(r), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    main_res = measure_workload(args.workload, args, env, steps=args.steps, warmup=args.warmup, verify_stride=args.verify_stride)
+    others = {}
+    if args.workload == DEFAULT_WORKLOAD and not args.no_other_workloads and not (args.streams or args.frames):
+        # the other BASELINE.json configs, three timed steps each, so that the driver's record carries them too
+        for name, stride in (("atrac1_stereo_1e6", 64), ("atrac3_lp4_stereo_1p25e6", 16), ("atrac3plus_stereo", 64)):
+            try:
+                r = measure_workload(name, args, env, steps=3, warmup=3, verify_stride=stride if args.verify_stride else 0)
+            except Exception as ex:                                     # never lose the headline line to a side workload
+                r = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"} if rank == 0 else None
+            if rank == 0 and r is not None:
+                if "error" not in r:
+                    r = {"value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                         "workload": r["config"]["workload"], "settings": r["config"]["settings"],
+                         "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "kernel", "kernel_ms", "kernels_ms_per_step")},
+                         "e2e": {k: v for k, v in r["e2e"].items() if k != "host_binding"}, "parity": r["parity"]}
+                others[name] = r
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": main_res["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": main_res["config"], "roofline": main_res["roofline"], "e2e": main_res["e2e"],
+                "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "parity": main_res["parity"]}
+        for k in ("collective_ms", "value_with_collectives"):
+            if k in main_res:
+                line[k] = main_res[k]
+        if others:
+            line["other_workloads"] = others
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_rate(WORKLOADS[args.workload], streams_per_core=8 if WORKLOADS[args.workload]["codec"] == 1 else 4)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -454,6 +590,9 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU (debug)")
     ap.add_argument("--frames", type=int, default=0, help="override frames per stream (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the 3-step passes over the other BASELINE.json configs")
+    ap.add_argument("--no-collectives", action="store_true", help="N > 1: skip the NCCL scatter / gather measurement")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's local cores")
     ap.add_argument("--verify-stride", type=int, default=8,
                     help="parity: every k-th stream of the batch goes through the reference encoder on the host cores "
                          "(default 8: >= 1.2*10^5 frames of the 10^6-frame batches; 1 = every frame; 0 = off)")

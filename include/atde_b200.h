@@ -156,6 +156,29 @@ int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* host_dst, size_t cap
 /* Device-side math self-test hooks (tests only): evaluates the glibc replicas on n inputs. */
 int atde_debug_math(int32_t device, int32_t fn /*0 log10f 1 log2f 2 logf*/, const float* x, float* y, int64_t n);
 
+/*
+ * Multi-GPU in ONE process: a group of encoders, one per device, that shards a batch BY STREAM (the reference's unit
+ * of independence is the encoder instance == stream; frames of one stream never leave a device).
+ * Stream s of an S-stream batch goes to member r with lo(r) <= s < lo(r+1), lo(r) = r*(S/n) + min(r, S%n) —
+ * contiguous ranges whose sizes differ by at most one.  atde_group_encode_batch() runs the members concurrently (one
+ * host thread per device); every device pulls its own shard of `pcm` from host memory over its own PCIe link and
+ * writes its own slice of `out`, so there is no inter-GPU traffic and no collective on the data path.  Layouts,
+ * stream-state and look-ahead semantics are those of atde_encode_batch() (the same S must be used from call to call
+ * until atde_group_reset()).  `devices` may name a device more than once (several members on one GPU).
+ * The reference has no counterpart (it is single-threaded, one encoder per process); this is what a caller that used
+ * to fork one `atracdenc` per file and core calls instead.
+ */
+typedef struct atde_group atde_group;
+int atde_create_group(const atde_settings* s, const int32_t* devices, int32_t n_devices, atde_group** out);
+void atde_destroy_group(atde_group* g);
+int atde_group_size(const atde_group* g);
+int atde_group_encode_batch(atde_group* g, const float* pcm, int32_t n_streams, int64_t n_frames,
+                            uint8_t* out, int32_t* sizes);
+int atde_group_encode_batch_i16(atde_group* g, const int16_t* pcm, int32_t n_streams, int64_t n_frames,
+                                uint8_t* out, int32_t* sizes);
+int64_t atde_group_output_frames(const atde_group* g, int64_t n_frames);
+int atde_group_reset(atde_group* g);
+
 const char* atde_last_error(void);
 const char* atde_version(void);
 

@@ -30,6 +30,7 @@ EXPORTS = [
     "atde_launch_count", "atde_set_profiling", "atde_kernel_times", "atde_debug_tap", "atde_debug_math", "atde_last_error", "atde_version",
     "atde_create_group", "atde_destroy_group", "atde_group_size", "atde_group_encode_batch", "atde_group_encode_batch_i16",
     "atde_group_output_frames", "atde_group_reset",
+    "atde_decoder_create", "atde_decoder_destroy", "atde_decode_batch", "atde_decoder_reset",
 ]
 
 
@@ -87,6 +88,11 @@ def load_library(path: os.PathLike | str | None = None) -> ctypes.CDLL:
     lib.atde_group_output_frames.argtypes = [vp, i64]
     lib.atde_group_output_frames.restype = i64
     lib.atde_group_reset.argtypes = [vp]
+    lib.atde_decoder_create.argtypes = [i32, i32, ctypes.POINTER(vp)]
+    lib.atde_decoder_destroy.argtypes = [vp]
+    lib.atde_decoder_destroy.restype = None
+    lib.atde_decode_batch.argtypes = [vp, vp, i32, i64, vp]
+    lib.atde_decoder_reset.argtypes = [vp]
     lib.atde_last_error.restype = ctypes.c_char_p
     lib.atde_version.restype = ctypes.c_char_p
     return lib
@@ -264,3 +270,35 @@ class EncoderGroup:
     def encode_ptr(self, pcm_ptr: int, n_streams: int, n_frames: int, out_ptr: int, i16: bool = False):
         fn = self.lib.atde_group_encode_batch_i16 if i16 else self.lib.atde_group_encode_batch
         self._check(fn(self.h, pcm_ptr, n_streams, n_frames, out_ptr, None))
+
+
+class Decoder:
+    """ATRAC1 decoder handle (atde_decoder_create): sound units [S][F][C][212] -> PCM [S][F*512][C]."""
+
+    def __init__(self, channels: int, device: int = 0, lib: ctypes.CDLL | None = None):
+        self.lib = lib or load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.atde_decoder_create(channels, device, ctypes.byref(h))
+        if rc < 0:
+            raise AtdeError(f"atde error {rc}: {self.lib.atde_last_error().decode()}")
+        self.h, self.channels = h, channels
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.atde_decoder_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self):
+        self.lib.atde_decoder_reset(self.h)
+
+    def decode(self, units: np.ndarray, n_streams: int) -> np.ndarray:
+        units = np.ascontiguousarray(units, dtype=np.uint8)
+        F = units.size // (n_streams * self.channels * 212)
+        assert F * n_streams * self.channels * 212 == units.size, "whole sound units only"
+        pcm = np.empty((n_streams, F * 512, self.channels), dtype=np.float32)
+        rc = self.lib.atde_decode_batch(self.h, units.ctypes.data, n_streams, F, pcm.ctypes.data)
+        if rc < 0:
+            raise AtdeError(f"atde error {rc}: {self.lib.atde_last_error().decode()}")
+        return pcm

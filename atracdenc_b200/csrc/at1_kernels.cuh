@@ -68,6 +68,31 @@ struct CarryParams {
     int S, C, F;
 };
 
+// ---- decoder (at1_decode.cu) ----
+struct DecTables {
+    float sine_window[32];       // atrac1.h:128-132
+    float scale_table[64];       // atrac1.h:122-127
+    float qmf_window[48];        // QmfWindow, qmf.cpp:36-45
+    float isincos512[256];       // TMIDCT<512>(512 * 2): CalcSinCos(512, 512)
+    float isincos256[128];       // TMIDCT<256>(256 * 2)
+    float isincos64[32];         // TMIDCT<64>(64 * 2)
+    cpx tw128[128], tw64[64], tw16[16];          // forward kissfft twiddles (TMDCTBase always plans a forward FFT)
+    unsigned char perm128[128], perm64[64], perm16[16];
+};
+
+struct DecodeParams {
+    const unsigned char* units;      // [S][F][C][212] sound units
+    const unsigned char* hist;       // [S][C][212] last sound unit of the previous batch
+    const unsigned char* started;    // [S] non-zero: `hist` is valid
+    unsigned char* hist_out;         // staging for the carry (may equal hist: written after the decode kernel)
+    unsigned char* started_out;
+    float* pcm;                      // [S][F*512][C] interleaved, clipped to [-1, 1]
+    int* status;                     // bit 0: a frame used a block-size code this decoder refuses
+    const DecTables* tab;
+    int S, C, F;
+};
+void launch_decode(const DecodeParams& p, cudaStream_t st);
+
 void upload_qmf_window(const float w[48]);
 void launch_analysis(const AnalysisParams& p, cudaStream_t st);
 void launch_loudness(const LoudnessParams& p, cudaStream_t st);

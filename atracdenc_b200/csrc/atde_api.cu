@@ -885,6 +885,115 @@ int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* dst, size_t capacity
     return (int64_t)bytes;
 }
 
+// ---- ATRAC1 decoder ----
+struct atde_decoder {
+    int channels = 0, device = 0;
+    atde::at1::DecTables* d_tab = nullptr;
+    DevBuf<unsigned char> units, hist, started;
+    DevBuf<float> pcm;
+    DevBuf<int> status;
+    int n_state_streams = 0;
+    cudaStream_t stream = nullptr;
+};
+
+int atde_decoder_create(int32_t channels, int32_t device, atde_decoder** out)
+{
+    using namespace atde;
+    if (!out) return fail(ATDE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (channels < 1 || channels > 2) return fail(ATDE_ERR_INVALID, "channels must be 1 or 2");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(ATDE_ERR_CUDA, "no CUDA device: libatde_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    atde_decoder* d = new (std::nothrow) atde_decoder();
+    at1::DecTables* h = new (std::nothrow) at1::DecTables();
+    if (!d || !h) { delete d; delete h; return fail(ATDE_ERR_NOMEM, "host alloc"); }
+    d->channels = channels; d->device = device;
+    memset(h, 0, sizeof(*h));
+    qmf_window(h->qmf_window);
+    for (uint32_t i = 0; i < 32; i++) h->sine_window[i] = sin((i + 0.5) * (M_PI / (2.0 * 32.0)));      // atrac1.h:128-132
+    for (uint32_t i = 0; i < 64; i++) h->scale_table[i] = pow(2.0, (double)(i / 3.0 - 21.0));         // atrac1.h:122-127
+    // TMIDCT<N>(N * 2) -> TMDCTBase(N, N) -> CalcSinCos(N, N) (atrac1denc.h:52-54, mdct.h:111-114)
+    const std::vector<float> s512 = mdct_sincos(512, 512.0f), s256 = mdct_sincos(256, 256.0f), s64 = mdct_sincos(64, 64.0f);
+    memcpy(h->isincos512, s512.data(), sizeof(h->isincos512));
+    memcpy(h->isincos256, s256.data(), sizeof(h->isincos256));
+    memcpy(h->isincos64, s64.data(), sizeof(h->isincos64));
+    const auto tw128 = kiss_twiddles(128, false), tw64 = kiss_twiddles(64, false), tw16 = kiss_twiddles(16, false);
+    memcpy(h->tw128, tw128.data(), sizeof(h->tw128));
+    memcpy(h->tw64, tw64.data(), sizeof(h->tw64));
+    memcpy(h->tw16, tw16.data(), sizeof(h->tw16));
+    const auto p128 = kiss_perm(128), p64 = kiss_perm(64), p16 = kiss_perm(16);
+    for (int i = 0; i < 128; i++) h->perm128[i] = (unsigned char)p128[i];
+    for (int i = 0; i < 64; i++) h->perm64[i] = (unsigned char)p64[i];
+    for (int i = 0; i < 16; i++) h->perm16[i] = (unsigned char)p16[i];
+    cudaError_t ce = cudaMalloc(&d->d_tab, sizeof(at1::DecTables));
+    if (ce == cudaSuccess) ce = cudaMemcpy(d->d_tab, h, sizeof(at1::DecTables), cudaMemcpyHostToDevice);
+    delete h;
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { atde_decoder_destroy(d); return fail(ATDE_ERR_CUDA, "decoder setup failed: %s", cudaGetErrorString(ce)); }
+    *out = d;
+    return 0;
+}
+
+void atde_decoder_destroy(atde_decoder* d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+    d->units.release(); d->hist.release(); d->started.release(); d->pcm.release(); d->status.release();
+    if (d->d_tab) cudaFree(d->d_tab);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int atde_decoder_reset(atde_decoder* d)
+{
+    if (!d) return fail(ATDE_ERR_INVALID, "null handle");
+    d->n_state_streams = 0;
+    return 0;
+}
+
+int atde_decode_batch(atde_decoder* d, const uint8_t* units, int32_t S, int64_t F, float* pcm)
+{
+    using namespace atde::at1;
+    if (!d || !units || !pcm) return fail(ATDE_ERR_INVALID, "null argument");
+    if (S <= 0 || F <= 0 || F > (1 << 21)) return fail(ATDE_ERR_INVALID, "bad batch (S=%d, F=%lld)", S, (long long)F);
+    CK(cudaSetDevice(d->device));
+    const int C = d->channels;
+    if (d->n_state_streams && d->n_state_streams != S)
+        return fail(ATDE_ERR_INVALID, "batch has %d streams but the handle carries state for %d; call atde_decoder_reset() first", S, d->n_state_streams);
+    int rc;
+    const size_t n_units = (size_t)S * F * C;
+    if ((rc = d->units.ensure(n_units * kUnitBytes))) return rc;
+    if ((rc = d->pcm.ensure(n_units * 512))) return rc;
+    if ((rc = d->status.ensure(1))) return rc;
+    if (!d->n_state_streams) {
+        if ((rc = d->hist.ensure((size_t)S * C * kUnitBytes))) return rc;
+        if ((rc = d->started.ensure(S))) return rc;
+        CK(cudaMemsetAsync(d->started.p, 0, S, d->stream));
+    }
+    CK(cudaMemsetAsync(d->status.p, 0, sizeof(int), d->stream));
+    CK(cudaMemcpyAsync(d->units.p, units, n_units * kUnitBytes, cudaMemcpyHostToDevice, d->stream));
+    DecodeParams p;
+    p.units = d->units.p; p.hist = d->hist.p; p.started = d->started.p;
+    p.hist_out = d->hist.p; p.started_out = d->started.p;
+    p.pcm = d->pcm.p; p.status = d->status.p; p.tab = d->d_tab;
+    p.S = S; p.C = C; p.F = (int)F;
+    launch_decode(p, d->stream);
+    CK(cudaGetLastError());
+    int status = 0;
+    CK(cudaMemcpyAsync(pcm, d->pcm.p, n_units * 512 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaMemcpyAsync(&status, d->status.p, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    d->n_state_streams = S;
+    if (status & 1) {
+        d->n_state_streams = 0;
+        return fail(ATDE_ERR_UNSUPPORTED, "a sound unit uses a block-size code the reference encoder never writes (partial short-block modes)");
+    }
+    return 0;
+}
+
 // ---- encoder groups: one member per device, streams sharded contiguously, members run concurrently ----
 struct atde_group {
     std::vector<atde_encoder*> members;

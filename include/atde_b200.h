@@ -179,6 +179,23 @@ int atde_group_encode_batch_i16(atde_group* g, const int16_t* pcm, int32_t n_str
 int64_t atde_group_output_frames(const atde_group* g, int64_t n_frames);
 int atde_group_reset(atde_group* g);
 
+/*
+ * ATRAC1 decoder (the step after the encode path): what TAtrac1Decoder's frame lambda writes
+ * (src/atrac1denc.cpp:139-177 — dequantise, IMDCT, QMF synthesis, clip to [-1, 1], interleave), for S streams x F
+ * frames at once, bit-exact.
+ *   units [S][F][channels][212] sound units in ICompressedInput::ReadFrame order (channel 0 first, src/aea.cpp)
+ *   pcm   [S][F*512][channels]  interleaved float, the layout the lambda fills (data[i*channels + ch])
+ * Streams continue across calls (same S) until atde_decoder_reset().  A unit the reference would reject (negative
+ * block-size code, mantissas running past the unit) decodes as silence, as there.  Block-size codes the reference
+ * encoder never writes (2-of-4 / 2- or 4-of-8 short blocks), for which the reference decoder reads stale buffer
+ * contents, are refused: ATDE_ERR_UNSUPPORTED.
+ */
+typedef struct atde_decoder atde_decoder;
+int atde_decoder_create(int32_t channels, int32_t device, atde_decoder** out);
+void atde_decoder_destroy(atde_decoder* d);
+int atde_decode_batch(atde_decoder* d, const uint8_t* units, int32_t n_streams, int64_t n_frames, float* pcm);
+int atde_decoder_reset(atde_decoder* d);
+
 const char* atde_last_error(void);
 const char* atde_version(void);
 

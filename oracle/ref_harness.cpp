@@ -19,6 +19,8 @@
  * scale factor indices) for bisecting a parity failure.
  */
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -275,6 +277,49 @@ void ref_kiss_fftri(int n, const float* in_ri /* n/2+1 complex */, float* out)
 }
 
 /* libm taps: the exact functions the reference resolves to on this box */
+/* ATRAC1 decoder (src/atrac1denc.cpp:139-177): TAtrac1Decoder's lambda driven frame by frame over in-memory sound
+ * units [F][C][212]; pcm receives what the lambda writes, [F*512][C] interleaved. */
+namespace {
+class TMemInput : public ICompressedInput {
+    const unsigned char* Units;
+    long Count, Pos = 0;
+    size_t Ch;
+public:
+    TMemInput(const unsigned char* u, long count, size_t ch) : Units(u), Count(count), Ch(ch) {}
+    std::unique_ptr<TFrame> ReadFrame() override {
+        std::unique_ptr<TFrame> f(new TFrame(212));
+        if (Pos < Count) memcpy(f->Get(), Units + 212 * Pos, 212); else memset(f->Get(), 0, 212);
+        Pos++;
+        return f;
+    }
+    uint64_t GetLengthInSamples() const override { return (uint64_t)(Count / (long)Ch) * 512; }
+    std::string GetName() const override { return "mem"; }
+    size_t GetChannelNum() const override { return Ch; }
+};
+} // namespace
+
+long ref_at1_decode(int channels, const unsigned char* units, long n_frames, float* pcm)
+{
+    try {
+        TCompressedInputPtr in(new TMemInput(units, n_frames * channels, channels));
+        /* TAtrac1Decoder leaves its overlap buffers PcmBufLow/Mid/Hi uninitialised (src/atrac1denc.h:112-114); the
+         * CLI allocates it with `new` on a fresh heap, i.e. in zero pages.  Give it zeroed storage here too, so that
+         * the oracle does not depend on what happens to lie on the stack. */
+        void* mem = calloc(1, sizeof(TAtrac1Decoder));
+        TAtrac1Decoder* dec = new (mem) TAtrac1Decoder(std::move(in));
+        {
+            auto lambda = dec->GetLambda();
+            TPCMEngine::ProcessMeta meta = {(uint16_t)channels};
+            for (long f = 0; f < n_frames; f++) lambda(pcm + (size_t)f * 512 * channels, meta);
+        }
+        dec->~TAtrac1Decoder();
+        free(mem);
+        return n_frames;
+    } catch (...) {
+        return -1;
+    }
+}
+
 float ref_log10f(float x) { return log10f(x); }
 float ref_log2f(float x) { return log2f(x); }
 double ref_log(double x) { return log(x); }

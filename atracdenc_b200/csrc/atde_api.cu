@@ -95,7 +95,8 @@ struct atde_encoder {
     atde::at3p::StreamState* at3p = nullptr;    // ATRAC3plus: carried stream state + workspaces (at3p_pipeline.cu)
     // ATRAC3 stream state beyond hist / loud_state / started
     DevBuf<float> prevhalf, next_scale, ctx;
-    Workspace ws[2];
+    static constexpr int kSlots = 3;   // pipeline slots of the host path: chunk k+2 is copied in while k+1 waits and k computes
+    Workspace ws[kSlots];
     // stream state, sized for n_state_streams
     DevBuf<float> hist;
     DevBuf<float> loud_state;
@@ -593,7 +594,7 @@ int atde_create(const atde_settings* s, atde_encoder** out)
         e->lookahead = 1;
         e->at3_js = cont->js;
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < atde_encoder::kSlots; i++) {
         cudaError_t ce = cudaStreamCreateWithFlags(&e->ws[i].stream, cudaStreamNonBlocking);
         if (ce != cudaSuccess) { delete e; return fail(ATDE_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
     }
@@ -611,7 +612,7 @@ void atde_destroy(atde_encoder* e)
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < atde_encoder::kSlots; i++) {
         e->ws[i].release();
         if (e->ws[i].stream) cudaStreamDestroy(e->ws[i].stream);
     }
@@ -653,8 +654,7 @@ int64_t atde_output_frames(const atde_encoder* e, int64_t n_frames)
 int atde_sync(atde_encoder* e)
 {
     if (!e) return fail(ATDE_ERR_INVALID, "null handle");
-    CK(cudaStreamSynchronize(e->ws[0].stream));
-    CK(cudaStreamSynchronize(e->ws[1].stream));
+    for (int i = 0; i < atde_encoder::kSlots; i++) CK(cudaStreamSynchronize(e->ws[i].stream));
     return 0;
 }
 
@@ -761,8 +761,7 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     // leaves the carried stream state half advanced: drain both pipeline slots and invalidate the state
     // (the next batch needs atde_reset()).
     auto bail = [&](int code) {
-        cudaStreamSynchronize(e->ws[0].stream);
-        cudaStreamSynchronize(e->ws[1].stream);
+        for (int i = 0; i < atde_encoder::kSlots; i++) cudaStreamSynchronize(e->ws[i].stream);
         e->have_state = false;
         e->n_state_streams = 0;
         e->streams_started = false;
@@ -776,7 +775,8 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
             return bail(fail(ATDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
     } while (0)
     int slot = 0;
-    for (int s0 = 0, n = first; s0 < S; s0 += n, n = chunk, slot ^= 1) {
+    const int n_slots = at3p ? 2 : atde_encoder::kSlots;      // (the ATRAC3plus pipeline keeps two work areas)
+    for (int s0 = 0, n = first; s0 < S; s0 += n, n = chunk, slot = (slot + 1) % n_slots) {
         if (n > S - s0) n = S - s0;
         Workspace& w = e->ws[slot];
         if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) return bail(rc);
@@ -809,8 +809,7 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
             CKB(cudaMemcpyAsync(sizes + (size_t)s0 * units_per_stream, w.sizes.p, (size_t)n * units_per_stream * sizeof(int),
                                cudaMemcpyDeviceToHost, w.stream));
     }
-    CK(cudaStreamSynchronize(e->ws[0].stream));
-    CK(cudaStreamSynchronize(e->ws[1].stream));
+    for (int i = 0; i < atde_encoder::kSlots; i++) CK(cudaStreamSynchronize(e->ws[i].stream));
 #undef CKB
     if (sizes && at3)                                  // every WriteFrame payload is exactly FrameSz bytes
         for (size_t i = 0; i < (size_t)S * units_per_stream; i++) sizes[i] = e->unit_bytes;

@@ -154,10 +154,6 @@ ATDE_D int scale_analyse(const DevTables* T, const float* v, int len, float& ene
 // =====================================================================================
 constexpr int kScaleWarps = 4;
 
-// Padded index of the per-line log table: lanes 8..28 walk their BFUs (16 / 32 / 64 lines apart) in lock step,
-// which without padding puts up to ten doubles of one access into the same bank (38 % of the kernel's
-// shared-memory wavefronts, ncu v6); one pad per 16 and one per 256 leaves 1.25 wavefronts per access.
-ATDE_D int lgp(int p) { return p + (p >> 4) + (p >> 8); }
 
 __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geometry g, Buffers b)
 {
@@ -165,7 +161,7 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
     __shared__ float run_val[kScaleWarps][32][5];
     __shared__ short run_start[kScaleWarps][32];
     __shared__ signed char run_len[kScaleWarps][32];
-    __shared__ double lg_all[kScaleWarps][688];         // 640 logs, padded: see lgp()
+    __shared__ double lg_all[kScaleWarps][64];          // logs of the lines of the BFU under exact evaluation
 
     const DevTables* __restrict__ T = b.tab;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -181,39 +177,66 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
     const int start = kBlockStart[lane], len = kBlockStart[lane + 1] - kBlockStart[lane];
     TonalList* tl = b.tonal + unit;
     if (!g.no_tonal) {
-        // CalcSpectralFlatnessPerBfu: geometric / arithmetic mean of the line energies, in double.
-        // The logs of the 640 lines of BFUs 8..28 are taken line-parallel; the two sums stay sequential.
+        // CalcSpectralFlatnessPerBfu: geometric / arithmetic mean of the line energies, in double, compared with 0.01
+        // (atrac3denc.cpp:586-590) — the value itself is used for nothing else.  Nearly every BFU is far from tonal
+        // (flatness ~0.5), so each BFU is first screened with plain fp32 and the hardware log2 (error of the screen
+        // ~1e-3 relative, generously): above 0.0125 the exact value cannot be below 0.01.  Only the BFUs the screen
+        // cannot clear take the reference's arithmetic: per-line double logs (glibc's log, line-parallel over the warp),
+        // the two sequential double sums, glibc's exp.
         const double floor_d = (double)1e-12f;
-        double* lg = lg_all[wib];
-        for (int i = 64 + lane; i < 704; i += 32) {
-            const float ef = fmul(sv[i], sv[i]);
-            const double e = (double)fmaxf(0.0f, ef);
-            lg[lgp(i - 64)] = g_log(e > floor_d ? e : floor_d);
-        }
-        __syncwarp();
+        bool maybe = false;
         if (lane >= 8 && lane < 29) {
-            double arith = 0.0, mean_log = 0.0;
-            // (these BFUs are 16, 32 or 64 lines long; one 16-byte load per four lines: the lanes' lines are 16 / 32 /
-            // 64 floats apart, so scalar loads would take nine shared-memory wavefronts each)
+            float aa = 0.0f, al = 0.0f;
             for (int i = 0; i < len; i += 4) {
                 const float4 q = *reinterpret_cast<const float4*>(sv + start + i);
                 const float x[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const float ef = fmul(x[k], x[k]);
-                    const double e = (double)fmaxf(0.0f, ef);
-                    arith = __dadd_rn(arith, e);
-                    mean_log = __dadd_rn(mean_log, lg[lgp(start - 64 + i + k)]);
+                    const float ef = x[k] * x[k];
+                    aa += ef;
+                    al += __log2f(fmaxf(ef, 1e-12f));
                 }
             }
-            arith = __ddiv_rn(arith, (double)len);
-            mean_log = __ddiv_rn(mean_log, (double)len);
-            float flat = 1.0f;
-            if (!(arith <= floor_d)) {
-                const double ratio = __ddiv_rn(g_exp(mean_log), arith);
-                const double cl = ratio < 0.0 ? 0.0 : (ratio > 1.0 ? 1.0 : ratio);   // min(1, max(0, ratio))
-                flat = __double2float_rn(cl);
+            const float A = aa / (float)len;
+            // near the energy floor (where the reference returns 1.0) or not clearly flat: the exact path decides
+            maybe = !(A > 4e-12f) || !(exp2f(al / (float)len) > 0.0125f * A);
+        }
+        double* lg = lg_all[wib];
+        float flat = 1.0f;
+        for (unsigned mm = __ballot_sync(0xffffffffu, maybe); mm; mm &= mm - 1) {
+            const int bf = __ffs((int)mm) - 1;
+            const int b0 = kBlockStart[bf], bl = kBlockStart[bf + 1] - b0;
+            __syncwarp();
+            for (int i = lane; i < bl; i += 32) {
+                const float ef = fmul(sv[b0 + i], sv[b0 + i]);
+                const double e = (double)fmaxf(0.0f, ef);
+                lg[i] = g_log(e > floor_d ? e : floor_d);
             }
+            __syncwarp();
+            if (lane == bf) {
+                double arith = 0.0, mean_log = 0.0;
+                for (int i = 0; i < len; i += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(sv + start + i);
+                    const float x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float ef = fmul(x[k], x[k]);
+                        const double e = (double)fmaxf(0.0f, ef);
+                        arith = __dadd_rn(arith, e);
+                        mean_log = __dadd_rn(mean_log, lg[i + k]);
+                    }
+                }
+                arith = __ddiv_rn(arith, (double)len);
+                mean_log = __ddiv_rn(mean_log, (double)len);
+                if (!(arith <= floor_d)) {
+                    const double ratio = __ddiv_rn(g_exp(mean_log), arith);
+                    const double cl = ratio < 0.0 ? 0.0 : (ratio > 1.0 ? 1.0 : ratio);   // min(1, max(0, ratio))
+                    flat = __double2float_rn(cl);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane >= 8 && lane < 29) {
             if (flat < 0.01f) {
                 // ExtractTonalComponents: best run of <= 5 lines by summed magnitude
                 const int max_len = min(5, len);

@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kPackWarps * 32) at1_pack_kernel(PackParams p)
         for (;;) {
             const bool exhausted = mx <= mn;
             const float shift = exhausted ? last
-                                          : __double2float_rn(__ddiv_rn((double)fadd(mx, mn), 2.0));
+                                          : __double2float_rn(__dmul_rn((double)fadd(mx, mn), 0.5));   // (max + min) / 2.0: halving is exact
             cur = shift;
             unsigned my_bits = 0;
             for (int h = 0; h < 2; h++) {

@@ -190,23 +190,35 @@ __global__ void __launch_bounds__(256, 4) at3_qmf_kernel(Geometry g, Buffers b)
         qmf_task(s1[ch][which], cw, task, one, lo, hi);
         float* ol = outb + (ch * 4 + (which ? 3 : 0)) * kQT + kQR * task;
         float* oh = outb + (ch * 4 + (which ? 2 : 1)) * kQT + kQR * task;
-#pragma unroll
-        for (int r = 0; r < kQR; r++) { ol[r] = lo[r]; oh[r] = hi[r]; }
+        static_assert(kQR == 8 && (kQT * 4) % 16 == 0, "two 16-byte stores per task and row");
+        reinterpret_cast<float4*>(ol)[0] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        reinterpret_cast<float4*>(ol)[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+        reinterpret_cast<float4*>(oh)[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        reinterpret_cast<float4*>(oh)[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
     }
     __syncthreads();
-    const int nvalid = min(kQT, g.BL - u0);
-    ATDE_PAR_FOR(w, 4 * kQT) {
-        const int band = w / kQT, q = w - band * kQT;
-        if (q < nvalid) {
-            if (g.js) {
-                const float l = outb[band * kQT + q], r = outb[(4 + band) * kQT + q];
-                b.bands[(((size_t)s * 2 + 0) * 4 + band) * g.BL + u0 + q] = fmul(fadd(l, r), 0.5f);
-                b.bands[(((size_t)s * 2 + 1) * 4 + band) * g.BL + u0 + q] = fmul(fsub(l, r), 0.5f);
-            } else {
-                for (int c = 0; c < g.C; c++)
-                    b.bands[(((size_t)s * g.C + c) * 4 + band) * g.BL + u0 + q] = outb[(c * 4 + band) * kQT + q];
-            }
+    if (g.js) {
+        // Matrixing (atrac3denc.cpp:665-677): (L + R) / 2, (L - R) / 2, in place in the output tile
+        ATDE_PAR_FOR(w, kQT) {                                    // 4 bands x kQT samples = kQT float4 columns
+            const int band = w / (kQT / 4), q4 = w - band * (kQT / 4);
+            float4* pl = reinterpret_cast<float4*>(outb + band * kQT) + q4;
+            float4* pr = reinterpret_cast<float4*>(outb + (4 + band) * kQT) + q4;
+            const float4 l = *pl, r = *pr;
+            *pl = make_float4(fmul(fadd(l.x, r.x), 0.5f), fmul(fadd(l.y, r.y), 0.5f), fmul(fadd(l.z, r.z), 0.5f), fmul(fadd(l.w, r.w), 0.5f));
+            *pr = make_float4(fmul(fsub(l.x, r.x), 0.5f), fmul(fsub(l.y, r.y), 0.5f), fmul(fsub(l.z, r.z), 0.5f), fmul(fsub(l.w, r.w), 0.5f));
         }
+    }
+    // The eight (channel, band) rows of the tile leave by bulk asynchronous copies (1-D TMA): rows are 16-byte aligned
+    // on both sides (kQT * 4 and BL * 4 are multiples of 16) and so is the length of a last, shorter tile.
+    async_proxy_fence();
+    __syncthreads();
+    if (tid == 0) {
+        const int nvalid = min(kQT, g.BL - u0);
+        for (int c = 0; c < g.C; c++)
+            for (int band = 0; band < 4; band++)
+                bulk_s2g(b.bands + (((size_t)s * g.C + c) * 4 + band) * g.BL + u0, outb + (c * 4 + band) * kQT, (unsigned)nvalid * 4u);
+        bulk_store_commit();
+        bulk_store_wait_read();                                  // shared memory is released when the block retires
     }
 }
 

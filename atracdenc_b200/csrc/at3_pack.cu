@@ -438,15 +438,13 @@ ATDE_D int elem_bfu(int i)
     if (i < 768) return 26 + ((i - 512) >> 6);
     return 30 + ((i - 768) >> 7);
 }
-// BFU of line 32 r + lane: the row index is warp-uniform, so the branches are too
-ATDE_D int row_bfu(int r, int lane)
-{
-    if (r < 2) return 4 * r + (lane >> 3);
-    if (r < 6) return 4 + 2 * r + (lane >> 4);
-    if (r < 16) return 10 + r;
-    if (r < 24) return 26 + ((r - 16) >> 1);
-    return 30 + ((r - 24) >> 2);
-}
+// BFU of line 32 r + lane = kRowBase[r] + (lane >> kRowShift[r]): rows 0-1 hold four 8-line BFUs, rows 2-5 two 16-line
+// BFUs, every later row lies inside one BFU.  (Constant-bank tables: the row index is warp-uniform.)
+__constant__ unsigned char kRowBase[32] = {0, 4, 8, 10, 12, 14, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25,
+                                           26, 26, 27, 27, 28, 28, 29, 29, 30, 30, 30, 30, 31, 31, 31, 31};
+__constant__ unsigned char kRowShift[32] = {3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5,
+                                            5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5};
+ATDE_D int row_bfu(int r, int lane) { return kRowBase[r] + (lane >> kRowShift[r]); }
 ATDE_D unsigned row_bfu_mask(int r)
 {
     if (r < 2) return 0xFu << (4 * r);
@@ -925,7 +923,7 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
             if (lane == 0) g_stats[4]++;
 #endif
             const bool exhausted = mx <= mn;
-            const float shift = exhausted ? last : __double2float_rn(__ddiv_rn((double)fadd(mx, mn), 2.0));
+            const float shift = exhausted ? last : __double2float_rn(__dmul_rn((double)fadd(mx, mn), 0.5));   // (max + min) / 2.0: halving is exact
             // CalcBitsAllocation (:272-336)
             prec = 0;
             if (lane < num_bfu && audible) {

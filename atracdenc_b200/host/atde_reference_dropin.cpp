@@ -6,6 +6,7 @@
 //     TAtrac1Encoder::TAtrac1Encoder / GetLambda               src/atrac1denc.h:105-106,  src/atrac1denc.cpp:60-68,180-254
 //     TAtrac3Encoder::TAtrac3Encoder / ~TAtrac3Encoder / GetLambda   src/atrac3denc.h:131-133,  src/atrac3denc.cpp:93-106,694-866
 //     TAt3PEnc::TAt3PEnc / GetLambda / ParseAdvancedOpt / TImpl      src/atrac3p.h:59-68,       src/atrac/at3p/at3p.cpp:36-284
+//     TAtrac1Decoder::TAtrac1Decoder / GetLambda               src/atrac1denc.h:109-124,  src/atrac1denc.cpp:46-49,139-177
 // so that src/main.cpp, src/pcmengin.h, the container writers and every header stay byte for byte what they are:
 // main.cpp's `new TAtrac1Encoder(std::move(aeaIO), std::move(encoderSettings))` allocates the reference's class and
 // runs THIS constructor.  The reference's encoder state members (filter banks, delay buffers ...) are constructed
@@ -19,7 +20,8 @@
 //
 // Build: the reference's atrac1denc.cpp / atrac3denc.cpp also hold code this path does not replace (TAtrac1MDCT,
 // TAtrac1Decoder, TAtrac3MDCT); they stay in the build with the encoder class renamed away by a per-file compile
-// definition (-DTAtrac1Encoder=TAtrac1EncoderCpu, -DTAtrac3Encoder=TAtrac3EncoderCpu); at3p.cpp is dropped.
+// definition (-DTAtrac1Encoder=TAtrac1EncoderCpu -DTAtrac1Decoder=TAtrac1DecoderCpu, -DTAtrac3Encoder=TAtrac3EncoderCpu);
+// at3p.cpp is dropped.
 #ifndef ATDE_USE_REFERENCE_HEADERS
 #error "atde_reference_dropin.cpp is built inside the atracdenc tree: define ATDE_USE_REFERENCE_HEADERS and put src/ on the include path"
 #endif
@@ -31,8 +33,11 @@
 
 #include "atde_batcher.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <exception>
 #include <iostream>
 
 namespace NAtracDEnc {
@@ -108,7 +113,88 @@ TPCMEngine::TProcessLambda MakeLambda(ICompressedOutput* member)
     return [d](float* data, const TPCMEngine::ProcessMeta& /*meta*/) { return d->Push(data); };
 }
 
+// The decoder side: the container as TAtrac1Decoder sees it.  The reference's lambda reads one sound unit per channel
+// per call and decodes it on the spot; here the units are read AHEAD in batches, decoded on the GPU
+// (atde_decode_batch) and handed out frame by frame.  A read error (the CLI's frame loop runs past the end of some
+// files, src/main.cpp:697-705 with pcmengin.h's 4096-sample buffer) is kept and rethrown by the call that would have
+// hit it in the reference.
+class TPrefetchInput : public ICompressedInput {
+public:
+    explicit TPrefetchInput(TCompressedInputPtr&& real)
+        : Real(std::move(real))
+        , Channels((int)Real->GetChannelNum())
+    {
+        if (atde_decoder_create(Channels, 0, &Dec) < 0)
+            throw std::runtime_error(std::string("atde_b200: ") + atde_last_error());
+        if (const char* env = getenv("ATDE_BATCH_FRAMES")) {
+            const long v = atol(env);
+            if (v > 0) BatchFrames = (size_t)v;
+        }
+    }
+    ~TPrefetchInput() override { atde_decoder_destroy(Dec); }
+    std::unique_ptr<TFrame> ReadFrame() override { return Real->ReadFrame(); }
+    uint64_t GetLengthInSamples() const override { return Real->GetLengthInSamples(); }
+    std::string GetName() const override { return Real->GetName(); }
+    size_t GetChannelNum() const override { return Real->GetChannelNum(); }
+
+    TPCMEngine::EProcessResult Next(float* data)
+    {
+        if (Served == Ready) Refill();
+        memcpy(data, &Pcm[Served * 512 * Channels], sizeof(float) * 512 * Channels);
+        Served++;
+        return TPCMEngine::EProcessResult::PROCESSED;
+    }
+
+private:
+    void Refill()
+    {
+        if (Pending) std::rethrow_exception(Pending);
+        // read ahead only inside the length the container announces (the caller decodes at least that much: src/main.cpp:351,
+        // 697-705); beyond it, one frame per call like the reference, so that no read happens that it would not do
+        const uint64_t announced = Real->GetLengthInSamples() / 512;
+        size_t want = Consumed < announced ? (size_t)std::min<uint64_t>(BatchFrames, announced - Consumed) : 1;
+        Units.resize(want * Channels * 212);
+        size_t frames = 0;
+        try {
+            for (; frames < want; frames++)
+                for (int ch = 0; ch < Channels; ch++) {
+                    std::unique_ptr<TFrame> f(Real->ReadFrame());
+                    memcpy(&Units[(frames * Channels + ch) * 212], f->Get(), 212);
+                }
+        } catch (...) {
+            Pending = std::current_exception();      // the frames read so far are still delivered first
+        }
+        if (frames == 0) std::rethrow_exception(Pending);
+        Pcm.resize(frames * 512 * Channels);
+        if (atde_decode_batch(Dec, Units.data(), 1, (int64_t)frames, Pcm.data()) < 0)
+            throw std::runtime_error(std::string("atde_b200: ") + atde_last_error());
+        Served = 0;
+        Ready = frames;
+        Consumed += frames;
+    }
+    TCompressedInputPtr Real;
+    int Channels;
+    atde_decoder* Dec = nullptr;
+    std::vector<uint8_t> Units;
+    std::vector<float> Pcm;
+    size_t Served = 0, Ready = 0, BatchFrames = 1024;
+    uint64_t Consumed = 0;
+    std::exception_ptr Pending;
+};
+
 } // namespace
+
+// ---- ATRAC1 decoder (src/atrac1denc.h:109-124) ----
+TAtrac1Decoder::TAtrac1Decoder(TCompressedInputPtr&& aea)
+    : Aea(new TPrefetchInput(std::move(aea)))
+{
+}
+
+TPCMEngine::TProcessLambda TAtrac1Decoder::GetLambda()
+{
+    TPrefetchInput* in = static_cast<TPrefetchInput*>(Aea.get());
+    return [in](float* data, const TPCMEngine::ProcessMeta& /*meta*/) { return in->Next(data); };
+}
 
 // ---- ATRAC1 (src/atrac1denc.h:57-107) ----
 TAtrac1Encoder::TAtrac1Encoder(TCompressedOutputPtr&& aea, NAtrac1::TAtrac1EncodeSettings&& settings)

@@ -106,6 +106,39 @@ def test_dropin_small_batches_and_errors(tmp_path):
     assert r2.returncode == r3.returncode == 1 and "unexpected end of key token" in r2.stderr and "unexpected end of key token" in r3.stderr
 
 
+def run_decode_pair(ref, got, tmp_path, seconds, env=None):
+    """`atracdenc -d`: both programs decode the same .aea (written by the reference CLI) to a WAV."""
+    for k, C in enumerate((2, 1)):
+        n = int(44100 * seconds) + 111 * k
+        wav = tmp_path / f"dsrc{k}.wav"
+        write_wav(wav, tl.synth_rich((n + 511) // 512, 512, C, seed=500 + k)[:n])
+        aea = tmp_path / f"d{k}.aea"
+        r = subprocess.run([str(ref), "-e", "atrac1", "-i", str(wav), "-o", str(aea), "--nostdout"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-400:]
+        outs = []
+        for exe, tag in ((ref, "ref"), (got, "got")):
+            out = tmp_path / f"dec_{tag}{k}.wav"
+            r = subprocess.run([str(exe), "-d", "-i", str(aea), "-o", str(out), "--nostdout"], capture_output=True, text=True,
+                               env=env, timeout=600)
+            outs.append((r.returncode, out.read_bytes()))
+        assert outs[0][0] == outs[1][0], (outs[0][0], outs[1][0])
+        assert len(outs[0][1]) > 4096 and outs[0][1] == outs[1][1], f"decoded WAVs differ ({C} channels)"
+
+
+def test_dropin_cli_decode_emulated(tmp_path):
+    import os
+    ref, got = _binaries("emu")
+    run_decode_pair(ref, got, tmp_path, seconds=0.3)
+    (tmp_path / "b").mkdir()
+    run_decode_pair(ref, got, tmp_path / "b", seconds=0.2, env=dict(os.environ, ATDE_BATCH_FRAMES="5"))
+
+
+@pytest.mark.gpu
+def test_dropin_cli_decode_gpu(tmp_path, gpu_lib):
+    ref, got = _binaries("gpu")
+    run_decode_pair(ref, got, tmp_path, seconds=4.0)
+
+
 def test_dropin_has_no_undefined_encoder_symbols():
     _, got = _binaries("emu")
     nm = subprocess.check_output(["nm", "-C", "--undefined-only", str(got)], text=True)

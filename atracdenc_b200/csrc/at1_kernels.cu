@@ -82,14 +82,6 @@ struct BandView {
     int size;            // 128 / 128 / 256
 };
 
-// HPF input sample: band sample k (k may reach -20 into the previous frame), spectrum-inverted for the mid/hi bands
-// (InvertSpectr, util.h:51-63: even indices negated).  `flip` is the sign-bit mask of the EVEN samples (0 for the low
-// band); negation is exact, so flipping the bit equals the reference's multiplication by -1.
-ATDE_D float hpf_in(const float* band0, int k, unsigned flip)
-{
-    return __uint_as_float(__float_as_uint(band0[k]) ^ ((k & 1) ? 0u : flip));
-}
-
 // MDCT input sample tmp[j] of TAtrac1MDCT::Mdct (atrac1denc.cpp:80-90), built on the fly.
 // band0 = pointer to sample 0 of this frame's band (negative indices = previous frame).
 ATDE_D float mdct_in_long(const float* band0, const float* W, int j, int size, int win_start)
@@ -148,6 +140,22 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
     {
         // ---- load input tile with halo ----
         const float* __restrict__ pcm = p.pcm + (size_t)s * F * 512 * C + c;
+        const int nbase = 512 * t0 - 304;
+        if (nbase >= 0 && nbase + kNX <= F * 512) {
+            // interior tile: every load independent and in flight at once
+            constexpr int kIters = (kNX + kAnaThreads - 1) / kAnaThreads;
+            float v[kIters];
+#pragma unroll
+            for (int it = 0; it < kIters; it++) {
+                const int k = threadIdx.x + kAnaThreads * it;
+                v[it] = k < kNX ? pcm[(size_t)(nbase + k) * C] : 0.0f;
+            }
+#pragma unroll
+            for (int it = 0; it < kIters; it++) {
+                const int k = threadIdx.x + kAnaThreads * it;
+                if (k < kNX) x[k] = v[it];
+            }
+        } else
         ATDE_PAR_FOR(k, kNX) {
             const int n = 512 * t0 - 304 + k;
             float v = 0.0f;
@@ -176,39 +184,59 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
         }
         __syncthreads();
 
-        const float* band0[3] = {lo + 40, mi + 40, s1hi + 89};   // sample 0 of tile-frame 0
+        // sample 0 of tile-frame 0 of band b: lo + 40, mi + 40, s1hi + 89
         float* filt = x;                                          // x is dead from here on
+        static_assert(kNFilt % 8 == 0 && (16 + kTile * 128) % 8 == 0, "HPF tasks of 8 outputs");
 
         if (p.window_auto) {
             // ---- 21-tap HPF (transient_detector.cpp:52-70) over every band sample of the tile
             //      plus the last 16 samples of the frame before it (for LastEnergy) ----
-            ATDE_PAR_FOR(u, kNFilt) {
-                int b, q;
-                if (u < 16 + kTile * 128) { b = 0; q = u; }
-                else if (u < 2 * (16 + kTile * 128)) { b = 1; q = u - (16 + kTile * 128); }
-                else { b = 2; q = u - 2 * (16 + kTile * 128); }
+            //      A task = 8 consecutive outputs of one band-frame (frame sizes and the 16-sample halo are multiples of 8,
+            //      so a task never straddles frames): its 29 input samples are loaded and sign-flipped once
+            //      (InvertSpectr negates the even samples of the mid / hi bands; the window starts at an even sample,
+            //      so the flipped positions are compile-time constants), then the 8 x 21 taps run on registers.
+            constexpr int kHpfTasks = kNFilt / 8;                         // 66 + 66 + 130
+            for (int task = threadIdx.x; task < kHpfTasks; task += blockDim.x) {
+                const int nb01 = (16 + kTile * 128) / 8;
+                const int b = task < nb01 ? 0 : (task < 2 * nb01 ? 1 : 2);
+                const int q0 = 8 * (task - b * nb01);                     // first output of the task within the band's region
                 const int size = (b == 2) ? 256 : 128;
-                int tl, i;
-                if (q < 16) { tl = -1; i = size - 16 + q; }
-                else { tl = (q - 16) / size; i = (q - 16) - tl * size; }
-                const float* fr = band0[b] + tl * size;          // sample 0 of that frame
-                const unsigned inv = b != 0 ? 0x80000000u : 0u;
+                int tl, i0;
+                if (q0 < 16) { tl = -1; i0 = size - 16 + q0; }
+                else { tl = (q0 - 16) / size; i0 = (q0 - 16) - tl * size; }
+                const float* base = b == 0 ? lo + 40 : (b == 1 ? mi + 40 : s1hi + 89);
+                const float* fr = base + tl * size + i0 - 20;            // w[t] = frame sample i0 - 20 + t
+                const unsigned flip = b != 0 ? 0x80000000u : 0u;
+                float w[29];
+#pragma unroll
+                for (int t = 0; t < 29; t++) {
+                    const unsigned v = __float_as_uint(fr[t]);
+                    w[t] = __uint_as_float((t & 1) ? v : (v ^ flip));    // i0 - 20 is even: even t <-> even sample
+                }
                 // inBuf[w] = frame sample (w - 20); inBuf[size + 20] is never written by the reference => 0
                 const float c0 = -8.65163e-18 * 2.0, c1 = -0.00851586 * 2.0, c2 = -6.74764e-18 * 2.0,
                             c3 = 0.0209036 * 2.0, c4 = -3.36639e-17 * 2.0, c5 = -0.0438162 * 2.0,
                             c6 = -1.54175e-17 * 2.0, c7 = 0.0931738 * 2.0, c8 = -5.52212e-17 * 2.0,
                             c9 = -0.313819 * 2.0;
                 const float cf[10] = {c0, c1, c2, c3, c4, c5, c6, c7, c8, c9};
-                float sacc = hpf_in(fr, i - 10, inv);
-                float s2 = 0.0f;
+                const bool frame_end = i0 + 8 == size;                    // output 7 is the frame's last sample
+                float o[8];
 #pragma unroll
-                for (int j = 0; j < 9; j += 2) {
-                    const int kr = i + 1 - j;                                 // w = i + 21 - j
-                    const float right = (kr >= size) ? 0.0f : hpf_in(fr, kr, inv);
-                    sacc = fadd(sacc, fmul(cf[j], fadd(hpf_in(fr, i + j - 20, inv), right)));
-                    s2 = fadd(s2, fmul(cf[j + 1], fadd(hpf_in(fr, i + j - 19, inv), hpf_in(fr, i - j, inv))));
+                for (int r = 0; r < 8; r++) {
+                    float sacc = w[r + 10];                               // sample i - 10
+                    float s2 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 9; j += 2) {
+                        // right = sample i + 1 - j; for j == 0 at the frame's last sample it lies past the frame: 0
+                        const float right = (j == 0 && r == 7 && frame_end) ? 0.0f : w[r + 21 - j];
+                        sacc = fadd(sacc, fmul(cf[j], fadd(w[r + j], right)));
+                        s2 = fadd(s2, fmul(cf[j + 1], fadd(w[r + j + 1], w[r + 20 - j])));
+                    }
+                    o[r] = __fdiv_rn(fadd(sacc, s2), 2.0f);
                 }
-                filt[u] = __fdiv_rn(fadd(sacc, s2), 2.0f);
+                float4* dst = reinterpret_cast<float4*>(filt + 8 * task);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
             }
             __syncthreads();
             // ---- RMS (dB-ish) of each 16-sample short block (transient_detector.cpp:33-40,81) ----
@@ -256,7 +284,7 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
             const int bslot = slot - (b == 0 ? 0 : (b == 1 ? 64 : 128));
             const int size = (b == 2) ? 256 : 128;
             const bool shrt = (smask[tl] >> b) & 1;
-            const float* fr = band0[b] + tl * size;
+            const float* fr = (b == 0 ? lo + 40 : (b == 1 ? mi + 40 : s1hi + 89)) + tl * size;
             int N, i, kb = 0;
             const float* cs;
             if (!shrt) {

@@ -25,8 +25,8 @@ for ln in sass.splitlines():
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kname], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hdr = rows[1]
-col = {n: hdr.index(n) for n in ('Address', 'Source', '# Samples', 'Instructions Executed', 'Thread Instructions Executed',
-                                 'L1 Wavefronts Shared', 'L1 Wavefronts Shared Ideal')}
+col = {n: (hdr.index(n) if n in hdr else -1) for n in ('Address', 'Source', '# Samples', 'Instructions Executed', 'Thread Instructions Executed',
+                                                         'L1 Wavefronts Shared', 'L1 Wavefronts Shared Ideal')}
 stall_cols = [(n, i) for i, n in enumerate(hdr) if n.startswith('stall_') and 'Not Issued' not in n]
 base = int(rows[2][col['Address']], 16)
 agg = defaultdict(lambda: [0, 0, 0, 0, 0]); stalls = defaultdict(lambda: defaultdict(int)); tot = [0, 0, 0]
@@ -38,7 +38,7 @@ for r in rows[2:]:
     key = line_of.get(off)
     n, t, s = int(r[col['Instructions Executed']]), int(r[col['Thread Instructions Executed']]), int(r[col['# Samples']])
     a = agg[key]
-    a[0] += n; a[1] += t; a[2] += s; a[3] += int(r[col['L1 Wavefronts Shared']] or 0); a[4] += int(r[col['L1 Wavefronts Shared Ideal']] or 0)
+    a[0] += n; a[1] += t; a[2] += s; a[3] += int((r[col['L1 Wavefronts Shared']] if col['L1 Wavefronts Shared'] >= 0 else 0) or 0); a[4] += int((r[col['L1 Wavefronts Shared Ideal']] if col['L1 Wavefronts Shared Ideal'] >= 0 else 0) or 0)
     tot[0] += n; tot[1] += t; tot[2] += s
     for nme, i in stall_cols:
         v = int(r[i] or 0)

@@ -82,28 +82,6 @@ struct BandView {
     int size;            // 128 / 128 / 256
 };
 
-// MDCT input sample tmp[j] of TAtrac1MDCT::Mdct (atrac1denc.cpp:80-90), built on the fly.
-// band0 = pointer to sample 0 of this frame's band (negative indices = previous frame).
-ATDE_D float mdct_in_long(const float* band0, const float* W, int j, int size, int win_start)
-{
-    const int jj = j - win_start;
-    if (jj < 0)
-        return 0.0f;
-    if (jj < 32)
-        return fmul(W[jj], band0[jj - 32]);                  // overlap tail kept from the previous frame
-    const int k = jj - 32;
-    if (k >= size)
-        return 0.0f;
-    const float v = band0[k];
-    return (k >= size - 32) ? fmul(W[31 - (k - (size - 32))], v) : v;
-}
-ATDE_D float mdct_in_short(const float* band0, const float* W, int j, int kb)
-{
-    if (j < 32)
-        return fmul(W[j], band0[32 * kb - 32 + j]);
-    return fmul(W[63 - j], band0[32 * kb + (j - 32)]);
-}
-
 // Stage-1 tasks of 9 output pairs (kNS1 = 1152 = 128 x 9: one task per thread), stage-2 tasks of 5 (111 tasks cover
 // kNS2 = 552 and three scratch outputs).  Odd task sizes keep the 64-bit loads conflict-free (qmf_dev.cuh).
 constexpr int kQ1 = 9, kQ2 = 5;
@@ -120,7 +98,6 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
     __shared__ __align__(16) float mi[kNS2T + 1];
     __shared__ __align__(16) float sp[kTile * 512];
     __shared__ float ener[kNEner];
-    __shared__ float W[32];
     __shared__ __align__(8) float cw[48];
     __shared__ unsigned char smask[kTile];
 
@@ -133,7 +110,6 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
     f32x2 one;
     one.x = p.one; one.y = p.one;
 
-    ATDE_PAR_FOR(i, 32) W[i] = T->sine_window[i];
     ATDE_PAR_FOR(i, 48) cw[i] = c_qmf1p[i];
     ATDE_PAR_FOR(i, 8) { x[kNX + i] = 0.0f; s1lo[kNS1 + i] = 0.0f; }
 
@@ -298,22 +274,24 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
                 cs = T->sincos64;
             }
             const int n = 2 * i, n4 = N >> 2, n34 = 3 * n4, n54 = 5 * n4;
-            const int win_start = (b == 2) ? 112 : 48;
-            float a0, a1, b0, b1;
+            // tmp[j] of TAtrac1MDCT::Mdct = weight[j - joff] * band[j - joff + boff] inside the windowed stretch, 0 outside
+            // (long: 32-sample slope over the previous frame's tail, the frame, slope over its last 32 samples;
+            //  short block kb: the 64 samples around it) — one table look-up and one range test per sample
+            const float* wt = shrt ? T->win_short : (b == 2 ? T->win_long256 : T->win_long128);
+            const int joff = shrt ? 0 : ((b == 2) ? 112 : 48);
+            const int boff = shrt ? 32 * kb - 32 : -32;
+            const unsigned range = shrt ? 64u : (unsigned)(size + 32);
             const int ia0 = n34 - 1 - n, ib0 = n4 + n;
             const int ia1 = (n < n4) ? n34 + n : n - n4;
             const int ib1 = (n < n4) ? n4 - 1 - n : n54 - 1 - n;
-            if (!shrt) {
-                a0 = mdct_in_long(fr, W, ia0, size, win_start);
-                a1 = mdct_in_long(fr, W, ia1, size, win_start);
-                b0 = mdct_in_long(fr, W, ib0, size, win_start);
-                b1 = mdct_in_long(fr, W, ib1, size, win_start);
-            } else {
-                a0 = mdct_in_short(fr, W, ia0, kb);
-                a1 = mdct_in_short(fr, W, ia1, kb);
-                b0 = mdct_in_short(fr, W, ib0, kb);
-                b1 = mdct_in_short(fr, W, ib1, kb);
-            }
+            auto tmp_at = [&](int j) {
+                const int t = j - joff;
+                const bool ok = (unsigned)t < range;
+                const int tc = ok ? t : 0;
+                const float v = fmul(wt[tc], fr[tc + boff]);
+                return ok ? v : 0.0f;
+            };
+            const float a0 = tmp_at(ia0), a1 = tmp_at(ia1), b0 = tmp_at(ib0), b1 = tmp_at(ib1);
             float r0, i0;
             if (n < n4) { r0 = fadd(a0, a1); i0 = fsub(b0, b1); }
             else        { r0 = fsub(a0, a1); i0 = fadd(b0, b1); }
@@ -380,16 +358,20 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
             out[pa] = va;
             out[pb] = vb;
         }
+        // ---- store spectra and masks (the loudness term has its own kernel: it is one sequential sum per frame).
+        //      A frame's 512 spectral lines are one 2 KB row in shared and in global memory: bulk asynchronous stores ----
+        async_proxy_fence();
         __syncthreads();
-        // ---- store spectra and masks (the loudness term has its own kernel: it is one sequential sum per frame) ----
-        ATDE_PAR_FOR(u, kTile * 512) {
-            const int tl = u >> 9, i = u & 511;
-            if (t0 + tl < F)
-                p.specs[(((size_t)s * F + t0 + tl) * C + c) * 512 + i] = sp[u];
+        if (threadIdx.x == 0) {
+            for (int tl = 0; tl < kTile; tl++)
+                if (t0 + tl < F)
+                    bulk_s2g(p.specs + (((size_t)s * F + t0 + tl) * C + c) * 512, sp + tl * 512, 2048u);
+            bulk_store_commit();
         }
         ATDE_PAR_FOR(tl, kTile) {
             if (t0 + tl < F) p.masks[((size_t)s * F + t0 + tl) * C + c] = smask[tl];
         }
+        if (threadIdx.x == 0) bulk_store_wait_read();                 // shared memory is released when the block retires
     }
 }
 

@@ -21,6 +21,9 @@ struct DevTables {
     float sincos64[32];          // TMDCT<64>(0.5)
     cpx tw128[128], tw64[64], tw16[16];          // forward kissfft twiddles
     unsigned char perm128[128], perm64[64], perm16[16];
+    // MDCT input weights (TAtrac1MDCT::Mdct, atrac1denc.cpp:80-90) as tables: position t of the windowed stretch of a
+    // long block (32-sample sine slope | 1.0 | mirrored slope) and of a 64-sample short block (slope | mirrored slope)
+    float win_long128[160], win_long256[288], win_short[64];
 };
 
 struct AnalysisParams {

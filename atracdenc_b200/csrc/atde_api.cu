@@ -129,6 +129,11 @@ int build_at1_tables(atde_encoder* e)
         h->sine_window[i] = sin((i + 0.5) * (M_PI / (2.0 * 32.0)));
     for (uint32_t i = 0; i < 64; i++)                                   // atrac1.h:122-127
         h->scale_table[i] = pow(2.0, (double)(i / 3.0 - 21.0));
+    for (int t = 0; t < 288; t++) {                                     // weights of TAtrac1MDCT::Mdct's input (atrac1denc.cpp:80-90)
+        if (t < 160) h->win_long128[t] = t < 32 ? h->sine_window[t] : (t < 128 ? 1.0f : h->sine_window[128 + 31 - t]);
+        h->win_long256[t] = t < 32 ? h->sine_window[t] : (t < 256 ? 1.0f : h->sine_window[256 + 31 - t]);
+        if (t < 64) h->win_short[t] = t < 32 ? h->sine_window[t] : h->sine_window[63 - t];
+    }
     const std::vector<float> curve = loudness_curve(512);
     memcpy(h->loud_curve, curve.data(), sizeof(h->loud_curve));
     {   // CalcAt1ATH (atrac1_bitalloc.cpp:118-135): min over the BFU's lines, dB -> power

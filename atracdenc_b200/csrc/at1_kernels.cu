@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
 {
     __shared__ __align__(16) float x[kNX + 8];      // input tile; later HPF output; later FFT buffer
     __shared__ __align__(16) float s1lo[kNS1 + 8];  // (+8: the three scratch outputs of stage 2 read past kNS1)
-    __shared__ __align__(16) float s1hi[kNS1];
+    __shared__ __align__(16) float s1hi_raw[kNS1 + 4];
+    float* const s1hi = s1hi_raw + 3;               // hi-band sample 0 of the tile sits at s1hi + 89: 16-byte aligned this way
     __shared__ __align__(16) float lo[kNS2T + 1];
     __shared__ __align__(16) float mi[kNS2T + 1];
     __shared__ __align__(16) float sp[kTile * 512];
@@ -183,11 +184,16 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
                 const float* base = b == 0 ? lo + 40 : (b == 1 ? mi + 40 : s1hi + 89);
                 const float* fr = base + tl * size + i0 - 20;            // w[t] = frame sample i0 - 20 + t
                 const unsigned flip = b != 0 ? 0x80000000u : 0u;
-                float w[29];
+                // (fr is 16-byte aligned: i0 - 20 is a multiple of 4 and so are the band origins; eight 16-byte loads, the
+                //  32-byte stride between the tasks of neighbouring lanes costs two wavefronts instead of eight)
+                float w[32];
 #pragma unroll
-                for (int t = 0; t < 29; t++) {
-                    const unsigned v = __float_as_uint(fr[t]);
-                    w[t] = __uint_as_float((t & 1) ? v : (v ^ flip));    // i0 - 20 is even: even t <-> even sample
+                for (int t4 = 0; t4 < 8; t4++) {
+                    const float4 v = reinterpret_cast<const float4*>(fr)[t4];
+                    w[4 * t4 + 0] = __uint_as_float(__float_as_uint(v.x) ^ flip);    // i0 - 20 is even: even t <-> even sample
+                    w[4 * t4 + 1] = v.y;
+                    w[4 * t4 + 2] = __uint_as_float(__float_as_uint(v.z) ^ flip);
+                    w[4 * t4 + 3] = v.w;
                 }
                 // inBuf[w] = frame sample (w - 20); inBuf[size + 20] is never written by the reference => 0
                 const float c0 = -8.65163e-18 * 2.0, c1 = -0.00851586 * 2.0, c2 = -6.74764e-18 * 2.0,

@@ -39,14 +39,16 @@ def gather_units(local_units: torch.Tensor, n_streams: int, dst: int = 0):
         bufs = [torch.empty((hi - lo,) + tail, dtype=local_units.dtype, device=local_units.device) for lo, hi in shapes]
     else:
         bufs = None
-    # shards may differ in size by one stream: point-to-point instead of a fixed-size gather
+    # shards may differ in size by one stream: point-to-point instead of a fixed-size gather; the receives are posted as
+    # ONE batch (a grouped NCCL call) so that the seven transfers run concurrently instead of one after the other
     if rank == dst:
         bufs[dst].copy_(local_units)
-        reqs = [dist.irecv(bufs[r], src=r) for r in range(world) if r != dst]
-        for q in reqs:
+        ops = [dist.P2POp(dist.irecv, bufs[r], r) for r in range(world) if r != dst]
+        for q in dist.batch_isend_irecv(ops):
             q.wait()
         return torch.cat(bufs, dim=0)
-    dist.send(local_units.contiguous(), dst=dst)
+    for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_units.contiguous(), dst)]):
+        q.wait()
     return None
 
 
@@ -58,15 +60,16 @@ def scatter_pcm(full_pcm: torch.Tensor | None, n_streams: int, per_stream_shape,
     lo, hi = shard_range(n_streams, rank, world)
     mine = torch.empty((hi - lo,) + tuple(per_stream_shape), dtype=dtype, device=device)
     if rank == src:
-        reqs = []
+        ops = []
         for r in range(world):
             a, b = shard_range(n_streams, r, world)
             if r == src:
                 mine.copy_(full_pcm[a:b])
             else:
-                reqs.append(dist.isend(full_pcm[a:b].contiguous(), dst=r))
-        for q in reqs:
+                ops.append(dist.P2POp(dist.isend, full_pcm[a:b].contiguous(), r))
+        for q in dist.batch_isend_irecv(ops):
             q.wait()
     else:
-        dist.recv(mine, src=src)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, mine, src)]):
+            q.wait()
     return mine

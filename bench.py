@@ -417,6 +417,7 @@ def measure_workload(name, args, env, *, steps, warmup, verify_stride, with_i16=
     if world > 1 and env.get("collectives") and name == DEFAULT_WORKLOAD:
         collective = measure_collectives(torch, dist, env, d_pcm, d_out[:, :fo].contiguous(), S)
 
+    ceiling = h2d_ceiling(torch, dist, env) if name == DEFAULT_WORKLOAD else None
     res = None
     if rank == 0:
         frames_total = S * F * world
@@ -454,6 +455,7 @@ def measure_workload(name, args, env, *, steps, warmup, verify_stride, with_i16=
                     "d2h_bytes_per_step": S * F * units * ub, "ms_per_step": host_ms / steps,
                     "host_and_device_outputs_equal": same, "host_buffers": host_kind,
                     "h2d_GBps_aggregate": world * h2d / (host_ms / steps / 1000.0) / 1e9,
+                    "h2d_GBps_ceiling_all_ranks_copying": ceiling,
                     "host_binding": env.get("binding")},
             "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
         }
@@ -469,6 +471,30 @@ def measure_workload(name, args, env, *, steps, warmup, verify_stride, with_i16=
     del d_pcm, d_out, h_out
     torch.cuda.empty_cache()
     return res
+
+
+def h2d_ceiling(torch, dist, env):
+    """Aggregate pinned host -> device copy rate with EVERY rank copying at once (1 GiB each, five times): the ceiling of
+    `e2e` on this host — all ranks share its memory controllers and PCIe root complexes."""
+    n = 1 << 30
+    try:
+        h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        d = torch.empty(n, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            d.copy_(h, non_blocking=True)
+        env["barrier"]()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1000.0
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if env["world"] > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        del h, d
+        return env["world"] * 5 * n / (float(t[0]) / 1000.0) / 1e9
+    except RuntimeError:
+        return None
 
 
 def measure_collectives(torch, dist, env, d_pcm, d_units, S):

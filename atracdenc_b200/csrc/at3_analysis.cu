@@ -130,12 +130,35 @@ __global__ void __launch_bounds__(256, 4) at3_qmf_kernel(Geometry g, Buffers b)
     one.x = g.one; one.y = g.one;
 
     if (tid < 48) cw[tid] = c_qmf3p[tid];
+#ifndef ATDE_K1_NO_TMA_LOAD
+    __shared__ mbar_t ldbar;
+    if (tid == 0) mbar_init(&ldbar, 1);
+    async_proxy_fence();
+    __syncthreads();
+#endif
     {
         const long long n0 = 4LL * m0 - 144 - (started ? 1024 : 0);    // tile sample 0 as an index into b.pcm
         const long long nlim = (long long)g.N * 1024;
         if (g.C == 2 && n0 >= 0 && n0 + kQX <= nlim) {
-            // interior tile: every load independent and in flight at once
             const float2* src = reinterpret_cast<const float2*>(b.pcm + ((size_t)s * g.N * 1024 + (size_t)n0) * 2);
+#ifndef ATDE_K1_NO_TMA_LOAD
+            // interior tile: the interleaved PCM (16.4 KB, 32-byte aligned) comes in by ONE bulk asynchronous copy into the
+            // stage-1 output area, which is idle until the tile has been de-interleaved, scaled and padded
+            float* raw = &s1[0][0][0];
+            static_assert(4 * kQS1P >= 2 * kQX && (kQX * 8) % 16 == 0 && kQX % 2 == 0, "staging area and copy size");
+            if (tid == 0) {
+                mbar_expect_tx(&ldbar, (unsigned)(kQX * 8));
+                bulk_g2s(raw, src, (unsigned)(kQX * 8), &ldbar);
+            }
+            mbar_wait(&ldbar, 0);
+            for (int t2 = tid; t2 < kQX / 2; t2 += 256) {                // two stereo samples per 16-byte load
+                const float4 v = reinterpret_cast<const float4*>(raw)[t2];
+                const int p = qphys(2 * t2);                              // samples 2 t2, 2 t2 + 1 are neighbours in the padded layout
+                *reinterpret_cast<float2*>(&xs[0][p]) = make_float2(fmul(v.x, 0.25f), fmul(v.z, 0.25f));   // data / 4.0 (atrac3denc.cpp:704)
+                *reinterpret_cast<float2*>(&xs[1][p]) = make_float2(fmul(v.y, 0.25f), fmul(v.w, 0.25f));
+            }
+#else
+            // interior tile: every load independent and in flight at once
             constexpr int kIters = (kQX + 255) / 256;
             float2 v[kIters];
 #pragma unroll
@@ -151,6 +174,7 @@ __global__ void __launch_bounds__(256, 4) at3_qmf_kernel(Geometry g, Buffers b)
                     xs[1][qphys(t)] = fmul(v[it].y, 0.25f);
                 }
             }
+#endif
         } else
         ATDE_PAR_FOR(t, kQX) {
             const long long nn = n0 + t;
@@ -334,14 +358,17 @@ ATDE_D void fwd_bfly(cpx* buf, int p, int d, cpx t1, cpx t2, cpx t3)
 // by the structural zeros is exact, so the values equal the full transform's (up to the sign of zero,
 // which no consumer can see: the output is squared).
 // Only output samples [1024, 3072) are consumed (AnalyzeGain), i.e. complex slots [512, 1536).
-__global__ void __launch_bounds__(kGainBlock, 7) at3_gain_kernel(Geometry g, Buffers b)
+#ifndef ATDE_GAIN_BLOCKS
+#define ATDE_GAIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) cpx big[2048 + 256 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ __align__(8) cpx tw2c[15][8];         // pass-2 twiddles of lane group k, compact
     __shared__ __align__(16) cpx fwd[256 + 16];
     __shared__ __align__(16) cpx freq[257 + 17];
     __shared__ __align__(16) cpx sup[257 + 17];      // super4096[k - 1] at fq(k), k = 1..256
-    __shared__ float micro[256];
+    float* const micro = reinterpret_cast<float*>(fwd);   // 256 micro-chunk RMS values: the forward FFT buffer is dead by then
     __shared__ float sgain[96];
     __shared__ double esum_part[kGainThreads / 32][2];   // per-warp partial sums of (|X_k|^2, |X_k H_k|^2)
     __shared__ float sstat[2];

@@ -364,10 +364,12 @@ ATDE_D void fwd_bfly(cpx* buf, int p, int d, cpx t1, cpx t2, cpx t3)
 __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) cpx big[2048 + 256 + 128];    // inverse FFT buffer, padded; later the real output
-    __shared__ __align__(8) cpx tw2c[15][8];         // pass-2 twiddles of lane group k, compact
-    __shared__ __align__(16) cpx fwd[256 + 16];
+    __shared__ tw4 tw2c[15][8];                      // pass-2 twiddles of lane group k, compact, pre-spread for the packed butterfly
+    __shared__ __align__(16) cpx fwd[257 + 17];
     __shared__ __align__(16) cpx freq[257 + 17];
-    __shared__ __align__(16) cpx sup[257 + 17];      // super4096[k - 1] at fq(k), k = 1..256
+    // super4096[k - 1] at fq(k), k = 1..256, moves into the forward FFT buffer once that is dead: every KB of shared
+    // memory saved is L1 for the twiddle tables (a separate 2 KB array cost 3.6 ms per 10^6 frames)
+    cpx* const sup = fwd;
     float* const micro = reinterpret_cast<float*>(fwd);   // 256 micro-chunk RMS values: the forward FFT buffer is dead by then
     __shared__ float sgain[96];
     __shared__ double esum_part[kGainThreads / 32][2];   // per-warp partial sums of (|X_k|^2, |X_k H_k|^2)
@@ -381,9 +383,15 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     const int tid = threadIdx.x;
     const cpx* __restrict__ tw = T->tw2048;
 
-    if (tid < 120) (&tw2c[0][0])[tid] = (&T->gtw2[0][0])[tid];
-    // the only super-twiddles kiss_fftri(4096) meets with a non-zero operand
-    for (int k = 1 + tid; k <= 256; k += kGainBlock) sup[fq(k)] = T->super4096[k - 1];
+    if (tid < 120) reinterpret_cast<float4*>(&tw2c[0][0])[tid] = reinterpret_cast<const float4*>(&T->gtw2[0][0])[tid];
+    f32x2 one2, mone2;
+    one2.x = one2.y = g.one;
+    mone2.x = mone2.y = -g.one;
+    // the only super-twiddles kiss_fftri(4096) meets with a non-zero operand (fetched now, parked in registers until
+    // the buffer is free)
+    cpx sup_reg[2];
+    sup_reg[0] = T->super4096[tid];
+    sup_reg[1] = T->super4096[tid + kGainBlock];
     // 1. Planck window, packed as the complex input of the half-size FFT; loaded in natural order and
     //    stored at its digit-reversed slot (base-4 reversal of 4 digits is an involution)
     ATDE_PAR_FOR(j, 256) {
@@ -442,6 +450,8 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     //     (relative) of one of the two thresholds, where the float rounding of the ratio could decide a comparison
     //     differently, is recomputed with the reference's sequential loop at the end of the kernel.
     const int lcb = T->low_cut_bin;
+    sup[fq(1 + tid)] = sup_reg[0];
+    sup[fq(1 + tid + kGainBlock)] = sup_reg[1];
     {
         double tot = 0.0, hi = 0.0;
         for (int k = tid; k < 257; k += kGainThreads) {
@@ -461,6 +471,7 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         }
         if ((tid & 31) == 0) { esum_part[tid >> 5][0] = tot; esum_part[tid >> 5][1] = hi; }
     }
+    __syncthreads();
     // 3/4. inverse FFT input Y[k] = 8*X[k]*H[k] (Nyquist bin halved), kiss_fftri pre-processing
     //      (kiss_fftr.c:131-151) with Y[2048-k] == 0, and pass 1 of the inverse FFT.
     auto tmp_pair = [&](int k, cpx& lo, cpx& hi) {
@@ -488,35 +499,79 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         lo.r = fadd(fek.r, fok.r);  lo.i = fadd(fek.i, fok.i);
         hi.r = fsub(fek.r, fok.r);  hi.i = fmul(fsub(fek.i, fok.i), -1.0f);
     };
+    // tmpbuf[k] alone / tmpbuf[2048-k] alone for a kept bin 1 <= k < 256 with the structural zeros folded away:
+    // fek = tp = fk (adding +-0), hi.i = -(fk.i - fok.i) = fok.i - fk.i
+    auto scaled_bin = [&](int k) {
+        cpx fk;
+        fk.r = fmul(freq[fq(k)].r, 8.0f);
+        fk.i = fmul(freq[fq(k)].i, 8.0f);
+        if (k < lcb + 2) {
+            const float w = T->hpf_h[k - lcb];
+            fk.r = fmul(fk.r, w);
+            fk.i = fmul(fk.i, w);
+        }
+        return fk;
+    };
     for (int grp = tid; grp < 256; grp += kGainThreads) {
         const int low = ((grp >> 6) & 3) | (((grp >> 4) & 3) << 2) | (((grp >> 2) & 3) << 4) | ((grp & 3) << 6);
-        cpx x0, x2, x7, dummy;
-        tmp_pair(low, x0, dummy);                        // slot 0: input index low (tmpbuf[0] is zero: bin 0 is cut)
-        tmp_pair(256 - low, dummy, x7);                  // slot 7: input index 1792 + low = 2048 - (256 - low)
-        x2.r = x2.i = 0.0f;
-        if (low == 0) { x0.r = x0.i = 0.0f; tmp_pair(256, x2, dummy); }   // slot 2: input index 256
-        if (lcb == 0 && low == 0) {
-            // bin 0 kept (not the encoder's configuration, kept for completeness): tmpbuf[0]
-            const float y0 = fmul(freq[0].r, 8.0f);
-            x0.r = fadd(y0, 0.0f); x0.i = fsub(y0, 0.0f);
-        }
-        // radix-2, m = 1, twiddle tw[0]: (F0,F1) = (x0, x0); (F2,F3) = (x2, x2); (F6,F7) = (x7, -x7)
-        const cpx t7 = cmul(x7, tw[0]);
-        cpx F6, F7;
-        F7.r = fsub(0.0f, t7.r); F7.i = fsub(0.0f, t7.i);
-        F6.r = fadd(0.0f, t7.r); F6.i = fadd(0.0f, t7.i);
         cpx o0, o1, o2, o3, o4, o5, o6, o7;
-        {   // radix-4, m = 2, k = 0: elements (x0, x2, 0, F6), twiddles tw[0]
-            cpx f0 = x0, f1 = x2, f2, f3 = F6;
-            f2.r = f2.i = 0.0f;
-            kf_bfly4<true>(f0, f1, f2, f3, tw[0], tw[0], tw[0]);
-            o0 = f0; o2 = f1; o4 = f2; o6 = f3;
-        }
-        {   // k = 1: elements (x0, x2, 0, F7), twiddles tw[256], tw[512], tw[768]
-            cpx f0 = x0, f1 = x2, f2, f3 = F7;
-            f2.r = f2.i = 0.0f;
-            kf_bfly4<true>(f0, f1, f2, f3, tw[256], tw[512], tw[768]);
-            o1 = f0; o3 = f1; o5 = f2; o7 = f3;
+        if (low == 0) {
+            // the one group with a third input (tmpbuf[256] in slot 2), and with tmpbuf[0] when bin 0 is kept: written out in full
+            cpx x0, x2, x7, dummy;
+            tmp_pair(low, x0, dummy);                        // slot 0: input index low (tmpbuf[0] is zero: bin 0 is cut)
+            tmp_pair(256 - low, dummy, x7);                  // slot 7: input index 1792 + low = 2048 - (256 - low)
+            x2.r = x2.i = 0.0f;
+            if (low == 0) { x0.r = x0.i = 0.0f; tmp_pair(256, x2, dummy); }   // slot 2: input index 256
+            if (lcb == 0 && low == 0) {
+                // bin 0 kept (not the encoder's configuration, kept for completeness): tmpbuf[0]
+                const float y0 = fmul(freq[0].r, 8.0f);
+                x0.r = fadd(y0, 0.0f); x0.i = fsub(y0, 0.0f);
+            }
+            // radix-2, m = 1, twiddle tw[0]: (F0,F1) = (x0, x0); (F2,F3) = (x2, x2); (F6,F7) = (x7, -x7)
+            const cpx t7 = cmul(x7, tw[0]);
+            cpx F6, F7;
+            F7.r = fsub(0.0f, t7.r); F7.i = fsub(0.0f, t7.i);
+            F6.r = fadd(0.0f, t7.r); F6.i = fadd(0.0f, t7.i);
+            {   // radix-4, m = 2, k = 0: elements (x0, x2, 0, F6), twiddles tw[0]
+                cpx f0 = x0, f1 = x2, f2, f3 = F6;
+                f2.r = f2.i = 0.0f;
+                kf_bfly4<true>(f0, f1, f2, f3, tw[0], tw[0], tw[0]);
+                o0 = f0; o2 = f1; o4 = f2; o6 = f3;
+            }
+            {   // k = 1: elements (x0, x2, 0, F7), twiddles tw[256], tw[512], tw[768]
+                cpx f0 = x0, f1 = x2, f2, f3 = F7;
+                f2.r = f2.i = 0.0f;
+                kf_bfly4<true>(f0, f1, f2, f3, tw[256], tw[512], tw[768]);
+                o1 = f0; o3 = f1; o5 = f2; o7 = f3;
+            }
+        } else {
+            // slots 0 and 7 only: x0 = tmpbuf[low], x7 = tmpbuf[1792 + low].  tw[0] = (1, 0) and every other input of the two
+            // butterflies is a structural zero, so (each line below is what kf_bfly2 / kf_bfly4 leave once the exact
+            // operations on zeros and the multiplications by one are dropped; only the sign of a zero can differ, and
+            // the consumers square the output):
+            //   radix-2:  F6 = x7, F7 = -x7
+            //   radix-4, k = 0: s2 = x7, s3 = x7, s4 = -x7          radix-4, k = 1: s2 = -c, s3 = -c, s4 = c, c = x7 * tw[768]
+            cpx x0, x7;
+            x0.r = x0.i = x7.r = x7.i = 0.0f;
+            if (low >= lcb) {
+                const cpx fk = scaled_bin(low);
+                const cpx fok = cmul(fk, sup[fq(low)]);
+                x0.r = fadd(fk.r, fok.r); x0.i = fadd(fk.i, fok.i);
+            }
+            if (256 - low >= lcb) {
+                const cpx fk = scaled_bin(256 - low);
+                const cpx fok = cmul(fk, sup[fq(256 - low)]);
+                x7.r = fsub(fk.r, fok.r); x7.i = fsub(fok.i, fk.i);
+            }
+            o0.r = fadd(x0.r, x7.r); o0.i = fadd(x0.i, x7.i);
+            o4.r = fsub(x0.r, x7.r); o4.i = fsub(x0.i, x7.i);
+            o2.r = fadd(x0.r, x7.i); o2.i = fsub(x0.i, x7.r);
+            o6.r = fsub(x0.r, x7.i); o6.i = fadd(x0.i, x7.r);
+            const cpx c = cmul(x7, tw[768]);
+            o1.r = fsub(x0.r, c.r); o1.i = fsub(x0.i, c.i);
+            o5.r = fadd(x0.r, c.r); o5.i = fadd(x0.i, c.i);
+            o3.r = fsub(x0.r, c.i); o3.i = fadd(x0.i, c.r);
+            o7.r = fadd(x0.r, c.i); o7.i = fsub(x0.i, c.r);
         }
         cpx* dst = big + gphys(8 * grp);
         dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3; dst[4] = o4; dst[5] = o5; dst[6] = o6; dst[7] = o7;
@@ -533,13 +588,13 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
 #pragma unroll
             for (int q = 0; q < 4; q++) x[a][q] = bg[9 * a + 36 * q];
         {
-            const cpx t1 = tw2c[0][k], t2 = tw2c[1][k], t3 = tw2c[2][k];      // tw[64k], tw[128k], tw[192k]
+            const tw4 t1 = tw2c[0][k], t2 = tw2c[1][k], t3 = tw2c[2][k];      // tw[64k], tw[128k], tw[192k]
 #pragma unroll
-            for (int q = 0; q < 4; q++) kf_bfly4<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3);
+            for (int q = 0; q < 4; q++) kf_bfly4_packed<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3, one2, mone2);
         }
 #pragma unroll
         for (int a = 0; a < 4; a++)                                            // kk = k + 8a: tw[16kk], tw[32kk], tw[48kk]
-            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw2c[3 + 3 * a][k], tw2c[4 + 3 * a][k], tw2c[5 + 3 * a][k]);
+            kf_bfly4_packed<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw2c[3 + 3 * a][k], tw2c[4 + 3 * a][k], tw2c[5 + 3 * a][k], one2, mone2);
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -558,13 +613,16 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
             for (int q = 0; q < 4; q++) x[a][q] = bg[152 * a + 608 * q];
         atde_named_barrier(1, kGainThreads);                                  // every slot is in registers: big can be overwritten
         {
-            const cpx t1 = T->gtw3a[0][k], t2 = T->gtw3a[1][k], t3 = T->gtw3a[2][k];     // tw[4k], tw[8k], tw[12k]
+            const float mone = mone2.x;
+            const tw4 t1 = spread_twiddle_dev(T->gtw3a[0][k], mone), t2 = spread_twiddle_dev(T->gtw3a[1][k], mone),
+                      t3 = spread_twiddle_dev(T->gtw3a[2][k], mone);                     // tw[4k], tw[8k], tw[12k]
 #pragma unroll
-            for (int q = 0; q < 4; q++) kf_bfly4<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3);
+            for (int q = 0; q < 4; q++) kf_bfly4_packed<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3, one2, mone2);
         }
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-            kf_bfly4<true>(x[a][0], x[a][1], x[a][2], x[a][3], T->gtw3b[a][0][k], T->gtw3b[a][1][k], T->gtw3b[a][2][k]);  // tw[kk], tw[2kk], tw[3kk]
+            kf_bfly4_packed<true>(x[a][0], x[a][1], x[a][2], x[a][3], spread_twiddle_dev(T->gtw3b[a][0][k], mone2.x),
+                                  spread_twiddle_dev(T->gtw3b[a][1][k], mone2.x), spread_twiddle_dev(T->gtw3b[a][2][k], mone2.x), one2, mone2);  // tw[kk], tw[2kk], tw[3kk]
             // 5. normalise (norm = 1/4096); complex slot kk + 512q -> output samples 2*slot, 2*slot+1
             cpx u, v;
             u.r = fmul(x[a][1].r, 1.0f / 4096.0f); u.i = fmul(x[a][1].i, 1.0f / 4096.0f);

@@ -98,6 +98,14 @@ struct atde_encoder {
     static constexpr int kSlots = 3;   // pipeline slots of the host path: chunk k+2 is copied in while k+1 waits and k computes
     Workspace ws[kSlots];
     cudaEvent_t chunk_done[kSlots] = {};   // host path: "the kernels of the chunk in this slot are finished"
+    // ATRAC3 host path: PCM arrives through its own ring of staging buffers on its own stream, so that the copy-in of
+    // chunk k+4 waits only for the FIRST kernel of chunk k (the QMF, the one reader of the PCM), not for the chunk's
+    // whole pipeline: the H2D copies then run back to back from the start of the call
+    static constexpr int kPcmRing = 4;
+    DevBuf<float> pcm_ring[kPcmRing];
+    DevBuf<short> pcm16_ring[kPcmRing];
+    cudaEvent_t pcm_ready[kPcmRing] = {}, pcm_free[kPcmRing] = {};
+    cudaStream_t copy_stream = nullptr;
     // stream state, sized for n_state_streams
     DevBuf<float> hist;
     DevBuf<float> loud_state;
@@ -269,16 +277,16 @@ int build_at3_tables(atde_encoder* e)
     }
     for (int k = 0; k < 8; k++) {
         for (int q = 0; q < 3; q++) {
-            memcpy(&h->gtw2[q][k], &tw2048[(size_t)64 * k * (q + 1)], sizeof(h->gtw2[0][0]));
+            h->gtw2[q][k] = atde::spread_twiddle(h->tw2048[(size_t)64 * k * (q + 1)]);
             for (int a = 0; a < 4; a++)
-                memcpy(&h->gtw2[3 + 3 * a + q][k], &tw2048[(size_t)16 * (k + 8 * a) * (q + 1)], sizeof(h->gtw2[0][0]));
+                h->gtw2[3 + 3 * a + q][k] = atde::spread_twiddle(h->tw2048[(size_t)16 * (k + 8 * a) * (q + 1)]);
         }
     }
     for (int k = 0; k < 128; k++)
         for (int q = 0; q < 3; q++) {
-            memcpy(&h->gtw3a[q][k], &tw2048[(size_t)4 * k * (q + 1)], sizeof(h->gtw3a[0][0]));
+            h->gtw3a[q][k] = h->tw2048[(size_t)4 * k * (q + 1)];
             for (int a = 0; a < 4; a++)
-                memcpy(&h->gtw3b[a][q][k], &tw2048[(size_t)(k + 128 * a) * (q + 1)], sizeof(h->gtw3b[0][0][0]));
+                h->gtw3b[a][q][k] = h->tw2048[(size_t)(k + 128 * a) * (q + 1)];
         }
 
     cudaError_t ce = cudaMalloc(&e->d_at3_tab, sizeof(at3::DevTables));
@@ -387,7 +395,7 @@ int run_at1(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
 // Runs the ATRAC3 pipeline for S streams x N new frames whose PCM is at d_pcm (device); s0 = first
 // stream index inside the handle's state arrays; `started` says whether the streams carry a frame.
 int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, long long N, bool started,
-            unsigned char* d_out)
+            unsigned char* d_out, cudaEvent_t pcm_consumed = nullptr)
 {
     using namespace atde::at3;
     const int C = e->cfg.channels;
@@ -444,6 +452,7 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
 
     { KernelTimer kt(e, w.stream, 0); launch_qmf(g, b, w.stream); }
     e->launches += 1;
+    if (pcm_consumed) CK(cudaEventRecord(pcm_consumed, w.stream));     // nothing after the QMF reads the PCM
     if (g.n_out > 0) {
         if (!g.no_gain) {
             { KernelTimer kt(e, w.stream, 3); launch_gain_analysis(g, b, w.stream); }
@@ -605,6 +614,14 @@ int atde_create(const atde_settings* s, atde_encoder** out)
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->ws[i].stream, cudaStreamNonBlocking);
         if (ce != cudaSuccess) { delete e; return fail(ATDE_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
     }
+    if (s->codec == ATDE_CODEC_ATRAC3) {
+        cudaError_t ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < atde_encoder::kPcmRing && ce == cudaSuccess; i++) {
+            ce = cudaEventCreateWithFlags(&e->pcm_ready[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->pcm_free[i], cudaEventDisableTiming);
+        }
+        if (ce != cudaSuccess) { atde_destroy(e); return fail(ATDE_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
+    }
     int rc = 0;
     if (s->codec == ATDE_CODEC_ATRAC1) rc = build_at1_tables(e);
     else if (s->codec == ATDE_CODEC_ATRAC3) rc = build_at3_tables(e);
@@ -624,6 +641,12 @@ void atde_destroy(atde_encoder* e)
         if (e->ws[i].stream) cudaStreamDestroy(e->ws[i].stream);
         if (e->chunk_done[i]) cudaEventDestroy(e->chunk_done[i]);
     }
+    for (int i = 0; i < atde_encoder::kPcmRing; i++) {
+        e->pcm_ring[i].release(); e->pcm16_ring[i].release();
+        if (e->pcm_ready[i]) cudaEventDestroy(e->pcm_ready[i]);
+        if (e->pcm_free[i]) cudaEventDestroy(e->pcm_free[i]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     e->hist.release(); e->loud_state.release(); e->started.release();
     e->prevhalf.release(); e->next_scale.release(); e->ctx.release();
     atde::at3p::pipeline_destroy(e->at3p);
@@ -769,6 +792,7 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     // leaves the carried stream state half advanced: drain both pipeline slots and invalidate the state
     // (the next batch needs atde_reset()).
     auto bail = [&](int code) {
+        if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
         for (int i = 0; i < atde_encoder::kSlots; i++) cudaStreamSynchronize(e->ws[i].stream);
         e->have_state = false;
         e->n_state_streams = 0;
@@ -789,13 +813,50 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     // ATRAC3 frames: the small serial scan kernels then leave the device idle.  Kept for experiments.)
     const bool ordered = !at3p && getenv("ATDE_HOST_ORDERED") != nullptr;
     cudaEvent_t prev_done = nullptr;
-    for (int s0 = 0, n = first; s0 < S; s0 += n, n = chunk, slot = (slot + 1) % n_slots) {
+    const bool ring = at3 && !at3p && e->copy_stream && getenv("ATDE_NO_PCM_RING") == nullptr;
+    const float* d_chunk_pcm = nullptr;
+    cudaEvent_t pcm_consumed = nullptr;
+    int k = 0;
+    if (ring) {
+        // size the staging buffers before anything is in flight (a cudaMalloc in mid-pipeline synchronises the device)
+        const int n_chunks = 1 + (S - first + chunk - 1) / chunk;
+        const size_t cnt = (size_t)std::max(first, std::min(chunk, S - first)) * pcm_per_stream;
+        for (int i = 0; i < std::min(n_chunks, (int)atde_encoder::kPcmRing); i++)
+            if ((rc = pcm16 ? e->pcm16_ring[i].ensure(cnt + 8) : e->pcm_ring[i].ensure(cnt))) return bail(rc);
+    }
+    for (int s0 = 0, n = first; s0 < S; s0 += n, n = chunk, slot = (slot + 1) % n_slots, k++) {
         if (n > S - s0) n = S - s0;
         Workspace& w = e->ws[slot];
-        if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) return bail(rc);
         if ((rc = w.out.ensure((size_t)n * out_per_stream + 1))) return bail(rc);
         if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return bail(rc);
-        if (pcm16) {
+        if (ring) {
+            const int pb = k % atde_encoder::kPcmRing;
+            const size_t cnt = (size_t)n * pcm_per_stream;
+            if (k >= atde_encoder::kPcmRing) CKB(cudaStreamWaitEvent(e->copy_stream, e->pcm_free[pb], 0));
+            if (pcm16) {
+                if ((rc = e->pcm16_ring[pb].ensure(cnt + 8))) return bail(rc);
+                if ((rc = w.pcm.ensure(cnt))) return bail(rc);
+                CKB(cudaMemcpyAsync(e->pcm16_ring[pb].p, pcm16 + (size_t)s0 * pcm_per_stream, cnt * sizeof(short), cudaMemcpyHostToDevice, e->copy_stream));
+            } else {
+                if ((rc = e->pcm_ring[pb].ensure(cnt))) return bail(rc);
+                CKB(cudaMemcpyAsync(e->pcm_ring[pb].p, pcm + (size_t)s0 * pcm_per_stream, cnt * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+            }
+            CKB(cudaEventRecord(e->pcm_ready[pb], e->copy_stream));
+            CKB(cudaStreamWaitEvent(w.stream, e->pcm_ready[pb], 0));
+            if (pcm16) {
+                const unsigned blocks = (unsigned)std::min<size_t>((cnt / 8 + 255) / 256 + 1, (size_t)148 * 16);
+                ATDE_LAUNCH(pcm_i16_to_f32_kernel, blocks, 256, 0, w.stream, (const short*)e->pcm16_ring[pb].p, w.pcm.p, (long long)cnt);
+                e->launches += 1;
+                CKB(cudaEventRecord(e->pcm_free[pb], w.stream));           // the conversion is the staging buffer's one reader
+                d_chunk_pcm = w.pcm.p;
+                pcm_consumed = nullptr;
+            } else {
+                d_chunk_pcm = e->pcm_ring[pb].p;
+                pcm_consumed = e->pcm_free[pb];
+            }
+        } else if ((rc = w.pcm.ensure((size_t)n * pcm_per_stream))) {
+            return bail(rc);
+        } else if (pcm16) {
             const size_t cnt = (size_t)n * pcm_per_stream;
             if ((rc = w.pcm16.ensure(cnt + 8))) return bail(rc);
             CKB(cudaMemcpyAsync(w.pcm16.p, pcm16 + (size_t)s0 * pcm_per_stream, cnt * sizeof(short), cudaMemcpyHostToDevice, w.stream));
@@ -813,7 +874,7 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
             prof.ctx = e; prof.begin = at3p_prof_begin; prof.end = at3p_prof_end;
             rc = atde::at3p::pipeline_run(e->at3p, w.pcm.p, s0, n, S, F, started, w.out.p, w.stream, slot, &e->launches, &why, &prof);
             if (rc) return bail(fail(rc == -3 ? ATDE_ERR_NOMEM : ATDE_ERR_CUDA, "ATRAC3plus pipeline: %s (%s)", why, cudaGetErrorString(cudaGetLastError())));
-        } else if (at3) rc = run_at3(e, w, w.pcm.p, s0, n, F, started, w.out.p);
+        } else if (at3) rc = run_at3(e, w, ring ? d_chunk_pcm : w.pcm.p, s0, n, F, started, w.out.p, ring ? pcm_consumed : nullptr);
         else rc = run_at1(e, w, w.pcm.p, s0, n, F, w.out.p, sizes ? w.sizes.p : nullptr);
         if (rc) return bail(rc);
         if (ordered) {
@@ -827,6 +888,7 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
             CKB(cudaMemcpyAsync(sizes + (size_t)s0 * units_per_stream, w.sizes.p, (size_t)n * units_per_stream * sizeof(int),
                                cudaMemcpyDeviceToHost, w.stream));
     }
+    if (e->copy_stream) CK(cudaStreamSynchronize(e->copy_stream));
     for (int i = 0; i < atde_encoder::kSlots; i++) CK(cudaStreamSynchronize(e->ws[i].stream));
 #undef CKB
     if (sizes && at3)                                  // every WriteFrame payload is exactly FrameSz bytes

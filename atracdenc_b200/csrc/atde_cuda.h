@@ -57,6 +57,7 @@ struct f32x2 { float x, y; };
 #ifdef ATDE_CPU_EMU
 ATDE_D f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; r.x = fmul(a.x, b.x); r.y = fmul(a.y, b.y); return r; }
 ATDE_D f32x2 add2(f32x2 a, f32x2 b, f32x2 /*one*/) { f32x2 r; r.x = fadd(a.x, b.x); r.y = fadd(a.y, b.y); return r; }
+ATDE_D f32x2 sub2(f32x2 a, f32x2 b, f32x2 /*mone*/) { f32x2 r; r.x = fsub(a.x, b.x); r.y = fsub(a.y, b.y); return r; }
 #else
 ATDE_D unsigned long long pack2(f32x2 a)
 {
@@ -80,6 +81,13 @@ ATDE_D f32x2 add2(f32x2 a, f32x2 b, f32x2 one)
 {
     unsigned long long r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(one)), "l"(pack2(b)));
+    return unpack2(r);
+}
+// a - b as b * (-1) + a with MONE = (-1.0f, -1.0f), opaque like ONE: the product is exact, one rounding
+ATDE_D f32x2 sub2(f32x2 a, f32x2 b, f32x2 mone)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(b)), "l"(pack2(mone)), "l"(pack2(a)));
     return unpack2(r);
 }
 #endif

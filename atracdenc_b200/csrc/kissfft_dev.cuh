@@ -45,6 +45,53 @@ ATDE_D void kf_bfly4(cpx& f0, cpx& f1, cpx& f2, cpx& f3, cpx t1, cpx t2, cpx t3)
     }
 }
 
+// ---- the same butterfly on packed fp32 pairs (FMUL2 / FFMA2): 22 issue slots instead of 34 ----
+// A twiddle t is stored pre-spread as (t.r, t.r | t.i, -t.i).  With a = (a.r, a.i) as one pair,
+//   P = a * (t.r, t.r)  = (a.r t.r,  a.i t.r)          Q = a * (t.i, -t.i) = (a.r t.i, -(a.i t.i))
+// hold C_MUL's four rounded products (a product by a negated factor is the negated product), and
+//   m.r = P.x + Q.y = a.r t.r - a.i t.i,   m.i = Q.x + P.y = a.r t.i + a.i t.r
+// are its two rounded sums.  The six complex additions of the butterfly are packed adds (spelled as FMAs by an opaque
+// +-1, see add2), the closing four mix real and imaginary parts and stay scalar.
+struct __align__(16) tw4 { float rr0, rr1, ii0, ii1; };
+inline tw4 spread_twiddle(cpx t) { tw4 w; w.rr0 = t.r; w.rr1 = t.r; w.ii0 = t.i; w.ii1 = -t.i; return w; }
+// the same from a compact twiddle, on the device (two extra instructions; pays when the twiddle is used more than once
+// or when the wider table would not stay cached)
+ATDE_D tw4 spread_twiddle_dev(cpx t, float mone) { tw4 w; w.rr0 = t.r; w.rr1 = t.r; w.ii0 = t.i; w.ii1 = fmul(t.i, mone); return w; }
+ATDE_D cpx cmul_tw(cpx a, tw4 t)
+{
+    f32x2 av, rr, ii;
+    av.x = a.r; av.y = a.i;
+    rr.x = t.rr0; rr.y = t.rr1;
+    ii.x = t.ii0; ii.y = t.ii1;
+    const f32x2 P = mul2(av, rr), Q = mul2(av, ii);
+    cpx m;
+    m.r = fadd(P.x, Q.y);
+    m.i = fadd(Q.x, P.y);
+    return m;
+}
+ATDE_D f32x2 as2(cpx a) { f32x2 v; v.x = a.r; v.y = a.i; return v; }
+ATDE_D cpx as_cpx(f32x2 v) { cpx a; a.r = v.x; a.i = v.y; return a; }
+template <bool INVERSE>
+ATDE_D void kf_bfly4_packed(cpx& f0, cpx& f1, cpx& f2, cpx& f3, tw4 t1, tw4 t2, tw4 t3, f32x2 one, f32x2 mone)
+{
+    const f32x2 s0 = as2(cmul_tw(f1, t1));
+    const f32x2 s1 = as2(cmul_tw(f2, t2));
+    const f32x2 s2 = as2(cmul_tw(f3, t3));
+    const f32x2 s5 = sub2(as2(f0), s1, mone);
+    f32x2 g0 = add2(as2(f0), s1, one);
+    const f32x2 s3 = add2(s0, s2, one);
+    const f32x2 s4 = sub2(s0, s2, mone);
+    f2 = as_cpx(sub2(g0, s3, mone));
+    f0 = as_cpx(add2(g0, s3, one));
+    if (INVERSE) {
+        f1.r = fsub(s5.x, s4.y);  f1.i = fadd(s5.y, s4.x);
+        f3.r = fadd(s5.x, s4.y);  f3.i = fsub(s5.y, s4.x);
+    } else {
+        f1.r = fadd(s5.x, s4.y);  f1.i = fsub(s5.y, s4.x);
+        f3.r = fsub(s5.x, s4.y);  f3.i = fadd(s5.y, s4.x);
+    }
+}
+
 // One radix-4 butterfly of a stage, operating in place on `buf` (shared memory).
 //   v      : butterfly number within this FFT instance, 0 <= v < n/4
 //   m      : sub-length of the stage;  fstride = n/(4*m)

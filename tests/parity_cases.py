@@ -665,9 +665,10 @@ def check_at3p_batch_split_invariance(lib, S=2, F=9, C=2, cuts=(1, 3, 2), seed=1
 
 
 def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700):
-    """atde_encode_batch() splits the streams of a batch into chunks (a short first one, then equal ones, on two
-    pipeline slots).  Forced down to four streams per chunk (1 + 4 + 4 + ...), the result must equal the
-    single-chunk batch, also on the continuation batch that starts from carried state."""
+    """atde_encode_batch() splits the streams of a batch into chunks (a short first one, then equal ones, on three
+    pipeline slots; ATRAC3 PCM through a ring of four staging buffers).  Forced down to four streams per chunk
+    (1 + 4 + 4 + ...) and to two (six chunks: the staging ring wraps), the result must equal the single-chunk batch,
+    also on the continuation batch that starts from carried state, and the int16 entry point must agree."""
     import os
     step = {ab.CODEC_ATRAC1: 512, ab.CODEC_ATRAC3: 1024, ab.CODEC_ATRAC3PLUS: 2048}[codec]
     rng = np.random.default_rng(seed)
@@ -676,17 +677,24 @@ def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700):
     old = os.environ.pop("ATDE_CHUNK_STREAMS", None)
     try:
         outs = []
-        for streams in (None, "4"):
+        q = np.clip(np.rint(pcm * 32768.0), -32768, 32767).astype(np.int16)
+        pcm = (q.astype(np.float32) * np.float32(1.0 / 32768.0)).astype(np.float32)
+        for streams in (None, "4", "2", "2/i16"):
             if streams:
-                os.environ["ATDE_CHUNK_STREAMS"] = streams
+                os.environ["ATDE_CHUNK_STREAMS"] = streams.split("/")[0]
             enc = ab.Encoder(codec, C, lib=lib)
-            a = enc.encode(pcm[:, :F * step], S, want_sizes=True)
-            b = enc.encode(pcm[:, F * step:], S, want_sizes=True)
+            if streams and streams.endswith("i16"):
+                a = enc.encode_i16(q[:, :F * step], S, want_sizes=True)
+                b = enc.encode_i16(q[:, F * step:], S, want_sizes=True)
+            else:
+                a = enc.encode(pcm[:, :F * step], S, want_sizes=True)
+                b = enc.encode(pcm[:, F * step:], S, want_sizes=True)
             enc.close()
             outs.append((a, b))
-        for (x, xs), (y, ys) in zip(outs[0], outs[1]):
-            assert np.array_equal(xs, ys)
-            assert np.array_equal(x, y)
+        for other in outs[1:]:
+            for (x, xs), (y, ys) in zip(outs[0], other):
+                assert np.array_equal(xs, ys)
+                assert np.array_equal(x, y)
     finally:
         os.environ.pop("ATDE_CHUNK_STREAMS", None)
         if old is not None:

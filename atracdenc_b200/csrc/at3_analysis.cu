@@ -343,7 +343,7 @@ ATDE_D void fwd_bfly(cpx* buf, int p, int d, cpx t1, cpx t2, cpx t3)
     buf[p] = f0; buf[p + d] = f1; buf[p + 2 * d] = f2; buf[p + 3 * d] = f3;
 }
 
-// One (stream, channel, band, frame) per block.
+// Two consecutive frames of one (stream, channel, band) per block.
 //
 // kiss_fftri(4096) = pre-processing + inverse complex FFT-2048 (4x4x4x4x4x2).  kissfft's decimation
 // in time is restated as a digit-reversed gather followed by the stages innermost first; the stages
@@ -365,104 +365,117 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
 {
     __shared__ __align__(16) cpx big[2048 + 256 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ tw4 tw2c[15][8];                      // pass-2 twiddles of lane group k, compact, pre-spread for the packed butterfly
-    __shared__ __align__(16) cpx fwd[257 + 17];
-    __shared__ __align__(16) cpx freq[257 + 17];
-    // super4096[k - 1] at fq(k), k = 1..256, moves into the forward FFT buffer once that is dead: every KB of shared
-    // memory saved is L1 for the twiddle tables (a separate 2 KB array cost 3.6 ms per 10^6 frames)
-    cpx* const sup = fwd;
-    float* const micro = reinterpret_cast<float*>(fwd);   // 256 micro-chunk RMS values: the forward FFT buffer is dead by then
-    __shared__ float sgain[96];
-    __shared__ double esum_part[kGainThreads / 32][2];   // per-warp partial sums of (|X_k|^2, |X_k H_k|^2)
+    __shared__ __align__(16) cpx freq2[2][257 + 17]; // spectra of the block's two frames
+    __shared__ __align__(16) cpx sup[257 + 17];      // super4096[k - 1] at fq(k), k = 1..256
+    // Shared memory is the kernel's occupancy limit (8 blocks per SM) and every KB saved is L1 for the twiddle tables, so
+    // the big buffer is used three times over: the two forward FFT buffers live in it while the forward transforms run,
+    // and once a frame's real output lies in its first 2176 floats, the 256 micro-chunk RMS values and the 96 output
+    // values are staged behind them
+    cpx (*const fwd2)[257 + 17] = reinterpret_cast<cpx (*)[257 + 17]>(big);
+    float* const micro = reinterpret_cast<float*>(big) + 2304;
+    float* const sgain = reinterpret_cast<float*>(big) + 2560;
+    __shared__ double esum_part[kGainThreads / 32][2];   // per-warp partial sums of (|X_k|^2, |X_k H_k|^2): warps 2h, 2h+1 = frame h
     __shared__ float sstat[2];
 
     const DevTables* __restrict__ T = b.tab;
-    const int f = blockIdx.x;
+    // A block takes TWO consecutive frames of one (stream, channel, band).  The forward FFT-256 has 64 butterflies per
+    // stage: the two halves of the block run the two frames' forward transforms side by side (every thread busy, half
+    // the barriers per frame); the inverse FFT-2048 wants all 128 threads and runs for one frame after the other.
+    const int f0 = 2 * blockIdx.x;
+    const int n_fr = min(2, g.n_out - f0);
     const int band = blockIdx.y % kGainBands, c = blockIdx.y / kGainBands;
     const int s = blockIdx.z;
-    const float* __restrict__ in = b.bands + (((size_t)s * g.C + c) * 4 + band) * g.BL + 256 * (size_t)f;
     const int tid = threadIdx.x;
+    const int half = tid >> 6, t = tid & 63;
+    const bool act = half < n_fr;
+    const float* __restrict__ in = b.bands + (((size_t)s * g.C + c) * 4 + band) * g.BL + 256 * (size_t)(f0 + half);
+    cpx* const fwd = fwd2[half];
     const cpx* __restrict__ tw = T->tw2048;
 
     if (tid < 120) reinterpret_cast<float4*>(&tw2c[0][0])[tid] = reinterpret_cast<const float4*>(&T->gtw2[0][0])[tid];
     f32x2 one2, mone2;
     one2.x = one2.y = g.one;
     mone2.x = mone2.y = -g.one;
-    // the only super-twiddles kiss_fftri(4096) meets with a non-zero operand (fetched now, parked in registers until
-    // the buffer is free)
-    cpx sup_reg[2];
-    sup_reg[0] = T->super4096[tid];
-    sup_reg[1] = T->super4096[tid + kGainBlock];
+    // the only super-twiddles kiss_fftri(4096) meets with a non-zero operand
+    sup[fq(1 + tid)] = T->super4096[tid];
+    sup[fq(1 + tid + kGainBlock)] = T->super4096[tid + kGainBlock];
     // 1. Planck window, packed as the complex input of the half-size FFT; loaded in natural order and
     //    stored at its digit-reversed slot (base-4 reversal of 4 digits is an involution)
-    ATDE_PAR_FOR(j, 256) {
-        const float2 x = *reinterpret_cast<const float2*>(in + 2 * j);
-        const float2 w = *reinterpret_cast<const float2*>(&T->planck[2 * j]);
-        cpx z;
-        z.r = fmul(x.x, w.x);
-        z.i = fmul(x.y, w.y);
-        const int o = ((j & 3) << 6) | (((j >> 2) & 3) << 4) | (((j >> 4) & 3) << 2) | (j >> 6);
-        fwd[fq(o)] = z;
+    if (act) {
+        for (int j = t; j < 256; j += 64) {
+            const float2 x = *reinterpret_cast<const float2*>(in + 2 * j);
+            const float2 w = *reinterpret_cast<const float2*>(&T->planck[2 * j]);
+            cpx z;
+            z.r = fmul(x.x, w.x);
+            z.i = fmul(x.y, w.y);
+            const int o = ((j & 3) << 6) | (((j >> 2) & 3) << 4) | (((j >> 4) & 3) << 2) | (j >> 6);
+            fwd[fq(o)] = z;
+        }
     }
     __syncthreads();
     // 2. forward complex FFT-256 = 4x4x4x4, innermost stage first; the lane -> butterfly map of every
     //    stage is chosen so that 16 consecutive lanes touch 16 different bank pairs
     //    (padded addresses: element F + m q of a butterfly lies at fq(F) + q * (m + m / 16))
-    if (tid < 64) fwd_bfly(fwd, 4 * tid + (tid >> 2), 1, T->ftw[0][0][0], T->ftw[0][1][0], T->ftw[0][2][0]);
+    if (act) fwd_bfly(fwd, 4 * t + (t >> 2), 1, T->ftw[0][0][0], T->ftw[0][1][0], T->ftw[0][2][0]);
     __syncthreads();
-    if (tid < 64) {
-        const int gq = tid & 15, k = tid >> 4;
+    if (act) {
+        const int gq = t & 15, k = t >> 4;
         fwd_bfly(fwd, 17 * gq + k, 4, T->ftw[1][0][k], T->ftw[1][1][k], T->ftw[1][2][k]);
     }
     __syncthreads();
-    if (tid < 64) {
-        const int gq = tid >> 4, k = tid & 15;
+    if (act) {
+        const int gq = t >> 4, k = t & 15;
         fwd_bfly(fwd, 68 * gq + k, 17, T->ftw[2][0][k], T->ftw[2][1][k], T->ftw[2][2][k]);
     }
     __syncthreads();
-    if (tid < 64) fwd_bfly(fwd, tid + (tid >> 4), 68, T->ftw[3][0][tid], T->ftw[3][1][tid], T->ftw[3][2][tid]);
+    if (act) fwd_bfly(fwd, t + (t >> 4), 68, T->ftw[3][0][t], T->ftw[3][1][t], T->ftw[3][2][t]);
     __syncthreads();
     // kiss_fftr post-processing (kiss_fftr.c:84-115)
-    ATDE_PAR_FOR(k, 129) {
-        if (k == 0) {
-            const float tr = fwd[0].r, ti = fwd[0].i;
-            freq[0].r = fadd(tr, ti);   freq[0].i = 0.0f;
-            freq[fq(256)].r = fsub(tr, ti); freq[fq(256)].i = 0.0f;
-        } else {
-            const cpx fpk = fwd[fq(k)];
-            cpx fpnk; fpnk.r = fwd[fq(256 - k)].r; fpnk.i = -fwd[fq(256 - k)].i;
-            cpx f1k, f2k;
-            f1k.r = fadd(fpk.r, fpnk.r); f1k.i = fadd(fpk.i, fpnk.i);
-            f2k.r = fsub(fpk.r, fpnk.r); f2k.i = fsub(fpk.i, fpnk.i);
-            const cpx t2 = cmul(f2k, T->super512[k - 1]);
-            cpx a, bb;
-            a.r = fmul(fadd(f1k.r, t2.r), 0.5f);  a.i = fmul(fadd(f1k.i, t2.i), 0.5f);
-            bb.r = fmul(fsub(f1k.r, t2.r), 0.5f); bb.i = fmul(fsub(t2.i, f1k.i), 0.5f);
-            freq[fq(k)] = a;                   // k == 128 writes the same element twice: the second
-            freq[fq(256 - k)] = bb;            // store (freqdata[ncfft-k]) wins, as in the reference
+    if (act) {
+        cpx* const fo = freq2[half];
+        for (int k = t; k < 129; k += 64) {
+            if (k == 0) {
+                const float tr = fwd[0].r, ti = fwd[0].i;
+                fo[0].r = fadd(tr, ti);   fo[0].i = 0.0f;
+                fo[fq(256)].r = fsub(tr, ti); fo[fq(256)].i = 0.0f;
+            } else {
+                const cpx fpk = fwd[fq(k)];
+                cpx fpnk; fpnk.r = fwd[fq(256 - k)].r; fpnk.i = -fwd[fq(256 - k)].i;
+                cpx f1k, f2k;
+                f1k.r = fadd(fpk.r, fpnk.r); f1k.i = fadd(fpk.i, fpnk.i);
+                f2k.r = fsub(fpk.r, fpnk.r); f2k.i = fsub(fpk.i, fpnk.i);
+                const cpx t2 = cmul(f2k, T->super512[k - 1]);
+                cpx a, bb;
+                a.r = fmul(fadd(f1k.r, t2.r), 0.5f);  a.i = fmul(fadd(f1k.i, t2.i), 0.5f);
+                bb.r = fmul(fsub(f1k.r, t2.r), 0.5f); bb.i = fmul(fsub(t2.i, f1k.i), 0.5f);
+                fo[fq(k)] = a;                     // k == 128 writes the same element twice: the second
+                fo[fq(256 - k)] = bb;              // store (freqdata[ncfft-k]) wins, as in the reference
+            }
         }
     }
     __syncthreads();
     // 2a. high-frequency energy ratio (upsampler.cpp:99-118).  The reference adds the 257 per-bin energies (and the
     //     HPF-weighted ones) SEQUENTIALLY in double and hands float(hi / tot) to the curve builder, where the value is
     //     only ever COMPARED with kHighFreqThreshold = 0.05f and with 0.3f (atrac3denc.cpp:352,431).  Here the two sums
-    //     are taken as a tree over the block — any summation order of 257 non-negative doubles agrees with the
-    //     sequential one to 257 * 2^-53 relative, the ratio to ~1.2e-13 — and a result that lands within 1e-7
+    //     are taken as a tree over the frame's two warps — any summation order of 257 non-negative doubles agrees with
+    //     the sequential one to 257 * 2^-53 relative, the ratio to ~1.2e-13 — and a result that lands within 1e-7
     //     (relative) of one of the two thresholds, where the float rounding of the ratio could decide a comparison
     //     differently, is recomputed with the reference's sequential loop at the end of the kernel.
     const int lcb = T->low_cut_bin;
-    sup[fq(1 + tid)] = sup_reg[0];
-    sup[fq(1 + tid + kGainBlock)] = sup_reg[1];
     {
         double tot = 0.0, hi = 0.0;
-        for (int k = tid; k < 257; k += kGainThreads) {
-            const cpx z = freq[fq(k)];
-            const double r = (double)z.r, i = (double)z.i;
-            const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
-            float H = 0.0f;
-            if (k >= lcb + 2) H = 1.0f;
-            else if (k >= lcb) H = T->hpf_h[k - lcb];
-            tot = __dadd_rn(tot, e);
-            hi = __dadd_rn(hi, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
+        if (act) {
+            const cpx* const fi = freq2[half];
+            for (int k = t; k < 257; k += 64) {
+                const cpx z = fi[fq(k)];
+                const double r = (double)z.r, i = (double)z.i;
+                const double e = __dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i));
+                float H = 0.0f;
+                if (k >= lcb + 2) H = 1.0f;
+                else if (k >= lcb) H = T->hpf_h[k - lcb];
+                tot = __dadd_rn(tot, e);
+                hi = __dadd_rn(hi, __dmul_rn(__dmul_rn(e, (double)H), (double)H));
+            }
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
@@ -472,6 +485,9 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         if ((tid & 31) == 0) { esum_part[tid >> 5][0] = tot; esum_part[tid >> 5][1] = hi; }
     }
     __syncthreads();
+    for (int it = 0; it < n_fr; it++) {
+    const cpx* const freq = freq2[it];
+    const int f = f0 + it;
     // 3/4. inverse FFT input Y[k] = 8*X[k]*H[k] (Nyquist bin halved), kiss_fftri pre-processing
     //      (kiss_fftr.c:131-151) with Y[2048-k] == 0, and pass 1 of the inverse FFT.
     auto tmp_pair = [&](int k, cpx& lo, cpx& hi) {
@@ -687,8 +703,8 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
     if (tid < 96) b.gain[item * 96 + tid] = sgain[tid];
     if (tid == 0) {
-        double tot = __dadd_rn(__dadd_rn(esum_part[0][0], esum_part[1][0]), __dadd_rn(esum_part[2][0], esum_part[3][0]));
-        double hi = __dadd_rn(__dadd_rn(esum_part[0][1], esum_part[1][1]), __dadd_rn(esum_part[2][1], esum_part[3][1]));
+        double tot = __dadd_rn(esum_part[2 * it][0], esum_part[2 * it + 1][0]);
+        double hi = __dadd_rn(esum_part[2 * it][1], esum_part[2 * it + 1][1]);
         if (tot > 0.0) {
             const double ratio = __ddiv_rn(hi, tot);
             const double t1 = (double)0.05f, t2 = (double)0.3f;
@@ -713,11 +729,13 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         st4.w = sgain[31];
         reinterpret_cast<float4*>(b.gstat)[item] = st4;
     }
+        __syncthreads();                       // the staged values are read: pass 1 of the next frame may overwrite them
+    }   // frames of the block
 }
 
 void launch_gain_analysis(const Geometry& g, const Buffers& b, cudaStream_t st)
 {
-    dim3 grid(g.n_out, g.C * kGainBands, g.S);
+    dim3 grid((g.n_out + 1) / 2, g.C * kGainBands, g.S);      // two frames per block
     ATDE_LAUNCH(at3_gain_kernel, grid, kGainBlock, 0, st, g, b);
 }
 

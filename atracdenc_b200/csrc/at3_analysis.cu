@@ -321,10 +321,12 @@ ATDE_D float plateau_target_warp(float a, int lane)
 constexpr int kGainThreads = 128;         // threads per block
 constexpr int kGainBlock = kGainThreads;
 
-// The 2048-point buffer is padded by one element per 8 (pass 1 stores 8 consecutive slots per thread:
-// a 9-element thread stride is conflict-free) and by 8 more per 128 (so the eight-lane groups of
-// pass 2, 128 slots apart, land on the other half of the banks).
-ATDE_D int gphys(int i) { return i + (i >> 3) + ((i >> 7) << 3); }
+// The 2048-point buffer is padded by one element per 16.  With 8-byte elements a half-warp access is conflict-free when
+// its 16 addresses differ mod 16, and this one padding gives that to all three passes:
+//   pass 1  thread grp stores slots 8 grp + j:             8 grp + grp / 2 + j       -> grp / 2 + 8 (grp & 1) + j  (mod 16)
+//   pass 2  lanes (k < 8, two groups G):                   136 G + k + const         -> k + 8 (G & 1) + const
+//   pass 3  16 consecutive k:                              k + k / 16 + const        -> a rotation of 0..15
+ATDE_D int gphys(int i) { return i + (i >> 4); }
 // The real output signal is padded by 4 floats per 64 so that the 32 sequential 64-sample RMS sums
 // (one lane each, 64 floats apart) read different banks.
 ATDE_D int sphys(int j) { return j + ((j >> 6) << 2); }
@@ -363,7 +365,7 @@ ATDE_D void fwd_bfly(cpx* buf, int p, int d, cpx t1, cpx t2, cpx t3)
 #endif
 __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(Geometry g, Buffers b)
 {
-    __shared__ __align__(16) cpx big[2048 + 256 + 128];    // inverse FFT buffer, padded; later the real output
+    __shared__ __align__(16) cpx big[2048 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ tw4 tw2c[15][8];                      // pass-2 twiddles of lane group k, compact, pre-spread for the packed butterfly
     __shared__ __align__(16) cpx freq2[2][257 + 17]; // spectra of the block's two frames
     __shared__ __align__(16) cpx sup[257 + 17];      // super4096[k - 1] at fq(k), k = 1..256
@@ -595,14 +597,14 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     atde_named_barrier(1, kGainThreads);
     // pass 2: radix-4 m = 8 (fstride 64), then m = 32 (fstride 16)
     {
-        // gphys(base + k + 8a + 32q) = gphys(base + k) + 9a + 36q  (k < 8, base a multiple of 128)
+        // gphys(base + k + 8a + 32q) = gphys(base + k) + 8a + a / 2 + 34q  (k < 8, base a multiple of 128)
         const int k = tid & 7;
         cpx* const bg = big + gphys(((tid >> 3) << 7) + k);
         cpx x[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) x[a][q] = bg[9 * a + 36 * q];
+            for (int q = 0; q < 4; q++) x[a][q] = bg[8 * a + (a >> 1) + 34 * q];
         {
             const tw4 t1 = tw2c[0][k], t2 = tw2c[1][k], t3 = tw2c[2][k];      // tw[64k], tw[128k], tw[192k]
 #pragma unroll
@@ -614,19 +616,19 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) bg[9 * a + 36 * q] = x[a][q];
+            for (int q = 0; q < 4; q++) bg[8 * a + (a >> 1) + 34 * q] = x[a][q];
     }
     atde_named_barrier(1, kGainThreads);
     // pass 3: radix-4 m = 128 (fstride 4), then m = 512 (fstride 1); keep slots [512, 1536), normalised
     {
-        // gphys(k + 128a + 512q) = k + k / 8 + 152a + 608q  (k < 128)
+        // gphys(k + 128a + 512q) = k + k / 16 + 136a + 544q  (k < 128)
         const int k = tid;
-        const cpx* const bg = big + k + (k >> 3);
+        const cpx* const bg = big + k + (k >> 4);
         cpx x[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) x[a][q] = bg[152 * a + 608 * q];
+            for (int q = 0; q < 4; q++) x[a][q] = bg[136 * a + 544 * q];
         atde_named_barrier(1, kGainThreads);                                  // every slot is in registers: big can be overwritten
         {
             const float mone = mone2.x;

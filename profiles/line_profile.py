@@ -32,7 +32,7 @@ base = int(rows[2][col['Address']], 16)
 agg = defaultdict(lambda: [0, 0, 0, 0, 0]); stalls = defaultdict(lambda: defaultdict(int)); tot = [0, 0, 0]
 ops = defaultdict(int); allst = defaultdict(int)
 for r in rows[2:]:
-    if len(r) < len(hdr):
+    if len(r) < len(hdr) or r[col['Address']] == 'Address':
         continue
     off = int(r[col['Address']], 16) - base
     key = line_of.get(off)

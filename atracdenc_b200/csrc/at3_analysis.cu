@@ -366,7 +366,9 @@ ATDE_D void fwd_bfly(cpx* buf, int p, int d, cpx t1, cpx t2, cpx t3)
 __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(Geometry g, Buffers b)
 {
     __shared__ __align__(16) cpx big[2048 + 128];    // inverse FFT buffer, padded; later the real output
-    __shared__ tw4 tw2c[15][8];                      // pass-2 twiddles of lane group k, compact, pre-spread for the packed butterfly
+    __shared__ __align__(8) cpx tw2c[15][8];         // pass-2 twiddles of lane group k (8-byte elements: a 16-byte pre-spread
+                                                     // form costs four wavefronts per warp load instead of two, and the
+                                                     // kernel is bound by the shared-memory pipe)
     __shared__ __align__(16) cpx freq2[2][257 + 17]; // spectra of the block's two frames
     __shared__ __align__(16) cpx sup[257 + 17];      // super4096[k - 1] at fq(k), k = 1..256
     // Shared memory is the kernel's occupancy limit (8 blocks per SM) and every KB saved is L1 for the twiddle tables, so
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     cpx* const fwd = fwd2[half];
     const cpx* __restrict__ tw = T->tw2048;
 
-    if (tid < 120) reinterpret_cast<float4*>(&tw2c[0][0])[tid] = reinterpret_cast<const float4*>(&T->gtw2[0][0])[tid];
+    if (tid < 120) (&tw2c[0][0])[tid] = (&T->gtw2[0][0])[tid];
     f32x2 one2, mone2;
     one2.x = one2.y = g.one;
     mone2.x = mone2.y = -g.one;
@@ -606,13 +608,15 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
 #pragma unroll
             for (int q = 0; q < 4; q++) x[a][q] = bg[8 * a + (a >> 1) + 34 * q];
         {
-            const tw4 t1 = tw2c[0][k], t2 = tw2c[1][k], t3 = tw2c[2][k];      // tw[64k], tw[128k], tw[192k]
+            const tw4 t1 = spread_twiddle_dev(tw2c[0][k], mone2.x), t2 = spread_twiddle_dev(tw2c[1][k], mone2.x),
+                      t3 = spread_twiddle_dev(tw2c[2][k], mone2.x);           // tw[64k], tw[128k], tw[192k]
 #pragma unroll
             for (int q = 0; q < 4; q++) kf_bfly4_packed<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3, one2, mone2);
         }
 #pragma unroll
         for (int a = 0; a < 4; a++)                                            // kk = k + 8a: tw[16kk], tw[32kk], tw[48kk]
-            kf_bfly4_packed<true>(x[a][0], x[a][1], x[a][2], x[a][3], tw2c[3 + 3 * a][k], tw2c[4 + 3 * a][k], tw2c[5 + 3 * a][k], one2, mone2);
+            kf_bfly4_packed<true>(x[a][0], x[a][1], x[a][2], x[a][3], spread_twiddle_dev(tw2c[3 + 3 * a][k], mone2.x),
+                                  spread_twiddle_dev(tw2c[4 + 3 * a][k], mone2.x), spread_twiddle_dev(tw2c[5 + 3 * a][k], mone2.x), one2, mone2);
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -660,7 +664,7 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         float a = 0.0f;
 #pragma unroll
         for (int i = 0; i < 8; i++) a = fadd(a, fmul(p[i], p[i]));
-        micro[q] = __fsqrt_rn(__fdiv_rn(a, 8.0f));
+        micro[q] = __fsqrt_rn(fmul(a, 0.125f));               // a / 8: a product by a power of two is the same rounded quotient
     }
     if (tid >= 32 && tid < 64) {
         const int sf = tid - 32;
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
             a = fadd(a, fmul(q.x, q.x)); a = fadd(a, fmul(q.y, q.y));
             a = fadd(a, fmul(q.z, q.z)); a = fadd(a, fmul(q.w, q.w));
         }
-        sgain[sf] = __fsqrt_rn(__fdiv_rn(a, 64.0f));
+        sgain[sf] = __fsqrt_rn(fmul(a, 0.015625f));         // a / 64
     }
     atde_named_barrier(1, kGainThreads);
     if (tid < 32) {

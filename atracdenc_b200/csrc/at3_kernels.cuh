@@ -46,10 +46,10 @@ struct DevTables {
     unsigned short iperm2048[2048];   // input index k -> gather slot of the digit-reversed order
     // the same twiddles regrouped per kernel pass so that consecutive lanes read consecutive elements
     cpx ftw[4][3][64];                // forward FFT-256, stage st (m = 4^st): tw256[(q+1) k (64/m)], k < m
-    // (inverse passes 2 and 3 run on packed pairs: pass-2 twiddles pre-spread as (r, r | i, -i), kissfft_dev.cuh)
-    tw4 gtw2[15][8];                  // inverse pass 2, lane group k: tw2048[64k(q+1)] | tw2048[16(k+8a)(q+1)]
-    cpx gtw3a[3][128];                // inverse pass 3, m = 128: tw2048[4k(q+1)]   (compact: spread on the fly, the wider
-    cpx gtw3b[4][3][128];             // inverse pass 3, m = 512: tw2048[(k+128a)(q+1)]   tables fall out of the small L1)
+    // (inverse passes 2 and 3 run on packed pairs; the twiddles are spread to (r, r | i, -i) on the fly, kissfft_dev.cuh)
+    cpx gtw2[15][8];                  // inverse pass 2, lane group k: tw2048[64k(q+1)] | tw2048[16(k+8a)(q+1)]
+    cpx gtw3a[3][128];                // inverse pass 3, m = 128: tw2048[4k(q+1)]
+    cpx gtw3b[4][3][128];             // inverse pass 3, m = 512: tw2048[(k+128a)(q+1)]
 };
 
 // Gain curve of one (stream, channel, band, frame): n points, each level (4 bit) / location (5 bit)

@@ -277,9 +277,9 @@ int build_at3_tables(atde_encoder* e)
     }
     for (int k = 0; k < 8; k++) {
         for (int q = 0; q < 3; q++) {
-            h->gtw2[q][k] = atde::spread_twiddle(h->tw2048[(size_t)64 * k * (q + 1)]);
+            h->gtw2[q][k] = h->tw2048[(size_t)64 * k * (q + 1)];
             for (int a = 0; a < 4; a++)
-                h->gtw2[3 + 3 * a + q][k] = atde::spread_twiddle(h->tw2048[(size_t)16 * (k + 8 * a) * (q + 1)]);
+                h->gtw2[3 + 3 * a + q][k] = h->tw2048[(size_t)16 * (k + 8 * a) * (q + 1)];
         }
     }
     for (int k = 0; k < 128; k++)

@@ -46,16 +46,15 @@ ATDE_D void kf_bfly4(cpx& f0, cpx& f1, cpx& f2, cpx& f3, cpx t1, cpx t2, cpx t3)
 }
 
 // ---- the same butterfly on packed fp32 pairs (FMUL2 / FFMA2): 22 issue slots instead of 34 ----
-// A twiddle t is stored pre-spread as (t.r, t.r | t.i, -t.i).  With a = (a.r, a.i) as one pair,
+// A twiddle t is spread to (t.r, t.r | t.i, -t.i).  With a = (a.r, a.i) as one pair,
 //   P = a * (t.r, t.r)  = (a.r t.r,  a.i t.r)          Q = a * (t.i, -t.i) = (a.r t.i, -(a.i t.i))
 // hold C_MUL's four rounded products (a product by a negated factor is the negated product), and
 //   m.r = P.x + Q.y = a.r t.r - a.i t.i,   m.i = Q.x + P.y = a.r t.i + a.i t.r
 // are its two rounded sums.  The six complex additions of the butterfly are packed adds (spelled as FMAs by an opaque
 // +-1, see add2), the closing four mix real and imaginary parts and stay scalar.
 struct __align__(16) tw4 { float rr0, rr1, ii0, ii1; };
-inline tw4 spread_twiddle(cpx t) { tw4 w; w.rr0 = t.r; w.rr1 = t.r; w.ii0 = t.i; w.ii1 = -t.i; return w; }
-// the same from a compact twiddle, on the device (two extra instructions; pays when the twiddle is used more than once
-// or when the wider table would not stay cached)
+// (spread on the fly, two extra instructions: 16-byte table entries were measured slower — they double the shared-memory
+// wavefronts of a warp load and the L1 footprint of the global tables)
 ATDE_D tw4 spread_twiddle_dev(cpx t, float mone) { tw4 w; w.rr0 = t.r; w.rr1 = t.r; w.ii0 = t.i; w.ii1 = fmul(t.i, mone); return w; }
 ATDE_D cpx cmul_tw(cpx a, tw4 t)
 {

@@ -120,10 +120,13 @@ int pipeline_run(StreamState* st, const float* d_pcm, int s0, int S, int total, 
     const int TS = nA + 2;                                    // tone records per stream: two carried + new
     StreamState::Work& w = st->w[slot];
     const int gha_blocks = gha_blocks_for((long long)S * (nA > 0 ? nA : 1));
-    if (!w.bands.ensure((size_t)S * C * L * kFrame) || !w.resid.ensure((size_t)S * C * (nA + 1) * kFrame) ||
-        !w.specs.ensure((size_t)S * (nA > 0 ? nA : 1) * C * kFrame) || !w.tones.ensure((size_t)S * TS) ||
-        !w.frame_out.ensure((size_t)S * (nA > 0 ? nA : 1) * gha_frame_out_bytes()) ||
-        !w.scratch.ensure(gha_scratch_bytes(gha_blocks))) { *err = "cudaMalloc (workspace)"; return -3; }
+    // (sized for the continuation case, N analyses, also on the first batch with its N - 1: the second call of a run must
+    // not re-allocate in mid-pipeline)
+    const size_t nAmax = (size_t)(N > 0 ? N : 1);
+    if (!w.bands.ensure((size_t)S * C * L * kFrame) || !w.resid.ensure((size_t)S * C * (nAmax + 1) * kFrame) ||
+        !w.specs.ensure((size_t)S * nAmax * C * kFrame) || !w.tones.ensure((size_t)S * (nAmax + 2)) ||
+        !w.frame_out.ensure((size_t)S * nAmax * gha_frame_out_bytes()) ||
+        !w.scratch.ensure(gha_scratch_bytes(gha_blocks_for((long long)S * nAmax)))) { *err = "cudaMalloc (workspace)"; return -3; }
 
     float* band_hist = st->band_hist.p + (size_t)s0 * C * 2 * kFrame;
     float* pcm_tail = st->pcm_tail.p + (size_t)s0 * kPqfOverlap * C;

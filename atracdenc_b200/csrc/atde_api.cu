@@ -19,6 +19,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <algorithm>
 
 namespace {
 
@@ -411,19 +412,22 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
     g.no_tonal = e->cfg.no_tonal != 0;
     g.bfu_idx_const = (int)e->cfg.bfu_idx_const;
     g.one = 1.0f;
-    const size_t units = (size_t)S * (size_t)(g.n_out > 0 ? g.n_out : 1) * C;
-    const size_t items = (size_t)S * C * kGainBands * (size_t)(g.n_out > 0 ? g.n_out : 1);
+    // (work areas are sized for the continuation case — N output frames, one carried frame in the band buffer — also on
+    // a stream's first batch, which produces one frame less: otherwise the second call of a run re-allocates every
+    // buffer in mid-pipeline, and a cudaMalloc synchronises the device)
+    const size_t units = (size_t)S * (size_t)(N > 0 ? N : 1) * C;
+    const size_t items = (size_t)S * C * kGainBands * (size_t)(N > 0 ? N : 1);
     int rc;
-    if ((rc = w.bands.ensure((size_t)S * C * 4 * g.BL))) return rc;
+    if ((rc = w.bands.ensure((size_t)S * C * 4 * (128 + 256 * ((size_t)N + 1))))) return rc;
     if ((rc = w.hist_tmp.ensure((size_t)S * (2 * 1024 * C + C * 4 * 256 + C * 4)))) return rc;
     if ((rc = w.specs.ensure(units * 1024))) return rc;
     if ((rc = w.gscale.ensure(units * 16))) return rc;
     if ((rc = w.chloud.ensure(units))) return rc;
-    if ((rc = w.loud.ensure((size_t)S * (g.n_out > 0 ? g.n_out : 1)))) return rc;
+    if ((rc = w.loud.ensure((size_t)S * (N > 0 ? N : 1)))) return rc;
     if ((rc = w.sfi.ensure(units * 32))) return rc;
     if ((rc = w.energy.ensure(units * 32))) return rc;
     if ((rc = w.tonal.ensure(units))) return rc;
-    if ((rc = w.curves.ensure((size_t)S * C * 4 * (g.n_out > 0 ? g.n_out : 1)))) return rc;
+    if ((rc = w.curves.ensure((size_t)S * C * 4 * (N > 0 ? N : 1)))) return rc;
     if (!g.no_gain) {
         if ((rc = w.gain.ensure(items * 96))) return rc;
         if ((rc = w.gstat.ensure(items * 4))) return rc;
@@ -783,10 +787,25 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     }
     if (chunk < 1) chunk = 1;
     if (chunk > S) chunk = S;
-    const int first = !at3p && chunk >= 4 && chunk < S ? chunk / 4 : chunk;
-    if (!at3p && first < S) {
-        const int rest = S - first, pieces = (rest + chunk - 1) / chunk;
-        chunk = (rest + pieces - 1) / pieces;
+    // The plan: a quarter-size first chunk (the device starts early), equal middle chunks, and a half- and a
+    // quarter-size chunk at the end — when the copy-in is as slow as the kernels (float PCM), the call ends one chunk's
+    // compute after the last byte has arrived, so the last chunk should be short.  ATDE_CHUNK_TAPER=0 turns the taper off.
+    std::vector<int> plan;
+    {
+        const int first = !at3p && chunk >= 4 && chunk < S ? chunk / 4 : chunk;
+        plan.push_back(first);
+        int rest = S - first;
+        const char* tp = getenv("ATDE_CHUNK_TAPER");
+        const bool taper = !at3p && chunk >= 8 && rest > 2 * chunk && !(tp && atoi(tp) == 0);
+        const int t1 = taper ? chunk / 2 : 0, t2 = taper ? chunk / 4 : 0;
+        rest -= t1 + t2;
+        if (rest > 0) {
+            const int pieces = at3p ? (rest + chunk - 1) / chunk : std::max(1, (rest + chunk - 1) / chunk);
+            const int each = at3p ? chunk : (rest + pieces - 1) / pieces;
+            for (int left = rest; left > 0; left -= each) plan.push_back(std::min(each, left));
+        }
+        if (t1) plan.push_back(t1);
+        if (t2) plan.push_back(t2);
     }
     // A failure inside the loop must not return while earlier chunks' copies still use the caller's buffers, and it
     // leaves the carried stream state half advanced: drain both pipeline slots and invalidate the state
@@ -819,15 +838,14 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     int k = 0;
     if (ring) {
         // size the staging buffers before anything is in flight (a cudaMalloc in mid-pipeline synchronises the device)
-        const int n_chunks = 1 + (S - first + chunk - 1) / chunk;
-        const size_t cnt = (size_t)std::max(first, std::min(chunk, S - first)) * pcm_per_stream;
-        for (int i = 0; i < std::min(n_chunks, (int)atde_encoder::kPcmRing); i++)
+        const size_t cnt = (size_t)*std::max_element(plan.begin(), plan.end()) * pcm_per_stream;
+        for (int i = 0; i < std::min((int)plan.size(), (int)atde_encoder::kPcmRing); i++)
             if ((rc = pcm16 ? e->pcm16_ring[i].ensure(cnt + 8) : e->pcm_ring[i].ensure(cnt))) return bail(rc);
     }
-    for (int s0 = 0, n = first; s0 < S; s0 += n, n = chunk, slot = (slot + 1) % n_slots, k++) {
-        if (n > S - s0) n = S - s0;
+    for (int s0 = 0; k < (int)plan.size(); s0 += plan[k], slot = (slot + 1) % n_slots, k++) {
+        const int n = plan[k];
         Workspace& w = e->ws[slot];
-        if ((rc = w.out.ensure((size_t)n * out_per_stream + 1))) return bail(rc);
+        if ((rc = w.out.ensure((size_t)n * F * e->units_per_frame * e->unit_bytes + 1))) return bail(rc);   // (F frames: no growth on the continuation call)
         if (sizes && (rc = w.sizes.ensure((size_t)n * units_per_stream))) return bail(rc);
         if (ring) {
             const int pb = k % atde_encoder::kPcmRing;

@@ -664,11 +664,12 @@ def check_at3p_batch_split_invariance(lib, S=2, F=9, C=2, cuts=(1, 3, 2), seed=1
     assert np.array_equal(np.concatenate(parts, axis=1), whole)
 
 
-def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700):
+def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700, variants=(None, "4", "2", "1", "2/i16")):
     """atde_encode_batch() splits the streams of a batch into chunks (a short first one, then equal ones, on three
     pipeline slots; ATRAC3 PCM through a ring of four staging buffers).  Forced down to four streams per chunk
-    (1 + 4 + 4 + ...) and to two (six chunks: the staging ring wraps), the result must equal the single-chunk batch,
-    also on the continuation batch that starts from carried state, and the int16 entry point must agree."""
+    (1 + 4 + 4 + ...), to two and to one (the staging ring wraps) — or, with S >= 27, to eight (2 + 7 + 7 + 5 + 4 + 2: a
+    tapered tail) — the result must equal the single-chunk batch, also on the continuation batch that starts from
+    carried state, and the int16 entry point must agree."""
     import os
     step = {ab.CODEC_ATRAC1: 512, ab.CODEC_ATRAC3: 1024, ab.CODEC_ATRAC3PLUS: 2048}[codec]
     rng = np.random.default_rng(seed)
@@ -679,7 +680,7 @@ def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700):
         outs = []
         q = np.clip(np.rint(pcm * 32768.0), -32768, 32767).astype(np.int16)
         pcm = (q.astype(np.float32) * np.float32(1.0 / 32768.0)).astype(np.float32)
-        for streams in (None, "4", "2", "2/i16"):
+        for streams in variants:
             if streams:
                 os.environ["ATDE_CHUNK_STREAMS"] = streams.split("/")[0]
             enc = ab.Encoder(codec, C, lib=lib)

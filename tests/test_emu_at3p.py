@@ -61,6 +61,7 @@ def test_encoder_batch_split_invariance(emu_lib):
 def test_host_chunking(emu_lib):
     import atracdenc_b200 as ab
     pc.check_host_chunking(emu_lib, ab.CODEC_ATRAC1, S=7, F=3)
+    pc.check_host_chunking(emu_lib, ab.CODEC_ATRAC1, S=27, F=2, variants=(None, "8", "8/i16"))
     pc.check_host_chunking(emu_lib, ab.CODEC_ATRAC3, S=7, F=2)
     pc.check_host_chunking(emu_lib, ab.CODEC_ATRAC3PLUS, S=6, F=2)
 

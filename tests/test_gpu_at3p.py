@@ -62,6 +62,8 @@ def test_encoder_batch_split_invariance(gpu_lib):
 def test_host_chunking(gpu_lib):
     import atracdenc_b200 as ab
     pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC1, S=11, F=4)
+    pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC1, S=27, F=3, variants=(None, "8", "8/i16"))
+    pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC3, S=27, F=3, variants=(None, "8", "8/i16"))
     pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC3, S=11, F=3)
     pc.check_host_chunking(gpu_lib, ab.CODEC_ATRAC3PLUS, S=10, F=2)
 

@@ -542,7 +542,7 @@ struct __align__(16) PackShared {
 // Returns (for need lanes) clc | vlc << 16 and the energy ratio e1/e2.
 #ifdef ATDE_PACK_STATS
 long long g_stats[64];
-struct StatsPrinter { ~StatsPrinter() { fprintf(stderr, "compute_units calls %lld, units %lld, walkers %lld, frames*ch %lld, bisect iters %lld\n", g_stats[0], g_stats[1], g_stats[2], g_stats[3], g_stats[4]); for (int q = 0; q < 32; q++) fprintf(stderr, "%lld ", g_stats[8 + q]); fprintf(stderr, "\n"); } } g_stats_printer;
+struct StatsPrinter { ~StatsPrinter() { fprintf(stderr, "compute_units calls %lld, units %lld, walkers %lld, frames*ch %lld, bisect iters %lld, memo hits %lld, settled passes %lld\n", g_stats[0], g_stats[1], g_stats[2], g_stats[3], g_stats[4], g_stats[5], g_stats[6]); for (int q = 0; q < 32; q++) fprintf(stderr, "%lld ", g_stats[8 + q]); fprintf(stderr, "\n"); } } g_stats_printer;
 #endif
 ATDE_NOINLINE unsigned compute_units(PackShared& sh, int lane, bool need, int wl, int start, int len, float e1, float& err_out)
 {
@@ -916,59 +916,101 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
 #endif
     unsigned prec = 0;
     unsigned mode = 1;
+    // CalcBitsAllocation (:272-336): this lane's word length at a given shift
+    auto alloc_prec = [&](float shift) {
+        unsigned p = 0;
+        if (lane < num_bfu && audible) {
+            const int tmp = __float2int_rz(fsub(fadd(fmul(spread, sfi_term), fix_term), shift));
+            p = tmp > 7 ? 7u : (tmp < 0 ? 0u : (tmp == 0 ? 1u : (unsigned)tmp));
+        }
+        if (lane < num_bfu && n_ton_mine && p > 2u)
+            p = max(2u, p - (unsigned)min(n_ton_mine, 8));
+        return p;
+    };
     for (;;) {                                                   // TConfigure: ba.Start(target, -8, 20)
         float mn = -8.0f, mx = 20.0f, last = 20.0f;
+        bool settled = false;
+        // The bit count of a step is a function of the word lengths CalcBitsAllocation hands out (for a fixed BFU
+        // count), and late in the bisection consecutive shifts hand out the same ones.  The last evaluation on either
+        // side of the target is kept (lane-wise: word lengths before and after the energy-error bumps; warp-wide:
+        // total and coding mode) and a step that meets one of them again takes its result instead of recounting.
+        unsigned key_lo = 0xffu, key_hi = 0xffu, res_lo = 0, res_hi = 0;   // 0xff: empty
+        unsigned tot_lo = 0, tot_hi = 0, mode_lo = 1, mode_hi = 1;
         for (;;) {                                               // TAlloc::Encode
 #ifdef ATDE_PACK_STATS
             if (lane == 0) g_stats[4]++;
 #endif
+            // CheckBfus (:587-600) repeats the whole search with one BFU less when the last BFU ends up without bits.
+            // Its word length never grows with the shift, every shift this search can still visit (midpoints, and
+            // `last` at exhaustion, which is >= mn up to rounding) lies above mn - 0.02, and a BFU without bits is not
+            // bumped: once it has none at mn - 0.02 the outcome is settled and the rest of the search is skipped.
+            if (!g.bfu_idx_const && num_bfu > 1) {
+                const unsigned p_low = alloc_prec(fsub(mn, 0.02f));
+                if (__shfl_sync(0xffffffffu, p_low, num_bfu - 1) == 0) { settled = true; break; }
+            }
             const bool exhausted = mx <= mn;
             const float shift = exhausted ? last : __double2float_rn(__dmul_rn((double)fadd(mx, mn), 0.5));   // (max + min) / 2.0: halving is exact
-            // CalcBitsAllocation (:272-336)
-            prec = 0;
-            if (lane < num_bfu && audible) {
-                const int tmp = __float2int_rz(fsub(fadd(fmul(spread, sfi_term), fix_term), shift));
-                prec = tmp > 7 ? 7u : (tmp < 0 ? 0u : (tmp == 0 ? 1u : (unsigned)tmp));
-            }
-            if (lane < num_bfu && n_ton_mine && prec > 2u)
-                prec = max(2u, prec - (unsigned)min(n_ton_mine, 8));
-            // CalcSpecsBitsConsumption + ConsiderEnergyErr (:190-257): every BFU's bump chain is independent;
-            // missing (bfu, wordlen) units are quantised by the whole warp together
-            unsigned cvb = 0;
-            for (;;) {
-                const bool active = lane < num_bfu && prec != 0;
-                const bool need = active && !((cached >> prec) & 1u);
-                if (__any_sync(0xffffffffu, need)) {
-                    float er;
-                    const unsigned cv2 = compute_units(sh, lane, need, (int)prec, start, len, e1, er);
-                    if (need) {
-                        sh.cache_vlc[prec][lane] = (unsigned short)(cv2 >> 16);
-                        if (lane < 10) sh.cache_err[prec][lane] = er;
-                        cached |= 1u << prec;
-                        mant_wl = prec;
+            prec = alloc_prec(shift);
+            const unsigned key = prec;
+            unsigned total;
+            if (__all_sync(0xffffffffu, key == key_lo)) {
+                prec = res_lo; total = tot_lo; mode = mode_lo;
+#ifdef ATDE_PACK_STATS
+                if (lane == 0) g_stats[5]++;
+#endif
+            } else if (__all_sync(0xffffffffu, key == key_hi)) {
+                prec = res_hi; total = tot_hi; mode = mode_hi;
+#ifdef ATDE_PACK_STATS
+                if (lane == 0) g_stats[5]++;
+#endif
+            } else {
+                // CalcSpecsBitsConsumption + ConsiderEnergyErr (:190-257): every BFU's bump chain is independent;
+                // missing (bfu, wordlen) units are quantised by the whole warp together
+                unsigned cvb = 0;
+                for (;;) {
+                    const bool active = lane < num_bfu && prec != 0;
+                    const bool need = active && !((cached >> prec) & 1u);
+                    if (__any_sync(0xffffffffu, need)) {
+                        float er;
+                        const unsigned cv2 = compute_units(sh, lane, need, (int)prec, start, len, e1, er);
+                        if (need) {
+                            sh.cache_vlc[prec][lane] = (unsigned short)(cv2 >> 16);
+                            if (lane < 10) sh.cache_err[prec][lane] = er;
+                            cached |= 1u << prec;
+                            mant_wl = prec;
+                        }
                     }
-                }
-                bool bump = false;
-                if (active) {
-                    cvb = ((prec > 1u ? (unsigned)kClcLen[prec] : 2u) * (unsigned)len) | ((unsigned)sh.cache_vlc[prec][lane] << 16);
-                    if (lane < 10) {                             // BOOST_NAQ_END
-                        const float e = sh.cache_err[prec][lane];
-                        bump = ((e > 0.0f && e < 0.7f) || e > 1.2f) && prec < 7u;
+                    bool bump = false;
+                    if (active) {
+                        cvb = ((prec > 1u ? (unsigned)kClcLen[prec] : 2u) * (unsigned)len) | ((unsigned)sh.cache_vlc[prec][lane] << 16);
+                        if (lane < 10) {                             // BOOST_NAQ_END
+                            const float e = sh.cache_err[prec][lane];
+                            bump = ((e > 0.0f && e < 0.7f) || e > 1.2f) && prec < 7u;
+                        }
                     }
+                    if (bump) prec++;
+                    if (!__any_sync(0xffffffffu, bump)) break;
                 }
-                if (bump) prec++;
-                if (!__any_sync(0xffffffffu, bump)) break;
+                const unsigned clc = warp_sum_u(prec ? (cvb & 0xffffu) : 0u);
+                const unsigned vlc = warp_sum_u(prec ? (cvb >> 16) : 0u);
+                const unsigned nz = __popc(__ballot_sync(0xffffffffu, prec != 0));
+                mode = clc <= vlc;
+                total = (unsigned)num_bfu * 3u + 6u * nz + (mode ? clc : vlc);
+                total += tonal_bits(sh, n_ton, lane, prec, num_bfu);
+                if (total < target) { key_lo = key; res_lo = prec; tot_lo = total; mode_lo = mode; }
+                else if (total > target) { key_hi = key; res_hi = prec; tot_hi = total; mode_hi = mode; }
             }
-            const unsigned clc = warp_sum_u(prec ? (cvb & 0xffffu) : 0u);
-            const unsigned vlc = warp_sum_u(prec ? (cvb >> 16) : 0u);
-            const unsigned nz = __popc(__ballot_sync(0xffffffffu, prec != 0));
-            mode = clc <= vlc;
-            unsigned total = (unsigned)num_bfu * 3u + 6u * nz + (mode ? clc : vlc);
-            total += tonal_bits(sh, n_ton, lane, prec, num_bfu);
             if (exhausted) break;
             if (total < target) { last = shift; mx = fsub(shift, 0.01f); }
             else if (total > target) { mn = fadd(shift, 0.01f); }
             else break;
+        }
+        if (settled) {
+#ifdef ATDE_PACK_STATS
+            if (lane == 0) g_stats[6]++;
+#endif
+            num_bfu--;
+            continue;
         }
         if (!g.bfu_idx_const && num_bfu > 1) {
             const unsigned last_prec = __shfl_sync(0xffffffffu, prec, num_bfu - 1);

@@ -925,26 +925,28 @@ ATDE_D void calc_curve(const float* in, const float* low, const float* high, flo
     }
 }
 
-__global__ void __launch_bounds__(128) at3_curve_kernel(Geometry g, Buffers b)
+ATDE_D Curve* curve_slot(const Geometry& g, const Buffers& b, long long item)
 {
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // ((s*C+c)*3+band)*n_out + f
-    const long long total = (long long)g.S * g.C * kGainBands * g.n_out;
-    if (item >= total) return;
-    const DevTables* __restrict__ T = b.tab;
     const int f = (int)(item % g.n_out);
     const long long scb = item / g.n_out;
     const int band = (int)(scb % kGainBands);
     const long long sc = scb / kGainBands;
+    return b.curves + ((size_t)sc * 4 + band) * g.n_out + f;
+}
+
+// The full curve construction of one item that passed the cheap tests of the kernel below.
+ATDE_D void curve_item(const Geometry& g, const Buffers& b, long long item)
+{
+    const DevTables* __restrict__ T = b.tab;
     Curve out;
     out.n = 0; out.pad = 0;
     for (int i = 0; i < 7; i++) { out.level[i] = 0; out.loc[i] = 0; }
-    Curve* dst = b.curves + ((size_t)sc * 4 + band) * g.n_out + f;
+    Curve* dst = curve_slot(g, b, item);
 
     const float4 st = reinterpret_cast<const float4*>(b.gstat)[item];
     const float4 pv = reinterpret_cast<const float4*>(b.gprev)[item];
     const float hfr = st.x, cur_hpf = st.y, target = st.z;
     const float prev_hpf = pv.x, saved_ll = pv.y, saved_lt = pv.z;
-    if (hfr < 0.05f) { *dst = out; return; }
 
     float gain[32], low[32], high[32];
     const float* gp = b.gain + (size_t)item * 96;
@@ -1017,10 +1019,40 @@ __global__ void __launch_bounds__(128) at3_curve_kernel(Geometry g, Buffers b)
     *dst = out;
 }
 
+// Most items leave after a glance at their statistics (no high-frequency content: atrac3denc.cpp:319-326; no target or
+// no previous level: transient_detector.cpp:287-295) and the rest is long, branchy, per-item work: with one thread per
+// item a warp ran its few surviving lanes at 7 of 32.  So the block first sorts its items — the cheap exits are
+// answered on the spot, the others are collected in a list — and then walks the list with dense warps.
+constexpr int kCurveBlock = 256;
+__global__ void __launch_bounds__(kCurveBlock) at3_curve_kernel(Geometry g, Buffers b)
+{
+    __shared__ int list[kCurveBlock];
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const long long item0 = (long long)blockIdx.x * kCurveBlock;                 // item = ((s*C+c)*3+band)*n_out + f
+    const long long total = (long long)g.S * g.C * kGainBands * g.n_out;
+    const long long item = item0 + threadIdx.x;
+    if (item < total) {
+        const float4 st = reinterpret_cast<const float4*>(b.gstat)[item];
+        const float4 pv = reinterpret_cast<const float4*>(b.gprev)[item];
+        if (st.x < 0.05f || st.z < 1e-6f || pv.y < 1e-6f) {                      // hfr | target | saved last level
+            Curve out;
+            out.n = 0; out.pad = 0;
+            for (int i = 0; i < 7; i++) { out.level[i] = 0; out.loc[i] = 0; }
+            *curve_slot(g, b, item) = out;
+        } else {
+            list[atomicAdd(&cnt, 1)] = (int)threadIdx.x;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += kCurveBlock) curve_item(g, b, item0 + list[i]);
+}
+
 void launch_gain_curve(const Geometry& g, const Buffers& b, cudaStream_t st)
 {
     const long long total = (long long)g.S * g.C * kGainBands * g.n_out;
-    ATDE_LAUNCH(at3_curve_kernel, (unsigned)((total + 127) / 128), 128, 0, st, g, b);
+    ATDE_LAUNCH(at3_curve_kernel, (unsigned)((total + kCurveBlock - 1) / kCurveBlock), kCurveBlock, 0, st, g, b);
 }
 
 // =====================================================================================

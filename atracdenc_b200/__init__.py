@@ -27,7 +27,7 @@ EXPORTS = [
     "atde_default_settings", "atde_create", "atde_destroy", "atde_frame_samples",
     "atde_units_per_frame", "atde_unit_bytes", "atde_lookahead_frames", "atde_output_frames", "atde_encode_batch", "atde_encode_batch_i16",
     "atde_encode_batch_device", "atde_sync", "atde_reset", "atde_cuda_stream",
-    "atde_launch_count", "atde_set_profiling", "atde_kernel_times", "atde_debug_tap", "atde_debug_math", "atde_last_error", "atde_version",
+    "atde_launch_count", "atde_set_profiling", "atde_set_gain_trace", "atde_kernel_times", "atde_debug_tap", "atde_debug_math", "atde_last_error", "atde_version",
     "atde_create_group", "atde_destroy_group", "atde_group_size", "atde_group_encode_batch", "atde_group_encode_batch_i16",
     "atde_group_output_frames", "atde_group_reset",
     "atde_decoder_create", "atde_decoder_destroy", "atde_decode_batch", "atde_decoder_reset",
@@ -75,6 +75,7 @@ def load_library(path: os.PathLike | str | None = None) -> ctypes.CDLL:
     lib.atde_launch_count.argtypes = [vp]
     lib.atde_launch_count.restype = i64
     lib.atde_set_profiling.argtypes = [vp, i32]
+    lib.atde_set_gain_trace.argtypes = [vp, i32]
     lib.atde_kernel_times.argtypes = [vp, vp, vp, i32]
     lib.atde_debug_tap.argtypes = [vp, i32, vp, ctypes.c_size_t]
     lib.atde_debug_tap.restype = i64

@@ -363,8 +363,14 @@ ATDE_D void fwd_bfly(cpx* buf, int p, int d, cpx t1, cpx t2, cpx t3)
 #ifndef ATDE_GAIN_BLOCKS
 #define ATDE_GAIN_BLOCKS 8
 #endif
+// TRACE = true is the instance behind the reference's `--yaml-log` gain-control trace (atrac3denc.cpp:305-400): it also
+// covers band 3 (analysed and logged by the reference although it never carries a curve), takes the high-frequency
+// ratio by the reference's sequential sums and forms `next_level` — the RMS of the first 64 up-sampled look-ahead
+// samples, output samples [3072, 3136) — and writes to the trace buffers only.  The encode path never launches it.
+template <bool TRACE>
 __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(Geometry g, Buffers b)
 {
+    constexpr int kNb = TRACE ? kBands : kGainBands;
     __shared__ __align__(16) cpx big[2048 + 128];    // inverse FFT buffer, padded; later the real output
     __shared__ __align__(8) cpx tw2c[15][8];         // pass-2 twiddles of lane group k (8-byte elements: a 16-byte pre-spread
                                                      // form costs four wavefronts per warp load instead of two, and the
@@ -387,10 +393,11 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     // the barriers per frame); the inverse FFT-2048 wants all 128 threads and runs for one frame after the other.
     const int f0 = 2 * blockIdx.x;
     const int n_fr = min(2, g.n_out - f0);
-    const int band = blockIdx.y % kGainBands, c = blockIdx.y / kGainBands;
+    const int band = blockIdx.y % kNb, c = blockIdx.y / kNb;
     const int s = blockIdx.z;
     const int tid = threadIdx.x;
     const int half = tid >> 6, t = tid & 63;
+    float* const nxt = reinterpret_cast<float*>(big) + 2688;     // TRACE: output samples [3072, 3136)
     const bool act = half < n_fr;
     const float* __restrict__ in = b.bands + (((size_t)s * g.C + c) * 4 + band) * g.BL + 256 * (size_t)(f0 + half);
     cpx* const fwd = fwd2[half];
@@ -653,6 +660,10 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
             float* sigw = reinterpret_cast<float*>(big) + 2 * k + 4 * (k >> 5);
             *reinterpret_cast<cpx*>(sigw + 272 * a) = u;                  // slot 512 + kk  -> samples 1024 + 2kk, +1
             *reinterpret_cast<cpx*>(sigw + 272 * a + 1088) = v;           // slot 1024 + kk -> samples 2048 + 2kk, +1
+            if (TRACE && a == 0 && k < 32) {                              // slot 1536 + k -> samples 3072 + 2k, +1
+                nxt[2 * k] = fmul(x[0][3].r, 1.0f / 4096.0f);
+                nxt[2 * k + 1] = fmul(x[0][3].i, 1.0f / 4096.0f);
+            }
         }
     }
     atde_named_barrier(1, kGainThreads);
@@ -706,15 +717,15 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         if (tid == 96) sstat[1] = tgt;
     }
     __syncthreads();
-    const size_t item = ((((size_t)s * g.C + c) * kGainBands + band) * g.n_out + f);
-    if (tid < 96) b.gain[item * 96 + tid] = sgain[tid];
+    const size_t item = ((((size_t)s * g.C + c) * kNb + band) * g.n_out + f);
+    if (tid < 96) (TRACE ? b.trace_gain : b.gain)[item * 96 + tid] = sgain[tid];
     if (tid == 0) {
         double tot = __dadd_rn(esum_part[2 * it][0], esum_part[2 * it + 1][0]);
         double hi = __dadd_rn(esum_part[2 * it][1], esum_part[2 * it + 1][1]);
         if (tot > 0.0) {
             const double ratio = __ddiv_rn(hi, tot);
             const double t1 = (double)0.05f, t2 = (double)0.3f;
-            if (fabs(ratio - t1) <= t1 * 1e-7 || fabs(ratio - t2) <= t2 * 1e-7) {
+            if (TRACE || fabs(ratio - t1) <= t1 * 1e-7 || fabs(ratio - t2) <= t2 * 1e-7) {
                 // too close to a decision threshold for a reordered sum: the reference's loop, bin by bin
                 tot = 0.0; hi = 0.0;
                 for (int k = 0; k <= 256; k++) {
@@ -733,7 +744,15 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         st4.y = sstat[0];
         st4.z = sstat[1];
         st4.w = sgain[31];
-        reinterpret_cast<float4*>(b.gstat)[item] = st4;
+        if (TRACE) {
+            // AnalyzeGain(signal + 3072, 64, 1, rms)[0] (atrac3denc.cpp:335, transient_detector.cpp:33-40)
+            float a = 0.0f;
+            for (int i = 0; i < 64; i++) a = fadd(a, fmul(nxt[i], nxt[i]));
+            st4.w = __fsqrt_rn(fmul(a, 0.015625f));
+            reinterpret_cast<float4*>(b.trace_stat)[item] = st4;           // hfr, curHpfEnergy, target, next_level
+        } else {
+            reinterpret_cast<float4*>(b.gstat)[item] = st4;
+        }
     }
         __syncthreads();                       // the staged values are read: pass 1 of the next frame may overwrite them
     }   // frames of the block
@@ -742,7 +761,13 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
 void launch_gain_analysis(const Geometry& g, const Buffers& b, cudaStream_t st)
 {
     dim3 grid((g.n_out + 1) / 2, g.C * kGainBands, g.S);      // two frames per block
-    ATDE_LAUNCH(at3_gain_kernel, grid, kGainBlock, 0, st, g, b);
+    ATDE_LAUNCH(at3_gain_kernel<false>, grid, kGainBlock, 0, st, g, b);
+}
+
+void launch_gain_trace(const Geometry& g, const Buffers& b, cudaStream_t st)
+{
+    dim3 grid((g.n_out + 1) / 2, g.C * kBands, g.S);
+    ATDE_LAUNCH(at3_gain_kernel<true>, grid, kGainBlock, 0, st, g, b);
 }
 
 // =====================================================================================

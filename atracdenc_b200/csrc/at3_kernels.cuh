@@ -115,12 +115,16 @@ struct Buffers {
     TonalList* tonal;                 // [S][n_out][C]
     unsigned char* out;               // [S][n_out][frame_sz]
     unsigned char* tap_prec;          // [S][n_out][C][32] or nullptr (0xff beyond numBfu)
+    // gain-control trace (`--yaml-log`), only allocated and written when atde_set_gain_trace() turned it on
+    float* trace_gain;                // [S][C][4][n_out][96]: gain[32], low[32], high[32] — all FOUR bands
+    float* trace_stat;                // [S][C][4][n_out][4]: hfr (sequential sums), curHpfEnergy, target, next_level
     const DevTables* tab;
 };
 
 void upload_qmf_window(const float w[48]);
 void launch_qmf(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_gain_analysis(const Geometry& g, const Buffers& b, cudaStream_t st);
+void launch_gain_trace(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_gain_scan(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_gain_curve(const Geometry& g, const Buffers& b, cudaStream_t st);
 void launch_mdct(const Geometry& g, const Buffers& b, cudaStream_t st);

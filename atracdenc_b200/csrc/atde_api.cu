@@ -72,6 +72,7 @@ struct Workspace {
     DevBuf<unsigned char> tap_sfi, tap_wl;
     // ATRAC3
     DevBuf<float> bands, gain, gstat, gprev, gscale, energy, hist_tmp;
+    DevBuf<float> trace_gain, trace_stat;   // gain-control trace only (atde_set_gain_trace)
     DevBuf<atde::at3::Curve> curves;
     DevBuf<atde::at3::TonalList> tonal;
     DevBuf<unsigned char> sfi;
@@ -82,6 +83,7 @@ struct Workspace {
         out.release(); sizes.release(); tap_sfi.release(); tap_wl.release();
         bands.release(); gain.release(); gstat.release(); gprev.release(); gscale.release();
         energy.release(); hist_tmp.release(); curves.release(); tonal.release(); sfi.release();
+        trace_gain.release(); trace_stat.release();
     }
 };
 
@@ -116,6 +118,7 @@ struct atde_encoder {
     bool streams_started = false;   // at least one batch went through since create/reset
     long long last_out = 0;         // output frames per stream of the last batch
     bool taps_enabled = false;
+    bool gain_trace = false;        // ATRAC3: also run the trace instance of the gain kernel (atde_set_gain_trace)
     // geometry of the last batch, for taps
     int last_S = 0; long long last_F = 0;
     long long launches = 0;
@@ -434,6 +437,12 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
         if ((rc = w.gprev.ensure(items * 4))) return rc;
     }
     if (e->taps_enabled && (rc = w.tap_wl.ensure(units * 32))) return rc;
+    const bool trace = e->gain_trace && !g.no_gain;
+    if (trace) {
+        const size_t titems = (size_t)S * C * kBands * (size_t)(N > 0 ? N : 1);
+        if ((rc = w.trace_gain.ensure(titems * 96))) return rc;
+        if ((rc = w.trace_stat.ensure(titems * 4))) return rc;
+    }
 
     Buffers b;
     memset(&b, 0, sizeof(b));
@@ -452,6 +461,8 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
     b.loud = w.loud.p; b.sfi = w.sfi.p; b.energy = w.energy.p; b.tonal = w.tonal.p;
     b.out = d_out;
     b.tap_prec = e->taps_enabled ? w.tap_wl.p : nullptr;
+    b.trace_gain = trace ? w.trace_gain.p : nullptr;
+    b.trace_stat = trace ? w.trace_stat.p : nullptr;
     b.tab = e->d_at3_tab;
 
     { KernelTimer kt(e, w.stream, 0); launch_qmf(g, b, w.stream); }
@@ -462,6 +473,7 @@ int run_at3(atde_encoder* e, Workspace& w, const float* d_pcm, int s0, int S, lo
             { KernelTimer kt(e, w.stream, 3); launch_gain_analysis(g, b, w.stream); }
             { KernelTimer kt(e, w.stream, 4); launch_gain_scan(g, b, w.stream); launch_gain_curve(g, b, w.stream); }
             e->launches += 3;
+            if (trace) { launch_gain_trace(g, b, w.stream); e->launches += 1; }
         }
         { KernelTimer kt(e, w.stream, 0); launch_mdct(g, b, w.stream); }
         { KernelTimer kt(e, w.stream, 1); launch_loudterm(g, b, w.stream); launch_loudness(g, b, w.stream); }
@@ -924,6 +936,15 @@ int atde_set_profiling(atde_encoder* e, int32_t on)
     return 0;
 }
 
+int atde_set_gain_trace(atde_encoder* e, int32_t on)
+{
+    if (!e) return fail(ATDE_ERR_INVALID, "null handle");
+    if (e->cfg.codec != ATDE_CODEC_ATRAC3) return fail(ATDE_ERR_UNSUPPORTED, "the gain-control trace exists for ATRAC3 only");
+    e->gain_trace = on != 0;
+    if (on) e->taps_enabled = true;
+    return 0;
+}
+
 int atde_kernel_times(atde_encoder* e, double* ms_sum, int64_t* count, int32_t n_kinds)
 {
     if (!e || !ms_sum || !count) return fail(ATDE_ERR_INVALID, "null argument");
@@ -962,6 +983,8 @@ int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* dst, size_t capacity
             case ATDE_TAP_ENERGY: src = w.energy.p; bytes = units * 32 * sizeof(float); break;
             case ATDE_TAP_TONAL: src = w.tonal.p; bytes = units * sizeof(atde::at3::TonalList); break;
             case ATDE_TAP_GAIN: src = w.gain.p; bytes = (size_t)e->last_S * e->cfg.channels * 3 * e->last_out * 96 * sizeof(float); break;
+            case ATDE_TAP_TRACE_GAIN: src = w.trace_gain.p; bytes = (size_t)e->last_S * e->cfg.channels * 4 * e->last_out * 96 * sizeof(float); break;
+            case ATDE_TAP_TRACE_STAT: src = w.trace_stat.p; bytes = (size_t)e->last_S * e->cfg.channels * 4 * e->last_out * 4 * sizeof(float); break;
             default: return fail(ATDE_ERR_INVALID, "unknown tap %d", what);
         }
     } else

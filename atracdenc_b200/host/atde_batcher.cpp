@@ -1,5 +1,6 @@
 // atde_batcher.cpp — see atde_batcher.h.
 #include "atde_batcher.h"
+#include "atde_gain_trace.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -32,6 +33,14 @@ TFrameBatcher::~TFrameBatcher()
     atde_destroy(Enc);
 }
 
+void TFrameBatcher::EnableGainTrace(std::ostream* log, bool gainControl)
+{
+    if (!log)
+        return;
+    Check(atde_set_gain_trace(Enc, 1));
+    Trace.reset(new TGainTraceWriter(log, Channels, gainControl));
+}
+
 TPCMEngine::EProcessResult TFrameBatcher::Push(const float* data, ICompressedOutput& out)
 {
     const size_t n = (size_t)FrameSamples * Channels;
@@ -58,6 +67,8 @@ void TFrameBatcher::Flush(ICompressedOutput& out)
     Sizes.resize(units + 1);
     Check(atde_encode_batch(Enc, Stage.data(), 1, (int64_t)Staged, Bytes.data(), Sizes.data()));
     Staged = 0;                                        // only now: a failed batch stays staged
+    if (Trace)
+        Trace->AppendBatch(Enc, (int64_t)(units / Units));
     for (size_t u = 0; u < units; u++) {
         // same bytes, same length, same order as the reference's WriteFrame calls; payload bytes beyond the
         // container frame size are the bit writer's zero growth slack

@@ -12,11 +12,15 @@
 #include "atde_boundary.h"
 #include "../../include/atde_b200.h"
 
+#include <iosfwd>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace NAtracDEnc {
+
+class TGainTraceWriter;
 
 class TFrameBatcher {
 public:
@@ -37,6 +41,9 @@ public:
     // Frames staged before a batch goes to the GPU (default 4096, or ATDE_BATCH_FRAMES from the environment).
     void SetBatchFrames(size_t n) { BatchFrames = n ? n : 1; }
     size_t Pending() const { return Staged; }
+    // ATRAC3: the reference's `--yaml-log` gain-control trace (TAtrac3EncoderSettings::YamlLog, src/atrac/at3/atrac3.h:276):
+    // every batch that comes back from the GPU appends its frames' documents to `log` (atde_gain_trace.h).
+    void EnableGainTrace(std::ostream* log, bool gainControl);
     int GetChannels() const { return Channels; }
 
 private:
@@ -47,6 +54,7 @@ private:
     std::vector<int32_t> Sizes;
     size_t Staged = 0, BatchFrames = 4096;
     uint64_t Calls = 0;
+    std::unique_ptr<TGainTraceWriter> Trace;
 };
 
 // TAt3PEnc::ParseAdvancedOpt (src/atrac/at3p/at3p.cpp:196-284): "key=value[,key=value...]" with the keys `ghadbg`

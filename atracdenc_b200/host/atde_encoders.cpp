@@ -85,6 +85,7 @@ static atde_settings MakeAt3Settings(const NAtrac3::TAtrac3EncoderSettings& s)
 TAtrac3Encoder::TAtrac3Encoder(TCompressedOutputPtr&& oma, NAtrac3::TAtrac3EncoderSettings&& encoderSettings)
     : TBatchedEncoderBase(std::move(oma), MakeAt3Settings(encoderSettings))
 {
+    Batcher.EnableGainTrace(encoderSettings.YamlLog, !encoderSettings.NoGainControll);
 }
 
 TPCMEngine::TProcessLambda TAtrac3Encoder::GetLambda()

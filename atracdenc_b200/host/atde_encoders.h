@@ -72,7 +72,7 @@ struct TAtrac3EncoderSettings {
     const bool NoTonalComponents;
     const uint8_t SourceChannels;
     const uint32_t BfuIdxConst;
-    std::ostream* YamlLog;   // accepted for signature compatibility; the GPU path does not produce the gain-control trace
+    std::ostream* YamlLog;   // nullable; gain control debug log (`--yaml-log`), written batch by batch (atde_gain_trace.h)
 };
 } // namespace NAtrac3
 #endif

@@ -70,6 +70,7 @@ public:
     size_t GetChannelNum() const override { return Real->GetChannelNum(); }
     void WriteFrame(std::vector<char> data) override { Real->WriteFrame(std::move(data)); }
     TPCMEngine::EProcessResult Push(const float* data) { return Batcher.Push(data, *Real); }
+    void EnableGainTrace(std::ostream* log, bool gainControl) { Batcher.EnableGainTrace(log, gainControl); }
 
 private:
     TCompressedOutputPtr Real;                 // destroyed after the flush above
@@ -94,7 +95,10 @@ TCompressedOutputPtr WrapAt3(TCompressedOutputPtr&& oma, const NAtrac3::TAtrac3E
     c.no_gain_control = s.NoGainControll;
     c.no_tonal = s.NoTonalComponents;
     c.bfu_idx_const = s.BfuIdxConst;
-    return TCompressedOutputPtr(new TDeferredOutput(std::move(oma), c));
+    TDeferredOutput* d = new TDeferredOutput(std::move(oma), c);
+    TCompressedOutputPtr res(d);
+    d->EnableGainTrace(s.YamlLog, !s.NoGainControll);       // `--yaml-log <file>` (src/main.cpp:661-673)
+    return res;
 }
 
 TCompressedOutputPtr WrapAt3p(TCompressedOutputPtr&& out, int channels, const TAt3PEnc::TSettings& s)
@@ -216,7 +220,7 @@ TAtrac3Encoder::TAtrac3Encoder(TCompressedOutputPtr&& oma, NAtrac3::TAtrac3Encod
     , LoudnessCurve()
     , Upsampler(11025.0f, 800.0f)
 {
-    YamlLog = Params.YamlLog;                  // accepted; the gain-control trace is not produced by this path
+    YamlLog = Params.YamlLog;                  // written batch by batch by the TDeferredOutput's batcher (atde_gain_trace.cpp)
 }
 
 TAtrac3Encoder::~TAtrac3Encoder()

@@ -149,9 +149,20 @@ typedef enum {
     ATDE_TAP_GSCALE = 9,    /* float  [S][F][C][4][4] PrevHalf, CurHalf, Frame, NextOverlapScale */
     ATDE_TAP_ENERGY = 10,   /* float  [S][F][C][32] BFU energies */
     ATDE_TAP_TONAL = 11,    /* tonal block lists [S][F][C] (at3_kernels.cuh: TonalList) */
-    ATDE_TAP_GAIN = 12      /* float  [S][C][3][F][96] sub-frame envelope: gain, low, high */
+    ATDE_TAP_GAIN = 12,     /* float  [S][C][3][F][96] sub-frame envelope: gain, low, high */
+    /* ATRAC3 with the gain-control trace on (atde_set_gain_trace): the same analysis over all FOUR bands */
+    ATDE_TAP_TRACE_GAIN = 13, /* float [S][C][4][F][96] gain, low, high */
+    ATDE_TAP_TRACE_STAT = 14  /* float [S][C][4][F][4] high-frequency ratio, mean envelope, plateau target, next_level */
 } atde_tap;
 int64_t atde_debug_tap(atde_encoder* e, int32_t what, void* host_dst, size_t capacity);
+
+/* ATRAC3: the data behind the reference's `--yaml-log <file>` gain-control trace (src/yaml_log.h:19-57; written by
+ * src/atrac3denc.cpp:305-579,743-800 and src/transient_detector.cpp:298-446 through TAtrac3EncoderSettings::YamlLog,
+ * src/atrac/at3/atrac3.h:263-276).  With the trace on, every following batch also runs the envelope analysis over band 3
+ * (which the reference analyses and logs although it never carries a curve), keeps the exact high-frequency ratio and
+ * the look-ahead level `next_level`, and keeps the taps above valid; the text itself is produced on the host from those
+ * taps (atracdenc_b200/host/atde_gain_trace.{h,cpp}).  A debugging aid: the encode path is unchanged when it is off. */
+int atde_set_gain_trace(atde_encoder* e, int32_t on);
 
 /* Device-side math self-test hooks (tests only): evaluates the glibc replicas on n inputs. */
 int atde_debug_math(int32_t device, int32_t fn /*0 log10f 1 log2f 2 logf*/, const float* x, float* y, int64_t n);

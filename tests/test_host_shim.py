@@ -21,6 +21,7 @@ def build_driver(so: Path, tag: str) -> Path:
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(out), str(ROOT / "tests" / "host_shim_driver.cpp"),
                            str(ROOT / "atracdenc_b200" / "host" / "atde_encoders.cpp"),
                            str(ROOT / "atracdenc_b200" / "host" / "atde_batcher.cpp"),
+                           str(ROOT / "atracdenc_b200" / "host" / "atde_gain_trace.cpp"),
                            str(ROOT / "atracdenc_b200" / "host" / "atde_containers.cpp"), str(so),
                            f"-Wl,-rpath,{so.parent}", "-pthread"])
     return out

@@ -149,3 +149,55 @@ def test_dropin_has_no_undefined_encoder_symbols():
 def test_dropin_cli_files_identical_gpu(tmp_path, gpu_lib):
     ref, got = _binaries("gpu")
     run_pair(ref, got, tmp_path, seconds=3.0)
+
+
+# ---- `--yaml-log <file>`: the gain-control trace (src/yaml_log.h, src/atrac3denc.cpp:305-579,743-800,
+# ---- src/transient_detector.cpp:298-446).  The reference CLI writes it while it encodes; the drop-in writes it batch by batch
+# ---- from the device's taps (atracdenc_b200/host/atde_gain_trace.cpp).  The two files must be byte-identical.
+YAML_CASES = [
+    # (channels, CLI options, signal kind, amplitude, ATDE_BATCH_FRAMES)
+    (2, [], "mix", 1.0, "16"),
+    (2, ["--bitrate", "64"], "steps", 1.0, "7"),           # LP4 joint stereo: the trace is over M/S
+    (1, [], "mix", 1.0, "4096"),                           # everything inside the destructor's flush
+    (2, [], "mix", 2e-3, "5"),                             # near silence: `skip: below_min_signal`, `skip: low_hfr`
+    (2, ["--nogaincontrol"], "mix", 1.0, "9"),             # frame headers only
+]
+
+
+def run_yaml_pair(ref, got, tmp_path, frames, cases=YAML_CASES):
+    import os
+    seen = set()
+    for k, (C, opts, kind, amp, batch) in enumerate(cases):
+        wav = tmp_path / f"y{k}.wav"
+        write_wav(wav, amp * tl.synth_rich(frames, 1024, C, seed=700 + k, kind=kind))
+        logs = []
+        for exe, tag in ((ref, "ref"), (got, "got")):
+            log, out = tmp_path / f"{tag}{k}.yaml", tmp_path / f"{tag}{k}.oma"
+            r = subprocess.run([str(exe), "-e", "atrac3", "-i", str(wav), "-o", str(out), "--nostdout", "--yaml-log", str(log)] + opts,
+                               capture_output=True, text=True, env=dict(os.environ, ATDE_BATCH_FRAMES=batch), timeout=900)
+            assert r.returncode == 0, (tag, opts, r.stderr[-800:])
+            logs.append((log.read_bytes(), out.read_bytes()))
+        assert logs[0][1] == logs[1][1], f"case {k}: encoded files differ"
+        assert logs[0][0].count(b"\n---\n") + 1 >= frames - 1, "the reference wrote fewer documents than frames"
+        if logs[0][0] != logs[1][0]:
+            a, b = logs[0][0].split(b"\n"), logs[1][0].split(b"\n")
+            at = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+            raise AssertionError(f"case {k} {opts}: yaml logs differ at line {at + 1}: {a[at][:160]!r} != {b[at][:160]!r}")
+        seen.update(key for key in (b"point0_guard: kept", b"point0_guard: reverted", b"transition_pruned", b"skip: low_hfr",
+                                    b"skip: below_min_signal", b"skip: amplify_low_hfr", b"skip: band_ge_3", b"curve_final",
+                                    b"source: in.back", b"sticky_frame_eligible: true") if key in logs[0][0])
+    return seen
+
+
+def test_dropin_yaml_log_identical_emulated(tmp_path):
+    ref, got = _binaries("emu")
+    seen = run_yaml_pair(ref, got, tmp_path, frames=24)
+    # the cases together must reach every kind of line the trace has
+    assert {b"point0_guard: kept", b"point0_guard: reverted", b"transition_pruned", b"skip: low_hfr", b"skip: amplify_low_hfr",
+            b"skip: below_min_signal", b"skip: band_ge_3", b"curve_final", b"source: in.back", b"sticky_frame_eligible: true"} <= seen, seen
+
+
+@pytest.mark.gpu
+def test_dropin_yaml_log_identical_gpu(tmp_path, gpu_lib):
+    ref, got = _binaries("gpu")
+    run_yaml_pair(ref, got, tmp_path, frames=400)

@@ -89,6 +89,117 @@ constexpr int kAnaThreads = 128;
 static_assert(kNS1 == kAnaThreads * kQ1, "stage-1 tasks fill the block exactly");
 constexpr int kNS2T = ((kNS2 + kQ2 - 1) / kQ2) * kQ2;           // 555
 
+// ---- the MDCT of one frame by one warp ---------------------------------------------------------------------------
+// kissfft stage with compile-time geometry (kissfft_dev.cuh: kf_stage4 divides by a run-time m)
+template <int M, int FSTRIDE>
+ATDE_D void stage4c(cpx* buf, const cpx* __restrict__ tw, int v)
+{
+    const int g = v / M, k = v % M;
+    cpx* F = buf + g * 4 * M + k;
+    cpx f0 = F[0], f1 = F[M], f2 = F[2 * M], f3 = F[3 * M];
+    kf_bfly4<false>(f0, f1, f2, f3, tw[k * FSTRIDE], tw[2 * k * FSTRIDE], tw[3 * k * FSTRIDE]);
+    F[0] = f0; F[M] = f1; F[2 * M] = f2; F[3 * M] = f3;
+}
+
+// Window + fold + pre-twiddle of one band (mdct.h:56-76 on TAtrac1MDCT::Mdct's input, atrac1denc.cpp:80-90), written in
+// kissfft's gather order: one long block, or (SHORT) the band's 4 / 8 short blocks of 32 samples, 16 slots each.  The
+// four input positions of an output slot are a property of the slot: the host tabulates them (DevTables::fold128 /
+// fold256 / fold64: four 10-bit positions t into the windowed stretch, 1023 = outside of it, where the reference's buffer
+// holds 0; bits 40.. = the slot's index i = n / 2), so the kernel neither permutes nor range-tests.
+template <bool SHORT>
+ATDE_D void fold_band(const unsigned long long* __restrict__ tab, int nslots, const float* __restrict__ wt,
+                      const float* fr, const float* __restrict__ cs, int q4, cpx* dst, int lane)
+{
+    for (int s = lane; s < nslots; s += 32) {
+        const unsigned long long e = tab[SHORT ? (s & 15) : s];
+        const float* const frb = SHORT ? fr + 32 * (s >> 4) : fr;  // short block kb windows the 64 samples around it
+        const unsigned el = (unsigned)e, eh = (unsigned)(e >> 32);
+        auto term = [&](unsigned t) {
+            const bool ok = t != 1023u;
+            const int tc = ok ? (int)t : 0;
+            const float v = fmul(wt[tc], frb[tc - 32]);          // the stretch starts 32 samples before the block
+            return ok ? v : 0.0f;
+        };
+        const float a0 = term(el & 1023u), a1 = term((el >> 10) & 1023u), b0 = term((el >> 20) & 1023u),
+                    b1 = term(((el >> 30) | (eh << 2)) & 1023u);
+        const int i = (int)((eh >> 8) & 127u);
+        float r0, i0;
+        if (i < q4) { r0 = fadd(a0, a1); i0 = fsub(b0, b1); }
+        else        { r0 = fsub(a0, a1); i0 = fadd(b0, b1); }
+        const float2 c = *reinterpret_cast<const float2*>(cs + 2 * i);
+        cpx X;
+        X.r = fadd(fmul(r0, c.x), fmul(i0, c.y));
+        X.i = fsub(fmul(i0, c.x), fmul(r0, c.y));
+        dst[s] = X;
+    }
+}
+
+// post-twiddle (mdct.h:92-101) of NB blocks of N2 spectral lines each, the band reversal of the mid / hi bands and the
+// level fix of the hi band's short blocks (atrac1denc.cpp:92-98)
+template <int N2, int NB, bool REV, bool TWICE>
+ATDE_D void post_band(const cpx* src, const float* __restrict__ cs, float* out, int lane)
+{
+#pragma unroll
+    for (int s = lane; s < NB * N2 / 2; s += 32) {
+        const int kb = s / (N2 / 2), i = s % (N2 / 2), n = 2 * i;
+        const cpx z = src[s];
+        const float2 c = *reinterpret_cast<const float2*>(cs + n);
+        float va = fsub(fmul(-z.r, c.x), fmul(z.i, c.y));
+        float vb = fadd(fmul(-z.r, c.y), fmul(z.i, c.x));
+        if (TWICE) { va = fmul(va, 2.0f); vb = fmul(vb, 2.0f); }
+        const int pa = REV ? N2 - 1 - n : n, pb = REV ? n : N2 - 1 - n;
+        out[N2 * kb + pa] = va;
+        out[N2 * kb + pb] = vb;
+    }
+}
+
+// One frame: window mask `msk`, bit b = band b (low, mid, hi) takes short blocks.  Every branch is uniform over the warp.
+//   low / mid   long: FFT64 = 4x4x4;  short: four FFT16 = 4x4.  The first two stages are THE SAME butterflies on the same
+//               slots for both (stage m=1 has no twiddle; stage m=4 pairs slots 16g+k+{0,4,8,12} with twiddles
+//               tw64[4k q] == tw16[k q], bit for bit: the phase -2 pi 4k / 64 is the phase -2 pi k / 16), so the two
+//               bands share the warp, 16 butterflies each, whatever their window
+//   hi          long: FFT128 = 4x4x4x2 (radix-2 innermost);  short: eight FFT16
+ATDE_D void mdct_frame(const DevTables* __restrict__ T, const float* f0, const float* f1, const float* f2, unsigned msk,
+                       cpx* fft, float* spf, int lane)
+{
+    const bool s0 = msk & 1u, s1 = msk & 2u, s2 = msk & 4u;
+    if (s0) fold_band<true>(T->fold64, 64, T->win_short, f0, T->sincos64, 8, fft, lane);
+    else fold_band<false>(T->fold128, 64, T->win_long128, f0, T->sincos256, 32, fft, lane);
+    if (s1) fold_band<true>(T->fold64, 64, T->win_short, f1, T->sincos64, 8, fft + 64, lane);
+    else fold_band<false>(T->fold128, 64, T->win_long128, f1, T->sincos256, 32, fft + 64, lane);
+    if (s2) fold_band<true>(T->fold64, 128, T->win_short, f2, T->sincos64, 8, fft + 128, lane);
+    else fold_band<false>(T->fold256, 128, T->win_long256, f2, T->sincos512, 64, fft + 128, lane);
+    __syncwarp();
+    cpx* const b01 = fft + 64 * (lane >> 4);
+    cpx* const b2 = fft + 128;
+    const int v = lane & 15;
+    stage4c<1, 16>(b01, T->tw64, v);
+    if (s2) {
+        stage4c<1, 4>(b2 + 16 * (lane >> 2), T->tw16, lane & 3);
+    } else {
+        kf_stage2(b2, T->tw128, lane, 1, 64);
+        kf_stage2(b2, T->tw128, lane + 32, 1, 64);
+    }
+    __syncwarp();
+    stage4c<4, 4>(b01, T->tw64, v);
+    if (s2) stage4c<4, 1>(b2 + 16 * (lane >> 2), T->tw16, lane & 3);
+    else stage4c<2, 16>(b2, T->tw128, lane);
+    __syncwarp();
+    if (!((lane >> 4) ? s1 : s0)) stage4c<16, 1>(b01, T->tw64, v);
+    if (!s2) {
+        stage4c<8, 4>(b2, T->tw128, lane);
+        __syncwarp();
+        stage4c<32, 1>(b2, T->tw128, lane);
+    }
+    __syncwarp();
+    if (s0) post_band<32, 4, false, false>(fft, T->sincos64, spf, lane);
+    else post_band<128, 1, false, false>(fft, T->sincos256, spf, lane);
+    if (s1) post_band<32, 4, true, false>(fft + 64, T->sincos64, spf + 128, lane);
+    else post_band<128, 1, true, false>(fft + 64, T->sincos256, spf + 128, lane);
+    if (s2) post_band<32, 8, true, true>(fft + 128, T->sincos64, spf + 256, lane);
+    else post_band<256, 1, true, false>(fft + 128, T->sincos512, spf + 256, lane);
+}
+
 __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisParams p)
 {
     __shared__ __align__(16) float x[kNX + 8];      // input tile; later HPF output; later FFT buffer
@@ -258,111 +369,18 @@ __global__ void __launch_bounds__(kAnaThreads, 6) at1_analysis_kernel(AnalysisPa
         }
         __syncthreads();
 
-        // ---- MDCT: window + fold + pre-twiddle, written straight into kissfft's gather order ----
-        cpx* fft = reinterpret_cast<cpx*>(x);                      // kTile*256 complex
-        ATDE_PAR_FOR(u, kTile * 256) {
-            const int tl = u >> 8, slot = u & 255;
-            const int b = slot < 64 ? 0 : (slot < 128 ? 1 : 2);
-            const int bslot = slot - (b == 0 ? 0 : (b == 1 ? 64 : 128));
-            const int size = (b == 2) ? 256 : 128;
-            const bool shrt = (smask[tl] >> b) & 1;
-            const float* fr = (b == 0 ? lo + 40 : (b == 1 ? mi + 40 : s1hi + 89)) + tl * size;
-            int N, i, kb = 0;
-            const float* cs;
-            if (!shrt) {
-                N = 2 * size;
-                i = (b == 2) ? T->perm128[bslot] : T->perm64[bslot];
-                cs = (b == 2) ? T->sincos512 : T->sincos256;
-            } else {
-                N = 64;
-                kb = bslot >> 4;
-                i = T->perm16[bslot & 15];
-                cs = T->sincos64;
+        // ---- MDCT (TAtrac1MDCT::Mdct, atrac1denc.cpp:70-102): ONE WARP PER FRAME of the tile, no block barrier until the
+        //      spectra are stored; long and short blocks are chosen per band, uniformly over the warp ----
+        {
+            cpx* const fft_all = reinterpret_cast<cpx*>(x);        // kTile*256 complex (x is dead: the energies are taken)
+            const int lane = threadIdx.x & 31;
+            for (int tl = threadIdx.x >> 5; tl < kTile; tl += kAnaThreads / 32) {
+                const unsigned msk = smask[tl];
+                const float* f0 = lo + 40 + tl * 128;
+                const float* f1 = mi + 40 + tl * 128;
+                const float* f2 = s1hi + 89 + tl * 256;
+                mdct_frame(T, f0, f1, f2, msk, fft_all + tl * 256, sp + tl * 512, lane);
             }
-            const int n = 2 * i, n4 = N >> 2, n34 = 3 * n4, n54 = 5 * n4;
-            // tmp[j] of TAtrac1MDCT::Mdct = weight[j - joff] * band[j - joff + boff] inside the windowed stretch, 0 outside
-            // (long: 32-sample slope over the previous frame's tail, the frame, slope over its last 32 samples;
-            //  short block kb: the 64 samples around it) — one table look-up and one range test per sample
-            const float* wt = shrt ? T->win_short : (b == 2 ? T->win_long256 : T->win_long128);
-            const int joff = shrt ? 0 : ((b == 2) ? 112 : 48);
-            const int boff = shrt ? 32 * kb - 32 : -32;
-            const unsigned range = shrt ? 64u : (unsigned)(size + 32);
-            const int ia0 = n34 - 1 - n, ib0 = n4 + n;
-            const int ia1 = (n < n4) ? n34 + n : n - n4;
-            const int ib1 = (n < n4) ? n4 - 1 - n : n54 - 1 - n;
-            auto tmp_at = [&](int j) {
-                const int t = j - joff;
-                const bool ok = (unsigned)t < range;
-                const int tc = ok ? t : 0;
-                const float v = fmul(wt[tc], fr[tc + boff]);
-                return ok ? v : 0.0f;
-            };
-            const float a0 = tmp_at(ia0), a1 = tmp_at(ia1), b0 = tmp_at(ib0), b1 = tmp_at(ib1);
-            float r0, i0;
-            if (n < n4) { r0 = fadd(a0, a1); i0 = fsub(b0, b1); }
-            else        { r0 = fsub(a0, a1); i0 = fadd(b0, b1); }
-            const float cc = cs[n], ss = cs[n + 1];
-            cpx X;
-            X.r = fadd(fmul(r0, cc), fmul(i0, ss));
-            X.i = fsub(fmul(i0, cc), fmul(r0, ss));
-            fft[u] = X;
-        }
-        __syncthreads();
-        // ---- FFT stages, innermost first.  Per frame: 16 (low) + 16 (mid) + 64 (hi) item slots ----
-        for (int st = 0; st < 4; st++) {
-            ATDE_PAR_FOR(u, kTile * 96) {
-                const int tl = u / 96, w = u - tl * 96;
-                const int b = w < 16 ? 0 : (w < 32 ? 1 : 2);
-                const int v = w - (b == 0 ? 0 : (b == 1 ? 16 : 32));
-                const bool shrt = (smask[tl] >> b) & 1;
-                cpx* buf = fft + tl * 256 + (b == 0 ? 0 : (b == 1 ? 64 : 128));
-                if (shrt) {
-                    // FFT16 = 4x4: stages m=1 (fstride 4), m=4 (fstride 1); 4 butterflies per instance
-                    const int ninst4 = (b == 2) ? 32 : 16;
-                    if (st < 2 && v < ninst4) {
-                        const int inst = v >> 2, vv = v & 3;
-                        kf_stage4<false>(buf + 16 * inst, T->tw16, vv, st == 0 ? 1 : 4, st == 0 ? 4 : 1);
-                    }
-                } else if (b != 2) {
-                    // FFT64 = 4x4x4: m = 1, 4, 16
-                    if (st < 3 && v < 16) {
-                        const int m = st == 0 ? 1 : (st == 1 ? 4 : 16);
-                        kf_stage4<false>(buf, T->tw64, v, m, 16 / m);
-                    }
-                } else {
-                    // FFT128 = 4x4x4x2: radix-2 innermost (m=1), then m = 2, 8, 32
-                    if (st == 0) {
-                        kf_stage2(buf, T->tw128, v, 1, 64);
-                    } else if (v < 32) {
-                        const int m = st == 1 ? 2 : (st == 2 ? 8 : 32);
-                        kf_stage4<false>(buf, T->tw128, v, m, 32 / m);
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        // ---- post-twiddle (mdct.h:92-101), level fix for hi/short, band reversal (atrac1denc.cpp:92-98) ----
-        ATDE_PAR_FOR(u, kTile * 256) {
-            const int tl = u >> 8, slot = u & 255;
-            const int b = slot < 64 ? 0 : (slot < 128 ? 1 : 2);
-            const int bslot = slot - (b == 0 ? 0 : (b == 1 ? 64 : 128));
-            const int size = (b == 2) ? 256 : 128;
-            const bool shrt = (smask[tl] >> b) & 1;
-            int n2, i, kb = 0;
-            const float* cs;
-            if (!shrt) { n2 = size; i = bslot; cs = (b == 2) ? T->sincos512 : T->sincos256; }
-            else { n2 = 32; kb = bslot >> 4; i = bslot & 15; cs = T->sincos64; }
-            const int n = 2 * i;
-            const cpx z = fft[u];
-            const float cc = cs[n], ss = cs[n + 1];
-            float va = fsub(fmul(-z.r, cc), fmul(z.i, ss));
-            float vb = fadd(fmul(-z.r, ss), fmul(z.i, cc));
-            if (shrt && b == 2) { va = fmul(va, 2.0f); vb = fmul(vb, 2.0f); }
-            int pa = n, pb = n2 - 1 - n;
-            if (b) { pa = n2 - 1 - pa; pb = n2 - 1 - pb; }
-            float* out = sp + tl * 512 + (b == 0 ? 0 : (b == 1 ? 128 : 256)) + 32 * kb;
-            out[pa] = va;
-            out[pb] = vb;
         }
         // ---- store spectra and masks (the loudness term has its own kernel: it is one sequential sum per frame).
         //      A frame's 512 spectral lines are one 2 KB row in shared and in global memory: bulk asynchronous stores ----

@@ -24,6 +24,10 @@ struct DevTables {
     // MDCT input weights (TAtrac1MDCT::Mdct, atrac1denc.cpp:80-90) as tables: position t of the windowed stretch of a
     // long block (32-sample sine slope | 1.0 | mirrored slope) and of a 64-sample short block (slope | mirrored slope)
     float win_long128[160], win_long256[288], win_short[64];
+    // Fold map of a long block / of a short block (mdct.h:56-76), per output slot in kissfft's gather order: the four positions
+    // t = j - joff of the slot's inputs in the windowed stretch, 10 bits each (a0 | a1 << 10 | b0 << 20 | b1 << 30;
+    // 1023 = outside the stretch, the reference's buffer holds 0 there), and the slot's index i = n / 2 at bit 40
+    alignas(8) unsigned long long fold128[64], fold256[128], fold64[16];   // long 128- / 256-sample band, short block
 };
 
 struct AnalysisParams {

@@ -179,6 +179,28 @@ int build_at1_tables(atde_encoder* e)
     for (int i = 0; i < 128; i++) h->perm128[i] = (unsigned char)p128[i];
     for (int i = 0; i < 64; i++) h->perm64[i] = (unsigned char)p64[i];
     for (int i = 0; i < 16; i++) h->perm16[i] = (unsigned char)p16[i];
+    for (int kind = 0; kind < 3; kind++) {
+        // kind 0 / 1: long block of a 128-sample (low, mid: MDCT-256) / 256-sample band (hi: MDCT-512); kind 2: a short
+        // block (MDCT-64).  TMDCT's fold (mdct.h:56-76) reads in[n34-1-n], in[n34+n | n-n4], in[n4+n], in[n4-1-n | n54-1-n];
+        // TAtrac1MDCT::Mdct's buffer is the windowed stretch (32 samples before the block + the block; a short block's
+        // stretch is 64 samples) at offset joff, zeros around it (atrac1denc.cpp:80-90)
+        const int N = kind == 0 ? 256 : (kind == 1 ? 512 : 64), n4 = N / 4, n34 = 3 * n4, n54 = 5 * n4;
+        const int joff = kind == 0 ? 48 : (kind == 1 ? 112 : 0), range = kind == 2 ? 64 : N / 2 + 32;
+        unsigned long long* tab = kind == 0 ? h->fold128 : (kind == 1 ? h->fold256 : h->fold64);
+        for (int slot = 0; slot < N / 4; slot++) {
+            const int i = kind == 0 ? p64[slot] : (kind == 1 ? p128[slot] : p16[slot]), n = 2 * i;
+            const int j[4] = {n34 - 1 - n, n < n4 ? n34 + n : n - n4, n4 + n, n < n4 ? n4 - 1 - n : n54 - 1 - n};
+            unsigned long long e = (unsigned long long)i << 40;
+            for (int q = 0; q < 4; q++) {
+                const int t = j[q] - joff;
+                e |= (unsigned long long)((t >= 0 && t < range) ? t : 1023) << (10 * q);
+            }
+            tab[slot] = e;
+        }
+    }
+    // the analysis kernel runs the first two FFT stages of long and short blocks with one table (at1_kernels.cu: mdct_frame)
+    for (int k = 0; k < 16; k++)
+        if (memcmp(&tw64[4 * k], &tw16[k], sizeof(tw16[k])) != 0) { delete h; return fail(ATDE_ERR_INVALID, "kissfft twiddles of 64 and 16 points disagree"); }
 
     cudaError_t ce = cudaMalloc(&e->d_at1_tab, sizeof(at1::DevTables));
     if (ce == cudaSuccess) ce = cudaMemcpy(e->d_at1_tab, h, sizeof(at1::DevTables), cudaMemcpyHostToDevice);

@@ -1,17 +1,17 @@
 #!/usr/bin/env python3
-"""Per-source-line view of one kernel of an .ncu-rep: executed warp-instructions, average active lanes, stall
-samples and shared-memory wavefronts, by joining `ncu --page source --csv` (SASS rows) with `nvdisasm -g` line
-info of the cubin the report was taken from.  Inlined code is attributed to the innermost source line.
-usage: line_profile.py <report.ncu-rep> <kernel name> <cubin> <mangled-substring> [top]"""
-import csv, re, subprocess, sys
+"""Per-source-line table of one kernel from an `ncu --page source --csv` dump joined with `nvdisasm -g -c` of the cubin
+the report was taken from: executed warp-instructions, active lanes per instruction, stall samples (with the top stall
+reasons) and shared-memory wavefronts (actual / ideal) per CUDA source line.
+usage: line_profile.py <ncu_source.csv> <nvdisasm_g.txt> <kernel-mangled-substring> [top] [--by-instr|--by-samples]"""
+import csv, re, sys
 from collections import defaultdict
-rep, kname, cubin, mangled = sys.argv[1:5]
-top = int(sys.argv[5]) if len(sys.argv) > 5 else 45
-sass = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+src_csv, sass_txt, kern = sys.argv[1:4]
+top = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 60
+order = "instr" if "--by-instr" in sys.argv else "samples"
 line_of, cur, inside = {}, None, False
-for ln in sass.splitlines():
+for ln in open(sass_txt):
     if ln.startswith('//---') and '.text.' in ln:
-        inside = mangled in ln
+        inside = kern in ln
         continue
     if not inside:
         continue
@@ -22,36 +22,35 @@ for ln in sass.splitlines():
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(\S.*?);', ln)
     if m:
         line_of[int(m.group(1), 16)] = cur
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kname], capture_output=True, text=True).stdout
-rows = list(csv.reader(src.splitlines()))
+rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
-col = {n: (hdr.index(n) if n in hdr else -1) for n in ('Address', 'Source', '# Samples', 'Instructions Executed', 'Thread Instructions Executed',
-                                                         'L1 Wavefronts Shared', 'L1 Wavefronts Shared Ideal')}
-stall_cols = [(n, i) for i, n in enumerate(hdr) if n.startswith('stall_') and 'Not Issued' not in n]
+col = {n: i for i, n in enumerate(hdr)}
+stalls = [n for n in hdr if n.startswith('stall_') and 'Not Issued' not in n]
 base = int(rows[2][col['Address']], 16)
-agg = defaultdict(lambda: [0, 0, 0, 0, 0]); stalls = defaultdict(lambda: defaultdict(int)); tot = [0, 0, 0]
-ops = defaultdict(int); allst = defaultdict(int)
+agg = defaultdict(lambda: defaultdict(float))
+tot_i = tot_s = 0
+reasons = defaultdict(float)
 for r in rows[2:]:
-    if len(r) < len(hdr) or r[col['Address']] == 'Address':
+    if len(r) < len(hdr):
         continue
-    off = int(r[col['Address']], 16) - base
-    key = line_of.get(off)
-    n, t, s = int(r[col['Instructions Executed']]), int(r[col['Thread Instructions Executed']]), int(r[col['# Samples']])
+    if r[col['Address']] == 'Address':          # a second launch of the kernel follows: the first one is enough
+        break
+    key = line_of.get(int(r[col['Address']], 16) - base)
     a = agg[key]
-    a[0] += n; a[1] += t; a[2] += s; a[3] += int((r[col['L1 Wavefronts Shared']] if col['L1 Wavefronts Shared'] >= 0 else 0) or 0); a[4] += int((r[col['L1 Wavefronts Shared Ideal']] if col['L1 Wavefronts Shared Ideal'] >= 0 else 0) or 0)
-    tot[0] += n; tot[1] += t; tot[2] += s
-    for nme, i in stall_cols:
-        v = int(r[i] or 0)
-        if v:
-            stalls[key][nme] += v; allst[nme] += v
-    w = r[col['Source']].split()
-    ops[w[1] if w[0].startswith('@') else w[0]] += n
-print(f"kernel {kname}: {tot[0]} warp-instructions, {tot[1] / max(1, tot[0]):.1f} lanes/instr, {tot[2]} stall samples")
-print("all samples by reason:", ", ".join(f"{k[6:]} {100 * v / tot[2]:.0f}%" for k, v in sorted(allst.items(), key=lambda kv: -kv[1])[:8]))
+    n = float(r[col['Instructions Executed']] or 0)
+    a['i'] += n; tot_i += n
+    a['t'] += float(r[col['Thread Instructions Executed']] or 0)
+    sm = float(r[col['# Samples']] or 0)
+    a['s'] += sm; tot_s += sm
+    a['w'] += float(r[col['L1 Wavefronts Shared']] or 0)
+    a['wi'] += float(r[col['L1 Wavefronts Shared Ideal']] or 0)
+    for st in stalls:
+        v = float(r[col[st]] or 0)
+        a[st] += v; reasons[st] += v
+print(f"kernel {kern}: {int(tot_i)} warp-instructions, {sum(a['t'] for a in agg.values()) / max(tot_i, 1):.1f} lanes/instr, {int(tot_s)} stall samples")
+print("all samples by reason: " + ", ".join(f"{k[6:]} {100 * v / max(tot_s, 1):.0f}%" for k, v in sorted(reasons.items(), key=lambda kv: -kv[1])[:8]))
 print(f"{'instr':>12} {'%':>5} {'lanes':>5} {'samp%':>6} {'shWave':>10} {'ideal':>10}  line  top stalls")
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
-    st = ", ".join(f"{n[6:]} {v}" for n, v in sorted(stalls[k].items(), key=lambda kv: -kv[1])[:3])
-    print(f"{a[0]:12d} {100 * a[0] / tot[0]:5.1f} {a[1] / max(1, a[0]):5.1f} {100 * a[2] / max(1, tot[2]):6.1f} {a[3]:10d} {a[4]:10d}  {k}  {st}")
-print('--- by opcode')
-for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:22]:
-    print(f'{v:14d} {100 * v / tot[0]:5.1f}%  {k}')
+keyf = (lambda kv: -kv[1]['i']) if order == "instr" else (lambda kv: -kv[1]['s'])
+for k, a in sorted(agg.items(), key=keyf)[:top]:
+    ts = sorted(((st[6:], a[st]) for st in stalls), key=lambda kv: -kv[1])[:3]
+    print(f"{int(a['i']):12d} {100 * a['i'] / tot_i:5.1f} {a['t'] / max(a['i'], 1):5.1f} {100 * a['s'] / max(tot_s, 1):6.1f} {int(a['w']):10d} {int(a['wi']):10d}  {k}  " + ", ".join(f"{n} {int(v)}" for n, v in ts))

@@ -474,24 +474,6 @@ constexpr int kPackWarps = 4;
 
 ATDE_D unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// CalcBitsAllocation for one BFU (atrac1_bitalloc.cpp:185-203)
-ATDE_D unsigned calc_wl(int sfi, float energy, bool short_block, float fix, float ath, float loud,
-                        float shift, float bias)
-{
-    const float a = fmul(ath, loud);
-    if (!short_block && energy < a)
-        return 0;
-    const float spread = 0.4f;
-    float v = fmul(spread, __fdiv_rn((float)sfi, 3.2f));
-    v = fadd(v, fmul(fsub(1.0f, spread), fix));
-    v = fsub(v, shift);
-    v = fadd(v, bias);
-    const int tmp = __float2int_rz(v);
-    if (tmp > 16) return 16;
-    if (tmp < 2) return 0;
-    return (unsigned)tmp;
-}
-
 // MSB-first bit field into a zeroed big-endian word array (value already masked to n bits)
 ATDE_D void put_bits(unsigned* words, int pos, int n, unsigned val)
 {
@@ -518,7 +500,7 @@ ATDE_D void bs_grow(int& size, int& used, int n)
 
 __global__ void __launch_bounds__(kPackWarps * 32) at1_pack_kernel(PackParams p)
 {
-    __shared__ float sv_all[kPackWarps][512];
+    __shared__ __align__(16) float sv_all[kPackWarps][512];
     __shared__ unsigned words_all[kPackWarps][56];
     __shared__ unsigned char wl_all[kPackWarps][kMaxBfus + 4];
 
@@ -536,7 +518,14 @@ __global__ void __launch_bounds__(kPackWarps * 32) at1_pack_kernel(PackParams p)
     const float loud = __fdiv_rn(p.loud[sf], kLoudFactor);        // Loudness / LoudFactor, atrac1denc.cpp:250
 
     const float* __restrict__ src = p.specs + (size_t)unit * 512;
-    for (int i = lane; i < 512; i += 32) sv[i] = src[i];
+    {   // the channel-frame's 2 KB: four 16-byte loads per lane, all in flight before the first store
+        const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
+        float4 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) v[r] = src4[lane + 32 * r];
+#pragma unroll
+        for (int r = 0; r < 4; r++) reinterpret_cast<float4*>(sv)[lane + 32 * r] = v[r];
+    }
     for (int i = lane; i < 56; i += 32) words[i] = 0;
     __syncwarp();
 
@@ -583,15 +572,20 @@ __global__ void __launch_bounds__(kPackWarps * 32) at1_pack_kernel(PackParams p)
     const unsigned sum_m32 = warp_sum(lane >= 20 ? (unsigned)sfi[0] : 0u);
     const unsigned sum_m36 = sum_m32 + warp_sum(lane < 4 ? (unsigned)sfi[1] : 0u);
 
-    float fix[2], ath[2];
-    bool shrt[2];
+    // CalcBitsAllocation (atrac1_bitalloc.cpp:185-203) evaluates spread * (sfi / 3.2f) + (1 - spread) * fix - shift + bias
+    // left to right: the first two terms and the audibility test do not depend on the search variable and are taken once
+    // per BFU (the search runs ~25 steps per channel-frame)
+    float wl_base[2];
+    bool audible[2], shrt[2];
     int len[2];
     for (int h = 0; h < 2; h++) {
         const int b = lane + 32 * h;
         const int bb = b < kMaxBfus ? b : kMaxBfus - 1;
         shrt[h] = (mask >> bfu_band(bb)) & 1;
-        fix[h] = shrt[h] ? (float)kFixShort[bb] : (float)kFixLong[bb];
-        ath[h] = T->ath_long[bb];
+        const float fix = shrt[h] ? (float)kFixShort[bb] : (float)kFixLong[bb];
+        const float spread = 0.4f;
+        audible[h] = shrt[h] || !(energy[h] < fmul(T->ath_long[bb], loud));
+        wl_base[h] = fadd(fmul(spread, __fdiv_rn((float)sfi[h], 3.2f)), fmul(fsub(1.0f, spread), fix));
         len[h] = kSpecsPerBlock[bb];
     }
 
@@ -628,8 +622,9 @@ __global__ void __launch_bounds__(kPackWarps * 32) at1_pack_kernel(PackParams p)
             for (int h = 0; h < 2; h++) {
                 const int b = lane + 32 * h;
                 wl[h] = 0;
-                if (b < nbfu) {
-                    wl[h] = calc_wl(sfi[h], energy[h], shrt[h], fix[h], ath[h], loud, shift, bias[h]);
+                if (b < nbfu && audible[h]) {
+                    const int tmp = __float2int_rz(fadd(fsub(wl_base[h], shift), bias[h]));
+                    wl[h] = tmp > 16 ? 16u : (tmp < 2 ? 0u : (unsigned)tmp);
                     my_bits += (unsigned)len[h] * wl[h];
                 }
             }

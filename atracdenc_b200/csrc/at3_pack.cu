@@ -791,7 +791,14 @@ __global__ void __launch_bounds__(64, ATDE_PACK_MINBLOCKS) at3_alloc_pack_kernel
 
     // ---- load; header + gain info size of both channels (WriteSoundUnit, :771-804) ----
     const float* gsp = b.specs + (size_t)unit * 1024;
-    for (int i = lane; i < 1024; i += 32) sh.sv[i] = gsp[i];
+    {   // the channel's 4 KB of scaled spectrum: eight 16-byte loads per lane, all in flight before the first store
+        const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gsp);
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = g4[lane + 32 * r];
+#pragma unroll
+        for (int r = 0; r < 8; r++) reinterpret_cast<float4*>(sh.sv)[lane + 32 * r] = v[r];
+    }
     const TonalList* tl = b.tonal + unit;
     const int n_ton = g.no_tonal ? 0 : tl->n;
     if (lane < n_ton) {

@@ -170,7 +170,14 @@ __global__ void __launch_bounds__(kScaleWarps * 32) at3_scale_tonal_kernel(Geome
     if (unit >= total) return;
     float* sv = sv_all[wib];
     float* gsp = b.specs + (size_t)unit * 1024;
-    for (int i = lane; i < 1024; i += 32) sv[i] = gsp[i];
+    {   // eight 16-byte loads per lane, all in flight before the first store
+        const float4* g4 = reinterpret_cast<const float4*>(gsp);
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = g4[lane + 32 * r];
+#pragma unroll
+        for (int r = 0; r < 8; r++) reinterpret_cast<float4*>(sv)[lane + 32 * r] = v[r];
+    }
     run_len[wib][lane] = 0;
     __syncwarp();
 
@@ -333,8 +340,16 @@ __global__ void __launch_bounds__(kLoudWarps * 32) at3_loudterm_kernel(Geometry 
     const int nrows = (int)min(32LL, total - unit0);
     float l = 0.0f;
     for (int t = 0; t < 32; t++) {
-        for (int r = 0; r < nrows; r++)
-            tile[r][lane] = b.specs[(size_t)(unit0 + r) * 1024 + 32 * t + lane];
+        // (eight rows' loads in flight at a time)
+        for (int r0 = 0; r0 < nrows; r0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                v[q] = r0 + q < nrows ? b.specs[(size_t)(unit0 + r0 + q) * 1024 + 32 * t + lane] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (r0 + q < nrows) tile[r0 + q][lane] = v[q];
+        }
         __syncwarp();
         const float f = fr[t >> 3];
         if (live) {

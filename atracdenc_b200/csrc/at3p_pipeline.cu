@@ -123,10 +123,14 @@ int pipeline_run(StreamState* st, const float* d_pcm, int s0, int S, int total, 
     // (sized for the continuation case, N analyses, also on the first batch with its N - 1: the second call of a run must
     // not re-allocate in mid-pipeline)
     const size_t nAmax = (size_t)(N > 0 ? N : 1);
+    // the tone search's block count is NOT monotonic in the number of analyses (more analyses can mean larger batches per
+    // block and fewer blocks): the scratch area covers this launch AND the continuation call's
+    const int blocks_cont = gha_blocks_for((long long)S * (long long)nAmax);
+    const int scratch_blocks = gha_blocks > blocks_cont ? gha_blocks : blocks_cont;
     if (!w.bands.ensure((size_t)S * C * L * kFrame) || !w.resid.ensure((size_t)S * C * (nAmax + 1) * kFrame) ||
         !w.specs.ensure((size_t)S * nAmax * C * kFrame) || !w.tones.ensure((size_t)S * (nAmax + 2)) ||
         !w.frame_out.ensure((size_t)S * nAmax * gha_frame_out_bytes()) ||
-        !w.scratch.ensure(gha_scratch_bytes(gha_blocks_for((long long)S * nAmax)))) { *err = "cudaMalloc (workspace)"; return -3; }
+        !w.scratch.ensure(gha_scratch_bytes(scratch_blocks))) { *err = "cudaMalloc (workspace)"; return -3; }
 
     float* band_hist = st->band_hist.p + (size_t)s0 * C * 2 * kFrame;
     float* pcm_tail = st->pcm_tail.p + (size_t)s0 * kPqfOverlap * C;

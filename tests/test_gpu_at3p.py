@@ -1,7 +1,10 @@
 """GPU parity suite, ATRAC3plus stage kernels (PQF analysis, MDCT-256 x16) against the
 reference's taps (oracle/_ref)."""
+import numpy as np
 import pytest
 
+import atde_testlib as tl
+import atracdenc_b200 as ab
 import parity_cases as pc
 
 pytestmark = pytest.mark.gpu
@@ -130,3 +133,23 @@ def test_full_size_properties(gpu_lib):
 def test_golden(gpu_lib):
     pc.check_at3p_golden(gpu_lib, "at3p_stereo.npz")
     pc.check_at3p_golden(gpu_lib, "at3p_mono.npz")
+
+
+def test_search_scratch_covers_first_and_continuation_batch(gpu_lib):
+    """The tone search runs ceil(n / fb(n)) blocks for n analyses, which is NOT monotonic in n: 37 streams x 64 analyses
+    (a fresh batch of 65 calls) take 296 blocks, the continuation batch's 37 x 65 take 268 — the scratch area is sized
+    for both (a batch of 128 x 123 once overran it: illegal memory access).  Frames are checked against the reference
+    for a few streams; both calls of a run go through."""
+    S, F, C = 37, 65, 2
+    pcm = pc._at3p_signal(S, 2 * F, C, 4242)
+    enc = ab.Encoder(ab.CODEC_ATRAC3PLUS, C, lib=gpu_lib)
+    first = enc.encode(pcm[:, :F * 2048], S)
+    second = enc.encode(pcm[:, F * 2048:], S)
+    enc.close()
+    assert first.shape == (S, F - 1, 1, 2048) and second.shape == (S, F, 1, 2048)
+    tl.require_ref()
+    for s in (0, 17, 36):
+        st = tl.ref_at3p_stages(C, pcm[s].reshape(-1))
+        got = np.concatenate([first[s, :, 0], second[s, :, 0]])
+        bad = np.argwhere((got != st["frames"]).any(-1))
+        assert bad.size == 0, f"stream {s}: differing frames {bad[:4].ravel().tolist()}"

@@ -48,6 +48,9 @@ static DevTables* build_tables()
     for (int i = 1; i < 8; i++) h->inv_mant[i] = 1.0f / bits_to_float(kAt3pMantTabBits[i]);   // TUnit::Multiplier, at3p_bitstream.cpp:365-368
     memcpy(h->spec_tab, kAt3pSpecTab, sizeof(h->spec_tab));
     memcpy(h->vlc_off, kAt3pVlcOff, sizeof(h->vlc_off));
+    for (int t = 0; t < 56; t++)
+        h->spec_pack[t] = (unsigned)kAt3pSpecTab[t][0] | (unsigned)kAt3pSpecTab[t][1] << 4 | (unsigned)kAt3pSpecTab[t][2] << 8 |
+                          (unsigned)kAt3pSpecTab[t][3] << 12 | kAt3pVlcOff[t] << 16;
     static_assert(sizeof(kAt3pVlc) == sizeof(DevTables::vlc), "generated VLC table size");
     memcpy(h->vlc, kAt3pVlc, sizeof(h->vlc));
     memcpy(h->wl_vlc, kAt3pWlVlc, sizeof(h->wl_vlc));
@@ -528,9 +531,32 @@ ATDE_D unsigned spec_symbol(const DevTables* T, int tab, const signed char* m, i
     int n = (int)(e >> 16);
     out = (out << nsign) | signs;
     n += nsign;
-    if (g != 1 && (s % g) == 0) { out |= 1u << n; n++; }
+    if (g != 1 && (s & (g - 1)) == 0) { out |= 1u << n; n++; }       // group sizes are 1, 2, 4
     nbits = n;
     return out;
+}
+
+// The bit count of the same symbol alone, for a table whose geometry (NC coefficients of `bits` bits per symbol, signed
+// or sign bits apart, group flag every g symbols) is uniform over the warp.
+template <int NC>
+ATDE_D unsigned symbol_bits(const unsigned* __restrict__ vlc, int g, int bits, int sgn, const signed char* m, int s)
+{
+    unsigned val = 0, n = 0;
+    const unsigned mask = (1u << bits) - 1u;
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        int t = m[s * NC + i];
+        if (!sgn) {
+            n += t != 0;
+            t = abs(t);
+        } else {
+            t &= (int)mask;
+        }
+        val |= (unsigned)t << (bits * i);
+    }
+    n += vlc[val & 255u] >> 16;
+    if (g != 1 && (s & (g - 1)) == 0) n++;
+    return n;
 }
 
 ATDE_D int first_set_bit(unsigned x) { return x ? 31 - __clz((int)x) : 0; }   // util.h:65-76
@@ -638,12 +664,17 @@ ATDE_D int write_tonal_block(const DevTables* T, unsigned* w, int cap, int pos, 
 
 ATDE_D unsigned warp_incl_scan(unsigned v, int lane)
 {
+#pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned a = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += a;
+        v += lane >= d ? a : 0u;
     }
     return v;
 }
+
+// quant unit of spectral line i (c_qu_start: 8 units of 16 lines, 8 of 32, 6 of 64, 10 of 128) and its first line
+ATDE_D int qu_of_line(int i) { return i < 128 ? i >> 4 : (i < 384 ? 8 + ((i - 128) >> 5) : (i < 768 ? 16 + ((i - 384) >> 6) : 22 + ((i - 768) >> 7))); }
+ATDE_D int qu_first_line(int q) { return q < 8 ? 16 * q : (q < 16 ? 128 + 32 * (q - 8) : (q < 22 ? 384 + 64 * (q - 16) : 768 + 128 * (q - 22))); }
 
 __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTables* __restrict__ T,
                                                                      const float* __restrict__ specs,
@@ -659,52 +690,60 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
     for (int i = lane; i < kFrameBytes / 4 + 4; i += 32) sh.words[i] = 0;
     for (int i = lane; i < 96; i += 32) sh.twords[i] = 0;
 
-    // ---- TScaler::Scale per quant unit + the fixed-word-length quantiser (QuantMantisas, ea = false)
-    for (int ch = 0; ch < C; ch++) {
-        const float* x = specs + ((size_t)unit * C + ch) * kFrame;
-        for (int qu = 0; qu < kQuantUnits; qu++) {
-            const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
+    // ---- TScaler::Scale per quant unit + the fixed-word-length quantiser (QuantMantisas, ea = false).
+    //      Lane q owns quant unit q for the maximum and the scale-factor search (32 units at once: the loads of a unit are
+    //      independent of every other unit's search); the division and rounding then run over the lines, coalesced
+    {
+        const int my_start = qu_first_line(lane), my_len = qu_first_line(lane + 1) - my_start;
+        const float my_mul = T->inv_mant[c_alloc[lane]];
+        for (int ch = 0; ch < C; ch++) {
+            const float* x = specs + ((size_t)unit * C + ch) * kFrame;
             float mx = 0.0f;
-            for (int i = lane; i < len; i += 32) mx = fmaxf(mx, fabsf(x[start + i]));
-            for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            for (int i = 0; i < my_len; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(x + my_start + i);
+                mx = fmaxf(fmaxf(fmaxf(mx, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+            }
             if (mx > 1.0f) mx = 1.0f;                                  // MAX_SCALE
             int lo = 0, hi = 63;                                       // lower_bound over the ascending table
-            while (lo < hi) {
+#pragma unroll
+            for (int it = 0; it < 6; it++) {                           // 64 entries: six halvings, then lo == hi
                 const int mid = (lo + hi) >> 1;
                 if (T->scale_table[mid] < mx) lo = mid + 1; else hi = mid;
             }
             const float sf = T->scale_table[lo];
-            const float mul = T->inv_mant[c_alloc[qu]];
-            for (int i = lane; i < len; i += 32) {
-                float v = __fdiv_rn(x[start + i], sf);
+            sh.sfi[ch][lane] = (unsigned char)lo;
+#pragma unroll 4
+            for (int r = 0; r < kFrame / 32; r++) {
+                const int i = 32 * r + lane, q = qu_of_line(i);
+                const float sfq = __shfl_sync(0xffffffffu, sf, q), mul = __shfl_sync(0xffffffffu, my_mul, q);
+                float v = __fdiv_rn(x[i], sfq);
                 if (fabsf(v) >= 1.0f) v = v > 0.0f ? 0.99999f : -0.99999f;
-                sh.mant[ch][start + i] = (signed char)__float2int_rn(fmul(v, mul));
+                sh.mant[ch][i] = (signed char)__float2int_rn(fmul(v, mul));
             }
-            if (lane == 0) sh.sfi[ch][qu] = (unsigned char)lo;
         }
     }
     __syncwarp();
-    // ---- TUnit::GetOrCompute (:370-397): cheapest of the 8 code tables per unit; lane = (table, quarter)
-    {
-        const int ti = lane >> 2, sub = lane & 3;
-        for (int ch = 0; ch < C; ch++)
-            for (int qu = 0; qu < kQuantUnits; qu++) {
-                const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
-                const int tab = c_alloc[qu] - 1 + 7 * ti;
-                const int nsym = len / T->spec_tab[tab][1];
+    // ---- TUnit::GetOrCompute (:370-397): cheapest of the 8 code tables per unit.  The tables are tried one after the
+    //      other with the lanes over the unit's symbols: a table's geometry (coefficients per symbol, bits, signedness,
+    //      group size) is then uniform over the warp and the symbol loop has no divergent branch
+    for (int ch = 0; ch < C; ch++)
+        for (int qu = 0; qu < kQuantUnits; qu++) {
+            const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
+            const signed char* m = sh.mant[ch] + start;
+            unsigned best = 0xffffffffu;
+            for (int ti = 0; ti < 8; ti++) {
+                const unsigned sp = T->spec_pack[c_alloc[qu] - 1 + 7 * ti];
+                const int g = sp & 15u, nc = (sp >> 4) & 15u, nb = (sp >> 8) & 15u, sgn = (sp >> 12) & 1u;
+                const unsigned* __restrict__ vlc = T->vlc + (sp >> 16);
                 unsigned bits = 0;
-                for (int sidx = sub; sidx < nsym; sidx += 4) {
-                    int nb;
-                    spec_symbol(T, tab, sh.mant[ch] + start, sidx, nb);
-                    bits += (unsigned)nb;
-                }
-                bits += __shfl_xor_sync(0xffffffffu, bits, 1);
-                bits += __shfl_xor_sync(0xffffffffu, bits, 2);
-                unsigned key = bits * 8u + (unsigned)ti;                 // first minimum wins (t < consumed)
-                for (int d = 4; d < 32; d <<= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d));
-                if (lane == 0) { sh.qbits[ch][qu] = (unsigned short)(key >> 3); sh.qtab[ch][qu] = (unsigned char)(key & 7u); }
+                if (nc == 1) { for (int sx = lane; sx < len; sx += 32) bits += symbol_bits<1>(vlc, g, nb, sgn, m, sx); }
+                else if (nc == 2) { for (int sx = lane; sx < len / 2; sx += 32) bits += symbol_bits<2>(vlc, g, nb, sgn, m, sx); }
+                else { for (int sx = lane; sx < len / 4; sx += 32) bits += symbol_bits<4>(vlc, g, nb, sgn, m, sx); }
+                bits = __reduce_add_sync(0xffffffffu, bits);
+                best = min(best, bits * 8u + (unsigned)ti);                  // first minimum wins (t < consumed)
             }
-    }
+            if (lane == 0) { sh.qbits[ch][qu] = (unsigned short)(best >> 3); sh.qtab[ch][qu] = (unsigned char)(best & 7u); }
+        }
     __syncwarp();
     // ---- TTonalComponentEncoder::Encode (:611-669), once: its buffer survives the Repeat rounds
     // tones == nullptr: GHA_WRITE_TONAL is off — `delay` never holds a tone block (at3p.cpp:173-177)

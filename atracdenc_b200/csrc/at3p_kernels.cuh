@@ -33,6 +33,7 @@ struct DevTables {
     float inv_mant[8];                // 1 / atrac3p_mant_tab[wl] (at3p_tables.cpp:28-38)
     unsigned char spec_tab[56][4];    // group_size, num_coeffs, bits, is_signed (ff/atrac3plus_data.h:1427)
     unsigned vlc_off[57];
+    unsigned spec_pack[56];           // the same per table in one word: group | coeffs << 4 | bits << 8 | signed << 12 | vlc_off << 16
     unsigned vlc[7812];               // code | len << 16 of THuffTables::VlcSpecs[0..55]
     unsigned wl_vlc[4][8];            // THuffTables::WordLens
     unsigned tone_bands_vlc[16];      // THuffTables::NumToneBands

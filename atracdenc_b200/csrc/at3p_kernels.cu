@@ -295,8 +295,18 @@ __global__ void __launch_bounds__(128) at3p_tone_filter_kernel(const DevTables* 
     const float* in = bands ? bands + (((size_t)s * C + ch) * lay.in_frames + lay.in_off + q) * kFrame : nullptr;
     float* out = resid + (((size_t)s * C + ch) * lay.out_frames + lay.out_off + q) * kFrame;
     const bool any = now->present || next->present;                    // tones_present || prev tones_present
+    // the thread's 16 samples (one per subband) are fetched together — every load in flight at once — and parked in
+    // shared memory (each thread reads back only what it wrote): the subband loop below stays rolled
+    __shared__ float xs[kSubbands][128];
+    {
+        float xin[kSubbands];
+#pragma unroll
+        for (int sb = 0; sb < kSubbands; sb++) xin[sb] = in ? in[sb * kSbSamples + i] : 0.0f;
+#pragma unroll
+        for (int sb = 0; sb < kSubbands; sb++) xs[sb][i] = xin[sb];
+    }
     for (int sb = 0; sb < kSubbands; sb++) {
-        float x = in ? in[sb * kSbSamples + i] : 0.0f;
+        float x = xs[sb][i];
         if (sb < 8 && any) {
             const WaveGroup gn = resolve_group(now, C, ch, sb), gx = resolve_group(next, C, ch, sb);
             if (gn.num_wavs || gx.num_wavs) {

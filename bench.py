@@ -30,15 +30,15 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 WORKLOADS = {
     # name: (codec id, frame samples, S, F, units/frame, unit bytes, algorithmic QMF+MDCT bytes per stereo frame)
-    "atrac1_stereo_1e6": dict(codec=1, step=512, S=1024, F=977, alg_bytes=8192, kbit=0,
+    "atrac1_stereo_1e6": dict(codec=1, step=512, S=1024, F=977, alg_bytes=8192, kbit=0, fp32_ops=2 * 48600,
                               kernel="at1_analysis_kernel (QMF+transient+MDCT)",
                               settings="reference defaults (EWM_AUTO, bfuidxconst 0)",
                               desc="ATRAC1 encode, 10^6-frame synthetic stereo batch (BASELINE.json configs[1])"),
-    "atrac3_lp2_stereo_1e6": dict(codec=3, step=1024, S=1024, F=977, alg_bytes=16384, kbit=0,
+    "atrac3_lp2_stereo_1e6": dict(codec=3, step=1024, S=1024, F=977, alg_bytes=16384, kbit=0, fp32_ops=2 * 125000,
                                   kernel="at3_qmf_kernel + at3_mdct_kernel (QMF tree, gain modulation, MDCT-512 x4)",
                                   settings="reference defaults: LP2 132300 bit/s, gain control + tonal components on",
                                   desc="ATRAC3 LP2 (132 kbps) encode, 10^6-frame synthetic stereo batch (BASELINE.json configs[2])"),
-    "atrac3_lp4_stereo_1p25e6": dict(codec=3, step=1024, S=1024, F=1221, alg_bytes=16384, kbit=64,
+    "atrac3_lp4_stereo_1p25e6": dict(codec=3, step=1024, S=1024, F=1221, alg_bytes=16384, kbit=64, fp32_ops=2 * 125000,
                                      kernel="at3_qmf_kernel + at3_mdct_kernel (QMF tree, M/S, gain modulation, MDCT-512 x4)",
                                      settings="LP4 66150 bit/s joint stereo, gain control + tonal components on",
                                      desc="ATRAC3 LP4 (66 kbps, joint-stereo) encode, 1.25*10^6 frames per GPU "
@@ -53,6 +53,20 @@ DEFAULT_WORKLOAD = "atrac3_lp2_stereo_1e6"
 KIND_NAMES = ["qmf_mdct", "loudness_scan", "alloc_quant_pack", "gain_envelope", "gain_curve", "tonal_scale"]
 KIND_NAMES_AT3P = ["pqf_mdct", "-", "scale_quant_pack", "tone_search", "tone_filter", "-"]
 METRIC = "ATRAC3 stereo frames/s at 1/2/4/8 B200; QMF+MDCT achieved HBM GB/s vs peak"
+
+
+def fp32_view(wl, frames, kernel_ms, clocks):
+    """The same kernel against the FP32 issue roofline (the un-fused QMF + MDCT arithmetic makes the pair
+    FP32-issue bound, not HBM bound): un-fused fp32 operations per stereo frame (SURVEY.md's count: 48.6 k per ATRAC1
+    channel-frame, 125 k per ATRAC3 channel-frame) / kernel time, against 148 SMs x 128 lanes x the SM clock."""
+    ops = wl.get("fp32_ops")
+    if not ops or not kernel_ms:
+        return None
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = 148 * 128 * mhz * 1e6 / 1e12
+    ach = ops * frames / (kernel_ms / 1000.0) / 1e12
+    return {"achieved": ach, "peak": peak, "unit": "T un-fused fp32 op/s", "frac": ach / peak,
+            "ops_per_stereo_frame": ops, "sm_mhz": mhz}
 
 
 def read_peak():
@@ -449,6 +463,7 @@ def measure_workload(name, args, env, *, steps, warmup, verify_stride, with_i16=
                          "kernel": wl["kernel"], "peak_source": f"of {peak_kind}",
                          "kernel_ms": k1_ms, "alg_bytes_per_launch": alg_bytes,
                          "kernel_share_of_step": (kms[0] / dev_ms) if dev_ms else None,
+                         "fp32": fp32_view(wl, S * F, k1_ms, clocks),
                          "kernels_ms_per_step": {(KIND_NAMES_AT3P if wl["codec"] == 4 else KIND_NAMES)[k]: kms[k] / max(1, steps)
                                                  for k in range(6) if kcnt[k]}},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
@@ -584,7 +599,7 @@ def run_ours(args):
                 if "error" not in r:
                     r = {"value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
                          "workload": r["config"]["workload"], "settings": r["config"]["settings"],
-                         "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "kernel", "kernel_ms", "kernels_ms_per_step")},
+                         "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "fp32", "kernel", "kernel_ms", "kernels_ms_per_step")},
                          "e2e": {k: v for k, v in r["e2e"].items() if k != "host_binding"}, "parity": r["parity"]}
                 others[name] = r
 

@@ -803,7 +803,11 @@ static int encode_batch_host(atde_encoder* e, const float* pcm, const int16_t* p
     // (Not for ATRAC3plus: its tone search has a long per-launch tail that the next chunk's kernels fill, and
     // 191 + 191 + ... + 69 streams measured 350 ms per 250,880 frames against 373 ms with the short first chunk
     // and 494 ms with seven equal ones.)
-    size_t target_floats = (size_t)(at3 ? 192 : 48) << 20;                      // ~768 / ~192 MiB of PCM per chunk
+    // ATRAC3 after the round-2 kernel work (10^6-frame batch, 168 ms of kernels against 149 ms of float copy-in): float PCM
+    // 192 / 256 / 320 / 384 / 512 / 768 / 1024 / 1536 MiB per chunk -> 184.9 / 183.1 / 185.7 / 185.0 / 186.8 / 188.4 / 191.9 /
+    // 195.5 ms per step; int16 PCM (half the bytes: compute-bound) 182.7 / 181.5 / 181.5 / 182.3 / 180.9 / 179.5 / 180.7 / 181.2
+    // (profiles/tools/sweep_chunk.sh): 256 MiB chunks for float input, 768 MiB-equivalent ones for int16
+    size_t target_floats = (size_t)(at3 ? (pcm16 || at3p ? 192 : 64) : 48) << 20;   // floats of PCM per chunk
     if (at3p) {
         // every tone-search launch ends in a ~14 ms tail: aim at about five chunks per batch, 768 MiB .. 3 GiB each
         // (10^6-frame batch: 21 chunks of 768 MiB 1479 ms per step against 1188 ms device-resident)

@@ -403,6 +403,20 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     cpx* const fwd = fwd2[half];
     const cpx* __restrict__ tw = T->tw2048;
 
+    // the frame's 512 band samples come from DRAM: their loads are issued before anything else (four per thread, all in
+    // flight while the twiddles are staged)
+    float2 xin[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) xin[q] = act ? *reinterpret_cast<const float2*>(in + 2 * (t + 64 * q)) : make_float2(0.0f, 0.0f);
+    // ... and so are the thread's twiddles of the four forward stages (each stage used to fetch its own right behind a barrier)
+    cpx ft[4][3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        ft[0][q] = T->ftw[0][q][0];
+        ft[1][q] = T->ftw[1][q][t >> 4];
+        ft[2][q] = T->ftw[2][q][t & 15];
+        ft[3][q] = T->ftw[3][q][t];
+    }
     if (tid < 120) (&tw2c[0][0])[tid] = (&T->gtw2[0][0])[tid];
     f32x2 one2, mone2;
     one2.x = one2.y = g.one;
@@ -413,8 +427,10 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     // 1. Planck window, packed as the complex input of the half-size FFT; loaded in natural order and
     //    stored at its digit-reversed slot (base-4 reversal of 4 digits is an involution)
     if (act) {
-        for (int j = t; j < 256; j += 64) {
-            const float2 x = *reinterpret_cast<const float2*>(in + 2 * j);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = t + 64 * q;
+            const float2 x = xin[q];
             const float2 w = *reinterpret_cast<const float2*>(&T->planck[2 * j]);
             cpx z;
             z.r = fmul(x.x, w.x);
@@ -427,19 +443,13 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
     // 2. forward complex FFT-256 = 4x4x4x4, innermost stage first; the lane -> butterfly map of every
     //    stage is chosen so that 16 consecutive lanes touch 16 different bank pairs
     //    (padded addresses: element F + m q of a butterfly lies at fq(F) + q * (m + m / 16))
-    if (act) fwd_bfly(fwd, 4 * t + (t >> 2), 1, T->ftw[0][0][0], T->ftw[0][1][0], T->ftw[0][2][0]);
+    if (act) fwd_bfly(fwd, 4 * t + (t >> 2), 1, ft[0][0], ft[0][1], ft[0][2]);
     __syncthreads();
-    if (act) {
-        const int gq = t & 15, k = t >> 4;
-        fwd_bfly(fwd, 17 * gq + k, 4, T->ftw[1][0][k], T->ftw[1][1][k], T->ftw[1][2][k]);
-    }
+    if (act) fwd_bfly(fwd, 17 * (t & 15) + (t >> 4), 4, ft[1][0], ft[1][1], ft[1][2]);
     __syncthreads();
-    if (act) {
-        const int gq = t >> 4, k = t & 15;
-        fwd_bfly(fwd, 68 * gq + k, 17, T->ftw[2][0][k], T->ftw[2][1][k], T->ftw[2][2][k]);
-    }
+    if (act) fwd_bfly(fwd, 68 * (t >> 4) + (t & 15), 17, ft[2][0], ft[2][1], ft[2][2]);
     __syncthreads();
-    if (act) fwd_bfly(fwd, t + (t >> 4), 68, T->ftw[3][0][t], T->ftw[3][1][t], T->ftw[3][2][t]);
+    if (act) fwd_bfly(fwd, t + (t >> 4), 68, ft[3][0], ft[3][1], ft[3][2]);
     __syncthreads();
     // kiss_fftr post-processing (kiss_fftr.c:84-115)
     if (act) {
@@ -635,6 +645,8 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         // gphys(k + 128a + 512q) = k + k / 16 + 136a + 544q  (k < 128)
         const int k = tid;
         const cpx* const bg = big + k + (k >> 4);
+        // (the first stage's twiddles are requested before the shared-memory reads and the barrier, not behind them)
+        const cpx g3a0 = T->gtw3a[0][k], g3a1 = T->gtw3a[1][k], g3a2 = T->gtw3a[2][k];
         cpx x[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -643,8 +655,8 @@ __global__ void __launch_bounds__(kGainBlock, ATDE_GAIN_BLOCKS) at3_gain_kernel(
         atde_named_barrier(1, kGainThreads);                                  // every slot is in registers: big can be overwritten
         {
             const float mone = mone2.x;
-            const tw4 t1 = spread_twiddle_dev(T->gtw3a[0][k], mone), t2 = spread_twiddle_dev(T->gtw3a[1][k], mone),
-                      t3 = spread_twiddle_dev(T->gtw3a[2][k], mone);                     // tw[4k], tw[8k], tw[12k]
+            const tw4 t1 = spread_twiddle_dev(g3a0, mone), t2 = spread_twiddle_dev(g3a1, mone),
+                      t3 = spread_twiddle_dev(g3a2, mone);                               // tw[4k], tw[8k], tw[12k]
 #pragma unroll
             for (int q = 0; q < 4; q++) kf_bfly4_packed<true>(x[0][q], x[1][q], x[2][q], x[3][q], t1, t2, t3, one2, mone2);
         }
@@ -974,8 +986,17 @@ ATDE_D void curve_item(const Geometry& g, const Buffers& b, long long item)
     const float prev_hpf = pv.x, saved_ll = pv.y, saved_lt = pv.z;
 
     float gain[32], low[32], high[32];
-    const float* gp = b.gain + (size_t)item * 96;
-    for (int i = 0; i < 32; i++) { gain[i] = gp[i]; low[i] = gp[32 + i]; high[i] = gp[64 + i]; }
+    {   // the item's 384-byte record by 16-byte loads (a lane's record is contiguous: a quarter of the load instructions
+        // and of the L1 wavefronts of scalar loads)
+        const float4* __restrict__ gp4 = reinterpret_cast<const float4*>(b.gain + (size_t)item * 96);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 a = gp4[i], l = gp4[8 + i], h = gp4[16 + i];
+            gain[4 * i] = a.x; gain[4 * i + 1] = a.y; gain[4 * i + 2] = a.z; gain[4 * i + 3] = a.w;
+            low[4 * i] = l.x;  low[4 * i + 1] = l.y;  low[4 * i + 2] = l.z;  low[4 * i + 3] = l.w;
+            high[4 * i] = h.x; high[4 * i + 1] = h.y; high[4 * i + 2] = h.z; high[4 * i + 3] = h.w;
+        }
+    }
 
     const float ratio = (cur_hpf > 1e-9f && prev_hpf > 1e-9f) ? __fdiv_rn(prev_hpf, cur_hpf) : 1.0f;
     const float min_score = fmul(1.9f, fminf(1.5f, fmaxf(1.0f, ratio)));

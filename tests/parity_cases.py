@@ -669,7 +669,7 @@ def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700, variants=(None, "
     pipeline slots; ATRAC3 PCM through a ring of four staging buffers).  Forced down to four streams per chunk
     (1 + 4 + 4 + ...), to two and to one (the staging ring wraps) — or, with S >= 27, to eight (2 + 7 + 7 + 5 + 4 + 2: a
     tapered tail) — the result must equal the single-chunk batch, also on the continuation batch that starts from
-    carried state, and the int16 entry point must agree."""
+    carried state, and the int16 entry point must agree.  Variant "/i16": the library's own plan through the int16 entry point."""
     import os
     step = {ab.CODEC_ATRAC1: 512, ab.CODEC_ATRAC3: 1024, ab.CODEC_ATRAC3PLUS: 2048}[codec]
     rng = np.random.default_rng(seed)
@@ -681,7 +681,8 @@ def check_host_chunking(lib, codec, C=2, S=11, F=5, seed=1700, variants=(None, "
         q = np.clip(np.rint(pcm * 32768.0), -32768, 32767).astype(np.int16)
         pcm = (q.astype(np.float32) * np.float32(1.0 / 32768.0)).astype(np.float32)
         for streams in variants:
-            if streams:
+            os.environ.pop("ATDE_CHUNK_STREAMS", None)
+            if streams and streams.split("/")[0]:                  # ("/i16": the library's own plan, int16 entry point)
                 os.environ["ATDE_CHUNK_STREAMS"] = streams.split("/")[0]
             enc = ab.Encoder(codec, C, lib=lib)
             if streams and streams.endswith("i16"):

@@ -546,26 +546,41 @@ ATDE_D unsigned spec_symbol(const DevTables* T, int tab, const signed char* m, i
     return out;
 }
 
-// The bit count of the same symbol alone, for a table whose geometry (NC coefficients of `bits` bits per symbol, signed
-// or sign bits apart, group flag every g symbols) is uniform over the warp.
-template <int NC>
-ATDE_D unsigned symbol_bits(const unsigned* __restrict__ vlc, int g, int bits, int sgn, const signed char* m, int s)
+// The bit count of the symbols of ONE GROUP OF FOUR LINES (mantissas mv[0..3], group gi of its quant unit) under the code
+// table described by `sp` (DevTables::spec_pack): four symbols of one coefficient, two of two or one of four; a symbol
+// costs its VLC code, a sign bit per non-zero coefficient of an unsigned table and a group flag every g-th symbol
+// (TQuantUnitsEncoder::EncodeQuSpectra, at3p_bitstream.cpp:283-343).
+ATDE_D unsigned group_cost(unsigned sp, const unsigned* __restrict__ vlc_all, const int* mv, int gi)
 {
-    unsigned val = 0, n = 0;
-    const unsigned mask = (1u << bits) - 1u;
+    const int g = sp & 15u, nc = (sp >> 4) & 15u, nb = (sp >> 8) & 15u;
+    const bool sgn = (sp >> 12) & 1u;
+    const unsigned* __restrict__ vlc = vlc_all + (sp >> 16);
+    const unsigned mask = (1u << nb) - 1u;
+    unsigned t[4], n = 0;
 #pragma unroll
-    for (int i = 0; i < NC; i++) {
-        int t = m[s * NC + i];
-        if (!sgn) {
-            n += t != 0;
-            t = abs(t);
+    for (int i = 0; i < 4; i++) {
+        if (sgn) {
+            t[i] = (unsigned)mv[i] & mask;
         } else {
-            t &= (int)mask;
+            t[i] = (unsigned)abs(mv[i]);
+            n += mv[i] != 0;
         }
-        val |= (unsigned)t << (bits * i);
     }
-    n += vlc[val & 255u] >> 16;
-    if (g != 1 && (s & (g - 1)) == 0) n++;
+    const unsigned gm = (unsigned)g - 1u;                     // group sizes are 1, 2, 4
+    if (nc == 4) {
+        n += vlc[(t[0] | t[1] << nb | t[2] << (2 * nb) | t[3] << (3 * nb)) & 255u] >> 16;
+        n += g != 1 && ((unsigned)gi & gm) == 0;
+    } else if (nc == 2) {
+        n += vlc[(t[0] | t[1] << nb) & 255u] >> 16;
+        n += vlc[(t[2] | t[3] << nb) & 255u] >> 16;
+        n += g != 1 && ((unsigned)(2 * gi) & gm) == 0;        // the odd symbol never opens a group
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            n += vlc[t[i] & 255u] >> 16;
+            n += g != 1 && ((unsigned)(4 * gi + i) & gm) == 0;
+        }
+    }
     return n;
 }
 
@@ -733,26 +748,26 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
         }
     }
     __syncwarp();
-    // ---- TUnit::GetOrCompute (:370-397): cheapest of the 8 code tables per unit.  The tables are tried one after the
-    //      other with the lanes over the unit's symbols: a table's geometry (coefficients per symbol, bits, signedness,
-    //      group size) is then uniform over the warp and the symbol loop has no divergent branch
+    // ---- TUnit::GetOrCompute (:370-397): cheapest of the 8 code tables per unit.  A lane takes FOUR LINES (one, two or
+    //      four symbols, whatever the table); a pass of the warp covers 128 lines, i.e. eight units of 16 lines, four of
+    //      32, two of 64 or one of 128 — lane segments of 4 / 8 / 16 / 32, summed with segmented shuffles.  The tables of
+    //      a pass are uniform over the warp except in the one pass where the word length changes between two units.
     for (int ch = 0; ch < C; ch++)
-        for (int qu = 0; qu < kQuantUnits; qu++) {
-            const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
-            const signed char* m = sh.mant[ch] + start;
+        for (int p = 0; p < kFrame / 128; p++) {
+            const int line0 = 128 * p + 4 * lane;
+            const int qu = qu_of_line(line0), gi = (line0 - qu_first_line(qu)) >> 2;
+            const int seg = p == 0 ? 4 : (p <= 2 ? 8 : (p <= 5 ? 16 : 32));     // lanes per unit in this pass
+            const int wl = c_alloc[qu];
+            const int mm = *reinterpret_cast<const int*>(sh.mant[ch] + line0);
+            const int mv[4] = {(int)(signed char)(mm & 0xff), (int)(signed char)((mm >> 8) & 0xff),
+                               (int)(signed char)((mm >> 16) & 0xff), (int)(signed char)((mm >> 24) & 0xff)};
             unsigned best = 0xffffffffu;
             for (int ti = 0; ti < 8; ti++) {
-                const unsigned sp = T->spec_pack[c_alloc[qu] - 1 + 7 * ti];
-                const int g = sp & 15u, nc = (sp >> 4) & 15u, nb = (sp >> 8) & 15u, sgn = (sp >> 12) & 1u;
-                const unsigned* __restrict__ vlc = T->vlc + (sp >> 16);
-                unsigned bits = 0;
-                if (nc == 1) { for (int sx = lane; sx < len; sx += 32) bits += symbol_bits<1>(vlc, g, nb, sgn, m, sx); }
-                else if (nc == 2) { for (int sx = lane; sx < len / 2; sx += 32) bits += symbol_bits<2>(vlc, g, nb, sgn, m, sx); }
-                else { for (int sx = lane; sx < len / 4; sx += 32) bits += symbol_bits<4>(vlc, g, nb, sgn, m, sx); }
-                bits = __reduce_add_sync(0xffffffffu, bits);
-                best = min(best, bits * 8u + (unsigned)ti);                  // first minimum wins (t < consumed)
+                unsigned bits = group_cost(T->spec_pack[wl - 1 + 7 * ti], T->vlc, mv, gi);
+                for (int d = 1; d < seg; d <<= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+                best = min(best, bits * 8u + (unsigned)ti);                      // first minimum wins (t < consumed)
             }
-            if (lane == 0) { sh.qbits[ch][qu] = (unsigned short)(best >> 3); sh.qtab[ch][qu] = (unsigned char)(best & 7u); }
+            if ((lane & (seg - 1)) == 0) { sh.qbits[ch][qu] = (unsigned short)(best >> 3); sh.qtab[ch][qu] = (unsigned char)(best & 7u); }
         }
     __syncwarp();
     // ---- TTonalComponentEncoder::Encode (:611-669), once: its buffer survives the Repeat rounds

@@ -520,13 +520,14 @@ ATDE_NOINLINE int put_field(unsigned* words, int cap_bits, int pos, unsigned v, 
 }
 
 // One VLC symbol of TQuantUnitsEncoder::EncodeQuSpectra (:283-343): optional group flag, code, sign bits.
-ATDE_D unsigned spec_symbol(const DevTables* T, int tab, const signed char* m, int s, int& nbits)
+template <int NC>
+ATDE_D unsigned spec_symbol(const unsigned* __restrict__ vlc, int g, int bits, bool sgn, const signed char* m, int s, int& nbits)
 {
-    const int g = T->spec_tab[tab][0], nc = T->spec_tab[tab][1], bits = T->spec_tab[tab][2], sgn = T->spec_tab[tab][3];
     unsigned val = 0, signs = 0;
     int nsign = 0;
-    for (int i = 0; i < nc; i++) {
-        int t = m[s * nc + i];
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        int t = m[s * NC + i];
         if (!sgn && t != 0) {
             signs = (signs << 1) | (t < 0 ? 1u : 0u);
             nsign++;
@@ -536,7 +537,7 @@ ATDE_D unsigned spec_symbol(const DevTables* T, int tab, const signed char* m, i
         }
         val |= (unsigned)t << (bits * i);
     }
-    const unsigned e = T->vlc[T->vlc_off[tab] + (val & 255u)];
+    const unsigned e = vlc[val & 255u];
     unsigned out = e & 0xffffu;
     int n = (int)(e >> 16);
     out = (out << nsign) | signs;
@@ -764,7 +765,11 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
             unsigned best = 0xffffffffu;
             for (int ti = 0; ti < 8; ti++) {
                 unsigned bits = group_cost(T->spec_pack[wl - 1 + 7 * ti], T->vlc, mv, gi);
-                for (int d = 1; d < seg; d <<= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {                               // segmented sum, branch-free
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, bits, d);
+                    bits += d < seg ? o : 0u;
+                }
                 best = min(best, bits * 8u + (unsigned)ti);                      // first minimum wins (t < consumed)
             }
             if ((lane & (seg - 1)) == 0) { sh.qbits[ch][qu] = (unsigned short)(best >> 3); sh.qtab[ch][qu] = (unsigned char)(best & 7u); }
@@ -865,13 +870,21 @@ __global__ void __launch_bounds__(kPackWarps * 32) at3p_pack_kernel(const DevTab
         for (int ch = 0; ch < C; ch++) {
             for (int qu = 0; qu < num_qu; qu++) {
                 const int start = c_qu_start[qu], len = c_qu_start[qu + 1] - start;
-                const int tab = c_alloc[qu] - 1 + 7 * sh.qtab[ch][qu];
-                const int nsym = len / T->spec_tab[tab][1];
+                // (the table's geometry is uniform over the warp: one of three unrolled symbol builders)
+                const unsigned sp = T->spec_pack[c_alloc[qu] - 1 + 7 * sh.qtab[ch][qu]];
+                const int g = sp & 15u, nc = (sp >> 4) & 15u, cb = (sp >> 8) & 15u;
+                const bool sgn = (sp >> 12) & 1u;
+                const unsigned* __restrict__ vlc = T->vlc + (sp >> 16);
+                const signed char* mq = sh.mant[ch] + start;
+                const int nsym = len / nc;
                 for (int s0 = 0; s0 < nsym; s0 += 32) {
                     const int sidx = s0 + lane;
                     int nb = 0;
                     unsigned code = 0;
-                    if (sidx < nsym) code = spec_symbol(T, tab, sh.mant[ch] + start, sidx, nb);
+                    if (sidx < nsym)
+                        code = nc == 1 ? spec_symbol<1>(vlc, g, cb, sgn, mq, sidx, nb)
+                             : nc == 2 ? spec_symbol<2>(vlc, g, cb, sgn, mq, sidx, nb)
+                                       : spec_symbol<4>(vlc, g, cb, sgn, mq, sidx, nb);
                     const unsigned inc = warp_incl_scan((unsigned)nb, lane);
                     put_bits(w, kFrameBits, p + (int)(inc - (unsigned)nb), nb, code);
                     p += (int)__shfl_sync(0xffffffffu, inc, 31);

@@ -793,18 +793,26 @@ __global__ void at3_gain_scan_kernel(Geometry g, Buffers b)
     float4 ctx = *ctxp;                                              // x LastLevel, y LastHpfEnergy, z LastTarget
     const float4* st = reinterpret_cast<const float4*>(b.gstat) + (size_t)idx * g.n_out;
     float4* pv = reinterpret_cast<float4*>(b.gprev) + (size_t)idx * g.n_out;
-    for (int f = 0; f < g.n_out; f++) {
-        const float4 v = st[f];
-        float4 o;
-        o.x = ctx.y; o.y = ctx.x; o.z = ctx.z; o.w = 0.0f;
-        if (v.x < 0.05f) {                                           // kHighFreqThreshold: LastLevel = 0, continue
-            ctx.x = 0.0f;
-        } else {
-            ctx.y = v.y;
-            ctx.x = v.w;
-            ctx.z = v.z;
+    for (int f0 = 0; f0 < g.n_out; f0 += 8) {                        // (eight frames' statistics in flight at once)
+        float4 vv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) vv[q] = f0 + q < g.n_out ? st[f0 + q] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (f0 + q < g.n_out) {
+                const float4 v = vv[q];
+                float4 o;
+                o.x = ctx.y; o.y = ctx.x; o.z = ctx.z; o.w = 0.0f;
+                if (v.x < 0.05f) {                                   // kHighFreqThreshold: LastLevel = 0, continue
+                    ctx.x = 0.0f;
+                } else {
+                    ctx.y = v.y;
+                    ctx.x = v.w;
+                    ctx.z = v.z;
+                }
+                pv[f0 + q] = o;
+            }
         }
-        pv[f] = o;
     }
     *ctxp = ctx;
 }
@@ -1570,15 +1578,30 @@ __global__ void at3_loudness_kernel(Geometry g, Buffers b)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= g.S) return;
     float L = b.loud_state[s];
-    for (int f = 0; f < g.n_out; f++) {
-        const size_t o = ((size_t)s * g.n_out + f) * g.C;
-        if (g.C == 2 && !g.js) {
-            const float sum = fadd(b.chloud[o], b.chloud[o + 1]);
-            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.01, (double)sum)));
-        } else {
-            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.02, (double)b.chloud[o])));
+    const bool two = g.C == 2 && !g.js;
+    // eight frames' terms are fetched before the recurrence runs over them (the stores of one frame would otherwise stand
+    // between the loads of the next: one exposed memory latency per frame on a thread that has nothing else to do)
+    for (int f0 = 0; f0 < g.n_out; f0 += 8) {
+        float t0[8], t1[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const size_t o = ((size_t)s * g.n_out + f0 + q) * g.C;
+            const bool in = f0 + q < g.n_out;
+            t0[q] = in ? b.chloud[o] : 0.0f;
+            t1[q] = in && two ? b.chloud[o + 1] : 0.0f;
         }
-        b.loud[(size_t)s * g.n_out + f] = L;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (f0 + q < g.n_out) {
+                if (two) {
+                    const float sum = fadd(t0[q], t1[q]);
+                    L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.01, (double)sum)));
+                } else {
+                    L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.02, (double)t0[q])));
+                }
+                b.loud[(size_t)s * g.n_out + f0 + q] = L;
+            }
+        }
     }
     b.loud_state[s] = L;
 }

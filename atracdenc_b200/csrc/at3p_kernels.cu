@@ -919,9 +919,9 @@ void launch_pack(const DevTables* T, const float* specs, const ToneBlock* tones,
 } // namespace atde
 
 // =====================================================================================
-// Stage entry points (host buffers in, host buffers out).  ATRAC3plus is not reachable through
-// atde_create() until the GHA stage exists; these let tests/ drive each finished kernel against the
-// reference's taps.  Declared in at3p_stage_api.h, not in include/.
+// Stage entry points (host buffers in, host buffers out): they let tests/ drive each kernel on its own against the
+// reference's taps (the whole codec runs through atde_create(ATDE_CODEC_ATRAC3PLUS) / at3p_pipeline.cu).
+// Declared in at3p_stage_api.h, not in include/.
 // =====================================================================================
 namespace {
 template <class T> struct ScopedDev {

@@ -22,6 +22,7 @@ CODEC_ATRAC3PLUS = 4
 
 TAP_SPECS, TAP_MASKS, TAP_CHLOUD, TAP_LOUDNESS, TAP_SFI, TAP_WORDLEN = 1, 2, 3, 4, 5, 6
 TAP_BANDS, TAP_CURVES, TAP_GSCALE, TAP_ENERGY, TAP_TONAL, TAP_GAIN = 7, 8, 9, 10, 11, 12
+TAP_TRACE_GAIN, TAP_TRACE_STAT = 13, 14      # with Encoder.set_gain_trace(True): the envelope analysis over all four bands
 
 EXPORTS = [
     "atde_default_settings", "atde_create", "atde_destroy", "atde_frame_samples",
@@ -199,6 +200,10 @@ class Encoder:
 
     def set_profiling(self, on: bool):
         self._check(self.lib.atde_set_profiling(self.h, int(on)))
+
+    def set_gain_trace(self, on: bool):
+        """ATRAC3: keep the data of the reference's `--yaml-log` gain-control trace (atde_set_gain_trace)."""
+        self._check(self.lib.atde_set_gain_trace(self.h, int(on)))
 
     def kernel_times(self, n_kinds: int = 3):
         """(ms_sum[kind], count[kind]) since the last query; kinds: 0 analysis, 1 loudness, 2 pack."""

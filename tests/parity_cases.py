@@ -815,3 +815,32 @@ def check_at3p_golden(lib, name, max_frames=None):
     assert out.shape == (S, F - 1, 1, 2048)
     bad = np.argwhere((out[:, :, 0] != frames[:, :F - 1]).any(-1))
     assert bad.size == 0, f"first differing (stream, frame) = {bad[:4].tolist()}"
+
+
+def check_at3_gain_trace_taps(lib, S=2, F=6, C=2, kbit=0, seed=2100):
+    """atde_set_gain_trace (the data behind `--yaml-log`): the trace instance of the gain kernel analyses all four bands;
+    on bands 0..2 its envelope must be bit-equal to the encode path's, its high-frequency ratio may differ from the
+    encode path's tree sum only in the last place, `next_level` is a finite RMS, band 3 is analysed too — and the frames
+    are the frames of an encoder without the trace."""
+    pcm = np.stack([tl.synth_rich(F, 1024, C, seed=seed + s, kind=("mix", "steps")[s % 2]) for s in range(S)]).astype(np.float32)
+    plain = ab.Encoder(ab.CODEC_ATRAC3, C, bitrate=kbit * 1024, lib=lib)
+    want = plain.encode(pcm, S)
+    plain.close()
+    enc = ab.Encoder(ab.CODEC_ATRAC3, C, bitrate=kbit * 1024, lib=lib)
+    enc.set_gain_trace(True)
+    got = enc.encode(pcm, S)
+    n_out = F - 1
+    gain = enc.tap(ab.TAP_GAIN, (S, C, 3, n_out, 96), np.float32)
+    tgain = enc.tap(ab.TAP_TRACE_GAIN, (S, C, 4, n_out, 96), np.float32)
+    tstat = enc.tap(ab.TAP_TRACE_STAT, (S, C, 4, n_out, 4), np.float32)
+    enc.close()
+    assert np.array_equal(got, want), "the trace must not change the encoded frames"
+    assert np.array_equal(tgain[:, :, :3].view(np.uint32), gain.view(np.uint32)), "trace envelope != encode path's envelope"
+    assert np.isfinite(tstat).all() and (tstat[..., 3] >= 0).all() and (tstat[..., 0] >= 0).all() and (tstat[..., 0] <= 1.0001).all()
+    assert np.abs(tgain[:, :, 3]).sum() > 0, "band 3 was not analysed"
+    # curHpfEnergy is the mean of the 32 sub-frame levels, in the reference's order
+    mean = np.zeros(tgain.shape[:4], np.float32)
+    for i in range(32):
+        mean = (mean + tgain[..., i]).astype(np.float32)
+    mean = (mean / np.float32(32.0)).astype(np.float32)
+    assert np.array_equal(mean.view(np.uint32), tstat[..., 1].view(np.uint32))

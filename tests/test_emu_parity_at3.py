@@ -60,3 +60,8 @@ def test_edge_inputs(emu_lib):
 
 def test_errors(emu_lib):
     pc.check_at3_errors(emu_lib)
+
+
+def test_gain_trace_taps(emu_lib):
+    pc.check_at3_gain_trace_taps(emu_lib, S=2, F=6, C=2)
+    pc.check_at3_gain_trace_taps(emu_lib, S=1, F=5, C=2, kbit=64, seed=2200)      # joint stereo: the trace is over M/S

@@ -100,3 +100,4 @@ def test_full_size_properties(gpu_lib, kbit):
     enc.sync()
     assert torch.equal(d_out, d_out2)
     enc.close()
+

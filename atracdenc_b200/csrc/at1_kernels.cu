@@ -449,16 +449,33 @@ __global__ void at1_loudness_kernel(LoudnessParams p)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.S) return;
     float L = p.loud_in ? p.loud_in[s] : kLoudFactor;
-    for (int f = 0; f < p.F; f++) {
-        const size_t o = ((size_t)s * p.F + f) * p.C;
-        const unsigned m0 = p.masks[o];
-        if (p.C == 2 && m0 == 0 && p.masks[o + 1] == 0) {
-            const float sum = fadd(p.chloud[o], p.chloud[o + 1]);
-            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.01, (double)sum)));
-        } else if (m0 == 0) {
-            L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.02, (double)p.chloud[o])));
+    // eight frames' masks and terms are fetched before the recurrence runs over them (the store of one frame would
+    // otherwise stand between the loads of the next: one exposed memory latency per frame)
+    const bool two = p.C == 2;
+    for (int f0 = 0; f0 < p.F; f0 += 8) {
+        unsigned m0[8], m1[8];
+        float t0[8], t1[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const size_t o = ((size_t)s * p.F + f0 + q) * p.C;
+            const bool in = f0 + q < p.F;
+            m0[q] = in ? p.masks[o] : 0u;
+            m1[q] = in && two ? p.masks[o + 1] : 0u;
+            t0[q] = in ? p.chloud[o] : 0.0f;
+            t1[q] = in && two ? p.chloud[o + 1] : 0.0f;
         }
-        p.loud[(size_t)s * p.F + f] = L;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (f0 + q < p.F) {
+                if (two && m0[q] == 0 && m1[q] == 0) {
+                    const float sum = fadd(t0[q], t1[q]);
+                    L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.01, (double)sum)));
+                } else if (m0[q] == 0) {
+                    L = __double2float_rn(__dadd_rn(__dmul_rn(0.98, (double)L), __dmul_rn(0.02, (double)t0[q])));
+                }
+                p.loud[(size_t)s * p.F + f0 + q] = L;
+            }
+        }
     }
 }
 

@@ -191,7 +191,7 @@ def run_yaml_pair(ref, got, tmp_path, frames, cases=YAML_CASES):
 
 def test_dropin_yaml_log_identical_emulated(tmp_path):
     ref, got = _binaries("emu")
-    seen = run_yaml_pair(ref, got, tmp_path, frames=24)
+    seen = run_yaml_pair(ref, got, tmp_path, frames=16)
     # the cases together must reach every kind of line the trace has
     assert {b"point0_guard: kept", b"point0_guard: reverted", b"transition_pruned", b"skip: low_hfr", b"skip: amplify_low_hfr",
             b"skip: below_min_signal", b"skip: band_ge_3", b"curve_final", b"source: in.back", b"sticky_frame_eligible: true"} <= seen, seen

@@ -267,7 +267,8 @@ float MismatchScore(const float* gain, float target, const TCurve& pts, const fl
 
 } // namespace
 
-// One band of CreateSubbandInfo (atrac3denc.cpp:311-578).  env: gain[32] low[32] high[32]; stat: hfr, -, -, next_level;
+// One band of CreateSubbandInfo (atrac3denc.cpp:311-578).  env: gain[32] low[32] high[32]; stat: hfr, the device's mean
+// envelope and plateau target (checked against the host's), next_level;
 // cur: the frame's 256 band samples; devCurve: the 16-byte curve record the device encoded with (bands 0..2).
 void TGainTraceWriter::Band(int channel, int band, const float* env, const float* stat, const float* cur, const uint8_t* devCurve)
 {
